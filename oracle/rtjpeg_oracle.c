@@ -1,0 +1,295 @@
+/*
+ * rtjpeg_oracle.c -- TEST INFRASTRUCTURE ONLY (see rtjpeg_oracle.h).
+ *
+ * Plain-C restatement of the reference's RTjpeg YUV420 decode, written from
+ * the behaviour of /root/reference/lib/RTjpeg.c (non-MMX C path).  Each
+ * function cites the reference lines it follows.  The structure is not the
+ * reference's: unpacking, the 1-D transform and the macroblock walk are
+ * separate table-driven pieces so that tests can exercise them one by one.
+ *
+ * Pinned by tests/test_oracle.py against (a) the unmodified reference
+ * compiled into oracle/_ref/ and (b) tests/golden/ fixtures produced by it.
+ */
+#include "rtjpeg_oracle.h"
+
+#include <string.h>
+
+/* zig-zag position -> raster index.  Same map as RTjpeg_ZZ (RTjpeg.c:59-74),
+ * generated here instead of tabulated: anti-diagonals d = r + c, walked
+ * downwards (towards larger row) when d is odd... the reference's order is the
+ * transpose of JPEG's, i.e. position 1 is raster 8 (row 1, col 0). */
+static uint8_t zz_map[64];
+static int     zz_ready;
+
+static void zz_build(void)
+{
+    int k = 0;
+    for (int d = 0; d < 15; d++) {
+        int lo = d < 8 ? 0 : d - 7;
+        int hi = d < 8 ? d : 7;
+        /* even diagonals run from (row lo, col hi) to (row hi, col lo)?  The
+         * reference sequence 0 | 8 1 | 2 9 16 | 24 17 10 3 | ... shows: odd d
+         * starts at the largest row, even d starts at the largest column. */
+        if (d & 1) {
+            for (int r = hi; r >= lo; r--) zz_map[k++] = (uint8_t)(r * 8 + (d - r));
+        } else {
+            for (int c = hi; c >= lo; c--) zz_map[k++] = (uint8_t)((d - c) * 8 + c);
+        }
+    }
+    zz_ready = 1;
+}
+
+static inline const uint8_t *zz(void)
+{
+    if (!zz_ready) zz_build();
+    return zz_map;
+}
+
+/* JPEG Annex K base tables, raster order (RTjpeg.c:87-107). */
+static const uint8_t base_luma[64] = {
+    16, 11, 10, 16, 24, 40, 51, 61,   12, 12, 14, 19, 26, 58, 60, 55,
+    14, 13, 16, 24, 40, 57, 69, 56,   14, 17, 22, 29, 51, 87, 80, 62,
+    18, 22, 37, 56, 68, 109, 103, 77, 24, 35, 55, 64, 81, 104, 113, 92,
+    49, 64, 78, 87, 103, 121, 120, 101, 72, 92, 95, 98, 112, 100, 103, 99
+};
+static const uint8_t base_chroma[64] = {
+    17, 18, 24, 47, 99, 99, 99, 99,   18, 21, 26, 66, 99, 99, 99, 99,
+    24, 26, 56, 99, 99, 99, 99, 99,   47, 66, 99, 99, 99, 99, 99, 99,
+    99, 99, 99, 99, 99, 99, 99, 99,   99, 99, 99, 99, 99, 99, 99, 99,
+    99, 99, 99, 99, 99, 99, 99, 99,   99, 99, 99, 99, 99, 99, 99, 99
+};
+
+/* AAN scale factors in Q32 (RTjpeg.c:76-85).  The table is separable:
+ * entry (r,c) = round-to-table of s[r]*s[c]*2^32 with s[0]=1,
+ * s[k]=sqrt(2)*cos(k*pi/16); the reference stores the rounded products, so
+ * they are tabulated (8x8 symmetric) rather than recomputed in floating point. */
+static const uint64_t aan_q32[64] = {
+    4294967296ULL, 5957222912ULL, 5611718144ULL, 5050464768ULL, 4294967296ULL, 3374581504ULL, 2324432128ULL, 1184891264ULL,
+    5957222912ULL, 8263040512ULL, 7783580160ULL, 7005009920ULL, 5957222912ULL, 4680582144ULL, 3224107520ULL, 1643641088ULL,
+    5611718144ULL, 7783580160ULL, 7331904512ULL, 6598688768ULL, 5611718144ULL, 4408998912ULL, 3036936960ULL, 1548224000ULL,
+    5050464768ULL, 7005009920ULL, 6598688768ULL, 5938608128ULL, 5050464768ULL, 3968072960ULL, 2733115392ULL, 1393296000ULL,
+    4294967296ULL, 5957222912ULL, 5611718144ULL, 5050464768ULL, 4294967296ULL, 3374581504ULL, 2324432128ULL, 1184891264ULL,
+    3374581504ULL, 4680582144ULL, 4408998912ULL, 3968072960ULL, 3374581504ULL, 2651326208ULL, 1826357504ULL, 931136000ULL,
+    2324432128ULL, 3224107520ULL, 3036936960ULL, 2733115392ULL, 2324432128ULL, 1826357504ULL, 1258030336ULL, 641204288ULL,
+    1184891264ULL, 1643641088ULL, 1548224000ULL, 1393296000ULL, 1184891264ULL, 931136000ULL, 641204288ULL, 326894240ULL
+};
+
+/* Number of leading zig-zag AC positions whose pre-AAN dequantiser is <= 8:
+ * those coefficients travel as raw signed bytes (RTjpeg.c:2362-2367, and the
+ * same loop in set_tables :2388-2393).  The reference loop has no upper bound;
+ * it is capped at 63 here (a table that is <= 8 everywhere). */
+static int raw_prefix_len(const int32_t *pre)
+{
+    const uint8_t *z = zz();
+    int k = 0;
+    while (k < 63 && pre[z[k + 1]] <= 8) k++;
+    return k;
+}
+
+static void apply_aan(int32_t *t)
+{
+    /* RTjpeg_idct_init, RTjpeg.c:1208-1217 */
+    for (int i = 0; i < 64; i++)
+        t[i] = (int32_t)(((uint64_t)(uint32_t)t[i] * aan_q32[i]) >> 32);
+}
+
+void rtjo_tables_from_quality(int Q, rtjo_tables *out)
+{
+    /* RTjpeg_set_quality :2408-2412 clamps, RTjpeg_calc_tbls :2344-2361 derives */
+    if (Q < 1) Q = 1;
+    if (Q > 255) Q = 255;
+    uint64_t qual = (uint64_t)Q << 25;
+    for (int i = 0; i < 64; i++) {
+        int32_t lq = (int32_t)((qual / ((uint64_t)base_luma[i] << 16)) >> 3);
+        int32_t cq = (int32_t)((qual / ((uint64_t)base_chroma[i] << 16)) >> 3);
+        if (lq == 0) lq = 1;
+        if (cq == 0) cq = 1;
+        out->liqt[i] = 65536 / (lq << 3);
+        out->ciqt[i] = 65536 / (cq << 3);
+    }
+    out->lb8 = raw_prefix_len(out->liqt);
+    out->cb8 = raw_prefix_len(out->ciqt);
+    apply_aan(out->liqt);
+    apply_aan(out->ciqt);
+}
+
+void rtjo_tables_from_raw(const uint32_t raw[128], rtjo_tables *out)
+{
+    /* RTjpeg_set_tables :2380-2395 */
+    for (int i = 0; i < 64; i++) {
+        out->liqt[i] = (int32_t)raw[i];
+        out->ciqt[i] = (int32_t)raw[64 + i];
+    }
+    out->lb8 = raw_prefix_len(out->liqt);
+    out->cb8 = raw_prefix_len(out->ciqt);
+    apply_aan(out->liqt);
+    apply_aan(out->ciqt);
+}
+
+void rtjo_decoder_reset(rtjo_decoder *d)
+{
+    /* RTjpeg_init :2495-2502: everything zero, so format 0 = YUV420 and no tables */
+    memset(d, 0, sizeof(*d));
+}
+
+/* Byte length of the block that starts at s (1 for a skip marker), without
+ * touching coefficients; *eob receives the count of zig-zag positions up to the
+ * last explicitly coded one.  Grammar: RTjpeg_s2b, RTjpeg.c:157-186. */
+static int block_extent(const uint8_t *s, size_t avail, int bt8, int *eob)
+{
+    if (avail < 1) return -1;
+    if (s[0] == 0xFF) { *eob = 0; return 1; }
+    size_t n = 1 + (size_t)bt8;          /* DC + raw bytes */
+    int pos = 1 + bt8;                   /* next zig-zag position to fill */
+    int last = pos;                      /* positions 0..bt8 are always explicit */
+    if (n > avail) return -1;
+    while (pos < 64) {
+        if (n >= avail) return -1;
+        int8_t b = (int8_t)s[n++];
+        if (b > 63) pos += b - 63;       /* run of zeros */
+        else { pos++; last = pos; }      /* one coefficient */
+    }
+    *eob = last;
+    return (int)n;
+}
+
+int rtjo_unpack_block(const uint8_t *s, int bt8, const int32_t *iqt, int16_t blk[64])
+{
+    /* RTjpeg_s2b :157-186.  Products are formed in uint32 and truncated to
+     * int16, exactly like `data[i] = strm[ci] * qtbl[i]` with qtbl uint32_t*. */
+    const uint8_t *z = zz();
+    memset(blk, 0, 64 * sizeof(int16_t));
+    blk[0] = (int16_t)((uint32_t)s[0] * (uint32_t)iqt[0]);
+    int n = 1, pos = 1;
+    for (; pos <= bt8; pos++, n++)
+        blk[z[pos]] = (int16_t)((uint32_t)(int32_t)(int8_t)s[n] * (uint32_t)iqt[z[pos]]);
+    while (pos < 64) {
+        int8_t b = (int8_t)s[n++];
+        if (b > 63) {
+            pos += b - 63;
+        } else {
+            blk[z[pos]] = (int16_t)((uint32_t)(int32_t)b * (uint32_t)iqt[z[pos]]);
+            pos++;
+        }
+    }
+    return n;
+}
+
+/* Fixed-point multiply of the reference (MULTIPLY, RTjpeg.c:1206): constants
+ * carry 8 fractional bits, rounding is +128 then arithmetic shift. */
+static inline int32_t fxmul(int32_t v, int32_t c) { return (int32_t)(v * c + 128) >> 8; }
+
+/* One 8-point pass (RTjpeg.c:2240-2283 for columns, :2289-2326 for rows; both
+ * passes run the same flow graph).  in[] natural order, out[] natural order. */
+static void aan8(const int32_t in[8], int32_t out[8])
+{
+    enum { C1 = 277, C2 = 362, C3 = 473, C4 = 669 };
+    int32_t s04 = in[0] + in[4], d04 = in[0] - in[4];
+    int32_t s26 = in[2] + in[6];
+    int32_t m26 = fxmul(in[2] - in[6], C2) - s26;
+    int32_t e0 = s04 + s26, e3 = s04 - s26, e1 = d04 + m26, e2 = d04 - m26;
+
+    int32_t z13 = in[5] + in[3], z10 = in[5] - in[3];
+    int32_t z11 = in[1] + in[7], z12 = in[1] - in[7];
+    int32_t o7 = z11 + z13;
+    int32_t o11 = fxmul(z11 - z13, C2);
+    int32_t z5 = fxmul(z10 + z12, C3);
+    int32_t o10 = fxmul(z12, C1) - z5;
+    int32_t o12 = fxmul(z10, -C4) + z5;
+    int32_t o6 = o12 - o7;
+    int32_t o5 = o11 - o6;
+    int32_t o4 = o10 + o5;
+
+    out[0] = e0 + o7; out[7] = e0 - o7;
+    out[1] = e1 + o6; out[6] = e1 - o6;
+    out[2] = e2 + o5; out[5] = e2 - o5;
+    out[4] = e3 + o4; out[3] = e3 - o4;
+}
+
+void rtjo_idct_block(const int16_t blk[64], uint8_t *dst, int pitch)
+{
+    /* RTjpeg_idct C path, RTjpeg.c:2209-2332.  The reference's DC-only column
+     * shortcut (:2223-2238) is value-identical to the general flow graph
+     * because fxmul(0, c) == 0, so it is not special-cased here. */
+    int32_t ws[64];
+    for (int c = 0; c < 8; c++) {
+        int32_t in[8], out[8];
+        for (int r = 0; r < 8; r++) in[r] = blk[r * 8 + c];
+        aan8(in, out);
+        for (int r = 0; r < 8; r++) ws[r * 8 + c] = out[r];
+    }
+    for (int r = 0; r < 8; r++) {
+        int32_t out[8];
+        aan8(&ws[r * 8], out);
+        for (int c = 0; c < 8; c++) {
+            int16_t p = (int16_t)((out[c] + 4) >> 3);      /* DESCALE :1200 */
+            dst[r * pitch + c] = (uint8_t)(p > 235 ? 235 : (p < 16 ? 16 : p)); /* RL :1204 */
+        }
+    }
+}
+
+long rtjo_walk_payload(const uint8_t *payload, size_t len, int nmb,
+                       int lb8, int cb8, uint32_t *offsets, uint8_t *eob)
+{
+    size_t at = 0;
+    for (int mb = 0; mb < nmb; mb++) {
+        for (int k = 0; k < 6; k++) {
+            int e;
+            int n = block_extent(payload + at, len - at, k < 4 ? lb8 : cb8, &e);
+            if (n < 0) return -1;
+            if (offsets) offsets[mb * 6 + k] = e ? (uint32_t)at : 0xFFFFFFFFu;
+            if (eob) eob[mb * 6 + k] = (uint8_t)e;
+            at += (size_t)n;
+        }
+    }
+    return (long)at;
+}
+
+long rtjo_decode_packet(rtjo_decoder *d, const uint8_t *pkt, size_t pkt_len,
+                        uint8_t *y, uint8_t *u, uint8_t *v)
+{
+    if (pkt_len < 12) return -1;
+    /* header fields, include/RTjpeg.h:100-109 (packed, little endian) */
+    int w = pkt[6] | (pkt[7] << 8);
+    int h = pkt[8] | (pkt[9] << 8);
+    int q = pkt[10];
+    /* lazy reconfiguration, RTjpeg_decompress :3568-3579 */
+    if (w != d->width || h != d->height) { d->width = w; d->height = h; }
+    if (q != d->Q) {
+        int qc = q < 1 ? 1 : q;          /* set_quality stores the clamped value */
+        d->Q = qc;
+        rtjo_tables_from_quality(qc, &d->t);
+    }
+    const uint8_t *s = pkt + 12;
+    size_t left = pkt_len - 12, at = 0;
+    int cw = w >> 1;
+    int16_t blk[64];
+    /* macroblock walk, RTjpeg_decompressYUV420 :2688-2749: rows of 16 luma
+     * lines, 16 luma columns per step, six blocks Y00 Y01 Y10 Y11 U V */
+    for (int my = 0; my < (h >> 4); my++) {
+        for (int mx = 0; mx < (w >> 4); mx++) {
+            for (int k = 0; k < 6; k++) {
+                int bt8 = k < 4 ? d->t.lb8 : d->t.cb8;
+                const int32_t *iq = k < 4 ? d->t.liqt : d->t.ciqt;
+                int e;
+                int n = block_extent(s + at, left - at, bt8, &e);
+                if (n < 0) return -1;
+                if (e) {
+                    uint8_t *dst;
+                    int pitch;
+                    if (k < 4) {
+                        pitch = w;
+                        dst = y + (size_t)(my * 16 + (k >> 1) * 8) * w + mx * 16 + (k & 1) * 8;
+                    } else {
+                        pitch = cw;
+                        dst = (k == 4 ? u : v) + (size_t)(my * 8) * cw + mx * 8;
+                    }
+                    rtjo_unpack_block(s + at, bt8, iq, blk);
+                    rtjo_idct_block(blk, dst, pitch);
+                }
+                at += (size_t)n;
+            }
+        }
+    }
+    return (long)at;
+}

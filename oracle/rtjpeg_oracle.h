@@ -1,0 +1,71 @@
+/*
+ * rtjpeg_oracle.h -- TEST INFRASTRUCTURE ONLY.
+ *
+ * CPU restatement of the RTjpeg YUV420 decode path of gmerlin-avdecoder
+ * (reference: lib/RTjpeg.c, include/RTjpeg.h).  It exists so that tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline leg can check the CUDA
+ * path.  Nothing in the shipped library (gmerlin-avdecoder_b200/) may include,
+ * link or call this file.
+ *
+ * Parity pin: the reference holds no golden vectors for this path (SURVEY.md
+ * section 4), so the restatement is pinned against the reference itself,
+ * compiled unmodified from /root/reference by oracle/Makefile into
+ * oracle/_ref/, and against fixtures under tests/golden/ made by that build.
+ */
+#ifndef RTJPEG_ORACLE_H
+#define RTJPEG_ORACLE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Dequantisation tables for one quality value (reference: RTjpeg_calc_tbls
+ * lib/RTjpeg.c:2344-2369 followed by RTjpeg_idct_init :1208-1217). */
+typedef struct {
+    int32_t liqt[64];   /* luma, raster order, AAN-scaled   */
+    int32_t ciqt[64];   /* chroma, raster order, AAN-scaled */
+    int     lb8;        /* #raw 8-bit coefficients after DC, luma   */
+    int     cb8;        /* #raw 8-bit coefficients after DC, chroma */
+} rtjo_tables;
+
+/* Decoder instance state that survives between frames (reference: RTjpeg_t,
+ * include/RTjpeg.h:54-92, decoder-relevant members only). */
+typedef struct {
+    int         width, height, Q;
+    rtjo_tables t;
+} rtjo_decoder;
+
+/* Q is clamped to 1..255 exactly as RTjpeg_set_quality does (:2408-2412). */
+void rtjo_tables_from_quality(int Q, rtjo_tables *out);
+
+/* 128 raw (pre-AAN) u32 table entries, as RTjpeg_set_tables takes (:2380-2395). */
+void rtjo_tables_from_raw(const uint32_t raw[128], rtjo_tables *out);
+
+void rtjo_decoder_reset(rtjo_decoder *d);
+
+/* One packet (12-byte header + payload) into persistent tight-pitch planes.
+ * Mirrors RTjpeg_decompress (:3565-3586) with f == RTJ_YUV420.
+ * Returns the number of payload bytes consumed, or -1 if the packet would be
+ * read past pkt_len (the reference has no such check; the oracle refuses
+ * instead of reading out of bounds). */
+long rtjo_decode_packet(rtjo_decoder *d, const uint8_t *pkt, size_t pkt_len,
+                        uint8_t *y, uint8_t *u, uint8_t *v);
+
+/* Block walker: byte offset (relative to the payload start) of each of the
+ * nblocks blocks, 0xFFFFFFFF for a skipped block, plus per-block end-of-block
+ * count (number of zig-zag positions up to and including the last coded one;
+ * 0 for a skipped block).  Returns payload bytes consumed or -1 on overrun. */
+long rtjo_walk_payload(const uint8_t *payload, size_t len, int nblocks_mb6,
+                       int lb8, int cb8, uint32_t *offsets, uint8_t *eob);
+
+/* Single 8x8 block primitives, exposed for unit tests. */
+int  rtjo_unpack_block(const uint8_t *s, int bt8, const int32_t *iqt, int16_t blk[64]);
+void rtjo_idct_block(const int16_t blk[64], uint8_t *dst, int pitch);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

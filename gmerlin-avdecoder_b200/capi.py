@@ -1,0 +1,322 @@
+"""ctypes binding of the C ABI declared in include/rtjpeg_b200.h.
+
+The library is built in-tree by ``make -C gmerlin-avdecoder_b200`` (see
+``build_library``).  Loading fails loudly when the shared object is missing and
+every context constructor fails loudly when no CUDA device is usable: there is
+no CPU path in this package.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG_DIR, "lib", "librtjpeg_b200.so")
+PLUGIN_PATH = os.path.join(PKG_DIR, "lib", "librtjpeg_b200_bgav.so")
+
+# mirrors of the C structs ---------------------------------------------------
+
+FRAME_DESC_DTYPE = np.dtype([("offset", "<u8"), ("length", "<u4"), ("table", "<u2"), ("flags", "<u2")])
+assert FRAME_DESC_DTYPE.itemsize == 16
+
+
+class State(C.Structure):
+    """rtjgpu_state: decoder state that crosses batch boundaries."""
+    _fields_ = [("width", C.c_int), ("height", C.c_int), ("table", C.c_int), ("quality", C.c_int)]
+
+
+class Timing(C.Structure):
+    _fields_ = [("scan_ms", C.c_float), ("resolve_ms", C.c_float), ("idct_ms", C.c_float), ("total_ms", C.c_float)]
+
+
+class BatchInfo(C.Structure):
+    _fields_ = [("skipped_blocks", C.c_uint64), ("payload_bytes", C.c_uint64),
+                ("bad_frames", C.c_uint32), ("first_bad_frame", C.c_int32)]
+
+
+OK = 0
+E_CUDA, E_ARG, E_HEADER, E_SIZE, E_FORMAT, E_OVERRUN, E_TOOBIG, E_NOMEM = -1, -2, -3, -4, -5, -6, -7, -8
+HOST_IN_PINNED, HOST_OUT_PINNED = 1, 2
+STREAM_SLACK_BYTES = 128
+TABLE_ZERO, TABLE_CUSTOM = 0, 256
+
+_u8p = C.POINTER(C.c_uint8)
+_u32p = C.POINTER(C.c_uint32)
+_u64p = C.POINTER(C.c_uint64)
+
+
+class RTjpegError(RuntimeError):
+    def __init__(self, code: int, what: str = ""):
+        self.code = code
+        msg = load_library().rtjgpu_strerror(code).decode() if _lib is not None else str(code)
+        super().__init__(f"{what}: {msg} ({code})" if what else f"{msg} ({code})")
+
+
+def build_library(verbose: bool = False) -> None:
+    """Compile every CUDA/C++ source for sm_100a into gmerlin-avdecoder_b200/lib/."""
+    cmd = ["make", "-C", PKG_DIR, "all"]
+    if not verbose:
+        cmd.insert(1, "-s")
+    subprocess.check_call(cmd)
+
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FileNotFoundError(
+            f"{LIB_PATH} is missing: run `make -C {PKG_DIR}` (or __graft_entry__.build()); "
+            "there is no fallback implementation")
+    L = C.CDLL(LIB_PATH)
+    vp = C.c_void_p
+    # Level 1
+    L.RTjpeg_init.restype = vp
+    L.RTjpeg_close.argtypes = [vp]
+    L.RTjpeg_close.restype = None
+    for name in ("RTjpeg_set_quality", "RTjpeg_set_format"):
+        getattr(L, name).argtypes = [vp, C.POINTER(C.c_int)]
+    L.RTjpeg_set_size.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.RTjpeg_set_intra.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.RTjpeg_get_tables.argtypes = [vp, _u32p]
+    L.RTjpeg_get_tables.restype = None
+    L.RTjpeg_set_tables.argtypes = [vp, _u32p]
+    L.RTjpeg_set_tables.restype = None
+    L.RTjpeg_decompress.argtypes = [vp, _u8p, C.POINTER(_u8p)]
+    L.RTjpeg_decompress.restype = None
+    L.RTjpeg_b200_decompress_n.argtypes = [vp, _u8p, C.c_size_t, C.POINTER(_u8p)]
+    L.RTjpeg_b200_last_error.argtypes = [vp]
+    # Level 2
+    L.rtjgpu_create.argtypes = [C.c_int, C.POINTER(vp)]
+    L.rtjgpu_destroy.argtypes = [vp]
+    L.rtjgpu_destroy.restype = None
+    L.rtjgpu_strerror.argtypes = [C.c_int]
+    L.rtjgpu_strerror.restype = C.c_char_p
+    L.rtjgpu_last_cuda_error.argtypes = [vp]
+    L.rtjgpu_set_custom_tables.argtypes = [vp, _u32p]
+    L.rtjgpu_plan.argtypes = [_u8p, _u64p, C.c_int, C.POINTER(State), vp]
+    L.rtjgpu_decode_device.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp]
+    L.rtjgpu_decode_host.argtypes = [vp, _u8p, _u64p, C.c_int, C.POINTER(State), _u8p, _u8p, C.c_int]
+    L.rtjgpu_sync.argtypes = [vp]
+    L.rtjgpu_enable_timing.argtypes = [vp, C.c_int]
+    L.rtjgpu_enable_timing.restype = None
+    L.rtjgpu_get_timing.argtypes = [vp, C.POINTER(Timing)]
+    L.rtjgpu_get_timing_at.argtypes = [vp, C.c_int, C.POINTER(Timing)]
+    L.rtjgpu_get_batch_info.argtypes = [vp, C.POINTER(BatchInfo)]
+    L.rtjgpu_get_skip_counts.argtypes = [vp, _u32p, C.c_int]
+    L.rtjgpu_launch_count.argtypes = [vp]
+    L.rtjgpu_launch_count.restype = C.c_uint64
+    L.rtjgpu_split_shards.argtypes = [_u8p, C.c_int, C.c_int, C.POINTER(C.c_int)]
+    L.rtjgpu_tables_for_quality.argtypes = [C.c_int, _u32p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.rtjgpu_tables_for_quality.restype = None
+    L.rtjgpu_tables_from_raw.argtypes = [_u32p, _u32p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.rtjgpu_tables_from_raw.restype = None
+    L.rtjgpu_host_alloc.argtypes = [C.c_size_t]
+    L.rtjgpu_host_alloc.restype = vp
+    L.rtjgpu_host_free.argtypes = [vp]
+    L.rtjgpu_host_free.restype = None
+    _lib = L
+    return L
+
+
+def _u8(a: np.ndarray):
+    return a.ctypes.data_as(_u8p)
+
+
+def _check(rc: int, what: str) -> None:
+    if rc != OK:
+        raise RTjpegError(rc, what)
+
+
+# Level 2 ----------------------------------------------------------------------
+
+def plan(stream: np.ndarray, offsets: np.ndarray, state: State | None = None):
+    """rtjgpu_plan: header parse + lazy reconfiguration -> (descriptors, state)."""
+    L = load_library()
+    stream = np.ascontiguousarray(stream, dtype=np.uint8)
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    F = len(offsets) - 1
+    st = State(0, 0, TABLE_ZERO, 0) if state is None else state
+    desc = np.zeros(max(F, 1), dtype=FRAME_DESC_DTYPE)
+    _check(L.rtjgpu_plan(_u8(stream), offsets.ctypes.data_as(_u64p), F, C.byref(st),
+                         C.c_void_p(desc.ctypes.data)), "rtjgpu_plan")
+    return desc[:F], st
+
+
+def tables_for_quality(Q: int):
+    """Host-only: (scaled[128], lb8, cb8) as RTjpeg_set_quality would leave them."""
+    out = np.zeros(128, dtype=np.uint32)
+    a, b = C.c_int(), C.c_int()
+    load_library().rtjgpu_tables_for_quality(Q, out.ctypes.data_as(_u32p), C.byref(a), C.byref(b))
+    return out, a.value, b.value
+
+
+def tables_from_raw(raw: np.ndarray):
+    raw = np.ascontiguousarray(raw, dtype=np.uint32)
+    out = np.zeros(128, dtype=np.uint32)
+    a, b = C.c_int(), C.c_int()
+    load_library().rtjgpu_tables_from_raw(raw.ctypes.data_as(_u32p), out.ctypes.data_as(_u32p), C.byref(a), C.byref(b))
+    return out, a.value, b.value
+
+
+def split_shards(clean: np.ndarray, n: int) -> np.ndarray:
+    L = load_library()
+    clean = np.ascontiguousarray(clean, dtype=np.uint8)
+    first = (C.c_int * (n + 1))()
+    _check(L.rtjgpu_split_shards(_u8(clean), len(clean), n, first), "rtjgpu_split_shards")
+    return np.array(first[:], dtype=np.int64)
+
+
+class BatchContext:
+    """rtjgpu_ctx: one per device and per decoding thread."""
+
+    def __init__(self, device: int = 0):
+        self._L = load_library()
+        h = C.c_void_p()
+        rc = self._L.rtjgpu_create(device, C.byref(h))
+        if rc != OK or not h.value:
+            raise RTjpegError(rc or E_CUDA, f"rtjgpu_create(device={device}): no usable CUDA device, and no CPU fallback")
+        self._h = h
+        self.device = device
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._L.rtjgpu_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def set_custom_tables(self, raw: np.ndarray) -> None:
+        raw = np.ascontiguousarray(raw, dtype=np.uint32)
+        assert raw.size == 128
+        _check(self._L.rtjgpu_set_custom_tables(self._h, raw.ctypes.data_as(_u32p)), "rtjgpu_set_custom_tables")
+
+    def decode_device(self, d_stream: int, d_desc: int, F: int, w: int, h: int, d_out: int,
+                      d_carry: int | None = None, cuda_stream: int | None = None) -> None:
+        """All pointers are raw device addresses (e.g. torch.Tensor.data_ptr())."""
+        _check(self._L.rtjgpu_decode_device(self._h, C.c_void_p(d_stream), C.c_void_p(d_desc), F, w, h,
+                                            C.c_void_p(d_out), C.c_void_p(d_carry or 0),
+                                            C.c_void_p(cuda_stream or 0)), "rtjgpu_decode_device")
+
+    def decode_host(self, stream: np.ndarray, offsets: np.ndarray, out: np.ndarray, state: State | None = None,
+                    carry: np.ndarray | None = None, flags: int = 0) -> State:
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        F = len(offsets) - 1
+        st = State(0, 0, TABLE_ZERO, 0) if state is None else state
+        assert stream.dtype == np.uint8 and out.dtype == np.uint8 and out.flags.c_contiguous
+        _check(self._L.rtjgpu_decode_host(self._h, _u8(stream), offsets.ctypes.data_as(_u64p), F, C.byref(st),
+                                          _u8(out), None if carry is None else _u8(carry), flags),
+               "rtjgpu_decode_host")
+        return st
+
+    def sync(self) -> None:
+        _check(self._L.rtjgpu_sync(self._h), "rtjgpu_sync")
+
+    def enable_timing(self, on: bool = True) -> None:
+        self._L.rtjgpu_enable_timing(self._h, 1 if on else 0)
+
+    def timing(self) -> Timing:
+        t = Timing()
+        _check(self._L.rtjgpu_get_timing(self._h, C.byref(t)), "rtjgpu_get_timing")
+        return t
+
+    def timing_at(self, calls_ago: int) -> Timing:
+        t = Timing()
+        _check(self._L.rtjgpu_get_timing_at(self._h, calls_ago, C.byref(t)), "rtjgpu_get_timing_at")
+        return t
+
+    def batch_info(self) -> BatchInfo:
+        b = BatchInfo()
+        _check(self._L.rtjgpu_get_batch_info(self._h, C.byref(b)), "rtjgpu_get_batch_info")
+        return b
+
+    def skip_counts(self, F: int) -> np.ndarray:
+        out = np.zeros(F, dtype=np.uint32)
+        _check(self._L.rtjgpu_get_skip_counts(self._h, out.ctypes.data_as(_u32p), F), "rtjgpu_get_skip_counts")
+        return out
+
+    def launch_count(self) -> int:
+        return int(self._L.rtjgpu_launch_count(self._h))
+
+
+# Level 1 ----------------------------------------------------------------------
+
+class RTjpeg:
+    """The reference's codec object (include/RTjpeg.h:115-139) -- decode side."""
+
+    def __init__(self):
+        self._L = load_library()
+        h = self._L.RTjpeg_init()
+        if not h:
+            raise RTjpegError(E_CUDA, "RTjpeg_init: no usable CUDA device, and no CPU fallback")
+        self._h = C.c_void_p(h)
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._L.RTjpeg_close(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def set_quality(self, q: int) -> int:
+        v = C.c_int(q)
+        self._L.RTjpeg_set_quality(self._h, C.byref(v))
+        return v.value
+
+    def set_format(self, fmt: int) -> None:
+        v = C.c_int(fmt)
+        self._L.RTjpeg_set_format(self._h, C.byref(v))
+
+    def set_size(self, w: int, h: int) -> int:
+        a, b = C.c_int(w), C.c_int(h)
+        return self._L.RTjpeg_set_size(self._h, C.byref(a), C.byref(b))
+
+    def set_intra(self, key: int, lm: int, cm: int):
+        a, b, c = C.c_int(key), C.c_int(lm), C.c_int(cm)
+        self._L.RTjpeg_set_intra(self._h, C.byref(a), C.byref(b), C.byref(c))
+        return a.value, b.value, c.value
+
+    def get_tables(self) -> np.ndarray:
+        out = np.zeros(128, dtype=np.uint32)
+        self._L.RTjpeg_get_tables(self._h, out.ctypes.data_as(_u32p))
+        return out
+
+    def set_tables(self, raw: np.ndarray) -> None:
+        raw = np.ascontiguousarray(raw, dtype=np.uint32).copy()
+        self._L.RTjpeg_set_tables(self._h, raw.ctypes.data_as(_u32p))
+
+    def _planes(self, planes: np.ndarray, w: int, h: int):
+        assert planes.dtype == np.uint8 and planes.flags.c_contiguous and planes.size >= w * h * 3 // 2
+        base = planes.ctypes.data
+        arr = (_u8p * 3)(C.cast(base, _u8p), C.cast(base + w * h, _u8p), C.cast(base + w * h * 5 // 4, _u8p))
+        return arr
+
+    def decompress(self, pkt: np.ndarray, planes: np.ndarray) -> None:
+        """RTjpeg_decompress: planes is one tight YUV420 buffer (Y|U|V) updated in place."""
+        pkt = np.ascontiguousarray(pkt, dtype=np.uint8)
+        w = int(pkt[6]) | int(pkt[7]) << 8
+        h = int(pkt[8]) | int(pkt[9]) << 8
+        self._L.RTjpeg_decompress(self._h, _u8(pkt), self._planes(planes, w, h))
+
+    def decompress_n(self, pkt: np.ndarray, planes: np.ndarray) -> int:
+        pkt = np.ascontiguousarray(pkt, dtype=np.uint8)
+        if pkt.size < 12:
+            return self._L.RTjpeg_b200_decompress_n(self._h, _u8(pkt), pkt.size, self._planes(planes, 0, 0))
+        w = int(pkt[6]) | int(pkt[7]) << 8
+        h = int(pkt[8]) | int(pkt[9]) << 8
+        return self._L.RTjpeg_b200_decompress_n(self._h, _u8(pkt), pkt.size, self._planes(planes, w, h))
+
+    def last_error(self) -> int:
+        return int(self._L.RTjpeg_b200_last_error(self._h))

@@ -1,0 +1,579 @@
+/*
+ * rtj_batch.cpp -- batch context of the B200 RTjpeg decoder (Level 2 of
+ * include/rtjpeg_b200.h): device tables, workspaces, the device-resident
+ * decode and the pinned-memory host pipeline.
+ *
+ * Host-side counterpart of what RTjpeg_decompress (lib/RTjpeg.c:3565-3586)
+ * does before it starts walking blocks: header parse and lazy size / quality
+ * reconfiguration -- done here once per batch on the CPU (rtjgpu_plan), the
+ * block work itself runs in rtj_kernels.cu.
+ */
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "rtj_common.h"
+
+namespace {
+
+struct Workspace {
+    uint32_t     *d_ent = nullptr;
+    uint16_t     *d_src = nullptr;
+    uint32_t     *d_frame_skips = nullptr;
+    rtj_dev_info *d_info = nullptr;
+    size_t        cap_entries = 0;
+    int           cap_frames = 0;
+};
+
+constexpr int HOST_SLOTS = 3;
+constexpr int TIMING_RING = 256;
+
+struct HostSlot {
+    cudaStream_t       stream = nullptr;
+    cudaEvent_t        decoded = nullptr;     /* kernels of the chunk in this slot have finished */
+    Workspace          ws;
+    uint8_t           *d_in = nullptr;   size_t d_in_cap = 0;
+    uint8_t           *d_out = nullptr;  size_t d_out_cap = 0;
+    rtjgpu_frame_desc *d_desc = nullptr; int    desc_cap = 0;
+    uint8_t           *h_in = nullptr;   size_t h_in_cap = 0;    /* pinned */
+    uint8_t           *h_out = nullptr;  size_t h_out_cap = 0;   /* pinned */
+    rtjgpu_frame_desc *h_desc = nullptr; int    h_desc_cap = 0;  /* pinned */
+    rtj_dev_info      *h_info = nullptr;                         /* pinned read-back of the chunk's counters */
+    /* pending drain of h_out into the caller's memory */
+    uint8_t           *pending_dst = nullptr;
+    size_t             pending_bytes = 0;
+    bool               busy = false;
+};
+
+} // namespace
+
+struct rtjgpu_ctx {
+    int            device = 0;
+    int            last_cuda = 0;
+    rtj_dev_table *d_tables = nullptr;
+    rtj_host_table h_tables[RTJ_NUM_TABLES];
+    Workspace      ws;                        /* rtjgpu_decode_device */
+    rtj_dev_info  *h_info_reset = nullptr;    /* pinned template {0,0,0,-1} */
+    rtj_dev_info  *h_info = nullptr;          /* pinned read-back */
+    int            last_F = 0;
+    void          *last_stream = nullptr;
+    bool           timing = false;
+    cudaEvent_t    ev[TIMING_RING][4] = {};   /* stage brackets of the last TIMING_RING device batches */
+    uint64_t       timed_calls = 0;
+    uint64_t       launches = 0;
+    HostSlot       slot[HOST_SLOTS];
+    bool           slots_ready = false;
+    uint8_t       *d_host_carry = nullptr;    /* carry plane of the host pipeline */
+    size_t         d_host_carry_cap = 0;
+    uint64_t       host_bad = 0;              /* overrun frames seen by the current rtjgpu_decode_host call */
+};
+
+namespace {
+
+#define CK(ctx, call)                                             \
+    do {                                                          \
+        cudaError_t e__ = (call);                                 \
+        if (e__ != cudaSuccess) {                                 \
+            (ctx)->last_cuda = (int)e__;                          \
+            return RTJGPU_E_CUDA;                                 \
+        }                                                         \
+    } while (0)
+
+int ws_reserve(rtjgpu_ctx *ctx, Workspace *ws, int F, int nblk)
+{
+    const size_t need = (size_t)F * (size_t)nblk;
+    if (need > ws->cap_entries) {
+        if (ws->d_ent) cudaFree(ws->d_ent);
+        if (ws->d_src) cudaFree(ws->d_src);
+        ws->d_ent = nullptr; ws->d_src = nullptr; ws->cap_entries = 0;
+        CK(ctx, cudaMalloc(&ws->d_ent, need * sizeof(uint32_t)));
+        CK(ctx, cudaMalloc(&ws->d_src, need * sizeof(uint16_t)));
+        ws->cap_entries = need;
+    }
+    if (F > ws->cap_frames) {
+        if (ws->d_frame_skips) cudaFree(ws->d_frame_skips);
+        ws->d_frame_skips = nullptr; ws->cap_frames = 0;
+        CK(ctx, cudaMalloc(&ws->d_frame_skips, (size_t)F * sizeof(uint32_t)));
+        ws->cap_frames = F;
+    }
+    if (!ws->d_info) CK(ctx, cudaMalloc(&ws->d_info, sizeof(rtj_dev_info)));
+    return RTJGPU_OK;
+}
+
+void ws_release(Workspace *ws)
+{
+    if (ws->d_ent) cudaFree(ws->d_ent);
+    if (ws->d_src) cudaFree(ws->d_src);
+    if (ws->d_frame_skips) cudaFree(ws->d_frame_skips);
+    if (ws->d_info) cudaFree(ws->d_info);
+    *ws = Workspace();
+}
+
+/* K1 -> K3 -> K2 on one stream.  ev != NULL brackets the stages with events. */
+int run_kernels(rtjgpu_ctx *ctx, Workspace *ws, const uint8_t *d_stream, const rtjgpu_frame_desc *d_desc,
+                int F, int w, int h, uint8_t *d_out, const uint8_t *d_carry, cudaStream_t st, cudaEvent_t *ev)
+{
+    rtj_launch_args a;
+    a.d_stream = d_stream; a.d_desc = d_desc; a.d_tables = ctx->d_tables;
+    a.F = F; a.w = w; a.h = h;
+    a.d_ent = ws->d_ent; a.d_src = ws->d_src; a.d_frame_skips = ws->d_frame_skips; a.d_info = ws->d_info;
+    a.d_out = d_out; a.d_carry = d_carry;
+
+    CK(ctx, cudaMemcpyAsync(ws->d_info, ctx->h_info_reset, sizeof(rtj_dev_info), cudaMemcpyHostToDevice, st));
+    if (ev) CK(ctx, cudaEventRecord(ev[0], st));
+    int e = rtj_launch_scan(&a, st);
+    if (e) { ctx->last_cuda = e; return RTJGPU_E_CUDA; }
+    if (ev) CK(ctx, cudaEventRecord(ev[1], st));
+    e = rtj_launch_resolve(&a, st);
+    if (e) { ctx->last_cuda = e; return RTJGPU_E_CUDA; }
+    if (ev) CK(ctx, cudaEventRecord(ev[2], st));
+    e = rtj_launch_idct(&a, st);
+    if (e) { ctx->last_cuda = e; return RTJGPU_E_CUDA; }
+    if (ev) CK(ctx, cudaEventRecord(ev[3], st));
+    ctx->launches += 3;
+    return RTJGPU_OK;
+}
+
+inline uint32_t rd_u32le(const uint8_t *p) { return (uint32_t)p[0] | (uint32_t)p[1] << 8 | (uint32_t)p[2] << 16 | (uint32_t)p[3] << 24; }
+inline uint16_t rd_u16le(const uint8_t *p) { return (uint16_t)(p[0] | p[1] << 8); }
+
+template <typename T>
+int grow_device(rtjgpu_ctx *ctx, T **p, size_t *cap, size_t need)
+{
+    if (need <= *cap) return RTJGPU_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr; *cap = 0;
+    CK(ctx, cudaMalloc(p, need * sizeof(T)));
+    *cap = need;
+    return RTJGPU_OK;
+}
+
+template <typename T>
+int grow_pinned(rtjgpu_ctx *ctx, T **p, size_t *cap, size_t need)
+{
+    if (need <= *cap) return RTJGPU_OK;
+    if (*p) cudaFreeHost(*p);
+    *p = nullptr; *cap = 0;
+    CK(ctx, cudaMallocHost(p, need * sizeof(T)));
+    *cap = need;
+    return RTJGPU_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+const char *rtjgpu_strerror(int code)
+{
+    switch (code) {
+    case RTJGPU_OK:        return "ok";
+    case RTJGPU_E_CUDA:    return "CUDA call failed";
+    case RTJGPU_E_ARG:     return "bad argument";
+    case RTJGPU_E_HEADER:  return "packet shorter than its header or framesize";
+    case RTJGPU_E_SIZE:    return "width/height zero, not a multiple of 16, or changing inside a batch";
+    case RTJGPU_E_FORMAT:  return "only YUV420 is decoded";
+    case RTJGPU_E_OVERRUN: return "block stream runs past the end of its packet";
+    case RTJGPU_E_TOOBIG:  return "batch exceeds RTJGPU_MAX_FRAMES_PER_BATCH / RTJGPU_MAX_PAYLOAD_BYTES";
+    case RTJGPU_E_NOMEM:   return "out of memory";
+    default:               return "unknown error";
+    }
+}
+
+int rtjgpu_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int rtjgpu_create(int device, rtjgpu_ctx **out)
+{
+    if (!out) return RTJGPU_E_ARG;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || device < 0 || device >= n) return RTJGPU_E_CUDA;   /* no CPU fallback */
+    rtjgpu_ctx *ctx = new (std::nothrow) rtjgpu_ctx();
+    if (!ctx) return RTJGPU_E_NOMEM;
+    ctx->device = device;
+    int rc = RTJGPU_OK;
+    do {
+        if ((e = cudaSetDevice(device)) != cudaSuccess) { rc = RTJGPU_E_CUDA; break; }
+        if (int k = rtj_kernels_init()) { e = (cudaError_t)k; rc = RTJGPU_E_CUDA; break; }
+        /* table 0: never-configured instance (all zero, lb8 = cb8 = 0); 1..255: quality; 256: custom */
+        memset(ctx->h_tables, 0, sizeof(ctx->h_tables));
+        std::vector<rtj_dev_table> dev(RTJ_NUM_TABLES);
+        for (int q = 1; q <= 255; q++) rtj_table_from_quality(q, &ctx->h_tables[q]);
+        for (int t = 0; t < RTJ_NUM_TABLES; t++) rtj_table_to_device_layout(&ctx->h_tables[t], &dev[t]);
+        if ((e = cudaMalloc(&ctx->d_tables, sizeof(rtj_dev_table) * RTJ_NUM_TABLES)) != cudaSuccess) { rc = RTJGPU_E_CUDA; break; }
+        if ((e = cudaMemcpy(ctx->d_tables, dev.data(), sizeof(rtj_dev_table) * RTJ_NUM_TABLES, cudaMemcpyHostToDevice)) != cudaSuccess) { rc = RTJGPU_E_CUDA; break; }
+        if ((e = cudaMallocHost(&ctx->h_info_reset, sizeof(rtj_dev_info))) != cudaSuccess) { rc = RTJGPU_E_CUDA; break; }
+        if ((e = cudaMallocHost(&ctx->h_info, sizeof(rtj_dev_info))) != cudaSuccess) { rc = RTJGPU_E_CUDA; break; }
+        memset(ctx->h_info_reset, 0, sizeof(rtj_dev_info));
+        ctx->h_info_reset->first_bad_frame = -1;
+        *ctx->h_info = *ctx->h_info_reset;
+        for (int i = 0; i < TIMING_RING * 4 && rc == RTJGPU_OK; i++)
+            if ((e = cudaEventCreate(&ctx->ev[i / 4][i % 4])) != cudaSuccess) rc = RTJGPU_E_CUDA;
+    } while (0);
+    if (rc != RTJGPU_OK) {
+        ctx->last_cuda = (int)e;
+        rtjgpu_destroy(ctx);
+        return rc;
+    }
+    *out = ctx;
+    return RTJGPU_OK;
+}
+
+void rtjgpu_destroy(rtjgpu_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    ws_release(&ctx->ws);
+    for (int i = 0; i < HOST_SLOTS; i++) {
+        HostSlot &s = ctx->slot[i];
+        ws_release(&s.ws);
+        if (s.d_in) cudaFree(s.d_in);
+        if (s.d_out) cudaFree(s.d_out);
+        if (s.d_desc) cudaFree(s.d_desc);
+        if (s.h_in) cudaFreeHost(s.h_in);
+        if (s.h_out) cudaFreeHost(s.h_out);
+        if (s.h_desc) cudaFreeHost(s.h_desc);
+        if (s.h_info) cudaFreeHost(s.h_info);
+        if (s.decoded) cudaEventDestroy(s.decoded);
+        if (s.stream) cudaStreamDestroy(s.stream);
+    }
+    if (ctx->d_host_carry) cudaFree(ctx->d_host_carry);
+    if (ctx->d_tables) cudaFree(ctx->d_tables);
+    if (ctx->h_info_reset) cudaFreeHost(ctx->h_info_reset);
+    if (ctx->h_info) cudaFreeHost(ctx->h_info);
+    for (int i = 0; i < TIMING_RING * 4; i++) if (ctx->ev[i / 4][i % 4]) cudaEventDestroy(ctx->ev[i / 4][i % 4]);
+    delete ctx;
+}
+
+int rtjgpu_last_cuda_error(const rtjgpu_ctx *ctx) { return ctx ? ctx->last_cuda : 0; }
+uint64_t rtjgpu_launch_count(const rtjgpu_ctx *ctx) { return ctx ? ctx->launches : 0; }
+void rtjgpu_enable_timing(rtjgpu_ctx *ctx, int on) { if (ctx) ctx->timing = on != 0; }
+
+int rtjgpu_set_custom_tables(rtjgpu_ctx *ctx, const uint32_t raw[128])
+{
+    if (!ctx || !raw) return RTJGPU_E_ARG;
+    CK(ctx, cudaSetDevice(ctx->device));
+    rtj_table_from_raw(raw, &ctx->h_tables[RTJGPU_TABLE_CUSTOM]);
+    rtj_dev_table dev;
+    rtj_table_to_device_layout(&ctx->h_tables[RTJGPU_TABLE_CUSTOM], &dev);
+    /* ordered after everything already queued on the device */
+    CK(ctx, cudaDeviceSynchronize());
+    CK(ctx, cudaMemcpy(ctx->d_tables + RTJGPU_TABLE_CUSTOM, &dev, sizeof(dev), cudaMemcpyHostToDevice));
+    return RTJGPU_OK;
+}
+
+/* internal: host tables in the reference's raster order (for RTjpeg_get_tables) */
+const rtj_host_table *rtjgpu_host_table(const rtjgpu_ctx *ctx, int table)
+{
+    if (!ctx || table < 0 || table >= RTJ_NUM_TABLES) return nullptr;
+    return &ctx->h_tables[table];
+}
+
+int rtjgpu_plan(const uint8_t *stream, const uint64_t *offsets, int F, rtjgpu_state *state, rtjgpu_frame_desc *desc)
+{
+    if (!stream || !offsets || !state || (F > 0 && !desc) || F < 0) return RTJGPU_E_ARG;
+    if (F > RTJGPU_MAX_FRAMES_PER_BATCH) return RTJGPU_E_TOOBIG;
+    rtjgpu_state st = *state;
+    int bw = 0, bh = 0;
+    for (int f = 0; f < F; f++) {
+        if (offsets[f + 1] < offsets[f]) return RTJGPU_E_ARG;
+        const uint64_t avail = offsets[f + 1] - offsets[f];
+        if (avail < RTJPEG_B200_HEADER_BYTES) return RTJGPU_E_HEADER;
+        if (offsets[f] & 3u) return RTJGPU_E_ARG;
+        const uint8_t *p = stream + offsets[f];
+        /* packed little-endian header, include/RTjpeg.h:100-109 */
+        const uint32_t framesize = rd_u32le(p);
+        const int w = rd_u16le(p + 6), h = rd_u16le(p + 8), q = p[10];
+        /* the reference never reads framesize/headersize (lib/RTjpeg.c:3565-3586); here the
+         * smaller of framesize and the bytes actually present bounds every read */
+        uint64_t len = avail;
+        if (framesize >= RTJPEG_B200_HEADER_BYTES && framesize < len) len = framesize;
+        if (len - RTJPEG_B200_HEADER_BYTES > RTJGPU_MAX_PAYLOAD_BYTES) return RTJGPU_E_TOOBIG;
+        if (w != st.width || h != st.height) { st.width = w; st.height = h; }   /* :3568-3574 */
+        if (w == 0 || h == 0 || (w & 15) || (h & 15)) return RTJGPU_E_SIZE;     /* the row loop of :2701 needs /16 */
+        if (f == 0) { bw = w; bh = h; }
+        else if (w != bw || h != bh) return RTJGPU_E_SIZE;
+        if (q != st.quality) {                                                   /* :3575-3579 */
+            const int qc = q < 1 ? 1 : q;                                        /* set_quality clamps, :2410-2412 */
+            st.quality = qc;
+            st.table = qc;
+        }
+        desc[f].offset = offsets[f];
+        desc[f].length = (uint32_t)len;
+        desc[f].table = (uint16_t)st.table;
+        desc[f].flags = 0;
+    }
+    *state = st;
+    return RTJGPU_OK;
+}
+
+int rtjgpu_decode_device(rtjgpu_ctx *ctx, const uint8_t *d_stream, const rtjgpu_frame_desc *d_desc, int F,
+                         int w, int h, uint8_t *d_out, const uint8_t *d_carry, void *cuda_stream)
+{
+    if (!ctx || F < 0) return RTJGPU_E_ARG;
+    if (F == 0) { ctx->last_F = 0; return RTJGPU_OK; }
+    if (!d_stream || !d_desc || !d_out) return RTJGPU_E_ARG;
+    if (w <= 0 || h <= 0 || (w & 15) || (h & 15) || w > 65535 || h > 65535) return RTJGPU_E_SIZE;
+    if (F > RTJGPU_MAX_FRAMES_PER_BATCH) return RTJGPU_E_TOOBIG;
+    CK(ctx, cudaSetDevice(ctx->device));
+    const int nblk = (w >> 4) * (h >> 4) * 6;
+    int rc = ws_reserve(ctx, &ctx->ws, F, nblk);
+    if (rc) return rc;
+    cudaEvent_t *ev = ctx->timing ? ctx->ev[ctx->timed_calls % TIMING_RING] : nullptr;
+    rc = run_kernels(ctx, &ctx->ws, d_stream, d_desc, F, w, h, d_out, d_carry, (cudaStream_t)cuda_stream, ev);
+    if (ev && rc == RTJGPU_OK) ctx->timed_calls++;
+    ctx->last_F = F;
+    ctx->last_stream = cuda_stream;
+    return rc;
+}
+
+int rtjgpu_sync(rtjgpu_ctx *ctx)
+{
+    if (!ctx) return RTJGPU_E_ARG;
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaDeviceSynchronize());
+    return RTJGPU_OK;
+}
+
+int rtjgpu_get_timing_at(rtjgpu_ctx *ctx, int calls_ago, rtjgpu_timing *out)
+{
+    if (!ctx || !out || calls_ago < 0 || calls_ago >= TIMING_RING) return RTJGPU_E_ARG;
+    memset(out, 0, sizeof(*out));
+    if ((uint64_t)calls_ago >= ctx->timed_calls) return RTJGPU_E_ARG;
+    cudaEvent_t *ev = ctx->ev[(ctx->timed_calls - 1 - (uint64_t)calls_ago) % TIMING_RING];
+    CK(ctx, cudaEventSynchronize(ev[3]));
+    CK(ctx, cudaEventElapsedTime(&out->scan_ms, ev[0], ev[1]));
+    CK(ctx, cudaEventElapsedTime(&out->resolve_ms, ev[1], ev[2]));
+    CK(ctx, cudaEventElapsedTime(&out->idct_ms, ev[2], ev[3]));
+    CK(ctx, cudaEventElapsedTime(&out->total_ms, ev[0], ev[3]));
+    return RTJGPU_OK;
+}
+
+int rtjgpu_get_timing(rtjgpu_ctx *ctx, rtjgpu_timing *out)
+{
+    if (!ctx || !out) return RTJGPU_E_ARG;
+    memset(out, 0, sizeof(*out));
+    if (!ctx->timed_calls) return RTJGPU_OK;
+    return rtjgpu_get_timing_at(ctx, 0, out);
+}
+
+int rtjgpu_get_batch_info(rtjgpu_ctx *ctx, rtjgpu_batch_info *out)
+{
+    if (!ctx || !out) return RTJGPU_E_ARG;
+    memset(out, 0, sizeof(*out));
+    out->first_bad_frame = -1;
+    if (ctx->last_F == 0 || !ctx->ws.d_info) return RTJGPU_OK;
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaDeviceSynchronize());
+    CK(ctx, cudaMemcpy(ctx->h_info, ctx->ws.d_info, sizeof(rtj_dev_info), cudaMemcpyDeviceToHost));
+    out->skipped_blocks = ctx->h_info->skipped_blocks;
+    out->payload_bytes = ctx->h_info->payload_bytes;
+    out->bad_frames = ctx->h_info->bad_frames;
+    out->first_bad_frame = ctx->h_info->first_bad_frame;
+    return RTJGPU_OK;
+}
+
+int rtjgpu_get_skip_counts(rtjgpu_ctx *ctx, uint32_t *counts, int F)
+{
+    if (!ctx || !counts || F < 0 || F > ctx->last_F) return RTJGPU_E_ARG;
+    if (F == 0) return RTJGPU_OK;
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaDeviceSynchronize());
+    CK(ctx, cudaMemcpy(counts, ctx->ws.d_frame_skips, (size_t)F * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    return RTJGPU_OK;
+}
+
+/* internal, for the Level-1 shim: block entries of the last device batch */
+int rtjgpu_get_entries(rtjgpu_ctx *ctx, uint32_t *entries, size_t n)
+{
+    if (!ctx || !entries) return RTJGPU_E_ARG;
+    CK(ctx, cudaMemcpy(entries, ctx->ws.d_ent, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    return RTJGPU_OK;
+}
+
+int rtjgpu_split_shards(const uint8_t *clean, int F, int n, int *first)
+{
+    if (!clean || !first || n < 1 || F < 0) return RTJGPU_E_ARG;
+    first[0] = 0;
+    for (int i = 1; i < n; i++) {
+        /* ideal cut, then the nearest clean frame at or after it (never before the previous cut) */
+        long ideal = (long)F * i / n;
+        int cut = (int)std::max<long>(ideal, first[i - 1]);
+        while (cut < F && !clean[cut]) cut++;
+        first[i] = cut;
+    }
+    first[n] = F;
+    return RTJGPU_OK;
+}
+
+static void export_table(const rtj_host_table &t, uint32_t scaled[128], int *lb8, int *cb8)
+{
+    for (int i = 0; i < 64; i++) {
+        scaled[i] = (uint32_t)t.liqt[i];
+        scaled[64 + i] = (uint32_t)t.ciqt[i];
+    }
+    if (lb8) *lb8 = t.lb8;
+    if (cb8) *cb8 = t.cb8;
+}
+
+void rtjgpu_tables_for_quality(int Q, uint32_t scaled[128], int *lb8, int *cb8)
+{
+    rtj_host_table t;
+    rtj_table_from_quality(Q, &t);
+    export_table(t, scaled, lb8, cb8);
+}
+
+void rtjgpu_tables_from_raw(const uint32_t raw[128], uint32_t scaled[128], int *lb8, int *cb8)
+{
+    rtj_host_table t;
+    rtj_table_from_raw(raw, &t);
+    export_table(t, scaled, lb8, cb8);
+}
+
+void *rtjgpu_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr;
+    return p;
+}
+
+void rtjgpu_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+/* ------------------------------------------------------------------------ */
+/* host pipeline                                                              */
+/* ------------------------------------------------------------------------ */
+
+static int slots_init(rtjgpu_ctx *ctx)
+{
+    if (ctx->slots_ready) return RTJGPU_OK;
+    for (int i = 0; i < HOST_SLOTS; i++) {
+        CK(ctx, cudaStreamCreateWithFlags(&ctx->slot[i].stream, cudaStreamNonBlocking));
+        CK(ctx, cudaEventCreateWithFlags(&ctx->slot[i].decoded, cudaEventDisableTiming));
+        CK(ctx, cudaMallocHost(&ctx->slot[i].h_info, sizeof(rtj_dev_info)));
+    }
+    ctx->slots_ready = true;
+    return RTJGPU_OK;
+}
+
+static int slot_drain(rtjgpu_ctx *ctx, HostSlot &s)
+{
+    if (!s.busy) return RTJGPU_OK;
+    CK(ctx, cudaStreamSynchronize(s.stream));
+    ctx->host_bad += s.h_info->bad_frames;
+    if (s.pending_dst) memcpy(s.pending_dst, s.h_out, s.pending_bytes);
+    s.pending_dst = nullptr;
+    s.pending_bytes = 0;
+    s.busy = false;
+    return RTJGPU_OK;
+}
+
+int rtjgpu_decode_host(rtjgpu_ctx *ctx, const uint8_t *h_stream, const uint64_t *offsets, int F,
+                       rtjgpu_state *state, uint8_t *h_out, uint8_t *h_carry_inout, int flags)
+{
+    if (!ctx || !state || F < 0) return RTJGPU_E_ARG;
+    if (F == 0) return RTJGPU_OK;
+    if (!h_stream || !offsets || !h_out) return RTJGPU_E_ARG;
+    CK(ctx, cudaSetDevice(ctx->device));
+    int rc = slots_init(ctx);
+    if (rc) return rc;
+
+    /* geometry from the first header; rtjgpu_plan re-checks every frame */
+    if (offsets[1] - offsets[0] < RTJPEG_B200_HEADER_BYTES) return RTJGPU_E_HEADER;
+    const int w = rd_u16le(h_stream + offsets[0] + 6), h = rd_u16le(h_stream + offsets[0] + 8);
+    if (w == 0 || h == 0 || (w & 15) || (h & 15)) return RTJGPU_E_SIZE;
+    const size_t fsz = (size_t)w * h * 3 / 2;
+    const int nblk = (w >> 4) * (h >> 4) * 6;
+
+    /* chunk size: ~64 MB of output per chunk keeps three slots in flight without
+     * hoarding memory; at least 1, at most the batch limit */
+    int chunk = (int)std::max<size_t>(1, (64u << 20) / fsz);
+    chunk = std::min(chunk, RTJGPU_MAX_FRAMES_PER_BATCH);
+    chunk = std::min(chunk, F);
+
+    rc = grow_device(ctx, &ctx->d_host_carry, &ctx->d_host_carry_cap, fsz);
+    if (rc) return rc;
+    const bool have_carry = h_carry_inout != nullptr;
+    if (have_carry)
+        CK(ctx, cudaMemcpy(ctx->d_host_carry, h_carry_inout, fsz, cudaMemcpyHostToDevice));
+
+    const uint8_t *d_prev = have_carry ? ctx->d_host_carry : nullptr;
+    cudaEvent_t prev_decoded = nullptr;
+    rtjgpu_state st = *state;
+    int result = RTJGPU_OK;
+    ctx->host_bad = 0;
+
+    for (int c0 = 0, ci = 0; c0 < F; c0 += chunk, ci++) {
+        const int n = std::min(chunk, F - c0);
+        HostSlot &s = ctx->slot[ci % HOST_SLOTS];
+        if ((rc = slot_drain(ctx, s))) { result = rc; break; }
+
+        const uint64_t b0 = offsets[c0], b1 = offsets[c0 + n];
+        const size_t in_bytes = (size_t)(b1 - b0);
+        if ((rc = grow_device(ctx, &s.d_in, &s.d_in_cap, in_bytes + RTJGPU_STREAM_SLACK_BYTES))) { result = rc; break; }
+        if ((rc = grow_device(ctx, &s.d_out, &s.d_out_cap, fsz * (size_t)n))) { result = rc; break; }
+        size_t dcap = (size_t)s.desc_cap;
+        if ((rc = grow_device(ctx, &s.d_desc, &dcap, (size_t)n))) { result = rc; break; }
+        s.desc_cap = (int)dcap;
+        size_t hcap = (size_t)s.h_desc_cap;
+        if ((rc = grow_pinned(ctx, &s.h_desc, &hcap, (size_t)n))) { result = rc; break; }
+        s.h_desc_cap = (int)hcap;
+        if ((rc = ws_reserve(ctx, &s.ws, n, nblk))) { result = rc; break; }
+
+        /* descriptors relative to the chunk's own device buffer */
+        std::vector<uint64_t> rel((size_t)n + 1);
+        for (int i = 0; i <= n; i++) rel[(size_t)i] = offsets[c0 + i] - b0;
+        if ((rc = rtjgpu_plan(h_stream + b0, rel.data(), n, &st, s.h_desc))) { result = rc; break; }
+        if (st.width != w || st.height != h) { result = RTJGPU_E_SIZE; break; }
+
+        const uint8_t *src = h_stream + b0;
+        if (!(flags & RTJGPU_HOST_IN_PINNED)) {
+            if ((rc = grow_pinned(ctx, &s.h_in, &s.h_in_cap, in_bytes))) { result = rc; break; }
+            memcpy(s.h_in, src, in_bytes);
+            src = s.h_in;
+        }
+        CK(ctx, cudaMemcpyAsync(s.d_in, src, in_bytes, cudaMemcpyHostToDevice, s.stream));
+        CK(ctx, cudaMemsetAsync(s.d_in + in_bytes, 0x7F, RTJGPU_STREAM_SLACK_BYTES, s.stream));
+        CK(ctx, cudaMemcpyAsync(s.d_desc, s.h_desc, sizeof(rtjgpu_frame_desc) * (size_t)n, cudaMemcpyHostToDevice, s.stream));
+        if (prev_decoded) CK(ctx, cudaStreamWaitEvent(s.stream, prev_decoded, 0));   /* carry comes from the previous chunk */
+        if ((rc = run_kernels(ctx, &s.ws, s.d_in, s.d_desc, n, w, h, s.d_out, d_prev, s.stream, nullptr))) { result = rc; break; }
+        CK(ctx, cudaEventRecord(s.decoded, s.stream));
+        CK(ctx, cudaMemcpyAsync(s.h_info, s.ws.d_info, sizeof(rtj_dev_info), cudaMemcpyDeviceToHost, s.stream));
+        prev_decoded = s.decoded;
+        d_prev = s.d_out + fsz * (size_t)(n - 1);
+
+        uint8_t *dst = h_out + fsz * (size_t)c0;
+        if (flags & RTJGPU_HOST_OUT_PINNED) {
+            CK(ctx, cudaMemcpyAsync(dst, s.d_out, fsz * (size_t)n, cudaMemcpyDeviceToHost, s.stream));
+            s.pending_dst = nullptr;
+        } else {
+            if ((rc = grow_pinned(ctx, &s.h_out, &s.h_out_cap, fsz * (size_t)n))) { result = rc; break; }
+            CK(ctx, cudaMemcpyAsync(s.h_out, s.d_out, fsz * (size_t)n, cudaMemcpyDeviceToHost, s.stream));
+            s.pending_dst = dst;
+            s.pending_bytes = fsz * (size_t)n;
+        }
+        s.busy = true;
+    }
+    /* drain in issue order so that later chunks' carries are complete */
+    for (int i = 0; i < HOST_SLOTS; i++) {
+        int rc2 = slot_drain(ctx, ctx->slot[i]);
+        if (rc2 && !result) result = rc2;
+    }
+    if (result == RTJGPU_OK && ctx->host_bad) result = RTJGPU_E_OVERRUN;
+    if (result == RTJGPU_OK || result == RTJGPU_E_OVERRUN) {
+        if (have_carry) memcpy(h_carry_inout, h_out + fsz * (size_t)(F - 1), fsz);
+        *state = st;
+    }
+    return result;
+}
+
+} // extern "C"

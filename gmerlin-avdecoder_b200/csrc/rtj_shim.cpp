@@ -1,0 +1,246 @@
+/*
+ * rtj_shim.cpp -- Level 1 of include/rtjpeg_b200.h: the reference's codec API
+ * (include/RTjpeg.h:115-139) on top of the batch context.
+ *
+ * One RTjpeg_t owns one rtjgpu_ctx (tables, workspace, streams) on the device
+ * named by $RTJPEG_B200_DEVICE.  RTjpeg_decompress is the one-frame batch:
+ * packet -> pinned staging -> device -> K1/K3/K2 -> pinned frame -> caller's
+ * planes.  The reference leaves skipped blocks untouched in the caller's
+ * planes (lib/RTjpeg.c:2704); the shim reproduces that on the host side by
+ * copying back only the blocks the frame coded, so the caller's memory -- not a
+ * device copy of it -- stays the single source of truth, exactly as in the
+ * reference.
+ */
+#include <cuda_runtime.h>
+
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "rtj_common.h"
+
+extern "C" const rtj_host_table *rtjgpu_host_table(const rtjgpu_ctx *ctx, int table);
+extern "C" int rtjgpu_get_entries(rtjgpu_ctx *ctx, uint32_t *entries, size_t n);
+
+namespace {
+
+struct Instance {
+    rtjgpu_ctx  *ctx = nullptr;
+    rtjgpu_state st = {0, 0, RTJGPU_TABLE_ZERO, 0};
+    int          format = RTJ_YUV420;
+    int          key = 0, lm = 0, cm = 0;
+    int          err = 0;
+    /* one-frame staging */
+    uint8_t           *h_pkt = nullptr;  size_t h_pkt_cap = 0;    /* pinned */
+    uint8_t           *h_frame = nullptr; size_t h_frame_cap = 0; /* pinned */
+    rtjgpu_frame_desc *h_desc = nullptr;                          /* pinned */
+    uint8_t           *d_pkt = nullptr;  size_t d_pkt_cap = 0;
+    uint8_t           *d_frame = nullptr; size_t d_frame_cap = 0;
+    rtjgpu_frame_desc *d_desc = nullptr;
+    cudaStream_t       stream = nullptr;
+    std::vector<uint32_t> entries;
+};
+
+int fail(Instance *in, int code) { in->err = code; return code; }
+
+int ensure(Instance *in, size_t pkt_bytes, size_t frame_bytes)
+{
+    if (pkt_bytes > in->h_pkt_cap) {
+        if (in->h_pkt) cudaFreeHost(in->h_pkt);
+        if (in->d_pkt) cudaFree(in->d_pkt);
+        in->h_pkt = nullptr; in->d_pkt = nullptr; in->h_pkt_cap = in->d_pkt_cap = 0;
+        const size_t cap = pkt_bytes + pkt_bytes / 2;
+        if (cudaMallocHost(&in->h_pkt, cap) != cudaSuccess) return RTJGPU_E_CUDA;
+        if (cudaMalloc(&in->d_pkt, cap) != cudaSuccess) return RTJGPU_E_CUDA;
+        in->h_pkt_cap = in->d_pkt_cap = cap;
+    }
+    if (frame_bytes > in->h_frame_cap) {
+        if (in->h_frame) cudaFreeHost(in->h_frame);
+        if (in->d_frame) cudaFree(in->d_frame);
+        in->h_frame = nullptr; in->d_frame = nullptr; in->h_frame_cap = in->d_frame_cap = 0;
+        if (cudaMallocHost(&in->h_frame, frame_bytes) != cudaSuccess) return RTJGPU_E_CUDA;
+        if (cudaMalloc(&in->d_frame, frame_bytes) != cudaSuccess) return RTJGPU_E_CUDA;
+        in->h_frame_cap = in->d_frame_cap = frame_bytes;
+    }
+    return RTJGPU_OK;
+}
+
+void copy_block(uint8_t *dst, const uint8_t *src, int pitch)
+{
+    for (int r = 0; r < 8; r++) memcpy(dst + (size_t)r * pitch, src + (size_t)r * pitch, 8);
+}
+
+} // namespace
+
+extern "C" {
+
+RTjpeg_t *RTjpeg_init(void)
+{
+    Instance *in = new (std::nothrow) Instance();
+    if (!in) return nullptr;
+    int dev = 0;
+    if (const char *e = getenv("RTJPEG_B200_DEVICE")) dev = atoi(e);
+    if (rtjgpu_create(dev, &in->ctx) != RTJGPU_OK) { delete in; return nullptr; }
+    bool ok = cudaStreamCreateWithFlags(&in->stream, cudaStreamNonBlocking) == cudaSuccess
+           && cudaMallocHost(&in->h_desc, sizeof(rtjgpu_frame_desc)) == cudaSuccess
+           && cudaMalloc(&in->d_desc, sizeof(rtjgpu_frame_desc)) == cudaSuccess;
+    if (!ok) { RTjpeg_close(in); return nullptr; }
+    return in;
+}
+
+void RTjpeg_close(RTjpeg_t *rtj)
+{
+    Instance *in = static_cast<Instance *>(rtj);
+    if (!in) return;
+    if (in->stream) { cudaStreamSynchronize(in->stream); cudaStreamDestroy(in->stream); }
+    if (in->h_pkt) cudaFreeHost(in->h_pkt);
+    if (in->h_frame) cudaFreeHost(in->h_frame);
+    if (in->h_desc) cudaFreeHost(in->h_desc);
+    if (in->d_pkt) cudaFree(in->d_pkt);
+    if (in->d_frame) cudaFree(in->d_frame);
+    if (in->d_desc) cudaFree(in->d_desc);
+    rtjgpu_destroy(in->ctx);
+    delete in;
+}
+
+int RTjpeg_set_quality(RTjpeg_t *rtj, int *quality)
+{
+    Instance *in = static_cast<Instance *>(rtj);
+    if (*quality < 1) *quality = 1;
+    if (*quality > 255) *quality = 255;
+    in->st.quality = *quality;
+    in->st.table = *quality;
+    return 0;
+}
+
+int RTjpeg_set_format(RTjpeg_t *rtj, int *format)
+{
+    static_cast<Instance *>(rtj)->format = *format;
+    return 0;
+}
+
+int RTjpeg_set_size(RTjpeg_t *rtj, int *w, int *h)
+{
+    Instance *in = static_cast<Instance *>(rtj);
+    if (*w < 0 || *w > 65535) return -1;
+    if (*h < 0 || *h > 65535) return -1;
+    in->st.width = *w;
+    in->st.height = *h;
+    return 0;
+}
+
+int RTjpeg_set_intra(RTjpeg_t *rtj, int *key, int *lm, int *cm)
+{
+    Instance *in = static_cast<Instance *>(rtj);
+    if (*key < 0) *key = 0;
+    if (*key > 255) *key = 255;
+    if (*lm < 0) *lm = 0;
+    if (*lm > 16) *lm = 16;
+    if (*cm < 0) *cm = 0;
+    if (*cm > 16) *cm = 16;
+    in->key = *key; in->lm = *lm; in->cm = *cm;
+    return 0;
+}
+
+void RTjpeg_get_tables(RTjpeg_t *rtj, uint32_t *tables)
+{
+    Instance *in = static_cast<Instance *>(rtj);
+    const rtj_host_table *t = rtjgpu_host_table(in->ctx, in->st.table);
+    for (int i = 0; i < 64; i++) {
+        tables[i] = (uint32_t)t->liqt[i];
+        tables[64 + i] = (uint32_t)t->ciqt[i];
+    }
+}
+
+void RTjpeg_set_tables(RTjpeg_t *rtj, uint32_t *tables)
+{
+    Instance *in = static_cast<Instance *>(rtj);
+    if (in->stream) cudaStreamSynchronize(in->stream);
+    if (rtjgpu_set_custom_tables(in->ctx, tables) != RTJGPU_OK) { in->err = RTJGPU_E_CUDA; return; }
+    in->st.table = RTJGPU_TABLE_CUSTOM;      /* quality (rtj->Q) is left alone, lib/RTjpeg.c:2380-2395 */
+}
+
+int RTjpeg_b200_last_error(RTjpeg_t *rtj)
+{
+    Instance *in = static_cast<Instance *>(rtj);
+    const int e = in->err;
+    in->err = 0;
+    return e;
+}
+
+int RTjpeg_b200_decompress_n(RTjpeg_t *rtj, const uint8_t *sp, size_t len, uint8_t **planes)
+{
+    Instance *in = static_cast<Instance *>(rtj);
+    if (!in || !sp || !planes) return RTJGPU_E_ARG;
+    if (in->format != RTJ_YUV420) return fail(in, RTJGPU_E_FORMAT);
+    if (len < RTJPEG_B200_HEADER_BYTES) return fail(in, RTJGPU_E_HEADER);
+
+    rtjgpu_state st = in->st;
+    const uint64_t offs[2] = {0, (uint64_t)len};
+    rtjgpu_frame_desc desc;
+    int rc = rtjgpu_plan(sp, offs, 1, &st, &desc);     /* sp may be unaligned: offset 0 is what is planned */
+    if (rc) return fail(in, rc);
+    const int w = st.width, h = st.height;
+    const size_t fsz = (size_t)w * h * 3 / 2;
+    const int nblk = (w >> 4) * (h >> 4) * 6;
+    const size_t plen = desc.length;
+
+    if ((rc = ensure(in, plen + RTJGPU_STREAM_SLACK_BYTES, fsz))) return fail(in, rc);
+    memcpy(in->h_pkt, sp, plen);
+    memset(in->h_pkt + plen, 0x7F, RTJGPU_STREAM_SLACK_BYTES);
+    *in->h_desc = desc;
+    cudaStream_t s = in->stream;
+    if (cudaMemcpyAsync(in->d_pkt, in->h_pkt, plen + RTJGPU_STREAM_SLACK_BYTES, cudaMemcpyHostToDevice, s) != cudaSuccess
+        || cudaMemcpyAsync(in->d_desc, in->h_desc, sizeof(desc), cudaMemcpyHostToDevice, s) != cudaSuccess)
+        return fail(in, RTJGPU_E_CUDA);
+    if ((rc = rtjgpu_decode_device(in->ctx, in->d_pkt, in->d_desc, 1, w, h, in->d_frame, nullptr, s)))
+        return fail(in, rc);
+    if (cudaMemcpyAsync(in->h_frame, in->d_frame, fsz, cudaMemcpyDeviceToHost, s) != cudaSuccess
+        || cudaStreamSynchronize(s) != cudaSuccess)
+        return fail(in, RTJGPU_E_CUDA);
+
+    rtjgpu_batch_info bi;
+    if ((rc = rtjgpu_get_batch_info(in->ctx, &bi))) return fail(in, rc);
+    in->st = st;        /* the reference reconfigures before it decodes, so state advances even on a bad stream */
+
+    const size_t ysz = (size_t)w * h, csz = ysz / 4;
+    if (bi.skipped_blocks == 0) {
+        memcpy(planes[0], in->h_frame, ysz);
+        memcpy(planes[1], in->h_frame + ysz, csz);
+        memcpy(planes[2], in->h_frame + ysz + csz, csz);
+    } else {
+        /* copy back only what this frame coded; skipped blocks keep the caller's pixels */
+        in->entries.resize((size_t)nblk);
+        if ((rc = rtjgpu_get_entries(in->ctx, in->entries.data(), (size_t)nblk))) return fail(in, rc);
+        const int mbw = w >> 4, cw = w >> 1;
+        for (int b = 0; b < nblk; b++) {
+            if ((in->entries[(size_t)b] >> RTJ_ENT_OFF_BITS) == 0) continue;
+            const int mb = b / 6, sub = b - mb * 6;
+            const int my = mb / mbw, mx = mb - my * mbw;
+            if (sub < 4) {
+                const size_t o = (size_t)(my * 16 + (sub >> 1) * 8) * w + mx * 16 + (sub & 1) * 8;
+                copy_block(planes[0] + o, in->h_frame + o, w);
+            } else {
+                const size_t o = (size_t)(my * 8) * cw + mx * 8;
+                copy_block(planes[sub - 3] + o, in->h_frame + ysz + (sub == 5 ? csz : 0) + o, cw);
+            }
+        }
+    }
+    if (bi.bad_frames) return fail(in, RTJGPU_E_OVERRUN);
+    return RTJGPU_OK;
+}
+
+void RTjpeg_decompress(RTjpeg_t *rtj, uint8_t *sp, uint8_t **planes)
+{
+    /* the reference trusts the packet (lib/RTjpeg.c:3565-3586 reads no length);
+     * the header's framesize field is the only length available here */
+    uint32_t framesize = (uint32_t)sp[0] | (uint32_t)sp[1] << 8 | (uint32_t)sp[2] << 16 | (uint32_t)sp[3] << 24;
+    if (framesize < RTJPEG_B200_HEADER_BYTES) {
+        static_cast<Instance *>(rtj)->err = RTJGPU_E_HEADER;
+        return;
+    }
+    RTjpeg_b200_decompress_n(rtj, sp, framesize, planes);
+}
+
+} // extern "C"

@@ -1,0 +1,235 @@
+/*
+ * rtjpeg_b200.h -- C ABI of the B200-native RTjpeg YUV420 decoder.
+ *
+ * Two levels, both plain C (pointers and sizes only, no CUDA or torch types):
+ *
+ *   Level 1  the reference's own codec API, same names, same argument meaning,
+ *            so that librtjpeg_b200.so can stand in for lib/RTjpeg.o when
+ *            libgmerlin_avdec is linked.  Every prototype cites the reference
+ *            declaration it replaces (paths relative to the gmerlin-avdecoder
+ *            tree).
+ *   Level 2  a batch interface (many packets -> many frames in one call), which
+ *            is what keeps a B200 busy; Level 1 is its one-frame special case.
+ *
+ * Scope: the YUV420 decode path only (format 0).  The encoder half of
+ * lib/RTjpeg.c, the YUV422 / 8-bit formats and the colour converters are not
+ * part of this library.
+ */
+#ifndef RTJPEG_B200_H
+#define RTJPEG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------ */
+/* Level 1: drop-in for include/RTjpeg.h                                     */
+/* ------------------------------------------------------------------------ */
+
+/* Opaque, as in include/RTjpeg.h:96 (`typedef void RTjpeg_t;`). */
+typedef void RTjpeg_t;
+
+/* Picture formats, include/RTjpeg.h:111-113.  Only RTJ_YUV420 decodes here. */
+#define RTJ_YUV420 0
+#define RTJ_YUV422 1
+#define RTJ_RGB8   2
+
+/* Fixed packet header length, include/RTjpeg.h:139 (RTJPEG_HEADER_SIZE). */
+#define RTJPEG_B200_HEADER_BYTES 12
+
+/* include/RTjpeg.h:115, lib/RTjpeg.c:2495.  New instance: no size, quality 0,
+ * format YUV420.  Binds to the CUDA device named by $RTJPEG_B200_DEVICE
+ * (default 0).  Returns NULL when no CUDA device can be used -- there is no
+ * CPU fallback. */
+RTjpeg_t *RTjpeg_init(void);
+
+/* include/RTjpeg.h:116, lib/RTjpeg.c:2504. */
+void RTjpeg_close(RTjpeg_t *rtj);
+
+/* include/RTjpeg.h:117, lib/RTjpeg.c:2408.  Clamps *quality to 1..255 in
+ * place, derives both dequantisation tables, returns 0. */
+int RTjpeg_set_quality(RTjpeg_t *rtj, int *quality);
+
+/* include/RTjpeg.h:118, lib/RTjpeg.c:2421.  Stores the format, returns 0.
+ * RTjpeg_decompress refuses (error RTJGPU_E_FORMAT) anything but RTJ_YUV420. */
+int RTjpeg_set_format(RTjpeg_t *rtj, int *format);
+
+/* include/RTjpeg.h:119, lib/RTjpeg.c:2427.  Returns -1 when a dimension is
+ * outside 0..65535, else 0. */
+int RTjpeg_set_size(RTjpeg_t *rtj, int *w, int *h);
+
+/* include/RTjpeg.h:120, lib/RTjpeg.c:2455.  Encoder-side knob; accepted and
+ * clamped (key 0..255, masks 0..16) for source compatibility, no effect on
+ * decoding. */
+int RTjpeg_set_intra(RTjpeg_t *rtj, int *key, int *lm, int *cm);
+
+/* include/RTjpeg.h:137, lib/RTjpeg.c:2371.  Writes the 128 AAN-scaled table
+ * entries currently in force (luma 0..63, chroma 64..127). */
+void RTjpeg_get_tables(RTjpeg_t *rtj, uint32_t *tables);
+
+/* include/RTjpeg.h:138, lib/RTjpeg.c:2380.  Loads 128 raw (not AAN-scaled)
+ * table entries; they stay in force until a packet whose quality byte differs
+ * from the instance's current quality arrives (lib/RTjpeg.c:3575). */
+void RTjpeg_set_tables(RTjpeg_t *rtj, uint32_t *tables);
+
+/* include/RTjpeg.h:126, lib/RTjpeg.c:3565.  One packet (12-byte header +
+ * payload) into planes[0..2] = Y, U, V, tight pitch (width, width/2, width/2).
+ * Blocks the stream marks as skipped are left untouched in the caller's
+ * planes, exactly like the reference.  Like the reference it returns nothing
+ * and trusts the header's framesize; errors are reported out of band through
+ * RTjpeg_b200_last_error(). */
+void RTjpeg_decompress(RTjpeg_t *rtj, uint8_t *sp, uint8_t **planes);
+
+/* Same as RTjpeg_decompress but with the packet length known to the caller
+ * (gavl_packet_t.buf.len in lib/video_rtjpeg.c:81), so a truncated packet is
+ * refused instead of read past.  Returns 0 or a negative RTJGPU_E_* code. */
+int RTjpeg_b200_decompress_n(RTjpeg_t *rtj, const uint8_t *sp, size_t len, uint8_t **planes);
+
+/* Sticky error of the instance (0 = none); cleared by the call. */
+int RTjpeg_b200_last_error(RTjpeg_t *rtj);
+
+/* ------------------------------------------------------------------------ */
+/* Level 2: batch decode                                                     */
+/* ------------------------------------------------------------------------ */
+
+enum {
+    RTJGPU_OK          =  0,
+    RTJGPU_E_CUDA      = -1,   /* a CUDA call failed; see rtjgpu_last_cuda_error */
+    RTJGPU_E_ARG       = -2,   /* bad argument */
+    RTJGPU_E_HEADER    = -3,   /* packet shorter than its header / framesize */
+    RTJGPU_E_SIZE      = -4,   /* width/height zero, not a multiple of 16, or changing inside a batch */
+    RTJGPU_E_FORMAT    = -5,   /* not YUV420 */
+    RTJGPU_E_OVERRUN   = -6,   /* a frame's block stream runs past its packet */
+    RTJGPU_E_TOOBIG    = -7,   /* batch exceeds the limits below */
+    RTJGPU_E_NOMEM     = -8
+};
+
+#define RTJGPU_MAX_FRAMES_PER_BATCH 65534      /* source-frame indices are 16 bit */
+#define RTJGPU_MAX_PAYLOAD_BYTES    (1u << 25) /* per frame; block offsets are 25 bit */
+#define RTJGPU_STREAM_SLACK_BYTES   128        /* readable bytes required after the last packet of a device stream */
+
+/* Which table set a frame uses: 0 = all-zero tables of a never-configured
+ * instance (lib/RTjpeg.c:2495-2502), 1..255 = quality, 256 = the custom set
+ * loaded with rtjgpu_set_custom_tables. */
+#define RTJGPU_TABLE_ZERO   0
+#define RTJGPU_TABLE_CUSTOM 256
+
+/* One frame of a batch, as the kernels see it (16 bytes, device-resident). */
+typedef struct rtjgpu_frame_desc {
+    uint64_t offset;   /* of the packet header inside the stream buffer; multiple of 4 */
+    uint32_t length;   /* packet bytes available (header + payload) */
+    uint16_t table;    /* RTJGPU_TABLE_* / quality */
+    uint16_t flags;    /* reserved, 0 */
+} rtjgpu_frame_desc;
+
+typedef struct rtjgpu_ctx rtjgpu_ctx;
+
+/* Decoder state that crosses batch boundaries (lib/RTjpeg.c:3565-3579 keeps
+ * the same three values in RTjpeg_t). */
+typedef struct rtjgpu_state {
+    int width, height;   /* 0,0 = unset */
+    int table;           /* RTJGPU_TABLE_* currently in force */
+    int quality;         /* rtj->Q: 0 on a fresh instance */
+} rtjgpu_state;
+
+/* Per-stage device time of the last rtjgpu_decode_device call, milliseconds
+ * (CUDA events on the launch stream; filled only when timing is enabled). */
+typedef struct rtjgpu_timing {
+    float scan_ms;      /* K1 block-offset scan */
+    float resolve_ms;   /* K3 last-writer resolution (0 when the batch has no skipped block) */
+    float idct_ms;      /* K2 unpack + dequantise + IDCT + store */
+    float total_ms;
+} rtjgpu_timing;
+
+/* Per-batch counters produced on the device, valid after rtjgpu_sync(). */
+typedef struct rtjgpu_batch_info {
+    uint64_t skipped_blocks;    /* 0xFF markers in the batch */
+    uint64_t payload_bytes;     /* bytes the scan consumed, summed over frames */
+    uint32_t bad_frames;        /* frames whose block stream overran the packet */
+    int32_t  first_bad_frame;   /* -1 when none */
+} rtjgpu_batch_info;
+
+int  rtjgpu_create(int device, rtjgpu_ctx **out);
+void rtjgpu_destroy(rtjgpu_ctx *ctx);
+int  rtjgpu_device_count(void);
+const char *rtjgpu_strerror(int code);
+/* cudaError_t of the last failing CUDA call on this context, as int. */
+int  rtjgpu_last_cuda_error(const rtjgpu_ctx *ctx);
+
+/* Raw (pre-AAN) tables for RTJGPU_TABLE_CUSTOM, the set_tables path. */
+int  rtjgpu_set_custom_tables(rtjgpu_ctx *ctx, const uint32_t raw[128]);
+
+/* Host-side planning: parse the headers of F packets laid out in one buffer
+ * (packet f starts at offsets[f]; offsets[F] is the end of the buffer),
+ * apply the lazy reconfiguration rules of RTjpeg_decompress
+ * (lib/RTjpeg.c:3568-3579) starting from *state, and fill desc[F].  All frames
+ * of a batch must share one size (split the batch where it changes).  *state
+ * is advanced past the batch on success. */
+int  rtjgpu_plan(const uint8_t *stream, const uint64_t *offsets, int F,
+                 rtjgpu_state *state, rtjgpu_frame_desc *desc);
+
+/* Device-resident decode: stream, descriptors, output and carry all live in
+ * device memory.  d_out receives F tight YUV420 frames (w*h*3/2 bytes each,
+ * Y then U then V).  d_carry (w*h*3/2 bytes, may be NULL = zero-filled planes)
+ * is the picture before the first frame: skipped blocks that no frame of the
+ * batch has written yet are taken from it (lib/video_rtjpeg.c:81 decodes into
+ * one persistent frame).  cuda_stream is a cudaStream_t passed as void*
+ * (NULL = the legacy default stream).  Asynchronous: returns after the launches. */
+int  rtjgpu_decode_device(rtjgpu_ctx *ctx, const uint8_t *d_stream,
+                          const rtjgpu_frame_desc *d_desc, int F, int w, int h,
+                          uint8_t *d_out, const uint8_t *d_carry, void *cuda_stream);
+
+/* Host-buffer decode: packets in host memory in, frames in host memory out.
+ * The batch is cut into chunks that move through pinned staging buffers with
+ * cudaMemcpyAsync on several streams so that copies overlap the kernels.
+ * h_carry_inout (may be NULL) supplies the picture before the first frame and
+ * receives the last decoded frame.  Synchronous.  flags: RTJGPU_HOST_* below. */
+#define RTJGPU_HOST_IN_PINNED   1   /* h_stream is page-locked: DMA straight from it */
+#define RTJGPU_HOST_OUT_PINNED  2   /* h_out is page-locked: DMA straight into it */
+int  rtjgpu_decode_host(rtjgpu_ctx *ctx, const uint8_t *h_stream, const uint64_t *offsets, int F,
+                        rtjgpu_state *state, uint8_t *h_out, uint8_t *h_carry_inout, int flags);
+
+/* Wait for everything this context has launched. */
+int  rtjgpu_sync(rtjgpu_ctx *ctx);
+
+void rtjgpu_enable_timing(rtjgpu_ctx *ctx, int on);
+int  rtjgpu_get_timing(rtjgpu_ctx *ctx, rtjgpu_timing *out);      /* last timed batch; waits for it */
+/* Stage times of the timed device batch issued `calls_ago` calls before the last
+ * one (0 = the last); the context keeps the most recent 256.  Reading after a
+ * run of batches costs no synchronisation inside the run. */
+int  rtjgpu_get_timing_at(rtjgpu_ctx *ctx, int calls_ago, rtjgpu_timing *out);
+int  rtjgpu_get_batch_info(rtjgpu_ctx *ctx, rtjgpu_batch_info *out); /* syncs */
+
+/* Per-frame skipped-block counts of the last device batch (F entries, host
+ * array); a frame with count 0 is a "clean" frame, the only safe place to cut
+ * an inter-coded stream into independent segments. */
+int  rtjgpu_get_skip_counts(rtjgpu_ctx *ctx, uint32_t *counts, int F);
+
+/* Number of kernels this library has launched on the context so far. */
+uint64_t rtjgpu_launch_count(const rtjgpu_ctx *ctx);
+
+/* Host-side multi-GPU split: cut F frames into n contiguous shards of roughly
+ * equal frame count such that every shard starts on a clean frame
+ * (clean[f] != 0).  first[n+1] receives the shard starts (first[n] = F).  A
+ * shard may come out empty when there are not enough clean frames.  Pure host
+ * arithmetic, no CUDA. */
+int  rtjgpu_split_shards(const uint8_t *clean, int F, int n, int *first);
+
+/* Host-only table derivation, no CUDA involved (what the context uploads at
+ * creation): the 128 AAN-scaled entries RTjpeg_get_tables would return after
+ * RTjpeg_set_quality(Q) (lib/RTjpeg.c:2344-2369, :1208-1217), respectively after
+ * RTjpeg_set_tables(raw) (:2380-2395), plus the raw-prefix lengths lb8 / cb8. */
+void rtjgpu_tables_for_quality(int Q, uint32_t scaled[128], int *lb8, int *cb8);
+void rtjgpu_tables_from_raw(const uint32_t raw[128], uint32_t scaled[128], int *lb8, int *cb8);
+
+/* Pinned host memory helpers for callers that stage packets themselves. */
+void *rtjgpu_host_alloc(size_t bytes);
+void  rtjgpu_host_free(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RTJPEG_B200_H */

@@ -1,0 +1,201 @@
+"""The two drop-in boundaries on the GPU: the RTjpeg.h-compatible codec API and the
+bgav 'RTJ0' video-decoder plugin (driven through a stub host, tests/bgav_host_stub.c)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import gmerlin_avdecoder_b200 as g
+from gmerlin_avdecoder_b200 import capi
+from oracle import oracle as O
+from streams import clip, golden, reference_frames
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _packets(s, o):
+    sz = O.packet_sizes(s, o)
+    return [s[int(o[f]):int(o[f]) + int(sz[f])] for f in range(len(o) - 1)]
+
+
+def test_rtjpeg_decompress_sequence_with_persistent_planes():
+    gd = golden("inter_64x48_q200_gop6")
+    w, h = 64, 48
+    planes = np.full(w * h * 3 // 2, 0x55, dtype=np.uint8)
+    r = g.RTjpeg()
+    for f, pkt in enumerate(_packets(gd["stream"], gd["offsets"])):
+        r.decompress(pkt, planes)
+        assert r.last_error() == 0
+        assert np.array_equal(planes, gd["frames"][f]), f
+    r.close()
+
+
+def test_rtjpeg_skipped_blocks_keep_the_callers_pixels():
+    """The reference leaves skipped blocks untouched in the CALLER's memory: scribbling on the
+    planes between calls must show through exactly where the stream skips."""
+    s, o = clip(160, 96, 128, 12, key_rate=11, lm=3, cm=3, noise_y=3)
+    w, h = 160, 96
+    rng = np.random.default_rng(1)
+    mine = np.zeros(w * h * 3 // 2, dtype=np.uint8)
+    ref = mine.copy()
+    r, od = g.RTjpeg(), O.OracleDecoder()
+    for f, pkt in enumerate(_packets(s, o)):
+        if f % 3 == 1:
+            at = rng.integers(0, mine.size, 500)
+            mine[at] = ref[at] = 0xEE
+        r.decompress(pkt, mine)
+        od.decode(pkt, ref)
+        assert np.array_equal(mine, ref), f
+    r.close()
+
+
+def test_rtjpeg_set_tables_path():
+    gt = golden("set_tables")
+    w, h = int(gt["w"]), int(gt["h"])
+    for i in range(3):
+        r = g.RTjpeg()
+        assert r.set_size(w, h) == 0
+        r.set_tables(gt[f"raw{i}"])
+        planes = np.full(w * h * 3 // 2, int(gt["init_fill"]), dtype=np.uint8)
+        r.decompress(gt[f"pkt{i}"], planes)
+        assert r.last_error() == 0
+        assert np.array_equal(planes, gt[f"planes{i}"]), i
+        want = np.concatenate([O.tables_from_raw(gt[f"raw{i}"]).liqt, O.tables_from_raw(gt[f"raw{i}"]).ciqt])
+        assert np.array_equal(r.get_tables(), want.astype(np.uint32))
+        r.close()
+
+
+def test_rtjpeg_setters_and_errors():
+    r = g.RTjpeg()
+    assert (r.get_tables() == 0).all()                       # fresh instance: zero tables
+    assert r.set_quality(0) == 1 and r.set_quality(999) == 255 and r.set_quality(128) == 128
+    assert np.array_equal(r.get_tables(), golden("tables")["tables"][127])
+    assert r.set_size(-1, 16) == -1 and r.set_size(16, 65536) == -1 and r.set_size(65535, 0) == 0
+    assert r.set_intra(300, -2, 99) == (255, 0, 16)
+    gd = golden("intra_64x48_q128")
+    pkt = _packets(gd["stream"], gd["offsets"])[0]
+    planes = np.zeros(64 * 48 * 3 // 2, dtype=np.uint8)
+    assert r.decompress_n(pkt[:8], planes) == capi.E_HEADER
+    assert r.decompress_n(pkt[:pkt.size // 2], planes) == capi.E_OVERRUN
+    assert r.last_error() == capi.E_OVERRUN and r.last_error() == 0
+    r.set_format(1)
+    assert r.decompress_n(pkt, planes) == capi.E_FORMAT
+    r.set_format(0)
+    assert r.decompress_n(pkt, planes) == 0
+    assert np.array_equal(planes, gd["frames"][0])
+    bad = pkt.copy()
+    bad[6] = 70
+    assert r.decompress_n(bad, planes) == capi.E_SIZE
+    r.close()
+
+
+# --------------------------------------------------------------------------
+# plugin
+# --------------------------------------------------------------------------
+
+@pytest.fixture(scope="module")
+def host():
+    build = os.path.join(HERE, "_build")
+    os.makedirs(build, exist_ok=True)
+    so = os.path.join(build, "libbgav_host_stub.so")
+    subprocess.check_call(["gcc", "-O1", "-fPIC", "-shared", "-Wall", "-Wno-unused-parameter",
+                           "-o", so, os.path.join(HERE, "bgav_host_stub.c")])
+    H = C.CDLL(so, mode=C.RTLD_GLOBAL)                       # the plugin resolves bgav_*/gavl_* against it
+    P = C.CDLL(g.PLUGIN_PATH, mode=C.RTLD_GLOBAL)
+    vp = C.c_void_p
+    H.stub_find_decoder.restype = vp
+    H.stub_find_decoder.argtypes = [C.c_uint32]
+    H.stub_decoder_name.restype = C.c_char_p
+    H.stub_decoder_name.argtypes = [vp]
+    H.stub_stream_create.restype = vp
+    H.stub_stream_create.argtypes = [C.c_int, C.c_int]
+    H.stub_stream_set_packets.argtypes = [vp, vp, vp, vp, C.c_int]
+    H.stub_init.argtypes = [vp, vp]
+    H.stub_close.argtypes = [vp, vp]
+    H.stub_decode.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.POINTER(C.c_int64)]
+    H.stub_stream_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                   C.POINTER(C.c_int), C.c_char_p, C.c_char_p]
+    H.stub_stream_destroy.argtypes = [vp]
+    P.bgav_init_video_decoders_rtjpeg.restype = None
+    P.bgav_init_video_decoders_rtjpeg()                      # what bgav_codecs_init does, lib/codecs.c:176
+    return H
+
+
+FOURCC_RTJ0 = (ord('R') << 24) | (ord('T') << 16) | (ord('J') << 8) | ord('0')
+
+
+def test_plugin_registers_rtj0(host):
+    assert host.stub_decoder_count() == 1
+    dec = host.stub_find_decoder(FOURCC_RTJ0)
+    assert dec
+    assert host.stub_decoder_name(dec) == b"rtjpeg video decoder"
+    assert not host.stub_find_decoder((ord('N') << 24) | (ord('U') << 16) | (ord('V') << 8) | ord(' '))
+
+
+def test_plugin_decodes_with_strides_and_frame_skips(host):
+    gd = golden("inter_64x48_q200_gop6")
+    s, o = np.ascontiguousarray(gd["stream"]), gd["offsets"]
+    sizes = O.packet_sizes(s, o).astype(np.uint32)
+    F = len(o) - 1
+    iw, ih = 60, 40                                          # image smaller than the padded 64x48 frame
+    dec = host.stub_find_decoder(FOURCC_RTJ0)
+    st = host.stub_stream_create(iw, ih)
+    offs = np.ascontiguousarray(o[:-1], dtype=np.uint64)
+    host.stub_stream_set_packets(st, s.ctypes.data, offs.ctypes.data, sizes.ctypes.data, F)
+    assert host.stub_init(dec, st) == 1
+    fw, fh, pf, done = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+    key, val = C.create_string_buffer(64), C.create_string_buffer(64)
+    host.stub_stream_info(st, fw, fh, pf, done, key, val)
+    assert (fw.value, fh.value) == (64, 48) and key.value == b"Format" and val.value == b"RTjpeg"
+
+    sy, sc = 80, 48                                          # padded strides
+    Y = np.zeros((ih, sy), dtype=np.uint8)
+    U = np.zeros(((ih + 1) // 2, sc), dtype=np.uint8)
+    V = np.zeros_like(U)
+    # the plugin's persistent picture starts zeroed; frames 3 and 7 are dropped undecoded
+    dropped = {3, 7}
+    od = O.OracleDecoder()
+    ref = np.zeros(64 * 48 * 3 // 2, dtype=np.uint8)
+    pts = C.c_int64()
+    for f in range(F):
+        pkt = s[int(o[f]):int(o[f]) + int(sizes[f])]
+        if f in dropped:
+            assert host.stub_decode(dec, st, None, None, None, 0, 0, None) == 1
+            continue
+        assert host.stub_decode(dec, st, Y.ctypes.data, U.ctypes.data, V.ctypes.data, sy, sc, C.byref(pts)) == 1
+        od.decode(pkt, ref)
+        assert pts.value == 1000 + 40 * f
+        ry = ref[:64 * 48].reshape(48, 64)
+        ru = ref[64 * 48:64 * 48 * 5 // 4].reshape(24, 32)
+        rv = ref[64 * 48 * 5 // 4:].reshape(24, 32)
+        assert np.array_equal(Y[:, :iw], ry[:ih, :iw]), f
+        assert np.array_equal(U[:, :iw // 2], ru[:ih // 2, :iw // 2]), f
+        assert np.array_equal(V[:, :iw // 2], rv[:ih // 2, :iw // 2]), f
+        assert (Y[:, iw:] == 0).all()                        # nothing written outside the image
+    assert host.stub_decode(dec, st, Y.ctypes.data, U.ctypes.data, V.ctypes.data, sy, sc, None) == 0   # EOF propagates
+    host.stub_stream_info(st, fw, fh, pf, done, key, val)
+    assert done.value == F                                   # every packet handed back exactly once
+    host.stub_close(dec, st)
+    host.stub_stream_destroy(st)
+
+
+def test_plugin_ends_stream_on_malformed_packet(host):
+    gd = golden("intra_64x48_q128")
+    s, o = np.ascontiguousarray(gd["stream"]), gd["offsets"]
+    sizes = O.packet_sizes(s, o).astype(np.uint32)
+    sizes[1] = sizes[1] // 2                                 # second packet arrives truncated
+    dec = host.stub_find_decoder(FOURCC_RTJ0)
+    st = host.stub_stream_create(64, 48)
+    offs = np.ascontiguousarray(o[:-1], dtype=np.uint64)
+    host.stub_stream_set_packets(st, s.ctypes.data, offs.ctypes.data, sizes.ctypes.data, 3)
+    assert host.stub_init(dec, st) == 1
+    Y = np.zeros((48, 64), dtype=np.uint8); U = np.zeros((24, 32), dtype=np.uint8); V = np.zeros_like(U)
+    assert host.stub_decode(dec, st, Y.ctypes.data, U.ctypes.data, V.ctypes.data, 64, 32, None) == 1
+    assert np.array_equal(Y.ravel(), gd["frames"][0][:64 * 48])
+    assert host.stub_decode(dec, st, Y.ctypes.data, U.ctypes.data, V.ctypes.data, 64, 32, None) == 0
+    host.stub_close(dec, st)
+    host.stub_stream_destroy(st)

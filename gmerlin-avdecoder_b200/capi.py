@@ -298,7 +298,9 @@ class RTjpeg:
         self._L.RTjpeg_set_tables(self._h, raw.ctypes.data_as(_u32p))
 
     def _planes(self, planes: np.ndarray, w: int, h: int):
-        assert planes.dtype == np.uint8 and planes.flags.c_contiguous and planes.size >= w * h * 3 // 2
+        assert planes.dtype == np.uint8 and planes.flags.c_contiguous
+        if planes.size < w * h * 3 // 2:      # header lies about the geometry: the library refuses it before any plane access
+            w = h = 0
         base = planes.ctypes.data
         arr = (_u8p * 3)(C.cast(base, _u8p), C.cast(base + w * h, _u8p), C.cast(base + w * h * 5 // 4, _u8p))
         return arr

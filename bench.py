@@ -272,7 +272,7 @@ def main():
     if rank == 0:
         peak, peak_src = measured_hbm_peak()
         dom = max(stage_ms, key=stage_ms.get)
-        kname = {"scan": "rtj_scan_kernel", "resolve": "rtj_resolve_kernel", "idct": "rtj_idct_kernel"}[dom]
+        kname = {"scan": "rtj_scan_lane_kernel" if F >= 512 else "rtj_scan_warp_kernel", "resolve": "rtj_resolve_kernel", "idct": "rtj_idct_kernel"}[dom]
         achieved = algo_bytes / (stage_ms[dom] * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world,

@@ -42,6 +42,7 @@ E_CUDA, E_ARG, E_HEADER, E_SIZE, E_FORMAT, E_OVERRUN, E_TOOBIG, E_NOMEM = -1, -2
 HOST_IN_PINNED, HOST_OUT_PINNED = 1, 2
 STREAM_SLACK_BYTES = 128
 TABLE_ZERO, TABLE_CUSTOM = 0, 256
+SCAN_AUTO, SCAN_LANE, SCAN_WARP = 0, 1, 2
 
 _u8p = C.POINTER(C.c_uint8)
 _u32p = C.POINTER(C.c_uint32)
@@ -100,6 +101,7 @@ def load_library() -> C.CDLL:
     L.rtjgpu_strerror.restype = C.c_char_p
     L.rtjgpu_last_cuda_error.argtypes = [vp]
     L.rtjgpu_set_custom_tables.argtypes = [vp, _u32p]
+    L.rtjgpu_set_scan_mode.argtypes = [vp, C.c_int]
     L.rtjgpu_plan.argtypes = [_u8p, _u64p, C.c_int, C.POINTER(State), vp]
     L.rtjgpu_decode_device.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp]
     L.rtjgpu_decode_host.argtypes = [vp, _u8p, _u64p, C.c_int, C.POINTER(State), _u8p, _u8p, C.c_int]
@@ -197,6 +199,10 @@ class BatchContext:
 
     def __exit__(self, *exc):
         self.close()
+
+    def set_scan_mode(self, mode: int) -> None:
+        """0 = auto, 1 = one thread per frame, 2 = one warp per frame."""
+        _check(self._L.rtjgpu_set_scan_mode(self._h, mode), "rtjgpu_set_scan_mode")
 
     def set_custom_tables(self, raw: np.ndarray) -> None:
         raw = np.ascontiguousarray(raw, dtype=np.uint32)

@@ -69,6 +69,7 @@ struct rtjgpu_ctx {
     bool           slots_ready = false;
     uint8_t       *d_host_carry = nullptr;    /* carry plane of the host pipeline */
     size_t         d_host_carry_cap = 0;
+    int            scan_mode = RTJGPU_SCAN_AUTO;
     uint64_t       host_bad = 0;              /* overrun frames seen by the current rtjgpu_decode_host call */
 };
 
@@ -122,6 +123,7 @@ int run_kernels(rtjgpu_ctx *ctx, Workspace *ws, const uint8_t *d_stream, const r
     a.F = F; a.w = w; a.h = h;
     a.d_ent = ws->d_ent; a.d_src = ws->d_src; a.d_frame_skips = ws->d_frame_skips; a.d_info = ws->d_info;
     a.d_out = d_out; a.d_carry = d_carry;
+    a.scan_mode = ctx->scan_mode;
 
     CK(ctx, cudaMemcpyAsync(ws->d_info, ctx->h_info_reset, sizeof(rtj_dev_info), cudaMemcpyHostToDevice, st));
     if (ev) CK(ctx, cudaEventRecord(ev[0], st));
@@ -258,6 +260,13 @@ void rtjgpu_destroy(rtjgpu_ctx *ctx)
 int rtjgpu_last_cuda_error(const rtjgpu_ctx *ctx) { return ctx ? ctx->last_cuda : 0; }
 uint64_t rtjgpu_launch_count(const rtjgpu_ctx *ctx) { return ctx ? ctx->launches : 0; }
 void rtjgpu_enable_timing(rtjgpu_ctx *ctx, int on) { if (ctx) ctx->timing = on != 0; }
+
+int rtjgpu_set_scan_mode(rtjgpu_ctx *ctx, int mode)
+{
+    if (!ctx || mode < RTJGPU_SCAN_AUTO || mode > RTJGPU_SCAN_WARP) return RTJGPU_E_ARG;
+    ctx->scan_mode = mode;
+    return RTJGPU_OK;
+}
 
 int rtjgpu_set_custom_tables(rtjgpu_ctx *ctx, const uint32_t raw[128])
 {

@@ -68,6 +68,7 @@ typedef struct rtj_launch_args {
     rtj_dev_info            *d_info;
     uint8_t                 *d_out;
     const uint8_t           *d_carry;
+    int                      scan_mode;     /* RTJGPU_SCAN_* */
 } rtj_launch_args;
 
 int rtj_launch_scan(const rtj_launch_args *a, void *stream);

@@ -42,7 +42,7 @@ constexpr int SCAN_WARPS = 4;
 } // namespace
 
 extern "C" __global__ void __launch_bounds__(SCAN_WARPS * 32)
-rtj_scan_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc *__restrict__ desc,
+rtj_scan_warp_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc *__restrict__ desc,
                 const rtj_dev_table *__restrict__ tables, int F, int nblk,
                 uint32_t *__restrict__ ent, uint32_t *__restrict__ frame_skips,
                 rtj_dev_info *__restrict__ info)
@@ -158,6 +158,151 @@ rtj_scan_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc *__r
     }
 }
 
+
+/* ------------------------------------------------------------------------ */
+/* K1, lane-serial flavour: one THREAD walks one frame                        */
+/* ------------------------------------------------------------------------ */
+/*
+ * The block grammar is a serial state machine (lib/RTjpeg.c:157-186): where a block
+ * ends depends on every token before it.  One lane walks one frame, four tokens
+ * per step with SIMD-within-a-register arithmetic:
+ *
+ *   t                     four token bytes
+ *   r = t & ~(t>>1) & 0x40404040        bit 6 of every byte of the form 01xxxxxx (a run token, 64..127)
+ *   x = t & ((r>>6) * 0x3F)             run length - 1 in run bytes, 0 in coefficient bytes
+ *   P = x * 0x01010101 + 0x04030201     byte k = positions filled by tokens 0..k  (each token fills 1 + x_k)
+ *   c = (P + (128-need) * 0x01010101) & 0x80808080
+ *                                       bit 7 of byte k set  <=>  tokens 0..k fill >= need positions
+ *
+ * so the first set bit of c names the block's last token.  Byte overflows and carries
+ * can only occur at or after that first crossing and never disturb it.  A lane costs
+ * ~1 issue slot per block, so thousands of frames parse at a sliver of the machine;
+ * the price is latency (one dependent chain per frame), which large batches hide.
+ * The warp-cooperative flavour above serves batches with few, large frames.
+ */
+namespace {
+
+__device__ __forceinline__ uint32_t ld_u32_unaligned(const uint32_t *__restrict__ base4, int byte_off)
+{
+    const uint32_t *wp = base4 + (byte_off >> 2);
+    return __funnelshift_r(__ldg(wp), __ldg(wp + 1), (unsigned)(byte_off & 3) * 8);
+}
+
+struct LaneResult { int blk, skips, consumed; };
+
+/* SWAR pieces: see the comment above.  swar_x: run length - 1 in run bytes, 0 elsewhere. */
+__device__ __forceinline__ uint32_t swar_runs(uint32_t t) { return t & ~(t >> 1) & 0x40404040u; }
+__device__ __forceinline__ uint32_t swar_x(uint32_t t, uint32_t r) { return t & ((r >> 6) * 0x3Fu); }
+
+template <bool RAW>
+__device__ __forceinline__ LaneResult lane_scan_frame(const uint8_t *__restrict__ pay, int len, int lb8, int cb8,
+                                                     uint32_t *__restrict__ out, int nblk)
+{
+    const uint32_t *base4 = reinterpret_cast<const uint32_t *>(pay);     /* packets start 4-byte aligned */
+    int o = 0, blk = 0, skips = 0, k6 = 0;
+    /* Lanes of a warp move in lockstep, so one lane missing L1 stalls all 32 (and with 128 sector
+     * look-ups per step somebody always misses).  A real load touches the sector each lane will need
+     * ~40 blocks from now; its value is consumed four steps later, by when even a DRAM miss is back. */
+    uint32_t touch0 = 0, touch1 = 0, touch2 = 0, touch3 = 0, sink = 0;
+    while (blk < nblk && o < len) {
+        const int bt8 = RAW ? (k6 < 4 ? lb8 : cb8) : 0;
+        if (RAW) k6 = k6 == 5 ? 0 : k6 + 1;
+        sink ^= touch3;
+        touch3 = touch2; touch2 = touch1; touch1 = touch0;
+        touch0 = __ldg(base4 + ((o + 160) >> 2));
+
+        /* the block's first byte and its first eight tokens */
+        uint32_t first, t0, t1;
+        {
+            const uint32_t *wp = base4 + (o >> 2);
+            const unsigned sh = (unsigned)(o & 3) * 8;
+            const uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2), w3 = __ldg(wp + 3);
+            const uint32_t u0 = __funnelshift_r(w0, w1, sh), u1 = __funnelshift_r(w1, w2, sh),
+                           u2 = __funnelshift_r(w2, w3, sh);
+            first = u0 & 0xFFu;
+            t0 = __funnelshift_r(u0, u1, 8);          /* bytes o+1 .. o+4 */
+            t1 = __funnelshift_r(u1, u2, 8);          /* bytes o+5 .. o+8 */
+        }
+        int tok = o + 1 + bt8;
+        if (RAW) {
+            const uint32_t *wp = base4 + (tok >> 2);
+            const unsigned sh = (unsigned)(tok & 3) * 8;
+            const uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2);
+            t0 = __funnelshift_r(w0, w1, sh);
+            t1 = __funnelshift_r(w1, w2, sh);
+        }
+        const bool isff = first == 0xFFu;             /* skipped block: one byte, lib/RTjpeg.c:2704 */
+        int need = 63 - bt8;                          /* positions the token tail has to fill */
+
+        /* eight tokens at once, no branches: the common block (<= 9 bytes) resolves here */
+        const uint32_t K = (uint32_t)(128 - need) * 0x01010101u;
+        const uint32_t r0 = swar_runs(t0), r1 = swar_runs(t1);
+        const uint32_t P0 = swar_x(t0, r0) * 0x01010101u + 0x04030201u;
+        const uint32_t P1 = swar_x(t1, r1) * 0x01010101u + 0x04030201u + (P0 >> 24) * 0x01010101u;
+        const uint32_t c0 = (P0 + K) & 0x80808080u, c1 = (P1 + K) & 0x80808080u;
+        uint32_t c = c0 ? c0 : c1, t = c0 ? t0 : t1, r = c0 ? r0 : r1;
+        int ntok = c0 ? 0 : 4;
+        if (!isff && c == 0 && need > 0) {            /* long block: keep going four tokens at a time */
+            need -= (int)(P1 >> 24);
+            ntok = 8;
+            for (;;) {
+                if (tok + ntok >= len + 64) { c = 0x80u; r = 0; break; }       /* runaway on a truncated frame */
+                t = ld_u32_unaligned(base4, tok + ntok);
+                r = swar_runs(t);
+                const uint32_t P = swar_x(t, r) * 0x01010101u + 0x04030201u;
+                c = (P + (uint32_t)(128 - need) * 0x01010101u) & 0x80808080u;
+                if (c) break;
+                need -= (int)(P >> 24);
+                ntok += 4;
+            }
+        }
+        const int bit = __ffs((int)c) - 1;            /* 7, 15, 23 or 31 */
+        ntok += (bit >> 3) + 1;
+        const uint32_t bk = (t >> (bit - 7)) & 0xFFu;
+        /* positions >= eob are zero: a final run of n zeros ends at 64, so it starts at 64 - n */
+        int eob = ((r >> (bit - 1)) & 1u) ? 63 - (int)(bk & 0x3Fu) : 64;
+        if (need <= 0) { ntok = 0; eob = 64; }        /* 63 raw coefficients: no token tail */
+        out[blk++] = isff ? RTJ_ENT(0, 0) : RTJ_ENT(min(o, len), max(eob, 1));
+        skips += isff;
+        o = isff ? o + 1 : tok + ntok;
+    }
+    if (sink == 0x5eed5eedu && (touch0 ^ touch1 ^ touch2) == 0x0badf00du) skips = -1;     /* keeps the touch loads alive; never true in effect */
+    LaneResult res = {blk, skips, o};
+    return res;
+}
+
+} // namespace
+
+extern "C" __global__ void __launch_bounds__(32)
+rtj_scan_lane_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc *__restrict__ desc,
+                     const rtj_dev_table *__restrict__ tables, int F, int nblk,
+                     uint32_t *__restrict__ ent, uint32_t *__restrict__ frame_skips,
+                     rtj_dev_info *__restrict__ info)
+{
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= F) return;
+    const rtjgpu_frame_desc d = desc[f];
+    const uint8_t *pay = stream + d.offset + RTJPEG_B200_HEADER_BYTES;
+    const int len = d.length > RTJPEG_B200_HEADER_BYTES ? (int)d.length - RTJPEG_B200_HEADER_BYTES : 0;
+    const int lb8 = tables[d.table].bt8[0];
+    const int cb8 = tables[d.table].bt8[1];
+    uint32_t *out = ent + (size_t)f * nblk;
+
+    const LaneResult res = (lb8 == 0 && cb8 == 0) ? lane_scan_frame<false>(pay, len, 0, 0, out, nblk)
+                                                  : lane_scan_frame<true>(pay, len, lb8, cb8, out, nblk);
+
+    /* a frame whose stream ends early or mid-block: flag it, give the missing blocks a harmless entry */
+    const bool bad = res.blk < nblk || res.consumed > len;
+    for (int b = res.blk; b < nblk; b++) out[b] = RTJ_ENT(len, 1);
+    frame_skips[f] = (uint32_t)res.skips;
+    if (res.skips) atomicAdd(&info->skipped_blocks, (unsigned long long)res.skips);
+    atomicAdd(&info->payload_bytes, (unsigned long long)min(res.consumed, len));
+    if (bad || len > (int)RTJGPU_MAX_PAYLOAD_BYTES) {
+        atomicAdd(&info->bad_frames, 1u);
+        atomicMin((unsigned int *)&info->first_bad_frame, (unsigned int)f);
+    }
+}
+
 /* ------------------------------------------------------------------------ */
 /* K3: last-writer resolution of skipped blocks                               */
 /* ------------------------------------------------------------------------ */
@@ -250,13 +395,51 @@ __device__ __forceinline__ uint32_t descale_pack4(int y0, int y1, int y2, int y3
     X(56,5,6) X(57,4,7) X(58,5,7) X(59,6,6) X(60,7,5) X(61,7,6) X(62,6,7) X(63,7,7)
 
 /*
- * Decode one block whose zig-zag positions >= K are known to be zero.
- * src points at the block's DC byte, iq at the 64 multipliers in zig-zag order,
- * bt8 is the raw-prefix length.  px receives 8 rows x 8 bytes.
+ * Byte source of one block for the sparse classes: the first 4*NW bytes sit in
+ * registers (aligned 32-bit loads, funnel-shifted to the block's byte offset) and
+ * leave through the low byte, so the token walk issues no dependent loads.
  */
-template <int K>
-__device__ __forceinline__ void decode_block(const uint8_t *__restrict__ src, const int *__restrict__ iq,
-                                             int bt8, uint32_t (&px)[16])
+template <int NW>
+struct RegBytes {
+    uint32_t u[NW];
+    __device__ __forceinline__ explicit RegBytes(const uint8_t *__restrict__ src)
+    {
+        const uintptr_t a = reinterpret_cast<uintptr_t>(src);
+        const uint32_t *wp = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
+        const unsigned sh = (unsigned)(a & 3) * 8;
+        uint32_t w[NW + 1];
+#pragma unroll
+        for (int i = 0; i <= NW; i++) w[i] = __ldg(wp + i);      /* independent loads; slack bytes follow the stream */
+#pragma unroll
+        for (int i = 0; i < NW; i++) u[i] = __funnelshift_r(w[i], w[i + 1], sh);
+    }
+    __device__ __forceinline__ int peek_u8() const { return (int)(u[0] & 0xFFu); }
+    __device__ __forceinline__ int peek_s8() const { return (int)(signed char)(u[0] & 0xFFu); }
+    __device__ __forceinline__ void advance(bool take)
+    {
+        const unsigned sh = take ? 8u : 0u;
+#pragma unroll
+        for (int i = 0; i < NW - 1; i++) u[i] = __funnelshift_r(u[i], u[i + 1], sh);
+        u[NW - 1] >>= sh;
+    }
+};
+
+/* Byte source for dense blocks: straight from global memory, one byte at a time. */
+struct MemBytes {
+    const uint8_t *q;
+    __device__ __forceinline__ explicit MemBytes(const uint8_t *__restrict__ src) : q(src) {}
+    __device__ __forceinline__ int peek_u8() const { return (int)__ldg(q); }
+    __device__ __forceinline__ int peek_s8() const { return (int)(signed char)__ldg(q); }
+    __device__ __forceinline__ void advance(bool take) { q += take ? 1 : 0; }
+};
+
+/*
+ * Decode one block whose zig-zag positions >= K are known to be zero.
+ * iq holds the 64 multipliers in zig-zag order, bt8 is the raw-prefix length.
+ * px receives 8 rows x 8 bytes.
+ */
+template <int K, typename Bytes>
+__device__ __forceinline__ void decode_block(Bytes &by, const int *__restrict__ iq, int bt8, uint32_t (&px)[16])
 {
     int m[8][8];
 #pragma unroll
@@ -266,20 +449,18 @@ __device__ __forceinline__ void decode_block(const uint8_t *__restrict__ src, co
 
     /* DC is an unsigned byte (lib/RTjpeg.c:163); +4 is DESCALE's rounding term, which
      * reaches every output unchanged because the DC path has no multiply. */
-    m[0][0] = wrap16((int)__ldg(src) * iq[0]) + 4;
+    m[0][0] = wrap16(by.peek_u8() * iq[0]) + 4;
+    by.advance(true);
 
-    const uint8_t *q = src + 1;
     int z = 0;          /* zero positions still owed by the last run token */
 #define RTJ_STEP(k, r, c)                                                   \
     if ((k) > 0 && (k) < K) {                                               \
-        int v = 0;                                                          \
-        if (z == 0) {                                                       \
-            const int bb = (int)(signed char)__ldg(q);                      \
-            q++;                                                            \
-            if ((k) > bt8 && bb > 63) z = bb - 64; else v = bb;             \
-        } else {                                                            \
-            z--;                                                            \
-        }                                                                   \
+        const bool take = z == 0;                                           \
+        const int bb = by.peek_s8();                                        \
+        const bool run = take && (k) > bt8 && bb > 63;                      \
+        const int v = (take && !run) ? bb : 0;                              \
+        z = take ? (run ? bb - 64 : 0) : z - 1;                             \
+        by.advance(take);                                                   \
         m[r][c] = wrap16(v * iq[k]);                                        \
     }
     RTJ_ZZ_LIST(RTJ_STEP)
@@ -304,124 +485,246 @@ __device__ __forceinline__ void decode_block(const uint8_t *__restrict__ src, co
     }
 }
 
-/* sparsity classes, most expensive first so that the long chunks start early */
-enum { CLS_FULLG = 0, CLS_FULL, CLS_T4, CLS_T2, CLS_DC, CLS_CARRY, NCLS };
+/*
+ * The commonest block of real streams: at most DC, zig-zag 1 (row 1, column 0) and zig-zag 2
+ * (row 0, column 1).  Column 1 of the first pass is then constant down the rows, so the odd
+ * half of every ROW pass is the same eight values D[j], and pixel (r, j) = A[r] + D[j] with
+ * A = the column-0 pass.  When |A| + |D| provably stays inside int16 (always, for streams an
+ * encoder made), the final butterfly add, DESCALE and the 16..235 clamp run two pixels per
+ * instruction: VIADDMNMX.S16x2 (add, lower clamp at 16*8), VIMNMX.S16x2 (upper clamp at
+ * 235*8+7), one 32-bit shift by 3 for both halves, one PRMT per four pixels.  Clamping before
+ * the shift is exact because >>3 is monotone; the int16 narrowing of DESCALE is the identity
+ * inside the bound.  Outside the bound the same sums take the exact 32-bit epilogue.
+ */
+__device__ __forceinline__ void decode_block_t2(const uint8_t *__restrict__ src, const int *__restrict__ iq,
+                                                int bt8, uint32_t (&px)[16])
+{
+    RegBytes<1> by(src);
+    const int x0 = wrap16(by.peek_u8() * iq[0]) + 4;            /* +4: DESCALE's rounding term */
+    by.advance(true);
+    int xs[2];
+    int z = 0;
+#pragma unroll
+    for (int k = 1; k <= 2; k++) {
+        const bool take = z == 0;
+        const int bb = by.peek_s8();
+        const bool run = take && k > bt8 && bb > 63;
+        const int v = (take && !run) ? bb : 0;
+        z = take ? (run ? bb - 64 : 0) : z - 1;
+        by.advance(take);
+        xs[k - 1] = wrap16(v * iq[k]);
+    }
+    const int x1 = xs[0], q = xs[1];
+
+    /* pass 1, column 0: inputs (x0, x1, 0, ...): even half = x0, odd half from x1 alone */
+    int A[8];
+    {
+        const int z5 = fxmul(x1, 473);
+        const int o6 = z5 - x1;                                  /* o12 = fxmul(0,-669) + z5 = z5 */
+        const int o5 = fxmul(x1, 362) - o6;
+        const int o4 = fxmul(x1, 277) - z5 + o5;
+        A[0] = x0 + x1; A[7] = x0 - x1;
+        A[1] = x0 + o6; A[6] = x0 - o6;
+        A[2] = x0 + o5; A[5] = x0 - o5;
+        A[4] = x0 + o4; A[3] = x0 - o4;
+    }
+    /* pass 2: column 1 holds q in every row -> one odd half for all rows */
+    int D[8];
+    {
+        const int z5 = fxmul(q, 473);
+        const int o6 = z5 - q;
+        const int o5 = fxmul(q, 362) - o6;
+        const int o4 = fxmul(q, 277) - z5 + o5;
+        D[0] = q; D[7] = -q; D[1] = o6; D[6] = -o6; D[2] = o5; D[5] = -o5; D[4] = o4; D[3] = -o4;
+    }
+    /* |A[r]| <= |x0| + |x1| + 3, |D[j]| <= |q| + 3 (every odd term is below |input| in magnitude) */
+    if (abs(x0) + abs(x1) + abs(q) < 32000) {
+        const uint32_t d01 = __byte_perm((uint32_t)D[0], (uint32_t)D[1], 0x5410);
+        const uint32_t d23 = __byte_perm((uint32_t)D[2], (uint32_t)D[3], 0x5410);
+        const uint32_t d45 = __byte_perm((uint32_t)D[4], (uint32_t)D[5], 0x5410);
+        const uint32_t d67 = __byte_perm((uint32_t)D[6], (uint32_t)D[7], 0x5410);
+        constexpr uint32_t LO = 0x00800080u;     /* 16 * 8 */
+        constexpr uint32_t HI = 0x075F075Fu;     /* 235 * 8 + 7 */
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            const uint32_t a2 = __byte_perm((uint32_t)A[r], 0u, 0x1010);
+            const uint32_t t0 = __vmins2(__viaddmax_s16x2(a2, d01, LO), HI) >> 3;
+            const uint32_t t1 = __vmins2(__viaddmax_s16x2(a2, d23, LO), HI) >> 3;
+            const uint32_t t2 = __vmins2(__viaddmax_s16x2(a2, d45, LO), HI) >> 3;
+            const uint32_t t3 = __vmins2(__viaddmax_s16x2(a2, d67, LO), HI) >> 3;
+            px[2 * r] = __byte_perm(t0, t1, 0x6420);
+            px[2 * r + 1] = __byte_perm(t2, t3, 0x6420);
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            px[2 * r] = descale_pack4(A[r] + D[0], A[r] + D[1], A[r] + D[2], A[r] + D[3]);
+            px[2 * r + 1] = descale_pack4(A[r] + D[4], A[r] + D[5], A[r] + D[6], A[r] + D[7]);
+        }
+    }
+}
+
+/* sparsity classes; the deferred ones are ordered most expensive first so long chunks start early */
+enum { CLS_FULLG = 0, CLS_FULL, CLS_T4, CLS_T3, CLS_CARRY, NDEFER, CLS_T2 = NDEFER };
 
 constexpr int IDCT_MAX_MB = 128;     /* macroblocks per CTA strip */
+constexpr int IDCT_THREADS = 128;
 
 struct IdctSmemHeader {
     int iq[2][64];
-    int cnt[NCLS + 1];
-    int base[NCLS + 1];
-    int cursor[NCLS + 1];
-    int nchunk_total;
+    int cnt[NDEFER];
+    int next_chunk;
+};
+
+__device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, unsigned bytes)
+{
+    /* TMA 1-D bulk copy shared -> global (UBLKCP) */
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 :: "l"(gdst), "r"((unsigned)__cvta_generic_to_shared(ssrc)), "r"(bytes) : "memory");
+}
+
+/* where block i of the strip lives inside the shared-memory picture strip */
+struct TileGeom {
+    uint8_t *tileY, *tileU, *tileV;
+    int segW, segC;
+    __device__ __forceinline__ void store(int i, const uint32_t (&px)[16]) const
+    {
+        const int mb = i / 6, sub = i - mb * 6;
+        uint8_t *dst;
+        int pitch;
+        if (sub < 4) {
+            pitch = segW;
+            dst = tileY + ((sub >> 1) * 8) * segW + mb * 16 + (sub & 1) * 8;
+        } else {
+            pitch = segC;
+            dst = (sub == 4 ? tileU : tileV) + mb * 8;
+        }
+#pragma unroll
+        for (int r = 0; r < 8; r++)
+            *reinterpret_cast<uint2 *>(dst + r * pitch) = make_uint2(px[2 * r], px[2 * r + 1]);
+    }
 };
 
 } // namespace
 
-extern "C" __global__ void __launch_bounds__(256)
+extern "C" __global__ void __launch_bounds__(IDCT_THREADS, 5)
 rtj_idct_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc *__restrict__ desc,
                 const rtj_dev_table *__restrict__ tables, const uint32_t *__restrict__ ent,
                 const uint16_t *__restrict__ srcf, int nblk, int w, int h, int seg_mb, int nstrips,
                 uint8_t *__restrict__ out, const uint8_t *__restrict__ carry)
 {
-    extern __shared__ __align__(16) uint8_t smem[];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NWARPS = IDCT_THREADS / 32;
     const int f = blockIdx.y;
     const int strip = blockIdx.x % nstrips, my = blockIdx.x / nstrips;
     const int mbw = w >> 4;
     const int mx0 = strip * seg_mb;
     const int mbs = min(seg_mb, mbw - mx0);
     const int nb = mbs * 6;
-    const int segW = mbs * 16, segC = mbs * 8;
 
-    uint8_t *tileY = smem;
-    uint8_t *tileU = tileY + 16 * segW;
-    uint8_t *tileV = tileU + 8 * segC;
-    IdctSmemHeader *hd = reinterpret_cast<IdctSmemHeader *>(tileV + 8 * segC);
-    uint32_t *s_ent = reinterpret_cast<uint32_t *>(hd + 1);
-    uint16_t *s_src = reinterpret_cast<uint16_t *>(s_ent + nb);
-    uint16_t *s_ord = s_src + nb;
-    uint8_t *s_cls = reinterpret_cast<uint8_t *>(s_ord + nb);
+    TileGeom tile;
+    tile.segW = mbs * 16;
+    tile.segC = mbs * 8;
+    tile.tileY = smem;
+    tile.tileU = tile.tileY + 16 * tile.segW;
+    tile.tileV = tile.tileU + 8 * tile.segC;
+    IdctSmemHeader *hd = reinterpret_cast<IdctSmemHeader *>(tile.tileV + 8 * tile.segC);
+    uint32_t *s_ent = reinterpret_cast<uint32_t *>(hd + 1);   /* [NDEFER][nb] entries of deferred blocks */
+    uint16_t *s_idx = reinterpret_cast<uint16_t *>(s_ent + NDEFER * nb);   /* their strip index ... */
+    uint16_t *s_src = s_idx + NDEFER * nb;                    /* ... and source frame */
 
     const rtjgpu_frame_desc fd = desc[f];
     const int mytable = fd.table;
-    if (tid < 128) hd->iq[tid >> 6][tid & 63] = tables[mytable].iq[tid >> 6][tid & 63];
-    if (tid < NCLS + 1) { hd->cnt[tid] = 0; hd->cursor[tid] = 0; }
+    hd->iq[tid >> 6][tid & 63] = tables[mytable].iq[tid >> 6][tid & 63];   /* IDCT_THREADS == 128 entries */
+    if (tid < NDEFER) hd->cnt[tid] = 0;
+    if (tid == NDEFER) hd->next_chunk = 0;
+    const int bt8_l = tables[mytable].bt8[0], bt8_c = tables[mytable].bt8[1];
     __syncthreads();
 
-    /* ---- gather the strip's entries, resolve skipped blocks, classify ---- */
-    const size_t frame_blk0 = (size_t)f * nblk + (size_t)(my * mbw + mx0) * 6;
-    for (int i0 = 0; i0 < nb; i0 += blockDim.x) {
+    /* ---- pass 1, stream order: the sparse majority (<= 3 coded positions) decodes right away,
+     *      everything else is deferred into per-class lists ---- */
+    const size_t strip_blk0 = (size_t)(my * mbw + mx0) * 6;
+    const size_t frame_blk0 = (size_t)f * nblk + strip_blk0;
+    const uint8_t *frame_pay = stream + fd.offset + RTJPEG_B200_HEADER_BYTES;
+    for (int i0 = 0; i0 < nb; i0 += IDCT_THREADS) {
         const int i = i0 + tid;
-        int cls = NCLS;
+        int cls = -1;
+        uint32_t e = 0;
+        unsigned sf = (unsigned)f;
         if (i < nb) {
-            uint32_t e = ent[frame_blk0 + i];
-            unsigned sf = (unsigned)f;
+            e = ent[frame_blk0 + i];
             if ((e >> RTJ_ENT_OFF_BITS) == 0) {
                 const unsigned s = srcf[frame_blk0 + i];
                 if (s != RTJ_SRC_CARRY) {
                     sf = s;
-                    e = ent[(size_t)s * nblk + (size_t)(my * mbw + mx0) * 6 + i];
+                    e = ent[(size_t)s * nblk + strip_blk0 + i];
                 }
             }
             const int eob = (int)(e >> RTJ_ENT_OFF_BITS);
             if (eob == 0) cls = CLS_CARRY;
             else if (sf != (unsigned)f && desc[sf].table != mytable) cls = CLS_FULLG;
-            else if (eob == 1) cls = CLS_DC;
             else if (eob <= 3) cls = CLS_T2;
+            else if (eob <= 6) cls = CLS_T3;
             else if (eob <= 10) cls = CLS_T4;
             else cls = CLS_FULL;
-            s_ent[i] = e;
-            s_src[i] = (uint16_t)sf;
-            s_cls[i] = (uint8_t)cls;
         }
-        const unsigned peers = __match_any_sync(FULL, cls);
-        if (lane == __ffs(peers) - 1) atomicAdd(&hd->cnt[cls], __popc(peers));
-    }
-    __syncthreads();
-    if (tid == 0) {
-        int acc = 0, chunks = 0;
-        for (int c = 0; c < NCLS; c++) {
-            hd->base[c] = acc;
-            acc += hd->cnt[c];
-            chunks += (hd->cnt[c] + 31) >> 5;
+        if (cls == CLS_T2) {
+            const int chroma = (i % 6) >= 4;
+            const uint8_t *src = (sf == (unsigned)f ? frame_pay : stream + desc[sf].offset + RTJPEG_B200_HEADER_BYTES)
+                                 + (e & RTJ_ENT_OFF_MASK);
+            uint32_t px[16];
+            decode_block_t2(src, hd->iq[chroma], chroma ? bt8_c : bt8_l, px);
+            tile.store(i, px);
         }
-        hd->nchunk_total = chunks;
-    }
-    __syncthreads();
-    for (int i0 = 0; i0 < nb; i0 += blockDim.x) {
-        const int i = i0 + tid;
-        const int cls = i < nb ? (int)s_cls[i] : NCLS;
-        const unsigned peers = __match_any_sync(FULL, cls);
-        const int leader = __ffs(peers) - 1;
-        int slot = 0;
-        if (lane == leader) slot = atomicAdd(&hd->cursor[cls], __popc(peers));
-        slot = __shfl_sync(FULL, slot, leader);
-        if (i < nb) s_ord[hd->base[cls] + slot + __popc(peers & ((1u << lane) - 1u))] = (uint16_t)i;
+        const unsigned deferred = __ballot_sync(FULL, cls >= 0 && cls < NDEFER);
+        if (deferred) {                                             /* warp-uniform */
+#pragma unroll
+            for (int c = 0; c < NDEFER; c++) {
+                const unsigned m = __ballot_sync(FULL, cls == c);
+                if (m == 0) continue;
+                int slot = 0;
+                const int leader = __ffs(m) - 1;
+                if (lane == leader) slot = atomicAdd(&hd->cnt[c], __popc(m));
+                slot = __shfl_sync(FULL, slot, leader);
+                if (cls == c) {
+                    const int at = c * nb + slot + __popc(m & ((1u << lane) - 1u));
+                    s_ent[at] = e;
+                    s_idx[at] = (uint16_t)i;
+                    s_src[at] = (uint16_t)sf;
+                }
+            }
+        }
     }
     __syncthreads();
 
-    /* ---- decode: one class-homogeneous chunk of 32 blocks per warp step ---- */
+    /* ---- pass 2: deferred blocks, one class-homogeneous chunk of 32 per warp step ---- */
     const size_t fsz = (size_t)w * h * 3 / 2;
-    const int total = hd->nchunk_total;
-    for (int ch = warp; ch < total; ch += nwarps) {
+    int total = 0;
+#pragma unroll
+    for (int c = 0; c < NDEFER; c++) total += (hd->cnt[c] + 31) >> 5;
+    while (total > 0) {
+        int ch = 0;
+        if (lane == 0) ch = atomicAdd(&hd->next_chunk, 1);
+        ch = __shfl_sync(FULL, ch, 0);
+        if (ch >= total) break;
         int cls = 0, rel = ch;
-        for (; cls < NCLS; cls++) {
-            const int nc = (hd->cnt[cls] + 31) >> 5;
-            if (rel < nc) break;
-            rel -= nc;
+#pragma unroll
+        for (int c = 0; c < NDEFER; c++) {
+            const int nc = (hd->cnt[c] + 31) >> 5;
+            if (cls == c) { if (rel >= nc) { rel -= nc; cls = c + 1; } }
         }
         const int idx = rel * 32 + lane;
-        const bool act = idx < hd->cnt[cls];
-        if (!act) continue;
-        const int i = s_ord[hd->base[cls] + idx];
-        const int mb = i / 6, sub = i - mb * 6;
+        if (idx >= hd->cnt[cls]) continue;
+        const int at = cls * nb + idx;
+        const int i = s_idx[at];
+        const int sub = i % 6;
         const int chroma = sub >= 4;
         uint32_t px[16];
 
         if (cls == CLS_CARRY) {
             if (carry) {
+                const int mb = i / 6;
                 const uint8_t *cp;
                 int pitch;
                 if (!chroma) {
@@ -443,55 +746,56 @@ rtj_idct_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc *__r
                 for (int r = 0; r < 16; r++) px[r] = 0;
             }
         } else {
-            const uint32_t e = s_ent[i];
-            const unsigned sf = s_src[i];
-            const uint64_t foff = sf == (unsigned)f ? fd.offset : desc[sf].offset;
-            const uint8_t *src = stream + foff + RTJPEG_B200_HEADER_BYTES + (e & RTJ_ENT_OFF_MASK);
+            const uint32_t e = s_ent[at];
+            const unsigned sf = s_src[at];
+            const uint8_t *src = (sf == (unsigned)f ? frame_pay : stream + desc[sf].offset + RTJPEG_B200_HEADER_BYTES)
+                                 + (e & RTJ_ENT_OFF_MASK);
             if (cls == CLS_FULLG) {
                 const rtj_dev_table *t = &tables[desc[sf].table];
-                decode_block<64>(src, t->iq[chroma], t->bt8[chroma], px);
+                MemBytes by(src);
+                decode_block<64>(by, t->iq[chroma], t->bt8[chroma], px);
             } else {
                 const int *iq = hd->iq[chroma];
-                const int bt8 = tables[mytable].bt8[chroma];
-                if (cls == CLS_FULL) decode_block<64>(src, iq, bt8, px);
-                else if (cls == CLS_T4) decode_block<10>(src, iq, bt8, px);
-                else if (cls == CLS_T2) decode_block<3>(src, iq, bt8, px);
-                else decode_block<1>(src, iq, bt8, px);
+                const int bt8 = chroma ? bt8_c : bt8_l;
+                if (cls == CLS_FULL) { MemBytes by(src); decode_block<64>(by, iq, bt8, px); }
+                else if (cls == CLS_T4) { RegBytes<3> by(src); decode_block<10>(by, iq, bt8, px); }
+                else { RegBytes<2> by(src); decode_block<6>(by, iq, bt8, px); }
             }
         }
-        uint8_t *dst;
-        int pitch;
-        if (!chroma) {
-            pitch = segW;
-            dst = tileY + ((sub >> 1) * 8) * segW + mb * 16 + (sub & 1) * 8;
-        } else {
-            pitch = segC;
-            dst = (sub == 4 ? tileU : tileV) + mb * 8;
-        }
-#pragma unroll
-        for (int r = 0; r < 8; r++)
-            *reinterpret_cast<uint2 *>(dst + r * pitch) = make_uint2(px[2 * r], px[2 * r + 1]);
+        tile.store(i, px);
     }
-    __syncthreads();
 
-    /* ---- the strip leaves as wide stores ---- */
+    /* ---- the strip leaves the SM ---- */
     uint8_t *oy = out + (size_t)f * fsz + (size_t)(my * 16) * w + mx0 * 16;
-    const int vy = segW >> 4;                        /* 16-byte vectors per luma row */
-    for (int v = tid; v < 16 * vy; v += blockDim.x) {
-        const int r = v / vy, c = v - r * vy;
-        *reinterpret_cast<uint4 *>(oy + (size_t)r * w + c * 16) =
-            *reinterpret_cast<const uint4 *>(tileY + r * segW + c * 16);
-    }
     const int cw = w >> 1;
     uint8_t *ou = out + (size_t)f * fsz + (size_t)w * h + (size_t)(my * 8) * cw + mx0 * 8;
     uint8_t *ov = ou + (size_t)cw * (h >> 1);
-    const int vc = segC >> 3;                        /* 8-byte vectors per chroma row */
-    for (int v = tid; v < 2 * 8 * vc; v += blockDim.x) {
-        const int pl = v >= 8 * vc;
-        const int vv = pl ? v - 8 * vc : v;
-        const int r = vv / vc, c = vv - r * vc;
-        *reinterpret_cast<uint2 *>((pl ? ov : ou) + (size_t)r * cw + c * 8) =
-            *reinterpret_cast<const uint2 *>((pl ? tileV : tileU) + r * segC + c * 8);
+    if (nstrips == 1) {
+        /* full-width strip: 16 luma rows and 2 x 8 chroma rows are each one contiguous run in the
+         * tight-pitch planes -> three TMA bulk stores issued by one thread */
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            bulk_store(oy, tile.tileY, 16u * (unsigned)tile.segW);
+            bulk_store(ou, tile.tileU, 8u * (unsigned)tile.segC);
+            bulk_store(ov, tile.tileV, 8u * (unsigned)tile.segC);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+    } else {
+        __syncthreads();
+        const int vy = tile.segW >> 4;               /* 16-byte vectors per luma row */
+        for (int r = warp; r < 16; r += NWARPS)
+            for (int c = lane; c < vy; c += 32)
+                *reinterpret_cast<uint4 *>(oy + (size_t)r * w + c * 16) =
+                    *reinterpret_cast<const uint4 *>(tile.tileY + r * tile.segW + c * 16);
+        const int vc = tile.segC >> 3;               /* 8-byte vectors per chroma row */
+        for (int r = warp; r < 16; r += NWARPS) {
+            const int pl = r >> 3, rr = r & 7;
+            for (int c = lane; c < vc; c += 32)
+                *reinterpret_cast<uint2 *>((pl ? ov : ou) + (size_t)rr * cw + c * 8) =
+                    *reinterpret_cast<const uint2 *>((pl ? tile.tileV : tile.tileU) + rr * tile.segC + c * 8);
+        }
     }
 }
 
@@ -509,7 +813,7 @@ inline size_t idct_smem_bytes(int seg_mb)
     const size_t nb = (size_t)seg_mb * 6;
     size_t s = (size_t)seg_mb * 16 * 24;             /* Y 16 rows + U,V 8 rows of half width */
     s += sizeof(IdctSmemHeader);
-    s += nb * (4 + 2 + 2 + 1);
+    s += nb * NDEFER * (4 + 2 + 2);
     return (s + 15) & ~(size_t)15;
 }
 
@@ -526,9 +830,17 @@ extern "C" int rtj_kernels_init(void)
 extern "C" int rtj_launch_scan(const rtj_launch_args *a, void *stream)
 {
     const int nblk = (a->w >> 4) * (a->h >> 4) * 6;
-    const int grid = (a->F + SCAN_WARPS - 1) / SCAN_WARPS;
-    rtj_scan_kernel<<<grid, SCAN_WARPS * 32, 0, (cudaStream_t)stream>>>(
-        a->d_stream, a->d_desc, a->d_tables, a->F, nblk, a->d_ent, a->d_frame_skips, a->d_info);
+    /* many frames: one lane per frame (cheap in issue slots, latency hidden by the batch);
+     * few frames: one warp per frame.  rtjgpu_set_scan_mode() forces a flavour. */
+    const bool lane = a->scan_mode ? a->scan_mode == RTJGPU_SCAN_LANE : a->F >= 512;
+    if (lane) {
+        rtj_scan_lane_kernel<<<(a->F + 31) / 32, 32, 0, (cudaStream_t)stream>>>(
+            a->d_stream, a->d_desc, a->d_tables, a->F, nblk, a->d_ent, a->d_frame_skips, a->d_info);
+    } else {
+        const int grid = (a->F + SCAN_WARPS - 1) / SCAN_WARPS;
+        rtj_scan_warp_kernel<<<grid, SCAN_WARPS * 32, 0, (cudaStream_t)stream>>>(
+            a->d_stream, a->d_desc, a->d_tables, a->F, nblk, a->d_ent, a->d_frame_skips, a->d_info);
+    }
     return (int)cudaGetLastError();
 }
 
@@ -546,9 +858,8 @@ extern "C" int rtj_launch_idct(const rtj_launch_args *a, void *stream)
     const int nblk = mbw * mbh * 6;
     int nstrips;
     const int seg_mb = idct_seg_mb(mbw, &nstrips);
-    const int threads = seg_mb * 6 >= 192 ? 256 : 128;
     dim3 grid((unsigned)(nstrips * mbh), (unsigned)a->F);
-    rtj_idct_kernel<<<grid, threads, idct_smem_bytes(seg_mb), (cudaStream_t)stream>>>(
+    rtj_idct_kernel<<<grid, IDCT_THREADS, idct_smem_bytes(seg_mb), (cudaStream_t)stream>>>(
         a->d_stream, a->d_desc, a->d_tables, a->d_ent, a->d_src, nblk, a->w, a->h, seg_mb, nstrips,
         a->d_out, a->d_carry);
     return (int)cudaGetLastError();

@@ -159,6 +159,14 @@ const char *rtjgpu_strerror(int code);
 /* cudaError_t of the last failing CUDA call on this context, as int. */
 int  rtjgpu_last_cuda_error(const rtjgpu_ctx *ctx);
 
+/* Which flavour of the block-offset scan (K1) runs: one thread per frame (cheap, latency
+ * hidden by large batches) or one warp per frame (few, large frames).  AUTO picks by
+ * batch size. */
+#define RTJGPU_SCAN_AUTO 0
+#define RTJGPU_SCAN_LANE 1
+#define RTJGPU_SCAN_WARP 2
+int  rtjgpu_set_scan_mode(rtjgpu_ctx *ctx, int mode);
+
 /* Raw (pre-AAN) tables for RTJGPU_TABLE_CUSTOM, the set_tables path. */
 int  rtjgpu_set_custom_tables(rtjgpu_ctx *ctx, const uint32_t raw[128]);
 

@@ -15,9 +15,12 @@ from streams import clip, golden, interleave, reference_frames
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def ctx():
+@pytest.fixture(scope="module", params=["lane", "warp"])
+def ctx(request):
+    """Every parity case runs under both flavours of the block-offset scan (K1)."""
     c = g.BatchContext(0)
+    c.set_scan_mode(capi.SCAN_LANE if request.param == "lane" else capi.SCAN_WARP)
+    c.flavour = request.param
     yield c
     c.close()
 
@@ -180,6 +183,7 @@ def test_truncated_frame_is_flagged_not_overread(ctx):
 
 
 def test_decode_host_pipeline(ctx):
+    ctx.set_scan_mode(capi.SCAN_AUTO)
     # 250 frames of 720x576 = three chunks through the pinned staging slots
     s, o = clip(720, 576, 128, 250, key_rate=29, lm=2, cm=2, noise_y=2)
     w, h = 720, 576
@@ -211,6 +215,9 @@ def test_full_size_config2_4096_frames(ctx):
     (threaded across the host's cores), plus the determinism property: decoding the same
     batch twice gives identical bytes."""
     import os
+    if ctx.flavour == "warp":
+        pytest.skip("full-size batch runs once, under the automatic flavour")
+    ctx.set_scan_mode(capi.SCAN_AUTO)
     w, h, F = 720, 576, 4096
     fsz = w * h * 3 // 2
     s, o = clip(w, h, 128, F)

@@ -128,7 +128,8 @@ int run_kernels(rtjgpu_ctx *ctx, Workspace *ws, const uint8_t *d_stream, const r
     CK(ctx, cudaMemcpyAsync(ws->d_info, ctx->h_info_reset, sizeof(rtj_dev_info), cudaMemcpyHostToDevice, st));
     if (ev) CK(ctx, cudaEventRecord(ev[0], st));
     int e = rtj_launch_scan(&a, st);
-    if (e) { ctx->last_cuda = e; return RTJGPU_E_CUDA; }
+    if (e < 0) { ctx->last_cuda = -e; return RTJGPU_E_CUDA; }
+    ctx->launches += (uint64_t)e;
     if (ev) CK(ctx, cudaEventRecord(ev[1], st));
     e = rtj_launch_resolve(&a, st);
     if (e) { ctx->last_cuda = e; return RTJGPU_E_CUDA; }
@@ -136,7 +137,7 @@ int run_kernels(rtjgpu_ctx *ctx, Workspace *ws, const uint8_t *d_stream, const r
     e = rtj_launch_idct(&a, st);
     if (e) { ctx->last_cuda = e; return RTJGPU_E_CUDA; }
     if (ev) CK(ctx, cudaEventRecord(ev[3], st));
-    ctx->launches += 3;
+    ctx->launches += 2;
     return RTJGPU_OK;
 }
 
@@ -263,7 +264,7 @@ void rtjgpu_enable_timing(rtjgpu_ctx *ctx, int on) { if (ctx) ctx->timing = on !
 
 int rtjgpu_set_scan_mode(rtjgpu_ctx *ctx, int mode)
 {
-    if (!ctx || mode < RTJGPU_SCAN_AUTO || mode > RTJGPU_SCAN_WARP) return RTJGPU_E_ARG;
+    if (!ctx || mode < RTJGPU_SCAN_AUTO || mode > RTJGPU_SCAN_CHUNK) return RTJGPU_E_ARG;
     ctx->scan_mode = mode;
     return RTJGPU_OK;
 }

@@ -12,13 +12,25 @@ extern "C" {
 #endif
 
 /* ---- K1 output: one 32-bit entry per 8x8 block ------------------------------
- *   bits  0..24  byte offset of the block inside its frame's payload
- *   bits 25..31  end-of-block bound E (1..64): every zig-zag position >= E is
- *                zero.  E == 0 marks a block the stream skipped (0xFF marker).
+ *   general   bit 31 = 0, bits 25..30 = E - 1, bits 0..24 = byte offset of the block
+ *             inside its frame's payload.  E (1..64) is an end-of-block bound: every
+ *             zig-zag position >= E is zero.
+ *   inline    bit 31 = 1, bits 24..30 = 0: a block with E <= 3 carried in the entry
+ *             itself -- bits 0..7 the DC byte (unsigned), bits 8..15 and 16..23 the
+ *             signed coefficients at zig-zag 1 and 2 (0 where a run token covers
+ *             them).  K2 never touches the payload for such a block.
+ *   skipped   0xFFFFFFFF: the stream's 0xFF marker (lib/RTjpeg.c:2704).
  */
 #define RTJ_ENT_OFF_BITS 25
 #define RTJ_ENT_OFF_MASK ((1u << RTJ_ENT_OFF_BITS) - 1u)
-#define RTJ_ENT(off, eob) ((uint32_t)(off) | ((uint32_t)(eob) << RTJ_ENT_OFF_BITS))
+#define RTJ_ENT(off, eob) ((uint32_t)(off) | ((uint32_t)((eob) - 1) << RTJ_ENT_OFF_BITS))
+#define RTJ_ENT_SKIP 0xFFFFFFFFu
+#define RTJ_ENT_INLINE_BIT 0x80000000u
+#define RTJ_ENT_INLINE(dc, c1, c2) \
+    (RTJ_ENT_INLINE_BIT | ((uint32_t)(dc) & 0xFFu) | (((uint32_t)(c1) & 0xFFu) << 8) | (((uint32_t)(c2) & 0xFFu) << 16))
+#define RTJ_ENT_IS_SKIP(e) ((e) == RTJ_ENT_SKIP)
+#define RTJ_ENT_IS_INLINE(e) (((e) & RTJ_ENT_INLINE_BIT) != 0u && (e) != RTJ_ENT_SKIP)
+#define RTJ_ENT_EOB(e) ((int)(((e) >> RTJ_ENT_OFF_BITS) & 63u) + 1)
 
 /* K3 output for skipped blocks: index of the last frame of the batch that
  * coded the block, or RTJ_SRC_CARRY when none has yet. */
@@ -71,7 +83,9 @@ typedef struct rtj_launch_args {
     int                      scan_mode;     /* RTJGPU_SCAN_* */
 } rtj_launch_args;
 
-int rtj_launch_scan(const rtj_launch_args *a, void *stream);
+int rtj_launch_scan(const rtj_launch_args *a, void *stream);          /* returns the number of launches (>0) or -cudaError */
+int rtj_launch_scan_chunk(const rtj_launch_args *a, void *stream);    /* rtj_scan_chunk.cu */
+int rtj_scan_chunk_init(void);
 int rtj_launch_resolve(const rtj_launch_args *a, void *stream);
 int rtj_launch_idct(const rtj_launch_args *a, void *stream);
 int rtj_kernels_init(void);   /* one-time function attributes (dynamic shared memory opt-in) */

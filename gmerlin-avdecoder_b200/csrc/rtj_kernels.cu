@@ -45,7 +45,7 @@ extern "C" __global__ void __launch_bounds__(SCAN_WARPS * 32)
 rtj_scan_warp_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc *__restrict__ desc,
                 const rtj_dev_table *__restrict__ tables, int F, int nblk,
                 uint32_t *__restrict__ ent, uint32_t *__restrict__ frame_skips,
-                rtj_dev_info *__restrict__ info)
+                rtj_dev_info *__restrict__ info, int raw_only)
 {
     const int lane = threadIdx.x & 31;
     const int f = blockIdx.x * SCAN_WARPS + (threadIdx.x >> 5);
@@ -56,6 +56,7 @@ rtj_scan_warp_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc
     const int len = d.length > RTJPEG_B200_HEADER_BYTES ? (int)d.length - RTJPEG_B200_HEADER_BYTES : 0;
     const int lb8 = tables[d.table].bt8[0];
     const int cb8 = tables[d.table].bt8[1];
+    if (raw_only && (lb8 | cb8) == 0) return;        /* rtj_scan_chunk_kernel has done this frame */
     uint32_t *out = ent + (size_t)f * nblk;
 
     /* warp-uniform parser state */
@@ -96,7 +97,7 @@ rtj_scan_warp_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc
                     s += 1;
                     skips++;
                     done = true;
-                    e_out = RTJ_ENT(0, 0);
+                    e_out = RTJ_ENT_SKIP;
                 } else {
                     const int bt8 = k6 < 4 ? lb8 : cb8;
                     cur_off = pos + s;
@@ -262,7 +263,7 @@ __device__ __forceinline__ LaneResult lane_scan_frame(const uint8_t *__restrict_
         /* positions >= eob are zero: a final run of n zeros ends at 64, so it starts at 64 - n */
         int eob = ((r >> (bit - 1)) & 1u) ? 63 - (int)(bk & 0x3Fu) : 64;
         if (need <= 0) { ntok = 0; eob = 64; }        /* 63 raw coefficients: no token tail */
-        out[blk++] = isff ? RTJ_ENT(0, 0) : RTJ_ENT(min(o, len), max(eob, 1));
+        out[blk++] = isff ? RTJ_ENT_SKIP : RTJ_ENT(min(o, len), max(eob, 1));
         skips += isff;
         o = isff ? o + 1 : tok + ntok;
     }
@@ -277,7 +278,7 @@ extern "C" __global__ void __launch_bounds__(32)
 rtj_scan_lane_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc *__restrict__ desc,
                      const rtj_dev_table *__restrict__ tables, int F, int nblk,
                      uint32_t *__restrict__ ent, uint32_t *__restrict__ frame_skips,
-                     rtj_dev_info *__restrict__ info)
+                     rtj_dev_info *__restrict__ info, int raw_only)
 {
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= F) return;
@@ -286,6 +287,7 @@ rtj_scan_lane_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc
     const int len = d.length > RTJPEG_B200_HEADER_BYTES ? (int)d.length - RTJPEG_B200_HEADER_BYTES : 0;
     const int lb8 = tables[d.table].bt8[0];
     const int cb8 = tables[d.table].bt8[1];
+    if (raw_only && (lb8 | cb8) == 0) return;        /* rtj_scan_chunk_kernel has done this frame */
     uint32_t *out = ent + (size_t)f * nblk;
 
     const LaneResult res = (lb8 == 0 && cb8 == 0) ? lane_scan_frame<false>(pay, len, 0, 0, out, nblk)
@@ -322,13 +324,13 @@ rtj_resolve_kernel(const uint32_t *__restrict__ ent, uint16_t *__restrict__ src,
         for (int j = 0; j < 8; j++) e[j] = ent[(size_t)(f + j) * nblk + b];
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-            if ((e[j] >> RTJ_ENT_OFF_BITS) == 0) src[(size_t)(f + j) * nblk + b] = (uint16_t)last;
+            if (RTJ_ENT_IS_SKIP(e[j])) src[(size_t)(f + j) * nblk + b] = (uint16_t)last;
             else last = (unsigned)(f + j);
         }
     }
     for (; f < F; f++) {
         const uint32_t e = ent[(size_t)f * nblk + b];
-        if ((e >> RTJ_ENT_OFF_BITS) == 0) src[(size_t)f * nblk + b] = (uint16_t)last;
+        if (RTJ_ENT_IS_SKIP(e)) src[(size_t)f * nblk + b] = (uint16_t)last;
         else last = (unsigned)f;
     }
 }
@@ -496,6 +498,8 @@ __device__ __forceinline__ void decode_block(Bytes &by, const int *__restrict__ 
  * the shift is exact because >>3 is monotone; the int16 narrowing of DESCALE is the identity
  * inside the bound.  Outside the bound the same sums take the exact 32-bit epilogue.
  */
+__device__ __forceinline__ void t2_pixels(int x0, int x1, int q, uint32_t (&px)[16]);
+
 __device__ __forceinline__ void decode_block_t2(const uint8_t *__restrict__ src, const int *__restrict__ iq,
                                                 int bt8, uint32_t (&px)[16])
 {
@@ -514,8 +518,21 @@ __device__ __forceinline__ void decode_block_t2(const uint8_t *__restrict__ src,
         by.advance(take);
         xs[k - 1] = wrap16(v * iq[k]);
     }
-    const int x1 = xs[0], q = xs[1];
+    t2_pixels(x0, xs[0], xs[1], px);
+}
 
+/* the same block from an inline entry (rtj_common.h): coefficients already separated by K1 */
+__device__ __forceinline__ void decode_block_inline(uint32_t e, const int *__restrict__ iq, uint32_t (&px)[16])
+{
+    const int x0 = wrap16((int)(e & 0xFFu) * iq[0]) + 4;
+    const int x1 = wrap16((int)(signed char)((e >> 8) & 0xFFu) * iq[1]);
+    const int q = wrap16((int)(signed char)((e >> 16) & 0xFFu) * iq[2]);
+    t2_pixels(x0, x1, q, px);
+}
+
+/* x0 = dequantised DC + 4, x1 = zig-zag 1 (row 1, column 0), q = zig-zag 2 (row 0, column 1) */
+__device__ __forceinline__ void t2_pixels(int x0, int x1, int q, uint32_t (&px)[16])
+{
     /* pass 1, column 0: inputs (x0, x1, 0, ...): even half = x0, odd half from x1 alone */
     int A[8];
     {
@@ -654,15 +671,15 @@ rtj_idct_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc *__r
         unsigned sf = (unsigned)f;
         if (i < nb) {
             e = ent[frame_blk0 + i];
-            if ((e >> RTJ_ENT_OFF_BITS) == 0) {
+            if (RTJ_ENT_IS_SKIP(e)) {
                 const unsigned s = srcf[frame_blk0 + i];
                 if (s != RTJ_SRC_CARRY) {
                     sf = s;
                     e = ent[(size_t)s * nblk + strip_blk0 + i];
                 }
             }
-            const int eob = (int)(e >> RTJ_ENT_OFF_BITS);
-            if (eob == 0) cls = CLS_CARRY;
+            const int eob = RTJ_ENT_IS_INLINE(e) ? 3 : RTJ_ENT_EOB(e);
+            if (RTJ_ENT_IS_SKIP(e)) cls = CLS_CARRY;
             else if (sf != (unsigned)f && desc[sf].table != mytable) cls = CLS_FULLG;
             else if (eob <= 3) cls = CLS_T2;
             else if (eob <= 6) cls = CLS_T3;
@@ -671,10 +688,14 @@ rtj_idct_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc *__r
         }
         if (cls == CLS_T2) {
             const int chroma = (i % 6) >= 4;
-            const uint8_t *src = (sf == (unsigned)f ? frame_pay : stream + desc[sf].offset + RTJPEG_B200_HEADER_BYTES)
-                                 + (e & RTJ_ENT_OFF_MASK);
             uint32_t px[16];
-            decode_block_t2(src, hd->iq[chroma], chroma ? bt8_c : bt8_l, px);
+            if (RTJ_ENT_IS_INLINE(e)) {
+                decode_block_inline(e, hd->iq[chroma], px);
+            } else {
+                const uint8_t *src = (sf == (unsigned)f ? frame_pay : stream + desc[sf].offset + RTJPEG_B200_HEADER_BYTES)
+                                     + (e & RTJ_ENT_OFF_MASK);
+                decode_block_t2(src, hd->iq[chroma], chroma ? bt8_c : bt8_l, px);
+            }
             tile.store(i, px);
         }
         const unsigned deferred = __ballot_sync(FULL, cls >= 0 && cls < NDEFER);
@@ -752,8 +773,12 @@ rtj_idct_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc *__r
                                  + (e & RTJ_ENT_OFF_MASK);
             if (cls == CLS_FULLG) {
                 const rtj_dev_table *t = &tables[desc[sf].table];
-                MemBytes by(src);
-                decode_block<64>(by, t->iq[chroma], t->bt8[chroma], px);
+                if (RTJ_ENT_IS_INLINE(e)) {
+                    decode_block_inline(e, t->iq[chroma], px);
+                } else {
+                    MemBytes by(src);
+                    decode_block<64>(by, t->iq[chroma], t->bt8[chroma], px);
+                }
             } else {
                 const int *iq = hd->iq[chroma];
                 const int bt8 = chroma ? bt8_c : bt8_l;
@@ -824,24 +849,37 @@ extern "C" int rtj_kernels_init(void)
     int nstrips;
     const size_t worst = idct_smem_bytes(idct_seg_mb(IDCT_MAX_MB, &nstrips));
     cudaError_t e = cudaFuncSetAttribute(rtj_idct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)worst);
-    return e == cudaSuccess ? 0 : (int)e;
+    if (e != cudaSuccess) return (int)e;
+    return rtj_scan_chunk_init();
 }
 
 extern "C" int rtj_launch_scan(const rtj_launch_args *a, void *stream)
 {
     const int nblk = (a->w >> 4) * (a->h >> 4) * 6;
+    cudaStream_t st = (cudaStream_t)stream;
+    int launches = 0, raw_only = 0;
+    /* AUTO: the chunk-parallel kernel takes every frame without a raw prefix, the serial kernels
+     * the rest.  rtjgpu_set_scan_mode() forces one serial flavour for every frame. */
+    if (a->scan_mode == RTJGPU_SCAN_AUTO || a->scan_mode == RTJGPU_SCAN_CHUNK) {
+        int e = rtj_launch_scan_chunk(a, stream);
+        if (e) return -e;
+        launches++;
+        raw_only = 1;
+    }
     /* many frames: one lane per frame (cheap in issue slots, latency hidden by the batch);
-     * few frames: one warp per frame.  rtjgpu_set_scan_mode() forces a flavour. */
-    const bool lane = a->scan_mode ? a->scan_mode == RTJGPU_SCAN_LANE : a->F >= 512;
+     * few frames: one warp per frame. */
+    const bool lane = a->scan_mode == RTJGPU_SCAN_LANE || (a->scan_mode != RTJGPU_SCAN_WARP && a->F >= 512);
     if (lane) {
-        rtj_scan_lane_kernel<<<(a->F + 31) / 32, 32, 0, (cudaStream_t)stream>>>(
-            a->d_stream, a->d_desc, a->d_tables, a->F, nblk, a->d_ent, a->d_frame_skips, a->d_info);
+        rtj_scan_lane_kernel<<<(a->F + 31) / 32, 32, 0, st>>>(
+            a->d_stream, a->d_desc, a->d_tables, a->F, nblk, a->d_ent, a->d_frame_skips, a->d_info, raw_only);
     } else {
         const int grid = (a->F + SCAN_WARPS - 1) / SCAN_WARPS;
-        rtj_scan_warp_kernel<<<grid, SCAN_WARPS * 32, 0, (cudaStream_t)stream>>>(
-            a->d_stream, a->d_desc, a->d_tables, a->F, nblk, a->d_ent, a->d_frame_skips, a->d_info);
+        rtj_scan_warp_kernel<<<grid, SCAN_WARPS * 32, 0, st>>>(
+            a->d_stream, a->d_desc, a->d_tables, a->F, nblk, a->d_ent, a->d_frame_skips, a->d_info, raw_only);
     }
-    return (int)cudaGetLastError();
+    launches++;
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? launches : -(int)e;
 }
 
 extern "C" int rtj_launch_resolve(const rtj_launch_args *a, void *stream)

@@ -1,0 +1,307 @@
+/*
+ * rtj_scan_chunk.cu -- K1, chunk-parallel flavour: the block-offset scan of one frame
+ * spread over a whole CTA.
+ *
+ * What it replaces: the `sp += RTjpeg_s2b(...)` / `sp++` pointer chase of
+ * RTjpeg_decompressYUV420 (lib/RTjpeg.c:2701-2745) with the length rules of RTjpeg_s2b
+ * (:157-186).  Where a block starts depends on every token before it, so the reference
+ * -- and a one-thread-per-frame GPU scan -- walk the frame serially.  Here the chain is
+ * cut into independent pieces:
+ *
+ *   level 0   for EVERY byte position p of the payload: delta(p) = length of the block
+ *             that would start at p.  Purely local (<= 64 bytes ahead), one thread per
+ *             four positions, SIMD-within-a-register over four tokens at a time.
+ *   DP        the payload is cut into chunks of CS_C bytes, one lane per chunk.  Walking
+ *             the chunk right to left, E(p) = E(p + delta(p)) gives for every p the place
+ *             where a parse entering at p leaves the chunk and how many blocks it starts
+ *             on the way.  Only a 64-entry ring per chunk is live, because delta <= 64.
+ *   chain     one thread hops chunk to chunk through the rings: the true entry point
+ *             and first block index of every chunk (CS_S / CS_C dependent steps instead
+ *             of one per block).
+ *   emit      every chunk lane walks its own blocks from its now known entry point and
+ *             writes their 32-bit entries to a shared staging area that leaves as
+ *             coalesced stores.
+ *
+ * Frames of any size stream through in segments of CS_S bytes; the entry point and the
+ * block count carry from segment to segment.
+ *
+ * Scope: frames whose tables have no raw 8-bit prefix (lb8 == cb8 == 0, i.e. quality
+ * <= 170 and most custom tables).  Other frames are left to the serial kernels of
+ * rtj_kernels.cu, which run right after this one and skip what is already done.
+ */
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "rtj_common.h"
+
+namespace {
+
+constexpr int CS_THREADS = 256;
+constexpr int CS_S = 16384;                        /* segment bytes */
+constexpr int CS_C = 128;                          /* chunk bytes (>= 64, multiple of 64) */
+constexpr int CS_NCH = CS_S / CS_C;                /* chunks per segment = DP lanes */
+constexpr int CS_LA = 128;                         /* look-ahead bytes behind a segment */
+constexpr int CS_RING = 66;                        /* u16 per chunk ring: 64 live + pad to 33 words (bank skew) */
+constexpr int CS_STAGE = CS_NCH * CS_RING / 2;     /* staged entries per emit round (aliases the rings) */
+constexpr int CS_PAY_WORDS = (CS_S + CS_LA + 16) / 4;
+constexpr int CS_DEL_WORDS = CS_NCH * (CS_C / 4 + 1);   /* one pad word per chunk (bank skew) */
+
+static_assert(CS_NCH <= CS_THREADS, "one DP lane per chunk");
+static_assert((CS_C % 64) == 0 && CS_C >= 64, "ring indexing assumes chunk starts are multiples of 64");
+static_assert((CS_C << 6) + 63 <= 0xFFFF, "ring entries are 16 bit: 6 bits exit offset + block count");
+
+struct CsShared {
+    uint32_t pay[CS_PAY_WORDS];        /* payload bytes of the segment (+ look-ahead), shifted by `mis` */
+    uint32_t del[CS_DEL_WORDS];        /* delta(p), one byte per position, chunk rows padded by one word */
+    uint32_t ring[CS_STAGE];           /* u16 rings during DP/chain, staged u32 entries during emit */
+    uint32_t base[CS_NCH + 1];         /* first block index of every chunk */
+    uint16_t entq[CS_NCH];             /* entry position of every chunk, relative to the segment */
+    int entry;                         /* first block start of the next segment, relative to its first byte */
+    int nb;                            /* blocks started so far in this frame */
+    int skips;
+    int consumed;
+};
+
+/* bit 6 of every byte of the form 01xxxxxx: a run token (signed value > 63, lib/RTjpeg.c:173) */
+__device__ __forceinline__ uint32_t swar_runs(uint32_t t) { return t & ~(t >> 1) & 0x40404040u; }
+/* run length - 1 in run bytes, 0 in coefficient bytes: a token fills 1 + x positions */
+__device__ __forceinline__ uint32_t swar_x(uint32_t t) { return t & ((swar_runs(t) >> 6) * 0x3Fu); }
+
+__device__ __forceinline__ uint32_t lds_u32_unaligned(const uint32_t *w, int byte)
+{
+    const uint32_t *p = w + (byte >> 2);
+    return __funnelshift_r(p[0], p[1], (unsigned)(byte & 3) * 8);
+}
+
+/* Token count of a block whose first eight tokens (starting at shared byte `tb`) fill
+ * `filled` < 63 positions: keep going four tokens at a time.  Ends within 63 tokens
+ * because every token fills at least one position. */
+__device__ __noinline__ int cs_long_block(const uint32_t *payw, int tb, int filled)
+{
+    int need = 63 - filled, ntok = 8;
+    for (;;) {
+        const uint32_t t = lds_u32_unaligned(payw, tb + ntok);
+        const uint32_t P = swar_x(t) * 0x01010101u + 0x04030201u;
+        const uint32_t c = (P + (uint32_t)(128 - need) * 0x01010101u) & 0x80808080u;
+        if (c) return ntok + ((__ffs((int)c) - 1) >> 3) + 1;
+        need -= (int)(P >> 24);
+        ntok += 4;
+    }
+}
+
+} // namespace
+
+extern "C" __global__ void __launch_bounds__(CS_THREADS, 4)
+rtj_scan_chunk_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc *__restrict__ desc,
+                      const rtj_dev_table *__restrict__ tables, int F, int nblk,
+                      uint32_t *__restrict__ ent, uint32_t *__restrict__ frame_skips,
+                      rtj_dev_info *__restrict__ info)
+{
+    extern __shared__ __align__(16) uint8_t cs_smem[];
+    CsShared &sh = *reinterpret_cast<CsShared *>(cs_smem);
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int f = blockIdx.x;
+    if (f >= F) return;
+    const rtjgpu_frame_desc d = desc[f];
+    if (tables[d.table].bt8[0] | tables[d.table].bt8[1]) return;     /* raw prefix: the serial kernels' frame */
+
+    const uint8_t *pay = stream + d.offset + RTJPEG_B200_HEADER_BYTES;
+    const int len = d.length > RTJPEG_B200_HEADER_BYTES ? (int)d.length - RTJPEG_B200_HEADER_BYTES : 0;
+    const int mis = (int)(reinterpret_cast<uintptr_t>(pay) & 15);     /* 0, 4, 8 or 12: packets start 4-byte aligned */
+    const uint8_t *gbase = pay - mis;                                   /* 16-byte aligned, never before the packet */
+    uint32_t *out = ent + (size_t)f * nblk;
+    const uint8_t *payb = reinterpret_cast<const uint8_t *>(sh.pay) + mis;   /* payb[q] = payload byte seg0 + q */
+    const uint8_t *delb = reinterpret_cast<const uint8_t *>(sh.del);
+
+    if (tid == 0) { sh.entry = 0; sh.nb = 0; sh.skips = 0; sh.consumed = 0; }
+    __syncthreads();
+
+    for (int seg0 = 0; seg0 < len; seg0 += CS_S) {
+        const int nb0 = sh.nb;
+        if (nb0 >= nblk) break;                                        /* uniform: everybody reads the same word */
+        const int lim = len - seg0;                                    /* payload bytes from here on */
+        const int nch = min(CS_NCH, (lim + CS_C - 1) / CS_C);
+        const int npos = nch * CS_C;
+
+        /* ---- load: 16-byte vectors; beyond the payload every byte reads 0x7F, a run token that
+         *      ends any block (the packet's own bytes are never read past its last 16-byte line) ---- */
+        {
+            const uint4 *g4 = reinterpret_cast<const uint4 *>(gbase + seg0);
+            uint4 *s4 = reinterpret_cast<uint4 *>(sh.pay);
+            const int nvec = (npos + CS_LA + 16) / 16;
+            const int vlim = lim + mis;                                /* shared byte index of the payload's end */
+            for (int v = tid; v < nvec; v += CS_THREADS) {
+                const int b0 = v * 16;
+                uint4 x = make_uint4(0x7F7F7F7Fu, 0x7F7F7F7Fu, 0x7F7F7F7Fu, 0x7F7F7F7Fu);
+                if (b0 < vlim) {
+                    x = __ldg(g4 + v);
+                    if (b0 + 16 > vlim) {
+                        uint32_t w[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            const int nv = vlim - (b0 + 4 * k);
+                            const uint32_t m = nv >= 4 ? 0xFFFFFFFFu : nv <= 0 ? 0u : (1u << (8 * nv)) - 1u;
+                            w[k] = (w[k] & m) | (0x7F7F7F7Fu & ~m);
+                        }
+                        x = make_uint4(w[0], w[1], w[2], w[3]);
+                    }
+                }
+                s4[v] = x;
+            }
+        }
+        __syncthreads();
+
+        /* ---- level 0: delta(p) for every position, four positions per thread ---- */
+        for (int q0 = tid * 4; q0 < npos; q0 += CS_THREADS * 4) {
+            const uint32_t *wp = sh.pay + ((q0 + mis) >> 2);
+            const uint32_t W0 = wp[0], W1 = wp[1], W2 = wp[2];
+            const uint32_t X0 = swar_x(W0), X1 = swar_x(W1), X2 = swar_x(W2);
+            uint32_t packed = 0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                /* tokens of a block starting at q0 + i: bytes q0+i+1 .. */
+                const uint32_t x0 = i == 3 ? X1 : __funnelshift_r(X0, X1, 8 * (i + 1));
+                const uint32_t x1 = i == 3 ? X2 : __funnelshift_r(X1, X2, 8 * (i + 1));
+                /* byte k of P = positions filled by tokens 0..k; bit 7 of (P + 65) set <=> >= 63 filled.
+                 * Overflows can only happen behind the first crossing and never disturb it. */
+                const uint32_t P0 = x0 * 0x01010101u + 0x04030201u;
+                const uint32_t P1 = x1 * 0x01010101u + 0x04030201u + (P0 >> 24) * 0x01010101u;
+                const uint32_t c0 = (P0 + 0x41414141u) & 0x80808080u;
+                const uint32_t c1 = (P1 + 0x41414141u) & 0x80808080u;
+                int dl;
+                if (c0 | c1) {
+                    const int bit = c0 ? __ffs((int)c0) - 1 : 31 + __ffs((int)c1);
+                    dl = (bit >> 3) + 2;                                /* DC byte + tokens */
+                } else {
+                    dl = 1 + cs_long_block(sh.pay, q0 + mis + i + 1, (int)(P1 >> 24));
+                }
+                if (((W0 >> (8 * i)) & 0xFFu) == 0xFFu) dl = 1;         /* skipped block: one byte, lib/RTjpeg.c:2704 */
+                packed |= (uint32_t)dl << (8 * i);
+            }
+            sh.del[(q0 >> 2) + (q0 / CS_C)] = packed;
+        }
+        __syncthreads();
+
+        /* ---- DP, one lane per chunk, right to left ---- */
+        if (tid < nch) {
+            uint16_t *ring = reinterpret_cast<uint16_t *>(sh.ring) + tid * CS_RING;
+            const uint32_t *dw = sh.del + tid * (CS_C / 4 + 1);
+            const int cq = tid * CS_C, endq = cq + CS_C;
+#pragma unroll 2
+            for (int w = CS_C / 4 - 1; w >= 0; --w) {
+                const uint32_t d4 = dw[w];
+#pragma unroll
+                for (int i = 3; i >= 0; --i) {
+                    const int q = cq + 4 * w + i;
+                    const int n = q + (int)((d4 >> (8 * i)) & 0xFFu);
+                    uint32_t v = ring[n & 63];
+                    v = n >= endq ? (uint32_t)(n - endq) | 64u : v + 64u;   /* exit offset | blocks << 6 */
+                    if (q >= lim) v = 0;                                    /* nothing starts behind the payload */
+                    ring[q & 63] = (uint16_t)v;
+                }
+            }
+        }
+        __syncthreads();
+
+        /* ---- chain: entry point and first block index of every chunk ---- */
+        if (tid == 0) {
+            const uint16_t *rings = reinterpret_cast<const uint16_t *>(sh.ring);
+            int e = sh.entry, nb = nb0;
+            for (int j = 0; j < nch; j++) {
+                sh.entq[j] = (uint16_t)(j * CS_C + e);
+                sh.base[j] = (uint32_t)nb;
+                const uint32_t v = rings[j * CS_RING + e];
+                e = (int)(v & 63u);
+                nb += (int)(v >> 6);
+            }
+            sh.base[nch] = (uint32_t)nb;
+            sh.entry = e;
+            sh.nb = nb;
+        }
+        __syncthreads();
+
+        /* ---- emit ---- */
+        const int nb1 = min(sh.nb, nblk);
+        int q = 0, i = 0, qend = 0, myskips = 0, lastend = -1;
+        if (tid < nch) {
+            q = sh.entq[tid];
+            i = (int)sh.base[tid];
+            qend = min((tid + 1) * CS_C, lim);
+        }
+        __syncthreads();                                   /* the rings are dead: their memory stages the entries */
+        for (int r0 = nb0; r0 < nb1; r0 += CS_STAGE) {
+            const int r1 = min(r0 + CS_STAGE, nb1);
+            if (tid < nch) {
+                while (q < qend && i < r1) {
+                    const int dl = delb[q + ((q / CS_C) << 2)];
+                    const uint32_t head = lds_u32_unaligned(sh.pay, q + mis);       /* DC, token 1, token 2, token 3 */
+                    const uint32_t last = payb[q + dl - 1];
+                    uint32_t e;
+                    if ((head & 0xFFu) == 0xFFu) {
+                        e = RTJ_ENT_SKIP;
+                        myskips++;
+                    } else {
+                        /* positions >= eob are zero: a final run of n zeros ends at 64, so it starts at 64 - n */
+                        int eob = (last - 64u) < 64u ? max(127 - (int)last, dl - 1) : 64;
+                        if (eob <= 3) {
+                            const uint32_t t1 = (head >> 8) & 0xFFu, t2 = (head >> 16) & 0xFFu;
+                            const uint32_t c1 = (eob >= 2 && (t1 - 64u) >= 64u) ? t1 : 0u;
+                            const uint32_t c2 = (eob >= 3 && (t2 - 64u) >= 64u) ? t2 : 0u;
+                            e = RTJ_ENT_INLINE(head, c1, c2);
+                        } else {
+                            e = RTJ_ENT(seg0 + q, eob);
+                        }
+                    }
+                    sh.ring[i - r0] = e;
+                    q += dl;
+                    i++;
+                    lastend = seg0 + q;
+                }
+            }
+            __syncthreads();
+            for (int k = tid; k < r1 - r0; k += CS_THREADS) out[r0 + k] = sh.ring[k];
+            __syncthreads();
+        }
+        if (tid < CS_NCH) {                                 /* whole warps: CS_NCH is a multiple of 32 */
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                myskips += __shfl_xor_sync(0xFFFFFFFFu, myskips, o);
+                lastend = max(lastend, __shfl_xor_sync(0xFFFFFFFFu, lastend, o));
+            }
+            if (lane == 0) {
+                if (myskips) atomicAdd(&sh.skips, myskips);
+                if (lastend >= 0) atomicMax(&sh.consumed, lastend);
+            }
+        }
+        __syncthreads();
+    }
+
+    /* a frame whose stream ends early or mid-block: flag it, give the missing blocks a harmless entry */
+    const int nbf = min(sh.nb, nblk);
+    for (int b = nbf + tid; b < nblk; b += CS_THREADS) out[b] = RTJ_ENT(min(len, (int)RTJ_ENT_OFF_MASK), 1);
+    if (tid == 0) {
+        const int consumed = sh.consumed, skips = sh.skips;
+        frame_skips[f] = (uint32_t)skips;
+        if (skips) atomicAdd(&info->skipped_blocks, (unsigned long long)skips);
+        atomicAdd(&info->payload_bytes, (unsigned long long)min(consumed, len));
+        if (nbf < nblk || consumed > len || len > (int)RTJGPU_MAX_PAYLOAD_BYTES) {
+            atomicAdd(&info->bad_frames, 1u);
+            atomicMin((unsigned int *)&info->first_bad_frame, (unsigned int)f);
+        }
+    }
+}
+
+extern "C" int rtj_scan_chunk_init(void)
+{
+    cudaError_t e = cudaFuncSetAttribute(rtj_scan_chunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)sizeof(CsShared));
+    return e == cudaSuccess ? 0 : (int)e;
+}
+
+extern "C" int rtj_launch_scan_chunk(const rtj_launch_args *a, void *stream)
+{
+    const int nblk = (a->w >> 4) * (a->h >> 4) * 6;
+    rtj_scan_chunk_kernel<<<a->F, CS_THREADS, sizeof(CsShared), (cudaStream_t)stream>>>(
+        a->d_stream, a->d_desc, a->d_tables, a->F, nblk, a->d_ent, a->d_frame_skips, a->d_info);
+    return (int)cudaGetLastError();
+}

@@ -215,7 +215,7 @@ int RTjpeg_b200_decompress_n(RTjpeg_t *rtj, const uint8_t *sp, size_t len, uint8
         if ((rc = rtjgpu_get_entries(in->ctx, in->entries.data(), (size_t)nblk))) return fail(in, rc);
         const int mbw = w >> 4, cw = w >> 1;
         for (int b = 0; b < nblk; b++) {
-            if ((in->entries[(size_t)b] >> RTJ_ENT_OFF_BITS) == 0) continue;
+            if (RTJ_ENT_IS_SKIP(in->entries[(size_t)b])) continue;
             const int mb = b / 6, sub = b - mb * 6;
             const int my = mb / mbw, mx = mb - my * mbw;
             if (sub < 4) {

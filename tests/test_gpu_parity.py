@@ -15,11 +15,12 @@ from streams import clip, golden, interleave, reference_frames
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module", params=["lane", "warp"])
+@pytest.fixture(scope="module", params=["auto", "lane", "warp"])
 def ctx(request):
-    """Every parity case runs under both flavours of the block-offset scan (K1)."""
+    """Every parity case runs under all flavours of the block-offset scan (K1): the default
+    (chunk-parallel kernel + serial kernel for raw-prefix frames) and each serial kernel alone."""
     c = g.BatchContext(0)
-    c.set_scan_mode(capi.SCAN_LANE if request.param == "lane" else capi.SCAN_WARP)
+    c.set_scan_mode({"auto": capi.SCAN_AUTO, "lane": capi.SCAN_LANE, "warp": capi.SCAN_WARP}[request.param])
     c.flavour = request.param
     yield c
     c.close()
@@ -147,11 +148,53 @@ def test_scan_entries_match_oracle_walker(ctx):
     for f in range(6):
         n, offs, eob = O.walk_payload(s[int(o[f]) + 12:int(o[f]) + int(sizes[f])], nblk // 6, t.lb8, t.cb8)
         coded = eob > 0
-        assert ((ent[f] >> 25 == 0) == ~coded).all()
+        assert ((ent[f] == 0xFFFFFFFF) == ~coded).all()
+        assert (ent[f][coded] >> 31 == 0).all()           # Q=200 has a raw prefix: no inline entries
         assert ((ent[f] & 0x1FFFFFF)[coded] == offs[coded]).all()
         # the kernel's bound may exceed the exact end-of-block, never undercut it
-        assert ((ent[f] >> 25)[coded] >= eob[coded]).all()
-        assert ((ent[f] >> 25)[coded] == eob[coded]).mean() > 0.99
+        keob = ((ent[f] >> 25) & 63) + 1
+        assert (keob[coded] >= eob[coded]).all()
+        assert (keob[coded] == eob[coded]).mean() > 0.99
+
+
+def test_scan_entries_inline_format(ctx):
+    """Frames without a raw prefix: the chunk-parallel scan carries blocks with an end-of-block
+    bound <= 3 inside the entry (DC and two coefficients), the rest by offset."""
+    if ctx.flavour != "auto":
+        pytest.skip("inline entries come from the chunk-parallel scan")
+    s, o = clip(208, 112, 128, 4, key_rate=1, lm=2, cm=2, noise_y=12, noise_c=3)
+    w, h = 208, 112
+    nblk = (w // 16) * (h // 16) * 6
+    gpu_decode(ctx, s, o, w, h)
+    L = g.load_library()
+    ent = np.zeros(4 * nblk, dtype=np.uint32)
+    L.rtjgpu_get_entries.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    assert L.rtjgpu_get_entries(ctx._h, C.c_void_p(ent.ctypes.data), ent.size) == 0
+    ent = ent.reshape(4, nblk)
+    sizes = O.packet_sizes(s, o)
+    seen_inline = seen_general = 0
+    for f in range(4):
+        pay = s[int(o[f]) + 12:int(o[f]) + int(sizes[f])]
+        n, offs, eob = O.walk_payload(pay, nblk // 6, 0, 0)
+        for b in range(nblk):
+            e = int(ent[f, b])
+            if eob[b] == 0:
+                assert e == 0xFFFFFFFF
+            elif e >> 31:
+                assert eob[b] <= 3 and (e >> 24) == 0x80
+                p = int(offs[b])
+                assert (e & 0xFF) == pay[p]
+                want = [0, 0]
+                if eob[b] >= 2:
+                    want[0] = int(pay[p + 1]) if not 64 <= pay[p + 1] < 128 else 0
+                if eob[b] >= 3:
+                    want[1] = int(pay[p + 2]) if not 64 <= pay[p + 2] < 128 else 0
+                assert ((e >> 8) & 0xFF, (e >> 16) & 0xFF) == tuple(want)
+                seen_inline += 1
+            else:
+                assert (e & 0x1FFFFFF) == offs[b] and ((e >> 25) & 63) + 1 >= max(int(eob[b]), 4)
+                seen_general += 1
+    assert seen_inline and seen_general
 
 
 def test_edge_geometries(ctx):
@@ -215,7 +258,7 @@ def test_full_size_config2_4096_frames(ctx):
     (threaded across the host's cores), plus the determinism property: decoding the same
     batch twice gives identical bytes."""
     import os
-    if ctx.flavour == "warp":
+    if ctx.flavour != "auto":
         pytest.skip("full-size batch runs once, under the automatic flavour")
     ctx.set_scan_mode(capi.SCAN_AUTO)
     w, h, F = 720, 576, 4096

@@ -23,6 +23,7 @@ namespace {
 struct Workspace {
     uint32_t     *d_ent = nullptr;
     uint16_t     *d_src = nullptr;
+    uint32_t     *d_hardq = nullptr;
     uint32_t     *d_frame_skips = nullptr;
     rtj_dev_info *d_info = nullptr;
     size_t        cap_entries = 0;
@@ -90,9 +91,11 @@ int ws_reserve(rtjgpu_ctx *ctx, Workspace *ws, int F, int nblk)
     if (need > ws->cap_entries) {
         if (ws->d_ent) cudaFree(ws->d_ent);
         if (ws->d_src) cudaFree(ws->d_src);
-        ws->d_ent = nullptr; ws->d_src = nullptr; ws->cap_entries = 0;
+        if (ws->d_hardq) cudaFree(ws->d_hardq);
+        ws->d_ent = nullptr; ws->d_src = nullptr; ws->d_hardq = nullptr; ws->cap_entries = 0;
         CK(ctx, cudaMalloc(&ws->d_ent, need * sizeof(uint32_t)));
         CK(ctx, cudaMalloc(&ws->d_src, need * sizeof(uint16_t)));
+        CK(ctx, cudaMalloc(&ws->d_hardq, need * sizeof(uint32_t)));
         ws->cap_entries = need;
     }
     if (F > ws->cap_frames) {
@@ -109,6 +112,7 @@ void ws_release(Workspace *ws)
 {
     if (ws->d_ent) cudaFree(ws->d_ent);
     if (ws->d_src) cudaFree(ws->d_src);
+    if (ws->d_hardq) cudaFree(ws->d_hardq);
     if (ws->d_frame_skips) cudaFree(ws->d_frame_skips);
     if (ws->d_info) cudaFree(ws->d_info);
     *ws = Workspace();
@@ -122,6 +126,7 @@ int run_kernels(rtjgpu_ctx *ctx, Workspace *ws, const uint8_t *d_stream, const r
     a.d_stream = d_stream; a.d_desc = d_desc; a.d_tables = ctx->d_tables;
     a.F = F; a.w = w; a.h = h;
     a.d_ent = ws->d_ent; a.d_src = ws->d_src; a.d_frame_skips = ws->d_frame_skips; a.d_info = ws->d_info;
+    a.d_hardq = ws->d_hardq;
     a.d_out = d_out; a.d_carry = d_carry;
     a.scan_mode = ctx->scan_mode;
 
@@ -137,7 +142,7 @@ int run_kernels(rtjgpu_ctx *ctx, Workspace *ws, const uint8_t *d_stream, const r
     e = rtj_launch_idct(&a, st);
     if (e) { ctx->last_cuda = e; return RTJGPU_E_CUDA; }
     if (ev) CK(ctx, cudaEventRecord(ev[3], st));
-    ctx->launches += 2;
+    ctx->launches += 3;                     /* K3, K2, K2b */
     return RTJGPU_OK;
 }
 
@@ -337,6 +342,7 @@ int rtjgpu_decode_device(rtjgpu_ctx *ctx, const uint8_t *d_stream, const rtjgpu_
     if (F > RTJGPU_MAX_FRAMES_PER_BATCH) return RTJGPU_E_TOOBIG;
     CK(ctx, cudaSetDevice(ctx->device));
     const int nblk = (w >> 4) * (h >> 4) * 6;
+    if ((uint64_t)F * (uint64_t)nblk >= (1ull << 32)) return RTJGPU_E_TOOBIG;   /* block indices are 32 bit */
     int rc = ws_reserve(ctx, &ctx->ws, F, nblk);
     if (rc) return rc;
     cudaEvent_t *ev = ctx->timing ? ctx->ev[ctx->timed_calls % TIMING_RING] : nullptr;

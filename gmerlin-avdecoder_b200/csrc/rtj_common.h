@@ -66,6 +66,8 @@ typedef struct rtj_dev_info {
     unsigned long long payload_bytes;
     unsigned int       bad_frames;
     int                first_bad_frame;
+    unsigned int       hard_blocks;      /* length of the K2 -> K2b queue */
+    unsigned int       pad;
 } rtj_dev_info;
 
 /* ---- kernel launchers (rtj_kernels.cu); stream is a cudaStream_t ----------- */
@@ -78,6 +80,7 @@ typedef struct rtj_launch_args {
     uint16_t                *d_src;         /* [F][nblk] */
     uint32_t                *d_frame_skips; /* [F] */
     rtj_dev_info            *d_info;
+    uint32_t                *d_hardq;       /* [F * nblk] global block indices queued for K2b */
     uint8_t                 *d_out;
     const uint8_t           *d_carry;
     int                      scan_mode;     /* RTJGPU_SCAN_* */
@@ -88,6 +91,7 @@ int rtj_launch_scan_chunk(const rtj_launch_args *a, void *stream);    /* rtj_sca
 int rtj_scan_chunk_init(void);
 int rtj_launch_resolve(const rtj_launch_args *a, void *stream);
 int rtj_launch_idct(const rtj_launch_args *a, void *stream);
+int rtj_idct_init(void);      /* rtj_idct.cu */
 int rtj_kernels_init(void);   /* one-time function attributes (dynamic shared memory opt-in) */
 
 #ifdef __cplusplus

@@ -1,0 +1,715 @@
+/*
+ * rtj_idct.cu -- K2 of the RTjpeg YUV420 decoder: unpack + dequantise + integer AAN IDCT +
+ * clamp + planar store, for sm_100a.
+ *
+ *   rtj_idct_kernel       one CTA per (frame, macroblock row [, strip]).  Replaces the value
+ *                         path of RTjpeg_s2b (lib/RTjpeg.c:162-183), RTjpeg_idct (:2209-2332)
+ *                         and the destination arithmetic of RTjpeg_decompressYUV420
+ *                         (:2690-2744).  The strip's blocks are renumbered so that a warp
+ *                         owns 32 horizontally adjacent 8x8 blocks (conflict-free shared
+ *                         stores); the picture strip leaves the SM as TMA bulk stores.
+ *                         Blocks are handled by sparsity class:
+ *                           T2     E <= 3 (DC + zig-zag 1, 2): decoded right away, two pixels
+ *                                  per instruction in packed 16-bit arithmetic
+ *                           M7     E <= 7 (adds (0,2), (1,1), (2,0), (3,0)): deferred, decoded
+ *                                  in class-homogeneous groups of 32
+ *                           CARRY  skipped and never written in this batch: copied from the
+ *                                  picture that precedes the batch
+ *                           HARD   everything else (long blocks, blocks whose last writer
+ *                                  used other tables): queued in device memory for ...
+ *   rtj_idct_hard_kernel  ... the general decoder, one thread per queued block, which patches
+ *                         its 8x8 pixels straight into the output frames afterwards.
+ *
+ * All arithmetic is integer and bit-exact with the reference.  The packed 16-bit epilogues
+ * are used only where a bound on the block's coefficients proves that no pixel leaves
+ * 16..235 and nothing overflows 16 bits; otherwise the same block takes the reference's
+ * 32-bit DESCALE / clamp sequence.
+ */
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "rtj_common.h"
+
+namespace {
+
+constexpr unsigned FULL = 0xFFFFFFFFu;
+
+/* MULTIPLY of the reference (lib/RTjpeg.c:1206): 8 fractional bits, +128, arithmetic shift. */
+__device__ __forceinline__ int fxmul(int v, int c) { return (v * c + 128) >> 8; }
+
+/* low 16 bits, sign-extended: the `int16_t` stores of RTjpeg_s2b and DESCALE */
+__device__ __forceinline__ int wrap16(int v) { return (int)(short)v; }
+
+/* 8-point AAN flow graph shared by both passes (lib/RTjpeg.c:2240-2283, :2289-2326).
+ * Inputs that are literal zeros fold away at compile time: fxmul(0, c) == 0. */
+__device__ __forceinline__ void aan8(int x0, int x1, int x2, int x3, int x4, int x5, int x6, int x7,
+                                     int (&y)[8])
+{
+    const int s04 = x0 + x4, d04 = x0 - x4;
+    const int s26 = x2 + x6;
+    const int m26 = fxmul(x2 - x6, 362) - s26;
+    const int e0 = s04 + s26, e3 = s04 - s26, e1 = d04 + m26, e2 = d04 - m26;
+
+    const int z13 = x5 + x3, z10 = x5 - x3, z11 = x1 + x7, z12 = x1 - x7;
+    const int o7 = z11 + z13;
+    const int o11 = fxmul(z11 - z13, 362);
+    const int z5 = fxmul(z10 + z12, 473);
+    const int o10 = fxmul(z12, 277) - z5;
+    const int o12 = fxmul(z10, -669) + z5;
+    const int o6 = o12 - o7;
+    const int o5 = o11 - o6;
+    const int o4 = o10 + o5;
+
+    y[0] = e0 + o7; y[7] = e0 - o7;
+    y[1] = e1 + o6; y[6] = e1 - o6;
+    y[2] = e2 + o5; y[5] = e2 - o5;
+    y[4] = e3 + o4; y[3] = e3 - o4;
+}
+
+/* Four row outputs (already carrying the +4 rounding term) -> four clamped bytes.
+ * DESCALE (lib/RTjpeg.c:1200) narrows to int16 before RL (:1204) clamps to 16..235;
+ * packing the low halves reproduces that narrowing exactly. */
+__device__ __forceinline__ uint32_t descale_pack4(int y0, int y1, int y2, int y3)
+{
+    uint32_t a = __byte_perm((uint32_t)(y0 >> 3), (uint32_t)(y1 >> 3), 0x5410);
+    uint32_t b = __byte_perm((uint32_t)(y2 >> 3), (uint32_t)(y3 >> 3), 0x5410);
+    a = __vmaxs2(__vmins2(a, 0x00EB00EBu), 0x00100010u);
+    b = __vmaxs2(__vmins2(b, 0x00EB00EBu), 0x00100010u);
+    return __byte_perm(a, b, 0x6420);
+}
+
+/* zig-zag position k sits at (row, col): lib/RTjpeg.c:59-74 */
+#define RTJ_ZZ_LIST(X) \
+    X(0,0,0) X(1,1,0) X(2,0,1) X(3,0,2) X(4,1,1) X(5,2,0) X(6,3,0) X(7,2,1) \
+    X(8,1,2) X(9,0,3) X(10,0,4) X(11,1,3) X(12,2,2) X(13,3,1) X(14,4,0) X(15,5,0) \
+    X(16,4,1) X(17,3,2) X(18,2,3) X(19,1,4) X(20,0,5) X(21,0,6) X(22,1,5) X(23,2,4) \
+    X(24,3,3) X(25,4,2) X(26,5,1) X(27,6,0) X(28,7,0) X(29,6,1) X(30,5,2) X(31,4,3) \
+    X(32,3,4) X(33,2,5) X(34,1,6) X(35,0,7) X(36,1,7) X(37,2,6) X(38,3,5) X(39,4,4) \
+    X(40,5,3) X(41,6,2) X(42,7,1) X(43,7,2) X(44,6,3) X(45,5,4) X(46,4,5) X(47,3,6) \
+    X(48,2,7) X(49,3,7) X(50,4,6) X(51,5,5) X(52,6,4) X(53,7,3) X(54,7,4) X(55,6,5) \
+    X(56,5,6) X(57,4,7) X(58,5,7) X(59,6,6) X(60,7,5) X(61,7,6) X(62,6,7) X(63,7,7)
+
+/*
+ * Byte source of one block for the sparse classes: the first 4*NW bytes sit in
+ * registers (aligned 32-bit loads, funnel-shifted to the block's byte offset) and
+ * leave through the low byte, so the token walk issues no dependent loads.
+ */
+template <int NW>
+struct RegBytes {
+    uint32_t u[NW];
+    __device__ __forceinline__ explicit RegBytes(const uint8_t *__restrict__ src)
+    {
+        const uintptr_t a = reinterpret_cast<uintptr_t>(src);
+        const uint32_t *wp = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
+        const unsigned sh = (unsigned)(a & 3) * 8;
+        uint32_t w[NW + 1];
+#pragma unroll
+        for (int i = 0; i <= NW; i++) w[i] = __ldg(wp + i);      /* independent loads; slack bytes follow the stream */
+#pragma unroll
+        for (int i = 0; i < NW; i++) u[i] = __funnelshift_r(w[i], w[i + 1], sh);
+    }
+    __device__ __forceinline__ int peek_u8() const { return (int)(u[0] & 0xFFu); }
+    __device__ __forceinline__ int peek_s8() const { return (int)(signed char)(u[0] & 0xFFu); }
+    __device__ __forceinline__ void advance(bool take)
+    {
+        const unsigned sh = take ? 8u : 0u;
+#pragma unroll
+        for (int i = 0; i < NW - 1; i++) u[i] = __funnelshift_r(u[i], u[i + 1], sh);
+        u[NW - 1] >>= sh;
+    }
+};
+
+/* Byte source for dense blocks: straight from global memory, one byte at a time. */
+struct MemBytes {
+    const uint8_t *q;
+    __device__ __forceinline__ explicit MemBytes(const uint8_t *__restrict__ src) : q(src) {}
+    __device__ __forceinline__ int peek_u8() const { return (int)__ldg(q); }
+    __device__ __forceinline__ int peek_s8() const { return (int)(signed char)__ldg(q); }
+    __device__ __forceinline__ void advance(bool take) { q += take ? 1 : 0; }
+};
+
+/* Coefficients 0..K-1 of one block, dequantised (lib/RTjpeg.c:162-183): x[0] is the DC term
+ * (unsigned byte) with DESCALE's +4 rounding term folded in -- it reaches every output
+ * unchanged because the DC path has no multiply -- x[k] the k-th zig-zag coefficient.
+ * iq holds the multipliers in zig-zag order, bt8 is the raw-prefix length. */
+template <int K, typename Bytes, typename IQ>
+__device__ __forceinline__ void unpack_block(Bytes &by, IQ iq, int bt8, int (&x)[K])
+{
+    x[0] = wrap16(by.peek_u8() * iq[0]) + 4;
+    by.advance(true);
+    int z = 0;          /* zero positions still owed by the last run token */
+#pragma unroll
+    for (int k = 1; k < K; k++) {
+        const bool take = z == 0;
+        const int bb = by.peek_s8();
+        const bool run = take && k > bt8 && bb > 63;
+        const int v = (take && !run) ? bb : 0;
+        z = take ? (run ? bb - 64 : 0) : z - 1;
+        by.advance(take);
+        x[k] = wrap16(v * iq[k]);
+    }
+}
+
+/* General 8x8 inverse transform of a block whose zig-zag positions >= K are zero:
+ * the reference's two passes with its DESCALE / clamp epilogue. */
+template <int K>
+__device__ __forceinline__ void idct_general(const int (&x)[K], uint32_t (&px)[16])
+{
+    int m[8][8];
+#pragma unroll
+    for (int r = 0; r < 8; r++)
+#pragma unroll
+        for (int c = 0; c < 8; c++) m[r][c] = 0;
+#define RTJ_PUT(k, r, c) if ((k) < K) m[r][c] = x[(k) < K ? (k) : 0];
+    RTJ_ZZ_LIST(RTJ_PUT)
+#undef RTJ_PUT
+
+    /* pass 1: columns (lib/RTjpeg.c:2221-2285) */
+    int ws[8][8];
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+        int y[8];
+        aan8(m[0][c], m[1][c], m[2][c], m[3][c], m[4][c], m[5][c], m[6][c], m[7][c], y);
+#pragma unroll
+        for (int r = 0; r < 8; r++) ws[r][c] = y[r];
+    }
+    /* pass 2: rows, descale, clamp (lib/RTjpeg.c:2287-2330) */
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        int y[8];
+        aan8(ws[r][0], ws[r][1], ws[r][2], ws[r][3], ws[r][4], ws[r][5], ws[r][6], ws[r][7], y);
+        px[2 * r] = descale_pack4(y[0], y[1], y[2], y[3]);
+        px[2 * r + 1] = descale_pack4(y[4], y[5], y[6], y[7]);
+    }
+}
+
+/* odd half of the flow graph when x1 is its only input: (o7, o6, o5, o4) */
+__device__ __forceinline__ void odd_from_x1(int x1, int &o7, int &o6, int &o5, int &o4)
+{
+    const int z5 = fxmul(x1, 473);
+    o7 = x1;
+    o6 = z5 - x1;                       /* o12 = fxmul(0, -669) + z5 = z5 */
+    o5 = fxmul(x1, 362) - o6;
+    o4 = fxmul(x1, 277) - z5 + o5;
+}
+
+/* (v << 5) of two values side by side in 16-bit halves, modulo 2^16 each */
+__device__ __forceinline__ uint32_t pack_scaled(int lo, int hi)
+{
+    return __byte_perm((uint32_t)lo << 5, (uint32_t)hi << 5, 0x5410);
+}
+
+/* Packed epilogue arithmetic.  A pixel is (y >> 3) with y = a + d known to lie in 128..1887
+ * (so neither clamp acts and DESCALE's int16 narrowing is the identity).  Halves hold
+ * (value << 5) modulo 2^16: the pixel is then the upper BYTE of its half.  The non-negative
+ * term carries a guard of 16 below the binary point, so the +-1 that a carry or borrow out of
+ * the low half leaks into the high half never reaches bit 5.  One 32-bit add or subtract
+ * makes two pixels, one PRMT gathers four. */
+constexpr uint32_t PK_DUP = 0x00200020u;    /* v * PK_DUP = (v << 5) in both halves, 0 <= v < 2048 */
+constexpr uint32_t PK_GUARD = 0x00100010u;
+
+/*
+ * T2: at most DC, zig-zag 1 (row 1, column 0) and zig-zag 2 (row 0, column 1).  Column 1 of
+ * the first pass is constant down the rows, so the odd half of every ROW pass is the same
+ * eight values D[j] and pixel (r, j) = A[r] + D[j], A = the column-0 pass.
+ * x0 = dequantised DC + 4, x1 = zig-zag 1, q = zig-zag 2.
+ */
+__device__ __forceinline__ bool t2_safe(int x0, int x1, int q)
+{
+    /* |A[r] - x0| <= |x1| + 3 and |D[j]| <= |q| + 3: every odd term is below its input in magnitude */
+    const int spread = abs(x1) + abs(q) + 6;
+    return x0 - spread >= 128 && x0 + spread <= 1887;
+}
+
+__device__ __forceinline__ void t2_pixels(int x0, int x1, int q, bool packed, uint32_t (&px)[16])
+{
+    int a7, a6, a5, a4, d7, d6, d5, d4;
+    odd_from_x1(x1, a7, a6, a5, a4);
+    odd_from_x1(q, d7, d6, d5, d4);
+    /* A[0]=x0+a7 A[7]=x0-a7 A[1]=x0+a6 A[6]=x0-a6 A[2]=x0+a5 A[5]=x0-a5 A[4]=x0+a4 A[3]=x0-a4;
+     * D[0]=d7 D[7]=-d7 D[1]=d6 D[6]=-d6 D[2]=d5 D[5]=-d5 D[4]=d4 D[3]=-d4 */
+    const int A[8] = {x0 + a7, x0 + a6, x0 + a5, x0 - a4, x0 + a4, x0 - a5, x0 - a6, x0 - a7};
+    if (packed) {
+        const uint32_t d01 = pack_scaled(d7, d6);         /* (D0, D1) */
+        const uint32_t d23 = pack_scaled(d5, -d4);        /* (D2, D3) */
+        const uint32_t d32 = __byte_perm(d23, 0u, 0x1032);   /* (D3, D2): (D4, D5) = -(D3, D2) */
+        const uint32_t d10 = __byte_perm(d01, 0u, 0x1032);   /* (D1, D0): (D6, D7) = -(D1, D0) */
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            const uint32_t a2 = (uint32_t)A[r] * PK_DUP + PK_GUARD;
+            px[2 * r] = __byte_perm(a2 + d01, a2 + d23, 0x7531);
+            px[2 * r + 1] = __byte_perm(a2 - d32, a2 - d10, 0x7531);
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            px[2 * r] = descale_pack4(A[r] + d7, A[r] + d6, A[r] + d5, A[r] - d4);
+            px[2 * r + 1] = descale_pack4(A[r] + d4, A[r] - d5, A[r] - d6, A[r] - d7);
+        }
+    }
+}
+
+/*
+ * M7: zig-zag positions 0..6 = (0,0) (1,0) (0,1) (0,2) (1,1) (2,0) (3,0).  Column 0 has four
+ * inputs, column 1 two, column 2 is constant (x[3] in every row).  In the row pass the even
+ * half is then w0[r] plus one of four constants and the odd half depends on w1[r] alone.
+ */
+__device__ __forceinline__ bool m7_safe(const int (&x)[7])
+{
+    /* every pixel stays within x[0] +- spread: |odd terms| <= |x1| + 1.18 |x3| + 3, even terms within
+     * |x2| + 1 of x0 (the gains of the flow graph), applied to both passes */
+    const int spread = abs(x[1]) + abs(x[5]) + abs(x[6]) + (abs(x[6]) >> 2) + abs(x[2]) + abs(x[4]) + abs(x[3]) + 16;
+    return x[0] - spread >= 128 && x[0] + spread <= 1887;
+}
+
+__device__ __forceinline__ void m7_pixels(const int (&x)[7], bool packed, uint32_t (&px)[16])
+{
+    /* pass 1, column 0: inputs rows 0..3 = x0 x1 x5 x6 */
+    int w0[8];
+    {
+        const int x0 = x[0], x1 = x[1], x2 = x[5], x3 = x[6];
+        const int t12 = fxmul(x2, 362) - x2;
+        const int e0 = x0 + x2, e3 = x0 - x2, e1 = x0 + t12, e2 = x0 - t12;
+        const int o7 = x1 + x3;
+        const int d13 = x1 - x3;
+        const int o11 = fxmul(d13, 362);
+        const int z5 = fxmul(d13, 473);
+        const int o10 = fxmul(x1, 277) - z5;
+        const int o12 = fxmul(-x3, -669) + z5;
+        const int o6 = o12 - o7, o5 = o11 - o6, o4 = o10 + o5;
+        w0[0] = e0 + o7; w0[7] = e0 - o7; w0[1] = e1 + o6; w0[6] = e1 - o6;
+        w0[2] = e2 + o5; w0[5] = e2 - o5; w0[4] = e3 + o4; w0[3] = e3 - o4;
+    }
+    /* pass 1, column 1: inputs rows 0, 1 = x2 x4 */
+    int w1[8];
+    {
+        int o7, o6, o5, o4;
+        odd_from_x1(x[4], o7, o6, o5, o4);
+        const int x0 = x[2];
+        w1[0] = x0 + o7; w1[7] = x0 - o7; w1[1] = x0 + o6; w1[6] = x0 - o6;
+        w1[2] = x0 + o5; w1[5] = x0 - o5; w1[4] = x0 + o4; w1[3] = x0 - o4;
+    }
+    /* pass 2: even half = w0[r] + {+c2, +t12, -t12, -c2}, odd half from w1[r] */
+    const int c2 = x[3];
+    const int t12 = fxmul(c2, 362) - c2;
+    if (packed) {
+        const uint32_t ce01 = pack_scaled(c2, t12);
+        const uint32_t ce23 = pack_scaled(-t12, -c2);
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            int o7, o6, o5, o4;
+            odd_from_x1(w1[r], o7, o6, o5, o4);
+            const uint32_t a2 = (uint32_t)w0[r] * PK_DUP + PK_GUARD;
+            const uint32_t e01 = a2 + ce01, e23 = a2 + ce23;          /* (e0, e1), (e2, e3): non-negative halves */
+            const uint32_t o76 = pack_scaled(o7, o6), o5m4 = pack_scaled(o5, -o4);
+            px[2 * r] = __byte_perm(e01 + o76, e23 + o5m4, 0x7531);      /* y0 y1 y2 y3 */
+            px[2 * r + 1] = __byte_perm(e23 - o5m4, e01 - o76, 0x5713);  /* y4 y5 y6 y7 */
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            int o7, o6, o5, o4;
+            odd_from_x1(w1[r], o7, o6, o5, o4);
+            const int e0 = w0[r] + c2, e1 = w0[r] + t12, e2 = w0[r] - t12, e3 = w0[r] - c2;
+            px[2 * r] = descale_pack4(e0 + o7, e1 + o6, e2 + o5, e3 - o4);
+            px[2 * r + 1] = descale_pack4(e3 + o4, e2 - o5, e1 - o6, e0 - o7);
+        }
+    }
+}
+
+constexpr int IDCT_MAX_MB = 128;     /* macroblocks per CTA strip */
+constexpr int IDCT_THREADS = 128;
+
+enum { Q_M7 = 0, Q_CARRY, Q_HARD, NQ, CLS_T2 = NQ, CLS_NONE = -1 };
+
+struct IdctSmemHeader {
+    int iq[2][64];
+    int cnt[NQ];
+    int next_chunk;
+};
+
+__device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, unsigned bytes)
+{
+    /* TMA 1-D bulk copy shared -> global (UBLKCP) */
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 :: "l"(gdst), "r"((unsigned)__cvta_generic_to_shared(ssrc)), "r"(bytes) : "memory");
+}
+
+/*
+ * Strip geometry.  A strip of `mbs` macroblocks holds 6*mbs blocks; stream order is
+ * i = 6*mb + sub (Y00 Y01 Y10 Y11 U V, lib/RTjpeg.c:2704-2739).  The kernel works in
+ * "picture order" p: [0, 2mbs) upper luma block row left to right, [2mbs, 4mbs) lower
+ * luma block row, [4mbs, 5mbs) U, [5mbs, 6mbs) V -- so consecutive p are horizontally
+ * adjacent 8-byte runs of the shared picture strip.
+ */
+struct StripGeom {
+    int mbs, segW, segC;
+    uint8_t *tileY, *tileU;          /* tileV = tileU + 8 * segC */
+    __device__ __forceinline__ int pic_of_stream(int i) const
+    {
+        const int mb = i / 6, sub = i - mb * 6;
+        return sub < 4 ? (sub >> 1) * 2 * mbs + 2 * mb + (sub & 1) : (sub - 4 + 4) * mbs + mb;
+    }
+    __device__ __forceinline__ int stream_of_pic(int p) const
+    {
+        if (p < 4 * mbs) {
+            const int hi = p >= 2 * mbs, c = p - hi * 2 * mbs;
+            return 6 * (c >> 1) + 2 * hi + (c & 1);
+        }
+        const int pc = p - 4 * mbs, hi = pc >= mbs;
+        return 6 * (pc - hi * mbs) + 4 + hi;
+    }
+    __device__ __forceinline__ uint8_t *dst_of_pic(int p, int &pitch) const
+    {
+        if (p < 4 * mbs) {
+            const int hi = p >= 2 * mbs, c = p - hi * 2 * mbs;
+            pitch = segW;
+            return tileY + hi * 8 * segW + c * 8;
+        }
+        const int pc = p - 4 * mbs, hi = pc >= mbs;
+        pitch = segC;
+        return tileU + hi * 8 * segC + (pc - hi * mbs) * 8;
+    }
+    __device__ __forceinline__ void store(int p, const uint32_t (&px)[16]) const
+    {
+        int pitch;
+        uint8_t *dst = dst_of_pic(p, pitch);
+#pragma unroll
+        for (int r = 0; r < 8; r++)
+            *reinterpret_cast<uint2 *>(dst + r * pitch) = make_uint2(px[2 * r], px[2 * r + 1]);
+    }
+};
+
+} // namespace
+
+extern "C" __global__ void __launch_bounds__(IDCT_THREADS, 8)
+rtj_idct_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc *__restrict__ desc,
+                const rtj_dev_table *__restrict__ tables, const uint32_t *__restrict__ ent,
+                const uint16_t *__restrict__ srcf, int nblk, int w, int h, int seg_mb, int nstrips,
+                uint8_t *__restrict__ out, const uint8_t *__restrict__ carry,
+                uint32_t *__restrict__ hardq, rtj_dev_info *__restrict__ info)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NWARPS = IDCT_THREADS / 32;
+    const int f = blockIdx.y;
+    const int strip = blockIdx.x % nstrips, my = blockIdx.x / nstrips;
+    const int mbw = w >> 4;
+    const int mx0 = strip * seg_mb;
+    const int mbs = min(seg_mb, mbw - mx0);
+    const int nb = mbs * 6;
+
+    StripGeom g;
+    g.mbs = mbs;
+    g.segW = mbs * 16;
+    g.segC = mbs * 8;
+    g.tileY = smem;
+    g.tileU = g.tileY + 16 * g.segW;
+    IdctSmemHeader *hd = reinterpret_cast<IdctSmemHeader *>(g.tileU + 16 * g.segC);
+    uint32_t *s_ent = reinterpret_cast<uint32_t *>(hd + 1);          /* [nb] entries, picture order, skips resolved */
+    uint16_t *s_src = reinterpret_cast<uint16_t *>(s_ent + nb);      /* [nb] frame whose stream holds the block */
+    uint16_t *s_q = s_src + nb;                                      /* [NQ][nb] queued picture indices */
+
+    const rtjgpu_frame_desc fd = desc[f];
+    const int mytable = fd.table;
+    const rtj_dev_table *tb = &tables[mytable];
+    hd->iq[tid >> 6][tid & 63] = tb->iq[tid >> 6][tid & 63];         /* IDCT_THREADS == 128 entries */
+    if (tid < NQ) hd->cnt[tid] = 0;
+    if (tid == NQ) hd->next_chunk = 0;
+    const int bt8_l = tb->bt8[0], bt8_c = tb->bt8[1];
+    /* T2 needs three multipliers per plane type: registers */
+    const int lq0 = tb->iq[0][0], lq1 = tb->iq[0][1], lq2 = tb->iq[0][2];
+    const int cq0 = tb->iq[1][0], cq1 = tb->iq[1][1], cq2 = tb->iq[1][2];
+
+    /* ---- stream order -> picture order, skipped blocks replaced by their last writer's entry ---- */
+    const size_t strip_blk0 = (size_t)(my * mbw + mx0) * 6;
+    const size_t frame_blk0 = (size_t)f * nblk + strip_blk0;
+    const uint8_t *frame_pay = stream + fd.offset + RTJPEG_B200_HEADER_BYTES;
+    for (int i = tid; i < nb; i += IDCT_THREADS) {
+        uint32_t e = ent[frame_blk0 + i];
+        unsigned sf = (unsigned)f;
+        if (RTJ_ENT_IS_SKIP(e)) {
+            const unsigned s = srcf[frame_blk0 + i];
+            if (s != RTJ_SRC_CARRY) {
+                sf = s;
+                e = ent[(size_t)s * nblk + strip_blk0 + i];
+            }
+        }
+        const int p = g.pic_of_stream(i);
+        s_ent[p] = e;
+        s_src[p] = (uint16_t)sf;
+    }
+    __syncthreads();
+
+    /* ---- pass 1, picture order: T2 blocks decode right away, the rest is queued by class ---- */
+    for (int p0 = 0; p0 < nb; p0 += IDCT_THREADS) {
+        const int p = p0 + tid;
+        int cls = CLS_NONE;
+        int x0 = 0, x1 = 0, q = 0;
+        bool safe = true;
+        if (p < nb) {
+            const uint32_t e = s_ent[p];
+            const unsigned sf = s_src[p];
+            const bool chroma = p >= 4 * mbs;
+            if (RTJ_ENT_IS_SKIP(e)) cls = Q_CARRY;
+            else if (sf != (unsigned)f && desc[sf].table != mytable) cls = Q_HARD;
+            else if (RTJ_ENT_IS_INLINE(e)) {
+                cls = CLS_T2;
+                x0 = wrap16((int)(e & 0xFFu) * (chroma ? cq0 : lq0)) + 4;
+                x1 = wrap16((int)(signed char)((e >> 8) & 0xFFu) * (chroma ? cq1 : lq1));
+                q = wrap16((int)(signed char)((e >> 16) & 0xFFu) * (chroma ? cq2 : lq2));
+            } else {
+                const int eob = RTJ_ENT_EOB(e);
+                if (eob <= 3) {
+                    cls = CLS_T2;
+                    const uint8_t *src = (sf == (unsigned)f ? frame_pay : stream + desc[sf].offset + RTJPEG_B200_HEADER_BYTES)
+                                         + (e & RTJ_ENT_OFF_MASK);
+                    RegBytes<1> by(src);
+                    int x[3];
+                    unpack_block<3>(by, hd->iq[chroma], chroma ? bt8_c : bt8_l, x);
+                    x0 = x[0]; x1 = x[1]; q = x[2];
+                } else if (eob <= 7) cls = Q_M7;
+                else cls = Q_HARD;
+            }
+            if (cls == CLS_T2) safe = t2_safe(x0, x1, q);
+        }
+        const bool packed = __all_sync(FULL, safe);          /* one epilogue flavour per warp */
+        if (cls == CLS_T2) {
+            uint32_t px[16];
+            t2_pixels(x0, x1, q, packed, px);
+            g.store(p, px);
+        }
+        const unsigned queued = __ballot_sync(FULL, cls >= 0 && cls < NQ);
+        if (queued) {                                        /* warp-uniform */
+#pragma unroll
+            for (int c = 0; c < NQ; c++) {
+                const unsigned m = __ballot_sync(FULL, cls == c);
+                if (m == 0) continue;
+                int slot = 0;
+                const int leader = __ffs(m) - 1;
+                if (lane == leader) slot = atomicAdd(&hd->cnt[c], __popc(m));
+                slot = __shfl_sync(FULL, slot, leader);
+                if (cls == c) s_q[c * nb + slot + __popc(m & ((1u << lane) - 1u))] = (uint16_t)p;
+            }
+        }
+    }
+    __syncthreads();
+
+    /* ---- pass 2: queued blocks, one class-homogeneous group of 32 per warp step ---- */
+    const size_t fsz = (size_t)w * h * 3 / 2;
+    const int nM = hd->cnt[Q_M7], nC = hd->cnt[Q_CARRY], nH = hd->cnt[Q_HARD];
+    const int chM = (nM + 31) >> 5, chC = (nC + 31) >> 5, chH = nH ? 1 : 0;
+    const int total = chM + chC + chH;
+    while (total > 0) {
+        int ch = 0;
+        if (lane == 0) ch = atomicAdd(&hd->next_chunk, 1);
+        ch = __shfl_sync(FULL, ch, 0);
+        if (ch >= total) break;
+        if (ch < chM) {
+            const int idx = ch * 32 + lane;
+            int x[7] = {1008, 0, 0, 0, 0, 0, 0};
+            int p = 0;
+            const bool live = idx < nM;
+            if (live) {
+                p = s_q[Q_M7 * nb + idx];
+                const uint32_t e = s_ent[p];
+                const unsigned sf = s_src[p];
+                const bool chroma = p >= 4 * mbs;
+                const uint8_t *src = (sf == (unsigned)f ? frame_pay : stream + desc[sf].offset + RTJPEG_B200_HEADER_BYTES)
+                                     + (e & RTJ_ENT_OFF_MASK);
+                RegBytes<2> by(src);
+                unpack_block<7>(by, hd->iq[chroma], chroma ? bt8_c : bt8_l, x);
+            }
+            const bool packed = __all_sync(FULL, m7_safe(x));
+            if (live) {
+                uint32_t px[16];
+                m7_pixels(x, packed, px);
+                g.store(p, px);
+            }
+        } else if (ch < chM + chC) {
+            const int idx = (ch - chM) * 32 + lane;
+            if (idx < nC) {
+                const int p = s_q[Q_CARRY * nb + idx];
+                uint32_t px[16];
+                if (carry) {
+                    const int i = g.stream_of_pic(p);
+                    const int mb = i / 6, sub = i - mb * 6;
+                    const uint8_t *cp;
+                    int pitch;
+                    if (sub < 4) {
+                        pitch = w;
+                        cp = carry + (size_t)(my * 16 + (sub >> 1) * 8) * w + (mx0 + mb) * 16 + (sub & 1) * 8;
+                    } else {
+                        pitch = w >> 1;
+                        cp = carry + (size_t)w * h + (sub == 5 ? (size_t)(w >> 1) * (h >> 1) : 0)
+                             + (size_t)(my * 8) * pitch + (mx0 + mb) * 8;
+                    }
+#pragma unroll
+                    for (int r = 0; r < 8; r++) {
+                        const uint2 v = *reinterpret_cast<const uint2 *>(cp + (size_t)r * pitch);
+                        px[2 * r] = v.x;
+                        px[2 * r + 1] = v.y;
+                    }
+                } else {
+#pragma unroll
+                    for (int r = 0; r < 16; r++) px[r] = 0;
+                }
+                g.store(p, px);
+            }
+        } else {
+            /* HARD blocks leave for rtj_idct_hard_kernel: one contiguous run of the device queue,
+             * in picture order so that neighbouring queue slots are neighbouring pixels */
+            unsigned base = 0;
+            if (lane == 0) base = atomicAdd(&info->hard_blocks, (unsigned)nH);
+            base = __shfl_sync(FULL, base, 0);
+            for (int idx = lane; idx < nH; idx += 32) {
+                const int p = s_q[Q_HARD * nb + idx];
+                hardq[base + idx] = (uint32_t)(frame_blk0 + g.stream_of_pic(p));
+            }
+        }
+    }
+
+    /* ---- the strip leaves the SM (a strip made of HARD blocks only has nothing to say) ---- */
+    if (nH == nb) return;
+    uint8_t *oy = out + (size_t)f * fsz + (size_t)(my * 16) * w + mx0 * 16;
+    const int cw = w >> 1;
+    uint8_t *ou = out + (size_t)f * fsz + (size_t)w * h + (size_t)(my * 8) * cw + mx0 * 8;
+    uint8_t *ov = ou + (size_t)cw * (h >> 1);
+    uint8_t *tileV = g.tileU + 8 * g.segC;
+    if (nstrips == 1) {
+        /* full-width strip: 16 luma rows and 2 x 8 chroma rows are each one contiguous run in the
+         * tight-pitch planes -> three TMA bulk stores issued by one thread */
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            bulk_store(oy, g.tileY, 16u * (unsigned)g.segW);
+            bulk_store(ou, g.tileU, 8u * (unsigned)g.segC);
+            bulk_store(ov, tileV, 8u * (unsigned)g.segC);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+    } else {
+        __syncthreads();
+        const int vy = g.segW >> 4;               /* 16-byte vectors per luma row */
+        for (int r = warp; r < 16; r += NWARPS)
+            for (int c = lane; c < vy; c += 32)
+                *reinterpret_cast<uint4 *>(oy + (size_t)r * w + c * 16) =
+                    *reinterpret_cast<const uint4 *>(g.tileY + r * g.segW + c * 16);
+        const int vc = g.segC >> 3;               /* 8-byte vectors per chroma row */
+        for (int r = warp; r < 16; r += NWARPS) {
+            const int pl = r >> 3, rr = r & 7;
+            for (int c = lane; c < vc; c += 32)
+                *reinterpret_cast<uint2 *>((pl ? ov : ou) + (size_t)rr * cw + c * 8) =
+                    *reinterpret_cast<const uint2 *>((pl ? tileV : g.tileU) + rr * g.segC + c * 8);
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------ */
+/* K2b: the general decoder for queued blocks                                  */
+/* ------------------------------------------------------------------------ */
+
+extern "C" __global__ void __launch_bounds__(128)
+rtj_idct_hard_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc *__restrict__ desc,
+                     const rtj_dev_table *__restrict__ tables, const uint32_t *__restrict__ ent,
+                     const uint16_t *__restrict__ srcf, int nblk, int w, int h,
+                     uint8_t *__restrict__ out, const uint32_t *__restrict__ hardq,
+                     const rtj_dev_info *__restrict__ info)
+{
+    const unsigned n = info->hard_blocks;
+    const int mbw = w >> 4, cw = w >> 1;
+    const size_t fsz = (size_t)w * h * 3 / 2;
+    for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const uint32_t gidx = hardq[k];
+        const unsigned f = gidx / (unsigned)nblk;
+        const int i = (int)(gidx - f * (unsigned)nblk);
+        uint32_t e = ent[gidx];
+        unsigned sf = f;
+        if (RTJ_ENT_IS_SKIP(e)) {                    /* queued skipped blocks always have a writer in the batch */
+            sf = srcf[gidx];
+            e = ent[(size_t)sf * nblk + i];
+        }
+        const int mb = i / 6, sub = i - mb * 6;
+        const int chroma = sub >= 4;
+        const rtj_dev_table *t = &tables[desc[sf].table];
+        uint32_t px[16];
+        if (RTJ_ENT_IS_INLINE(e)) {
+            const int x0 = wrap16((int)(e & 0xFFu) * t->iq[chroma][0]) + 4;
+            const int x1 = wrap16((int)(signed char)((e >> 8) & 0xFFu) * t->iq[chroma][1]);
+            const int q = wrap16((int)(signed char)((e >> 16) & 0xFFu) * t->iq[chroma][2]);
+            t2_pixels(x0, x1, q, false, px);
+        } else {
+            MemBytes by(stream + desc[sf].offset + RTJPEG_B200_HEADER_BYTES + (e & RTJ_ENT_OFF_MASK));
+            int x[64];
+            unpack_block<64>(by, t->iq[chroma], t->bt8[chroma], x);
+            idct_general<64>(x, px);
+        }
+        const int my = mb / mbw, mx = mb - my * mbw;
+        uint8_t *dst;
+        int pitch;
+        if (!chroma) {
+            pitch = w;
+            dst = out + (size_t)f * fsz + (size_t)(my * 16 + (sub >> 1) * 8) * w + mx * 16 + (sub & 1) * 8;
+        } else {
+            pitch = cw;
+            dst = out + (size_t)f * fsz + (size_t)w * h + (sub == 5 ? (size_t)cw * (h >> 1) : 0)
+                  + (size_t)(my * 8) * cw + mx * 8;
+        }
+#pragma unroll
+        for (int r = 0; r < 8; r++)
+            *reinterpret_cast<uint2 *>(dst + (size_t)r * pitch) = make_uint2(px[2 * r], px[2 * r + 1]);
+    }
+}
+
+namespace {
+
+inline int idct_seg_mb(int mbw, int *nstrips)
+{
+    const int n = (mbw + IDCT_MAX_MB - 1) / IDCT_MAX_MB;
+    *nstrips = n;
+    return (mbw + n - 1) / n;
+}
+
+inline size_t idct_smem_bytes(int seg_mb)
+{
+    const size_t nb = (size_t)seg_mb * 6;
+    size_t s = (size_t)seg_mb * 16 * 24;             /* Y 16 rows + U,V 8 rows of half width */
+    s += sizeof(IdctSmemHeader);
+    s += nb * (4 + 2 + 2 * NQ);
+    return (s + 15) & ~(size_t)15;
+}
+
+int g_sm_count = 0;
+
+} // namespace
+
+extern "C" int rtj_idct_init(void)
+{
+    int nstrips;
+    const size_t worst = idct_smem_bytes(idct_seg_mb(IDCT_MAX_MB, &nstrips));
+    cudaError_t e = cudaFuncSetAttribute(rtj_idct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)worst);
+    if (e != cudaSuccess) return (int)e;
+    int dev = 0;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return (int)e;
+    if ((e = cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return (int)e;
+    return 0;
+}
+
+extern "C" int rtj_launch_idct(const rtj_launch_args *a, void *stream)
+{
+    const int mbw = a->w >> 4, mbh = a->h >> 4;
+    const int nblk = mbw * mbh * 6;
+    int nstrips;
+    const int seg_mb = idct_seg_mb(mbw, &nstrips);
+    dim3 grid((unsigned)(nstrips * mbh), (unsigned)a->F);
+    rtj_idct_kernel<<<grid, IDCT_THREADS, idct_smem_bytes(seg_mb), (cudaStream_t)stream>>>(
+        a->d_stream, a->d_desc, a->d_tables, a->d_ent, a->d_src, nblk, a->w, a->h, seg_mb, nstrips,
+        a->d_out, a->d_carry, a->d_hardq, a->d_info);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+    /* the queue's length is only known on the device: a fixed grid strides over it */
+    const int sms = g_sm_count > 0 ? g_sm_count : 148;
+    rtj_idct_hard_kernel<<<sms * 4, 128, 0, (cudaStream_t)stream>>>(
+        a->d_stream, a->d_desc, a->d_tables, a->d_ent, a->d_src, nblk, a->w, a->h, a->d_out, a->d_hardq, a->d_info);
+    return (int)cudaGetLastError();
+}

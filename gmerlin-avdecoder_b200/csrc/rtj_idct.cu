@@ -340,49 +340,48 @@ __device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, unsigne
  * i = 6*mb + sub (Y00 Y01 Y10 Y11 U V, lib/RTjpeg.c:2704-2739).  The kernel works in
  * "picture order" p: [0, 2mbs) upper luma block row left to right, [2mbs, 4mbs) lower
  * luma block row, [4mbs, 5mbs) U, [5mbs, 6mbs) V -- so consecutive p are horizontally
- * adjacent 8-byte runs of the shared picture strip.
+ * adjacent 8-byte runs of the shared picture strip (16 luma rows of 16*mbs bytes, then
+ * 8 U rows and 8 V rows of 8*mbs bytes), and a warp's stores never conflict.
  */
-struct StripGeom {
-    int mbs, segW, segC;
-    uint8_t *tileY, *tileU;          /* tileV = tileU + 8 * segC */
-    __device__ __forceinline__ int pic_of_stream(int i) const
-    {
-        const int mb = i / 6, sub = i - mb * 6;
-        return sub < 4 ? (sub >> 1) * 2 * mbs + 2 * mb + (sub & 1) : (sub - 4 + 4) * mbs + mb;
-    }
-    __device__ __forceinline__ int stream_of_pic(int p) const
-    {
-        if (p < 4 * mbs) {
-            const int hi = p >= 2 * mbs, c = p - hi * 2 * mbs;
-            return 6 * (c >> 1) + 2 * hi + (c & 1);
-        }
-        const int pc = p - 4 * mbs, hi = pc >= mbs;
-        return 6 * (pc - hi * mbs) + 4 + hi;
-    }
-    __device__ __forceinline__ uint8_t *dst_of_pic(int p, int &pitch) const
-    {
-        if (p < 4 * mbs) {
-            const int hi = p >= 2 * mbs, c = p - hi * 2 * mbs;
-            pitch = segW;
-            return tileY + hi * 8 * segW + c * 8;
-        }
-        const int pc = p - 4 * mbs, hi = pc >= mbs;
-        pitch = segC;
-        return tileU + hi * 8 * segC + (pc - hi * mbs) * 8;
-    }
-    __device__ __forceinline__ void store(int p, const uint32_t (&px)[16]) const
-    {
-        int pitch;
-        uint8_t *dst = dst_of_pic(p, pitch);
-#pragma unroll
-        for (int r = 0; r < 8; r++)
-            *reinterpret_cast<uint2 *>(dst + r * pitch) = make_uint2(px[2 * r], px[2 * r + 1]);
-    }
+struct PicPos {
+    int i;          /* stream-order index inside the strip */
+    int off;        /* byte offset of the block's first row inside the shared strip */
+    int pitch;      /* row pitch there */
+    bool chroma;
 };
+
+__device__ __forceinline__ PicPos pic_pos(int p, int mbs)
+{
+    PicPos r;
+    if (p < 4 * mbs) {
+        const int hi = p >= 2 * mbs ? 1 : 0, c = p - hi * 2 * mbs;
+        r.i = 3 * c - 2 * (c & 1) + 2 * hi;               /* 6 * (c >> 1) + 2 * hi + (c & 1) */
+        r.off = hi * 128 * mbs + 8 * c;
+        r.pitch = 16 * mbs;
+        r.chroma = false;
+    } else {
+        const int pc = p - 4 * mbs, hi = pc >= mbs ? 1 : 0;
+        r.i = 6 * (pc - hi * mbs) + 4 + hi;
+        r.off = 256 * mbs + 8 * pc + hi * 56 * mbs;        /* V follows the 8 rows of U */
+        r.pitch = 8 * mbs;
+        r.chroma = true;
+    }
+    return r;
+}
+
+__device__ __forceinline__ void store_block(uint8_t *dst, int pitch, const uint32_t (&px)[16])
+{
+#pragma unroll
+    for (int r = 0; r < 8; r++)
+        *reinterpret_cast<uint2 *>(dst + r * pitch) = make_uint2(px[2 * r], px[2 * r + 1]);
+}
 
 } // namespace
 
-extern "C" __global__ void __launch_bounds__(IDCT_THREADS, 8)
+/* SINGLE: the strip is the whole macroblock row (frames up to IDCT_MAX_MB macroblocks wide):
+ * no strip arithmetic, and the picture strip is contiguous in the tight-pitch output planes. */
+template <bool SINGLE>
+__global__ void __launch_bounds__(IDCT_THREADS, 8)
 rtj_idct_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc *__restrict__ desc,
                 const rtj_dev_table *__restrict__ tables, const uint32_t *__restrict__ ent,
                 const uint16_t *__restrict__ srcf, int nblk, int w, int h, int seg_mb, int nstrips,
@@ -392,26 +391,21 @@ rtj_idct_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc *__r
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NWARPS = IDCT_THREADS / 32;
-    const int f = blockIdx.y;
-    const int strip = blockIdx.x % nstrips, my = blockIdx.x / nstrips;
+    const unsigned f = blockIdx.y;
     const int mbw = w >> 4;
+    const int strip = SINGLE ? 0 : (int)(blockIdx.x % (unsigned)nstrips);
+    const int my = SINGLE ? (int)blockIdx.x : (int)(blockIdx.x / (unsigned)nstrips);
     const int mx0 = strip * seg_mb;
-    const int mbs = min(seg_mb, mbw - mx0);
+    const int mbs = SINGLE ? mbw : min(seg_mb, mbw - mx0);
     const int nb = mbs * 6;
 
-    StripGeom g;
-    g.mbs = mbs;
-    g.segW = mbs * 16;
-    g.segC = mbs * 8;
-    g.tileY = smem;
-    g.tileU = g.tileY + 16 * g.segW;
-    IdctSmemHeader *hd = reinterpret_cast<IdctSmemHeader *>(g.tileU + 16 * g.segC);
-    uint32_t *s_ent = reinterpret_cast<uint32_t *>(hd + 1);          /* [nb] entries, picture order, skips resolved */
-    uint16_t *s_src = reinterpret_cast<uint16_t *>(s_ent + nb);      /* [nb] frame whose stream holds the block */
-    uint16_t *s_q = s_src + nb;                                      /* [NQ][nb] queued picture indices */
+    uint8_t *tile = smem;                                            /* 384 * mbs bytes: Y, U, V */
+    IdctSmemHeader *hd = reinterpret_cast<IdctSmemHeader *>(tile + 384 * mbs);
+    uint32_t *s_qe = reinterpret_cast<uint32_t *>(hd + 1);           /* [NQ][nb] queued entries (skips resolved) ... */
+    uint32_t *s_qp = s_qe + NQ * nb;                                 /* ... and picture index | source frame << 16 */
 
     const rtjgpu_frame_desc fd = desc[f];
-    const int mytable = fd.table;
+    const unsigned mytable = fd.table;
     const rtj_dev_table *tb = &tables[mytable];
     hd->iq[tid >> 6][tid & 63] = tb->iq[tid >> 6][tid & 63];         /* IDCT_THREADS == 128 entries */
     if (tid < NQ) hd->cnt[tid] = 0;
@@ -421,24 +415,10 @@ rtj_idct_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc *__r
     const int lq0 = tb->iq[0][0], lq1 = tb->iq[0][1], lq2 = tb->iq[0][2];
     const int cq0 = tb->iq[1][0], cq1 = tb->iq[1][1], cq2 = tb->iq[1][2];
 
-    /* ---- stream order -> picture order, skipped blocks replaced by their last writer's entry ---- */
-    const size_t strip_blk0 = (size_t)(my * mbw + mx0) * 6;
-    const size_t frame_blk0 = (size_t)f * nblk + strip_blk0;
+    const unsigned strip_blk0 = (unsigned)(my * mbw + mx0) * 6u;
+    const unsigned frame_blk0 = f * (unsigned)nblk + strip_blk0;     /* F * nblk < 2^32 (checked by the host) */
+    const uint32_t *my_ent = ent + frame_blk0;
     const uint8_t *frame_pay = stream + fd.offset + RTJPEG_B200_HEADER_BYTES;
-    for (int i = tid; i < nb; i += IDCT_THREADS) {
-        uint32_t e = ent[frame_blk0 + i];
-        unsigned sf = (unsigned)f;
-        if (RTJ_ENT_IS_SKIP(e)) {
-            const unsigned s = srcf[frame_blk0 + i];
-            if (s != RTJ_SRC_CARRY) {
-                sf = s;
-                e = ent[(size_t)s * nblk + strip_blk0 + i];
-            }
-        }
-        const int p = g.pic_of_stream(i);
-        s_ent[p] = e;
-        s_src[p] = (uint16_t)sf;
-    }
     __syncthreads();
 
     /* ---- pass 1, picture order: T2 blocks decode right away, the rest is queued by class ---- */
@@ -447,26 +427,34 @@ rtj_idct_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc *__r
         int cls = CLS_NONE;
         int x0 = 0, x1 = 0, q = 0;
         bool safe = true;
+        uint32_t e = 0;
+        unsigned sf = f;
+        PicPos pp = pic_pos(p, mbs);
         if (p < nb) {
-            const uint32_t e = s_ent[p];
-            const unsigned sf = s_src[p];
-            const bool chroma = p >= 4 * mbs;
+            e = my_ent[pp.i];
+            if (RTJ_ENT_IS_SKIP(e)) {                        /* skipped: take the entry of its last writer */
+                const unsigned s = srcf[frame_blk0 + pp.i];
+                if (s != RTJ_SRC_CARRY) {
+                    sf = s;
+                    e = ent[s * (unsigned)nblk + strip_blk0 + pp.i];
+                }
+            }
             if (RTJ_ENT_IS_SKIP(e)) cls = Q_CARRY;
-            else if (sf != (unsigned)f && desc[sf].table != mytable) cls = Q_HARD;
+            else if (sf != f && desc[sf].table != mytable) cls = Q_HARD;
             else if (RTJ_ENT_IS_INLINE(e)) {
                 cls = CLS_T2;
-                x0 = wrap16((int)(e & 0xFFu) * (chroma ? cq0 : lq0)) + 4;
-                x1 = wrap16((int)(signed char)((e >> 8) & 0xFFu) * (chroma ? cq1 : lq1));
-                q = wrap16((int)(signed char)((e >> 16) & 0xFFu) * (chroma ? cq2 : lq2));
+                x0 = wrap16((int)(e & 0xFFu) * (pp.chroma ? cq0 : lq0)) + 4;
+                x1 = wrap16((int)(signed char)((e >> 8) & 0xFFu) * (pp.chroma ? cq1 : lq1));
+                q = wrap16((int)(signed char)((e >> 16) & 0xFFu) * (pp.chroma ? cq2 : lq2));
             } else {
                 const int eob = RTJ_ENT_EOB(e);
                 if (eob <= 3) {
                     cls = CLS_T2;
-                    const uint8_t *src = (sf == (unsigned)f ? frame_pay : stream + desc[sf].offset + RTJPEG_B200_HEADER_BYTES)
+                    const uint8_t *src = (sf == f ? frame_pay : stream + desc[sf].offset + RTJPEG_B200_HEADER_BYTES)
                                          + (e & RTJ_ENT_OFF_MASK);
                     RegBytes<1> by(src);
                     int x[3];
-                    unpack_block<3>(by, hd->iq[chroma], chroma ? bt8_c : bt8_l, x);
+                    unpack_block<3>(by, hd->iq[pp.chroma], pp.chroma ? bt8_c : bt8_l, x);
                     x0 = x[0]; x1 = x[1]; q = x[2];
                 } else if (eob <= 7) cls = Q_M7;
                 else cls = Q_HARD;
@@ -477,7 +465,7 @@ rtj_idct_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc *__r
         if (cls == CLS_T2) {
             uint32_t px[16];
             t2_pixels(x0, x1, q, packed, px);
-            g.store(p, px);
+            store_block(tile + pp.off, pp.pitch, px);
         }
         const unsigned queued = __ballot_sync(FULL, cls >= 0 && cls < NQ);
         if (queued) {                                        /* warp-uniform */
@@ -489,14 +477,17 @@ rtj_idct_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc *__r
                 const int leader = __ffs(m) - 1;
                 if (lane == leader) slot = atomicAdd(&hd->cnt[c], __popc(m));
                 slot = __shfl_sync(FULL, slot, leader);
-                if (cls == c) s_q[c * nb + slot + __popc(m & ((1u << lane) - 1u))] = (uint16_t)p;
+                if (cls == c) {
+                    const int at = c * nb + slot + __popc(m & ((1u << lane) - 1u));
+                    s_qe[at] = e;
+                    s_qp[at] = (uint32_t)p | (sf << 16);
+                }
             }
         }
     }
     __syncthreads();
 
     /* ---- pass 2: queued blocks, one class-homogeneous group of 32 per warp step ---- */
-    const size_t fsz = (size_t)w * h * 3 / 2;
     const int nM = hd->cnt[Q_M7], nC = hd->cnt[Q_CARRY], nH = hd->cnt[Q_HARD];
     const int chM = (nM + 31) >> 5, chC = (nC + 31) >> 5, chH = nH ? 1 : 0;
     const int total = chM + chC + chH;
@@ -508,32 +499,31 @@ rtj_idct_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc *__r
         if (ch < chM) {
             const int idx = ch * 32 + lane;
             int x[7] = {1008, 0, 0, 0, 0, 0, 0};
-            int p = 0;
             const bool live = idx < nM;
+            PicPos pp = pic_pos(0, mbs);
             if (live) {
-                p = s_q[Q_M7 * nb + idx];
-                const uint32_t e = s_ent[p];
-                const unsigned sf = s_src[p];
-                const bool chroma = p >= 4 * mbs;
-                const uint8_t *src = (sf == (unsigned)f ? frame_pay : stream + desc[sf].offset + RTJPEG_B200_HEADER_BYTES)
+                const uint32_t e = s_qe[Q_M7 * nb + idx];
+                const uint32_t ps = s_qp[Q_M7 * nb + idx];
+                const unsigned sf = ps >> 16;
+                pp = pic_pos((int)(ps & 0xFFFFu), mbs);
+                const uint8_t *src = (sf == f ? frame_pay : stream + desc[sf].offset + RTJPEG_B200_HEADER_BYTES)
                                      + (e & RTJ_ENT_OFF_MASK);
                 RegBytes<2> by(src);
-                unpack_block<7>(by, hd->iq[chroma], chroma ? bt8_c : bt8_l, x);
+                unpack_block<7>(by, hd->iq[pp.chroma], pp.chroma ? bt8_c : bt8_l, x);
             }
             const bool packed = __all_sync(FULL, m7_safe(x));
             if (live) {
                 uint32_t px[16];
                 m7_pixels(x, packed, px);
-                g.store(p, px);
+                store_block(tile + pp.off, pp.pitch, px);
             }
         } else if (ch < chM + chC) {
             const int idx = (ch - chM) * 32 + lane;
             if (idx < nC) {
-                const int p = s_q[Q_CARRY * nb + idx];
+                const PicPos pp = pic_pos((int)(s_qp[Q_CARRY * nb + idx] & 0xFFFFu), mbs);
                 uint32_t px[16];
                 if (carry) {
-                    const int i = g.stream_of_pic(p);
-                    const int mb = i / 6, sub = i - mb * 6;
+                    const int mb = pp.i / 6, sub = pp.i - mb * 6;
                     const uint8_t *cp;
                     int pitch;
                     if (sub < 4) {
@@ -554,7 +544,7 @@ rtj_idct_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc *__r
 #pragma unroll
                     for (int r = 0; r < 16; r++) px[r] = 0;
                 }
-                g.store(p, px);
+                store_block(tile + pp.off, pp.pitch, px);
             }
         } else {
             /* HARD blocks leave for rtj_idct_hard_kernel: one contiguous run of the device queue,
@@ -563,44 +553,44 @@ rtj_idct_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc *__r
             if (lane == 0) base = atomicAdd(&info->hard_blocks, (unsigned)nH);
             base = __shfl_sync(FULL, base, 0);
             for (int idx = lane; idx < nH; idx += 32) {
-                const int p = s_q[Q_HARD * nb + idx];
-                hardq[base + idx] = (uint32_t)(frame_blk0 + g.stream_of_pic(p));
+                const PicPos pp = pic_pos((int)(s_qp[Q_HARD * nb + idx] & 0xFFFFu), mbs);
+                hardq[base + idx] = frame_blk0 + (unsigned)pp.i;
             }
         }
     }
 
     /* ---- the strip leaves the SM (a strip made of HARD blocks only has nothing to say) ---- */
     if (nH == nb) return;
-    uint8_t *oy = out + (size_t)f * fsz + (size_t)(my * 16) * w + mx0 * 16;
+    const size_t fsz = (size_t)w * h * 3 / 2;
     const int cw = w >> 1;
+    uint8_t *oy = out + (size_t)f * fsz + (size_t)(my * 16) * w + mx0 * 16;
     uint8_t *ou = out + (size_t)f * fsz + (size_t)w * h + (size_t)(my * 8) * cw + mx0 * 8;
     uint8_t *ov = ou + (size_t)cw * (h >> 1);
-    uint8_t *tileV = g.tileU + 8 * g.segC;
-    if (nstrips == 1) {
+    const uint8_t *tileU = tile + 256 * mbs, *tileV = tile + 320 * mbs;
+    if (SINGLE) {
         /* full-width strip: 16 luma rows and 2 x 8 chroma rows are each one contiguous run in the
          * tight-pitch planes -> three TMA bulk stores issued by one thread */
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
         if (tid == 0) {
-            bulk_store(oy, g.tileY, 16u * (unsigned)g.segW);
-            bulk_store(ou, g.tileU, 8u * (unsigned)g.segC);
-            bulk_store(ov, tileV, 8u * (unsigned)g.segC);
+            bulk_store(oy, tile, 256u * (unsigned)mbs);
+            bulk_store(ou, tileU, 64u * (unsigned)mbs);
+            bulk_store(ov, tileV, 64u * (unsigned)mbs);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         }
     } else {
         __syncthreads();
-        const int vy = g.segW >> 4;               /* 16-byte vectors per luma row */
+        const int segW = 16 * mbs, segC = 8 * mbs;
         for (int r = warp; r < 16; r += NWARPS)
-            for (int c = lane; c < vy; c += 32)
+            for (int c = lane; c < mbs; c += 32)                 /* 16-byte vectors per luma row */
                 *reinterpret_cast<uint4 *>(oy + (size_t)r * w + c * 16) =
-                    *reinterpret_cast<const uint4 *>(g.tileY + r * g.segW + c * 16);
-        const int vc = g.segC >> 3;               /* 8-byte vectors per chroma row */
+                    *reinterpret_cast<const uint4 *>(tile + r * segW + c * 16);
         for (int r = warp; r < 16; r += NWARPS) {
             const int pl = r >> 3, rr = r & 7;
-            for (int c = lane; c < vc; c += 32)
+            for (int c = lane; c < mbs; c += 32)                 /* 8-byte vectors per chroma row */
                 *reinterpret_cast<uint2 *>((pl ? ov : ou) + (size_t)rr * cw + c * 8) =
-                    *reinterpret_cast<const uint2 *>((pl ? tileV : g.tileU) + rr * g.segC + c * 8);
+                    *reinterpret_cast<const uint2 *>((pl ? tileV : tileU) + rr * segC + c * 8);
         }
     }
 }
@@ -675,7 +665,7 @@ inline size_t idct_smem_bytes(int seg_mb)
     const size_t nb = (size_t)seg_mb * 6;
     size_t s = (size_t)seg_mb * 16 * 24;             /* Y 16 rows + U,V 8 rows of half width */
     s += sizeof(IdctSmemHeader);
-    s += nb * (4 + 2 + 2 * NQ);
+    s += nb * (4 + 4) * NQ;
     return (s + 15) & ~(size_t)15;
 }
 
@@ -687,7 +677,9 @@ extern "C" int rtj_idct_init(void)
 {
     int nstrips;
     const size_t worst = idct_smem_bytes(idct_seg_mb(IDCT_MAX_MB, &nstrips));
-    cudaError_t e = cudaFuncSetAttribute(rtj_idct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)worst);
+    cudaError_t e = cudaFuncSetAttribute(rtj_idct_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)worst);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(rtj_idct_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)worst);
     if (e != cudaSuccess) return (int)e;
     int dev = 0;
     if ((e = cudaGetDevice(&dev)) != cudaSuccess) return (int)e;
@@ -702,9 +694,14 @@ extern "C" int rtj_launch_idct(const rtj_launch_args *a, void *stream)
     int nstrips;
     const int seg_mb = idct_seg_mb(mbw, &nstrips);
     dim3 grid((unsigned)(nstrips * mbh), (unsigned)a->F);
-    rtj_idct_kernel<<<grid, IDCT_THREADS, idct_smem_bytes(seg_mb), (cudaStream_t)stream>>>(
-        a->d_stream, a->d_desc, a->d_tables, a->d_ent, a->d_src, nblk, a->w, a->h, seg_mb, nstrips,
-        a->d_out, a->d_carry, a->d_hardq, a->d_info);
+    if (nstrips == 1)
+        rtj_idct_kernel<true><<<grid, IDCT_THREADS, idct_smem_bytes(seg_mb), (cudaStream_t)stream>>>(
+            a->d_stream, a->d_desc, a->d_tables, a->d_ent, a->d_src, nblk, a->w, a->h, seg_mb, nstrips,
+            a->d_out, a->d_carry, a->d_hardq, a->d_info);
+    else
+        rtj_idct_kernel<false><<<grid, IDCT_THREADS, idct_smem_bytes(seg_mb), (cudaStream_t)stream>>>(
+            a->d_stream, a->d_desc, a->d_tables, a->d_ent, a->d_src, nblk, a->w, a->h, seg_mb, nstrips,
+            a->d_out, a->d_carry, a->d_hardq, a->d_info);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
     /* the queue's length is only known on the device: a fixed grid strides over it */

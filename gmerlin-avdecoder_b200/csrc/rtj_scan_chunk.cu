@@ -186,18 +186,33 @@ rtj_scan_chunk_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_des
         if (tid < nch) {
             uint16_t *ring = reinterpret_cast<uint16_t *>(sh.ring) + tid * CS_RING;
             const uint32_t *dw = sh.del + tid * (CS_C / 4 + 1);
-            const int cq = tid * CS_C, endq = cq + CS_C;
-#pragma unroll 2
-            for (int w = CS_C / 4 - 1; w >= 0; --w) {
-                const uint32_t d4 = dw[w];
+            const int cq = tid * CS_C;
+            /* the 64 positions behind the chunk: a parse that lands there has left the chunk, at that
+             * offset, without starting another block.  Their ring slots are exactly their offsets. */
 #pragma unroll
-                for (int i = 3; i >= 0; --i) {
-                    const int q = cq + 4 * w + i;
-                    const int n = q + (int)((d4 >> (8 * i)) & 0xFFu);
-                    uint32_t v = ring[n & 63];
-                    v = n >= endq ? (uint32_t)(n - endq) | 64u : v + 64u;   /* exit offset | blocks << 6 */
-                    if (q >= lim) v = 0;                                    /* nothing starts behind the payload */
-                    ring[q & 63] = (uint16_t)v;
+            for (int k = 0; k < 64; k += 2) reinterpret_cast<uint32_t *>(ring)[k >> 1] = (uint32_t)k | ((uint32_t)(k + 1) << 16);
+            if (cq + CS_C <= lim) {
+#pragma unroll 2
+                for (int w = CS_C / 4 - 1; w >= 0; --w) {
+                    const uint32_t d4 = dw[w];
+                    uint16_t *slot = ring + ((4 * w) & 63);
+#pragma unroll
+                    for (int i = 3; i >= 0; --i) {
+                        const int n = 4 * w + i + (int)((d4 >> (8 * i)) & 0xFFu);
+                        slot[i] = (uint16_t)(ring[n & 63] + 64u);          /* exit offset | blocks << 6 */
+                    }
+                }
+            } else {                                                       /* the chunk the payload ends in */
+                for (int w = CS_C / 4 - 1; w >= 0; --w) {
+                    const uint32_t d4 = dw[w];
+#pragma unroll
+                    for (int i = 3; i >= 0; --i) {
+                        const int qq = 4 * w + i;
+                        const int n = qq + (int)((d4 >> (8 * i)) & 0xFFu);
+                        uint32_t v = ring[n & 63] + 64u;
+                        if (cq + qq >= lim) v = 0;                         /* nothing starts behind the payload */
+                        ring[qq & 63] = (uint16_t)v;
+                    }
                 }
             }
         }
@@ -236,23 +251,16 @@ rtj_scan_chunk_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_des
                     const int dl = delb[q + ((q / CS_C) << 2)];
                     const uint32_t head = lds_u32_unaligned(sh.pay, q + mis);       /* DC, token 1, token 2, token 3 */
                     const uint32_t last = payb[q + dl - 1];
-                    uint32_t e;
-                    if ((head & 0xFFu) == 0xFFu) {
-                        e = RTJ_ENT_SKIP;
-                        myskips++;
-                    } else {
-                        /* positions >= eob are zero: a final run of n zeros ends at 64, so it starts at 64 - n */
-                        int eob = (last - 64u) < 64u ? max(127 - (int)last, dl - 1) : 64;
-                        if (eob <= 3) {
-                            const uint32_t t1 = (head >> 8) & 0xFFu, t2 = (head >> 16) & 0xFFu;
-                            const uint32_t c1 = (eob >= 2 && (t1 - 64u) >= 64u) ? t1 : 0u;
-                            const uint32_t c2 = (eob >= 3 && (t2 - 64u) >= 64u) ? t2 : 0u;
-                            e = RTJ_ENT_INLINE(head, c1, c2);
-                        } else {
-                            e = RTJ_ENT(seg0 + q, eob);
-                        }
-                    }
-                    sh.ring[i - r0] = e;
+                    const bool isff = (head & 0xFFu) == 0xFFu;                      /* skipped block */
+                    /* positions >= eob are zero: a final run of n zeros ends at 64, so it starts at 64 - n */
+                    const int eob = (last - 64u) < 64u ? max(127 - (int)last, dl - 1) : 64;
+                    const uint32_t t1 = (head >> 8) & 0xFFu, t2 = (head >> 16) & 0xFFu;
+                    const uint32_t c1 = (eob >= 2 && (t1 - 64u) >= 64u) ? t1 : 0u;
+                    const uint32_t c2 = (eob >= 3 && (t2 - 64u) >= 64u) ? t2 : 0u;
+                    const uint32_t e_inl = RTJ_ENT_INLINE_BIT | (head & 0xFFu) | (c1 << 8) | (c2 << 16);
+                    const uint32_t e_gen = RTJ_ENT(seg0 + q, eob);
+                    sh.ring[i - r0] = isff ? RTJ_ENT_SKIP : (eob <= 3 ? e_inl : e_gen);
+                    myskips += isff ? 1 : 0;
                     q += dl;
                     i++;
                     lastend = seg0 + q;

@@ -370,7 +370,7 @@ __device__ __forceinline__ void store_block(uint8_t *dst, int pitch, const uint3
         *reinterpret_cast<uint2 *>(dst + r * pitch) = make_uint2(px[2 * r], px[2 * r + 1]);
 }
 
-/* everything both flavours of the kernel take from the host */
+/* what the kernel takes from the host */
 struct K2Params {
     const uint8_t *stream;
     const rtjgpu_frame_desc *desc;
@@ -382,128 +382,171 @@ struct K2Params {
     const uint8_t *carry;
     uint32_t *hardq;
     rtj_dev_info *info;
-    int nitems;                      /* persistent flavour: macroblock rows in the batch */
 };
 
-/* one work item: a strip of one macroblock row of one frame */
-struct Item {
-    unsigned f;
-    int my, mx0, mbs, nb;
-    unsigned strip_blk0, frame_blk0;
-    const uint8_t *frame_pay;
-    unsigned table;
-    int bt8_l, bt8_c;
-    int lq0, lq1, lq2, cq0, cq1, cq2;     /* T2 needs three multipliers per plane type: registers */
-};
+constexpr int K2_WARPS = IDCT_THREADS / 32;
+constexpr int K2_ROUNDS_MAX = (IDCT_MAX_MB * 6 + IDCT_THREADS - 1) / IDCT_THREADS;     /* 6 */
+constexpr int K2_WQ = K2_ROUNDS_MAX * 32;          /* queue slots of one warp: every block it looked at */
 
-struct QueueSmem {
-    int cnt[NQ];
-    int next_chunk;
-};
+} // namespace
 
-/* pass 1 for one block: raw entry `e` of picture position p -> decoded (T2) or queued */
-__device__ __forceinline__ void k2_pass1(const K2Params &P, const Item &it, const int (*iq)[64], QueueSmem *qs,
-                                         uint32_t *s_qe, uint32_t *s_qp, uint8_t *tile,
-                                         int p, const PicPos &pp, uint32_t e, int lane)
+/*
+ * One CTA per (frame, macroblock row [, strip]).  Warps work on their own: a warp takes 32
+ * picture positions per round, decodes the T2 blocks among them at once and parks the others in
+ * its private queue (M7 from the front, CARRY / HARD from the back); after its last round it
+ * decodes its M7 blocks in one go (a warp sees ~20 of them per macroblock row of typical
+ * material, so one pass of the M7 flow graph serves them all), copies CARRY blocks and hands HARD
+ * blocks to the device queue.  No block-wide barrier until the picture strip is complete.
+ *
+ * SINGLE: the strip is the whole macroblock row (frames up to IDCT_MAX_MB macroblocks wide): no
+ * strip arithmetic, and the strip is contiguous in the tight-pitch output planes -> TMA bulk stores.
+ */
+template <bool SINGLE>
+__global__ void __launch_bounds__(IDCT_THREADS, 8)
+rtj_idct_kernel(const K2Params P)
 {
-    int cls = CLS_NONE;
-    int x0 = 0, x1 = 0, q = 0;
-    bool safe = true;
-    unsigned sf = it.f;
-    if (p < it.nb) {
-        if (RTJ_ENT_IS_SKIP(e)) {                        /* skipped: take the entry of its last writer */
-            const unsigned s = P.srcf[it.frame_blk0 + pp.i];
-            if (s != RTJ_SRC_CARRY) {
-                sf = s;
-                e = P.ent[s * (unsigned)P.nblk + it.strip_blk0 + pp.i];
-            }
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned f = blockIdx.y;
+    const int w = P.w, h = P.h, mbw = w >> 4;
+    const int strip = SINGLE ? 0 : (int)(blockIdx.x % (unsigned)P.nstrips);
+    const int my = SINGLE ? (int)blockIdx.x : (int)(blockIdx.x / (unsigned)P.nstrips);
+    const int mx0 = strip * P.seg_mb;
+    const int mbs = SINGLE ? mbw : min(P.seg_mb, mbw - mx0);
+    const int nb = mbs * 6;
+    const unsigned strip_blk0 = (unsigned)(my * mbw + mx0) * 6u;
+    const unsigned frame_blk0 = f * (unsigned)P.nblk + strip_blk0;   /* F * nblk < 2^32 (checked by the host) */
+    const uint32_t *my_ent = P.ent + frame_blk0;
+
+    uint8_t *tile = smem;                                            /* 384 * mbs bytes: Y, U, V */
+    int *s_hard = reinterpret_cast<int *>(tile + 384 * mbs);         /* HARD blocks of the strip, per warp */
+    static_assert(K2_WARPS == 4, "s_hard holds four counters");
+    uint32_t *wq_e = reinterpret_cast<uint32_t *>(s_hard + 4) + warp * K2_WQ;      /* this warp's queue: entries ... */
+    uint32_t *wq_p = reinterpret_cast<uint32_t *>(s_hard + 4) + (K2_WARPS + warp) * K2_WQ;   /* ... picture index | source << 16 */
+
+    /* everything that does not depend on anything else is fetched first: the first round's entry
+     * and the frame descriptor; the table constants follow the descriptor */
+    const int rounds = (nb + IDCT_THREADS - 1) / IDCT_THREADS;
+    uint32_t e_first = tid < nb ? my_ent[pic_pos(tid, mbs).i] : 0u;
+    const rtjgpu_frame_desc fd = P.desc[f];
+    const unsigned mytable = fd.table;
+    const rtj_dev_table *tb = &P.tables[mytable];
+    const uint8_t *frame_pay = P.stream + fd.offset + RTJPEG_B200_HEADER_BYTES;
+    const int bt8_l = tb->bt8[0], bt8_c = tb->bt8[1];
+    /* T2 needs three multipliers per plane type: registers */
+    const int lq0 = tb->iq[0][0], lq1 = tb->iq[0][1], lq2 = tb->iq[0][2];
+    const int cq0 = tb->iq[1][0], cq1 = tb->iq[1][1], cq2 = tb->iq[1][2];
+
+    /* ---- pass 1, picture order: T2 blocks decode right away, the rest is queued ---- */
+    int nfront = 0, nback = 0;                               /* warp-uniform queue fill: M7 | CARRY, HARD */
+    for (int r = 0; r < rounds; r++) {
+        const int p = r * IDCT_THREADS + tid;
+        const PicPos pp = pic_pos(p, mbs);
+        uint32_t e = e_first;
+        if (r + 1 < rounds) {                                /* next round's entry: in flight during this round */
+            const int pn = p + IDCT_THREADS;
+            e_first = pn < nb ? my_ent[pic_pos(pn, mbs).i] : 0u;
         }
-        if (RTJ_ENT_IS_SKIP(e)) cls = Q_CARRY;
-        else if (sf != it.f && P.desc[sf].table != it.table) cls = Q_HARD;
-        else if (RTJ_ENT_IS_INLINE(e)) {
-            cls = CLS_T2;
-            x0 = wrap16((int)(e & 0xFFu) * (pp.chroma ? it.cq0 : it.lq0)) + 4;
-            x1 = wrap16((int)(signed char)((e >> 8) & 0xFFu) * (pp.chroma ? it.cq1 : it.lq1));
-            q = wrap16((int)(signed char)((e >> 16) & 0xFFu) * (pp.chroma ? it.cq2 : it.lq2));
-        } else {
-            const int eob = RTJ_ENT_EOB(e);
-            if (eob <= 3) {
+        int cls = CLS_NONE;
+        int x0 = 0, x1 = 0, q = 0;
+        bool safe = true;
+        unsigned sf = f;
+        if (p < nb) {
+            if (RTJ_ENT_IS_SKIP(e)) {                        /* skipped: take the entry of its last writer */
+                const unsigned s = P.srcf[frame_blk0 + pp.i];
+                if (s != RTJ_SRC_CARRY) {
+                    sf = s;
+                    e = P.ent[s * (unsigned)P.nblk + strip_blk0 + pp.i];
+                }
+            }
+            if (RTJ_ENT_IS_SKIP(e)) cls = Q_CARRY;
+            else if (sf != f && P.desc[sf].table != mytable) cls = Q_HARD;
+            else if (RTJ_ENT_IS_INLINE(e)) {
                 cls = CLS_T2;
-                const uint8_t *src = (sf == it.f ? it.frame_pay : P.stream + P.desc[sf].offset + RTJPEG_B200_HEADER_BYTES)
-                                     + (e & RTJ_ENT_OFF_MASK);
-                RegBytes<1> by(src);
-                int x[3];
-                unpack_block<3>(by, iq[pp.chroma], pp.chroma ? it.bt8_c : it.bt8_l, x);
-                x0 = x[0]; x1 = x[1]; q = x[2];
-            } else if (eob <= 7) cls = Q_M7;
-            else cls = Q_HARD;
-        }
-        if (cls == CLS_T2) safe = t2_safe(x0, x1, q);
-    }
-    const bool packed = __all_sync(FULL, safe);          /* one epilogue flavour per warp */
-    if (cls == CLS_T2) {
-        uint32_t px[16];
-        t2_pixels(x0, x1, q, packed, px);
-        store_block(tile + pp.off, pp.pitch, px);
-    }
-    const unsigned queued = __ballot_sync(FULL, cls >= 0 && cls < NQ);
-    if (queued) {                                        /* warp-uniform */
-#pragma unroll
-        for (int c = 0; c < NQ; c++) {
-            const unsigned m = __ballot_sync(FULL, cls == c);
-            if (m == 0) continue;
-            int slot = 0;
-            const int leader = __ffs(m) - 1;
-            if (lane == leader) slot = atomicAdd(&qs->cnt[c], __popc(m));
-            slot = __shfl_sync(FULL, slot, leader);
-            if (cls == c) {
-                const int at = c * it.nb + slot + __popc(m & ((1u << lane) - 1u));
-                s_qe[at] = e;
-                s_qp[at] = (uint32_t)p | (sf << 16);
+                x0 = wrap16((int)(e & 0xFFu) * (pp.chroma ? cq0 : lq0)) + 4;
+                x1 = wrap16((int)(signed char)((e >> 8) & 0xFFu) * (pp.chroma ? cq1 : lq1));
+                q = wrap16((int)(signed char)((e >> 16) & 0xFFu) * (pp.chroma ? cq2 : lq2));
+            } else {
+                const int eob = RTJ_ENT_EOB(e);
+                if (eob <= 3) {
+                    cls = CLS_T2;
+                    const uint8_t *src = (sf == f ? frame_pay : P.stream + P.desc[sf].offset + RTJPEG_B200_HEADER_BYTES)
+                                         + (e & RTJ_ENT_OFF_MASK);
+                    RegBytes<1> by(src);
+                    int x[3];
+                    unpack_block<3>(by, tb->iq[pp.chroma], pp.chroma ? bt8_c : bt8_l, x);
+                    x0 = x[0]; x1 = x[1]; q = x[2];
+                } else if (eob <= 7) cls = Q_M7;
+                else cls = Q_HARD;
             }
+            if (cls == CLS_T2) safe = t2_safe(x0, x1, q);
         }
+        const bool packed = __all_sync(FULL, safe);          /* one epilogue flavour per warp */
+        if (cls == CLS_T2) {
+            uint32_t px[16];
+            t2_pixels(x0, x1, q, packed, px);
+            store_block(tile + pp.off, pp.pitch, px);
+        }
+        const unsigned mM = __ballot_sync(FULL, cls == Q_M7);
+        const unsigned mB = __ballot_sync(FULL, cls == Q_CARRY || cls == Q_HARD);
+        const unsigned below = (1u << lane) - 1u;
+        if (cls == Q_M7) {
+            const int at = nfront + __popc(mM & below);
+            wq_e[at] = e;
+            wq_p[at] = (uint32_t)p | (sf << 16);
+        } else if (cls == Q_CARRY || cls == Q_HARD) {
+            const int at = K2_WQ - 1 - (nback + __popc(mB & below));
+            wq_e[at] = cls == Q_CARRY ? RTJ_ENT_SKIP : e;
+            wq_p[at] = (uint32_t)p | (sf << 16);
+        }
+        nfront += __popc(mM);
+        nback += __popc(mB);
     }
-}
+    __syncwarp();
 
-/* pass 2: queued blocks, one class-homogeneous group of 32 per warp step.  Returns the number of
- * HARD blocks of the item (they are pushed to the device queue here). */
-__device__ __forceinline__ int k2_pass2(const K2Params &P, const Item &it, const int (*iq)[64], QueueSmem *qs,
-                                        const uint32_t *s_qe, const uint32_t *s_qp, uint8_t *tile, int lane)
-{
-    const int nb = it.nb, mbs = it.mbs, w = P.w, h = P.h;
-    const int nM = qs->cnt[Q_M7], nC = qs->cnt[Q_CARRY], nH = qs->cnt[Q_HARD];
-    const int chM = (nM + 31) >> 5, chC = (nC + 31) >> 5, chH = nH ? 1 : 0;
-    const int total = chM + chC + chH;
-    while (total > 0) {
-        int ch = 0;
-        if (lane == 0) ch = atomicAdd(&qs->next_chunk, 1);
-        ch = __shfl_sync(FULL, ch, 0);
-        if (ch >= total) break;
-        if (ch < chM) {
-            const int idx = ch * 32 + lane;
-            int x[7] = {1008, 0, 0, 0, 0, 0, 0};
-            const bool live = idx < nM;
-            PicPos pp = pic_pos(0, mbs);
-            if (live) {
-                const uint32_t e = s_qe[Q_M7 * nb + idx];
-                const uint32_t ps = s_qp[Q_M7 * nb + idx];
-                const unsigned sf = ps >> 16;
-                pp = pic_pos((int)(ps & 0xFFFFu), mbs);
-                const uint8_t *src = (sf == it.f ? it.frame_pay : P.stream + P.desc[sf].offset + RTJPEG_B200_HEADER_BYTES)
-                                     + (e & RTJ_ENT_OFF_MASK);
-                RegBytes<2> by(src);
-                unpack_block<7>(by, iq[pp.chroma], pp.chroma ? it.bt8_c : it.bt8_l, x);
+    /* ---- pass 2, still warp-private: the M7 blocks, 32 at a time ---- */
+    for (int c0 = 0; c0 < nfront; c0 += 32) {
+        const int idx = c0 + lane;
+        int x[7] = {1008, 0, 0, 0, 0, 0, 0};
+        const bool live = idx < nfront;
+        PicPos pp = pic_pos(0, mbs);
+        if (live) {
+            const uint32_t e = wq_e[idx];
+            const uint32_t ps = wq_p[idx];
+            const unsigned sf = ps >> 16;
+            pp = pic_pos((int)(ps & 0xFFFFu), mbs);
+            const uint8_t *src = (sf == f ? frame_pay : P.stream + P.desc[sf].offset + RTJPEG_B200_HEADER_BYTES)
+                                 + (e & RTJ_ENT_OFF_MASK);
+            RegBytes<2> by(src);
+            unpack_block<7>(by, tb->iq[pp.chroma], pp.chroma ? bt8_c : bt8_l, x);
+        }
+        const bool packed = __all_sync(FULL, m7_safe(x));
+        if (live) {
+            uint32_t px[16];
+            m7_pixels(x, packed, px);
+            store_block(tile + pp.off, pp.pitch, px);
+        }
+    }
+    /* ---- CARRY blocks are copied from the picture before the batch, HARD blocks leave for
+     *      rtj_idct_hard_kernel through the device queue ---- */
+    int nhard = 0;
+    if (nback) {                                             /* warp-uniform */
+        for (int c0 = 0; c0 < nback; c0 += 32) {
+            const int idx = c0 + lane;
+            const bool live = idx < nback;
+            uint32_t e = RTJ_ENT_SKIP, ps = 0;
+            if (live) { e = wq_e[K2_WQ - 1 - idx]; ps = wq_p[K2_WQ - 1 - idx]; }
+            const bool hard = live && !RTJ_ENT_IS_SKIP(e);
+            const PicPos pp = pic_pos((int)(ps & 0xFFFFu), mbs);
+            const unsigned mH = __ballot_sync(FULL, hard);
+            if (mH) {
+                unsigned base = 0;
+                if (lane == 0) base = atomicAdd(&P.info->hard_blocks, (unsigned)__popc(mH));
+                base = __shfl_sync(FULL, base, 0);
+                if (hard) P.hardq[base + __popc(mH & ((1u << lane) - 1u))] = frame_blk0 + (unsigned)pp.i;
+                nhard += __popc(mH);
             }
-            const bool packed = __all_sync(FULL, m7_safe(x));
-            if (live) {
-                uint32_t px[16];
-                m7_pixels(x, packed, px);
-                store_block(tile + pp.off, pp.pitch, px);
-            }
-        } else if (ch < chM + chC) {
-            const int idx = (ch - chM) * 32 + lane;
-            if (idx < nC) {
-                const PicPos pp = pic_pos((int)(s_qp[Q_CARRY * nb + idx] & 0xFFFFu), mbs);
+            if (live && !hard) {
                 uint32_t px[16];
                 if (P.carry) {
                     const int mb = pp.i / 6, sub = pp.i - mb * 6;
@@ -511,11 +554,11 @@ __device__ __forceinline__ int k2_pass2(const K2Params &P, const Item &it, const
                     int pitch;
                     if (sub < 4) {
                         pitch = w;
-                        cp = P.carry + (size_t)(it.my * 16 + (sub >> 1) * 8) * w + (it.mx0 + mb) * 16 + (sub & 1) * 8;
+                        cp = P.carry + (size_t)(my * 16 + (sub >> 1) * 8) * w + (mx0 + mb) * 16 + (sub & 1) * 8;
                     } else {
                         pitch = w >> 1;
                         cp = P.carry + (size_t)w * h + (sub == 5 ? (size_t)(w >> 1) * (h >> 1) : 0)
-                             + (size_t)(it.my * 8) * pitch + (it.mx0 + mb) * 8;
+                             + (size_t)(my * 8) * pitch + (mx0 + mb) * 8;
                     }
 #pragma unroll
                     for (int r = 0; r < 8; r++) {
@@ -529,214 +572,43 @@ __device__ __forceinline__ int k2_pass2(const K2Params &P, const Item &it, const
                 }
                 store_block(tile + pp.off, pp.pitch, px);
             }
-        } else {
-            /* HARD blocks leave for rtj_idct_hard_kernel: one contiguous run of the device queue,
-             * in picture order so that neighbouring queue slots are neighbouring pixels */
-            unsigned base = 0;
-            if (lane == 0) base = atomicAdd(&P.info->hard_blocks, (unsigned)nH);
-            base = __shfl_sync(FULL, base, 0);
-            for (int idx = lane; idx < nH; idx += 32) {
-                const PicPos pp = pic_pos((int)(s_qp[Q_HARD * nb + idx] & 0xFFFFu), mbs);
-                P.hardq[base + idx] = it.frame_blk0 + (unsigned)pp.i;
-            }
         }
     }
-    return nH;
-}
-
-/* per-frame part of an item; the T2 multipliers come from the shared copy of the tables */
-__device__ __forceinline__ void item_set_frame(Item &it, const K2Params &P, const rtjgpu_frame_desc &fd,
-                                               const rtj_dev_table *tb)
-{
-    it.frame_pay = P.stream + fd.offset + RTJPEG_B200_HEADER_BYTES;
-    it.table = fd.table;
-    it.bt8_l = tb->bt8[0]; it.bt8_c = tb->bt8[1];
-    it.lq0 = tb->iq[0][0]; it.lq1 = tb->iq[0][1]; it.lq2 = tb->iq[0][2];
-    it.cq0 = tb->iq[1][0]; it.cq1 = tb->iq[1][1]; it.cq2 = tb->iq[1][2];
-}
-
-} // namespace
-
-/*
- * Strip flavour: one CTA per (frame, macroblock row, strip of <= IDCT_MAX_MB macroblocks).  Serves
- * frames wider than IDCT_MAX_MB macroblocks, whose rows do not fit one shared picture strip.
- */
-__global__ void __launch_bounds__(IDCT_THREADS, 8)
-rtj_idct_strip_kernel(const K2Params P)
-{
-    extern __shared__ __align__(128) uint8_t smem[];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int NWARPS = IDCT_THREADS / 32;
-    const int mbw = P.w >> 4;
-    const int strip = (int)(blockIdx.x % (unsigned)P.nstrips);
-    Item it;
-    it.f = blockIdx.y;
-    it.my = (int)(blockIdx.x / (unsigned)P.nstrips);
-    it.mx0 = strip * P.seg_mb;
-    it.mbs = min(P.seg_mb, mbw - it.mx0);
-    it.nb = it.mbs * 6;
-    it.strip_blk0 = (unsigned)(it.my * mbw + it.mx0) * 6u;
-    it.frame_blk0 = it.f * (unsigned)P.nblk + it.strip_blk0;     /* F * nblk < 2^32 (checked by the host) */
-    const int mbs = it.mbs, nb = it.nb;
-
-    uint8_t *tile = smem;                                            /* 384 * mbs bytes: Y, U, V */
-    int (*iq)[64] = reinterpret_cast<int (*)[64]>(tile + 384 * mbs);
-    QueueSmem *qs = reinterpret_cast<QueueSmem *>(iq + 2);
-    uint32_t *s_qe = reinterpret_cast<uint32_t *>(qs + 1);           /* [NQ][nb] queued entries (skips resolved) ... */
-    uint32_t *s_qp = s_qe + NQ * nb;                                 /* ... and picture index | source frame << 16 */
-
-    const rtjgpu_frame_desc fd = P.desc[it.f];
-    const rtj_dev_table *tb = &P.tables[fd.table];
-    iq[tid >> 6][tid & 63] = tb->iq[tid >> 6][tid & 63];             /* IDCT_THREADS == 128 entries */
-    if (tid < NQ) qs->cnt[tid] = 0;
-    if (tid == NQ) qs->next_chunk = 0;
-    item_set_frame(it, P, fd, tb);
-    __syncthreads();
-
-    const uint32_t *my_ent = P.ent + it.frame_blk0;
-    for (int p0 = 0; p0 < nb; p0 += IDCT_THREADS) {
-        const int p = p0 + tid;
-        const PicPos pp = pic_pos(p, mbs);
-        const uint32_t e = p < nb ? my_ent[pp.i] : 0u;
-        k2_pass1(P, it, iq, qs, s_qe, s_qp, tile, p, pp, e, lane);
-    }
-    __syncthreads();
-    const int nH = k2_pass2(P, it, iq, qs, s_qe, s_qp, tile, lane);
+    if (lane == 0) s_hard[warp] = nhard;
 
     /* ---- the strip leaves the SM (a strip made of HARD blocks only has nothing to say) ---- */
-    if (nH == nb) return;
-    const int w = P.w, h = P.h;
+    if (SINGLE) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (s_hard[0] + s_hard[1] + s_hard[2] + s_hard[3] == nb) return;
     const size_t fsz = (size_t)w * h * 3 / 2;
     const int cw = w >> 1;
-    uint8_t *oy = P.out + (size_t)it.f * fsz + (size_t)(it.my * 16) * w + it.mx0 * 16;
-    uint8_t *ou = P.out + (size_t)it.f * fsz + (size_t)w * h + (size_t)(it.my * 8) * cw + it.mx0 * 8;
+    uint8_t *oy = P.out + (size_t)f * fsz + (size_t)(my * 16) * w + mx0 * 16;
+    uint8_t *ou = P.out + (size_t)f * fsz + (size_t)w * h + (size_t)(my * 8) * cw + mx0 * 8;
     uint8_t *ov = ou + (size_t)cw * (h >> 1);
     const uint8_t *tileU = tile + 256 * mbs, *tileV = tile + 320 * mbs;
-    __syncthreads();
-    const int segW = 16 * mbs, segC = 8 * mbs;
-    for (int r = warp; r < 16; r += NWARPS)
-        for (int c = lane; c < mbs; c += 32)                 /* 16-byte vectors per luma row */
-            *reinterpret_cast<uint4 *>(oy + (size_t)r * w + c * 16) =
-                *reinterpret_cast<const uint4 *>(tile + r * segW + c * 16);
-    for (int r = warp; r < 16; r += NWARPS) {
-        const int pl = r >> 3, rr = r & 7;
-        for (int c = lane; c < mbs; c += 32)                 /* 8-byte vectors per chroma row */
-            *reinterpret_cast<uint2 *>((pl ? ov : ou) + (size_t)rr * cw + c * 8) =
-                *reinterpret_cast<const uint2 *>((pl ? tileV : tileU) + rr * segC + c * 8);
-    }
-}
-
-/*
- * Row flavour (frames up to IDCT_MAX_MB macroblocks wide): persistent CTAs, each walking the
- * batch's macroblock rows with a fixed stride.  The picture strip of a whole macroblock row is
- * contiguous in the tight-pitch planes (16 luma rows, 8 U rows, 8 V rows), so it leaves the SM as
- * three TMA bulk stores; two strips alternate so that the stores of row k overlap the arithmetic of
- * row k+1.  The entries of the next row are fetched while the current one is decoded.
- */
-constexpr int ROW_ROUNDS_MAX = (IDCT_MAX_MB * 6 + IDCT_THREADS - 1) / IDCT_THREADS;   /* 6 */
-
-template <int ROUNDS>
-__global__ void __launch_bounds__(IDCT_THREADS, 5)
-rtj_idct_rows_kernel(const K2Params P)
-{
-    extern __shared__ __align__(128) uint8_t smem[];
-    const int tid = threadIdx.x, lane = tid & 31;
-    const int mbw = P.w >> 4, mbh = P.h >> 4;
-    const int mbs = mbw, nb = mbw * 6;
-    const int tile_bytes = 384 * mbs;
-
-    uint8_t *tiles = smem;                                           /* 2 x (Y, U, V) */
-    int (*iq)[64] = reinterpret_cast<int (*)[64]>(tiles + 2 * tile_bytes);
-    QueueSmem *qs2 = reinterpret_cast<QueueSmem *>(iq + 2);          /* [2], alternating like the strips */
-    uint32_t *s_qe = reinterpret_cast<uint32_t *>(qs2 + 2);          /* [NQ][nb] */
-    uint32_t *s_qp = s_qe + NQ * nb;
-
-    /* picture positions of this thread: the same for every row */
-    PicPos pp[ROUNDS];
-#pragma unroll
-    for (int r = 0; r < ROUNDS; r++) pp[r] = pic_pos(r * IDCT_THREADS + tid, mbs);
-
-    const size_t fsz = (size_t)P.w * P.h * 3 / 2;
-    const int cw = P.w >> 1;
-    Item it;
-    it.mx0 = 0; it.mbs = mbs; it.nb = nb;
-    it.table = 0xFFFFFFFFu;                                          /* no table in shared memory yet */
-
-    int item = blockIdx.x;
-    if (item >= P.nitems) return;
-    if (tid < 2 * (NQ + 1)) reinterpret_cast<int *>(qs2)[tid] = 0;
-
-    /* entries of the first row */
-    uint32_t e_cur[ROUNDS];
-    {
-        const unsigned f = (unsigned)item / (unsigned)mbh;
-        const int my = item - (int)f * mbh;
-        const uint32_t *src = P.ent + (f * (unsigned)P.nblk + (unsigned)(my * mbw) * 6u);
-#pragma unroll
-        for (int r = 0; r < ROUNDS; r++) e_cur[r] = (r * IDCT_THREADS + tid) < nb ? src[pp[r].i] : 0u;
-    }
-
-    for (int k = 0; item < P.nitems; k++, item += gridDim.x) {
-        const int b = k & 1;
-        uint8_t *tile = tiles + b * tile_bytes;
-        QueueSmem *qs = qs2 + b;
-        it.f = (unsigned)item / (unsigned)mbh;
-        it.my = item - (int)it.f * mbh;
-        it.strip_blk0 = (unsigned)(it.my * mbw) * 6u;
-        it.frame_blk0 = it.f * (unsigned)P.nblk + it.strip_blk0;
-
-        /* fetch the next row's entries now; they are consumed one iteration later */
-        uint32_t e_next[ROUNDS];
-        {
-            const int nitem = item + gridDim.x;
-            const bool have = nitem < P.nitems;
-            const unsigned nf = have ? (unsigned)nitem / (unsigned)mbh : 0u;
-            const int nmy = have ? nitem - (int)nf * mbh : 0;
-            const uint32_t *src = P.ent + (nf * (unsigned)P.nblk + (unsigned)(nmy * mbw) * 6u);
-#pragma unroll
-            for (int r = 0; r < ROUNDS; r++) e_next[r] = (have && (r * IDCT_THREADS + tid) < nb) ? src[pp[r].i] : 0u;
-        }
-
-        /* the frame's tables: reloaded into shared memory only when they change */
-        const rtjgpu_frame_desc fd = P.desc[it.f];
-        if (fd.table != it.table) {                                  /* uniform over the CTA */
-            __syncthreads();                                         /* pass 2 of the previous row still reads iq */
-            const rtj_dev_table *tb = &P.tables[fd.table];
-            iq[tid >> 6][tid & 63] = tb->iq[tid >> 6][tid & 63];     /* IDCT_THREADS == 128 entries */
-            item_set_frame(it, P, fd, tb);
-            __syncthreads();
-        } else {
-            it.frame_pay = P.stream + fd.offset + RTJPEG_B200_HEADER_BYTES;
-        }
-
-#pragma unroll
-        for (int r = 0; r < ROUNDS; r++) {
-            const int p = r * IDCT_THREADS + tid;
-            if (r * IDCT_THREADS < nb)                               /* uniform */
-                k2_pass1(P, it, iq, qs, s_qe, s_qp, tile, p, pp[r], e_cur[r], lane);
-        }
-        __syncthreads();
-        const int nH = k2_pass2(P, it, iq, qs, s_qe, s_qp, tile, lane);
-        if (tid < NQ + 1) reinterpret_cast<int *>(qs2 + (b ^ 1))[tid] = 0;   /* the other set: idle since the last row */
-
-        /* the strip leaves the SM: generic-proxy writes made visible to the async proxy, the store that
-         * read the OTHER strip (issued one row ago) finished, then three bulk stores by one thread */
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        __syncthreads();
-        if (tid == 0 && nH != nb) {                                  /* a row made of HARD blocks only has nothing to say */
-            uint8_t *oy = P.out + (size_t)it.f * fsz + (size_t)(it.my * 16) * P.w;
-            uint8_t *ou = P.out + (size_t)it.f * fsz + (size_t)P.w * P.h + (size_t)(it.my * 8) * cw;
-            uint8_t *ov = ou + (size_t)cw * (P.h >> 1);
+    if (SINGLE) {
+        /* 16 luma rows and 2 x 8 chroma rows are each one contiguous run in the tight-pitch planes:
+         * three TMA bulk stores issued by one thread */
+        if (tid == 0) {
             bulk_store(oy, tile, 256u * (unsigned)mbs);
-            bulk_store(ou, tile + 256 * mbs, 64u * (unsigned)mbs);
-            bulk_store(ov, tile + 320 * mbs, 64u * (unsigned)mbs);
+            bulk_store(ou, tileU, 64u * (unsigned)mbs);
+            bulk_store(ov, tileV, 64u * (unsigned)mbs);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         }
-#pragma unroll
-        for (int r = 0; r < ROUNDS; r++) e_cur[r] = e_next[r];
+    } else {
+        const int segW = 16 * mbs, segC = 8 * mbs;
+        for (int r = warp; r < 16; r += K2_WARPS)
+            for (int c = lane; c < mbs; c += 32)                 /* 16-byte vectors per luma row */
+                *reinterpret_cast<uint4 *>(oy + (size_t)r * w + c * 16) =
+                    *reinterpret_cast<const uint4 *>(tile + r * segW + c * 16);
+        for (int r = warp; r < 16; r += K2_WARPS) {
+            const int pl = r >> 3, rr = r & 7;
+            for (int c = lane; c < mbs; c += 32)                 /* 8-byte vectors per chroma row */
+                *reinterpret_cast<uint2 *>((pl ? ov : ou) + (size_t)rr * cw + c * 8) =
+                    *reinterpret_cast<const uint2 *>((pl ? tileV : tileU) + rr * segC + c * 8);
+        }
     }
-    if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
 /* ------------------------------------------------------------------------ */
@@ -804,52 +676,26 @@ inline int idct_seg_mb(int mbw, int *nstrips)
     return (mbw + n - 1) / n;
 }
 
-inline size_t idct_smem_bytes(int seg_mb, int tiles)
+inline size_t idct_smem_bytes(int seg_mb)
 {
-    const size_t nb = (size_t)seg_mb * 6;
-    size_t s = (size_t)seg_mb * 16 * 24 * (size_t)tiles;   /* Y 16 rows + U,V 8 rows of half width */
-    s += 2 * 64 * sizeof(int);
-    s += 2 * sizeof(QueueSmem);
-    s += nb * (4 + 4) * NQ;
+    size_t s = (size_t)seg_mb * 16 * 24;             /* Y 16 rows + U,V 8 rows of half width */
+    s += 16;                                         /* counters */
+    s += (size_t)2 * K2_WARPS * K2_WQ * 4;           /* warp queues */
     return (s + 15) & ~(size_t)15;
 }
 
 int g_sm_count = 0;
-
-template <int ROUNDS>
-cudaError_t rows_attr()
-{
-    return cudaFuncSetAttribute(rtj_idct_rows_kernel<ROUNDS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)idct_smem_bytes(IDCT_MAX_MB, 2));
-}
-
-template <int ROUNDS>
-cudaError_t rows_launch(const K2Params &P, int mbw, cudaStream_t st)
-{
-    const size_t smem = idct_smem_bytes(mbw, 2);
-    int per_sm = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rtj_idct_rows_kernel<ROUNDS>, IDCT_THREADS, smem);
-    if (e != cudaSuccess) return e;
-    if (per_sm < 1) per_sm = 1;
-    const int sms = g_sm_count > 0 ? g_sm_count : 148;
-    const int grid = P.nitems < sms * per_sm ? P.nitems : sms * per_sm;
-    rtj_idct_rows_kernel<ROUNDS><<<grid, IDCT_THREADS, smem, st>>>(P);
-    return cudaGetLastError();
-}
 
 } // namespace
 
 extern "C" int rtj_idct_init(void)
 {
     int nstrips;
-    const size_t worst = idct_smem_bytes(idct_seg_mb(IDCT_MAX_MB, &nstrips), 1);
-    cudaError_t e = cudaFuncSetAttribute(rtj_idct_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)worst);
+    const size_t worst = idct_smem_bytes(idct_seg_mb(IDCT_MAX_MB, &nstrips));
+    cudaError_t e = cudaFuncSetAttribute(rtj_idct_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)worst);
     if (e != cudaSuccess) return (int)e;
-    if ((e = rows_attr<1>()) != cudaSuccess) return (int)e;
-    if ((e = rows_attr<2>()) != cudaSuccess) return (int)e;
-    if ((e = rows_attr<3>()) != cudaSuccess) return (int)e;
-    if ((e = rows_attr<4>()) != cudaSuccess) return (int)e;
-    if ((e = rows_attr<6>()) != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(rtj_idct_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)worst);
+    if (e != cudaSuccess) return (int)e;
     int dev = 0;
     if ((e = cudaGetDevice(&dev)) != cudaSuccess) return (int)e;
     if ((e = cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return (int)e;
@@ -865,20 +711,12 @@ extern "C" int rtj_launch_idct(const rtj_launch_args *a, void *stream)
     P.nblk = mbw * mbh * 6; P.w = a->w; P.h = a->h;
     P.seg_mb = idct_seg_mb(mbw, &P.nstrips);
     P.out = a->d_out; P.carry = a->d_carry; P.hardq = a->d_hardq; P.info = a->d_info;
-    P.nitems = a->F * mbh;
-    cudaError_t e;
-    if (P.nstrips == 1) {
-        const int rounds = (mbw * 6 + IDCT_THREADS - 1) / IDCT_THREADS;
-        if (rounds <= 1) e = rows_launch<1>(P, mbw, st);
-        else if (rounds == 2) e = rows_launch<2>(P, mbw, st);
-        else if (rounds == 3) e = rows_launch<3>(P, mbw, st);
-        else if (rounds == 4) e = rows_launch<4>(P, mbw, st);
-        else e = rows_launch<6>(P, mbw, st);
-    } else {
-        dim3 grid((unsigned)(P.nstrips * mbh), (unsigned)a->F);
-        rtj_idct_strip_kernel<<<grid, IDCT_THREADS, idct_smem_bytes(P.seg_mb, 1), st>>>(P);
-        e = cudaGetLastError();
-    }
+    dim3 grid((unsigned)(P.nstrips * mbh), (unsigned)a->F);
+    if (P.nstrips == 1)
+        rtj_idct_kernel<true><<<grid, IDCT_THREADS, idct_smem_bytes(P.seg_mb), st>>>(P);
+    else
+        rtj_idct_kernel<false><<<grid, IDCT_THREADS, idct_smem_bytes(P.seg_mb), st>>>(P);
+    cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
     /* the queue's length is only known on the device: a fixed grid strides over it */
     const int sms = g_sm_count > 0 ? g_sm_count : 148;

@@ -339,32 +339,31 @@ __device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, unsigne
  */
 struct PicPos {
     int i;          /* stream-order index inside the strip */
-    int off;        /* byte offset of the block's first row inside the shared strip */
-    int pitch;      /* row pitch there */
-    bool chroma;
+    int off;        /* byte offset of the block's first row inside the shared strip (< 65536) */
 };
 
+/* branch-free; luma positions come first */
 __device__ __forceinline__ PicPos pic_pos(int p, int mbs)
 {
+    const bool luma = p < 4 * mbs;
+    const int half = luma ? 2 * mbs : mbs;
+    const int t = luma ? p : p - 4 * mbs;
+    const int hi = t >= half ? 1 : 0;
+    const int c = t - (hi ? half : 0);
     PicPos r;
-    if (p < 4 * mbs) {
-        const int hi = p >= 2 * mbs ? 1 : 0, c = p - hi * 2 * mbs;
-        r.i = 3 * c - 2 * (c & 1) + 2 * hi;               /* 6 * (c >> 1) + 2 * hi + (c & 1) */
-        r.off = hi * 128 * mbs + 8 * c;
-        r.pitch = 16 * mbs;
-        r.chroma = false;
-    } else {
-        const int pc = p - 4 * mbs, hi = pc >= mbs ? 1 : 0;
-        r.i = 6 * (pc - hi * mbs) + 4 + hi;
-        r.off = 256 * mbs + 8 * pc + hi * 56 * mbs;        /* V follows the 8 rows of U */
-        r.pitch = 8 * mbs;
-        r.chroma = true;
-    }
+    r.i = luma ? 3 * c - 2 * (c & 1) + 2 * hi              /* 6 * (c >> 1) + 2 * hi + (c & 1) */
+               : 6 * c + 4 + hi;
+    r.off = 8 * c + (luma ? hi * 128 * mbs : (256 + hi * 64) * mbs);     /* V follows the 8 rows of U */
     return r;
 }
 
-__device__ __forceinline__ void store_block(uint8_t *dst, int pitch, const uint32_t (&px)[16])
+/* the strip holds 16 luma rows of 16*mbs bytes, then 8 U rows and 8 V rows of 8*mbs bytes */
+__device__ __forceinline__ bool off_is_chroma(int off, int mbs) { return off >= 256 * mbs; }
+
+__device__ __forceinline__ void store_block(uint8_t *tile, int off, int mbs, const uint32_t (&px)[16])
 {
+    uint8_t *dst = tile + off;
+    const int pitch = off_is_chroma(off, mbs) ? 8 * mbs : 16 * mbs;
 #pragma unroll
     for (int r = 0; r < 8; r++)
         *reinterpret_cast<uint2 *>(dst + r * pitch) = make_uint2(px[2 * r], px[2 * r + 1]);
@@ -427,7 +426,8 @@ rtj_idct_kernel(const K2Params P)
     /* everything that does not depend on anything else is fetched first: the first round's entry
      * and the frame descriptor; the table constants follow the descriptor */
     const int rounds = (nb + IDCT_THREADS - 1) / IDCT_THREADS;
-    uint32_t e_first = tid < nb ? my_ent[pic_pos(tid, mbs).i] : 0u;
+    PicPos pp_next = pic_pos(tid, mbs);
+    uint32_t e_first = tid < nb ? my_ent[pp_next.i] : 0u;
     const rtjgpu_frame_desc fd = P.desc[f];
     const unsigned mytable = fd.table;
     const rtj_dev_table *tb = &P.tables[mytable];
@@ -441,11 +441,12 @@ rtj_idct_kernel(const K2Params P)
     int nfront = 0, nback = 0;                               /* warp-uniform queue fill: M7 | CARRY, HARD */
     for (int r = 0; r < rounds; r++) {
         const int p = r * IDCT_THREADS + tid;
-        const PicPos pp = pic_pos(p, mbs);
+        const PicPos pp = pp_next;
+        const bool chroma = off_is_chroma(pp.off, mbs);
         uint32_t e = e_first;
         if (r + 1 < rounds) {                                /* next round's entry: in flight during this round */
-            const int pn = p + IDCT_THREADS;
-            e_first = pn < nb ? my_ent[pic_pos(pn, mbs).i] : 0u;
+            pp_next = pic_pos(p + IDCT_THREADS, mbs);
+            e_first = p + IDCT_THREADS < nb ? my_ent[pp_next.i] : 0u;
         }
         int cls = CLS_NONE;
         int x0 = 0, x1 = 0, q = 0;
@@ -463,9 +464,9 @@ rtj_idct_kernel(const K2Params P)
             else if (sf != f && P.desc[sf].table != mytable) cls = Q_HARD;
             else if (RTJ_ENT_IS_INLINE(e)) {
                 cls = CLS_T2;
-                x0 = wrap16((int)(e & 0xFFu) * (pp.chroma ? cq0 : lq0)) + 4;
-                x1 = wrap16((int)(signed char)((e >> 8) & 0xFFu) * (pp.chroma ? cq1 : lq1));
-                q = wrap16((int)(signed char)((e >> 16) & 0xFFu) * (pp.chroma ? cq2 : lq2));
+                x0 = wrap16((int)(e & 0xFFu) * (chroma ? cq0 : lq0)) + 4;
+                x1 = wrap16((int)(signed char)((e >> 8) & 0xFFu) * (chroma ? cq1 : lq1));
+                q = wrap16((int)(signed char)((e >> 16) & 0xFFu) * (chroma ? cq2 : lq2));
             } else {
                 const int eob = RTJ_ENT_EOB(e);
                 if (eob <= 3) {
@@ -474,7 +475,7 @@ rtj_idct_kernel(const K2Params P)
                                          + (e & RTJ_ENT_OFF_MASK);
                     RegBytes<1> by(src);
                     int x[3];
-                    unpack_block<3>(by, tb->iq[pp.chroma], pp.chroma ? bt8_c : bt8_l, x);
+                    unpack_block<3>(by, tb->iq[chroma], chroma ? bt8_c : bt8_l, x);
                     x0 = x[0]; x1 = x[1]; q = x[2];
                 } else if (eob <= 7) cls = Q_M7;
                 else cls = Q_HARD;
@@ -485,7 +486,7 @@ rtj_idct_kernel(const K2Params P)
         if (cls == CLS_T2) {
             uint32_t px[16];
             t2_pixels(x0, x1, q, packed, px);
-            store_block(tile + pp.off, pp.pitch, px);
+            store_block(tile, pp.off, mbs, px);
         }
         const unsigned mM = __ballot_sync(FULL, cls == Q_M7);
         const unsigned mB = __ballot_sync(FULL, cls == Q_CARRY || cls == Q_HARD);
@@ -493,11 +494,11 @@ rtj_idct_kernel(const K2Params P)
         if (cls == Q_M7) {
             const int at = nfront + __popc(mM & below);
             wq_e[at] = e;
-            wq_p[at] = (uint32_t)p | (sf << 16);
+            wq_p[at] = (uint32_t)pp.off | (sf << 16);
         } else if (cls == Q_CARRY || cls == Q_HARD) {
             const int at = K2_WQ - 1 - (nback + __popc(mB & below));
-            wq_e[at] = cls == Q_CARRY ? RTJ_ENT_SKIP : e;
-            wq_p[at] = (uint32_t)p | (sf << 16);
+            wq_e[at] = (uint32_t)pp.i | (cls == Q_CARRY ? 0x80000000u : 0u);
+            wq_p[at] = (uint32_t)pp.off;
         }
         nfront += __popc(mM);
         nback += __popc(mB);
@@ -509,22 +510,23 @@ rtj_idct_kernel(const K2Params P)
         const int idx = c0 + lane;
         int x[7] = {1008, 0, 0, 0, 0, 0, 0};
         const bool live = idx < nfront;
-        PicPos pp = pic_pos(0, mbs);
+        int off = 0;
         if (live) {
             const uint32_t e = wq_e[idx];
             const uint32_t ps = wq_p[idx];
             const unsigned sf = ps >> 16;
-            pp = pic_pos((int)(ps & 0xFFFFu), mbs);
+            off = (int)(ps & 0xFFFFu);
+            const bool chroma = off_is_chroma(off, mbs);
             const uint8_t *src = (sf == f ? frame_pay : P.stream + P.desc[sf].offset + RTJPEG_B200_HEADER_BYTES)
                                  + (e & RTJ_ENT_OFF_MASK);
             RegBytes<2> by(src);
-            unpack_block<7>(by, tb->iq[pp.chroma], pp.chroma ? bt8_c : bt8_l, x);
+            unpack_block<7>(by, tb->iq[chroma], chroma ? bt8_c : bt8_l, x);
         }
         const bool packed = __all_sync(FULL, m7_safe(x));
         if (live) {
             uint32_t px[16];
             m7_pixels(x, packed, px);
-            store_block(tile + pp.off, pp.pitch, px);
+            store_block(tile, off, mbs, px);
         }
     }
     /* ---- CARRY blocks are copied from the picture before the batch, HARD blocks leave for
@@ -534,22 +536,23 @@ rtj_idct_kernel(const K2Params P)
         for (int c0 = 0; c0 < nback; c0 += 32) {
             const int idx = c0 + lane;
             const bool live = idx < nback;
-            uint32_t e = RTJ_ENT_SKIP, ps = 0;
-            if (live) { e = wq_e[K2_WQ - 1 - idx]; ps = wq_p[K2_WQ - 1 - idx]; }
-            const bool hard = live && !RTJ_ENT_IS_SKIP(e);
-            const PicPos pp = pic_pos((int)(ps & 0xFFFFu), mbs);
+            uint32_t ie = 0x80000000u;
+            int off = 0;
+            if (live) { ie = wq_e[K2_WQ - 1 - idx]; off = (int)wq_p[K2_WQ - 1 - idx]; }
+            const bool hard = live && !(ie >> 31);
+            const int bi = (int)(ie & 0x7FFFFFFFu);              /* stream-order index inside the strip */
             const unsigned mH = __ballot_sync(FULL, hard);
             if (mH) {
                 unsigned base = 0;
                 if (lane == 0) base = atomicAdd(&P.info->hard_blocks, (unsigned)__popc(mH));
                 base = __shfl_sync(FULL, base, 0);
-                if (hard) P.hardq[base + __popc(mH & ((1u << lane) - 1u))] = frame_blk0 + (unsigned)pp.i;
+                if (hard) P.hardq[base + __popc(mH & ((1u << lane) - 1u))] = frame_blk0 + (unsigned)bi;
                 nhard += __popc(mH);
             }
             if (live && !hard) {
                 uint32_t px[16];
                 if (P.carry) {
-                    const int mb = pp.i / 6, sub = pp.i - mb * 6;
+                    const int mb = bi / 6, sub = bi - mb * 6;
                     const uint8_t *cp;
                     int pitch;
                     if (sub < 4) {
@@ -570,7 +573,7 @@ rtj_idct_kernel(const K2Params P)
 #pragma unroll
                     for (int r = 0; r < 16; r++) px[r] = 0;
                 }
-                store_block(tile + pp.off, pp.pitch, px);
+                store_block(tile, off, mbs, px);
             }
         }
     }

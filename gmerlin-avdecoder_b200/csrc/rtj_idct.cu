@@ -390,12 +390,11 @@ constexpr int K2_WQ = K2_ROUNDS_MAX * 32;          /* queue slots of one warp: e
 } // namespace
 
 /*
- * One CTA per (frame, macroblock row [, strip]).  Warps work on their own: a warp takes 32
- * picture positions per round, decodes the T2 blocks among them at once and parks the others in
- * its private queue (M7 from the front, CARRY / HARD from the back); after its last round it
- * decodes its M7 blocks in one go (a warp sees ~20 of them per macroblock row of typical
- * material, so one pass of the M7 flow graph serves them all), copies CARRY blocks and hands HARD
- * blocks to the device queue.  No block-wide barrier until the picture strip is complete.
+ * One CTA per (frame, macroblock row [, strip]).  A warp takes 32 picture positions per round,
+ * decodes the T2 blocks among them at once and parks the others in its own queue (M7 from the
+ * front, CARRY / HARD from the back), without atomics.  After one barrier the M7 blocks of all
+ * warps are decoded pooled, 32 per pass; CARRY blocks are copied and HARD blocks handed to the
+ * device queue by the warp that found them.  A second barrier, and the picture strip leaves.
  *
  * SINGLE: the strip is the whole macroblock row (frames up to IDCT_MAX_MB macroblocks wide): no
  * strip arithmetic, and the strip is contiguous in the tight-pitch output planes -> TMA bulk stores.
@@ -420,8 +419,8 @@ rtj_idct_kernel(const K2Params P)
     uint8_t *tile = smem;                                            /* 384 * mbs bytes: Y, U, V */
     int *s_hard = reinterpret_cast<int *>(tile + 384 * mbs);         /* HARD blocks of the strip, per warp */
     static_assert(K2_WARPS == 4, "s_hard holds four counters");
-    uint32_t *wq_e = reinterpret_cast<uint32_t *>(s_hard + 4) + warp * K2_WQ;      /* this warp's queue: entries ... */
-    uint32_t *wq_p = reinterpret_cast<uint32_t *>(s_hard + 4) + (K2_WARPS + warp) * K2_WQ;   /* ... picture index | source << 16 */
+    uint32_t *wq_e = reinterpret_cast<uint32_t *>(s_hard + 8) + warp * K2_WQ;      /* this warp's queue: entries ... */
+    uint32_t *wq_p = reinterpret_cast<uint32_t *>(s_hard + 8) + (K2_WARPS + warp) * K2_WQ;   /* ... strip offset | source << 16 */
 
     /* everything that does not depend on anything else is fetched first: the first round's entry
      * and the frame descriptor; the table constants follow the descriptor */
@@ -503,17 +502,26 @@ rtj_idct_kernel(const K2Params P)
         nfront += __popc(mM);
         nback += __popc(mB);
     }
-    __syncwarp();
-
-    /* ---- pass 2, still warp-private: the M7 blocks, 32 at a time ---- */
-    for (int c0 = 0; c0 < nfront; c0 += 32) {
+    /* ---- pass 2: the M7 blocks of all four warps pooled, 32 at a time (a macroblock row of typical
+     *      material holds ~55 of them: two full passes of the flow graph instead of four part-filled
+     *      ones).  The queues stay where the warps wrote them; an index is mapped to (warp, slot)
+     *      through the four counts. ---- */
+    if (lane == 0) s_hard[4 + warp] = nfront;
+    __syncthreads();
+    const int n0 = s_hard[4], n1 = n0 + s_hard[5], n2 = n1 + s_hard[6], nM = n2 + s_hard[7];
+    const uint32_t *q_e = reinterpret_cast<const uint32_t *>(s_hard + 8);
+    const uint32_t *q_p = q_e + K2_WARPS * K2_WQ;
+    /* the last warps start first: warp 0 is the one with a part-filled extra round behind it */
+    for (int c0 = (K2_WARPS - 1 - warp) * 32; c0 < nM; c0 += K2_WARPS * 32) {
         const int idx = c0 + lane;
         int x[7] = {1008, 0, 0, 0, 0, 0, 0};
-        const bool live = idx < nfront;
+        const bool live = idx < nM;
         int off = 0;
         if (live) {
-            const uint32_t e = wq_e[idx];
-            const uint32_t ps = wq_p[idx];
+            const int qw = (idx >= n0) + (idx >= n1) + (idx >= n2);
+            const int at = qw * K2_WQ + idx - (qw == 0 ? 0 : qw == 1 ? n0 : qw == 2 ? n1 : n2);
+            const uint32_t e = q_e[at];
+            const uint32_t ps = q_p[at];
             const unsigned sf = ps >> 16;
             off = (int)(ps & 0xFFFFu);
             const bool chroma = off_is_chroma(off, mbs);
@@ -682,7 +690,7 @@ inline int idct_seg_mb(int mbw, int *nstrips)
 inline size_t idct_smem_bytes(int seg_mb)
 {
     size_t s = (size_t)seg_mb * 16 * 24;             /* Y 16 rows + U,V 8 rows of half width */
-    s += 16;                                         /* counters */
+    s += 32;                                         /* counters */
     s += (size_t)2 * K2_WARPS * K2_WQ * 4;           /* warp queues */
     return (s + 15) & ~(size_t)15;
 }

@@ -36,12 +36,12 @@
 
 namespace {
 
-constexpr int CS_THREADS = 256;
-constexpr int CS_S = 16384;                        /* segment bytes */
+constexpr int CS_THREADS = 128;
+constexpr int CS_S = 8192;                         /* segment bytes */
 constexpr int CS_C = 128;                          /* chunk bytes (>= 64, multiple of 64) */
 constexpr int CS_NCH = CS_S / CS_C;                /* chunks per segment = DP lanes */
 constexpr int CS_LA = 128;                         /* look-ahead bytes behind a segment */
-constexpr int CS_RING = 66;                        /* u16 per chunk ring: 64 live + pad to 33 words (bank skew) */
+constexpr int CS_RING = 82;                        /* u16 per chunk ring: 64 live + pad to 33 words (bank skew) */
 constexpr int CS_STAGE = CS_NCH * CS_RING / 2;     /* staged entries per emit round (aliases the rings) */
 constexpr int CS_PAY_WORDS = (CS_S + CS_LA + 16) / 4;
 constexpr int CS_DEL_WORDS = CS_NCH * (CS_C / 4 + 1);   /* one pad word per chunk (bank skew) */
@@ -91,7 +91,7 @@ __device__ __noinline__ int cs_long_block(const uint32_t *payw, int tb, int fill
 
 } // namespace
 
-extern "C" __global__ void __launch_bounds__(CS_THREADS, 4)
+extern "C" __global__ void __launch_bounds__(CS_THREADS, 8)
 rtj_scan_chunk_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc *__restrict__ desc,
                       const rtj_dev_table *__restrict__ tables, int F, int nblk,
                       uint32_t *__restrict__ ent, uint32_t *__restrict__ frame_skips,

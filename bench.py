@@ -5,7 +5,7 @@
     python bench.py --impl reference [--gpus N] [--steps K] ...       # the reference's CPU decoder
     torchrun --nproc-per-node N ... bench.py --gpus N ...             # one rank per GPU
 
-A "step" is one pass of the hot path (K1 scan -> K3 resolve -> K2 idct) over one batch of
+A "step" is one pass of the hot path (K1 scan -> K3 resolve -> K2 idct -> K2b hard blocks) over one batch of
 4096 synthetic 720x576 frames (BASELINE.json configs[1]: intra-only, Q=128).  The batch is
 produced once, outside every timed region, by the reference's own RTjpeg_compress
 (oracle/_ref, as north_star prescribes for the synthetic streams) from the seeded source in
@@ -272,7 +272,7 @@ def main():
     if rank == 0:
         peak, peak_src = measured_hbm_peak()
         dom = max(stage_ms, key=stage_ms.get)
-        kname = {"scan": "rtj_scan_lane_kernel" if F >= 512 else "rtj_scan_warp_kernel", "resolve": "rtj_resolve_kernel", "idct": "rtj_idct_kernel"}[dom]
+        kname = {"scan": "rtj_scan_chunk_kernel", "resolve": "rtj_resolve_kernel", "idct": "rtj_idct_kernel"}[dom]
         achieved = algo_bytes / (stage_ms[dom] * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world,

@@ -162,21 +162,27 @@ rtj_scan_chunk_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_des
                 /* tokens of a block starting at q0 + i: bytes q0+i+1 .. */
                 const uint32_t x0 = i == 3 ? X1 : __funnelshift_r(X0, X1, 8 * (i + 1));
                 const uint32_t x1 = i == 3 ? X2 : __funnelshift_r(X1, X2, 8 * (i + 1));
-                /* byte k of P = positions filled by tokens 0..k; bit 7 of (P + 65) set <=> >= 63 filled.
-                 * Overflows can only happen behind the first crossing and never disturb it. */
-                const uint32_t P0 = x0 * 0x01010101u + 0x04030201u;
+                /* byte k of P = 65 + positions filled by tokens 0..k, so bit 7 <=> >= 63 filled.  Overflows
+                 * can only happen behind the first crossing and never disturb it.  The top byte of P0 less
+                 * 65 carries the first four tokens' fill into P1: 0x45444342 - 65 * 0x01010101 = 0x04030201. */
+                const uint32_t P0 = x0 * 0x01010101u + 0x45444342u;
                 const uint32_t P1 = x1 * 0x01010101u + 0x04030201u + (P0 >> 24) * 0x01010101u;
-                const uint32_t c0 = (P0 + 0x41414141u) & 0x80808080u;
-                const uint32_t c1 = (P1 + 0x41414141u) & 0x80808080u;
+                const uint32_t c0 = P0 & 0x80808080u;
+                const uint32_t c1 = P1 & 0x80808080u;
                 int dl;
                 if (c0 | c1) {
                     const int bit = c0 ? __ffs((int)c0) - 1 : 31 + __ffs((int)c1);
                     dl = (bit >> 3) + 2;                                /* DC byte + tokens */
                 } else {
-                    dl = 1 + cs_long_block(sh.pay, q0 + mis + i + 1, (int)(P1 >> 24));
+                    dl = 1 + cs_long_block(sh.pay, q0 + mis + i + 1, (int)(P1 >> 24) - 65);
                 }
-                if (((W0 >> (8 * i)) & 0xFFu) == 0xFFu) dl = 1;         /* skipped block: one byte, lib/RTjpeg.c:2704 */
                 packed |= (uint32_t)dl << (8 * i);
+            }
+            {   /* skipped blocks (lib/RTjpeg.c:2704): a byte 0xFF is a block of its own, one byte long */
+                const uint32_t y = ~W0;
+                const uint32_t z = ~(((y & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | y | 0x7F7F7F7Fu);      /* bit 7 of every byte of W0 that is 0xFF */
+                const uint32_t m = (z >> 7) * 0xFFu;
+                packed = (packed & ~m) | (0x01010101u & m);
             }
             sh.del[(q0 >> 2) + (q0 / CS_C)] = packed;
         }

@@ -24,6 +24,7 @@ struct Workspace {
     uint32_t     *d_ent = nullptr;
     uint16_t     *d_src = nullptr;
     uint32_t     *d_hardq = nullptr;
+    uint16_t     *d_chunk_last = nullptr;
     uint32_t     *d_frame_skips = nullptr;
     rtj_dev_info *d_info = nullptr;
     size_t        cap_entries = 0;
@@ -92,10 +93,12 @@ int ws_reserve(rtjgpu_ctx *ctx, Workspace *ws, int F, int nblk)
         if (ws->d_ent) cudaFree(ws->d_ent);
         if (ws->d_src) cudaFree(ws->d_src);
         if (ws->d_hardq) cudaFree(ws->d_hardq);
-        ws->d_ent = nullptr; ws->d_src = nullptr; ws->d_hardq = nullptr; ws->cap_entries = 0;
+        if (ws->d_chunk_last) cudaFree(ws->d_chunk_last);
+        ws->d_ent = nullptr; ws->d_src = nullptr; ws->d_hardq = nullptr; ws->d_chunk_last = nullptr; ws->cap_entries = 0;
         CK(ctx, cudaMalloc(&ws->d_ent, need * sizeof(uint32_t)));
         CK(ctx, cudaMalloc(&ws->d_src, need * sizeof(uint16_t)));
         CK(ctx, cudaMalloc(&ws->d_hardq, need * sizeof(uint32_t)));
+        CK(ctx, cudaMalloc(&ws->d_chunk_last, need * sizeof(uint16_t)));   /* ceil(F / 32) rows of nblk: at most F * nblk */
         ws->cap_entries = need;
     }
     if (F > ws->cap_frames) {
@@ -113,6 +116,7 @@ void ws_release(Workspace *ws)
     if (ws->d_ent) cudaFree(ws->d_ent);
     if (ws->d_src) cudaFree(ws->d_src);
     if (ws->d_hardq) cudaFree(ws->d_hardq);
+    if (ws->d_chunk_last) cudaFree(ws->d_chunk_last);
     if (ws->d_frame_skips) cudaFree(ws->d_frame_skips);
     if (ws->d_info) cudaFree(ws->d_info);
     *ws = Workspace();
@@ -126,7 +130,7 @@ int run_kernels(rtjgpu_ctx *ctx, Workspace *ws, const uint8_t *d_stream, const r
     a.d_stream = d_stream; a.d_desc = d_desc; a.d_tables = ctx->d_tables;
     a.F = F; a.w = w; a.h = h;
     a.d_ent = ws->d_ent; a.d_src = ws->d_src; a.d_frame_skips = ws->d_frame_skips; a.d_info = ws->d_info;
-    a.d_hardq = ws->d_hardq;
+    a.d_hardq = ws->d_hardq; a.d_chunk_last = ws->d_chunk_last;
     a.d_out = d_out; a.d_carry = d_carry;
     a.scan_mode = ctx->scan_mode;
 
@@ -142,7 +146,7 @@ int run_kernels(rtjgpu_ctx *ctx, Workspace *ws, const uint8_t *d_stream, const r
     e = rtj_launch_idct(&a, st);
     if (e) { ctx->last_cuda = e; return RTJGPU_E_CUDA; }
     if (ev) CK(ctx, cudaEventRecord(ev[3], st));
-    ctx->launches += 3;                     /* K3, K2, K2b */
+    ctx->launches += 4;                     /* K3 (two kernels), K2, K2b */
     return RTJGPU_OK;
 }
 

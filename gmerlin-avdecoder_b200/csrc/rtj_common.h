@@ -81,6 +81,7 @@ typedef struct rtj_launch_args {
     uint32_t                *d_frame_skips; /* [F] */
     rtj_dev_info            *d_info;
     uint32_t                *d_hardq;       /* [F * nblk] global block indices queued for K2b */
+    uint16_t                *d_chunk_last;  /* [ceil(F / 32)][nblk] K3: last writer inside each chunk of frames */
     uint8_t                 *d_out;
     const uint8_t           *d_carry;
     int                      scan_mode;     /* RTJGPU_SCAN_* */

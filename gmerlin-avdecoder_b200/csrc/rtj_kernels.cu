@@ -309,17 +309,51 @@ rtj_scan_lane_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc
 /* K3: last-writer resolution of skipped blocks                               */
 /* ------------------------------------------------------------------------ */
 
+/*
+ * Two kernels over (block position, chunk of RESOLVE_T frames), so that the scan over the batch's
+ * frames -- serial in the reference, where it is simply "the picture persists" -- is spread over
+ * F / RESOLVE_T times nblk threads:
+ *   rtj_resolve_last_kernel   last frame of the chunk that coded the position (or none)
+ *   rtj_resolve_kernel        carry-in = nearest earlier chunk with a writer (a short look-back,
+ *                             usually one step), then the walk over the chunk's own frames that
+ *                             gives every skipped block its last writer.
+ */
+constexpr int RESOLVE_T = 32;
+
 extern "C" __global__ void __launch_bounds__(128)
-rtj_resolve_kernel(const uint32_t *__restrict__ ent, uint16_t *__restrict__ src, int F, int nblk,
-                   const rtj_dev_info *__restrict__ info)
+rtj_resolve_last_kernel(const uint32_t *__restrict__ ent, uint16_t *__restrict__ chunk_last, int F, int nblk,
+                        const rtj_dev_info *__restrict__ info)
 {
     if (info->skipped_blocks == 0) return;           /* intra-only batch: nothing to resolve */
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nblk) return;
+    const int f0 = blockIdx.y * RESOLVE_T, f1 = min(F, f0 + RESOLVE_T);
     unsigned last = RTJ_SRC_CARRY;
-    int f = 0;
-    for (; f + 8 <= F; f += 8) {
-        uint32_t e[8];
+    uint32_t e[8];
+    int f = f0;
+    for (; f + 8 <= f1; f += 8) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) e[j] = ent[(size_t)(f + j) * nblk + b];
+#pragma unroll
+        for (int j = 0; j < 8; j++) if (!RTJ_ENT_IS_SKIP(e[j])) last = (unsigned)(f + j);
+    }
+    for (; f < f1; f++) if (!RTJ_ENT_IS_SKIP(ent[(size_t)f * nblk + b])) last = (unsigned)f;
+    chunk_last[(size_t)blockIdx.y * nblk + b] = (uint16_t)last;
+}
+
+extern "C" __global__ void __launch_bounds__(128)
+rtj_resolve_kernel(const uint32_t *__restrict__ ent, const uint16_t *__restrict__ chunk_last,
+                   uint16_t *__restrict__ src, int F, int nblk, const rtj_dev_info *__restrict__ info)
+{
+    if (info->skipped_blocks == 0) return;
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nblk) return;
+    const int f0 = blockIdx.y * RESOLVE_T, f1 = min(F, f0 + RESOLVE_T);
+    unsigned last = RTJ_SRC_CARRY;
+    for (int c = (int)blockIdx.y - 1; c >= 0 && last == RTJ_SRC_CARRY; c--) last = chunk_last[(size_t)c * nblk + b];
+    uint32_t e[8];
+    int f = f0;
+    for (; f + 8 <= f1; f += 8) {
 #pragma unroll
         for (int j = 0; j < 8; j++) e[j] = ent[(size_t)(f + j) * nblk + b];
 #pragma unroll
@@ -328,9 +362,9 @@ rtj_resolve_kernel(const uint32_t *__restrict__ ent, uint16_t *__restrict__ src,
             else last = (unsigned)(f + j);
         }
     }
-    for (; f < F; f++) {
-        const uint32_t e = ent[(size_t)f * nblk + b];
-        if (RTJ_ENT_IS_SKIP(e)) src[(size_t)f * nblk + b] = (uint16_t)last;
+    for (; f < f1; f++) {
+        const uint32_t ee = ent[(size_t)f * nblk + b];
+        if (RTJ_ENT_IS_SKIP(ee)) src[(size_t)f * nblk + b] = (uint16_t)last;
         else last = (unsigned)f;
     }
 }
@@ -374,8 +408,8 @@ extern "C" int rtj_launch_scan(const rtj_launch_args *a, void *stream)
 extern "C" int rtj_launch_resolve(const rtj_launch_args *a, void *stream)
 {
     const int nblk = (a->w >> 4) * (a->h >> 4) * 6;
-    rtj_resolve_kernel<<<(nblk + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
-        a->d_ent, a->d_src, a->F, nblk, a->d_info);
+    dim3 grid((unsigned)((nblk + 127) / 128), (unsigned)((a->F + RESOLVE_T - 1) / RESOLVE_T));
+    rtj_resolve_last_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(a->d_ent, a->d_chunk_last, a->F, nblk, a->d_info);
+    rtj_resolve_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(a->d_ent, a->d_chunk_last, a->d_src, a->F, nblk, a->d_info);
     return (int)cudaGetLastError();
 }
-

@@ -90,6 +90,8 @@ typedef struct rtj_launch_args {
 int rtj_launch_scan(const rtj_launch_args *a, void *stream);          /* returns the number of launches (>0) or -cudaError */
 int rtj_launch_scan_chunk(const rtj_launch_args *a, void *stream);    /* rtj_scan_chunk.cu */
 int rtj_scan_chunk_init(void);
+int rtj_launch_scan_mb(const rtj_launch_args *a, void *stream);       /* rtj_scan_mb.cu */
+int rtj_scan_mb_init(void);
 int rtj_launch_resolve(const rtj_launch_args *a, void *stream);
 int rtj_launch_idct(const rtj_launch_args *a, void *stream);
 int rtj_idct_init(void);      /* rtj_idct.cu */

@@ -373,6 +373,7 @@ extern "C" int rtj_kernels_init(void)
 {
     int e = rtj_idct_init();
     if (e) return e;
+    if ((e = rtj_scan_mb_init())) return e;
     return rtj_scan_chunk_init();
 }
 
@@ -380,29 +381,26 @@ extern "C" int rtj_launch_scan(const rtj_launch_args *a, void *stream)
 {
     const int nblk = (a->w >> 4) * (a->h >> 4) * 6;
     cudaStream_t st = (cudaStream_t)stream;
-    int launches = 0, raw_only = 0;
-    /* AUTO: the chunk-parallel kernel takes every frame without a raw prefix, the serial kernels
-     * the rest.  rtjgpu_set_scan_mode() forces one serial flavour for every frame. */
+    /* AUTO: the chunk-parallel kernels -- rtj_scan_chunk_kernel takes every frame without a raw prefix,
+     * rtj_scan_mb_kernel the others; each returns at once on the other's frames. */
     if (a->scan_mode == RTJGPU_SCAN_AUTO || a->scan_mode == RTJGPU_SCAN_CHUNK) {
         int e = rtj_launch_scan_chunk(a, stream);
         if (e) return -e;
-        launches++;
-        raw_only = 1;
+        e = rtj_launch_scan_mb(a, stream);
+        return e ? -e : 2;
     }
-    /* many frames: one lane per frame (cheap in issue slots, latency hidden by the batch);
-     * few frames: one warp per frame. */
-    const bool lane = a->scan_mode == RTJGPU_SCAN_LANE || (a->scan_mode != RTJGPU_SCAN_WARP && a->F >= 512);
-    if (lane) {
+    /* rtjgpu_set_scan_mode() forces one serial flavour for every frame: one lane per frame (cheap in
+     * issue slots, latency hidden only by very large batches) or one warp per frame. */
+    if (a->scan_mode == RTJGPU_SCAN_LANE) {
         rtj_scan_lane_kernel<<<(a->F + 31) / 32, 32, 0, st>>>(
-            a->d_stream, a->d_desc, a->d_tables, a->F, nblk, a->d_ent, a->d_frame_skips, a->d_info, raw_only);
+            a->d_stream, a->d_desc, a->d_tables, a->F, nblk, a->d_ent, a->d_frame_skips, a->d_info, 0);
     } else {
         const int grid = (a->F + SCAN_WARPS - 1) / SCAN_WARPS;
         rtj_scan_warp_kernel<<<grid, SCAN_WARPS * 32, 0, st>>>(
-            a->d_stream, a->d_desc, a->d_tables, a->F, nblk, a->d_ent, a->d_frame_skips, a->d_info, raw_only);
+            a->d_stream, a->d_desc, a->d_tables, a->F, nblk, a->d_ent, a->d_frame_skips, a->d_info, 0);
     }
-    launches++;
     cudaError_t e = cudaGetLastError();
-    return e == cudaSuccess ? launches : -(int)e;
+    return e == cudaSuccess ? 1 : -(int)e;
 }
 
 extern "C" int rtj_launch_resolve(const rtj_launch_args *a, void *stream)

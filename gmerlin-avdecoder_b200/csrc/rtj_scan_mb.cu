@@ -1,0 +1,311 @@
+/*
+ * rtj_scan_mb.cu -- K1, chunk-parallel flavour for frames whose tables carry a raw 8-bit prefix
+ * (lb8 / cb8 != 0: quality > 170 or custom tables, lib/RTjpeg.c:2362-2367, :2389-2394).
+ *
+ * With a raw prefix the block grammar depends on the block's place in its macroblock (the four
+ * luma blocks use lb8, U and V use cb8, lib/RTjpeg.c:2704-2739), so "the block that starts at p"
+ * is not one function of p any more.  The scheme of rtj_scan_chunk.cu is kept, one level up:
+ *
+ *   level 0   TWO length tables, deltaL(p) and deltaC(p): the block that would start at p under
+ *             the luma and under the chroma grammar (same SIMD-within-a-register token walk,
+ *             shifted by the raw prefix and with the prefix taken off the positions to fill)
+ *   compose   deltaMB(p) = length of a whole MACROBLOCK starting at p: L, L, L, L, C, C chained
+ *   DP        chunks of MB_C bytes, one lane per chunk, right to left over macroblock starts,
+ *             in a ring of 512 entries (a macroblock is at most 6 x 64 bytes long)
+ *   chain     one thread, chunk to chunk; entries are macroblock boundaries, so no grammar
+ *             state travels
+ *   emit      every chunk lane walks its macroblocks and writes six entries for each
+ *
+ * Same outputs, counters and malformed-stream policy as rtj_scan_chunk_kernel.  Blocks coded
+ * under a grammar without prefix (chroma at the standard tables) still go inline when short.
+ */
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "rtj_common.h"
+
+namespace {
+
+constexpr int MB_THREADS = 128;
+constexpr int MB_S = 8192;                          /* segment bytes */
+constexpr int MB_C = 512;                           /* chunk bytes: a power of two >= the longest macroblock (384) */
+constexpr int MB_NCH = MB_S / MB_C;                 /* 16 DP lanes */
+constexpr int MB_MAXLEN = 6 * 64;                   /* longest macroblock */
+constexpr int MB_DLA = MB_MAXLEN;                   /* positions behind the segment that still need a block length */
+constexpr int MB_LA = MB_DLA + 64 + 64 + 32;        /* payload bytes behind the segment that level 0 may read */
+constexpr int MB_RING = MB_C + 2;                   /* u16 per lane: 257 words (bank skew) */
+constexpr int MB_STAGE = MB_NCH * MB_RING / 2;      /* staged entries per emit round (aliases the rings) */
+constexpr int MB_POS = MB_S + MB_DLA;               /* positions with block lengths */
+
+struct MbShared {
+    uint32_t pay[(MB_S + MB_LA + 16) / 4];
+    uint32_t delL[MB_POS / 4];                      /* one byte per position */
+    uint32_t delC[MB_POS / 4];
+    uint16_t dmb[MB_S + 2 * MB_NCH];                /* macroblock length per position; chunk rows skewed by one word */
+    uint32_t ring[MB_STAGE];                        /* u16 rings during DP/chain, staged u32 entries during emit */
+    uint32_t base[MB_NCH + 1];
+    uint16_t entq[MB_NCH];
+    int entry, nb, skips, consumed;
+};
+
+__device__ __forceinline__ uint32_t swar_runs(uint32_t t) { return t & ~(t >> 1) & 0x40404040u; }
+__device__ __forceinline__ uint32_t swar_x(uint32_t t) { return t & ((swar_runs(t) >> 6) * 0x3Fu); }
+
+__device__ __forceinline__ uint32_t lds_u32_unaligned(const uint32_t *w, int byte)
+{
+    const uint32_t *p = w + (byte >> 2);
+    return __funnelshift_r(p[0], p[1], (unsigned)(byte & 3) * 8);
+}
+
+/* tokens still to read when the first eight (from shared byte tb) fill `filled` of `need` positions */
+__device__ __noinline__ int mb_long_block(const uint32_t *payw, int tb, int need)
+{
+    int ntok = 8;
+    for (;;) {
+        const uint32_t t = lds_u32_unaligned(payw, tb + ntok);
+        const uint32_t P = swar_x(t) * 0x01010101u + 0x04030201u;
+        const uint32_t c = (P + (uint32_t)(128 - need) * 0x01010101u) & 0x80808080u;
+        if (c) return ntok + ((__ffs((int)c) - 1) >> 3) + 1;
+        need -= (int)(P >> 24);
+        ntok += 4;
+    }
+}
+
+/* Block lengths of the four positions starting at shared byte `byte0` (a multiple of 4) under the
+ * grammar with raw prefix b (0..63): DC byte, b raw bytes, tokens until 63 - b positions are filled. */
+__device__ __forceinline__ uint32_t mb_level0(const uint32_t *payw, int byte0, int b)
+{
+    const uint32_t W0 = payw[byte0 >> 2];                   /* the four candidate DC bytes */
+    uint32_t packed;
+    if (b >= 63) {
+        packed = 0x40404040u;                               /* 63 raw coefficients: no token tail, 64 bytes */
+    } else {
+        const int t0 = byte0 + 1 + b;                       /* token 0 of position 0 */
+        const uint32_t *wp = payw + (t0 >> 2);
+        const unsigned sh = (unsigned)(t0 & 3) * 8;
+        const uint32_t X0 = swar_x(wp[0]), X1 = swar_x(wp[1]), X2 = swar_x(wp[2]), X3 = swar_x(wp[3]);
+        const uint32_t Y0 = __funnelshift_r(X0, X1, sh), Y1 = __funnelshift_r(X1, X2, sh), Y2 = __funnelshift_r(X2, X3, sh);
+        const uint32_t kk = (uint32_t)(65 + b) * 0x01010101u;      /* bit 7 of (fill + 65 + b) <=> fill >= 63 - b */
+        packed = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const uint32_t x0 = i == 0 ? Y0 : __funnelshift_r(Y0, Y1, 8 * i);
+            const uint32_t x1 = i == 0 ? Y1 : __funnelshift_r(Y1, Y2, 8 * i);
+            const uint32_t P0 = x0 * 0x01010101u + 0x04030201u + kk;
+            const uint32_t P1 = x1 * 0x01010101u + 0x04030201u + (P0 >> 24) * 0x01010101u;
+            const uint32_t c0 = P0 & 0x80808080u, c1 = P1 & 0x80808080u;
+            int ntok;
+            if (c0 | c1) {
+                const int bit = c0 ? __ffs((int)c0) - 1 : 31 + __ffs((int)c1);
+                ntok = (bit >> 3) + 1;
+            } else {
+                ntok = mb_long_block(payw, t0 + i, 128 - (int)(P1 >> 24));   /* need = 63 - b - filled, P1>>24 = 65 + b + filled */
+            }
+            packed |= (uint32_t)(1 + b + ntok) << (8 * i);
+        }
+    }
+    /* skipped blocks (lib/RTjpeg.c:2704): a byte 0xFF is a block of its own, one byte long */
+    const uint32_t y = ~W0;
+    const uint32_t z = ~(((y & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | y | 0x7F7F7F7Fu);
+    const uint32_t m = (z >> 7) * 0xFFu;
+    return (packed & ~m) | (0x01010101u & m);
+}
+
+} // namespace
+
+extern "C" __global__ void __launch_bounds__(MB_THREADS, 3)
+rtj_scan_mb_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc *__restrict__ desc,
+                   const rtj_dev_table *__restrict__ tables, int F, int nblk,
+                   uint32_t *__restrict__ ent, uint32_t *__restrict__ frame_skips,
+                   rtj_dev_info *__restrict__ info)
+{
+    extern __shared__ __align__(16) uint8_t mb_smem[];
+    MbShared &sh = *reinterpret_cast<MbShared *>(mb_smem);
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int f = blockIdx.x;
+    if (f >= F) return;
+    const rtjgpu_frame_desc d = desc[f];
+    const int lb8 = tables[d.table].bt8[0], cb8 = tables[d.table].bt8[1];
+    if ((lb8 | cb8) == 0) return;                       /* no raw prefix: rtj_scan_chunk_kernel's frame */
+
+    const uint8_t *pay = stream + d.offset + RTJPEG_B200_HEADER_BYTES;
+    const int len = d.length > RTJPEG_B200_HEADER_BYTES ? (int)d.length - RTJPEG_B200_HEADER_BYTES : 0;
+    const int mis = (int)(reinterpret_cast<uintptr_t>(pay) & 15);
+    const uint8_t *gbase = pay - mis;
+    uint32_t *out = ent + (size_t)f * nblk;
+    const uint8_t *payb = reinterpret_cast<const uint8_t *>(sh.pay) + mis;
+    const uint8_t *dLb = reinterpret_cast<const uint8_t *>(sh.delL);
+    const uint8_t *dCb = lb8 == cb8 ? dLb : reinterpret_cast<const uint8_t *>(sh.delC);
+    const uint32_t missing = RTJ_ENT(min(len, (int)RTJ_ENT_OFF_MASK), 1);
+
+    if (tid == 0) { sh.entry = 0; sh.nb = 0; sh.skips = 0; sh.consumed = 0; }
+    __syncthreads();
+
+    for (int seg0 = 0; seg0 < len; seg0 += MB_S) {
+        const int nb0 = sh.nb;
+        if (nb0 >= nblk) break;
+        const int lim = len - seg0;
+        const int nch = min(MB_NCH, (lim + MB_C - 1) / MB_C);
+        const int npos = nch * MB_C;
+
+        /* ---- load; beyond the payload every byte reads 0x7F, a run token that ends any block ---- */
+        {
+            const uint4 *g4 = reinterpret_cast<const uint4 *>(gbase + seg0);
+            uint4 *s4 = reinterpret_cast<uint4 *>(sh.pay);
+            const int nvec = (npos + MB_LA + 16) / 16;
+            const int vlim = lim + mis;
+            for (int v = tid; v < nvec; v += MB_THREADS) {
+                const int b0 = v * 16;
+                uint4 x = make_uint4(0x7F7F7F7Fu, 0x7F7F7F7Fu, 0x7F7F7F7Fu, 0x7F7F7F7Fu);
+                if (b0 < vlim) {
+                    x = __ldg(g4 + v);
+                    if (b0 + 16 > vlim) {
+                        uint32_t w[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            const int nv = vlim - (b0 + 4 * k);
+                            const uint32_t m = nv >= 4 ? 0xFFFFFFFFu : nv <= 0 ? 0u : (1u << (8 * nv)) - 1u;
+                            w[k] = (w[k] & m) | (0x7F7F7F7Fu & ~m);
+                        }
+                        x = make_uint4(w[0], w[1], w[2], w[3]);
+                    }
+                }
+                s4[v] = x;
+            }
+        }
+        __syncthreads();
+
+        /* ---- level 0: both block-length tables, for the segment and the look-ahead behind it ---- */
+        for (int q0 = tid * 4; q0 < npos + MB_DLA; q0 += MB_THREADS * 4) {
+            sh.delL[q0 >> 2] = mb_level0(sh.pay, q0 + mis, lb8);
+            if (lb8 != cb8) sh.delC[q0 >> 2] = mb_level0(sh.pay, q0 + mis, cb8);
+        }
+        __syncthreads();
+
+        /* ---- compose: length of the macroblock that would start at every position ---- */
+        for (int q = tid; q < npos; q += MB_THREADS) {
+            int n = q;
+            n += dLb[n]; n += dLb[n]; n += dLb[n]; n += dLb[n];
+            n += dCb[n]; n += dCb[n];
+            sh.dmb[q + ((q / MB_C) << 1)] = (uint16_t)(n - q);
+        }
+        __syncthreads();
+
+        /* ---- DP over macroblock starts, one lane per chunk, right to left.  Ring entry: exit offset
+         *      (9 bits) | macroblocks started << 9 ---- */
+        if (tid < nch) {
+            uint16_t *ring = reinterpret_cast<uint16_t *>(sh.ring) + tid * MB_RING;
+            const int cq = tid * MB_C;
+            for (int k = 0; k < MB_C; k += 2) reinterpret_cast<uint32_t *>(ring)[k >> 1] = (uint32_t)k | ((uint32_t)(k + 1) << 16);
+            for (int qq = MB_C - 1; qq >= 0; --qq) {
+                const int n = qq + (int)sh.dmb[cq + 2 * tid + qq];
+                uint32_t v = ring[n & (MB_C - 1)] + (1u << 9);
+                if (cq + qq >= lim) v = 0;                                  /* nothing starts behind the payload */
+                ring[qq] = (uint16_t)v;
+            }
+        }
+        __syncthreads();
+
+        /* ---- chain ---- */
+        if (tid == 0) {
+            const uint16_t *rings = reinterpret_cast<const uint16_t *>(sh.ring);
+            int e = sh.entry, nb = nb0;
+            for (int j = 0; j < nch; j++) {
+                sh.entq[j] = (uint16_t)(j * MB_C + e);
+                sh.base[j] = (uint32_t)nb;
+                const uint32_t v = rings[j * MB_RING + e];
+                e = (int)(v & 511u);
+                nb += 6 * (int)(v >> 9);
+            }
+            sh.base[nch] = (uint32_t)nb;
+            sh.entry = e;
+            sh.nb = nb;
+        }
+        __syncthreads();
+
+        /* ---- emit: six entries per macroblock ---- */
+        const int nb1 = min(sh.nb, nblk);
+        int q = 0, i = 0, qend = 0, myskips = 0, lastend = -1, k6 = 0;
+        if (tid < nch) {
+            q = sh.entq[tid];
+            i = (int)sh.base[tid];
+            qend = (tid + 1) * MB_C;
+        }
+        __syncthreads();
+        for (int r0 = nb0; r0 < nb1; r0 += MB_STAGE) {
+            const int r1 = min(r0 + MB_STAGE, nb1);
+            if (tid < nch) {
+                /* a macroblock belongs to the chunk it starts in; its later blocks may lie behind the chunk */
+                while ((k6 != 0 || q < min(qend, lim)) && i < r1) {
+                    const int bt8 = k6 < 4 ? lb8 : cb8;
+                    uint32_t e;
+                    if (q >= lim) {
+                        e = missing;                                        /* the payload ended inside this macroblock */
+                    } else {
+                        const int dl = (k6 < 4 ? dLb : dCb)[q];
+                        const uint32_t head = lds_u32_unaligned(sh.pay, q + mis);
+                        const uint32_t last = payb[q + dl - 1];
+                        const bool isff = (head & 0xFFu) == 0xFFu;
+                        const int eob = bt8 >= 63 ? 64 : ((last - 64u) < 64u ? max(127 - (int)last, dl - 1) : 64);
+                        const uint32_t t1 = (head >> 8) & 0xFFu, t2 = (head >> 16) & 0xFFu;
+                        const uint32_t c1 = (eob >= 2 && (t1 - 64u) >= 64u) ? t1 : 0u;
+                        const uint32_t c2 = (eob >= 3 && (t2 - 64u) >= 64u) ? t2 : 0u;
+                        const uint32_t e_inl = RTJ_ENT_INLINE_BIT | (head & 0xFFu) | (c1 << 8) | (c2 << 16);
+                        const uint32_t e_gen = RTJ_ENT(seg0 + q, eob);
+                        e = isff ? RTJ_ENT_SKIP : ((bt8 == 0 && eob <= 3) ? e_inl : e_gen);
+                        myskips += isff ? 1 : 0;
+                        q += dl;
+                        lastend = seg0 + q;
+                    }
+                    sh.ring[i - r0] = e;
+                    i++;
+                    k6 = k6 == 5 ? 0 : k6 + 1;
+                }
+            }
+            __syncthreads();
+            for (int k = tid; k < r1 - r0; k += MB_THREADS) out[r0 + k] = sh.ring[k];
+            __syncthreads();
+        }
+        if (tid < 32) {                                     /* MB_NCH <= 32: the chunk lanes are warp 0 */
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                myskips += __shfl_xor_sync(0xFFFFFFFFu, myskips, o);
+                lastend = max(lastend, __shfl_xor_sync(0xFFFFFFFFu, lastend, o));
+            }
+            if (lane == 0) {
+                sh.skips += myskips;
+                sh.consumed = max(sh.consumed, lastend);
+            }
+        }
+        __syncthreads();
+    }
+
+    /* a frame whose stream ends early or mid-block: flag it, give the missing blocks a harmless entry */
+    const int nbf = min(sh.nb, nblk);
+    for (int b = nbf + tid; b < nblk; b += MB_THREADS) out[b] = missing;
+    if (tid == 0) {
+        const int consumed = sh.consumed, skips = sh.skips;
+        frame_skips[f] = (uint32_t)skips;
+        if (skips) atomicAdd(&info->skipped_blocks, (unsigned long long)skips);
+        atomicAdd(&info->payload_bytes, (unsigned long long)min(consumed, len));
+        if (nbf < nblk || consumed > len || len > (int)RTJGPU_MAX_PAYLOAD_BYTES) {
+            atomicAdd(&info->bad_frames, 1u);
+            atomicMin((unsigned int *)&info->first_bad_frame, (unsigned int)f);
+        }
+    }
+}
+
+extern "C" int rtj_scan_mb_init(void)
+{
+    cudaError_t e = cudaFuncSetAttribute(rtj_scan_mb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)sizeof(MbShared));
+    return e == cudaSuccess ? 0 : (int)e;
+}
+
+extern "C" int rtj_launch_scan_mb(const rtj_launch_args *a, void *stream)
+{
+    const int nblk = (a->w >> 4) * (a->h >> 4) * 6;
+    rtj_scan_mb_kernel<<<a->F, MB_THREADS, sizeof(MbShared), (cudaStream_t)stream>>>(
+        a->d_stream, a->d_desc, a->d_tables, a->F, nblk, a->d_ent, a->d_frame_skips, a->d_info);
+    return (int)cudaGetLastError();
+}

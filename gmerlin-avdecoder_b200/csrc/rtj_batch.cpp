@@ -27,6 +27,11 @@ struct Workspace {
     uint16_t     *d_chunk_last = nullptr;
     uint32_t     *d_frame_skips = nullptr;
     rtj_dev_info *d_info = nullptr;
+    /* segment-parallel scan */
+    uint32_t     *d_seg_sum = nullptr;   size_t seg_sum_cap = 0;     /* entries */
+    uint32_t     *d_seg_entry = nullptr; size_t seg_cap = 0;         /* entries of entry / base */
+    uint32_t     *d_seg_base = nullptr;
+    int32_t      *d_seg_nbf = nullptr;   int    seg_frames_cap = 0;
     size_t        cap_entries = 0;
     int           cap_frames = 0;
 };
@@ -111,6 +116,44 @@ int ws_reserve(rtjgpu_ctx *ctx, Workspace *ws, int F, int nblk)
     return RTJGPU_OK;
 }
 
+/* Workspace of the segment-parallel scan, when the batch qualifies: forced by the scan mode, or AUTO
+ * with a batch too small to fill the device with one CTA per frame.  Fills *sp (sum == NULL: not used). */
+constexpr int    SEG_AUTO_MAX_FRAMES = 256;
+constexpr size_t SEG_MAX_SUM_BYTES = (size_t)1 << 30;
+
+int seg_reserve(rtjgpu_ctx *ctx, Workspace *ws, int F, int nblk, int scan_mode, rtj_seg_plan *sp)
+{
+    memset(sp, 0, sizeof(*sp));
+    if (scan_mode != RTJGPU_SCAN_SEGMENT && !(scan_mode == RTJGPU_SCAN_AUTO && F <= SEG_AUTO_MAX_FRAMES)) return RTJGPU_OK;
+    /* a frame needs at most 64 bytes per block */
+    const size_t maxseg = ((size_t)nblk * 64 + RTJ_SEG_BYTES - 1) / RTJ_SEG_BYTES + 1;
+    const size_t nseg = (size_t)F * maxseg, nsum = nseg * RTJ_SEG_NE;
+    if (nsum * sizeof(uint32_t) > SEG_MAX_SUM_BYTES) return RTJGPU_OK;          /* too big: one CTA per frame instead */
+    if (nsum > ws->seg_sum_cap) {
+        if (ws->d_seg_sum) cudaFree(ws->d_seg_sum);
+        ws->d_seg_sum = nullptr; ws->seg_sum_cap = 0;
+        CK(ctx, cudaMalloc(&ws->d_seg_sum, nsum * sizeof(uint32_t)));
+        ws->seg_sum_cap = nsum;
+    }
+    if (nseg > ws->seg_cap) {
+        if (ws->d_seg_entry) cudaFree(ws->d_seg_entry);
+        if (ws->d_seg_base) cudaFree(ws->d_seg_base);
+        ws->d_seg_entry = ws->d_seg_base = nullptr; ws->seg_cap = 0;
+        CK(ctx, cudaMalloc(&ws->d_seg_entry, nseg * sizeof(uint32_t)));
+        CK(ctx, cudaMalloc(&ws->d_seg_base, nseg * sizeof(uint32_t)));
+        ws->seg_cap = nseg;
+    }
+    if (F > ws->seg_frames_cap) {
+        if (ws->d_seg_nbf) cudaFree(ws->d_seg_nbf);
+        ws->d_seg_nbf = nullptr; ws->seg_frames_cap = 0;
+        CK(ctx, cudaMalloc(&ws->d_seg_nbf, (size_t)F * sizeof(int32_t)));
+        ws->seg_frames_cap = F;
+    }
+    sp->sum = ws->d_seg_sum; sp->entry = ws->d_seg_entry; sp->base = ws->d_seg_base; sp->nbf = ws->d_seg_nbf;
+    sp->maxseg = (int)maxseg;
+    return RTJGPU_OK;
+}
+
 void ws_release(Workspace *ws)
 {
     if (ws->d_ent) cudaFree(ws->d_ent);
@@ -119,6 +162,10 @@ void ws_release(Workspace *ws)
     if (ws->d_chunk_last) cudaFree(ws->d_chunk_last);
     if (ws->d_frame_skips) cudaFree(ws->d_frame_skips);
     if (ws->d_info) cudaFree(ws->d_info);
+    if (ws->d_seg_sum) cudaFree(ws->d_seg_sum);
+    if (ws->d_seg_entry) cudaFree(ws->d_seg_entry);
+    if (ws->d_seg_base) cudaFree(ws->d_seg_base);
+    if (ws->d_seg_nbf) cudaFree(ws->d_seg_nbf);
     *ws = Workspace();
 }
 
@@ -133,6 +180,10 @@ int run_kernels(rtjgpu_ctx *ctx, Workspace *ws, const uint8_t *d_stream, const r
     a.d_hardq = ws->d_hardq; a.d_chunk_last = ws->d_chunk_last;
     a.d_out = d_out; a.d_carry = d_carry;
     a.scan_mode = ctx->scan_mode;
+    {
+        const int rc = seg_reserve(ctx, ws, F, (w >> 4) * (h >> 4) * 6, ctx->scan_mode, &a.seg);
+        if (rc) return rc;
+    }
 
     CK(ctx, cudaMemcpyAsync(ws->d_info, ctx->h_info_reset, sizeof(rtj_dev_info), cudaMemcpyHostToDevice, st));
     if (ev) CK(ctx, cudaEventRecord(ev[0], st));
@@ -273,7 +324,7 @@ void rtjgpu_enable_timing(rtjgpu_ctx *ctx, int on) { if (ctx) ctx->timing = on !
 
 int rtjgpu_set_scan_mode(rtjgpu_ctx *ctx, int mode)
 {
-    if (!ctx || mode < RTJGPU_SCAN_AUTO || mode > RTJGPU_SCAN_CHUNK) return RTJGPU_E_ARG;
+    if (!ctx || mode < RTJGPU_SCAN_AUTO || mode > RTJGPU_SCAN_SEGMENT) return RTJGPU_E_ARG;
     ctx->scan_mode = mode;
     return RTJGPU_OK;
 }

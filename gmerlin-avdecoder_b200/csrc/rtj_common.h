@@ -70,6 +70,22 @@ typedef struct rtj_dev_info {
     unsigned int       pad;
 } rtj_dev_info;
 
+/* ---- segment-parallel scan (few, large frames): a frame's 8 KB segments are parsed by separate
+ * CTAs.  Where a segment is entered depends on everything before it, so the work is split in three:
+ * every segment first reports, for EVERY possible entry offset, where a parse would leave it and how
+ * many units (blocks or macroblocks) it would start; one thread per frame chains these summaries;
+ * then every segment is parsed again from its now known entry and emits its entries. */
+#define RTJ_SEG_BYTES 8192
+#define RTJ_SEG_NE    384          /* entry offsets a segment is summarised for (64 used without raw prefix) */
+#define RTJ_SEG_UNUSED 0xFFFFFFFFu
+typedef struct rtj_seg_plan {
+    uint32_t *sum;      /* [F][maxseg][RTJ_SEG_NE]  exit offset | units << 9 */
+    uint32_t *entry;    /* [F][maxseg]  entry offset of the segment */
+    uint32_t *base;     /* [F][maxseg]  first block index; RTJ_SEG_UNUSED = the frame is complete before it */
+    int32_t  *nbf;      /* [F]  blocks the frame's stream holds, capped at nblk */
+    int       maxseg;
+} rtj_seg_plan;
+
 /* ---- kernel launchers (rtj_kernels.cu); stream is a cudaStream_t ----------- */
 typedef struct rtj_launch_args {
     const uint8_t           *d_stream;
@@ -85,12 +101,14 @@ typedef struct rtj_launch_args {
     uint8_t                 *d_out;
     const uint8_t           *d_carry;
     int                      scan_mode;     /* RTJGPU_SCAN_* */
+    rtj_seg_plan             seg;           /* workspace of the segment-parallel scan (sum == NULL: not available) */
 } rtj_launch_args;
 
 int rtj_launch_scan(const rtj_launch_args *a, void *stream);          /* returns the number of launches (>0) or -cudaError */
-int rtj_launch_scan_chunk(const rtj_launch_args *a, void *stream);    /* rtj_scan_chunk.cu */
+/* phase: 0 = one CTA per frame does everything, 1 = segment summaries, 2 = segment emit */
+int rtj_launch_scan_chunk(const rtj_launch_args *a, int phase, void *stream);    /* rtj_scan_chunk.cu */
 int rtj_scan_chunk_init(void);
-int rtj_launch_scan_mb(const rtj_launch_args *a, void *stream);       /* rtj_scan_mb.cu */
+int rtj_launch_scan_mb(const rtj_launch_args *a, int phase, void *stream);       /* rtj_scan_mb.cu */
 int rtj_scan_mb_init(void);
 int rtj_launch_resolve(const rtj_launch_args *a, void *stream);
 int rtj_launch_idct(const rtj_launch_args *a, void *stream);

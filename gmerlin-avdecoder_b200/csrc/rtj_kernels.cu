@@ -369,6 +369,43 @@ rtj_resolve_kernel(const uint32_t *__restrict__ ent, const uint16_t *__restrict_
     }
 }
 
+/* ------------------------------------------------------------------------ */
+/* K1, segment-parallel flavour: the frame-level chain between the two passes */
+/* ------------------------------------------------------------------------ */
+
+extern "C" __global__ void __launch_bounds__(64)
+rtj_scan_plan_kernel(const rtjgpu_frame_desc *__restrict__ desc, const rtj_dev_table *__restrict__ tables, int F, int nblk,
+                     uint32_t *__restrict__ ent, uint32_t *__restrict__ frame_skips, rtj_dev_info *__restrict__ info,
+                     const rtj_seg_plan sp)
+{
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= F) return;
+    const rtjgpu_frame_desc d = desc[f];
+    const int len = d.length > RTJPEG_B200_HEADER_BYTES ? (int)d.length - RTJPEG_B200_HEADER_BYTES : 0;
+    /* with a raw prefix the summaries count macroblocks (rtj_scan_mb.cu), without it blocks */
+    const int unit = (tables[d.table].bt8[0] | tables[d.table].bt8[1]) ? 6 : 1;
+    int e = 0, nb = 0, seg = 0;
+    for (; seg < sp.maxseg && (long long)seg * RTJ_SEG_BYTES < len && nb < nblk; seg++) {
+        const size_t idx = (size_t)f * sp.maxseg + seg;
+        sp.entry[idx] = (uint32_t)e;
+        sp.base[idx] = (uint32_t)nb;
+        const uint32_t v = sp.sum[idx * RTJ_SEG_NE + e];
+        e = (int)(v & 511u);
+        nb += unit * (int)(v >> 9);
+    }
+    for (int s2 = seg; s2 < sp.maxseg; s2++) sp.base[(size_t)f * sp.maxseg + s2] = RTJ_SEG_UNUSED;
+    const int nbf = min(nb, nblk);
+    sp.nbf[f] = nbf;
+    frame_skips[f] = 0;
+    /* a frame whose stream ends early: give the missing blocks a harmless entry; a frame without any
+     * block is closed here, every other frame by the segment that holds its last block */
+    for (int b = nbf; b < nblk; b++) ent[(size_t)f * nblk + b] = RTJ_ENT(min(len, (int)RTJ_ENT_OFF_MASK), 1);
+    if (nbf == 0 && nblk > 0) {
+        atomicAdd(&info->bad_frames, 1u);
+        atomicMin((unsigned int *)&info->first_bad_frame, (unsigned int)f);
+    }
+}
+
 extern "C" int rtj_kernels_init(void)
 {
     int e = rtj_idct_init();
@@ -383,10 +420,22 @@ extern "C" int rtj_launch_scan(const rtj_launch_args *a, void *stream)
     cudaStream_t st = (cudaStream_t)stream;
     /* AUTO: the chunk-parallel kernels -- rtj_scan_chunk_kernel takes every frame without a raw prefix,
      * rtj_scan_mb_kernel the others; each returns at once on the other's frames. */
-    if (a->scan_mode == RTJGPU_SCAN_AUTO || a->scan_mode == RTJGPU_SCAN_CHUNK) {
-        int e = rtj_launch_scan_chunk(a, stream);
+    if (a->scan_mode == RTJGPU_SCAN_AUTO || a->scan_mode == RTJGPU_SCAN_CHUNK || a->scan_mode == RTJGPU_SCAN_SEGMENT) {
+        if (a->seg.sum) {
+            /* few frames: their segments are parsed by separate CTAs -- summaries, frame-level chain, emit */
+            int e = rtj_launch_scan_chunk(a, 1, stream);
+            if (!e) e = rtj_launch_scan_mb(a, 1, stream);
+            if (e) return -e;
+            rtj_scan_plan_kernel<<<(a->F + 63) / 64, 64, 0, st>>>(a->d_desc, a->d_tables, a->F, nblk, a->d_ent,
+                                                                  a->d_frame_skips, a->d_info, a->seg);
+            if ((e = (int)cudaGetLastError())) return -e;
+            e = rtj_launch_scan_chunk(a, 2, stream);
+            if (!e) e = rtj_launch_scan_mb(a, 2, stream);
+            return e ? -e : 5;
+        }
+        int e = rtj_launch_scan_chunk(a, 0, stream);
         if (e) return -e;
-        e = rtj_launch_scan_mb(a, stream);
+        e = rtj_launch_scan_mb(a, 0, stream);
         return e ? -e : 2;
     }
     /* rtjgpu_set_scan_mode() forces one serial flavour for every frame: one lane per frame (cheap in

@@ -91,16 +91,19 @@ __device__ __noinline__ int cs_long_block(const uint32_t *payw, int tb, int fill
 
 } // namespace
 
-extern "C" __global__ void __launch_bounds__(CS_THREADS, 8)
+/* PHASE 0: the whole frame, segment after segment.  PHASE 1 / 2: one segment (blockIdx.x) of frame
+ * blockIdx.y -- its summary for the frame-level chain, resp. its entries (rtj_common.h, rtj_seg_plan). */
+template <int PHASE>
+__global__ void __launch_bounds__(CS_THREADS, 8)
 rtj_scan_chunk_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc *__restrict__ desc,
                       const rtj_dev_table *__restrict__ tables, int F, int nblk,
                       uint32_t *__restrict__ ent, uint32_t *__restrict__ frame_skips,
-                      rtj_dev_info *__restrict__ info)
+                      rtj_dev_info *__restrict__ info, const rtj_seg_plan sp)
 {
     extern __shared__ __align__(16) uint8_t cs_smem[];
     CsShared &sh = *reinterpret_cast<CsShared *>(cs_smem);
     const int tid = threadIdx.x, lane = tid & 31;
-    const int f = blockIdx.x;
+    const int f = PHASE == 0 ? blockIdx.x : blockIdx.y;
     if (f >= F) return;
     const rtjgpu_frame_desc d = desc[f];
     if (tables[d.table].bt8[0] | tables[d.table].bt8[1]) return;     /* raw prefix: the serial kernels' frame */
@@ -113,10 +116,17 @@ rtj_scan_chunk_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_des
     const uint8_t *payb = reinterpret_cast<const uint8_t *>(sh.pay) + mis;   /* payb[q] = payload byte seg0 + q */
     const uint8_t *delb = reinterpret_cast<const uint8_t *>(sh.del);
 
-    if (tid == 0) { sh.entry = 0; sh.nb = 0; sh.skips = 0; sh.consumed = 0; }
+    const size_t my_seg = (size_t)f * sp.maxseg + blockIdx.x;       /* PHASE 1 / 2 */
+    if (PHASE == 2 && sp.base[my_seg] == RTJ_SEG_UNUSED) return;    /* the frame is complete before this segment */
+    if (tid == 0) {
+        sh.entry = PHASE == 2 ? (int)sp.entry[my_seg] : 0;
+        sh.nb = PHASE == 2 ? (int)sp.base[my_seg] : 0;
+        sh.skips = 0;
+        sh.consumed = 0;
+    }
     __syncthreads();
 
-    for (int seg0 = 0; seg0 < len; seg0 += CS_S) {
+    for (int seg0 = PHASE == 0 ? 0 : (int)blockIdx.x * CS_S; seg0 < len; seg0 += CS_S) {
         const int nb0 = sh.nb;
         if (nb0 >= nblk) break;                                        /* uniform: everybody reads the same word */
         const int lim = len - seg0;                                    /* payload bytes from here on */
@@ -224,6 +234,21 @@ rtj_scan_chunk_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_des
         }
         __syncthreads();
 
+        if (PHASE == 1) {
+            /* ---- summary: for every entry offset, where the parse leaves the segment and what it starts ---- */
+            const uint16_t *rings = reinterpret_cast<const uint16_t *>(sh.ring);
+            for (int e0 = tid; e0 < 64; e0 += CS_THREADS) {
+                int e = e0, units = 0;
+                for (int j = 0; j < nch; j++) {
+                    const uint32_t v = rings[j * CS_RING + e];
+                    e = (int)(v & 63u);
+                    units += (int)(v >> 6);
+                }
+                sp.sum[my_seg * RTJ_SEG_NE + e0] = (uint32_t)e | ((uint32_t)units << 9);
+            }
+            return;
+        }
+
         /* ---- chain: entry point and first block index of every chunk ---- */
         if (tid == 0) {
             const uint16_t *rings = reinterpret_cast<const uint16_t *>(sh.ring);
@@ -288,6 +313,28 @@ rtj_scan_chunk_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_des
             }
         }
         __syncthreads();
+        if (PHASE != 0) break;
+    }
+
+    if (PHASE == 1) return;                             /* nothing of the payload lies in this segment */
+    if (PHASE == 2) {
+        /* this segment's share of the frame's counters; the segment holding the frame's last block closes the frame */
+        if (tid == 0) {
+            const int skips = sh.skips, nbf = sp.nbf[f], nb0 = (int)sp.base[my_seg];
+            if (skips) {
+                atomicAdd(&frame_skips[f], (uint32_t)skips);
+                atomicAdd(&info->skipped_blocks, (unsigned long long)skips);
+            }
+            if (nb0 < nbf && nbf <= sh.nb) {
+                const int consumed = sh.consumed;
+                atomicAdd(&info->payload_bytes, (unsigned long long)min(consumed, len));
+                if (nbf < nblk || consumed > len || len > (int)RTJGPU_MAX_PAYLOAD_BYTES) {
+                    atomicAdd(&info->bad_frames, 1u);
+                    atomicMin((unsigned int *)&info->first_bad_frame, (unsigned int)f);
+                }
+            }
+        }
+        return;
     }
 
     /* a frame whose stream ends early or mid-block: flag it, give the missing blocks a harmless entry */
@@ -307,15 +354,26 @@ rtj_scan_chunk_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_des
 
 extern "C" int rtj_scan_chunk_init(void)
 {
-    cudaError_t e = cudaFuncSetAttribute(rtj_scan_chunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)sizeof(CsShared));
+    cudaError_t e = cudaFuncSetAttribute(rtj_scan_chunk_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CsShared));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(rtj_scan_chunk_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CsShared));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(rtj_scan_chunk_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CsShared));
     return e == cudaSuccess ? 0 : (int)e;
 }
 
-extern "C" int rtj_launch_scan_chunk(const rtj_launch_args *a, void *stream)
+extern "C" int rtj_launch_scan_chunk(const rtj_launch_args *a, int phase, void *stream)
 {
+    static_assert(CS_S == RTJ_SEG_BYTES, "segment size is shared with the frame-level chain");
     const int nblk = (a->w >> 4) * (a->h >> 4) * 6;
-    rtj_scan_chunk_kernel<<<a->F, CS_THREADS, sizeof(CsShared), (cudaStream_t)stream>>>(
-        a->d_stream, a->d_desc, a->d_tables, a->F, nblk, a->d_ent, a->d_frame_skips, a->d_info);
+    cudaStream_t st = (cudaStream_t)stream;
+    const dim3 grid = phase == 0 ? dim3((unsigned)a->F) : dim3((unsigned)a->seg.maxseg, (unsigned)a->F);
+    if (phase == 0)
+        rtj_scan_chunk_kernel<0><<<grid, CS_THREADS, sizeof(CsShared), st>>>(
+            a->d_stream, a->d_desc, a->d_tables, a->F, nblk, a->d_ent, a->d_frame_skips, a->d_info, a->seg);
+    else if (phase == 1)
+        rtj_scan_chunk_kernel<1><<<grid, CS_THREADS, sizeof(CsShared), st>>>(
+            a->d_stream, a->d_desc, a->d_tables, a->F, nblk, a->d_ent, a->d_frame_skips, a->d_info, a->seg);
+    else
+        rtj_scan_chunk_kernel<2><<<grid, CS_THREADS, sizeof(CsShared), st>>>(
+            a->d_stream, a->d_desc, a->d_tables, a->F, nblk, a->d_ent, a->d_frame_skips, a->d_info, a->seg);
     return (int)cudaGetLastError();
 }

@@ -36,6 +36,8 @@ constexpr int MB_LA = MB_DLA + 64 + 64 + 32;        /* payload bytes behind the 
 constexpr int MB_RING = MB_C + 2;                   /* u16 per lane: 257 words (bank skew) */
 constexpr int MB_STAGE = MB_NCH * MB_RING / 2;      /* staged entries per emit round (aliases the rings) */
 constexpr int MB_POS = MB_S + MB_DLA;               /* positions with block lengths */
+constexpr int MB_RUN = 68;                          /* positions per thread in level 0 */
+static_assert(MB_RUN * MB_THREADS >= MB_POS && (MB_RUN % 4) == 0 && ((MB_RUN / 4) & 1), "level-0 runs cover the positions; odd word stride");
 
 struct MbShared {
     uint32_t pay[(MB_S + MB_LA + 16) / 4];
@@ -57,72 +59,60 @@ __device__ __forceinline__ uint32_t lds_u32_unaligned(const uint32_t *w, int byt
     return __funnelshift_r(p[0], p[1], (unsigned)(byte & 3) * 8);
 }
 
-/* tokens still to read when the first eight (from shared byte tb) fill `filled` of `need` positions */
-__device__ __noinline__ int mb_long_block(const uint32_t *payw, int tb, int need)
-{
-    int ntok = 8;
-    for (;;) {
-        const uint32_t t = lds_u32_unaligned(payw, tb + ntok);
-        const uint32_t P = swar_x(t) * 0x01010101u + 0x04030201u;
-        const uint32_t c = (P + (uint32_t)(128 - need) * 0x01010101u) & 0x80808080u;
-        if (c) return ntok + ((__ffs((int)c) - 1) >> 3) + 1;
-        need -= (int)(P >> 24);
-        ntok += 4;
-    }
-}
+/* positions one token fills: a run token (signed value > 63, lib/RTjpeg.c:173) b - 63, anything else 1 */
+__device__ __forceinline__ int token_fill(unsigned v) { return (v - 64u) < 64u ? (int)v - 63 : 1; }
 
-/* Block lengths of the four positions starting at shared byte `byte0` (a multiple of 4) under the
- * grammar with raw prefix b (0..63): DC byte, b raw bytes, tokens until 63 - b positions are filled. */
-__device__ __forceinline__ uint32_t mb_level0(const uint32_t *payw, int byte0, int b)
+/*
+ * Level 0 for one grammar (raw prefix b), positions [q_begin, q_end) -- one thread, left to right.
+ * The block that would start at q reads its tokens from ws = q + 1 + b on and ends behind the first
+ * token that brings the filled positions to 63 - b.  Moving q one byte to the right drops one token
+ * from the front of that window and (the fills being positive) can only push its end further right:
+ * two pointers, a constant number of steps per position however long the blocks are.
+ */
+__device__ __forceinline__ void mb_level0_run(const uint8_t *__restrict__ payb, uint8_t *__restrict__ del,
+                                              int q_begin, int q_end, int b)
 {
-    const uint32_t W0 = payw[byte0 >> 2];                   /* the four candidate DC bytes */
-    uint32_t packed;
-    if (b >= 63) {
-        packed = 0x40404040u;                               /* 63 raw coefficients: no token tail, 64 bytes */
-    } else {
-        const int t0 = byte0 + 1 + b;                       /* token 0 of position 0 */
-        const uint32_t *wp = payw + (t0 >> 2);
-        const unsigned sh = (unsigned)(t0 & 3) * 8;
-        const uint32_t X0 = swar_x(wp[0]), X1 = swar_x(wp[1]), X2 = swar_x(wp[2]), X3 = swar_x(wp[3]);
-        const uint32_t Y0 = __funnelshift_r(X0, X1, sh), Y1 = __funnelshift_r(X1, X2, sh), Y2 = __funnelshift_r(X2, X3, sh);
-        const uint32_t kk = (uint32_t)(65 + b) * 0x01010101u;      /* bit 7 of (fill + 65 + b) <=> fill >= 63 - b */
-        packed = 0;
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const uint32_t x0 = i == 0 ? Y0 : __funnelshift_r(Y0, Y1, 8 * i);
-            const uint32_t x1 = i == 0 ? Y1 : __funnelshift_r(Y1, Y2, 8 * i);
-            const uint32_t P0 = x0 * 0x01010101u + 0x04030201u + kk;
-            const uint32_t P1 = x1 * 0x01010101u + 0x04030201u + (P0 >> 24) * 0x01010101u;
-            const uint32_t c0 = P0 & 0x80808080u, c1 = P1 & 0x80808080u;
-            int ntok;
-            if (c0 | c1) {
-                const int bit = c0 ? __ffs((int)c0) - 1 : 31 + __ffs((int)c1);
-                ntok = (bit >> 3) + 1;
-            } else {
-                ntok = mb_long_block(payw, t0 + i, 128 - (int)(P1 >> 24));   /* need = 63 - b - filled, P1>>24 = 65 + b + filled */
-            }
-            packed |= (uint32_t)(1 + b + ntok) << (8 * i);
+    if (q_begin >= q_end) return;
+    if (b >= 63) {                                          /* 63 raw coefficients: no token tail, 64 bytes */
+        for (int q = q_begin; q < q_end; q++) del[q] = payb[q] == 0xFFu ? 1 : 64;
+        return;
+    }
+    /* One step per iteration -- either the window grows by a token or a position is finished and the
+     * window loses its first token -- so that the lanes of a warp, whose runs need the two kinds of
+     * step in different order, never wait for each other. */
+    const int need = 63 - b;
+    int q = q_begin, ws = q_begin + 1 + b, n = ws, sum = 0;
+    while (q < q_end) {
+        const bool grow = sum < need;
+        const int f = token_fill(payb[grow ? n : ws]);
+        if (grow) {
+            sum += f;
+            n++;
+        } else {
+            /* skipped block (lib/RTjpeg.c:2704): a byte 0xFF is a block of its own, one byte long */
+            del[q] = (uint8_t)(payb[q] == 0xFFu ? 1 : n - q);
+            sum -= f;
+            ws++;
+            q++;
         }
     }
-    /* skipped blocks (lib/RTjpeg.c:2704): a byte 0xFF is a block of its own, one byte long */
-    const uint32_t y = ~W0;
-    const uint32_t z = ~(((y & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | y | 0x7F7F7F7Fu);
-    const uint32_t m = (z >> 7) * 0xFFu;
-    return (packed & ~m) | (0x01010101u & m);
 }
 
 } // namespace
 
-extern "C" __global__ void __launch_bounds__(MB_THREADS, 3)
+/* PHASE 0: the whole frame, segment after segment.  PHASE 1 / 2: one segment (blockIdx.x) of frame
+ * blockIdx.y -- its summary for the frame-level chain, resp. its entries (rtj_common.h, rtj_seg_plan). */
+template <int PHASE>
+__global__ void __launch_bounds__(MB_THREADS, 3)
 rtj_scan_mb_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc *__restrict__ desc,
                    const rtj_dev_table *__restrict__ tables, int F, int nblk,
                    uint32_t *__restrict__ ent, uint32_t *__restrict__ frame_skips,
-                   rtj_dev_info *__restrict__ info)
+                   rtj_dev_info *__restrict__ info, const rtj_seg_plan sp)
 {
     extern __shared__ __align__(16) uint8_t mb_smem[];
     MbShared &sh = *reinterpret_cast<MbShared *>(mb_smem);
     const int tid = threadIdx.x, lane = tid & 31;
-    const int f = blockIdx.x;
+    const int f = PHASE == 0 ? blockIdx.x : blockIdx.y;
     if (f >= F) return;
     const rtjgpu_frame_desc d = desc[f];
     const int lb8 = tables[d.table].bt8[0], cb8 = tables[d.table].bt8[1];
@@ -138,10 +128,17 @@ rtj_scan_mb_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc *
     const uint8_t *dCb = lb8 == cb8 ? dLb : reinterpret_cast<const uint8_t *>(sh.delC);
     const uint32_t missing = RTJ_ENT(min(len, (int)RTJ_ENT_OFF_MASK), 1);
 
-    if (tid == 0) { sh.entry = 0; sh.nb = 0; sh.skips = 0; sh.consumed = 0; }
+    const size_t my_seg = (size_t)f * sp.maxseg + blockIdx.x;       /* PHASE 1 / 2 */
+    if (PHASE == 2 && sp.base[my_seg] == RTJ_SEG_UNUSED) return;    /* the frame is complete before this segment */
+    if (tid == 0) {
+        sh.entry = PHASE == 2 ? (int)sp.entry[my_seg] : 0;
+        sh.nb = PHASE == 2 ? (int)sp.base[my_seg] : 0;
+        sh.skips = 0;
+        sh.consumed = 0;
+    }
     __syncthreads();
 
-    for (int seg0 = 0; seg0 < len; seg0 += MB_S) {
+    for (int seg0 = PHASE == 0 ? 0 : (int)blockIdx.x * MB_S; seg0 < len; seg0 += MB_S) {
         const int nb0 = sh.nb;
         if (nb0 >= nblk) break;
         const int lim = len - seg0;
@@ -175,10 +172,14 @@ rtj_scan_mb_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc *
         }
         __syncthreads();
 
-        /* ---- level 0: both block-length tables, for the segment and the look-ahead behind it ---- */
-        for (int q0 = tid * 4; q0 < npos + MB_DLA; q0 += MB_THREADS * 4) {
-            sh.delL[q0 >> 2] = mb_level0(sh.pay, q0 + mis, lb8);
-            if (lb8 != cb8) sh.delC[q0 >> 2] = mb_level0(sh.pay, q0 + mis, cb8);
+        /* ---- level 0: both block-length tables, for the segment and the look-ahead behind it; every
+         *      thread owns a run of MB_RUN consecutive positions (17 words: bank-skewed) ---- */
+        {
+            uint8_t *dL = reinterpret_cast<uint8_t *>(sh.delL), *dC = reinterpret_cast<uint8_t *>(sh.delC);
+            const int npos2 = npos + MB_DLA;
+            const int q_begin = tid * MB_RUN, q_end = min(q_begin + MB_RUN, npos2);
+            mb_level0_run(payb, dL, q_begin, q_end, lb8);
+            if (lb8 != cb8) mb_level0_run(payb, dC, q_begin, q_end, cb8);
         }
         __syncthreads();
 
@@ -205,6 +206,21 @@ rtj_scan_mb_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc *
             }
         }
         __syncthreads();
+
+        if (PHASE == 1) {
+            /* ---- summary: for every entry offset, where the parse leaves the segment and what it starts ---- */
+            const uint16_t *rings = reinterpret_cast<const uint16_t *>(sh.ring);
+            for (int e0 = tid; e0 < 384; e0 += MB_THREADS) {
+                int e = e0, units = 0;
+                for (int j = 0; j < nch; j++) {
+                    const uint32_t v = rings[j * MB_RING + e];
+                    e = (int)(v & 511u);
+                    units += (int)(v >> 9);
+                }
+                sp.sum[my_seg * RTJ_SEG_NE + e0] = (uint32_t)e | ((uint32_t)units << 9);
+            }
+            return;
+        }
 
         /* ---- chain ---- */
         if (tid == 0) {
@@ -278,6 +294,28 @@ rtj_scan_mb_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc *
             }
         }
         __syncthreads();
+        if (PHASE != 0) break;
+    }
+
+    if (PHASE == 1) return;                             /* nothing of the payload lies in this segment */
+    if (PHASE == 2) {
+        /* this segment's share of the frame's counters; the segment holding the frame's last block closes the frame */
+        if (tid == 0) {
+            const int skips = sh.skips, nbf = sp.nbf[f], nb0 = (int)sp.base[my_seg];
+            if (skips) {
+                atomicAdd(&frame_skips[f], (uint32_t)skips);
+                atomicAdd(&info->skipped_blocks, (unsigned long long)skips);
+            }
+            if (nb0 < nbf && nbf <= sh.nb) {
+                const int consumed = sh.consumed;
+                atomicAdd(&info->payload_bytes, (unsigned long long)min(consumed, len));
+                if (nbf < nblk || consumed > len || len > (int)RTJGPU_MAX_PAYLOAD_BYTES) {
+                    atomicAdd(&info->bad_frames, 1u);
+                    atomicMin((unsigned int *)&info->first_bad_frame, (unsigned int)f);
+                }
+            }
+        }
+        return;
     }
 
     /* a frame whose stream ends early or mid-block: flag it, give the missing blocks a harmless entry */
@@ -297,15 +335,26 @@ rtj_scan_mb_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc *
 
 extern "C" int rtj_scan_mb_init(void)
 {
-    cudaError_t e = cudaFuncSetAttribute(rtj_scan_mb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)sizeof(MbShared));
+    cudaError_t e = cudaFuncSetAttribute(rtj_scan_mb_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MbShared));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(rtj_scan_mb_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MbShared));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(rtj_scan_mb_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MbShared));
     return e == cudaSuccess ? 0 : (int)e;
 }
 
-extern "C" int rtj_launch_scan_mb(const rtj_launch_args *a, void *stream)
+extern "C" int rtj_launch_scan_mb(const rtj_launch_args *a, int phase, void *stream)
 {
+    static_assert(MB_S == RTJ_SEG_BYTES && MB_DLA <= RTJ_SEG_NE, "segment size and entry range are shared with the frame-level chain");
     const int nblk = (a->w >> 4) * (a->h >> 4) * 6;
-    rtj_scan_mb_kernel<<<a->F, MB_THREADS, sizeof(MbShared), (cudaStream_t)stream>>>(
-        a->d_stream, a->d_desc, a->d_tables, a->F, nblk, a->d_ent, a->d_frame_skips, a->d_info);
+    cudaStream_t st = (cudaStream_t)stream;
+    const dim3 grid = phase == 0 ? dim3((unsigned)a->F) : dim3((unsigned)a->seg.maxseg, (unsigned)a->F);
+    if (phase == 0)
+        rtj_scan_mb_kernel<0><<<grid, MB_THREADS, sizeof(MbShared), st>>>(
+            a->d_stream, a->d_desc, a->d_tables, a->F, nblk, a->d_ent, a->d_frame_skips, a->d_info, a->seg);
+    else if (phase == 1)
+        rtj_scan_mb_kernel<1><<<grid, MB_THREADS, sizeof(MbShared), st>>>(
+            a->d_stream, a->d_desc, a->d_tables, a->F, nblk, a->d_ent, a->d_frame_skips, a->d_info, a->seg);
+    else
+        rtj_scan_mb_kernel<2><<<grid, MB_THREADS, sizeof(MbShared), st>>>(
+            a->d_stream, a->d_desc, a->d_tables, a->F, nblk, a->d_ent, a->d_frame_skips, a->d_info, a->seg);
     return (int)cudaGetLastError();
 }

@@ -159,15 +159,17 @@ const char *rtjgpu_strerror(int code);
 /* cudaError_t of the last failing CUDA call on this context, as int. */
 int  rtjgpu_last_cuda_error(const rtjgpu_ctx *ctx);
 
-/* Which flavour of the block-offset scan (K1) runs.  AUTO (the default): the chunk-parallel
- * kernel (a CTA per frame, every byte position examined in parallel) for frames whose tables
- * have no raw 8-bit prefix, a serial kernel for the others.  LANE / WARP force a serial
- * flavour for every frame: one thread per frame (large batches) or one warp per frame (few,
- * large frames).  CHUNK is AUTO spelled out. */
-#define RTJGPU_SCAN_AUTO  0
-#define RTJGPU_SCAN_LANE  1
-#define RTJGPU_SCAN_WARP  2
-#define RTJGPU_SCAN_CHUNK 3
+/* Which flavour of the block-offset scan (K1) runs.  AUTO (the default) picks between the two
+ * chunk-parallel arrangements by batch size: CHUNK = one CTA per frame walks the frame's 8 KB
+ * segments in turn (every byte position examined in parallel inside a segment) -- many frames;
+ * SEGMENT = the segments of a frame go to separate CTAs, with a frame-level chain between a summary
+ * pass and an emit pass -- few, large frames (and the one-frame RTjpeg_decompress).  LANE / WARP
+ * force a serial walk instead: one thread per frame or one warp per frame. */
+#define RTJGPU_SCAN_AUTO    0
+#define RTJGPU_SCAN_LANE    1
+#define RTJGPU_SCAN_WARP    2
+#define RTJGPU_SCAN_CHUNK   3
+#define RTJGPU_SCAN_SEGMENT 4
 int  rtjgpu_set_scan_mode(rtjgpu_ctx *ctx, int mode);
 
 /* Raw (pre-AAN) tables for RTJGPU_TABLE_CUSTOM, the set_tables path. */

@@ -15,12 +15,14 @@ from streams import clip, golden, interleave, reference_frames
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module", params=["auto", "lane", "warp"])
+@pytest.fixture(scope="module", params=["auto", "chunk", "lane", "warp"])
 def ctx(request):
-    """Every parity case runs under all flavours of the block-offset scan (K1): the default
-    (chunk-parallel kernel + serial kernel for raw-prefix frames) and each serial kernel alone."""
+    """Every parity case runs under all flavours of the block-offset scan (K1): the default (which
+    picks the segment-parallel arrangement for the small batches of this suite and one CTA per frame
+    for the full-size one), one CTA per frame forced, and each serial kernel alone."""
     c = g.BatchContext(0)
-    c.set_scan_mode({"auto": capi.SCAN_AUTO, "lane": capi.SCAN_LANE, "warp": capi.SCAN_WARP}[request.param])
+    c.set_scan_mode({"auto": capi.SCAN_AUTO, "chunk": capi.SCAN_CHUNK, "lane": capi.SCAN_LANE,
+                     "warp": capi.SCAN_WARP}[request.param])
     c.flavour = request.param
     yield c
     c.close()
@@ -154,7 +156,7 @@ def test_scan_entries_match_oracle_walker(ctx):
         chroma = (np.arange(nblk) % 6) >= 4
         assert not (inline & ~chroma).any()
         assert (eob[inline] <= 3).all()
-        if ctx.flavour != "auto":
+        if ctx.flavour in ("lane", "warp"):
             assert not inline.any()                      # the serial kernels never emit inline entries
         gen = coded & ~inline
         assert ((ent[f] & 0x1FFFFFF)[gen] == offs[gen]).all()
@@ -167,7 +169,7 @@ def test_scan_entries_match_oracle_walker(ctx):
 def test_scan_entries_inline_format(ctx):
     """Frames without a raw prefix: the chunk-parallel scan carries blocks with an end-of-block
     bound <= 3 inside the entry (DC and two coefficients), the rest by offset."""
-    if ctx.flavour != "auto":
+    if ctx.flavour in ("lane", "warp"):
         pytest.skip("inline entries come from the chunk-parallel scan")
     s, o = clip(208, 112, 128, 4, key_rate=1, lm=2, cm=2, noise_y=12, noise_c=3)
     w, h = 208, 112

@@ -327,18 +327,20 @@ rtj_resolve_last_kernel(const uint32_t *__restrict__ ent, uint16_t *__restrict__
     if (info->skipped_blocks == 0) return;           /* intra-only batch: nothing to resolve */
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nblk) return;
-    const int f0 = blockIdx.y * RESOLVE_T, f1 = min(F, f0 + RESOLVE_T);
-    unsigned last = RTJ_SRC_CARRY;
-    uint32_t e[8];
-    int f = f0;
-    for (; f + 8 <= f1; f += 8) {
+    for (int c = blockIdx.y; c * RESOLVE_T < F; c += gridDim.y) {
+        const int f0 = c * RESOLVE_T, f1 = min(F, f0 + RESOLVE_T);
+        unsigned last = RTJ_SRC_CARRY;
+        uint32_t e[8];
+        int f = f0;
+        for (; f + 8 <= f1; f += 8) {
 #pragma unroll
-        for (int j = 0; j < 8; j++) e[j] = ent[(size_t)(f + j) * nblk + b];
+            for (int j = 0; j < 8; j++) e[j] = ent[(size_t)(f + j) * nblk + b];
 #pragma unroll
-        for (int j = 0; j < 8; j++) if (!RTJ_ENT_IS_SKIP(e[j])) last = (unsigned)(f + j);
+            for (int j = 0; j < 8; j++) if (!RTJ_ENT_IS_SKIP(e[j])) last = (unsigned)(f + j);
+        }
+        for (; f < f1; f++) if (!RTJ_ENT_IS_SKIP(ent[(size_t)f * nblk + b])) last = (unsigned)f;
+        chunk_last[(size_t)c * nblk + b] = (uint16_t)last;
     }
-    for (; f < f1; f++) if (!RTJ_ENT_IS_SKIP(ent[(size_t)f * nblk + b])) last = (unsigned)f;
-    chunk_last[(size_t)blockIdx.y * nblk + b] = (uint16_t)last;
 }
 
 extern "C" __global__ void __launch_bounds__(128)
@@ -348,24 +350,26 @@ rtj_resolve_kernel(const uint32_t *__restrict__ ent, const uint16_t *__restrict_
     if (info->skipped_blocks == 0) return;
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nblk) return;
-    const int f0 = blockIdx.y * RESOLVE_T, f1 = min(F, f0 + RESOLVE_T);
-    unsigned last = RTJ_SRC_CARRY;
-    for (int c = (int)blockIdx.y - 1; c >= 0 && last == RTJ_SRC_CARRY; c--) last = chunk_last[(size_t)c * nblk + b];
-    uint32_t e[8];
-    int f = f0;
-    for (; f + 8 <= f1; f += 8) {
+    for (int c0 = blockIdx.y; c0 * RESOLVE_T < F; c0 += gridDim.y) {
+        const int f0 = c0 * RESOLVE_T, f1 = min(F, f0 + RESOLVE_T);
+        unsigned last = RTJ_SRC_CARRY;
+        for (int c = c0 - 1; c >= 0 && last == RTJ_SRC_CARRY; c--) last = chunk_last[(size_t)c * nblk + b];
+        uint32_t e[8];
+        int f = f0;
+        for (; f + 8 <= f1; f += 8) {
 #pragma unroll
-        for (int j = 0; j < 8; j++) e[j] = ent[(size_t)(f + j) * nblk + b];
+            for (int j = 0; j < 8; j++) e[j] = ent[(size_t)(f + j) * nblk + b];
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            if (RTJ_ENT_IS_SKIP(e[j])) src[(size_t)(f + j) * nblk + b] = (uint16_t)last;
-            else last = (unsigned)(f + j);
+            for (int j = 0; j < 8; j++) {
+                if (RTJ_ENT_IS_SKIP(e[j])) src[(size_t)(f + j) * nblk + b] = (uint16_t)last;
+                else last = (unsigned)(f + j);
+            }
         }
-    }
-    for (; f < f1; f++) {
-        const uint32_t ee = ent[(size_t)f * nblk + b];
-        if (RTJ_ENT_IS_SKIP(ee)) src[(size_t)f * nblk + b] = (uint16_t)last;
-        else last = (unsigned)f;
+        for (; f < f1; f++) {
+            const uint32_t ee = ent[(size_t)f * nblk + b];
+            if (RTJ_ENT_IS_SKIP(ee)) src[(size_t)f * nblk + b] = (uint16_t)last;
+            else last = (unsigned)f;
+        }
     }
 }
 
@@ -455,7 +459,10 @@ extern "C" int rtj_launch_scan(const rtj_launch_args *a, void *stream)
 extern "C" int rtj_launch_resolve(const rtj_launch_args *a, void *stream)
 {
     const int nblk = (a->w >> 4) * (a->h >> 4) * 6;
-    dim3 grid((unsigned)((nblk + 127) / 128), (unsigned)((a->F + RESOLVE_T - 1) / RESOLVE_T));
+    /* a batch without skip markers only pays for the launches: keep the grid modest and let a CTA
+     * stride over the chunks of frames */
+    const int nchunks = (a->F + RESOLVE_T - 1) / RESOLVE_T;
+    dim3 grid((unsigned)((nblk + 127) / 128), (unsigned)(nchunks < 16 ? nchunks : 16));
     rtj_resolve_last_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(a->d_ent, a->d_chunk_last, a->F, nblk, a->d_info);
     rtj_resolve_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(a->d_ent, a->d_chunk_last, a->d_src, a->F, nblk, a->d_info);
     return (int)cudaGetLastError();

@@ -134,7 +134,13 @@ rtj_scan_chunk_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_des
         const int npos = nch * CS_C;
 
         /* ---- load: 16-byte vectors; beyond the payload every byte reads 0x7F, a run token that
-         *      ends any block (the packet's own bytes are never read past its last 16-byte line) ---- */
+         *      ends any block (the packet's own bytes are never read past its last 16-byte line).
+         *      The next segment's lines are asked into L2 now: they are wanted one segment time later. ---- */
+        if (PHASE == 0) {
+            const int next = seg0 + CS_S + tid * 128;                  /* one 128-byte line per thread: CS_THREADS * 128 >= CS_S */
+            if (tid * 128 < CS_S + CS_LA && next < len)
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(gbase + next));
+        }
         {
             const uint4 *g4 = reinterpret_cast<const uint4 *>(gbase + seg0);
             uint4 *s4 = reinterpret_cast<uint4 *>(sh.pay);

@@ -7,11 +7,15 @@ Python package is only the binding that tests and ``bench.py`` drive it through:
 * :mod:`capi`   -- ctypes mirror of ``include/rtjpeg_b200.h``
 * :mod:`device` -- torch-backed device buffers for the device-resident entry point
 
+The library also carries a NuppelVideo container reader (``rtjnuv_*``) that rewraps the RTjpeg
+frames of a ``.nuv`` file as ``'RTJ0'`` packets for the decoder.
+
 The directory name carries a hyphen (it is the reference's name); import it as
 ``gmerlin_avdecoder_b200`` through the shim module at the repository root.
 """
 from .capi import (  # noqa: F401
     BatchContext, BatchInfo, RTjpeg, RTjpegError, State, Timing,
     FRAME_DESC_DTYPE, HOST_IN_PINNED, HOST_OUT_PINNED, LIB_PATH, PLUGIN_PATH, STREAM_SLACK_BYTES,
-    TABLE_CUSTOM, TABLE_ZERO, build_library, load_library, plan, split_shards, tables_for_quality, tables_from_raw,
+    TABLE_CUSTOM, TABLE_ZERO, NuvHeader, build_library, load_library, nuv_extract_rtj0, nuv_open, nuv_packets, nuv_probe,
+    plan, raw_tables_for_quality, split_shards, tables_for_quality, tables_from_raw,
 )

@@ -37,6 +37,18 @@ class BatchInfo(C.Structure):
                 ("bad_frames", C.c_uint32), ("first_bad_frame", C.c_int32)]
 
 
+class NuvHeader(C.Structure):
+    """rtjnuv_header: what lib/demux_nuv.c:58-243 reads before the first frame."""
+    _fields_ = [("width", C.c_int), ("height", C.c_int), ("interlaced", C.c_int), ("is_mythtv", C.c_int),
+                ("aspect", C.c_double), ("fps", C.c_double), ("video_packets", C.c_uint32), ("audio_packets", C.c_uint32),
+                ("has_tables", C.c_int), ("tables", C.c_uint32 * 128), ("data_start", C.c_uint64)]
+
+
+class NuvPacket(C.Structure):
+    _fields_ = [("type", C.c_uint8), ("comptype", C.c_uint8), ("keyframe", C.c_uint8), ("filters", C.c_uint8),
+                ("timecode", C.c_uint32), ("size", C.c_uint32), ("payload_offset", C.c_uint64)]
+
+
 OK = 0
 E_CUDA, E_ARG, E_HEADER, E_SIZE, E_FORMAT, E_OVERRUN, E_TOOBIG, E_NOMEM = -1, -2, -3, -4, -5, -6, -7, -8
 HOST_IN_PINNED, HOST_OUT_PINNED = 1, 2
@@ -119,6 +131,13 @@ def load_library() -> C.CDLL:
     L.rtjgpu_tables_for_quality.restype = None
     L.rtjgpu_tables_from_raw.argtypes = [_u32p, _u32p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.rtjgpu_tables_from_raw.restype = None
+    L.rtjgpu_raw_tables_for_quality.argtypes = [C.c_int, _u32p]
+    L.rtjgpu_raw_tables_for_quality.restype = None
+    L.rtjnuv_probe.argtypes = [_u8p, C.c_size_t]
+    L.rtjnuv_open.argtypes = [_u8p, C.c_size_t, C.POINTER(NuvHeader)]
+    L.rtjnuv_next.argtypes = [_u8p, C.c_size_t, _u64p, C.POINTER(NuvPacket)]
+    L.rtjnuv_extract_rtj0.argtypes = [_u8p, C.c_size_t, C.POINTER(NuvHeader), _u8p, C.c_size_t, _u64p, _u32p,
+                                      C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.rtjgpu_host_alloc.argtypes = [C.c_size_t]
     L.rtjgpu_host_alloc.restype = vp
     L.rtjgpu_host_free.argtypes = [vp]
@@ -165,6 +184,56 @@ def tables_from_raw(raw: np.ndarray):
     a, b = C.c_int(), C.c_int()
     load_library().rtjgpu_tables_from_raw(raw.ctypes.data_as(_u32p), out.ctypes.data_as(_u32p), C.byref(a), C.byref(b))
     return out, a.value, b.value
+
+
+def raw_tables_for_quality(Q: int) -> np.ndarray:
+    """The 128 raw (not AAN-scaled) entries RTjpeg_set_tables takes for quality Q."""
+    out = np.zeros(128, dtype=np.uint32)
+    load_library().rtjgpu_raw_tables_for_quality(Q, out.ctypes.data_as(_u32p))
+    return out
+
+
+# NuppelVideo container (host only) --------------------------------------------
+
+def nuv_probe(data: np.ndarray) -> bool:
+    data = np.ascontiguousarray(data, dtype=np.uint8)
+    return bool(load_library().rtjnuv_probe(_u8(data), data.size))
+
+
+def nuv_open(data: np.ndarray) -> NuvHeader:
+    data = np.ascontiguousarray(data, dtype=np.uint8)
+    h = NuvHeader()
+    _check(load_library().rtjnuv_open(_u8(data), data.size, C.byref(h)), "rtjnuv_open")
+    return h
+
+
+def nuv_packets(data: np.ndarray, hdr: NuvHeader):
+    """Every frame header behind the codec data: list of (type, comptype, keyframe, timecode, size, payload_offset)."""
+    data = np.ascontiguousarray(data, dtype=np.uint8)
+    L = load_library()
+    pos = C.c_uint64(hdr.data_start)
+    p = NuvPacket()
+    out = []
+    while L.rtjnuv_next(_u8(data), data.size, C.byref(pos), C.byref(p)):
+        out.append((chr(p.type), chr(p.comptype), int(p.keyframe), int(p.timecode), int(p.size), int(p.payload_offset)))
+    return out
+
+
+def nuv_extract_rtj0(data: np.ndarray, hdr: NuvHeader):
+    """The file's RTjpeg video frames as 'RTJ0' packets -> (stream, offsets, timecodes, unsupported)."""
+    data = np.ascontiguousarray(data, dtype=np.uint8)
+    L = load_library()
+    cap = max(int(hdr.video_packets), sum(1 for p in nuv_packets(data, hdr) if p[0] == "V"))
+    offsets = np.zeros(cap + 1, dtype=np.uint64)
+    n, bad = C.c_int(), C.c_int()
+    _check(L.rtjnuv_extract_rtj0(_u8(data), data.size, C.byref(hdr), None, 0, offsets.ctypes.data_as(_u64p), None,
+                                 cap, C.byref(n), C.byref(bad)), "rtjnuv_extract_rtj0 (sizing)")
+    total = int(offsets[n.value])
+    stream = np.full(total + STREAM_SLACK_BYTES, 0x7F, dtype=np.uint8)
+    tc = np.zeros(cap, dtype=np.uint32)
+    _check(L.rtjnuv_extract_rtj0(_u8(data), data.size, C.byref(hdr), _u8(stream), total, offsets.ctypes.data_as(_u64p),
+                                 tc.ctypes.data_as(_u32p), cap, C.byref(n), C.byref(bad)), "rtjnuv_extract_rtj0")
+    return stream, offsets[:n.value + 1].copy(), tc[:n.value].copy(), int(bad.value)
 
 
 def split_shards(clean: np.ndarray, n: int) -> np.ndarray:

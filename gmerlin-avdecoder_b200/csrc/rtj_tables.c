@@ -97,6 +97,19 @@ void rtj_table_from_quality(int Q, rtj_host_table *out)
     scale_by_aan(out->ciqt);
 }
 
+void rtjgpu_raw_tables_for_quality(int Q, uint32_t raw[128])
+{
+    if (Q < 1) Q = 1;
+    if (Q > 255) Q = 255;
+    const uint64_t scaled_q = (uint64_t)Q << 25;
+    for (int i = 0; i < 64; i++) {
+        int32_t ql = (int32_t)((scaled_q / ((uint64_t)annexk_luma[i] << 16)) >> 3);
+        int32_t qc = (int32_t)((scaled_q / ((uint64_t)annexk_chroma[i] << 16)) >> 3);
+        raw[i] = (uint32_t)(65536 / ((ql ? ql : 1) << 3));
+        raw[64 + i] = (uint32_t)(65536 / ((qc ? qc : 1) << 3));
+    }
+}
+
 void rtj_table_from_raw(const uint32_t raw[128], rtj_host_table *out)
 {
     for (int i = 0; i < 64; i++) {

@@ -238,6 +238,46 @@ int  rtjgpu_split_shards(const uint8_t *clean, int F, int n, int *first);
 void rtjgpu_tables_for_quality(int Q, uint32_t scaled[128], int *lb8, int *cb8);
 void rtjgpu_tables_from_raw(const uint32_t raw[128], uint32_t scaled[128], int *lb8, int *cb8);
 
+/* The 128 raw (not AAN-scaled) entries RTjpeg_set_tables takes for quality Q -- what a
+ * NuppelVideo writer puts into the file's 'D'/'R' packet. */
+void rtjgpu_raw_tables_for_quality(int Q, uint32_t raw[128]);
+
+/* ------------------------------------------------------------------------ */
+/* NuppelVideo / MythTV container in front of the decoder (host only)         */
+/* ------------------------------------------------------------------------ */
+/* lib/demux_nuv.c tags its video 'NUV ' and hands it to libavcodec; these helpers instead
+ * rewrap the RTjpeg-coded frames of a .nuv file as 'RTJ0' packets for the decoder above. */
+typedef struct rtjnuv_header {
+    int      width, height;          /* lib/demux_nuv.c:78-80 */
+    int      interlaced;             /* :84-89 */
+    int      is_mythtv;              /* :69-72 */
+    double   aspect, fps;            /* :93-94 */
+    uint32_t video_packets, audio_packets;   /* :95-96 */
+    int      has_tables;             /* a 'D' packet of subtype 'R' was found (:157-176) */
+    uint32_t tables[128];            /* its contents: raw tables for RTjpeg_set_tables */
+    uint64_t data_start;             /* offset of the first frame after the codec data (:241) */
+} rtjnuv_header;
+
+typedef struct rtjnuv_packet {
+    uint8_t  type;                   /* 'V' video, 'A' audio, 'D' extradata, 'S' seek point, 'X' MythTV ext, ... */
+    uint8_t  comptype;               /* video: '0' raw, '1' RTjpeg, '2' RTjpeg + LZO, '3' raw + LZO, 'N' black, 'L' repeat */
+    uint8_t  keyframe, filters;
+    uint32_t timecode;               /* milliseconds */
+    uint32_t size;                   /* payload bytes (0 for seek points) */
+    uint64_t payload_offset;
+} rtjnuv_packet;
+
+int rtjnuv_probe(const uint8_t *data, size_t len);                                 /* lib/demux_nuv.c:44 */
+int rtjnuv_open(const uint8_t *data, size_t len, rtjnuv_header *out);              /* lib/demux_nuv.c:58 */
+int rtjnuv_next(const uint8_t *data, size_t len, uint64_t *pos, rtjnuv_packet *out);   /* lib/demux_nuv.c:246; 1 = a packet, 0 = end */
+/* Every RTjpeg-coded ('1') or repeated ('L', written as a frame of skip markers) video frame as an
+ * 'RTJ0' packet: out receives the packets 16-byte aligned, offsets[0..*nframes] their starts (pass
+ * out = NULL to size the buffer: offsets[*nframes] is the total).  Headers carry quality 0: decode
+ * with rtjgpu_set_custom_tables(hdr->tables) and a state {width, height, RTJGPU_TABLE_CUSTOM, 0}.
+ * *unsupported counts video frames of other compression types, which are left out. */
+int rtjnuv_extract_rtj0(const uint8_t *data, size_t len, const rtjnuv_header *hdr, uint8_t *out, size_t out_cap,
+                        uint64_t *offsets, uint32_t *timecodes, int max_frames, int *nframes, int *unsupported);
+
 /* Pinned host memory helpers for callers that stage packets themselves. */
 void *rtjgpu_host_alloc(size_t bytes);
 void  rtjgpu_host_free(void *p);

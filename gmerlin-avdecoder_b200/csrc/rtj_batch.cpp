@@ -126,7 +126,7 @@ int seg_reserve(rtjgpu_ctx *ctx, Workspace *ws, int F, int nblk, int scan_mode, 
     memset(sp, 0, sizeof(*sp));
     if (scan_mode != RTJGPU_SCAN_SEGMENT && !(scan_mode == RTJGPU_SCAN_AUTO && F <= SEG_AUTO_MAX_FRAMES)) return RTJGPU_OK;
     /* a frame needs at most 64 bytes per block */
-    const size_t maxseg = ((size_t)nblk * 64 + RTJ_SEG_BYTES - 1) / RTJ_SEG_BYTES + 1;
+    const size_t maxseg = ((size_t)nblk * 64 + RTJ_SEG_BYTES_MB - 1) / RTJ_SEG_BYTES_MB + 1;   /* the smaller segment size rules */
     const size_t nseg = (size_t)F * maxseg, nsum = nseg * RTJ_SEG_NE;
     if (nsum * sizeof(uint32_t) > SEG_MAX_SUM_BYTES) return RTJGPU_OK;          /* too big: one CTA per frame instead */
     if (nsum > ws->seg_sum_cap) {

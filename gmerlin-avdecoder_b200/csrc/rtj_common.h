@@ -75,7 +75,8 @@ typedef struct rtj_dev_info {
  * every segment first reports, for EVERY possible entry offset, where a parse would leave it and how
  * many units (blocks or macroblocks) it would start; one thread per frame chains these summaries;
  * then every segment is parsed again from its now known entry and emits its entries. */
-#define RTJ_SEG_BYTES 8192
+#define RTJ_SEG_BYTES    8192      /* segment of a frame without raw prefix (rtj_scan_chunk.cu) */
+#define RTJ_SEG_BYTES_MB 4096      /* segment of a frame with raw prefix (rtj_scan_mb.cu) */
 #define RTJ_SEG_NE    384          /* entry offsets a segment is summarised for (64 used without raw prefix) */
 #define RTJ_SEG_UNUSED 0xFFFFFFFFu
 typedef struct rtj_seg_plan {

@@ -387,9 +387,11 @@ rtj_scan_plan_kernel(const rtjgpu_frame_desc *__restrict__ desc, const rtj_dev_t
     const rtjgpu_frame_desc d = desc[f];
     const int len = d.length > RTJPEG_B200_HEADER_BYTES ? (int)d.length - RTJPEG_B200_HEADER_BYTES : 0;
     /* with a raw prefix the summaries count macroblocks (rtj_scan_mb.cu), without it blocks */
-    const int unit = (tables[d.table].bt8[0] | tables[d.table].bt8[1]) ? 6 : 1;
+    const bool raw = (tables[d.table].bt8[0] | tables[d.table].bt8[1]) != 0;
+    const int unit = raw ? 6 : 1;
+    const int segbytes = raw ? RTJ_SEG_BYTES_MB : RTJ_SEG_BYTES;
     int e = 0, nb = 0, seg = 0;
-    for (; seg < sp.maxseg && (long long)seg * RTJ_SEG_BYTES < len && nb < nblk; seg++) {
+    for (; seg < sp.maxseg && (long long)seg * segbytes < len && nb < nblk; seg++) {
         const size_t idx = (size_t)f * sp.maxseg + seg;
         sp.entry[idx] = (uint32_t)e;
         sp.base[idx] = (uint32_t)nb;

@@ -27,16 +27,16 @@
 namespace {
 
 constexpr int MB_THREADS = 128;
-constexpr int MB_S = 8192;                          /* segment bytes */
+constexpr int MB_S = 4096;                          /* segment bytes */
 constexpr int MB_C = 512;                           /* chunk bytes: a power of two >= the longest macroblock (384) */
-constexpr int MB_NCH = MB_S / MB_C;                 /* 16 DP lanes */
+constexpr int MB_NCH = MB_S / MB_C;                 /* 8 DP lanes */
 constexpr int MB_MAXLEN = 6 * 64;                   /* longest macroblock */
 constexpr int MB_DLA = MB_MAXLEN;                   /* positions behind the segment that still need a block length */
 constexpr int MB_LA = MB_DLA + 64 + 64 + 32;        /* payload bytes behind the segment that level 0 may read */
 constexpr int MB_RING = MB_C + 2;                   /* u16 per lane: 257 words (bank skew) */
 constexpr int MB_STAGE = MB_NCH * MB_RING / 2;      /* staged entries per emit round (aliases the rings) */
 constexpr int MB_POS = MB_S + MB_DLA;               /* positions with block lengths */
-constexpr int MB_RUN = 68;                          /* positions per thread in level 0 */
+constexpr int MB_RUN = 36;                          /* positions per thread in level 0 */
 static_assert(MB_RUN * MB_THREADS >= MB_POS && (MB_RUN % 4) == 0 && ((MB_RUN / 4) & 1), "level-0 runs cover the positions; odd word stride");
 
 struct MbShared {
@@ -103,7 +103,7 @@ __device__ __forceinline__ void mb_level0_run(const uint8_t *__restrict__ payb, 
 /* PHASE 0: the whole frame, segment after segment.  PHASE 1 / 2: one segment (blockIdx.x) of frame
  * blockIdx.y -- its summary for the frame-level chain, resp. its entries (rtj_common.h, rtj_seg_plan). */
 template <int PHASE>
-__global__ void __launch_bounds__(MB_THREADS, 3)
+__global__ void __launch_bounds__(MB_THREADS, 7)
 rtj_scan_mb_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc *__restrict__ desc,
                    const rtj_dev_table *__restrict__ tables, int F, int nblk,
                    uint32_t *__restrict__ ent, uint32_t *__restrict__ frame_skips,
@@ -343,7 +343,7 @@ extern "C" int rtj_scan_mb_init(void)
 
 extern "C" int rtj_launch_scan_mb(const rtj_launch_args *a, int phase, void *stream)
 {
-    static_assert(MB_S == RTJ_SEG_BYTES && MB_DLA <= RTJ_SEG_NE, "segment size and entry range are shared with the frame-level chain");
+    static_assert(MB_S == RTJ_SEG_BYTES_MB && MB_DLA <= RTJ_SEG_NE, "segment size and entry range are shared with the frame-level chain");
     const int nblk = (a->w >> 4) * (a->h >> 4) * 6;
     cudaStream_t st = (cudaStream_t)stream;
     const dim3 grid = phase == 0 ? dim3((unsigned)a->F) : dim3((unsigned)a->seg.maxseg, (unsigned)a->F);

@@ -66,8 +66,8 @@ typedef struct rtj_dev_info {
     unsigned long long payload_bytes;
     unsigned int       bad_frames;
     int                first_bad_frame;
-    unsigned int       hard_blocks;      /* length of the K2 -> K2b queue */
-    unsigned int       pad;
+    unsigned int       hard_blocks;      /* K2 -> K2b queue: mid-size blocks, filled from the front ... */
+    unsigned int       hard_full;        /* ... and long blocks, filled from the back */
 } rtj_dev_info;
 
 /* ---- segment-parallel scan (few, large frames): a frame's 8 KB segments are parsed by separate

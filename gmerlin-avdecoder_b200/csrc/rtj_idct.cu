@@ -380,6 +380,7 @@ struct K2Params {
     uint8_t *out;
     const uint8_t *carry;
     uint32_t *hardq;
+    unsigned hardq_cap;              /* entries of hardq: F * nblk */
     rtj_dev_info *info;
 };
 
@@ -496,7 +497,9 @@ rtj_idct_kernel(const K2Params P)
             wq_p[at] = (uint32_t)pp.off | (sf << 16);
         } else if (cls == Q_CARRY || cls == Q_HARD) {
             const int at = K2_WQ - 1 - (nback + __popc(mB & below));
-            wq_e[at] = (uint32_t)pp.i | (cls == Q_CARRY ? 0x80000000u : 0u);
+            /* HARD blocks split once more for the general kernel: long ones (E > 16) apart from the rest */
+            const bool full = cls == Q_HARD && !RTJ_ENT_IS_INLINE(e) && RTJ_ENT_EOB(e) > 16;
+            wq_e[at] = (uint32_t)pp.i | (cls == Q_CARRY ? 0x80000000u : 0u) | (full ? 0x40000000u : 0u);
             wq_p[at] = (uint32_t)pp.off;
         }
         nfront += __popc(mM);
@@ -548,14 +551,22 @@ rtj_idct_kernel(const K2Params P)
             int off = 0;
             if (live) { ie = wq_e[K2_WQ - 1 - idx]; off = (int)wq_p[K2_WQ - 1 - idx]; }
             const bool hard = live && !(ie >> 31);
-            const int bi = (int)(ie & 0x7FFFFFFFu);              /* stream-order index inside the strip */
-            const unsigned mH = __ballot_sync(FULL, hard);
-            if (mH) {
-                unsigned base = 0;
-                if (lane == 0) base = atomicAdd(&P.info->hard_blocks, (unsigned)__popc(mH));
+            const bool full = hard && ((ie >> 30) & 1u);
+            const int bi = (int)(ie & 0x3FFFFFFFu);              /* stream-order index inside the strip */
+            const unsigned mH = __ballot_sync(FULL, hard && !full), mF = __ballot_sync(FULL, full);
+            if (mH | mF) {
+                /* the device queue is filled from both ends: mid-size blocks from the front, long ones from the back */
+                unsigned base = 0, baseF = 0;
+                if (lane == 0) {
+                    if (mH) base = atomicAdd(&P.info->hard_blocks, (unsigned)__popc(mH));
+                    if (mF) baseF = atomicAdd(&P.info->hard_full, (unsigned)__popc(mF));
+                }
                 base = __shfl_sync(FULL, base, 0);
-                if (hard) P.hardq[base + __popc(mH & ((1u << lane) - 1u))] = frame_blk0 + (unsigned)bi;
-                nhard += __popc(mH);
+                baseF = __shfl_sync(FULL, baseF, 0);
+                const unsigned below = (1u << lane) - 1u;
+                if (hard && !full) P.hardq[base + __popc(mH & below)] = frame_blk0 + (unsigned)bi;
+                if (full) P.hardq[P.hardq_cap - 1u - (baseF + __popc(mF & below))] = frame_blk0 + (unsigned)bi;
+                nhard += __popc(mH) + __popc(mF);
             }
             if (live && !hard) {
                 uint32_t px[16];
@@ -626,18 +637,41 @@ rtj_idct_kernel(const K2Params P)
 /* K2b: the general decoder for queued blocks                                  */
 /* ------------------------------------------------------------------------ */
 
+namespace {
+
+/* destination of block i (stream order) of frame f in the tight-pitch planes */
+__device__ __forceinline__ uint8_t *block_dst(uint8_t *out, unsigned f, int i, int w, int h, int &pitch)
+{
+    const int mbw = w >> 4, cw = w >> 1;
+    const size_t fsz = (size_t)w * h * 3 / 2;
+    const int mb = i / 6, sub = i - mb * 6;
+    const int my = mb / mbw, mx = mb - my * mbw;
+    if (sub < 4) {
+        pitch = w;
+        return out + (size_t)f * fsz + (size_t)(my * 16 + (sub >> 1) * 8) * w + mx * 16 + (sub & 1) * 8;
+    }
+    pitch = cw;
+    return out + (size_t)f * fsz + (size_t)w * h + (sub == 5 ? (size_t)cw * (h >> 1) : 0) + (size_t)(my * 8) * cw + mx * 8;
+}
+
+} // namespace
+
+/* One thread per queued block.  The queue holds mid-size blocks (E <= 16, or carried inline but last
+ * written under other tables) at its front and long blocks at its back, so that a warp runs one flow
+ * graph: the first 16 zig-zag positions touch rows 0..5 and columns 0..4 only and fit 24 bytes held in
+ * registers; long blocks take the reference's full two passes, fed byte by byte. */
 extern "C" __global__ void __launch_bounds__(128)
 rtj_idct_hard_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc *__restrict__ desc,
                      const rtj_dev_table *__restrict__ tables, const uint32_t *__restrict__ ent,
                      const uint16_t *__restrict__ srcf, int nblk, int w, int h,
-                     uint8_t *__restrict__ out, const uint32_t *__restrict__ hardq,
+                     uint8_t *__restrict__ out, const uint32_t *__restrict__ hardq, unsigned hardq_cap,
                      const rtj_dev_info *__restrict__ info)
 {
-    const unsigned n = info->hard_blocks;
-    const int mbw = w >> 4, cw = w >> 1;
-    const size_t fsz = (size_t)w * h * 3 / 2;
-    for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
-        const uint32_t gidx = hardq[k];
+    const unsigned n16 = info->hard_blocks, nfull = info->hard_full;
+    const unsigned stride = gridDim.x * blockDim.x, first = blockIdx.x * blockDim.x + threadIdx.x;
+    for (unsigned k = first; k < n16 + nfull; k += stride) {
+        const bool full = k >= n16;
+        const uint32_t gidx = full ? hardq[hardq_cap - 1u - (k - n16)] : hardq[k];
         const unsigned f = gidx / (unsigned)nblk;
         const int i = (int)(gidx - f * (unsigned)nblk);
         uint32_t e = ent[gidx];
@@ -646,32 +680,28 @@ rtj_idct_hard_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc
             sf = srcf[gidx];
             e = ent[(size_t)sf * nblk + i];
         }
-        const int mb = i / 6, sub = i - mb * 6;
-        const int chroma = sub >= 4;
+        const int chroma = (i % 6) >= 4;
         const rtj_dev_table *t = &tables[desc[sf].table];
+        const uint8_t *src = stream + desc[sf].offset + RTJPEG_B200_HEADER_BYTES + (e & RTJ_ENT_OFF_MASK);
         uint32_t px[16];
-        if (RTJ_ENT_IS_INLINE(e)) {
+        if (full) {
+            MemBytes by(src);
+            int x[64];
+            unpack_block<64>(by, t->iq[chroma], t->bt8[chroma], x);
+            idct_general<64>(x, px);
+        } else if (RTJ_ENT_IS_INLINE(e)) {
             const int x0 = wrap16((int)(e & 0xFFu) * t->iq[chroma][0]) + 4;
             const int x1 = wrap16((int)(signed char)((e >> 8) & 0xFFu) * t->iq[chroma][1]);
             const int q = wrap16((int)(signed char)((e >> 16) & 0xFFu) * t->iq[chroma][2]);
             t2_pixels(x0, x1, q, false, px);
         } else {
-            MemBytes by(stream + desc[sf].offset + RTJPEG_B200_HEADER_BYTES + (e & RTJ_ENT_OFF_MASK));
-            int x[64];
-            unpack_block<64>(by, t->iq[chroma], t->bt8[chroma], x);
-            idct_general<64>(x, px);
+            RegBytes<6> by(src);
+            int x[16];
+            unpack_block<16>(by, t->iq[chroma], t->bt8[chroma], x);
+            idct_general<16>(x, px);
         }
-        const int my = mb / mbw, mx = mb - my * mbw;
-        uint8_t *dst;
         int pitch;
-        if (!chroma) {
-            pitch = w;
-            dst = out + (size_t)f * fsz + (size_t)(my * 16 + (sub >> 1) * 8) * w + mx * 16 + (sub & 1) * 8;
-        } else {
-            pitch = cw;
-            dst = out + (size_t)f * fsz + (size_t)w * h + (sub == 5 ? (size_t)cw * (h >> 1) : 0)
-                  + (size_t)(my * 8) * cw + mx * 8;
-        }
+        uint8_t *dst = block_dst(out, f, i, w, h, pitch);
 #pragma unroll
         for (int r = 0; r < 8; r++)
             *reinterpret_cast<uint2 *>(dst + (size_t)r * pitch) = make_uint2(px[2 * r], px[2 * r + 1]);
@@ -722,6 +752,7 @@ extern "C" int rtj_launch_idct(const rtj_launch_args *a, void *stream)
     P.nblk = mbw * mbh * 6; P.w = a->w; P.h = a->h;
     P.seg_mb = idct_seg_mb(mbw, &P.nstrips);
     P.out = a->d_out; P.carry = a->d_carry; P.hardq = a->d_hardq; P.info = a->d_info;
+    P.hardq_cap = (unsigned)((size_t)a->F * (size_t)P.nblk);
     dim3 grid((unsigned)(P.nstrips * mbh), (unsigned)a->F);
     if (P.nstrips == 1)
         rtj_idct_kernel<true><<<grid, IDCT_THREADS, idct_smem_bytes(P.seg_mb), st>>>(P);
@@ -732,6 +763,6 @@ extern "C" int rtj_launch_idct(const rtj_launch_args *a, void *stream)
     /* the queue's length is only known on the device: a fixed grid strides over it */
     const int sms = g_sm_count > 0 ? g_sm_count : 148;
     rtj_idct_hard_kernel<<<sms * 4, 128, 0, st>>>(
-        a->d_stream, a->d_desc, a->d_tables, a->d_ent, a->d_src, P.nblk, a->w, a->h, a->d_out, a->d_hardq, a->d_info);
+        a->d_stream, a->d_desc, a->d_tables, a->d_ent, a->d_src, P.nblk, a->w, a->h, a->d_out, a->d_hardq, P.hardq_cap, a->d_info);
     return (int)cudaGetLastError();
 }

@@ -199,3 +199,67 @@ def test_plugin_ends_stream_on_malformed_packet(host):
     assert host.stub_decode(dec, st, Y.ctypes.data, U.ctypes.data, V.ctypes.data, 64, 32, None) == 0
     host.stub_close(dec, st)
     host.stub_stream_destroy(st)
+
+
+@pytest.mark.parametrize("lookahead", [1, 5, 32])
+def test_plugin_lookahead_is_invisible(host, lookahead, monkeypatch):
+    """The plugin reads packets ahead and decodes them in batches; what the caller sees must be what
+    lib/video_rtjpeg.c shows it: frames in order with their packets' timestamps, and a dropped packet
+    (NULL frame) leaving the picture -- and every skipped block of later frames -- untouched."""
+    from streams import clip
+    monkeypatch.setenv("RTJPEG_B200_LOOKAHEAD", str(lookahead))
+    w, h, F = 96, 64, 41
+    s, o = clip(w, h, 128, F, key_rate=9, lm=2, cm=2, noise_y=4)
+    s = np.ascontiguousarray(s)
+    sizes = O.packet_sizes(s, o).astype(np.uint32)
+    dec = host.stub_find_decoder(FOURCC_RTJ0)
+    st = host.stub_stream_create(w, h)
+    offs = np.ascontiguousarray(o[:-1], dtype=np.uint64)
+    host.stub_stream_set_packets(st, s.ctypes.data, offs.ctypes.data, sizes.ctypes.data, F)
+    assert host.stub_init(dec, st) == 1
+    Y = np.zeros((h, w), dtype=np.uint8); U = np.zeros((h // 2, w // 2), dtype=np.uint8); V = np.zeros_like(U)
+    dropped = {0, 4, 5, 6, 17, 31, 32, 40}                   # at ring borders, in runs, first and last
+    od = O.OracleDecoder()
+    ref = np.zeros(w * h * 3 // 2, dtype=np.uint8)
+    pts = C.c_int64()
+    for f in range(F):
+        if f in dropped:
+            assert host.stub_decode(dec, st, None, None, None, 0, 0, None) == 1
+            continue
+        assert host.stub_decode(dec, st, Y.ctypes.data, U.ctypes.data, V.ctypes.data, w, w // 2, C.byref(pts)) == 1
+        od.decode(s[int(o[f]):int(o[f]) + int(sizes[f])], ref)   # the reference never saw the dropped packets
+        assert pts.value == 1000 + 40 * f
+        got = np.concatenate([Y.ravel(), U.ravel(), V.ravel()])
+        assert np.array_equal(got, ref), f
+    assert host.stub_decode(dec, st, Y.ctypes.data, U.ctypes.data, V.ctypes.data, w, w // 2, None) == 0
+    fw, fh, pf, done = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+    key, val = C.create_string_buffer(64), C.create_string_buffer(64)
+    host.stub_stream_info(st, fw, fh, pf, done, key, val)
+    assert done.value == F
+    host.stub_close(dec, st)
+    host.stub_stream_destroy(st)
+
+
+def test_plugin_serves_frames_before_a_damaged_packet(host, monkeypatch):
+    monkeypatch.setenv("RTJPEG_B200_LOOKAHEAD", "8")
+    from streams import clip, reference_frames
+    w, h, F = 320, 240, 6
+    s, o = clip(w, h, 128, F, noise_y=3)
+    s = np.ascontiguousarray(s)
+    want = reference_frames(s, o, w, h, np.zeros(w * h * 3 // 2, dtype=np.uint8))
+    sizes = O.packet_sizes(s, o).astype(np.uint32)
+    sizes[2] = sizes[2] // 3                                 # third packet arrives truncated, inside the first batch
+    dec = host.stub_find_decoder(FOURCC_RTJ0)
+    st = host.stub_stream_create(w, h)
+    offs = np.ascontiguousarray(o[:-1], dtype=np.uint64)
+    host.stub_stream_set_packets(st, s.ctypes.data, offs.ctypes.data, sizes.ctypes.data, F)
+    assert host.stub_init(dec, st) == 1
+    Y = np.zeros((h, w), dtype=np.uint8); U = np.zeros((h // 2, w // 2), dtype=np.uint8); V = np.zeros_like(U)
+    for f in range(2):
+        assert host.stub_decode(dec, st, Y.ctypes.data, U.ctypes.data, V.ctypes.data, w, w // 2, None) == 1
+        assert np.array_equal(np.concatenate([Y.ravel(), U.ravel(), V.ravel()]), want[f]), f
+    assert host.stub_decode(dec, st, Y.ctypes.data, U.ctypes.data, V.ctypes.data, w, w // 2, None) == 0
+    assert host.stub_decode(dec, st, Y.ctypes.data, U.ctypes.data, V.ctypes.data, w, w // 2, None) == 0
+    host.stub_close(dec, st)
+    host.stub_stream_destroy(st)
+

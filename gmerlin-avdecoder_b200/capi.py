@@ -114,6 +114,7 @@ def load_library() -> C.CDLL:
     L.rtjgpu_last_cuda_error.argtypes = [vp]
     L.rtjgpu_set_custom_tables.argtypes = [vp, _u32p]
     L.rtjgpu_set_scan_mode.argtypes = [vp, C.c_int]
+    L.rtjgpu_set_format.argtypes = [vp, C.c_int]
     L.rtjgpu_plan.argtypes = [_u8p, _u64p, C.c_int, C.POINTER(State), vp]
     L.rtjgpu_decode_device.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp]
     L.rtjgpu_decode_host.argtypes = [vp, _u8p, _u64p, C.c_int, C.POINTER(State), _u8p, _u8p, C.c_int]
@@ -144,6 +145,11 @@ def load_library() -> C.CDLL:
     L.rtjgpu_host_free.restype = None
     _lib = L
     return L
+
+
+def frame_bytes(fmt: int, w: int, h: int) -> int:
+    """Tight planes of one picture: YUV420 w*h*3/2, YUV422 w*h*2, 8-bit grey w*h."""
+    return w * h * 3 // 2 if fmt == 0 else w * h * 2 if fmt == 1 else w * h
 
 
 def _u8(a: np.ndarray):
@@ -273,6 +279,10 @@ class BatchContext:
         """0 = auto, 1 = one thread per frame, 2 = one warp per frame."""
         _check(self._L.rtjgpu_set_scan_mode(self._h, mode), "rtjgpu_set_scan_mode")
 
+    def set_format(self, fmt: int) -> None:
+        """RTJ_YUV420 (default), RTJ_YUV422 or RTJ_RGB8 (8-bit grey) for the batches that follow."""
+        _check(self._L.rtjgpu_set_format(self._h, fmt), "rtjgpu_set_format")
+
     def set_custom_tables(self, raw: np.ndarray) -> None:
         raw = np.ascontiguousarray(raw, dtype=np.uint32)
         assert raw.size == 128
@@ -353,6 +363,7 @@ class RTjpeg:
     def set_format(self, fmt: int) -> None:
         v = C.c_int(fmt)
         self._L.RTjpeg_set_format(self._h, C.byref(v))
+        self._fmt = fmt
 
     def set_size(self, w: int, h: int) -> int:
         a, b = C.c_int(w), C.c_int(h)
@@ -374,14 +385,16 @@ class RTjpeg:
 
     def _planes(self, planes: np.ndarray, w: int, h: int):
         assert planes.dtype == np.uint8 and planes.flags.c_contiguous
-        if planes.size < w * h * 3 // 2:      # header lies about the geometry: the library refuses it before any plane access
+        fmt = getattr(self, "_fmt", 0)
+        if planes.size < frame_bytes(fmt, w, h):      # header lies about the geometry: the library refuses it before any plane access
             w = h = 0
         base = planes.ctypes.data
-        arr = (_u8p * 3)(C.cast(base, _u8p), C.cast(base + w * h, _u8p), C.cast(base + w * h * 5 // 4, _u8p))
+        csz = w * h // 4 if fmt == 0 else w * h // 2 if fmt == 1 else 0
+        arr = (_u8p * 3)(C.cast(base, _u8p), C.cast(base + w * h, _u8p), C.cast(base + w * h + csz, _u8p))
         return arr
 
     def decompress(self, pkt: np.ndarray, planes: np.ndarray) -> None:
-        """RTjpeg_decompress: planes is one tight YUV420 buffer (Y|U|V) updated in place."""
+        """RTjpeg_decompress: planes is one tight buffer (Y|U|V in the current format) updated in place."""
         pkt = np.ascontiguousarray(pkt, dtype=np.uint8)
         w = int(pkt[6]) | int(pkt[7]) << 8
         h = int(pkt[8]) | int(pkt[9]) << 8

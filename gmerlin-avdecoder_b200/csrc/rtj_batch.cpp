@@ -77,6 +77,7 @@ struct rtjgpu_ctx {
     uint8_t       *d_host_carry = nullptr;    /* carry plane of the host pipeline */
     size_t         d_host_carry_cap = 0;
     int            scan_mode = RTJGPU_SCAN_AUTO;
+    int            format = RTJ_YUV420;
     uint64_t       host_bad = 0;              /* overrun frames seen by the current rtjgpu_decode_host call */
 };
 
@@ -176,12 +177,13 @@ int run_kernels(rtjgpu_ctx *ctx, Workspace *ws, const uint8_t *d_stream, const r
     rtj_launch_args a;
     a.d_stream = d_stream; a.d_desc = d_desc; a.d_tables = ctx->d_tables;
     a.F = F; a.w = w; a.h = h;
+    a.fmt = ctx->format;
     a.d_ent = ws->d_ent; a.d_src = ws->d_src; a.d_frame_skips = ws->d_frame_skips; a.d_info = ws->d_info;
     a.d_hardq = ws->d_hardq; a.d_chunk_last = ws->d_chunk_last;
     a.d_out = d_out; a.d_carry = d_carry;
     a.scan_mode = ctx->scan_mode;
     {
-        const int rc = seg_reserve(ctx, ws, F, (w >> 4) * (h >> 4) * 6, ctx->scan_mode, &a.seg);
+        const int rc = seg_reserve(ctx, ws, F, RTJ_FMT_NBLK(ctx->format, w, h), ctx->scan_mode, &a.seg);
         if (rc) return rc;
     }
 
@@ -329,6 +331,13 @@ int rtjgpu_set_scan_mode(rtjgpu_ctx *ctx, int mode)
     return RTJGPU_OK;
 }
 
+int rtjgpu_set_format(rtjgpu_ctx *ctx, int format)
+{
+    if (!ctx || format < RTJ_YUV420 || format > RTJ_RGB8) return RTJGPU_E_ARG;
+    ctx->format = format;
+    return RTJGPU_OK;
+}
+
 int rtjgpu_set_custom_tables(rtjgpu_ctx *ctx, const uint32_t raw[128])
 {
     if (!ctx || !raw) return RTJGPU_E_ARG;
@@ -396,7 +405,7 @@ int rtjgpu_decode_device(rtjgpu_ctx *ctx, const uint8_t *d_stream, const rtjgpu_
     if (w <= 0 || h <= 0 || (w & 15) || (h & 15) || w > 65535 || h > 65535) return RTJGPU_E_SIZE;
     if (F > RTJGPU_MAX_FRAMES_PER_BATCH) return RTJGPU_E_TOOBIG;
     CK(ctx, cudaSetDevice(ctx->device));
-    const int nblk = (w >> 4) * (h >> 4) * 6;
+    const int nblk = RTJ_FMT_NBLK(ctx->format, w, h);
     if ((uint64_t)F * (uint64_t)nblk >= (1ull << 32)) return RTJGPU_E_TOOBIG;   /* block indices are 32 bit */
     int rc = ws_reserve(ctx, &ctx->ws, F, nblk);
     if (rc) return rc;
@@ -562,8 +571,8 @@ int rtjgpu_decode_host(rtjgpu_ctx *ctx, const uint8_t *h_stream, const uint64_t 
     if (offsets[1] - offsets[0] < RTJPEG_B200_HEADER_BYTES) return RTJGPU_E_HEADER;
     const int w = rd_u16le(h_stream + offsets[0] + 6), h = rd_u16le(h_stream + offsets[0] + 8);
     if (w == 0 || h == 0 || (w & 15) || (h & 15)) return RTJGPU_E_SIZE;
-    const size_t fsz = (size_t)w * h * 3 / 2;
-    const int nblk = (w >> 4) * (h >> 4) * 6;
+    const size_t fsz = RTJ_FMT_FRAME_BYTES(ctx->format, w, h);
+    const int nblk = RTJ_FMT_NBLK(ctx->format, w, h);
 
     /* chunk size: ~64 MB of output per chunk keeps three slots in flight without
      * hoarding memory; at least 1, at most the batch limit */

@@ -32,6 +32,18 @@ extern "C" {
 #define RTJ_ENT_IS_INLINE(e) (((e) & RTJ_ENT_INLINE_BIT) != 0u && (e) != RTJ_ENT_SKIP)
 #define RTJ_ENT_EOB(e) ((int)(((e) >> RTJ_ENT_OFF_BITS) & 63u) + 1)
 
+/* ---- picture formats (include/RTjpeg.h:111-113; RTjpeg_decompress dispatches on them, lib/RTjpeg.c:3580-3585) --
+ * A picture is walked in UNITS: YUV420 a 16x16 macroblock of 4 luma + 2 chroma blocks (lib/RTjpeg.c:2701-2745),
+ * YUV422 a 16x8 unit of 2 luma + 2 chroma blocks (:2654-2681, chroma half width, full height), 8-bit grey
+ * a single 8x8 luma block (:2761-2770). */
+#define RTJ_FMT_UNIT_BLOCKS(fmt) ((fmt) == 0 ? 6 : (fmt) == 1 ? 4 : 1)
+#define RTJ_FMT_UNIT_LUMA(fmt)   ((fmt) == 0 ? 4 : (fmt) == 1 ? 2 : 1)
+#define RTJ_FMT_UNITS_X(fmt, w)  ((fmt) == 2 ? (w) >> 3 : (w) >> 4)
+#define RTJ_FMT_UNITS_Y(fmt, h)  ((fmt) == 0 ? (h) >> 4 : (h) >> 3)
+#define RTJ_FMT_NBLK(fmt, w, h)  (RTJ_FMT_UNITS_X(fmt, w) * RTJ_FMT_UNITS_Y(fmt, h) * RTJ_FMT_UNIT_BLOCKS(fmt))
+#define RTJ_FMT_FRAME_BYTES(fmt, w, h) \
+    ((fmt) == 0 ? (size_t)(w) * (h) * 3 / 2 : (fmt) == 1 ? (size_t)(w) * (h) * 2 : (size_t)(w) * (h))
+
 /* K3 output for skipped blocks: index of the last frame of the batch that
  * coded the block, or RTJ_SRC_CARRY when none has yet. */
 #define RTJ_SRC_CARRY 0xFFFFu
@@ -93,6 +105,7 @@ typedef struct rtj_launch_args {
     const rtjgpu_frame_desc *d_desc;
     const rtj_dev_table     *d_tables;
     int                      F, w, h;
+    int                      fmt;           /* RTJ_YUV420 / RTJ_YUV422 / RTJ_RGB8 */
     uint32_t                *d_ent;         /* [F][nblk] */
     uint16_t                *d_src;         /* [F][nblk] */
     uint32_t                *d_frame_skips; /* [F] */

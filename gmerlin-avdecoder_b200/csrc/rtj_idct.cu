@@ -330,43 +330,127 @@ __device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, unsigne
 }
 
 /*
- * Strip geometry.  A strip of `mbs` macroblocks holds 6*mbs blocks; stream order is
- * i = 6*mb + sub (Y00 Y01 Y10 Y11 U V, lib/RTjpeg.c:2704-2739).  The kernel works in
- * "picture order" p: [0, 2mbs) upper luma block row left to right, [2mbs, 4mbs) lower
- * luma block row, [4mbs, 5mbs) U, [5mbs, 6mbs) V -- so consecutive p are horizontally
- * adjacent 8-byte runs of the shared picture strip (16 luma rows of 16*mbs bytes, then
- * 8 U rows and 8 V rows of 8*mbs bytes), and a warp's stores never conflict.
+ * Strip geometry, per picture format (rtj_common.h).  A strip of `mbs` units holds BLK*mbs blocks in
+ * stream order i = BLK*unit + sub: YUV420 Y00 Y01 Y10 Y11 U V (lib/RTjpeg.c:2704-2739), YUV422
+ * Y0 Y1 U V (:2654-2681), grey Y (:2761-2770).  The kernel works in "picture order" p -- luma block
+ * rows left to right, then U, then V -- so consecutive p are horizontally adjacent 8-byte runs of the
+ * shared picture strip and a warp's stores never conflict.  The strip holds the luma rows
+ * (16 or 8 rows), then 8 U rows and 8 V rows of half the width.
  */
 struct PicPos {
     int i;          /* stream-order index inside the strip */
     int off;        /* byte offset of the block's first row inside the shared strip (< 65536) */
 };
 
-/* branch-free; luma positions come first */
-__device__ __forceinline__ PicPos pic_pos(int p, int mbs)
-{
-    const bool luma = p < 4 * mbs;
-    const int half = luma ? 2 * mbs : mbs;
-    const int t = luma ? p : p - 4 * mbs;
-    const int hi = t >= half ? 1 : 0;
-    const int c = t - (hi ? half : 0);
-    PicPos r;
-    r.i = luma ? 3 * c - 2 * (c & 1) + 2 * hi              /* 6 * (c >> 1) + 2 * hi + (c & 1) */
-               : 6 * c + 4 + hi;
-    r.off = 8 * c + (luma ? hi * 128 * mbs : (256 + hi * 64) * mbs);     /* V follows the 8 rows of U */
-    return r;
-}
+template <int FMT> struct Geo;
 
-/* the strip holds 16 luma rows of 16*mbs bytes, then 8 U rows and 8 V rows of 8*mbs bytes */
-__device__ __forceinline__ bool off_is_chroma(int off, int mbs) { return off >= 256 * mbs; }
+template <> struct Geo<0> {                 /* YUV420: units of 16x16 */
+    static constexpr int BLK = 6, UNIT_W = 16, LUMA_ROWS = 16, TILE = 384, CHROMA_AT = 256, PLANES = 3;
+    __device__ static __forceinline__ PicPos pic_pos(int p, int mbs)        /* branch-free; luma positions come first */
+    {
+        const bool luma = p < 4 * mbs;
+        const int half = luma ? 2 * mbs : mbs;
+        const int t = luma ? p : p - 4 * mbs;
+        const int hi = t >= half ? 1 : 0;
+        const int c = t - (hi ? half : 0);
+        PicPos r;
+        r.i = luma ? 3 * c - 2 * (c & 1) + 2 * hi              /* 6 * (c >> 1) + 2 * hi + (c & 1) */
+                   : 6 * c + 4 + hi;
+        r.off = 8 * c + (luma ? hi * 128 * mbs : (256 + hi * 64) * mbs);     /* V follows the 8 rows of U */
+        return r;
+    }
+    /* block bi (stream order inside the strip that starts at unit mx0 of unit row my) in a tight-pitch picture */
+    __device__ static __forceinline__ const uint8_t *carry_src(const uint8_t *pic, int bi, int my, int mx0, int w, int h, int &pitch)
+    {
+        const int mb = bi / 6, sub = bi - mb * 6;
+        if (sub < 4) {
+            pitch = w;
+            return pic + (size_t)(my * 16 + (sub >> 1) * 8) * w + (mx0 + mb) * 16 + (sub & 1) * 8;
+        }
+        pitch = w >> 1;
+        return pic + (size_t)w * h + (sub == 5 ? (size_t)(w >> 1) * (h >> 1) : 0) + (size_t)(my * 8) * pitch + (mx0 + mb) * 8;
+    }
+};
 
+template <> struct Geo<1> {                 /* YUV422: units of 16x8, chroma half width and full height */
+    static constexpr int BLK = 4, UNIT_W = 16, LUMA_ROWS = 8, TILE = 256, CHROMA_AT = 128, PLANES = 3;
+    __device__ static __forceinline__ PicPos pic_pos(int p, int mbs)
+    {
+        const bool luma = p < 2 * mbs;
+        const int t = luma ? p : p - 2 * mbs;
+        const int hi = (!luma && t >= mbs) ? 1 : 0;
+        const int c = t - hi * mbs;
+        PicPos r;
+        r.i = luma ? 2 * c - (c & 1) : 4 * c + 2 + hi;         /* 4 * (c >> 1) + (c & 1) */
+        r.off = 8 * c + (luma ? 0 : (128 + hi * 64) * mbs);
+        return r;
+    }
+    __device__ static __forceinline__ const uint8_t *carry_src(const uint8_t *pic, int bi, int my, int mx0, int w, int h, int &pitch)
+    {
+        const int un = bi >> 2, sub = bi & 3;
+        if (sub < 2) {
+            pitch = w;
+            return pic + (size_t)(my * 8) * w + (mx0 + un) * 16 + sub * 8;
+        }
+        pitch = w >> 1;
+        return pic + (size_t)w * h + (sub == 3 ? (size_t)pitch * h : 0) + (size_t)(my * 8) * pitch + (mx0 + un) * 8;
+    }
+};
+
+template <> struct Geo<2> {                 /* 8-bit grey: units of 8x8, luma only */
+    static constexpr int BLK = 1, UNIT_W = 8, LUMA_ROWS = 8, TILE = 64, CHROMA_AT = 64, PLANES = 1;
+    __device__ static __forceinline__ PicPos pic_pos(int p, int mbs)
+    {
+        PicPos r;
+        r.i = p;
+        r.off = 8 * p;
+        return r;
+    }
+    __device__ static __forceinline__ const uint8_t *carry_src(const uint8_t *pic, int bi, int my, int mx0, int w, int h, int &pitch)
+    {
+        pitch = w;
+        return pic + (size_t)(my * 8) * w + (mx0 + bi) * 8;
+    }
+};
+
+template <int FMT>
+__device__ __forceinline__ bool off_is_chroma(int off, int mbs) { return Geo<FMT>::PLANES == 3 && off >= Geo<FMT>::CHROMA_AT * mbs; }
+
+template <int FMT>
 __device__ __forceinline__ void store_block(uint8_t *tile, int off, int mbs, const uint32_t (&px)[16])
 {
     uint8_t *dst = tile + off;
-    const int pitch = off_is_chroma(off, mbs) ? 8 * mbs : 16 * mbs;
+    const int luma_pitch = Geo<FMT>::UNIT_W * mbs;
+    const int pitch = off_is_chroma<FMT>(off, mbs) ? luma_pitch / 2 : luma_pitch;
 #pragma unroll
     for (int r = 0; r < 8; r++)
         *reinterpret_cast<uint2 *>(dst + r * pitch) = make_uint2(px[2 * r], px[2 * r + 1]);
+}
+
+/* Where block i (stream order, whole frame) of frame f lives in the tight-pitch output planes. */
+__device__ __forceinline__ uint8_t *block_dst(uint8_t *base, int fmt, int i, int w, int h, int &pitch)
+{
+    const int cw = w >> 1;
+    if (fmt == 0) {
+        const int mbw = w >> 4;
+        const int mb = i / 6, sub = i - mb * 6;
+        const int my = mb / mbw, mx = mb - my * mbw;
+        if (sub < 4) { pitch = w; return base + (size_t)(my * 16 + (sub >> 1) * 8) * w + mx * 16 + (sub & 1) * 8; }
+        pitch = cw;
+        return base + (size_t)w * h + (sub == 5 ? (size_t)cw * (h >> 1) : 0) + (size_t)(my * 8) * cw + mx * 8;
+    }
+    if (fmt == 1) {
+        const int uw = w >> 4;
+        const int un = i >> 2, sub = i & 3;
+        const int by = un / uw, ux = un - by * uw;
+        if (sub < 2) { pitch = w; return base + (size_t)(by * 8) * w + ux * 16 + sub * 8; }
+        pitch = cw;
+        return base + (size_t)w * h + (sub == 3 ? (size_t)cw * h : 0) + (size_t)(by * 8) * cw + ux * 8;
+    }
+    const int bw = w >> 3;
+    const int by = i / bw, bx = i - by * bw;
+    pitch = w;
+    return base + (size_t)(by * 8) * w + bx * 8;
 }
 
 /* what the kernel takes from the host */
@@ -379,6 +463,7 @@ struct K2Params {
     int nblk, w, h, seg_mb, nstrips;
     uint8_t *out;
     const uint8_t *carry;
+    int fmt;
     uint32_t *hardq;
     unsigned hardq_cap;              /* entries of hardq: F * nblk */
     rtj_dev_info *info;
@@ -400,25 +485,26 @@ constexpr int K2_WQ = K2_ROUNDS_MAX * 32;          /* queue slots of one warp: e
  * SINGLE: the strip is the whole macroblock row (frames up to IDCT_MAX_MB macroblocks wide): no
  * strip arithmetic, and the strip is contiguous in the tight-pitch output planes -> TMA bulk stores.
  */
-template <bool SINGLE>
+template <bool SINGLE, int FMT>
 __global__ void __launch_bounds__(IDCT_THREADS, 8)
 rtj_idct_kernel(const K2Params P)
 {
+    typedef Geo<FMT> G;
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned f = blockIdx.y;
-    const int w = P.w, h = P.h, mbw = w >> 4;
+    const int w = P.w, h = P.h, mbw = w / G::UNIT_W;           /* units per picture row */
     const int strip = SINGLE ? 0 : (int)(blockIdx.x % (unsigned)P.nstrips);
     const int my = SINGLE ? (int)blockIdx.x : (int)(blockIdx.x / (unsigned)P.nstrips);
     const int mx0 = strip * P.seg_mb;
     const int mbs = SINGLE ? mbw : min(P.seg_mb, mbw - mx0);
-    const int nb = mbs * 6;
-    const unsigned strip_blk0 = (unsigned)(my * mbw + mx0) * 6u;
+    const int nb = mbs * G::BLK;
+    const unsigned strip_blk0 = (unsigned)(my * mbw + mx0) * (unsigned)G::BLK;
     const unsigned frame_blk0 = f * (unsigned)P.nblk + strip_blk0;   /* F * nblk < 2^32 (checked by the host) */
     const uint32_t *my_ent = P.ent + frame_blk0;
 
-    uint8_t *tile = smem;                                            /* 384 * mbs bytes: Y, U, V */
-    int *s_hard = reinterpret_cast<int *>(tile + 384 * mbs);         /* HARD blocks of the strip, per warp */
+    uint8_t *tile = smem;                                            /* TILE * mbs bytes: Y, U, V */
+    int *s_hard = reinterpret_cast<int *>(tile + G::TILE * mbs);     /* HARD blocks of the strip, per warp */
     static_assert(K2_WARPS == 4, "s_hard holds four counters");
     uint32_t *wq_e = reinterpret_cast<uint32_t *>(s_hard + 8) + warp * K2_WQ;      /* this warp's queue: entries ... */
     uint32_t *wq_p = reinterpret_cast<uint32_t *>(s_hard + 8) + (K2_WARPS + warp) * K2_WQ;   /* ... strip offset | source << 16 */
@@ -426,7 +512,7 @@ rtj_idct_kernel(const K2Params P)
     /* everything that does not depend on anything else is fetched first: the first round's entry
      * and the frame descriptor; the table constants follow the descriptor */
     const int rounds = (nb + IDCT_THREADS - 1) / IDCT_THREADS;
-    PicPos pp_next = pic_pos(tid, mbs);
+    PicPos pp_next = G::pic_pos(tid, mbs);
     uint32_t e_first = tid < nb ? my_ent[pp_next.i] : 0u;
     const rtjgpu_frame_desc fd = P.desc[f];
     const unsigned mytable = fd.table;
@@ -442,10 +528,10 @@ rtj_idct_kernel(const K2Params P)
     for (int r = 0; r < rounds; r++) {
         const int p = r * IDCT_THREADS + tid;
         const PicPos pp = pp_next;
-        const bool chroma = off_is_chroma(pp.off, mbs);
+        const bool chroma = off_is_chroma<FMT>(pp.off, mbs);
         uint32_t e = e_first;
         if (r + 1 < rounds) {                                /* next round's entry: in flight during this round */
-            pp_next = pic_pos(p + IDCT_THREADS, mbs);
+            pp_next = G::pic_pos(p + IDCT_THREADS, mbs);
             e_first = p + IDCT_THREADS < nb ? my_ent[pp_next.i] : 0u;
         }
         int cls = CLS_NONE;
@@ -486,7 +572,7 @@ rtj_idct_kernel(const K2Params P)
         if (cls == CLS_T2) {
             uint32_t px[16];
             t2_pixels(x0, x1, q, packed, px);
-            store_block(tile, pp.off, mbs, px);
+            store_block<FMT>(tile, pp.off, mbs, px);
         }
         const unsigned mM = __ballot_sync(FULL, cls == Q_M7);
         const unsigned mB = __ballot_sync(FULL, cls == Q_CARRY || cls == Q_HARD);
@@ -527,7 +613,7 @@ rtj_idct_kernel(const K2Params P)
             const uint32_t ps = q_p[at];
             const unsigned sf = ps >> 16;
             off = (int)(ps & 0xFFFFu);
-            const bool chroma = off_is_chroma(off, mbs);
+            const bool chroma = off_is_chroma<FMT>(off, mbs);
             const uint8_t *src = (sf == f ? frame_pay : P.stream + P.desc[sf].offset + RTJPEG_B200_HEADER_BYTES)
                                  + (e & RTJ_ENT_OFF_MASK);
             RegBytes<2> by(src);
@@ -537,7 +623,7 @@ rtj_idct_kernel(const K2Params P)
         if (live) {
             uint32_t px[16];
             m7_pixels(x, packed, px);
-            store_block(tile, off, mbs, px);
+            store_block<FMT>(tile, off, mbs, px);
         }
     }
     /* ---- CARRY blocks are copied from the picture before the batch, HARD blocks leave for
@@ -571,17 +657,8 @@ rtj_idct_kernel(const K2Params P)
             if (live && !hard) {
                 uint32_t px[16];
                 if (P.carry) {
-                    const int mb = bi / 6, sub = bi - mb * 6;
-                    const uint8_t *cp;
                     int pitch;
-                    if (sub < 4) {
-                        pitch = w;
-                        cp = P.carry + (size_t)(my * 16 + (sub >> 1) * 8) * w + (mx0 + mb) * 16 + (sub & 1) * 8;
-                    } else {
-                        pitch = w >> 1;
-                        cp = P.carry + (size_t)w * h + (sub == 5 ? (size_t)(w >> 1) * (h >> 1) : 0)
-                             + (size_t)(my * 8) * pitch + (mx0 + mb) * 8;
-                    }
+                    const uint8_t *cp = G::carry_src(P.carry, bi, my, mx0, w, h, pitch);
 #pragma unroll
                     for (int r = 0; r < 8; r++) {
                         const uint2 v = *reinterpret_cast<const uint2 *>(cp + (size_t)r * pitch);
@@ -592,7 +669,7 @@ rtj_idct_kernel(const K2Params P)
 #pragma unroll
                     for (int r = 0; r < 16; r++) px[r] = 0;
                 }
-                store_block(tile, off, mbs, px);
+                store_block<FMT>(tile, off, mbs, px);
             }
         }
     }
@@ -602,33 +679,45 @@ rtj_idct_kernel(const K2Params P)
     if (SINGLE) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
     if (s_hard[0] + s_hard[1] + s_hard[2] + s_hard[3] == nb) return;
-    const size_t fsz = (size_t)w * h * 3 / 2;
+    const size_t fsz = RTJ_FMT_FRAME_BYTES(FMT, w, h);
     const int cw = w >> 1;
-    uint8_t *oy = P.out + (size_t)f * fsz + (size_t)(my * 16) * w + mx0 * 16;
+    const int lw = G::UNIT_W * mbs;                              /* luma bytes per strip row */
+    uint8_t *oy = P.out + (size_t)f * fsz + (size_t)(my * G::LUMA_ROWS) * w + mx0 * G::UNIT_W;
     uint8_t *ou = P.out + (size_t)f * fsz + (size_t)w * h + (size_t)(my * 8) * cw + mx0 * 8;
-    uint8_t *ov = ou + (size_t)cw * (h >> 1);
-    const uint8_t *tileU = tile + 256 * mbs, *tileV = tile + 320 * mbs;
+    uint8_t *ov = ou + (FMT == 0 ? (size_t)cw * (h >> 1) : (size_t)cw * h);
+    const uint8_t *tileU = tile + G::CHROMA_AT * mbs, *tileV = tileU + 64 * mbs;
     if (SINGLE) {
-        /* 16 luma rows and 2 x 8 chroma rows are each one contiguous run in the tight-pitch planes:
-         * three TMA bulk stores issued by one thread */
+        /* the luma rows and the 2 x 8 chroma rows are each one contiguous run in the tight-pitch planes:
+         * TMA bulk stores issued by one thread */
         if (tid == 0) {
-            bulk_store(oy, tile, 256u * (unsigned)mbs);
-            bulk_store(ou, tileU, 64u * (unsigned)mbs);
-            bulk_store(ov, tileV, 64u * (unsigned)mbs);
+            bulk_store(oy, tile, (unsigned)(G::LUMA_ROWS * lw));
+            if (G::PLANES == 3) {
+                bulk_store(ou, tileU, 64u * (unsigned)mbs);
+                bulk_store(ov, tileV, 64u * (unsigned)mbs);
+            }
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         }
     } else {
-        const int segW = 16 * mbs, segC = 8 * mbs;
-        for (int r = warp; r < 16; r += K2_WARPS)
-            for (int c = lane; c < mbs; c += 32)                 /* 16-byte vectors per luma row */
-                *reinterpret_cast<uint4 *>(oy + (size_t)r * w + c * 16) =
-                    *reinterpret_cast<const uint4 *>(tile + r * segW + c * 16);
-        for (int r = warp; r < 16; r += K2_WARPS) {
-            const int pl = r >> 3, rr = r & 7;
-            for (int c = lane; c < mbs; c += 32)                 /* 8-byte vectors per chroma row */
-                *reinterpret_cast<uint2 *>((pl ? ov : ou) + (size_t)rr * cw + c * 8) =
-                    *reinterpret_cast<const uint2 *>((pl ? tileV : tileU) + rr * segC + c * 8);
+        if (G::UNIT_W == 16) {
+            for (int r = warp; r < G::LUMA_ROWS; r += K2_WARPS)
+                for (int c = lane; c < mbs; c += 32)                 /* 16-byte vectors per luma row */
+                    *reinterpret_cast<uint4 *>(oy + (size_t)r * w + c * 16) =
+                        *reinterpret_cast<const uint4 *>(tile + r * lw + c * 16);
+        } else {
+            for (int r = warp; r < G::LUMA_ROWS; r += K2_WARPS)
+                for (int c = lane; c < mbs; c += 32)                 /* 8-byte vectors: a grey strip may be an odd number of blocks */
+                    *reinterpret_cast<uint2 *>(oy + (size_t)r * w + c * 8) =
+                        *reinterpret_cast<const uint2 *>(tile + r * lw + c * 8);
+        }
+        if (G::PLANES == 3) {
+            const int segC = lw >> 1;
+            for (int r = warp; r < 16; r += K2_WARPS) {
+                const int pl = r >> 3, rr = r & 7;
+                for (int c = lane; c < (segC >> 3); c += 32)     /* 8-byte vectors per chroma row */
+                    *reinterpret_cast<uint2 *>((pl ? ov : ou) + (size_t)rr * cw + c * 8) =
+                        *reinterpret_cast<const uint2 *>((pl ? tileV : tileU) + rr * segC + c * 8);
+            }
         }
     }
 }
@@ -637,25 +726,6 @@ rtj_idct_kernel(const K2Params P)
 /* K2b: the general decoder for queued blocks                                  */
 /* ------------------------------------------------------------------------ */
 
-namespace {
-
-/* destination of block i (stream order) of frame f in the tight-pitch planes */
-__device__ __forceinline__ uint8_t *block_dst(uint8_t *out, unsigned f, int i, int w, int h, int &pitch)
-{
-    const int mbw = w >> 4, cw = w >> 1;
-    const size_t fsz = (size_t)w * h * 3 / 2;
-    const int mb = i / 6, sub = i - mb * 6;
-    const int my = mb / mbw, mx = mb - my * mbw;
-    if (sub < 4) {
-        pitch = w;
-        return out + (size_t)f * fsz + (size_t)(my * 16 + (sub >> 1) * 8) * w + mx * 16 + (sub & 1) * 8;
-    }
-    pitch = cw;
-    return out + (size_t)f * fsz + (size_t)w * h + (sub == 5 ? (size_t)cw * (h >> 1) : 0) + (size_t)(my * 8) * cw + mx * 8;
-}
-
-} // namespace
-
 /* One thread per queued block.  The queue holds mid-size blocks (E <= 16, or carried inline but last
  * written under other tables) at its front and long blocks at its back, so that a warp runs one flow
  * graph: the first 16 zig-zag positions touch rows 0..5 and columns 0..4 only and fit 24 bytes held in
@@ -663,11 +733,13 @@ __device__ __forceinline__ uint8_t *block_dst(uint8_t *out, unsigned f, int i, i
 extern "C" __global__ void __launch_bounds__(128)
 rtj_idct_hard_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc *__restrict__ desc,
                      const rtj_dev_table *__restrict__ tables, const uint32_t *__restrict__ ent,
-                     const uint16_t *__restrict__ srcf, int nblk, int w, int h,
+                     const uint16_t *__restrict__ srcf, int nblk, int w, int h, int fmt,
                      uint8_t *__restrict__ out, const uint32_t *__restrict__ hardq, unsigned hardq_cap,
                      const rtj_dev_info *__restrict__ info)
 {
     const unsigned n16 = info->hard_blocks, nfull = info->hard_full;
+    const size_t fsz = RTJ_FMT_FRAME_BYTES(fmt, w, h);
+    const int unit = RTJ_FMT_UNIT_BLOCKS(fmt), unit_luma = RTJ_FMT_UNIT_LUMA(fmt);
     const unsigned stride = gridDim.x * blockDim.x, first = blockIdx.x * blockDim.x + threadIdx.x;
     for (unsigned k = first; k < n16 + nfull; k += stride) {
         const bool full = k >= n16;
@@ -680,7 +752,7 @@ rtj_idct_hard_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc
             sf = srcf[gidx];
             e = ent[(size_t)sf * nblk + i];
         }
-        const int chroma = (i % 6) >= 4;
+        const int chroma = (i % unit) >= unit_luma;
         const rtj_dev_table *t = &tables[desc[sf].table];
         const uint8_t *src = stream + desc[sf].offset + RTJPEG_B200_HEADER_BYTES + (e & RTJ_ENT_OFF_MASK);
         uint32_t px[16];
@@ -701,7 +773,7 @@ rtj_idct_hard_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc
             idct_general<16>(x, px);
         }
         int pitch;
-        uint8_t *dst = block_dst(out, f, i, w, h, pitch);
+        uint8_t *dst = block_dst(out + (size_t)f * fsz, fmt, i, w, h, pitch);
 #pragma unroll
         for (int r = 0; r < 8; r++)
             *reinterpret_cast<uint2 *>(dst + (size_t)r * pitch) = make_uint2(px[2 * r], px[2 * r + 1]);
@@ -717,9 +789,9 @@ inline int idct_seg_mb(int mbw, int *nstrips)
     return (mbw + n - 1) / n;
 }
 
-inline size_t idct_smem_bytes(int seg_mb)
+inline size_t idct_smem_bytes(int seg_mb, int fmt)
 {
-    size_t s = (size_t)seg_mb * 16 * 24;             /* Y 16 rows + U,V 8 rows of half width */
+    size_t s = (size_t)seg_mb * (fmt == 0 ? 384 : fmt == 1 ? 256 : 64);    /* the picture strip */
     s += 32;                                         /* counters */
     s += (size_t)2 * K2_WARPS * K2_WQ * 4;           /* warp queues */
     return (s + 15) & ~(size_t)15;
@@ -727,15 +799,32 @@ inline size_t idct_smem_bytes(int seg_mb)
 
 int g_sm_count = 0;
 
+template <bool SINGLE, int FMT>
+cudaError_t k2_attr()
+{
+    return cudaFuncSetAttribute(rtj_idct_kernel<SINGLE, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)idct_smem_bytes(IDCT_MAX_MB, FMT));
+}
+
+template <int FMT>
+cudaError_t k2_launch(const K2Params &P, dim3 grid, cudaStream_t st)
+{
+    const size_t smem = idct_smem_bytes(P.seg_mb, FMT);
+    if (P.nstrips == 1) rtj_idct_kernel<true, FMT><<<grid, IDCT_THREADS, smem, st>>>(P);
+    else rtj_idct_kernel<false, FMT><<<grid, IDCT_THREADS, smem, st>>>(P);
+    return cudaGetLastError();
+}
+
 } // namespace
 
 extern "C" int rtj_idct_init(void)
 {
-    int nstrips;
-    const size_t worst = idct_smem_bytes(idct_seg_mb(IDCT_MAX_MB, &nstrips));
-    cudaError_t e = cudaFuncSetAttribute(rtj_idct_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)worst);
-    if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(rtj_idct_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)worst);
+    cudaError_t e = k2_attr<true, 0>();
+    if (e == cudaSuccess) e = k2_attr<false, 0>();
+    if (e == cudaSuccess) e = k2_attr<true, 1>();
+    if (e == cudaSuccess) e = k2_attr<false, 1>();
+    if (e == cudaSuccess) e = k2_attr<true, 2>();
+    if (e == cudaSuccess) e = k2_attr<false, 2>();
     if (e != cudaSuccess) return (int)e;
     int dev = 0;
     if ((e = cudaGetDevice(&dev)) != cudaSuccess) return (int)e;
@@ -745,24 +834,22 @@ extern "C" int rtj_idct_init(void)
 
 extern "C" int rtj_launch_idct(const rtj_launch_args *a, void *stream)
 {
-    const int mbw = a->w >> 4, mbh = a->h >> 4;
+    const int fmt = a->fmt;
+    const int ux = RTJ_FMT_UNITS_X(fmt, a->w), uy = RTJ_FMT_UNITS_Y(fmt, a->h);
     cudaStream_t st = (cudaStream_t)stream;
     K2Params P;
     P.stream = a->d_stream; P.desc = a->d_desc; P.tables = a->d_tables; P.ent = a->d_ent; P.srcf = a->d_src;
-    P.nblk = mbw * mbh * 6; P.w = a->w; P.h = a->h;
-    P.seg_mb = idct_seg_mb(mbw, &P.nstrips);
+    P.nblk = RTJ_FMT_NBLK(fmt, a->w, a->h); P.w = a->w; P.h = a->h;
+    P.seg_mb = idct_seg_mb(ux, &P.nstrips);
     P.out = a->d_out; P.carry = a->d_carry; P.hardq = a->d_hardq; P.info = a->d_info;
     P.hardq_cap = (unsigned)((size_t)a->F * (size_t)P.nblk);
-    dim3 grid((unsigned)(P.nstrips * mbh), (unsigned)a->F);
-    if (P.nstrips == 1)
-        rtj_idct_kernel<true><<<grid, IDCT_THREADS, idct_smem_bytes(P.seg_mb), st>>>(P);
-    else
-        rtj_idct_kernel<false><<<grid, IDCT_THREADS, idct_smem_bytes(P.seg_mb), st>>>(P);
-    cudaError_t e = cudaGetLastError();
+    P.fmt = fmt;
+    dim3 grid((unsigned)(P.nstrips * uy), (unsigned)a->F);
+    cudaError_t e = fmt == 0 ? k2_launch<0>(P, grid, st) : fmt == 1 ? k2_launch<1>(P, grid, st) : k2_launch<2>(P, grid, st);
     if (e != cudaSuccess) return (int)e;
     /* the queue's length is only known on the device: a fixed grid strides over it */
     const int sms = g_sm_count > 0 ? g_sm_count : 148;
     rtj_idct_hard_kernel<<<sms * 4, 128, 0, st>>>(
-        a->d_stream, a->d_desc, a->d_tables, a->d_ent, a->d_src, P.nblk, a->w, a->h, a->d_out, a->d_hardq, P.hardq_cap, a->d_info);
+        a->d_stream, a->d_desc, a->d_tables, a->d_ent, a->d_src, P.nblk, a->w, a->h, fmt, a->d_out, a->d_hardq, P.hardq_cap, a->d_info);
     return (int)cudaGetLastError();
 }

@@ -45,7 +45,7 @@ extern "C" __global__ void __launch_bounds__(SCAN_WARPS * 32)
 rtj_scan_warp_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc *__restrict__ desc,
                 const rtj_dev_table *__restrict__ tables, int F, int nblk,
                 uint32_t *__restrict__ ent, uint32_t *__restrict__ frame_skips,
-                rtj_dev_info *__restrict__ info, int raw_only)
+                rtj_dev_info *__restrict__ info, int raw_only, int unit, int unit_luma)
 {
     const int lane = threadIdx.x & 31;
     const int f = blockIdx.x * SCAN_WARPS + (threadIdx.x >> 5);
@@ -99,7 +99,7 @@ rtj_scan_warp_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc
                     done = true;
                     e_out = RTJ_ENT_SKIP;
                 } else {
-                    const int bt8 = k6 < 4 ? lb8 : cb8;
+                    const int bt8 = k6 < unit_luma ? lb8 : cb8;
                     cur_off = pos + s;
                     rawleft = 1 + bt8;               /* DC byte + raw 8-bit coefficients */
                     need = 63 - bt8;
@@ -139,7 +139,7 @@ rtj_scan_warp_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc
             if (done) {
                 if (lane == (blk & 31)) held = e_out;
                 blk++;
-                k6 = k6 == 5 ? 0 : k6 + 1;
+                k6 = k6 == unit - 1 ? 0 : k6 + 1;
                 if ((blk & 31) == 0) out[blk - 32 + lane] = held;
             }
         }
@@ -197,7 +197,7 @@ __device__ __forceinline__ uint32_t swar_x(uint32_t t, uint32_t r) { return t & 
 
 template <bool RAW>
 __device__ __forceinline__ LaneResult lane_scan_frame(const uint8_t *__restrict__ pay, int len, int lb8, int cb8,
-                                                     uint32_t *__restrict__ out, int nblk)
+                                                     uint32_t *__restrict__ out, int nblk, int unit, int unit_luma)
 {
     const uint32_t *base4 = reinterpret_cast<const uint32_t *>(pay);     /* packets start 4-byte aligned */
     int o = 0, blk = 0, skips = 0, k6 = 0;
@@ -206,8 +206,8 @@ __device__ __forceinline__ LaneResult lane_scan_frame(const uint8_t *__restrict_
      * ~40 blocks from now; its value is consumed four steps later, by when even a DRAM miss is back. */
     uint32_t touch0 = 0, touch1 = 0, touch2 = 0, touch3 = 0, sink = 0;
     while (blk < nblk && o < len) {
-        const int bt8 = RAW ? (k6 < 4 ? lb8 : cb8) : 0;
-        if (RAW) k6 = k6 == 5 ? 0 : k6 + 1;
+        const int bt8 = RAW ? (k6 < unit_luma ? lb8 : cb8) : 0;
+        if (RAW) k6 = k6 == unit - 1 ? 0 : k6 + 1;
         sink ^= touch3;
         touch3 = touch2; touch2 = touch1; touch1 = touch0;
         touch0 = __ldg(base4 + ((o + 160) >> 2));
@@ -278,7 +278,7 @@ extern "C" __global__ void __launch_bounds__(32)
 rtj_scan_lane_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc *__restrict__ desc,
                      const rtj_dev_table *__restrict__ tables, int F, int nblk,
                      uint32_t *__restrict__ ent, uint32_t *__restrict__ frame_skips,
-                     rtj_dev_info *__restrict__ info, int raw_only)
+                     rtj_dev_info *__restrict__ info, int raw_only, int unit, int unit_luma)
 {
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= F) return;
@@ -290,8 +290,8 @@ rtj_scan_lane_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc
     if (raw_only && (lb8 | cb8) == 0) return;        /* rtj_scan_chunk_kernel has done this frame */
     uint32_t *out = ent + (size_t)f * nblk;
 
-    const LaneResult res = (lb8 == 0 && cb8 == 0) ? lane_scan_frame<false>(pay, len, 0, 0, out, nblk)
-                                                  : lane_scan_frame<true>(pay, len, lb8, cb8, out, nblk);
+    const LaneResult res = (lb8 == 0 && cb8 == 0) ? lane_scan_frame<false>(pay, len, 0, 0, out, nblk, unit, unit_luma)
+                                                  : lane_scan_frame<true>(pay, len, lb8, cb8, out, nblk, unit, unit_luma);
 
     /* a frame whose stream ends early or mid-block: flag it, give the missing blocks a harmless entry */
     const bool bad = res.blk < nblk || res.consumed > len;
@@ -380,7 +380,7 @@ rtj_resolve_kernel(const uint32_t *__restrict__ ent, const uint16_t *__restrict_
 extern "C" __global__ void __launch_bounds__(64)
 rtj_scan_plan_kernel(const rtjgpu_frame_desc *__restrict__ desc, const rtj_dev_table *__restrict__ tables, int F, int nblk,
                      uint32_t *__restrict__ ent, uint32_t *__restrict__ frame_skips, rtj_dev_info *__restrict__ info,
-                     const rtj_seg_plan sp)
+                     const rtj_seg_plan sp, int unit_blocks)
 {
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= F) return;
@@ -388,7 +388,7 @@ rtj_scan_plan_kernel(const rtjgpu_frame_desc *__restrict__ desc, const rtj_dev_t
     const int len = d.length > RTJPEG_B200_HEADER_BYTES ? (int)d.length - RTJPEG_B200_HEADER_BYTES : 0;
     /* with a raw prefix the summaries count macroblocks (rtj_scan_mb.cu), without it blocks */
     const bool raw = (tables[d.table].bt8[0] | tables[d.table].bt8[1]) != 0;
-    const int unit = raw ? 6 : 1;
+    const int unit = raw ? unit_blocks : 1;
     const int segbytes = raw ? RTJ_SEG_BYTES_MB : RTJ_SEG_BYTES;
     int e = 0, nb = 0, seg = 0;
     for (; seg < sp.maxseg && (long long)seg * segbytes < len && nb < nblk; seg++) {
@@ -422,7 +422,7 @@ extern "C" int rtj_kernels_init(void)
 
 extern "C" int rtj_launch_scan(const rtj_launch_args *a, void *stream)
 {
-    const int nblk = (a->w >> 4) * (a->h >> 4) * 6;
+    const int nblk = RTJ_FMT_NBLK(a->fmt, a->w, a->h);
     cudaStream_t st = (cudaStream_t)stream;
     /* AUTO: the chunk-parallel kernels -- rtj_scan_chunk_kernel takes every frame without a raw prefix,
      * rtj_scan_mb_kernel the others; each returns at once on the other's frames. */
@@ -433,7 +433,8 @@ extern "C" int rtj_launch_scan(const rtj_launch_args *a, void *stream)
             if (!e) e = rtj_launch_scan_mb(a, 1, stream);
             if (e) return -e;
             rtj_scan_plan_kernel<<<(a->F + 63) / 64, 64, 0, st>>>(a->d_desc, a->d_tables, a->F, nblk, a->d_ent,
-                                                                  a->d_frame_skips, a->d_info, a->seg);
+                                                                  a->d_frame_skips, a->d_info, a->seg,
+                                                                  RTJ_FMT_UNIT_BLOCKS(a->fmt));
             if ((e = (int)cudaGetLastError())) return -e;
             e = rtj_launch_scan_chunk(a, 2, stream);
             if (!e) e = rtj_launch_scan_mb(a, 2, stream);
@@ -448,11 +449,13 @@ extern "C" int rtj_launch_scan(const rtj_launch_args *a, void *stream)
      * issue slots, latency hidden only by very large batches) or one warp per frame. */
     if (a->scan_mode == RTJGPU_SCAN_LANE) {
         rtj_scan_lane_kernel<<<(a->F + 31) / 32, 32, 0, st>>>(
-            a->d_stream, a->d_desc, a->d_tables, a->F, nblk, a->d_ent, a->d_frame_skips, a->d_info, 0);
+            a->d_stream, a->d_desc, a->d_tables, a->F, nblk, a->d_ent, a->d_frame_skips, a->d_info, 0,
+            RTJ_FMT_UNIT_BLOCKS(a->fmt), RTJ_FMT_UNIT_LUMA(a->fmt));
     } else {
         const int grid = (a->F + SCAN_WARPS - 1) / SCAN_WARPS;
         rtj_scan_warp_kernel<<<grid, SCAN_WARPS * 32, 0, st>>>(
-            a->d_stream, a->d_desc, a->d_tables, a->F, nblk, a->d_ent, a->d_frame_skips, a->d_info, 0);
+            a->d_stream, a->d_desc, a->d_tables, a->F, nblk, a->d_ent, a->d_frame_skips, a->d_info, 0,
+            RTJ_FMT_UNIT_BLOCKS(a->fmt), RTJ_FMT_UNIT_LUMA(a->fmt));
     }
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 1 : -(int)e;
@@ -460,7 +463,7 @@ extern "C" int rtj_launch_scan(const rtj_launch_args *a, void *stream)
 
 extern "C" int rtj_launch_resolve(const rtj_launch_args *a, void *stream)
 {
-    const int nblk = (a->w >> 4) * (a->h >> 4) * 6;
+    const int nblk = RTJ_FMT_NBLK(a->fmt, a->w, a->h);
     /* a batch without skip markers only pays for the launches: keep the grid modest and let a CTA
      * stride over the chunks of frames */
     const int nchunks = (a->F + RESOLVE_T - 1) / RESOLVE_T;

@@ -369,7 +369,7 @@ extern "C" int rtj_scan_chunk_init(void)
 extern "C" int rtj_launch_scan_chunk(const rtj_launch_args *a, int phase, void *stream)
 {
     static_assert(CS_S == RTJ_SEG_BYTES, "segment size is shared with the frame-level chain");
-    const int nblk = (a->w >> 4) * (a->h >> 4) * 6;
+    const int nblk = RTJ_FMT_NBLK(a->fmt, a->w, a->h);
     cudaStream_t st = (cudaStream_t)stream;
     const dim3 grid = phase == 0 ? dim3((unsigned)a->F) : dim3((unsigned)a->seg.maxseg, (unsigned)a->F);
     if (phase == 0)

@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(MB_THREADS, 7)
 rtj_scan_mb_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc *__restrict__ desc,
                    const rtj_dev_table *__restrict__ tables, int F, int nblk,
                    uint32_t *__restrict__ ent, uint32_t *__restrict__ frame_skips,
-                   rtj_dev_info *__restrict__ info, const rtj_seg_plan sp)
+                   rtj_dev_info *__restrict__ info, const rtj_seg_plan sp, int unit, int unit_luma)
 {
     extern __shared__ __align__(16) uint8_t mb_smem[];
     MbShared &sh = *reinterpret_cast<MbShared *>(mb_smem);
@@ -186,8 +186,8 @@ rtj_scan_mb_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc *
         /* ---- compose: length of the macroblock that would start at every position ---- */
         for (int q = tid; q < npos; q += MB_THREADS) {
             int n = q;
-            n += dLb[n]; n += dLb[n]; n += dLb[n]; n += dLb[n];
-            n += dCb[n]; n += dCb[n];
+            for (int k = 0; k < unit_luma; k++) n += dLb[n];
+            for (int k = unit_luma; k < unit; k++) n += dCb[n];
             sh.dmb[q + ((q / MB_C) << 1)] = (uint16_t)(n - q);
         }
         __syncthreads();
@@ -231,7 +231,7 @@ rtj_scan_mb_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc *
                 sh.base[j] = (uint32_t)nb;
                 const uint32_t v = rings[j * MB_RING + e];
                 e = (int)(v & 511u);
-                nb += 6 * (int)(v >> 9);
+                nb += unit * (int)(v >> 9);
             }
             sh.base[nch] = (uint32_t)nb;
             sh.entry = e;
@@ -253,12 +253,12 @@ rtj_scan_mb_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc *
             if (tid < nch) {
                 /* a macroblock belongs to the chunk it starts in; its later blocks may lie behind the chunk */
                 while ((k6 != 0 || q < min(qend, lim)) && i < r1) {
-                    const int bt8 = k6 < 4 ? lb8 : cb8;
+                    const int bt8 = k6 < unit_luma ? lb8 : cb8;
                     uint32_t e;
                     if (q >= lim) {
                         e = missing;                                        /* the payload ended inside this macroblock */
                     } else {
-                        const int dl = (k6 < 4 ? dLb : dCb)[q];
+                        const int dl = (k6 < unit_luma ? dLb : dCb)[q];
                         const uint32_t head = lds_u32_unaligned(sh.pay, q + mis);
                         const uint32_t last = payb[q + dl - 1];
                         const bool isff = (head & 0xFFu) == 0xFFu;
@@ -275,7 +275,7 @@ rtj_scan_mb_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc *
                     }
                     sh.ring[i - r0] = e;
                     i++;
-                    k6 = k6 == 5 ? 0 : k6 + 1;
+                    k6 = k6 == unit - 1 ? 0 : k6 + 1;
                 }
             }
             __syncthreads();
@@ -344,17 +344,18 @@ extern "C" int rtj_scan_mb_init(void)
 extern "C" int rtj_launch_scan_mb(const rtj_launch_args *a, int phase, void *stream)
 {
     static_assert(MB_S == RTJ_SEG_BYTES_MB && MB_DLA <= RTJ_SEG_NE, "segment size and entry range are shared with the frame-level chain");
-    const int nblk = (a->w >> 4) * (a->h >> 4) * 6;
+    const int nblk = RTJ_FMT_NBLK(a->fmt, a->w, a->h);
+    const int unit = RTJ_FMT_UNIT_BLOCKS(a->fmt), unit_luma = RTJ_FMT_UNIT_LUMA(a->fmt);
     cudaStream_t st = (cudaStream_t)stream;
     const dim3 grid = phase == 0 ? dim3((unsigned)a->F) : dim3((unsigned)a->seg.maxseg, (unsigned)a->F);
     if (phase == 0)
         rtj_scan_mb_kernel<0><<<grid, MB_THREADS, sizeof(MbShared), st>>>(
-            a->d_stream, a->d_desc, a->d_tables, a->F, nblk, a->d_ent, a->d_frame_skips, a->d_info, a->seg);
+            a->d_stream, a->d_desc, a->d_tables, a->F, nblk, a->d_ent, a->d_frame_skips, a->d_info, a->seg, unit, unit_luma);
     else if (phase == 1)
         rtj_scan_mb_kernel<1><<<grid, MB_THREADS, sizeof(MbShared), st>>>(
-            a->d_stream, a->d_desc, a->d_tables, a->F, nblk, a->d_ent, a->d_frame_skips, a->d_info, a->seg);
+            a->d_stream, a->d_desc, a->d_tables, a->F, nblk, a->d_ent, a->d_frame_skips, a->d_info, a->seg, unit, unit_luma);
     else
         rtj_scan_mb_kernel<2><<<grid, MB_THREADS, sizeof(MbShared), st>>>(
-            a->d_stream, a->d_desc, a->d_tables, a->F, nblk, a->d_ent, a->d_frame_skips, a->d_info, a->seg);
+            a->d_stream, a->d_desc, a->d_tables, a->F, nblk, a->d_ent, a->d_frame_skips, a->d_info, a->seg, unit, unit_luma);
     return (int)cudaGetLastError();
 }

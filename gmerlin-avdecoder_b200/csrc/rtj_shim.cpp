@@ -173,7 +173,8 @@ int RTjpeg_b200_decompress_n(RTjpeg_t *rtj, const uint8_t *sp, size_t len, uint8
 {
     Instance *in = static_cast<Instance *>(rtj);
     if (!in || !sp || !planes) return RTJGPU_E_ARG;
-    if (in->format != RTJ_YUV420) return fail(in, RTJGPU_E_FORMAT);
+    const int fmt = in->format;
+    if (fmt < RTJ_YUV420 || fmt > RTJ_RGB8) return fail(in, RTJGPU_E_FORMAT);
     if (len < RTJPEG_B200_HEADER_BYTES) return fail(in, RTJGPU_E_HEADER);
 
     rtjgpu_state st = in->st;
@@ -182,8 +183,8 @@ int RTjpeg_b200_decompress_n(RTjpeg_t *rtj, const uint8_t *sp, size_t len, uint8
     int rc = rtjgpu_plan(sp, offs, 1, &st, &desc);     /* sp may be unaligned: offset 0 is what is planned */
     if (rc) return fail(in, rc);
     const int w = st.width, h = st.height;
-    const size_t fsz = (size_t)w * h * 3 / 2;
-    const int nblk = (w >> 4) * (h >> 4) * 6;
+    const size_t fsz = RTJ_FMT_FRAME_BYTES(fmt, w, h);
+    const int nblk = RTJ_FMT_NBLK(fmt, w, h);
     const size_t plen = desc.length;
 
     if ((rc = ensure(in, plen + RTJGPU_STREAM_SLACK_BYTES, fsz))) return fail(in, rc);
@@ -194,6 +195,7 @@ int RTjpeg_b200_decompress_n(RTjpeg_t *rtj, const uint8_t *sp, size_t len, uint8
     if (cudaMemcpyAsync(in->d_pkt, in->h_pkt, plen + RTJGPU_STREAM_SLACK_BYTES, cudaMemcpyHostToDevice, s) != cudaSuccess
         || cudaMemcpyAsync(in->d_desc, in->h_desc, sizeof(desc), cudaMemcpyHostToDevice, s) != cudaSuccess)
         return fail(in, RTJGPU_E_CUDA);
+    rtjgpu_set_format(in->ctx, fmt);
     if ((rc = rtjgpu_decode_device(in->ctx, in->d_pkt, in->d_desc, 1, w, h, in->d_frame, nullptr, s)))
         return fail(in, rc);
     if (cudaMemcpyAsync(in->h_frame, in->d_frame, fsz, cudaMemcpyDeviceToHost, s) != cudaSuccess
@@ -204,26 +206,35 @@ int RTjpeg_b200_decompress_n(RTjpeg_t *rtj, const uint8_t *sp, size_t len, uint8
     if ((rc = rtjgpu_get_batch_info(in->ctx, &bi))) return fail(in, rc);
     in->st = st;        /* the reference reconfigures before it decodes, so state advances even on a bad stream */
 
-    const size_t ysz = (size_t)w * h, csz = ysz / 4;
+    /* plane p of the tight frame: Y, then U and V (quarter size in YUV420, half size in YUV422, none in grey) */
+    const size_t ysz = (size_t)w * h, csz = fmt == RTJ_YUV420 ? ysz / 4 : fmt == RTJ_YUV422 ? ysz / 2 : 0;
+    const int nplanes = fmt == RTJ_RGB8 ? 1 : 3;
     if (bi.skipped_blocks == 0) {
         memcpy(planes[0], in->h_frame, ysz);
-        memcpy(planes[1], in->h_frame + ysz, csz);
-        memcpy(planes[2], in->h_frame + ysz + csz, csz);
+        if (nplanes == 3) {
+            memcpy(planes[1], in->h_frame + ysz, csz);
+            memcpy(planes[2], in->h_frame + ysz + csz, csz);
+        }
     } else {
         /* copy back only what this frame coded; skipped blocks keep the caller's pixels */
         in->entries.resize((size_t)nblk);
         if ((rc = rtjgpu_get_entries(in->ctx, in->entries.data(), (size_t)nblk))) return fail(in, rc);
-        const int mbw = w >> 4, cw = w >> 1;
+        const int cw = w >> 1;
+        const int unit = RTJ_FMT_UNIT_BLOCKS(fmt), unit_luma = RTJ_FMT_UNIT_LUMA(fmt), ux = RTJ_FMT_UNITS_X(fmt, w);
         for (int b = 0; b < nblk; b++) {
             if (RTJ_ENT_IS_SKIP(in->entries[(size_t)b])) continue;
-            const int mb = b / 6, sub = b - mb * 6;
-            const int my = mb / mbw, mx = mb - my * mbw;
-            if (sub < 4) {
-                const size_t o = (size_t)(my * 16 + (sub >> 1) * 8) * w + mx * 16 + (sub & 1) * 8;
+            const int un = b / unit, sub = b - un * unit;
+            const int uy = un / ux, uxx = un - uy * ux;
+            if (sub < unit_luma) {
+                /* YUV420: four luma blocks of a 16x16 macroblock; YUV422: two of a 16x8 unit; grey: the 8x8 block */
+                const int rows = fmt == RTJ_YUV420 ? 16 : 8, uw = fmt == RTJ_RGB8 ? 8 : 16;
+                const size_t o = (size_t)(uy * rows + (fmt == RTJ_YUV420 ? (sub >> 1) * 8 : 0)) * w
+                               + (size_t)uxx * uw + (size_t)(fmt == RTJ_YUV420 ? (sub & 1) : sub) * 8;
                 copy_block(planes[0] + o, in->h_frame + o, w);
             } else {
-                const size_t o = (size_t)(my * 8) * cw + mx * 8;
-                copy_block(planes[sub - 3] + o, in->h_frame + ysz + (sub == 5 ? csz : 0) + o, cw);
+                const int pl = sub - unit_luma;                  /* 0 = U, 1 = V */
+                const size_t o = (size_t)(uy * 8) * cw + (size_t)uxx * 8;
+                copy_block(planes[1 + pl] + o, in->h_frame + ysz + (pl ? csz : 0) + o, cw);
             }
         }
     }

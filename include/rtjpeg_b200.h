@@ -11,9 +11,10 @@
  *   Level 2  a batch interface (many packets -> many frames in one call), which
  *            is what keeps a B200 busy; Level 1 is its one-frame special case.
  *
- * Scope: the YUV420 decode path only (format 0).  The encoder half of
- * lib/RTjpeg.c, the YUV422 / 8-bit formats and the colour converters are not
- * part of this library.
+ * Scope: the decode half of lib/RTjpeg.c -- RTjpeg_decompress in its three
+ * formats (YUV420, the one gmerlin-avdecoder's plugin uses, YUV422 and 8-bit
+ * grey).  The encoder half and the colour converters are not part of this
+ * library.
  */
 #ifndef RTJPEG_B200_H
 #define RTJPEG_B200_H
@@ -32,7 +33,7 @@ extern "C" {
 /* Opaque, as in include/RTjpeg.h:96 (`typedef void RTjpeg_t;`). */
 typedef void RTjpeg_t;
 
-/* Picture formats, include/RTjpeg.h:111-113.  Only RTJ_YUV420 decodes here. */
+/* Picture formats, include/RTjpeg.h:111-113. */
 #define RTJ_YUV420 0
 #define RTJ_YUV422 1
 #define RTJ_RGB8   2
@@ -54,7 +55,7 @@ void RTjpeg_close(RTjpeg_t *rtj);
 int RTjpeg_set_quality(RTjpeg_t *rtj, int *quality);
 
 /* include/RTjpeg.h:118, lib/RTjpeg.c:2421.  Stores the format, returns 0.
- * RTjpeg_decompress refuses (error RTJGPU_E_FORMAT) anything but RTJ_YUV420. */
+ * RTjpeg_decompress refuses (error RTJGPU_E_FORMAT) a value outside 0..2. */
 int RTjpeg_set_format(RTjpeg_t *rtj, int *format);
 
 /* include/RTjpeg.h:119, lib/RTjpeg.c:2427.  Returns -1 when a dimension is
@@ -76,7 +77,8 @@ void RTjpeg_get_tables(RTjpeg_t *rtj, uint32_t *tables);
 void RTjpeg_set_tables(RTjpeg_t *rtj, uint32_t *tables);
 
 /* include/RTjpeg.h:126, lib/RTjpeg.c:3565.  One packet (12-byte header +
- * payload) into planes[0..2] = Y, U, V, tight pitch (width, width/2, width/2).
+ * payload) into planes[0..2] = Y, U, V, tight pitch (width, width/2, width/2;
+ * YUV422: U and V have the full height; grey: planes[0] only).
  * Blocks the stream marks as skipped are left untouched in the caller's
  * planes, exactly like the reference.  Like the reference it returns nothing
  * and trusts the header's framesize; errors are reported out of band through
@@ -171,6 +173,12 @@ int  rtjgpu_last_cuda_error(const rtjgpu_ctx *ctx);
 #define RTJGPU_SCAN_CHUNK   3
 #define RTJGPU_SCAN_SEGMENT 4
 int  rtjgpu_set_scan_mode(rtjgpu_ctx *ctx, int mode);
+
+/* Picture format of the batches this context decodes (RTJ_YUV420, the default, RTJ_YUV422 or RTJ_RGB8 =
+ * 8-bit grey): what RTjpeg_set_format is to an RTjpeg_t (lib/RTjpeg.c:2421, dispatch :3580-3585).  Frames
+ * come out as tight planes: YUV420 w*h*3/2 bytes (Y, U, V), YUV422 w*h*2 bytes (Y, then U and V of
+ * (w/2) x h), grey w*h bytes.  Width and height must be multiples of 16 in every format here. */
+int  rtjgpu_set_format(rtjgpu_ctx *ctx, int format);
 
 /* Raw (pre-AAN) tables for RTJGPU_TABLE_CUSTOM, the set_tables path. */
 int  rtjgpu_set_custom_tables(rtjgpu_ctx *ctx, const uint32_t raw[128]);

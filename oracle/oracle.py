@@ -76,6 +76,8 @@ def oracle_lib():
         L.rtjo_decoder_reset.argtypes = [C.POINTER(_Decoder)]
         L.rtjo_decode_packet.argtypes = [C.POINTER(_Decoder), _u8p, C.c_size_t, _u8p, _u8p, _u8p]
         L.rtjo_decode_packet.restype = C.c_long
+        L.rtjo_decode_packet_fmt.argtypes = [C.POINTER(_Decoder), C.c_int, _u8p, C.c_size_t, _u8p, _u8p, _u8p]
+        L.rtjo_decode_packet_fmt.restype = C.c_long
         L.rtjo_walk_payload.argtypes = [_u8p, C.c_size_t, C.c_int, C.c_int, C.c_int, _u32p, _u8p]
         L.rtjo_walk_payload.restype = C.c_long
         L.rtjo_unpack_block.argtypes = [_u8p, C.c_int, _i32p, C.POINTER(C.c_int16)]
@@ -203,6 +205,9 @@ def ref_lib():
         L.refdrv_encode_clip.argtypes = [C.POINTER(Clip), C.c_int, C.c_int, _u8p, C.c_size_t, _u64p, C.c_int]
         L.refdrv_encode_clip.restype = C.c_size_t
         L.refdrv_decode_seq.argtypes = [_u8p, _u64p, C.c_int, C.c_int, C.c_int, _u8p, _u8p, _u8p]
+        L.refdrv_encode_frames_fmt.argtypes = [C.POINTER(Clip), C.c_int, _u8p, C.c_int, _u8p, C.c_size_t, _u64p, C.c_int]
+        L.refdrv_encode_frames_fmt.restype = C.c_size_t
+        L.refdrv_decode_seq_fmt.argtypes = [_u8p, _u64p, C.c_int, C.c_int, C.c_int, C.c_int, _u8p, _u8p, _u8p]
         L.refdrv_decode_threaded.argtypes = [_u8p, _u64p, C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int,
                                              C.c_int, C.c_int, _u8p]
         L.refdrv_decode_threaded.restype = C.c_double
@@ -364,3 +369,91 @@ def pack_packets(pkts, align: int = 16):
     for i, p in enumerate(pkts):
         buf[int(offs[i]):int(offs[i]) + len(p)] = p
     return buf, offs
+
+
+# ---- the other two formats of RTjpeg_decompress: 1 = YUV422, 2 = 8-bit grey ------------------
+
+def frame_bytes(fmt: int, w: int, h: int) -> int:
+    return w * h * 3 // 2 if fmt == 0 else w * h * 2 if fmt == 1 else w * h
+
+
+def frames_in_format(frames420: np.ndarray, w: int, h: int, fmt: int) -> np.ndarray:
+    """Synthetic YUV420 frames [F, w*h*3/2] -> tight planes of format fmt (422: chroma rows doubled
+    and roughened a little so that the two rows of a pair differ; grey: luma only)."""
+    frames420 = _np_u8(frames420)
+    F = frames420.shape[0]
+    ysz = w * h
+    if fmt == 0:
+        return frames420.copy()
+    if fmt == 2:
+        return np.ascontiguousarray(frames420[:, :ysz])
+    out = np.empty((F, 2 * ysz), dtype=np.uint8)
+    out[:, :ysz] = frames420[:, :ysz]
+    for k, lo in ((0, ysz), (1, ysz + ysz // 4)):
+        c = frames420[:, lo:lo + ysz // 4].reshape(F, h // 2, w // 2).astype(np.int16)
+        up = np.repeat(c, 2, axis=1)
+        up[:, 1::2, :] += ((np.arange(w // 2) % 5) - 2)[None, None, :]
+        out[:, ysz + k * (ysz // 2):ysz + (k + 1) * (ysz // 2)] = np.clip(up, 16, 235).astype(np.uint8).reshape(F, -1)
+    return out
+
+
+def encode_frames_fmt(clip: Clip, fmt: int, frames: np.ndarray, align: int = 16):
+    """Reference RTjpeg_compress in format fmt over caller-supplied tight planes [F, frame_bytes]."""
+    L = ref_lib()
+    frames = _np_u8(frames)
+    F = frames.shape[0]
+    cap = (12 + (clip.w // 8) * (clip.h // 8) * 2 * 64 + 64 + align) * max(F, 1) + 64
+    buf = np.zeros(cap, dtype=np.uint8)
+    offs = np.empty(F + 1, dtype=np.uint64)
+    used = L.refdrv_encode_frames_fmt(C.byref(clip), fmt, _ptr(frames), F, _ptr(buf), cap, _ptr(offs, _u64p), align)
+    if not used and F:
+        raise RuntimeError("encode buffer too small")
+    return buf[:int(used)].copy(), offs
+
+
+def ref_decode_seq_fmt(stream, offsets, w, h, fmt, init=None):
+    stream = _np_u8(stream)
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    F = len(offsets) - 1
+    fsz = frame_bytes(fmt, w, h)
+    frames = np.empty((F, fsz), dtype=np.uint8)
+    last = np.empty(fsz, dtype=np.uint8)
+    initp = None if init is None else _ptr(_np_u8(init))
+    padded = np.concatenate([stream, np.full(256, 0x7F, dtype=np.uint8)])
+    ref_lib().refdrv_decode_seq_fmt(_ptr(padded), _ptr(offsets, _u64p), F, w, h, fmt, initp, _ptr(frames), _ptr(last))
+    return frames
+
+
+def decode_stream_fmt(stream, offsets, w: int, h: int, fmt: int, init: np.ndarray | None = None) -> np.ndarray:
+    """Restatement decode of a whole stream in format fmt; returns [F, frame_bytes]."""
+    stream = _np_u8(stream)
+    L = oracle_lib()
+    F = len(offsets) - 1
+    fsz = frame_bytes(fmt, w, h)
+    ysz = w * h
+    csz = ysz // 4 if fmt == 0 else ysz // 2 if fmt == 1 else 0
+    planes = np.zeros(fsz, dtype=np.uint8) if init is None else np.array(init, dtype=np.uint8).copy()
+    d = _Decoder()
+    L.rtjo_decoder_reset(C.byref(d))
+    out = np.empty((F, fsz), dtype=np.uint8)
+    for f in range(F):
+        pkt = np.ascontiguousarray(stream[int(offsets[f]):int(offsets[f + 1])])
+        base = planes.ctypes.data
+        y = C.cast(base, _u8p)
+        u = C.cast(base + ysz, _u8p)
+        v = C.cast(base + ysz + csz, _u8p)
+        n = L.rtjo_decode_packet_fmt(C.byref(d), fmt, _ptr(pkt), pkt.size, y, u, v)
+        if n < 0:
+            raise ValueError("truncated packet")
+        out[f] = planes
+    return out
+
+
+def encode_clip_fmt(w: int, h: int, Q: int, F: int, fmt: int, key_rate: int = -1, lm: int = 0, cm: int = 0, **kw):
+    """A synthetic clip in format fmt: the seeded YUV420 source of ref_driver.c (taken through one
+    high-quality reference round trip), reshaped by frames_in_format and coded by the reference's
+    own RTjpeg_compress in that format.  Returns (stream, offsets)."""
+    src = make_clip(w, h, 255, **kw)
+    s, o = encode_clip(src, F, threads=1)
+    frames = frames_in_format(ref_decode_seq(s, o, w, h), w, h, fmt)
+    return encode_frames_fmt(make_clip(w, h, Q, key_rate, lm, cm), fmt, frames)

@@ -340,3 +340,73 @@ void refdrv_decode_with_tables(const uint32_t raw[128], const uint8_t *pkt, int 
     ref_RTjpeg_decompress(d, (uint8_t *)pkt, pl);
     ref_RTjpeg_close(d);
 }
+
+/* ------------------------------------------------------------------ */
+/* the other two formats (YUV422, 8-bit grey)                          */
+/* ------------------------------------------------------------------ */
+
+static size_t fmt_frame_bytes(int fmt, int w, int h)
+{
+    return fmt == 0 ? (size_t)w * h * 3 / 2 : fmt == 1 ? (size_t)w * h * 2 : (size_t)w * h;
+}
+
+static void fmt_planes(int fmt, int w, int h, uint8_t *base, uint8_t *pl[3])
+{
+    size_t ysz = (size_t)w * h, csz = fmt == 0 ? ysz / 4 : fmt == 1 ? ysz / 2 : 0;
+    pl[0] = base;
+    pl[1] = base + ysz;
+    pl[2] = base + ysz + csz;
+}
+
+/* Encode caller-supplied frames (tight planes of format fmt) with one reference encoder. */
+size_t refdrv_encode_frames_fmt(const refdrv_clip *c, int fmt, const uint8_t *frames, int F,
+                                uint8_t *out, size_t cap, uint64_t *offsets, int align)
+{
+    RTjpeg_t *e = ref_RTjpeg_init();
+    int f0 = fmt, w = c->w, h = c->h, q = c->Q;
+    ref_RTjpeg_set_format(e, &f0);
+    ref_RTjpeg_set_size(e, &w, &h);
+    ref_RTjpeg_set_quality(e, &q);
+    if (c->key_rate >= 0) {
+        int k = c->key_rate, lm = c->lm, cm = c->cm;
+        ref_RTjpeg_set_intra(e, &k, &lm, &cm);
+    }
+    size_t fsz = fmt_frame_bytes(fmt, c->w, c->h), at = 0;
+    size_t bound = 12 + (size_t)(c->w / 8) * (c->h / 8) * 2 * 64 + 64;
+    uint8_t *tmp = (uint8_t *)malloc(bound);
+    for (int f = 0; f < F; f++) {
+        uint8_t *pl[3];
+        fmt_planes(fmt, c->w, c->h, (uint8_t *)frames + fsz * f, pl);
+        int n = ref_RTjpeg_compress(e, tmp, pl);
+        at = (at + (size_t)align - 1) / (size_t)align * (size_t)align;
+        if (at + (size_t)n > cap) { free(tmp); ref_RTjpeg_close(e); return 0; }
+        memcpy(out + at, tmp, (size_t)n);
+        offsets[f] = at;
+        at += (size_t)n;
+    }
+    offsets[F] = at;
+    free(tmp);
+    ref_RTjpeg_close(e);
+    return at;
+}
+
+/* Sequential reference decode in format fmt into one persistent plane set. */
+void refdrv_decode_seq_fmt(const uint8_t *stream, const uint64_t *offsets, int F, int w, int h, int fmt,
+                           const uint8_t *init, uint8_t *frames_out, uint8_t *last_out)
+{
+    size_t fsz = fmt_frame_bytes(fmt, w, h);
+    uint8_t *pl_mem = (uint8_t *)malloc(fsz);
+    if (init) memcpy(pl_mem, init, fsz); else memset(pl_mem, 0, fsz);
+    uint8_t *pl[3];
+    fmt_planes(fmt, w, h, pl_mem, pl);
+    RTjpeg_t *d = ref_RTjpeg_init();
+    int f0 = fmt;
+    ref_RTjpeg_set_format(d, &f0);
+    for (int f = 0; f < F; f++) {
+        ref_RTjpeg_decompress(d, (uint8_t *)stream + offsets[f], pl);
+        if (frames_out) memcpy(frames_out + fsz * f, pl_mem, fsz);
+    }
+    if (last_out) memcpy(last_out, pl_mem, fsz);
+    ref_RTjpeg_close(d);
+    free(pl_mem);
+}

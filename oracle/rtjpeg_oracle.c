@@ -293,3 +293,67 @@ long rtjo_decode_packet(rtjo_decoder *d, const uint8_t *pkt, size_t pkt_len,
     }
     return (long)at;
 }
+
+/* Plane bytes of one picture in the three formats RTjpeg_decompress dispatches on
+ * (RTjpeg.c:3580-3585): 0 = YUV420, 1 = YUV422, 2 = 8-bit grey ("RGB8"). */
+size_t rtjo_frame_bytes(int fmt, int w, int h)
+{
+    return fmt == 0 ? (size_t)w * h * 3 / 2 : fmt == 1 ? (size_t)w * h * 2 : (size_t)w * h;
+}
+
+long rtjo_decode_packet_fmt(rtjo_decoder *d, int fmt, const uint8_t *pkt, size_t pkt_len,
+                            uint8_t *y, uint8_t *u, uint8_t *v)
+{
+    if (fmt == 0) return rtjo_decode_packet(d, pkt, pkt_len, y, u, v);
+    if (pkt_len < 12) return -1;
+    int w = pkt[6] | (pkt[7] << 8);
+    int h = pkt[8] | (pkt[9] << 8);
+    int q = pkt[10];
+    if (w != d->width || h != d->height) { d->width = w; d->height = h; }
+    if (q != d->Q) {
+        int qc = q < 1 ? 1 : q;
+        d->Q = qc;
+        rtjo_tables_from_quality(qc, &d->t);
+    }
+    const uint8_t *s = pkt + 12;
+    size_t left = pkt_len - 12, at = 0;
+    int cw = w >> 1;
+    int16_t blk[64];
+    if (fmt == 1) {
+        /* RTjpeg_decompressYUV422 :2639-2686: rows of 8 lines, 16 luma columns per step, four
+         * blocks Y0 Y1 U V; chroma is half width, FULL height */
+        for (int by = 0; by < (h >> 3); by++) {
+            for (int mx = 0; mx < (w >> 4); mx++) {
+                for (int k = 0; k < 4; k++) {
+                    int bt8 = k < 2 ? d->t.lb8 : d->t.cb8;
+                    const int32_t *iq = k < 2 ? d->t.liqt : d->t.ciqt;
+                    int e;
+                    int n = block_extent(s + at, left - at, bt8, &e);
+                    if (n < 0) return -1;
+                    if (e) {
+                        uint8_t *dst = k < 2 ? y + (size_t)(by * 8) * w + mx * 16 + k * 8
+                                             : (k == 2 ? u : v) + (size_t)(by * 8) * cw + mx * 8;
+                        rtjo_unpack_block(s + at, bt8, iq, blk);
+                        rtjo_idct_block(blk, dst, k < 2 ? w : cw);
+                    }
+                    at += (size_t)n;
+                }
+            }
+        }
+    } else {
+        /* RTjpeg_decompress8 :2751-2772: luma blocks only, raster order */
+        for (int by = 0; by < (h >> 3); by++) {
+            for (int bx = 0; bx < (w >> 3); bx++) {
+                int e;
+                int n = block_extent(s + at, left - at, d->t.lb8, &e);
+                if (n < 0) return -1;
+                if (e) {
+                    rtjo_unpack_block(s + at, d->t.lb8, d->t.liqt, blk);
+                    rtjo_idct_block(blk, y + (size_t)(by * 8) * w + bx * 8, w);
+                }
+                at += (size_t)n;
+            }
+        }
+    }
+    return (long)at;
+}

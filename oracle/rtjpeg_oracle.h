@@ -65,6 +65,13 @@ long rtjo_walk_payload(const uint8_t *payload, size_t len, int nblocks_mb6,
 int  rtjo_unpack_block(const uint8_t *s, int bt8, const int32_t *iqt, int16_t blk[64]);
 void rtjo_idct_block(const int16_t blk[64], uint8_t *dst, int pitch);
 
+/* The other two formats of RTjpeg_decompress (RTjpeg.c:3580-3585): fmt 1 = YUV422
+ * (RTjpeg_decompressYUV422 :2639-2686; u, v are (w/2) x h), fmt 2 = 8-bit grey
+ * (RTjpeg_decompress8 :2751-2772; u, v unused).  fmt 0 forwards to rtjo_decode_packet. */
+size_t rtjo_frame_bytes(int fmt, int w, int h);
+long rtjo_decode_packet_fmt(rtjo_decoder *d, int fmt, const uint8_t *pkt, size_t pkt_len,
+                            uint8_t *y, uint8_t *u, uint8_t *v);
+
 #ifdef __cplusplus
 }
 #endif

@@ -119,6 +119,16 @@ def set_tables_case(seed=11):
     print("set_tables: 3 cases")
 
 
+def fmt_case(name, fmt, w, h, Q, F, key_rate=-1, lm=0, cm=0, init_fill=0, **kw):
+    """YUV422 (fmt 1) and 8-bit grey (fmt 2): the other two branches of RTjpeg_decompress (:3580-3585)."""
+    stream, offs = O.encode_clip_fmt(w, h, Q, F, fmt, key_rate, lm, cm, **kw)
+    init = np.full(O.frame_bytes(fmt, w, h), init_fill, dtype=np.uint8)
+    frames = O.ref_decode_seq_fmt(stream, offs, w, h, fmt, init=init)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), stream=stream, offsets=offs, w=w, h=h, Q=Q, fmt=fmt,
+                        init_fill=init_fill, frames=frames, sha=np.array([sha(f) for f in frames]))
+    print(f"{name}: {F} frames, {stream.size} stream bytes")
+
+
 if __name__ == "__main__":
     O.build()
     assert O.have_ref(), "needs /root/reference"
@@ -131,3 +141,7 @@ if __name__ == "__main__":
     random_case("random_48x32", 48, 32, [1, 32, 170, 171, 200, 228, 255])
     tables_case()
     set_tables_case()
+    fmt_case("yuv422_inter_64x48_q200_gop4", 1, 64, 48, 200, 9, key_rate=3, lm=2, cm=2, noise_y=30, noise_c=8, init_fill=0x55)
+    fmt_case("yuv422_intra_96x32_q128", 1, 96, 32, 128, 3, noise_y=6, noise_c=3)
+    fmt_case("grey_inter_64x48_q255_gop4", 2, 64, 48, 255, 9, key_rate=3, lm=2, cm=2, noise_y=40, init_fill=0x55)
+    fmt_case("grey_intra_96x32_q64", 2, 96, 32, 64, 3, noise_y=6)

@@ -6,10 +6,10 @@ import gmerlin_avdecoder_b200 as g
 from gmerlin_avdecoder_b200 import device as D
 
 
-def gpu_decode(ctx, stream, offsets, w, h, carry=None, state=None):
-    """rtjgpu_plan + rtjgpu_decode_device; returns frames [F, w*h*3/2] as numpy."""
+def gpu_decode(ctx, stream, offsets, w, h, carry=None, state=None, fmt=0):
+    """rtjgpu_plan + rtjgpu_decode_device; returns frames [F, frame bytes] as numpy."""
     desc, st = g.plan(stream, offsets, state)
-    b = D.upload(stream, desc, w, h)
+    b = D.upload(stream, desc, w, h, fmt=fmt)
     ct = None if carry is None else torch.from_numpy(np.ascontiguousarray(carry)).cuda()
     # poison the output so that an unwritten byte cannot pass by accident
     b.out.fill_(0xCD)

@@ -39,3 +39,9 @@ def interleave(streams):
             size = int(O.packet_sizes(s, o)[f])
             pk.append(s[int(o[f]):int(o[f]) + size])
     return O.pack_packets(pk)
+
+
+def reference_frames_fmt(stream, offsets, w, h, fmt, init=None):
+    if O.have_ref():
+        return O.ref_decode_seq_fmt(stream, offsets, w, h, fmt, init=init)
+    return O.decode_stream_fmt(stream, offsets, w, h, fmt, init=init)

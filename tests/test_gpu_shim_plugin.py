@@ -82,7 +82,7 @@ def test_rtjpeg_setters_and_errors():
     assert r.decompress_n(pkt[:8], planes) == capi.E_HEADER
     assert r.decompress_n(pkt[:pkt.size // 2], planes) == capi.E_OVERRUN
     assert r.last_error() == capi.E_OVERRUN and r.last_error() == 0
-    r.set_format(1)
+    r.set_format(7)                                          # the reference's switch has no such case (lib/RTjpeg.c:3580-3585)
     assert r.decompress_n(pkt, planes) == capi.E_FORMAT
     r.set_format(0)
     assert r.decompress_n(pkt, planes) == 0

@@ -21,6 +21,31 @@ def test_restatement_matches_golden(name):
         assert np.array_equal(frames, g["frames"])
 
 
+FMT_CLIPS = ["yuv422_inter_64x48_q200_gop4", "yuv422_intra_96x32_q128", "grey_inter_64x48_q255_gop4",
+             "grey_intra_96x32_q64"]
+
+
+@pytest.mark.parametrize("name", FMT_CLIPS)
+def test_restatement_matches_golden_other_formats(name):
+    # YUV422 and 8-bit grey: RTjpeg_decompressYUV422 / RTjpeg_decompress8 (lib/RTjpeg.c:2639-2686, :2751-2772)
+    g = golden(name)
+    w, h, fmt = int(g["w"]), int(g["h"]), int(g["fmt"])
+    init = np.full(O.frame_bytes(fmt, w, h), int(g["init_fill"]), dtype=np.uint8)
+    frames = O.decode_stream_fmt(g["stream"], g["offsets"], w, h, fmt, init=init)
+    assert [sha(f) for f in frames] == list(g["sha"])
+    assert np.array_equal(frames, g["frames"])
+
+
+@pytest.mark.skipif(not O.have_ref(), reason="reference build absent (oracle/_ref)")
+@pytest.mark.parametrize("fmt", [1, 2])
+def test_restatement_matches_live_reference_other_formats(fmt):
+    for (w, h, Q, kr, lm) in [(96, 64, 57, -1, 0), (64, 48, 171, 4, 1), (48, 32, 255, 3, 4), (160, 32, 32, 2, 6)]:
+        s, o = O.encode_clip_fmt(w, h, Q, 7, fmt, kr, lm, lm, noise_y=12, noise_c=4, dark=1, seed=Q)
+        init = np.full(O.frame_bytes(fmt, w, h), 0xA5, dtype=np.uint8)
+        assert np.array_equal(O.ref_decode_seq_fmt(s, o, w, h, fmt, init=init),
+                              O.decode_stream_fmt(s, o, w, h, fmt, init=init)), (w, h, Q)
+
+
 def test_tables_match_golden():
     tabs = golden("tables")["tables"]
     for q in range(1, 256):

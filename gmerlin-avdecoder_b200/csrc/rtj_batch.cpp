@@ -34,6 +34,9 @@ struct Workspace {
     int32_t      *d_seg_nbf = nullptr;   int    seg_frames_cap = 0;
     size_t        cap_entries = 0;
     int           cap_frames = 0;
+    /* K2's picture-order position table, rebuilt when the geometry changes */
+    void         *d_lut = nullptr;       size_t lut_cap = 0;     /* bytes */
+    int           lut_fmt = -1, lut_w = 0, lut_h = 0;
 };
 
 constexpr int HOST_SLOTS = 3;
@@ -78,6 +81,7 @@ struct rtjgpu_ctx {
     size_t         d_host_carry_cap = 0;
     int            scan_mode = RTJGPU_SCAN_AUTO;
     int            format = RTJ_YUV420;
+    bool           k2_strip = getenv("RTJGPU_K2_STRIP") != nullptr;   /* development switch: the strip flavour of K2 */
     uint64_t       host_bad = 0;              /* overrun frames seen by the current rtjgpu_decode_host call */
 };
 
@@ -167,6 +171,7 @@ void ws_release(Workspace *ws)
     if (ws->d_seg_entry) cudaFree(ws->d_seg_entry);
     if (ws->d_seg_base) cudaFree(ws->d_seg_base);
     if (ws->d_seg_nbf) cudaFree(ws->d_seg_nbf);
+    if (ws->d_lut) cudaFree(ws->d_lut);
     *ws = Workspace();
 }
 
@@ -185,6 +190,24 @@ int run_kernels(rtjgpu_ctx *ctx, Workspace *ws, const uint8_t *d_stream, const r
     {
         const int rc = seg_reserve(ctx, ws, F, RTJ_FMT_NBLK(ctx->format, w, h), ctx->scan_mode, &a.seg);
         if (rc) return rc;
+    }
+
+    a.d_lut = nullptr;
+    if (!ctx->k2_strip) {
+        if (ws->lut_fmt != ctx->format || ws->lut_w != w || ws->lut_h != h) {
+            const size_t need = rtj_lut_bytes(ctx->format, w, h);
+            if (need > ws->lut_cap) {
+                if (ws->d_lut) cudaFree(ws->d_lut);
+                ws->d_lut = nullptr; ws->lut_cap = 0; ws->lut_fmt = -1;
+                CK(ctx, cudaMalloc(&ws->d_lut, need));
+                ws->lut_cap = need;
+            }
+            const int e0 = rtj_launch_build_lut(ctx->format, w, h, ws->d_lut, st);
+            if (e0) { ctx->last_cuda = e0; return RTJGPU_E_CUDA; }
+            ws->lut_fmt = ctx->format; ws->lut_w = w; ws->lut_h = h;
+            ctx->launches += 1;
+        }
+        a.d_lut = ws->d_lut;
     }
 
     CK(ctx, cudaMemcpyAsync(ws->d_info, ctx->h_info_reset, sizeof(rtj_dev_info), cudaMemcpyHostToDevice, st));
@@ -407,6 +430,7 @@ int rtjgpu_decode_device(rtjgpu_ctx *ctx, const uint8_t *d_stream, const rtjgpu_
     CK(ctx, cudaSetDevice(ctx->device));
     const int nblk = RTJ_FMT_NBLK(ctx->format, w, h);
     if ((uint64_t)F * (uint64_t)nblk >= (1ull << 32)) return RTJGPU_E_TOOBIG;   /* block indices are 32 bit */
+    if ((uint64_t)RTJ_FMT_FRAME_BYTES(ctx->format, w, h) >= (1ull << 32)) return RTJGPU_E_TOOBIG;   /* and so are offsets inside a frame */
     int rc = ws_reserve(ctx, &ctx->ws, F, nblk);
     if (rc) return rc;
     cudaEvent_t *ev = ctx->timing ? ctx->ev[ctx->timed_calls % TIMING_RING] : nullptr;

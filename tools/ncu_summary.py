@@ -71,20 +71,23 @@ def main():
         # source lines through the cubin's line table
         for cb in cubins:
             dis = subprocess.run(["nvdisasm", "-g", "-c", cb], capture_output=True, text=True).stdout
-            seq, cur, infn = [], None, False
+            # one instruction sequence per function whose name matches (template instantiations each
+            # have their own); the one as long as the report's listing is the kernel that ran
+            seqs, cur, fn = collections.defaultdict(list), None, None
             for l in dis.splitlines():
                 m = re.match(r"\s*\.text\.(\S+):", l)
                 if m:
-                    infn = base in m.group(1)
+                    fn = m.group(1) if base in m.group(1) else None
                     continue
-                if not infn:
+                if fn is None:
                     continue
                 m = re.search(r'//## File "([^"]+)", line (\d+)', l)
                 if m:
                     cur = (os.path.basename(m.group(1)), int(m.group(2)))
                 elif re.match(r"\s*/\*[0-9a-f]{4,}\*/", l):
-                    seq.append(cur)
-            if len(seq) != len(src) - 2:
+                    seqs[fn].append(cur)
+            seq = next((v for v in seqs.values() if len(v) == len(src) - 2), None)
+            if seq is None:
                 continue
             agg = collections.defaultdict(lambda: [0, 0])
             for ln, r in zip(seq, src[2:]):

@@ -14,7 +14,8 @@ import subprocess
 import numpy as np
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "lib", "librtjpeg_b200.so")
+# RTJPEG_B200_LIBFILE: development switch, another build of the same library (kernel variants side by side)
+LIB_PATH = os.environ.get("RTJPEG_B200_LIBFILE") or os.path.join(PKG_DIR, "lib", "librtjpeg_b200.so")
 PLUGIN_PATH = os.path.join(PKG_DIR, "lib", "librtjpeg_b200_bgav.so")
 
 # mirrors of the C structs ---------------------------------------------------

@@ -34,7 +34,7 @@ struct Workspace {
     int32_t      *d_seg_nbf = nullptr;   int    seg_frames_cap = 0;
     size_t        cap_entries = 0;
     int           cap_frames = 0;
-    /* K2's picture-order position table, rebuilt when the geometry changes */
+    /* K2's position table, rebuilt when the geometry changes */
     void         *d_lut = nullptr;       size_t lut_cap = 0;     /* bytes */
     int           lut_fmt = -1, lut_w = 0, lut_h = 0;
 };
@@ -81,7 +81,6 @@ struct rtjgpu_ctx {
     size_t         d_host_carry_cap = 0;
     int            scan_mode = RTJGPU_SCAN_AUTO;
     int            format = RTJ_YUV420;
-    bool           k2_strip = getenv("RTJGPU_K2_STRIP") != nullptr;   /* development switch: the strip flavour of K2 */
     uint64_t       host_bad = 0;              /* overrun frames seen by the current rtjgpu_decode_host call */
 };
 
@@ -193,7 +192,7 @@ int run_kernels(rtjgpu_ctx *ctx, Workspace *ws, const uint8_t *d_stream, const r
     }
 
     a.d_lut = nullptr;
-    if (!ctx->k2_strip) {
+    {
         if (ws->lut_fmt != ctx->format || ws->lut_w != w || ws->lut_h != h) {
             const size_t need = rtj_lut_bytes(ctx->format, w, h);
             if (need > ws->lut_cap) {

@@ -114,7 +114,7 @@ typedef struct rtj_launch_args {
     uint16_t                *d_chunk_last;  /* [ceil(F / 32)][nblk] K3: last writer inside each chunk of frames */
     uint8_t                 *d_out;
     const uint8_t           *d_carry;
-    const void              *d_lut;         /* K2: picture-order position table of this geometry (rtj_launch_build_lut) */
+    const void              *d_lut;         /* K2: position table of this geometry (rtj_launch_build_lut) */
     int                      scan_mode;     /* RTJGPU_SCAN_* */
     rtj_seg_plan             seg;           /* workspace of the segment-parallel scan (sum == NULL: not available) */
 } rtj_launch_args;
@@ -127,7 +127,7 @@ int rtj_launch_scan_mb(const rtj_launch_args *a, int phase, void *stream);      
 int rtj_scan_mb_init(void);
 int rtj_launch_resolve(const rtj_launch_args *a, void *stream);
 int rtj_launch_idct(const rtj_launch_args *a, void *stream);
-/* d_lut: rtj_lut_bytes() bytes -- the unit table followed by the position table of this geometry */
+/* d_lut: rtj_lut_bytes() bytes -- where each block of a row of units goes, for K2 */
 size_t rtj_lut_bytes(int fmt, int w, int h);
 int rtj_launch_build_lut(int fmt, int w, int h, void *d_lut, void *stream);
 int rtj_idct_init(void);      /* rtj_idct.cu */

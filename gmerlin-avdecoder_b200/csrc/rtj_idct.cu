@@ -228,19 +228,24 @@ __device__ __forceinline__ void t2_pixels(int x0, int x1, int q, bool packed, ui
     odd_from_x1(q, d7, d6, d5, d4);
     /* A[0]=x0+a7 A[7]=x0-a7 A[1]=x0+a6 A[6]=x0-a6 A[2]=x0+a5 A[5]=x0-a5 A[4]=x0+a4 A[3]=x0-a4;
      * D[0]=d7 D[7]=-d7 D[1]=d6 D[6]=-d6 D[2]=d5 D[5]=-d5 D[4]=d4 D[3]=-d4 */
-    const int A[8] = {x0 + a7, x0 + a6, x0 + a5, x0 - a4, x0 + a4, x0 - a5, x0 - a6, x0 - a7};
     if (packed) {
+        /* pixel (r, j) = x0 + a(r) + d(j): the four pairs x0 + d(j) are made once, a row adds or subtracts its a(r) */
+        const uint32_t X = (uint32_t)x0 * PK_DUP + PK_GUARD;
         const uint32_t d01 = pack_scaled(d7, d6);         /* (D0, D1) */
         const uint32_t d23 = pack_scaled(d5, -d4);        /* (D2, D3) */
-        const uint32_t d32 = __byte_perm(d23, 0u, 0x1032);   /* (D3, D2): (D4, D5) = -(D3, D2) */
-        const uint32_t d10 = __byte_perm(d01, 0u, 0x1032);   /* (D1, D0): (D6, D7) = -(D1, D0) */
-#pragma unroll
-        for (int r = 0; r < 8; r++) {
-            const uint32_t a2 = (uint32_t)A[r] * PK_DUP + PK_GUARD;
-            px[2 * r] = __byte_perm(a2 + d01, a2 + d23, 0x7531);
-            px[2 * r + 1] = __byte_perm(a2 - d32, a2 - d10, 0x7531);
-        }
+        const uint32_t X01 = X + d01, X23 = X + d23;
+        const uint32_t X45 = X - __byte_perm(d23, 0u, 0x1032);   /* (D4, D5) = -(D3, D2) */
+        const uint32_t X67 = X - __byte_perm(d01, 0u, 0x1032);   /* (D6, D7) = -(D1, D0) */
+        const uint32_t k7 = (uint32_t)a7 * PK_DUP, k6 = (uint32_t)a6 * PK_DUP, k5 = (uint32_t)a5 * PK_DUP, k4 = (uint32_t)a4 * PK_DUP;
+        /* modulo 2^32 these are the sums of the reference's rows, (x0 +- a) * PK_DUP + PK_GUARD +- d with x0 +- a >= 0 */
+#define RTJ_T2_ROW(r, op, k) \
+        px[2 * (r)] = __byte_perm(X01 op k, X23 op k, 0x7531); \
+        px[2 * (r) + 1] = __byte_perm(X45 op k, X67 op k, 0x7531);
+        RTJ_T2_ROW(0, +, k7) RTJ_T2_ROW(1, +, k6) RTJ_T2_ROW(2, +, k5) RTJ_T2_ROW(3, -, k4)
+        RTJ_T2_ROW(4, +, k4) RTJ_T2_ROW(5, -, k5) RTJ_T2_ROW(6, -, k6) RTJ_T2_ROW(7, -, k7)
+#undef RTJ_T2_ROW
     } else {
+        const int A[8] = {x0 + a7, x0 + a6, x0 + a5, x0 - a4, x0 + a4, x0 - a5, x0 - a6, x0 - a7};
 #pragma unroll
         for (int r = 0; r < 8; r++) {
             px[2 * r] = descale_pack4(A[r] + d7, A[r] + d6, A[r] + d5, A[r] - d4);
@@ -467,6 +472,7 @@ struct K2Params {
     uint32_t *hardq;
     unsigned hardq_cap;              /* entries of hardq: F * nblk */
     rtj_dev_info *info;
+    const uint32_t *pos;             /* SINGLE: pic_pos of every position of a row, i | off << 16 (rtj_build_lut_kernel) */
 };
 
 constexpr int K2_WARPS = IDCT_THREADS / 32;
@@ -512,7 +518,19 @@ rtj_idct_kernel(const K2Params P)
     /* everything that does not depend on anything else is fetched first: the first round's entry
      * and the frame descriptor; the table constants follow the descriptor */
     const int rounds = (nb + IDCT_THREADS - 1) / IDCT_THREADS;
-    PicPos pp_next = G::pic_pos(tid, mbs);
+    /* the positions of a whole row are the same for every row of every frame: a table, hot in L1 (padded to a
+     * multiple of IDCT_THREADS); strips of wider pictures work them out */
+    auto pos_of = [&](int p) -> PicPos {
+        if (SINGLE) {
+            const uint32_t v = __ldg(P.pos + p);
+            PicPos r;
+            r.i = (int)(v & 0xFFFFu);
+            r.off = (int)(v >> 16);
+            return r;
+        }
+        return G::pic_pos(p, mbs);
+    };
+    PicPos pp_next = pos_of(tid);
     uint32_t e_first = tid < nb ? my_ent[pp_next.i] : 0u;
     const rtjgpu_frame_desc fd = P.desc[f];
     const unsigned mytable = fd.table;
@@ -531,7 +549,7 @@ rtj_idct_kernel(const K2Params P)
         const bool chroma = off_is_chroma<FMT>(pp.off, mbs);
         uint32_t e = e_first;
         if (r + 1 < rounds) {                                /* next round's entry: in flight during this round */
-            pp_next = G::pic_pos(p + IDCT_THREADS, mbs);
+            pp_next = pos_of(p + IDCT_THREADS);
             e_first = p + IDCT_THREADS < nb ? my_ent[pp_next.i] : 0u;
         }
         int cls = CLS_NONE;
@@ -722,332 +740,13 @@ rtj_idct_kernel(const K2Params P)
     }
 }
 
-/* ------------------------------------------------------------------------ */
-/* K2, warp-autonomous: one warp, one picture row of blocks at a time          */
-/* ------------------------------------------------------------------------ */
-
-namespace {
-
-/*
- * Work is cut into UNITS.  A unit is one row of 8x8 blocks of the luma plane (or a strip of it, for
- * pictures wider than K2R_MAX_STRIP blocks), or the U row plus the V row that belong to the same
- * macroblocks -- so every unit of a launch has the same number of block positions and, when it spans
- * the picture's width, its 8 pixel rows are ONE contiguous byte range of the tight-pitch plane (two
- * ranges for a chroma unit).  A unit's positions are padded to a multiple of 32: a PASS is 32
- * positions, one block per lane.
- *
- *   lut[p]    p = (unit * passes_per_unit + pass) * 32 + lane:
- *             .x = stream-order index of the block (RTJ_LUT_PAD: no block), .y = byte offset of the
- *             block's first row inside the unit's tile
- *   units[u]  .x / .y = byte offset of the unit's first (second) range inside a frame, .z = bytes per
- *             pixel row of the unit, .w = flags
- */
-constexpr uint32_t RTJ_LUT_PAD = 0xFFFFFFFFu;
-constexpr uint32_t RTJ_UNIT_CHROMA = 1u, RTJ_UNIT_CONTIG = 2u;
-constexpr int K2R_MAX_STRIP = 128;   /* blocks per unit at most: an 8 KB tile */
-
-struct RowGeo {
-    int fmt, w, h;
-    int w8, uw;                      /* luma blocks, macroblock columns per picture row */
-    int nstr, S;                     /* strips per picture row, blocks per strip */
-    int ppu;                         /* passes per unit */
-    int upg;                         /* units per group: a group is what one row of the format's units holds */
-    int nunits;
-};
-
-__host__ __device__ inline RowGeo row_geo(int fmt, int w, int h)
+template <int FMT>
+__global__ void rtj_build_lut_kernel(uint32_t *__restrict__ pos, int mbs, int npad)
 {
-    RowGeo g;
-    g.fmt = fmt; g.w = w; g.h = h;
-    g.w8 = w >> 3; g.uw = w >> 4;
-    g.nstr = (g.w8 + K2R_MAX_STRIP - 1) / K2R_MAX_STRIP;
-    g.S = g.nstr == 1 ? g.w8 : ((g.w8 + g.nstr - 1) / g.nstr + 3) & ~3;
-    g.ppu = (g.S + 31) / 32;
-    /* YUV420: a macroblock row = two luma rows and one chroma row; YUV422: a luma row and a chroma row; grey: a luma row */
-    g.upg = (fmt == 0 ? 3 : fmt == 1 ? 2 : 1) * g.nstr;
-    g.nunits = (fmt == 0 ? h >> 4 : h >> 3) * g.upg;
-    return g;
-}
-
-struct K2RParams {
-    const uint8_t *stream;
-    const rtjgpu_frame_desc *desc;
-    const rtj_dev_table *tables;
-    const uint32_t *ent;
-    const uint16_t *srcf;
-    const uint2 *lut;
-    const uint4 *units;
-    int nblk, nunits, upw, ppu;      /* units per frame, units per warp, passes per unit */
-    unsigned ts_l, ts_c;             /* bytes between pixel rows inside a luma / chroma tile */
-    unsigned pitch_l, pitch_c;
-    unsigned tile_bytes, qcap;       /* per warp: tile, slots of the M7 queue (a power of two) */
-    size_t fsz;
-    uint8_t *out;
-    const uint8_t *carry;
-    uint32_t *hardq;
-    unsigned hardq_cap;
-    rtj_dev_info *info;
-};
-
-constexpr int KW_WARPS = 4;
-
-__device__ __forceinline__ void sts64(unsigned saddr, uint32_t a, uint32_t b)
-{
-    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" :: "r"(saddr), "r"(a), "r"(b) : "memory");
-}
-
-} // namespace
-
-extern "C" __global__ void rtj_build_lut_kernel(uint2 *__restrict__ lut, uint4 *__restrict__ units, int fmt, int w, int h)
-{
-    const RowGeo g = row_geo(fmt, w, h);
-    const int per_unit = g.ppu * 32;
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= g.nunits * per_unit) return;
-    const int u = p / per_unit, j = p - u * per_unit;
-    const int grp = u / g.upg, t = u - grp * g.upg;
-    const int kind = t / g.nstr, s = t - kind * g.nstr;          /* YUV420: 0, 1 = luma rows, 2 = chroma; YUV422: 0 luma, 1 chroma */
-    const bool chroma = fmt == 0 ? kind == 2 : fmt == 1 ? kind == 1 : false;
-    const int b0 = s * g.S, nb = min(g.S, g.w8 - b0);            /* luma blocks of this strip */
-    const int cw = w >> 1;
-    uint32_t i = RTJ_LUT_PAD, toff = 0;
-    uint4 ud;
-    if (!chroma) {
-        const int by = fmt == 0 ? 2 * grp + kind : grp;
-        ud = make_uint4((uint32_t)(by * 8) * (uint32_t)w + (uint32_t)b0 * 8u, 0u, (uint32_t)nb * 8u,
-                        g.nstr == 1 ? RTJ_UNIT_CONTIG : 0u);
-        if (j < nb) {
-            const int bx = b0 + j;
-            toff = (uint32_t)j * 8u;
-            if (fmt == 0) i = (uint32_t)((by >> 1) * g.uw + (bx >> 1)) * 6u + (uint32_t)((by & 1) * 2 + (bx & 1));   /* lib/RTjpeg.c:2704-2727 */
-            else if (fmt == 1) i = (uint32_t)(by * g.uw + (bx >> 1)) * 4u + (uint32_t)(bx & 1);                      /* :2654-2665 */
-            else i = (uint32_t)(by * g.w8 + bx);                                                                   /* :2761-2770 */
-        }
-    } else {
-        const int cb0 = b0 >> 1, ncb = nb >> 1;
-        const uint32_t csz = (uint32_t)cw * (uint32_t)(fmt == 0 ? h >> 1 : h);
-        const uint32_t g0 = (uint32_t)w * (uint32_t)h + (uint32_t)(grp * 8) * (uint32_t)cw + (uint32_t)cb0 * 8u;
-        ud = make_uint4(g0, g0 + csz, (uint32_t)ncb * 8u, RTJ_UNIT_CHROMA | (g.nstr == 1 ? RTJ_UNIT_CONTIG : 0u));
-        if (j < 2 * ncb) {
-            const int v = j >= ncb ? 1 : 0;
-            const int cx = cb0 + j - v * ncb;
-            toff = (uint32_t)v * 8u * (uint32_t)(g.S * 4) + (uint32_t)(j - v * ncb) * 8u;      /* the V rows follow the 8 U rows */
-            i = (uint32_t)(grp * g.uw + cx) * (fmt == 0 ? 6u : 4u) + (fmt == 0 ? 4u : 2u) + (uint32_t)v;         /* :2728-2739, :2666-2677 */
-        }
-    }
-    lut[p] = make_uint2(i, toff);
-    if (j == 0) units[u] = ud;
-}
-
-/*
- * A warp owns a run of units of one frame and assembles each in its own shared-memory tile, which then
- * leaves as 16-byte vectors covering whole 32-byte sectors (a sector written in part costs the L2 a
- * read-modify-write against DRAM; picture rows of 720 or 360 bytes start in the middle of one).  T2
- * blocks are decoded in the pass that meets them.  M7 blocks wait in the warp's queue and are decoded 32
- * at a time after the tile that holds their placeholder has left, straight into the output planes (by
- * then resident in L2).  CARRY blocks are copied into the tile, HARD blocks handed to the device queue.
- * Nothing is shared between warps: no barrier.
- */
-extern "C" __global__ void __launch_bounds__(KW_WARPS * 32, 7)
-rtj_idct_row_kernel(const K2RParams P)
-{
-    extern __shared__ __align__(128) uint8_t k2r_smem[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const unsigned f = blockIdx.y;
-    const int u0 = ((int)blockIdx.x * KW_WARPS + warp) * P.upw;
-    if (u0 >= P.nunits) return;
-    const int u1 = min(u0 + P.upw, P.nunits);
-    uint8_t *tile = k2r_smem + (size_t)warp * (P.tile_bytes + 12u * P.qcap);
-    uint32_t *q_e = reinterpret_cast<uint32_t *>(tile + P.tile_bytes), *q_d = q_e + P.qcap, *q_s = q_d + P.qcap;
-    const unsigned tile_s = (unsigned)__cvta_generic_to_shared(tile);
-    const unsigned qmask = P.qcap - 1u;
-
-    const uint32_t *my_ent = P.ent + (size_t)f * (unsigned)P.nblk;
-    const unsigned frame_blk0 = f * (unsigned)P.nblk;               /* F * nblk < 2^32 (checked by the host) */
-    int k = u0 * P.ppu;
-    const int kend = u1 * P.ppu;
-    /* two passes of the position table and one pass of entries are in flight ahead of the arithmetic */
-    uint2 L0 = P.lut[k * 32 + lane];
-    uint2 L1 = k + 1 < kend ? P.lut[(k + 1) * 32 + lane] : make_uint2(RTJ_LUT_PAD, 0u);
-    uint32_t e0 = L0.x != RTJ_LUT_PAD ? my_ent[L0.x] : 0u;
-    const rtjgpu_frame_desc fd = P.desc[f];
-    const unsigned mytable = fd.table;
-    const rtj_dev_table *tb = &P.tables[mytable];
-    const uint8_t *frame_pay = P.stream + fd.offset + RTJPEG_B200_HEADER_BYTES;
-    uint8_t *out_f = P.out + (size_t)f * P.fsz;
-    const int bt8_l = tb->bt8[0], bt8_c = tb->bt8[1];
-    const int lq0 = tb->iq[0][0], lq1 = tb->iq[0][1], lq2 = tb->iq[0][2];
-    const int cq0 = tb->iq[1][0], cq1 = tb->iq[1][1], cq2 = tb->iq[1][2];
-    const unsigned below = (1u << lane) - 1u;
-    const unsigned vbase = 8u * P.ts_c;                             /* tile offset of the V rows of a chroma unit */
-
-    unsigned qh = 0;                                                /* warp-uniform: head and fill of the M7 queue */
-    int qn = 0;
-    for (int u = u0; u <= u1; u++) {
-        if (u < u1) {
-            const uint4 ud = P.units[u];
-            const bool chroma = (ud.w & RTJ_UNIT_CHROMA) != 0u;     /* warp-uniform */
-            const int q0 = chroma ? cq0 : lq0, q1 = chroma ? cq1 : lq1, q2 = chroma ? cq2 : lq2;
-            const unsigned ts = chroma ? P.ts_c : P.ts_l, pitch = chroma ? P.pitch_c : P.pitch_l;
-            for (int pp = 0; pp < P.ppu; pp++, k++) {
-                const uint2 L = L0;
-                uint32_t e = e0;
-                L0 = L1;
-                e0 = L0.x != RTJ_LUT_PAD ? my_ent[L0.x] : 0u;
-                L1 = k + 2 < kend ? P.lut[(k + 2) * 32 + lane] : make_uint2(RTJ_LUT_PAD, 0u);
-
-                const unsigned i = L.x;
-                const bool live = i != RTJ_LUT_PAD;
-                int cls = CLS_NONE;
-                int x0 = 1008, x1 = 0, q = 0;
-                unsigned sf = f;
-                if (live) {
-                    if (RTJ_ENT_IS_INLINE(e)) {                      /* the common case first */
-                        cls = CLS_T2;
-                    } else {
-                        if (RTJ_ENT_IS_SKIP(e)) {                    /* skipped: take the entry of its last writer */
-                            const unsigned s = P.srcf[frame_blk0 + i];
-                            if (s != RTJ_SRC_CARRY) {
-                                sf = s;
-                                e = P.ent[s * (unsigned)P.nblk + i];
-                            }
-                        }
-                        if (RTJ_ENT_IS_SKIP(e)) cls = Q_CARRY;
-                        else if (sf != f && P.desc[sf].table != mytable) cls = Q_HARD;
-                        else if (RTJ_ENT_IS_INLINE(e)) cls = CLS_T2;
-                        else {
-                            const int eob = RTJ_ENT_EOB(e);
-                            cls = eob <= 3 ? CLS_T2 : eob <= 7 ? Q_M7 : Q_HARD;
-                        }
-                    }
-                    if (cls == CLS_T2) {
-                        if (RTJ_ENT_IS_INLINE(e)) {
-                            x0 = wrap16((int)(e & 0xFFu) * q0) + 4;
-                            x1 = wrap16((int)(signed char)((e >> 8) & 0xFFu) * q1);
-                            q = wrap16((int)(signed char)((e >> 16) & 0xFFu) * q2);
-                        } else {
-                            const uint8_t *src = (sf == f ? frame_pay : P.stream + P.desc[sf].offset + RTJPEG_B200_HEADER_BYTES)
-                                                 + (e & RTJ_ENT_OFF_MASK);
-                            RegBytes<1> by(src);
-                            int x[3];
-                            unpack_block<3>(by, tb->iq[chroma], chroma ? bt8_c : bt8_l, x);
-                            x0 = x[0]; x1 = x[1]; q = x[2];
-                        }
-                    }
-                }
-                /* every lane runs the T2 arithmetic (blocks of the other classes on neutral values: their pixels
-                 * are placeholders, replaced below or after the tile has left) */
-                const bool packed = __all_sync(FULL, t2_safe(x0, x1, q));    /* one epilogue flavour per warp */
-                {
-                    uint32_t px[16];
-                    t2_pixels(x0, x1, q, packed, px);
-                    if (live) {
-                        const unsigned sa = tile_s + L.y;
-#pragma unroll
-                        for (int r = 0; r < 8; r++) sts64(sa + (unsigned)r * ts, px[2 * r], px[2 * r + 1]);
-                    }
-                }
-                const unsigned mM = __ballot_sync(FULL, cls == Q_M7);
-                const unsigned mB = __ballot_sync(FULL, cls == Q_CARRY || cls == Q_HARD);
-                if (mM | mB) {
-                    /* where the block's first row lives in the frame */
-                    const bool vplane = chroma && L.y >= vbase;
-                    const uint32_t goff = (vplane ? ud.y - vbase : ud.x) + L.y;
-                    if (cls == Q_M7) {
-                        const unsigned at = (qh + (unsigned)qn + (unsigned)__popc(mM & below)) & qmask;
-                        q_e[at] = e;
-                        q_d[at] = goff;
-                        q_s[at] = sf | (chroma ? 0x80000000u : 0u);
-                    }
-                    qn += __popc(mM);
-                    if (mB) {                                        /* rare */
-                        const bool hard = cls == Q_HARD;
-                        /* HARD blocks split once more for the general kernel: long ones (E > 16) apart from the rest */
-                        const bool full = hard && !RTJ_ENT_IS_INLINE(e) && RTJ_ENT_EOB(e) > 16;
-                        const unsigned mH = __ballot_sync(FULL, hard && !full), mF = __ballot_sync(FULL, full);
-                        if (mH | mF) {
-                            /* the device queue is filled from both ends: mid-size blocks from the front, long ones from the back */
-                            unsigned base = 0, baseF = 0;
-                            if (lane == 0) {
-                                if (mH) base = atomicAdd(&P.info->hard_blocks, (unsigned)__popc(mH));
-                                if (mF) baseF = atomicAdd(&P.info->hard_full, (unsigned)__popc(mF));
-                            }
-                            base = __shfl_sync(FULL, base, 0);
-                            baseF = __shfl_sync(FULL, baseF, 0);
-                            if (hard && !full) P.hardq[base + __popc(mH & below)] = frame_blk0 + i;
-                            if (full) P.hardq[P.hardq_cap - 1u - (baseF + __popc(mF & below))] = frame_blk0 + i;
-                        }
-                        if (cls == Q_CARRY) {                        /* never written in this batch: the picture before it */
-                            const unsigned sa = tile_s + L.y;
-#pragma unroll
-                            for (int r = 0; r < 8; r++) {
-                                uint2 v = make_uint2(0u, 0u);
-                                if (P.carry) v = *reinterpret_cast<const uint2 *>(P.carry + goff + (size_t)((unsigned)r * pitch));
-                                sts64(sa + (unsigned)r * ts, v.x, v.y);
-                            }
-                        }
-                    }
-                }
-            }
-            /* ---- the unit leaves ---- */
-            __syncwarp();
-            {
-                const unsigned nsub = chroma ? 2u : 1u;
-                if (ud.w & RTJ_UNIT_CONTIG) {                        /* 8 pixel rows = one contiguous, sector-aligned range */
-                    const unsigned bytes = 8u * ud.z;
-                    for (unsigned sub = 0; sub < nsub; sub++) {
-                        uint8_t *g = out_f + (sub ? ud.y : ud.x);
-                        const uint8_t *t = tile + sub * vbase;
-                        for (unsigned o = (unsigned)lane * 16u; o < bytes; o += 512u)
-                            *reinterpret_cast<uint4 *>(g + o) = *reinterpret_cast<const uint4 *>(t + o);
-                    }
-                } else {                                             /* a strip of a wider picture: row by row */
-                    for (unsigned sub = 0; sub < nsub; sub++) {
-                        uint8_t *g = out_f + (sub ? ud.y : ud.x);
-                        const uint8_t *t = tile + sub * vbase;
-                        for (unsigned r = 0; r < 8; r++)
-                            for (unsigned o = (unsigned)lane * 8u; o < ud.z; o += 256u)
-                                *reinterpret_cast<uint2 *>(g + (size_t)r * pitch + o) = *reinterpret_cast<const uint2 *>(t + r * ts + o);
-                    }
-                }
-            }
-            __syncwarp();
-            if (qn < 32) continue;
-        } else if (qn == 0) break;
-        /* ---- passes of M7 blocks from the queue: full ones, or what is left at the end of the run.  Their tiles
-         *      have left: the pixels go straight to the frame. ---- */
-        do {
-            const int n = min(qn, 32);
-            const bool live = lane < n;
-            int x[7] = {1008, 0, 0, 0, 0, 0, 0};
-            uint32_t doff = 0;
-            bool chroma = false;
-            if (live) {
-                const unsigned at = (qh + (unsigned)lane) & qmask;
-                const uint32_t e = q_e[at], ss = q_s[at];
-                doff = q_d[at];
-                chroma = (ss >> 31) != 0u;
-                const unsigned sf = ss & 0x7FFFFFFFu;
-                const uint8_t *src = (sf == f ? frame_pay : P.stream + P.desc[sf].offset + RTJPEG_B200_HEADER_BYTES)
-                                     + (e & RTJ_ENT_OFF_MASK);
-                RegBytes<2> by(src);
-                unpack_block<7>(by, tb->iq[chroma], chroma ? bt8_c : bt8_l, x);
-            }
-            const bool packed = __all_sync(FULL, m7_safe(x));
-            if (live) {
-                uint32_t px[16];
-                m7_pixels(x, packed, px);
-                uint8_t *dst = out_f + doff;
-                const unsigned pitch = chroma ? P.pitch_c : P.pitch_l;
-#pragma unroll
-                for (int r = 0; r < 8; r++)
-                    *reinterpret_cast<uint2 *>(dst + (size_t)((unsigned)r * pitch)) = make_uint2(px[2 * r], px[2 * r + 1]);
-            }
-            qh = (qh + (unsigned)n) & qmask;
-            qn -= n;
-            __syncwarp();
-        } while (qn >= 32 || (u == u1 && qn > 0));
-    }
+    if (p >= npad) return;
+    const PicPos r = Geo<FMT>::pic_pos(min(p, mbs * Geo<FMT>::BLK - 1), mbs);       /* the padding repeats the last position */
+    pos[p] = (uint32_t)r.i | (uint32_t)r.off << 16;
 }
 
 /* ------------------------------------------------------------------------ */
@@ -1153,9 +852,6 @@ extern "C" int rtj_idct_init(void)
     if (e == cudaSuccess) e = k2_attr<false, 1>();
     if (e == cudaSuccess) e = k2_attr<true, 2>();
     if (e == cudaSuccess) e = k2_attr<false, 2>();
-    if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(rtj_idct_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 KW_WARPS * (K2R_MAX_STRIP * 64 + 12 * 256));
     if (e != cudaSuccess) return (int)e;
     int dev = 0;
     if ((e = cudaGetDevice(&dev)) != cudaSuccess) return (int)e;
@@ -1163,18 +859,23 @@ extern "C" int rtj_idct_init(void)
     return 0;
 }
 
+/* The position table of rtj_idct_kernel<SINGLE = true> for this geometry: 4 bytes per position of one row of units. */
 extern "C" size_t rtj_lut_bytes(int fmt, int w, int h)
 {
-    const RowGeo g = row_geo(fmt, w, h);
-    return (size_t)g.nunits * sizeof(uint4) + (size_t)g.nunits * g.ppu * 32 * sizeof(uint2);
+    const int nb = RTJ_FMT_UNITS_X(fmt, w) * RTJ_FMT_UNIT_BLOCKS(fmt);
+    return (size_t)((nb + IDCT_THREADS - 1) / IDCT_THREADS * IDCT_THREADS) * sizeof(uint32_t);
 }
 
 extern "C" int rtj_launch_build_lut(int fmt, int w, int h, void *d_lut, void *stream)
 {
-    const RowGeo g = row_geo(fmt, w, h);
-    uint4 *units = reinterpret_cast<uint4 *>(d_lut);
-    const int n = g.nunits * g.ppu * 32;
-    rtj_build_lut_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<uint2 *>(units + g.nunits), units, fmt, w, h);
+    const int mbs = RTJ_FMT_UNITS_X(fmt, w);
+    const int npad = (int)(rtj_lut_bytes(fmt, w, h) / sizeof(uint32_t));
+    uint32_t *pos = reinterpret_cast<uint32_t *>(d_lut);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (mbs > IDCT_MAX_MB) return 0;                 /* strips: no table */
+    if (fmt == 0) rtj_build_lut_kernel<0><<<(npad + 127) / 128, 128, 0, st>>>(pos, mbs, npad);
+    else if (fmt == 1) rtj_build_lut_kernel<1><<<(npad + 127) / 128, 128, 0, st>>>(pos, mbs, npad);
+    else rtj_build_lut_kernel<2><<<(npad + 127) / 128, 128, 0, st>>>(pos, mbs, npad);
     return (int)cudaGetLastError();
 }
 
@@ -1190,38 +891,10 @@ extern "C" int rtj_launch_idct(const rtj_launch_args *a, void *stream)
     P.out = a->d_out; P.carry = a->d_carry; P.hardq = a->d_hardq; P.info = a->d_info;
     P.hardq_cap = (unsigned)((size_t)a->F * (size_t)P.nblk);
     P.fmt = fmt;
-    if (!a->d_lut) {        /* the strip kernel: kept for comparison */
-        dim3 grid((unsigned)(P.nstrips * uy), (unsigned)a->F);
-        cudaError_t e = fmt == 0 ? k2_launch<0>(P, grid, st) : fmt == 1 ? k2_launch<1>(P, grid, st) : k2_launch<2>(P, grid, st);
-        if (e != cudaSuccess) return (int)e;
-    } else if (a->F > 0) {
-        const RowGeo g = row_geo(fmt, a->w, a->h);
-        K2RParams W;
-        W.stream = a->d_stream; W.desc = a->d_desc; W.tables = a->d_tables; W.ent = a->d_ent; W.srcf = a->d_src;
-        W.units = reinterpret_cast<const uint4 *>(a->d_lut);
-        W.lut = reinterpret_cast<const uint2 *>(W.units + g.nunits);
-        W.nblk = P.nblk; W.nunits = g.nunits; W.ppu = g.ppu;
-        W.ts_l = (unsigned)g.S * 8u; W.ts_c = (unsigned)g.S * 4u;
-        W.pitch_l = (unsigned)a->w; W.pitch_c = (unsigned)(a->w >> 1);
-        W.tile_bytes = (unsigned)g.S * 64u;
-        unsigned qcap = 64;
-        while (qcap < 32u + (unsigned)g.ppu * 32u) qcap <<= 1;
-        W.qcap = qcap;
-        W.fsz = RTJ_FMT_FRAME_BYTES(fmt, a->w, a->h);
-        W.out = a->d_out; W.carry = a->d_carry; W.hardq = a->d_hardq; W.hardq_cap = P.hardq_cap; W.info = a->d_info;
-        /* long runs keep the M7 queue's last, part-filled pass rare; short ones fill the device when frames are few */
-        const int sms0 = g_sm_count > 0 ? g_sm_count : 148;
-        long long upw = ((long long)g.nunits * a->F) / ((long long)sms0 * 28 * 4);
-        const long long most = (24 + g.ppu - 1) / g.ppu;             /* about 24 passes */
-        upw = upw < 1 ? 1 : upw > most ? most : upw;
-        W.upw = (int)upw;
-        const int wpf = (g.nunits + W.upw - 1) / W.upw;
-        dim3 grid((unsigned)((wpf + KW_WARPS - 1) / KW_WARPS), (unsigned)a->F);
-        const size_t smem = (size_t)KW_WARPS * (W.tile_bytes + 12u * W.qcap);
-        rtj_idct_row_kernel<<<grid, KW_WARPS * 32, smem, st>>>(W);
-        cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess) return (int)e;
-    }
+    P.pos = reinterpret_cast<const uint32_t *>(a->d_lut);
+    dim3 grid((unsigned)(P.nstrips * uy), (unsigned)a->F);
+    cudaError_t e = fmt == 0 ? k2_launch<0>(P, grid, st) : fmt == 1 ? k2_launch<1>(P, grid, st) : k2_launch<2>(P, grid, st);
+    if (e != cudaSuccess) return (int)e;
     /* the queue's length is only known on the device: a fixed grid strides over it */
     const int sms = g_sm_count > 0 ? g_sm_count : 148;
     rtj_idct_hard_kernel<<<sms * 4, 128, 0, st>>>(

@@ -102,13 +102,15 @@ __device__ __forceinline__ void mb_level0_run(const uint8_t *__restrict__ payb, 
 
 /* PHASE 0: the whole frame, segment after segment.  PHASE 1 / 2: one segment (blockIdx.x) of frame
  * blockIdx.y -- its summary for the frame-level chain, resp. its entries (rtj_common.h, rtj_seg_plan). */
-template <int PHASE>
+/* FMT: the picture format fixes how many blocks a unit holds and how many of them are luma (rtj_common.h) */
+template <int PHASE, int FMT>
 __global__ void __launch_bounds__(MB_THREADS, 7)
 rtj_scan_mb_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc *__restrict__ desc,
                    const rtj_dev_table *__restrict__ tables, int F, int nblk,
                    uint32_t *__restrict__ ent, uint32_t *__restrict__ frame_skips,
-                   rtj_dev_info *__restrict__ info, const rtj_seg_plan sp, int unit, int unit_luma)
+                   rtj_dev_info *__restrict__ info, const rtj_seg_plan sp)
 {
+    constexpr int unit = RTJ_FMT_UNIT_BLOCKS(FMT), unit_luma = RTJ_FMT_UNIT_LUMA(FMT);
     extern __shared__ __align__(16) uint8_t mb_smem[];
     MbShared &sh = *reinterpret_cast<MbShared *>(mb_smem);
     const int tid = threadIdx.x, lane = tid & 31;
@@ -186,7 +188,9 @@ rtj_scan_mb_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc *
         /* ---- compose: length of the macroblock that would start at every position ---- */
         for (int q = tid; q < npos; q += MB_THREADS) {
             int n = q;
+#pragma unroll
             for (int k = 0; k < unit_luma; k++) n += dLb[n];
+#pragma unroll
             for (int k = unit_luma; k < unit; k++) n += dCb[n];
             sh.dmb[q + ((q / MB_C) << 1)] = (uint16_t)(n - q);
         }
@@ -333,29 +337,48 @@ rtj_scan_mb_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc *
     }
 }
 
-extern "C" int rtj_scan_mb_init(void)
+namespace {
+
+template <int FMT>
+cudaError_t scan_mb_launch(const rtj_launch_args *a, int phase, int nblk, cudaStream_t st)
 {
-    cudaError_t e = cudaFuncSetAttribute(rtj_scan_mb_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MbShared));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(rtj_scan_mb_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MbShared));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(rtj_scan_mb_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MbShared));
-    return e == cudaSuccess ? 0 : (int)e;
+    const dim3 grid = phase == 0 ? dim3((unsigned)a->F) : dim3((unsigned)a->seg.maxseg, (unsigned)a->F);
+    if (phase == 0)
+        rtj_scan_mb_kernel<0, FMT><<<grid, MB_THREADS, sizeof(MbShared), st>>>(
+            a->d_stream, a->d_desc, a->d_tables, a->F, nblk, a->d_ent, a->d_frame_skips, a->d_info, a->seg);
+    else if (phase == 1)
+        rtj_scan_mb_kernel<1, FMT><<<grid, MB_THREADS, sizeof(MbShared), st>>>(
+            a->d_stream, a->d_desc, a->d_tables, a->F, nblk, a->d_ent, a->d_frame_skips, a->d_info, a->seg);
+    else
+        rtj_scan_mb_kernel<2, FMT><<<grid, MB_THREADS, sizeof(MbShared), st>>>(
+            a->d_stream, a->d_desc, a->d_tables, a->F, nblk, a->d_ent, a->d_frame_skips, a->d_info, a->seg);
+    return cudaGetLastError();
 }
+
+template <int FMT>
+cudaError_t scan_mb_attr()
+{
+    cudaError_t e = cudaFuncSetAttribute(rtj_scan_mb_kernel<0, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MbShared));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(rtj_scan_mb_kernel<1, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MbShared));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(rtj_scan_mb_kernel<2, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MbShared));
+    return e;
+}
+
+} // namespace
 
 extern "C" int rtj_launch_scan_mb(const rtj_launch_args *a, int phase, void *stream)
 {
     static_assert(MB_S == RTJ_SEG_BYTES_MB && MB_DLA <= RTJ_SEG_NE, "segment size and entry range are shared with the frame-level chain");
     const int nblk = RTJ_FMT_NBLK(a->fmt, a->w, a->h);
-    const int unit = RTJ_FMT_UNIT_BLOCKS(a->fmt), unit_luma = RTJ_FMT_UNIT_LUMA(a->fmt);
     cudaStream_t st = (cudaStream_t)stream;
-    const dim3 grid = phase == 0 ? dim3((unsigned)a->F) : dim3((unsigned)a->seg.maxseg, (unsigned)a->F);
-    if (phase == 0)
-        rtj_scan_mb_kernel<0><<<grid, MB_THREADS, sizeof(MbShared), st>>>(
-            a->d_stream, a->d_desc, a->d_tables, a->F, nblk, a->d_ent, a->d_frame_skips, a->d_info, a->seg, unit, unit_luma);
-    else if (phase == 1)
-        rtj_scan_mb_kernel<1><<<grid, MB_THREADS, sizeof(MbShared), st>>>(
-            a->d_stream, a->d_desc, a->d_tables, a->F, nblk, a->d_ent, a->d_frame_skips, a->d_info, a->seg, unit, unit_luma);
-    else
-        rtj_scan_mb_kernel<2><<<grid, MB_THREADS, sizeof(MbShared), st>>>(
-            a->d_stream, a->d_desc, a->d_tables, a->F, nblk, a->d_ent, a->d_frame_skips, a->d_info, a->seg, unit, unit_luma);
-    return (int)cudaGetLastError();
+    return (int)(a->fmt == 0 ? scan_mb_launch<0>(a, phase, nblk, st) : a->fmt == 1 ? scan_mb_launch<1>(a, phase, nblk, st)
+                                                                     : scan_mb_launch<2>(a, phase, nblk, st));
+}
+
+extern "C" int rtj_scan_mb_init(void)
+{
+    cudaError_t e = scan_mb_attr<0>();
+    if (e == cudaSuccess) e = scan_mb_attr<1>();
+    if (e == cudaSuccess) e = scan_mb_attr<2>();
+    return e == cudaSuccess ? 0 : (int)e;
 }

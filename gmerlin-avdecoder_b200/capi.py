@@ -116,6 +116,12 @@ def load_library() -> C.CDLL:
     L.rtjgpu_set_custom_tables.argtypes = [vp, _u32p]
     L.rtjgpu_set_scan_mode.argtypes = [vp, C.c_int]
     L.rtjgpu_set_format.argtypes = [vp, C.c_int]
+    L.rtjgpu_convert_device.argtypes = [vp, C.c_int, vp, C.c_size_t, C.c_int, C.c_int, C.c_int, vp, C.c_size_t, C.c_size_t,
+                                        C.c_int, vp]
+    L.rtjgpu_convert_bpp.argtypes = [C.c_int]
+    for name in CONVERTERS:
+        getattr(L, name).argtypes = [vp, C.POINTER(_u8p), C.POINTER(_u8p)]
+        getattr(L, name).restype = None
     L.rtjgpu_plan.argtypes = [_u8p, _u64p, C.c_int, C.POINTER(State), vp]
     L.rtjgpu_decode_device.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp]
     L.rtjgpu_decode_host.argtypes = [vp, _u8p, _u64p, C.c_int, C.POINTER(State), _u8p, _u8p, C.c_int]
@@ -146,6 +152,13 @@ def load_library() -> C.CDLL:
     L.rtjgpu_host_free.restype = None
     _lib = L
     return L
+
+
+# the converters of include/RTjpeg.h:128-136, indexed by RTJ_CONV_*
+CONV_RGB32, CONV_BGR32, CONV_RGB24, CONV_BGR24, CONV_RGB16, CONV_RGB8, CONV_YUV422_RGB24 = range(7)
+CONVERTERS = ("RTjpeg_yuv420rgb32", "RTjpeg_yuv420bgr32", "RTjpeg_yuv420rgb24", "RTjpeg_yuv420bgr24",
+              "RTjpeg_yuv420rgb16", "RTjpeg_yuv420rgb8", "RTjpeg_yuv422rgb24")
+CONV_BPP = (4, 4, 3, 3, 2, 1, 3)
 
 
 def frame_bytes(fmt: int, w: int, h: int) -> int:
@@ -284,6 +297,13 @@ class BatchContext:
         """RTJ_YUV420 (default), RTJ_YUV422 or RTJ_RGB8 (8-bit grey) for the batches that follow."""
         _check(self._L.rtjgpu_set_format(self._h, fmt), "rtjgpu_set_format")
 
+    def convert_device(self, kind: int, d_frames: int, src_frame_bytes: int, F: int, w: int, h: int, d_out: int,
+                       row_pitch: int, frame_pitch: int, alpha: int = 0, cuda_stream: int | None = None) -> None:
+        """The reference's colour converter `kind` (CONV_*) over F device-resident pictures."""
+        _check(self._L.rtjgpu_convert_device(self._h, kind, C.c_void_p(d_frames), src_frame_bytes, F, w, h,
+                                             C.c_void_p(d_out), row_pitch, frame_pitch, alpha,
+                                             C.c_void_p(cuda_stream or 0)), "rtjgpu_convert_device")
+
     def set_custom_tables(self, raw: np.ndarray) -> None:
         raw = np.ascontiguousarray(raw, dtype=np.uint32)
         assert raw.size == 128
@@ -408,6 +428,17 @@ class RTjpeg:
         w = int(pkt[6]) | int(pkt[7]) << 8
         h = int(pkt[8]) | int(pkt[9]) << 8
         return self._L.RTjpeg_b200_decompress_n(self._h, _u8(pkt), pkt.size, self._planes(planes, w, h))
+
+    def convert(self, kind: int, planes: np.ndarray, w: int, h: int, out: np.ndarray) -> None:
+        """RTjpeg_yuv420rgb32 & co.: planes is one tight picture (Y|Cb|Cr), out a [h, pitch] byte array whose rows
+        are handed over as the reference's `rows`."""
+        assert planes.dtype == np.uint8 and planes.flags.c_contiguous and out.dtype == np.uint8 and out.ndim == 2
+        ysz = w * h
+        csz = 0 if kind == CONV_RGB8 else ysz // 2 if kind == CONV_YUV422_RGB24 else ysz // 4
+        base = planes.ctypes.data
+        pl = (_u8p * 3)(C.cast(base, _u8p), C.cast(base + ysz, _u8p), C.cast(base + ysz + csz, _u8p))
+        rows = (_u8p * h)(*[C.cast(out[r].ctypes.data, _u8p) for r in range(h)])
+        getattr(self._L, CONVERTERS[kind])(self._h, pl, rows)
 
     def last_error(self) -> int:
         return int(self._L.RTjpeg_b200_last_error(self._h))

@@ -262,7 +262,7 @@ const char *rtjgpu_strerror(int code)
     case RTJGPU_E_ARG:     return "bad argument";
     case RTJGPU_E_HEADER:  return "packet shorter than its header or framesize";
     case RTJGPU_E_SIZE:    return "width/height zero, not a multiple of 16, or changing inside a batch";
-    case RTJGPU_E_FORMAT:  return "only YUV420 is decoded";
+    case RTJGPU_E_FORMAT:  return "unknown picture format or converter";
     case RTJGPU_E_OVERRUN: return "block stream runs past the end of its packet";
     case RTJGPU_E_TOOBIG:  return "batch exceeds RTJGPU_MAX_FRAMES_PER_BATCH / RTJGPU_MAX_PAYLOAD_BYTES";
     case RTJGPU_E_NOMEM:   return "out of memory";
@@ -357,6 +357,33 @@ int rtjgpu_set_format(rtjgpu_ctx *ctx, int format)
 {
     if (!ctx || format < RTJ_YUV420 || format > RTJ_RGB8) return RTJGPU_E_ARG;
     ctx->format = format;
+    return RTJGPU_OK;
+}
+
+int rtjgpu_convert_bpp(int kind) { return rtj_convert_bpp(kind); }
+
+int rtjgpu_convert_device(rtjgpu_ctx *ctx, int kind, const uint8_t *d_frames, size_t src_frame_bytes,
+                          int F, int w, int h, uint8_t *d_out, size_t row_pitch, size_t frame_pitch,
+                          int alpha, void *cuda_stream)
+{
+    if (!ctx || F < 0) return RTJGPU_E_ARG;
+    const int bpp = rtj_convert_bpp(kind);
+    if (!bpp) return RTJGPU_E_FORMAT;
+    if (F == 0) return RTJGPU_OK;
+    if (!d_frames || !d_out) return RTJGPU_E_ARG;
+    if (w <= 0 || h <= 0 || (w & 15) || (h & 15) || w > 65535 || h > 65535) return RTJGPU_E_SIZE;
+    if (F > 65535) return RTJGPU_E_TOOBIG;                                   /* frames are the grid's second dimension */
+    if ((row_pitch & 15) || row_pitch < (size_t)w * bpp || frame_pitch < row_pitch * (size_t)h
+        || ((uintptr_t)d_out & 15) || ((uintptr_t)d_frames & 7) || (src_frame_bytes & 7) || (frame_pitch & 15))
+        return RTJGPU_E_ARG;
+    const size_t ysz = (size_t)w * h;
+    const size_t need = kind == RTJ_CONV_RGB8 ? ysz : kind == RTJ_CONV_YUV422_RGB24 ? 2 * ysz : ysz + ysz / 2;
+    if (src_frame_bytes < need) return RTJGPU_E_ARG;
+    CK(ctx, cudaSetDevice(ctx->device));
+    const int e = rtj_launch_convert(kind, d_frames, src_frame_bytes, F, w, h, d_out, row_pitch, frame_pitch,
+                                     (unsigned)alpha, cuda_stream);
+    if (e) { ctx->last_cuda = e; return RTJGPU_E_CUDA; }
+    ctx->launches += 1;
     return RTJGPU_OK;
 }
 

@@ -131,6 +131,10 @@ int rtj_launch_idct(const rtj_launch_args *a, void *stream);
 size_t rtj_lut_bytes(int fmt, int w, int h);
 int rtj_launch_build_lut(int fmt, int w, int h, void *d_lut, void *stream);
 int rtj_idct_init(void);      /* rtj_idct.cu */
+/* rtj_convert.cu: returns a cudaError */
+int rtj_launch_convert(int kind, const uint8_t *d_src, size_t src_frame_bytes, int F, int w, int h,
+                       uint8_t *d_out, size_t row_pitch, size_t frame_pitch, unsigned alpha, void *stream);
+int rtj_convert_bpp(int kind);
 int rtj_kernels_init(void);   /* one-time function attributes (dynamic shared memory opt-in) */
 
 #ifdef __cplusplus

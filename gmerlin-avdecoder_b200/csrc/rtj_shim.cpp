@@ -161,6 +161,62 @@ void RTjpeg_set_tables(RTjpeg_t *rtj, uint32_t *tables)
     in->st.table = RTJGPU_TABLE_CUSTOM;      /* quality (rtj->Q) is left alone, lib/RTjpeg.c:2380-2395 */
 }
 
+} // extern "C"
+
+namespace {
+
+/* One picture through a device converter: planes -> pinned staging -> device -> converter -> pinned -> rows.
+ * The 32-bit kinds run as their 24-bit twins and are spread out here, so that the fourth byte of the caller's
+ * pixels stays as it is (lib/RTjpeg.c:3147). */
+void convert_rows(Instance *in, int kind, uint8_t **planes, uint8_t **rows)
+{
+    if (!in || !planes || !rows) return;
+    const int w = in->st.width, h = in->st.height;
+    if (w <= 0 || h <= 0 || (w & 15) || (h & 15)) { in->err = RTJGPU_E_SIZE; return; }
+    const bool wide = kind == RTJ_CONV_RGB32 || kind == RTJ_CONV_BGR32;
+    const int dkind = kind == RTJ_CONV_RGB32 ? RTJ_CONV_RGB24 : kind == RTJ_CONV_BGR32 ? RTJ_CONV_BGR24 : kind;
+    const int bpp = rtjgpu_convert_bpp(dkind);
+    const size_t ysz = (size_t)w * h;
+    const size_t csz = kind == RTJ_CONV_RGB8 ? 0 : kind == RTJ_CONV_YUV422_RGB24 ? ysz / 2 : ysz / 4;
+    const size_t src_bytes = ysz + 2 * csz, row_bytes = (size_t)w * bpp, out_bytes = row_bytes * h;
+    /* the staging pair holds source and result side by side */
+    if (ensure(in, 16, src_bytes + out_bytes)) { in->err = RTJGPU_E_CUDA; return; }
+    memcpy(in->h_frame, planes[0], ysz);
+    if (csz) {
+        memcpy(in->h_frame + ysz, planes[1], csz);
+        memcpy(in->h_frame + ysz + csz, planes[2], csz);
+    }
+    cudaStream_t s = in->stream;
+    uint8_t *d_rgb = in->d_frame + src_bytes, *h_rgb = in->h_frame + src_bytes;       /* src_bytes is a multiple of 64 */
+    if (cudaMemcpyAsync(in->d_frame, in->h_frame, src_bytes, cudaMemcpyHostToDevice, s) != cudaSuccess) { in->err = RTJGPU_E_CUDA; return; }
+    const int rc = rtjgpu_convert_device(in->ctx, dkind, in->d_frame, src_bytes, 1, w, h, d_rgb, row_bytes, out_bytes, 0, s);
+    if (rc) { in->err = rc; return; }
+    if (cudaMemcpyAsync(h_rgb, d_rgb, out_bytes, cudaMemcpyDeviceToHost, s) != cudaSuccess
+        || cudaStreamSynchronize(s) != cudaSuccess) { in->err = RTJGPU_E_CUDA; return; }
+    for (int r = 0; r < h; r++) {
+        const uint8_t *src = h_rgb + (size_t)r * row_bytes;
+        uint8_t *dst = rows[r];
+        if (!wide) { memcpy(dst, src, row_bytes); continue; }
+        for (int x = 0; x < w; x++) {
+            dst[4 * x] = src[3 * x];
+            dst[4 * x + 1] = src[3 * x + 1];
+            dst[4 * x + 2] = src[3 * x + 2];
+        }
+    }
+}
+
+} // namespace
+
+extern "C" {
+
+void RTjpeg_yuv420rgb32(RTjpeg_t *rtj, uint8_t **planes, uint8_t **rows) { convert_rows(static_cast<Instance *>(rtj), RTJ_CONV_RGB32, planes, rows); }
+void RTjpeg_yuv420bgr32(RTjpeg_t *rtj, uint8_t **planes, uint8_t **rows) { convert_rows(static_cast<Instance *>(rtj), RTJ_CONV_BGR32, planes, rows); }
+void RTjpeg_yuv420rgb24(RTjpeg_t *rtj, uint8_t **planes, uint8_t **rows) { convert_rows(static_cast<Instance *>(rtj), RTJ_CONV_RGB24, planes, rows); }
+void RTjpeg_yuv420bgr24(RTjpeg_t *rtj, uint8_t **planes, uint8_t **rows) { convert_rows(static_cast<Instance *>(rtj), RTJ_CONV_BGR24, planes, rows); }
+void RTjpeg_yuv420rgb16(RTjpeg_t *rtj, uint8_t **planes, uint8_t **rows) { convert_rows(static_cast<Instance *>(rtj), RTJ_CONV_RGB16, planes, rows); }
+void RTjpeg_yuv420rgb8(RTjpeg_t *rtj, uint8_t **planes, uint8_t **rows) { convert_rows(static_cast<Instance *>(rtj), RTJ_CONV_RGB8, planes, rows); }
+void RTjpeg_yuv422rgb24(RTjpeg_t *rtj, uint8_t **planes, uint8_t **rows) { convert_rows(static_cast<Instance *>(rtj), RTJ_CONV_YUV422_RGB24, planes, rows); }
+
 int RTjpeg_b200_last_error(RTjpeg_t *rtj)
 {
     Instance *in = static_cast<Instance *>(rtj);

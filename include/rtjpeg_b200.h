@@ -38,6 +38,15 @@ typedef void RTjpeg_t;
 #define RTJ_YUV422 1
 #define RTJ_RGB8   2
 
+/* The colour converters of include/RTjpeg.h:128-136, as numbered by rtjgpu_convert_device. */
+#define RTJ_CONV_RGB32        0   /* RTjpeg_yuv420rgb32, lib/RTjpeg.c:3123: R G B x */
+#define RTJ_CONV_BGR32        1   /* RTjpeg_yuv420bgr32, :3192: B G R x */
+#define RTJ_CONV_RGB24        2   /* RTjpeg_yuv420rgb24, :3261 */
+#define RTJ_CONV_BGR24        3   /* RTjpeg_yuv420bgr24, :3326 */
+#define RTJ_CONV_RGB16        4   /* RTjpeg_yuv420rgb16, :3391: 5-6-5, low byte first */
+#define RTJ_CONV_RGB8         5   /* RTjpeg_yuv420rgb8, :3477: the luma plane */
+#define RTJ_CONV_YUV422_RGB24 6   /* RTjpeg_yuv422rgb24, :3077 */
+
 /* Fixed packet header length, include/RTjpeg.h:139 (RTJPEG_HEADER_SIZE). */
 #define RTJPEG_B200_HEADER_BYTES 12
 
@@ -179,6 +188,18 @@ int  rtjgpu_set_scan_mode(rtjgpu_ctx *ctx, int mode);
  * come out as tight planes: YUV420 w*h*3/2 bytes (Y, U, V), YUV422 w*h*2 bytes (Y, then U and V of
  * (w/2) x h), grey w*h bytes.  Width and height must be multiples of 16 in every format here. */
 int  rtjgpu_set_format(rtjgpu_ctx *ctx, int format);
+
+/* The converters above over a batch that is resident on the device -- typically the frames
+ * rtjgpu_decode_device has just written.  d_frames: F tight pictures src_frame_bytes apart (Y, then Cb and Cr:
+ * quarter size for the yuv420 kinds, half size for RTJ_CONV_YUV422_RGB24, unused by RTJ_CONV_RGB8).  Picture row r
+ * of frame f goes to d_out + f * frame_pitch + r * row_pitch; row_pitch must be a multiple of 16.  Unlike the
+ * reference, which steps over the fourth byte of a 32-bit pixel (lib/RTjpeg.c:3147), this call writes `alpha`
+ * there.  Runs on cuda_stream. */
+int  rtjgpu_convert_device(rtjgpu_ctx *ctx, int kind, const uint8_t *d_frames, size_t src_frame_bytes,
+                           int F, int w, int h, uint8_t *d_out, size_t row_pitch, size_t frame_pitch,
+                           int alpha, void *cuda_stream);
+/* Bytes per pixel a converter writes (4, 3, 2 or 1); 0 for an unknown kind. */
+int  rtjgpu_convert_bpp(int kind);
 
 /* Raw (pre-AAN) tables for RTJGPU_TABLE_CUSTOM, the set_tables path. */
 int  rtjgpu_set_custom_tables(rtjgpu_ctx *ctx, const uint32_t raw[128]);

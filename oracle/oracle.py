@@ -457,3 +457,41 @@ def encode_clip_fmt(w: int, h: int, Q: int, F: int, fmt: int, key_rate: int = -1
     s, o = encode_clip(src, F, threads=1)
     frames = frames_in_format(ref_decode_seq(s, o, w, h), w, h, fmt)
     return encode_frames_fmt(make_clip(w, h, Q, key_rate, lm, cm), fmt, frames)
+
+
+# ---- colour converters (RTjpeg.c:3071-3486) ---------------------------------------------------
+
+CONV_RGB32, CONV_BGR32, CONV_RGB24, CONV_BGR24, CONV_RGB16, CONV_RGB8, CONV_YUV422_RGB24 = range(7)
+CONV_BPP = (4, 4, 3, 3, 2, 1, 3)
+
+
+def _convert(fn, kind: int, frame: np.ndarray, w: int, h: int, pitch: int | None, fill: int) -> np.ndarray:
+    frame = _np_u8(frame)
+    pitch = w * CONV_BPP[kind] if pitch is None else pitch
+    ysz = w * h
+    csz = ysz // 2 if kind == CONV_YUV422_RGB24 else ysz // 4
+    if kind == CONV_RGB8:
+        assert frame.size >= ysz
+    else:
+        assert frame.size >= ysz + 2 * csz
+    out = np.full(h * pitch, fill, dtype=np.uint8)
+    base = frame.ctypes.data
+    fn(kind, w, h, C.cast(base, _u8p), C.cast(base + ysz, _u8p), C.cast(base + ysz + csz, _u8p), _ptr(out), pitch)
+    return out.reshape(h, pitch)
+
+
+def convert(kind: int, frame: np.ndarray, w: int, h: int, pitch: int | None = None, fill: int = 0) -> np.ndarray:
+    """Restatement of the reference's converter `kind` over one tight picture; bytes the converter does not
+    write (the fourth byte of a 32-bit pixel, row padding) keep the value `fill`."""
+    L = oracle_lib()
+    L.rtjo_convert.argtypes = [C.c_int, C.c_int, C.c_int, _u8p, _u8p, _u8p, _u8p, C.c_size_t]
+    L.rtjo_convert.restype = None
+    return _convert(L.rtjo_convert, kind, frame, w, h, pitch, fill)
+
+
+def ref_convert(kind: int, frame: np.ndarray, w: int, h: int, pitch: int | None = None, fill: int = 0) -> np.ndarray:
+    """The unmodified reference's converter (RTjpeg_yuv420rgb32 ...)."""
+    L = ref_lib()
+    L.refdrv_convert.argtypes = [C.c_int, C.c_int, C.c_int, _u8p, _u8p, _u8p, _u8p, C.c_size_t]
+    L.refdrv_convert.restype = None
+    return _convert(L.refdrv_convert, kind, frame, w, h, pitch, fill)

@@ -410,3 +410,40 @@ void refdrv_decode_seq_fmt(const uint8_t *stream, const uint64_t *offsets, int F
     ref_RTjpeg_close(d);
     free(pl_mem);
 }
+
+/* ------------------------------------------------------------------ */
+/* colour converters                                                   */
+/* ------------------------------------------------------------------ */
+
+extern void ref_RTjpeg_yuv420rgb32(RTjpeg_t *, uint8_t **, uint8_t **);
+extern void ref_RTjpeg_yuv420bgr32(RTjpeg_t *, uint8_t **, uint8_t **);
+extern void ref_RTjpeg_yuv420rgb24(RTjpeg_t *, uint8_t **, uint8_t **);
+extern void ref_RTjpeg_yuv420bgr24(RTjpeg_t *, uint8_t **, uint8_t **);
+extern void ref_RTjpeg_yuv420rgb16(RTjpeg_t *, uint8_t **, uint8_t **);
+extern void ref_RTjpeg_yuv420rgb8(RTjpeg_t *, uint8_t **, uint8_t **);
+extern void ref_RTjpeg_yuv422rgb24(RTjpeg_t *, uint8_t **, uint8_t **);
+
+/* The reference's converter `kind` (numbered as in rtjpeg_oracle.c) over one picture given as tight planes
+ * y, u, v; picture row r goes to out + r * pitch. */
+void refdrv_convert(int kind, int w, int h, const uint8_t *y, const uint8_t *u, const uint8_t *v,
+                    uint8_t *out, size_t pitch)
+{
+    RTjpeg_t *d = ref_RTjpeg_init();
+    int ww = w, hh = h;
+    ref_RTjpeg_set_size(d, &ww, &hh);
+    uint8_t *pl[3] = {(uint8_t *)y, (uint8_t *)u, (uint8_t *)v};
+    uint8_t **rows = (uint8_t **)malloc(sizeof(uint8_t *) * (size_t)h);
+    for (int r = 0; r < h; r++) rows[r] = out + (size_t)r * pitch;
+    switch (kind) {
+    case 0: ref_RTjpeg_yuv420rgb32(d, pl, rows); break;
+    case 1: ref_RTjpeg_yuv420bgr32(d, pl, rows); break;
+    case 2: ref_RTjpeg_yuv420rgb24(d, pl, rows); break;
+    case 3: ref_RTjpeg_yuv420bgr24(d, pl, rows); break;
+    case 4: ref_RTjpeg_yuv420rgb16(d, pl, rows); break;
+    case 5: ref_RTjpeg_yuv420rgb8(d, pl, rows); break;
+    case 6: ref_RTjpeg_yuv422rgb24(d, pl, rows); break;
+    default: break;
+    }
+    free(rows);
+    ref_RTjpeg_close(d);
+}

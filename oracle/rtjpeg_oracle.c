@@ -357,3 +357,61 @@ long rtjo_decode_packet_fmt(rtjo_decoder *d, int fmt, const uint8_t *pkt, size_t
     }
     return (long)at;
 }
+
+/* ------------------------------------------------------------------ */
+/* colour converters (RTjpeg.c:3071-3486)                              */
+/* ------------------------------------------------------------------ */
+
+/* The fixed-point matrix of RTjpeg.c:3071-3075: 16 fractional bits, luma offset 16, chroma offset 128. */
+enum { RTJO_KY = 76284, RTJO_KCRR = 76284, RTJO_KCRG = 53281, RTJO_KCBG = 25625, RTJO_KCBB = 132252 };
+
+static inline uint8_t sat8(int32_t v) { return (uint8_t)(v > 255 ? 255 : (v < 0 ? 0 : v)); }
+
+/* one pixel: y, and the chroma pair shared by its 2x1 (4:2:2) or 2x2 (4:2:0) neighbourhood; u = planes[1] is Cb,
+ * v = planes[2] is Cr (:3084-3085, :3097-3100) */
+static inline void px_rgb(int yv, int cb, int cr, uint8_t *r, uint8_t *g, uint8_t *b)
+{
+    int32_t y = (yv - 16) * RTJO_KY;
+    *r = sat8((y + (cr - 128) * RTJO_KCRR) >> 16);
+    *g = sat8((y - (cr - 128) * RTJO_KCRG - (cb - 128) * RTJO_KCBG) >> 16);
+    *b = sat8((y + (cb - 128) * RTJO_KCBB) >> 16);
+}
+
+size_t rtjo_convert_bpp(int kind)
+{
+    static const size_t bpp[7] = {4, 4, 3, 3, 2, 1, 3};
+    return kind >= 0 && kind < 7 ? bpp[kind] : 0;
+}
+
+/* kind: 0 yuv420rgb32 (:3123) 1 yuv420bgr32 (:3192) 2 yuv420rgb24 (:3261) 3 yuv420bgr24 (:3326)
+ *       4 yuv420rgb16 (:3391) 5 yuv420rgb8 (:3477, the luma plane copied) 6 yuv422rgb24 (:3077).
+ * Row r of the picture is written at out + r * pitch; the fourth byte of a 32-bit pixel is not written,
+ * exactly as the reference steps over it (:3147, :3157, ...). */
+void rtjo_convert(int kind, int w, int h, const uint8_t *y, const uint8_t *u, const uint8_t *v,
+                  uint8_t *out, size_t pitch)
+{
+    const int cw = w >> 1;
+    for (int r = 0; r < h; r++) {
+        uint8_t *o = out + (size_t)r * pitch;
+        const uint8_t *yr = y + (size_t)r * w;
+        if (kind == 5) { memcpy(o, yr, (size_t)w); continue; }
+        const size_t crow = (size_t)(kind == 6 ? r : r >> 1) * cw;        /* 4:2:2 chroma has the full height */
+        for (int x = 0; x < w; x++) {
+            uint8_t R, G, B;
+            px_rgb(yr[x], u[crow + (x >> 1)], v[crow + (x >> 1)], &R, &G, &B);
+            switch (kind) {
+            case 0: o[4 * x] = R; o[4 * x + 1] = G; o[4 * x + 2] = B; break;
+            case 1: o[4 * x] = B; o[4 * x + 1] = G; o[4 * x + 2] = R; break;
+            case 2: case 6: o[3 * x] = R; o[3 * x + 1] = G; o[3 * x + 2] = B; break;
+            case 3: o[3 * x] = B; o[3 * x + 1] = G; o[3 * x + 2] = R; break;
+            case 4: {                                                       /* 5-6-5, low byte first (:3420-3425) */
+                int t = (B >> 3) | ((G >> 2) << 5) | ((R >> 3) << 11);
+                o[2 * x] = (uint8_t)(t & 0xff);
+                o[2 * x + 1] = (uint8_t)(t >> 8);
+                break;
+            }
+            default: break;
+            }
+        }
+    }
+}

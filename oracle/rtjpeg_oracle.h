@@ -72,6 +72,11 @@ size_t rtjo_frame_bytes(int fmt, int w, int h);
 long rtjo_decode_packet_fmt(rtjo_decoder *d, int fmt, const uint8_t *pkt, size_t pkt_len,
                             uint8_t *y, uint8_t *u, uint8_t *v);
 
+/* Colour converters of RTjpeg.c:3071-3486 (RTjpeg_yuv420rgb32 ... RTjpeg_yuv422rgb24), see rtjpeg_oracle.c. */
+size_t rtjo_convert_bpp(int kind);
+void rtjo_convert(int kind, int w, int h, const uint8_t *y, const uint8_t *u, const uint8_t *v,
+                  uint8_t *out, size_t pitch);
+
 #ifdef __cplusplus
 }
 #endif

@@ -129,6 +129,19 @@ def fmt_case(name, fmt, w, h, Q, F, key_rate=-1, lm=0, cm=0, init_fill=0, **kw):
     print(f"{name}: {F} frames, {stream.size} stream bytes")
 
 
+def convert_case(seed=21):
+    """The colour converters (lib/RTjpeg.c:3077-3486) over one full-range random picture per chroma layout."""
+    rng = np.random.default_rng(seed)
+    w, h = 48, 32
+    pic420 = rng.integers(0, 256, w * h * 3 // 2).astype(np.uint8)
+    pic422 = rng.integers(0, 256, w * h * 2).astype(np.uint8)
+    names = ["rgb32", "bgr32", "rgb24", "bgr24", "rgb16", "rgb8", "yuv422rgb24"]
+    d = {n: O.ref_convert(k, pic422 if k == O.CONV_YUV422_RGB24 else pic420, w, h, fill=0x5A) for k, n in enumerate(names)}
+    np.savez_compressed(os.path.join(OUT, "convert_48x32.npz"), pic420=pic420, pic422=pic422,
+                        sha420=hashlib.sha256(pic420.tobytes()).hexdigest()[:16], **d)
+    print("convert_48x32: 7 converters")
+
+
 if __name__ == "__main__":
     O.build()
     assert O.have_ref(), "needs /root/reference"
@@ -141,6 +154,7 @@ if __name__ == "__main__":
     random_case("random_48x32", 48, 32, [1, 32, 170, 171, 200, 228, 255])
     tables_case()
     set_tables_case()
+    convert_case()
     fmt_case("yuv422_inter_64x48_q200_gop4", 1, 64, 48, 200, 9, key_rate=3, lm=2, cm=2, noise_y=30, noise_c=8, init_fill=0x55)
     fmt_case("yuv422_intra_96x32_q128", 1, 96, 32, 128, 3, noise_y=6, noise_c=3)
     fmt_case("grey_inter_64x48_q255_gop4", 2, 64, 48, 255, 9, key_rate=3, lm=2, cm=2, noise_y=40, init_fill=0x55)

@@ -473,9 +473,11 @@ struct K2Params {
     unsigned hardq_cap;              /* entries of hardq: F * nblk */
     rtj_dev_info *info;
     const uint32_t *pos;             /* SINGLE: pic_pos of every position of a row, i | off << 16 (rtj_build_lut_kernel) */
+    int ahead;                       /* frames between a CTA and the one that follows it on the same SM slot */
 };
 
 constexpr int K2_WARPS = IDCT_THREADS / 32;
+constexpr int K2_PF_LINES = 12;                   /* 128-byte lines of payload asked into L2 for the CTA that follows */
 constexpr int K2_ROUNDS_MAX = (IDCT_MAX_MB * 6 + IDCT_THREADS - 1) / IDCT_THREADS;     /* 6 */
 constexpr int K2_WQ = K2_ROUNDS_MAX * 32;          /* queue slots of one warp: every block it looked at */
 
@@ -508,6 +510,11 @@ rtj_idct_kernel(const K2Params P)
     const unsigned strip_blk0 = (unsigned)(my * mbw + mx0) * (unsigned)G::BLK;
     const unsigned frame_blk0 = f * (unsigned)P.nblk + strip_blk0;   /* F * nblk < 2^32 (checked by the host) */
     const uint32_t *my_ent = P.ent + frame_blk0;
+    /* A CTA lives a few microseconds, of which the first read of its entries from DRAM -- under the write traffic of
+     * this kernel -- is a good part.  So it asks for the entries of the CTA that will take its place when it retires
+     * (same strip, P.ahead frames on) into L2 now. */
+    if (f + (unsigned)P.ahead < gridDim.y && tid * 32 < nb)
+        asm volatile("prefetch.global.L2 [%0];" :: "l"(my_ent + (size_t)P.ahead * (unsigned)P.nblk + tid * 32));
 
     uint8_t *tile = smem;                                            /* TILE * mbs bytes: Y, U, V */
     int *s_hard = reinterpret_cast<int *>(tile + G::TILE * mbs);     /* HARD blocks of the strip, per warp */
@@ -608,6 +615,16 @@ rtj_idct_kernel(const K2Params P)
         }
         nfront += __popc(mM);
         nback += __popc(mB);
+    }
+    /* ... and the part of that frame's payload where its blocks of this row should lie, if the payload is spread
+     * evenly over the rows: the M7 blocks read it */
+    if (f + (unsigned)P.ahead < gridDim.y && warp == K2_WARPS - 1 && lane < K2_PF_LINES) {
+        const rtjgpu_frame_desc nd = P.desc[f + (unsigned)P.ahead];
+        const unsigned rows_total = SINGLE ? gridDim.x : gridDim.x / (unsigned)P.nstrips;
+        const unsigned plen = nd.length > RTJPEG_B200_HEADER_BYTES ? nd.length - RTJPEG_B200_HEADER_BYTES : 0u;
+        const unsigned at = (unsigned)(((unsigned long long)plen * (unsigned)my) / rows_total);
+        const unsigned o = (at & ~127u) + (unsigned)lane * 128u;
+        if (o < plen) asm volatile("prefetch.global.L2 [%0];" :: "l"(P.stream + nd.offset + RTJPEG_B200_HEADER_BYTES + o));
     }
     /* ---- pass 2: the M7 blocks of all four warps pooled, 32 at a time (a macroblock row of typical
      *      material holds ~55 of them: two full passes of the flow graph instead of four part-filled
@@ -893,6 +910,10 @@ extern "C" int rtj_launch_idct(const rtj_launch_args *a, void *stream)
     P.fmt = fmt;
     P.pos = reinterpret_cast<const uint32_t *>(a->d_lut);
     dim3 grid((unsigned)(P.nstrips * uy), (unsigned)a->F);
+    {
+        const int resident = (g_sm_count > 0 ? g_sm_count : 148) * 8;
+        P.ahead = (resident + (int)grid.x - 1) / (int)grid.x;
+    }
     cudaError_t e = fmt == 0 ? k2_launch<0>(P, grid, st) : fmt == 1 ? k2_launch<1>(P, grid, st) : k2_launch<2>(P, grid, st);
     if (e != cudaSuccess) return (int)e;
     /* the queue's length is only known on the device: a fixed grid strides over it */

@@ -57,6 +57,11 @@ def main():
         src = list(csv.reader(ncu(rep, "--page", "source", "--kernel-name", "regex:" + base).splitlines()))
         if len(src) < 3:
             continue
+        # one listing per matching launch: keep the first
+        for j in range(2, len(src)):
+            if src[j] == src[1]:
+                src = src[:j - 1]
+                break
         h = src[1]
         isrc, iex, ism = h.index("Source"), h.index("Instructions Executed"), h.index("# Samples")
         mix = collections.Counter()

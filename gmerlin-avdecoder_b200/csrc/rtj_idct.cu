@@ -421,15 +421,16 @@ template <> struct Geo<2> {                 /* 8-bit grey: units of 8x8, luma on
 template <int FMT>
 __device__ __forceinline__ bool off_is_chroma(int off, int mbs) { return Geo<FMT>::PLANES == 3 && off >= Geo<FMT>::CHROMA_AT * mbs; }
 
+/* tile_s: the strip's address in the shared window (32 bit: one add per row, no generic pointers) */
 template <int FMT>
-__device__ __forceinline__ void store_block(uint8_t *tile, int off, int mbs, const uint32_t (&px)[16])
+__device__ __forceinline__ void store_block(unsigned tile_s, int off, int mbs, const uint32_t (&px)[16])
 {
-    uint8_t *dst = tile + off;
-    const int luma_pitch = Geo<FMT>::UNIT_W * mbs;
-    const int pitch = off_is_chroma<FMT>(off, mbs) ? luma_pitch / 2 : luma_pitch;
+    const unsigned luma_pitch = (unsigned)(Geo<FMT>::UNIT_W * mbs);
+    const unsigned pitch = off_is_chroma<FMT>(off, mbs) ? luma_pitch >> 1 : luma_pitch;
+    unsigned sa = tile_s + (unsigned)off;
 #pragma unroll
-    for (int r = 0; r < 8; r++)
-        *reinterpret_cast<uint2 *>(dst + r * pitch) = make_uint2(px[2 * r], px[2 * r + 1]);
+    for (int r = 0; r < 8; r++, sa += pitch)
+        asm volatile("st.shared.v2.u32 [%0], {%1, %2};" :: "r"(sa), "r"(px[2 * r]), "r"(px[2 * r + 1]) : "memory");
 }
 
 /* Where block i (stream order, whole frame) of frame f lives in the tight-pitch output planes. */
@@ -517,6 +518,7 @@ rtj_idct_kernel(const K2Params P)
         asm volatile("prefetch.global.L2 [%0];" :: "l"(my_ent + (size_t)P.ahead * (unsigned)P.nblk + tid * 32));
 
     uint8_t *tile = smem;                                            /* TILE * mbs bytes: Y, U, V */
+    const unsigned tile_s = (unsigned)__cvta_generic_to_shared(tile);
     int *s_hard = reinterpret_cast<int *>(tile + G::TILE * mbs);     /* HARD blocks of the strip, per warp */
     static_assert(K2_WARPS == 4, "s_hard holds four counters");
     uint32_t *wq_e = reinterpret_cast<uint32_t *>(s_hard + 8) + warp * K2_WQ;      /* this warp's queue: entries ... */
@@ -597,7 +599,7 @@ rtj_idct_kernel(const K2Params P)
         if (cls == CLS_T2) {
             uint32_t px[16];
             t2_pixels(x0, x1, q, packed, px);
-            store_block<FMT>(tile, pp.off, mbs, px);
+            store_block<FMT>(tile_s, pp.off, mbs, px);
         }
         const unsigned mM = __ballot_sync(FULL, cls == Q_M7);
         const unsigned mB = __ballot_sync(FULL, cls == Q_CARRY || cls == Q_HARD);
@@ -658,7 +660,7 @@ rtj_idct_kernel(const K2Params P)
         if (live) {
             uint32_t px[16];
             m7_pixels(x, packed, px);
-            store_block<FMT>(tile, off, mbs, px);
+            store_block<FMT>(tile_s, off, mbs, px);
         }
     }
     /* ---- CARRY blocks are copied from the picture before the batch, HARD blocks leave for
@@ -704,7 +706,7 @@ rtj_idct_kernel(const K2Params P)
 #pragma unroll
                     for (int r = 0; r < 16; r++) px[r] = 0;
                 }
-                store_block<FMT>(tile, off, mbs, px);
+                store_block<FMT>(tile_s, off, mbs, px);
             }
         }
     }

@@ -10,8 +10,9 @@
  *             the luma and under the chroma grammar (same SIMD-within-a-register token walk,
  *             shifted by the raw prefix and with the prefix taken off the positions to fill)
  *   compose   deltaMB(p) = length of a whole MACROBLOCK starting at p: L, L, L, L, C, C chained
- *   DP        chunks of MB_C bytes, one lane per chunk, right to left over macroblock starts,
- *             in a ring of 512 entries (a macroblock is at most 6 x 64 bytes long)
+ *   walk      chunks of MB_C bytes; for every position, where a parse starting a macroblock there leaves
+ *             its chunk and how many macroblocks it starts (512 entries per chunk; a macroblock is at
+ *             most 6 x 64 bytes long, so a parse can only land in the next chunk)
  *   chain     one thread, chunk to chunk; entries are macroblock boundaries, so no grammar
  *             state travels
  *   emit      every chunk lane walks its macroblocks and writes six entries for each
@@ -196,17 +197,27 @@ rtj_scan_mb_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc *
         }
         __syncthreads();
 
-        /* ---- DP over macroblock starts, one lane per chunk, right to left.  Ring entry: exit offset
-         *      (9 bits) | macroblocks started << 9 ---- */
-        if (tid < nch) {
-            uint16_t *ring = reinterpret_cast<uint16_t *>(sh.ring) + tid * MB_RING;
-            const int cq = tid * MB_C;
-            for (int k = 0; k < MB_C; k += 2) reinterpret_cast<uint32_t *>(ring)[k >> 1] = (uint32_t)k | ((uint32_t)(k + 1) << 16);
-            for (int qq = MB_C - 1; qq >= 0; --qq) {
-                const int n = qq + (int)sh.dmb[cq + 2 * tid + qq];
-                uint32_t v = ring[n & (MB_C - 1)] + (1u << 9);
-                if (cq + qq >= lim) v = 0;                                  /* nothing starts behind the payload */
-                ring[qq] = (uint16_t)v;
+        /* ---- for every position of the segment: where a parse that starts a macroblock there leaves its chunk,
+         *      and how many macroblocks it starts on the way.  Ring entry: exit offset (9 bits) | macroblocks << 9.
+         *      Every position walks its own chain -- a macroblock is 6 to 384 bytes long, so a chain has few links
+         *      (two or three in a dense stream), the walks are independent of each other and all threads take part;
+         *      a right-to-left recurrence over the 512 positions of a chunk would keep one lane per chunk busy. ---- */
+        {
+            uint16_t *rings = reinterpret_cast<uint16_t *>(sh.ring);
+            for (int q = tid; q < npos; q += MB_THREADS) {
+                const int c = q / MB_C, cend = (c + 1) * MB_C;
+                uint32_t v = 0;                                             /* nothing starts behind the payload */
+                if (q < lim) {
+                    int n = q, cnt = 0;
+                    for (;;) {
+                        n += (int)sh.dmb[n + 2 * c];
+                        cnt++;
+                        if (n >= cend) { v = (uint32_t)(n - cend); break; }
+                        if (n >= lim) break;                                /* the payload ends inside the chunk: exit 0 */
+                    }
+                    v |= (uint32_t)cnt << 9;
+                }
+                rings[c * MB_RING + (q & (MB_C - 1))] = (uint16_t)v;
             }
         }
         __syncthreads();

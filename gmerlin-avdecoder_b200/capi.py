@@ -119,6 +119,12 @@ def load_library() -> C.CDLL:
     L.rtjgpu_convert_device.argtypes = [vp, C.c_int, vp, C.c_size_t, C.c_int, C.c_int, C.c_int, vp, C.c_size_t, C.c_size_t,
                                         C.c_int, vp]
     L.rtjgpu_convert_bpp.argtypes = [C.c_int]
+    L.rtjgpu_encoder_set_quality.argtypes = [vp, C.c_int]
+    L.rtjgpu_encoder_set_intra.argtypes = [vp, C.c_int, C.c_int, C.c_int]
+    L.rtjgpu_encoder_reset.argtypes = [vp]
+    L.rtjgpu_encode_device.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp, C.c_size_t, vp, vp]
+    L.rtjgpu_get_encode_info.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_int)]
+    L.RTjpeg_compress.argtypes = [vp, _u8p, C.POINTER(_u8p)]
     for name in CONVERTERS:
         getattr(L, name).argtypes = [vp, C.POINTER(_u8p), C.POINTER(_u8p)]
         getattr(L, name).restype = None
@@ -304,6 +310,22 @@ class BatchContext:
                                              C.c_void_p(d_out), row_pitch, frame_pitch, alpha,
                                              C.c_void_p(cuda_stream or 0)), "rtjgpu_convert_device")
 
+    def encoder_config(self, quality: int, key_rate: int = 0, lm: int = 0, cm: int = 0) -> None:
+        """RTjpeg_set_quality + RTjpeg_set_intra on a fresh encoder (key counter 0, no block sent yet)."""
+        _check(self._L.rtjgpu_encoder_set_quality(self._h, quality), "rtjgpu_encoder_set_quality")
+        _check(self._L.rtjgpu_encoder_set_intra(self._h, key_rate, lm, cm), "rtjgpu_encoder_set_intra")
+        _check(self._L.rtjgpu_encoder_reset(self._h), "rtjgpu_encoder_reset")
+
+    def encode_device(self, d_frames: int, F: int, w: int, h: int, d_stream: int, capacity: int, d_offsets: int,
+                      cuda_stream: int | None = None) -> None:
+        _check(self._L.rtjgpu_encode_device(self._h, C.c_void_p(d_frames), F, w, h, C.c_void_p(d_stream), capacity,
+                                            C.c_void_p(d_offsets), C.c_void_p(cuda_stream or 0)), "rtjgpu_encode_device")
+
+    def encode_info(self):
+        b, o = C.c_uint64(), C.c_int()
+        _check(self._L.rtjgpu_get_encode_info(self._h, C.byref(b), C.byref(o)), "rtjgpu_get_encode_info")
+        return int(b.value), bool(o.value)
+
     def set_custom_tables(self, raw: np.ndarray) -> None:
         raw = np.ascontiguousarray(raw, dtype=np.uint32)
         assert raw.size == 128
@@ -428,6 +450,18 @@ class RTjpeg:
         w = int(pkt[6]) | int(pkt[7]) << 8
         h = int(pkt[8]) | int(pkt[9]) << 8
         return self._L.RTjpeg_b200_decompress_n(self._h, _u8(pkt), pkt.size, self._planes(planes, w, h))
+
+    def compress(self, planes: np.ndarray, w: int, h: int) -> np.ndarray:
+        """RTjpeg_compress: one tight picture in the current format -> one packet."""
+        fmt = getattr(self, "_fmt", 0)
+        ysz = w * h
+        csz = ysz // 4 if fmt == 0 else ysz // 2 if fmt == 1 else 0
+        assert planes.dtype == np.uint8 and planes.flags.c_contiguous
+        base = planes.ctypes.data
+        pl = (_u8p * 3)(C.cast(base, _u8p), C.cast(base + ysz, _u8p), C.cast(base + ysz + csz, _u8p))
+        out = np.zeros(12 + (w // 8) * (h // 8) * 2 * 64 + 64, dtype=np.uint8)
+        n = self._L.RTjpeg_compress(self._h, _u8(out), pl)
+        return out[:n].copy()
 
     def convert(self, kind: int, planes: np.ndarray, w: int, h: int, out: np.ndarray) -> None:
         """RTjpeg_yuv420rgb32 & co.: planes is one tight picture (Y|Cb|Cr), out a [h, pitch] byte array whose rows

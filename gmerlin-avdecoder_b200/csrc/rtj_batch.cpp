@@ -81,6 +81,20 @@ struct rtjgpu_ctx {
     size_t         d_host_carry_cap = 0;
     int            scan_mode = RTJGPU_SCAN_AUTO;
     int            format = RTJ_YUV420;
+    /* encoder: configuration, state between calls, workspace */
+    int            enc_quality = 0, enc_lb8 = 0, enc_cb8 = 0;
+    int            enc_key_rate = 0, enc_key_count = 0, enc_lm = 0, enc_cm = 0;
+    bool           enc_clear_old = true;
+    int            enc_w = 0, enc_h = 0, enc_fmt = -1;
+    int32_t       *d_enc_qt = nullptr;
+    int16_t       *d_enc_old = nullptr;       size_t enc_old_cap = 0;      /* blocks */
+    uint8_t       *d_enc_slots = nullptr;     size_t enc_blocks_cap = 0;   /* blocks of a batch */
+    uint8_t       *d_enc_lens = nullptr;
+    uint32_t      *d_enc_boff = nullptr;
+    uint32_t      *d_enc_fsize = nullptr;     size_t enc_frames_cap = 0;
+    uint64_t      *d_enc_total = nullptr;
+    uint64_t      *h_enc_total = nullptr;     /* pinned */
+    void          *enc_stream = nullptr;
     uint64_t       host_bad = 0;              /* overrun frames seen by the current rtjgpu_decode_host call */
 };
 
@@ -335,6 +349,14 @@ void rtjgpu_destroy(rtjgpu_ctx *ctx)
         if (s.stream) cudaStreamDestroy(s.stream);
     }
     if (ctx->d_host_carry) cudaFree(ctx->d_host_carry);
+    if (ctx->d_enc_qt) cudaFree(ctx->d_enc_qt);
+    if (ctx->d_enc_old) cudaFree(ctx->d_enc_old);
+    if (ctx->d_enc_slots) cudaFree(ctx->d_enc_slots);
+    if (ctx->d_enc_lens) cudaFree(ctx->d_enc_lens);
+    if (ctx->d_enc_boff) cudaFree(ctx->d_enc_boff);
+    if (ctx->d_enc_fsize) cudaFree(ctx->d_enc_fsize);
+    if (ctx->d_enc_total) cudaFree(ctx->d_enc_total);
+    if (ctx->h_enc_total) cudaFreeHost(ctx->h_enc_total);
     if (ctx->d_tables) cudaFree(ctx->d_tables);
     if (ctx->h_info_reset) cudaFreeHost(ctx->h_info_reset);
     if (ctx->h_info) cudaFreeHost(ctx->h_info);
@@ -357,6 +379,114 @@ int rtjgpu_set_format(rtjgpu_ctx *ctx, int format)
 {
     if (!ctx || format < RTJ_YUV420 || format > RTJ_RGB8) return RTJGPU_E_ARG;
     ctx->format = format;
+    return RTJGPU_OK;
+}
+
+/* ---- encoder ---------------------------------------------------------------------------------------- */
+
+int rtjgpu_encoder_set_quality(rtjgpu_ctx *ctx, int quality)
+{
+    if (!ctx) return RTJGPU_E_ARG;
+    CK(ctx, cudaSetDevice(ctx->device));
+    if (quality < 1) quality = 1;
+    if (quality > 255) quality = 255;
+    int32_t qt[128];
+    rtj_encoder_table_from_quality(quality, qt, &ctx->enc_lb8, &ctx->enc_cb8);
+    if (!ctx->d_enc_qt) CK(ctx, cudaMalloc(&ctx->d_enc_qt, sizeof(qt)));
+    if (ctx->enc_stream) CK(ctx, cudaStreamSynchronize((cudaStream_t)ctx->enc_stream));   /* a batch may still read the old tables */
+    CK(ctx, cudaMemcpy(ctx->d_enc_qt, qt, sizeof(qt), cudaMemcpyHostToDevice));
+    ctx->enc_quality = quality;
+    return RTJGPU_OK;
+}
+
+int rtjgpu_encoder_set_intra(rtjgpu_ctx *ctx, int key_rate, int lm, int cm)
+{
+    if (!ctx) return RTJGPU_E_ARG;
+    ctx->enc_key_rate = key_rate < 0 ? 0 : key_rate > 255 ? 255 : key_rate;
+    ctx->enc_lm = lm < 0 ? 0 : lm > 16 ? 16 : lm;
+    ctx->enc_cm = cm < 0 ? 0 : cm > 16 ? 16 : cm;
+    ctx->enc_clear_old = true;           /* lib/RTjpeg.c:2488: the stored blocks are cleared; the key counter is not touched */
+    return RTJGPU_OK;
+}
+
+int rtjgpu_encoder_reset(rtjgpu_ctx *ctx)
+{
+    if (!ctx) return RTJGPU_E_ARG;
+    ctx->enc_key_count = 0;
+    ctx->enc_clear_old = true;
+    return RTJGPU_OK;
+}
+
+int rtjgpu_encode_device(rtjgpu_ctx *ctx, const uint8_t *d_frames, int F, int w, int h,
+                         uint8_t *d_stream, size_t capacity, uint64_t *d_offsets, void *cuda_stream)
+{
+    if (!ctx || F < 0) return RTJGPU_E_ARG;
+    if (ctx->format != RTJ_YUV420 && ctx->format != RTJ_YUV422) return RTJGPU_E_FORMAT;
+    if (w <= 0 || h <= 0 || (w & 15) || (h & 15) || w > 65535 || h > 65535) return RTJGPU_E_SIZE;
+    if (F > RTJGPU_MAX_FRAMES_PER_BATCH) return RTJGPU_E_TOOBIG;
+    if (!d_offsets || (F && (!d_frames || !d_stream)) || ((uintptr_t)d_frames & 7) || ((uintptr_t)d_stream & 3)) return RTJGPU_E_ARG;
+    CK(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const size_t nblk = (size_t)RTJ_FMT_NBLK(ctx->format, w, h);
+    if (!ctx->d_enc_qt) {                /* never configured: the all-zero tables of a fresh RTjpeg_t (lib/RTjpeg.c:2499) */
+        CK(ctx, cudaMalloc(&ctx->d_enc_qt, 128 * sizeof(int32_t)));
+        CK(ctx, cudaMemset(ctx->d_enc_qt, 0, 128 * sizeof(int32_t)));
+    }
+    if (!ctx->d_enc_total) {
+        CK(ctx, cudaMalloc(&ctx->d_enc_total, 2 * sizeof(uint64_t)));
+        CK(ctx, cudaMallocHost(&ctx->h_enc_total, 2 * sizeof(uint64_t)));
+    }
+    if (ctx->enc_w != w || ctx->enc_h != h || ctx->enc_fmt != ctx->format) {
+        ctx->enc_w = w; ctx->enc_h = h; ctx->enc_fmt = ctx->format;
+        ctx->enc_clear_old = true;
+    }
+    int rc = grow_device(ctx, &ctx->d_enc_old, &ctx->enc_old_cap, nblk * 64);
+    if (rc) return rc;
+    if (ctx->enc_clear_old) {
+        CK(ctx, cudaMemsetAsync(ctx->d_enc_old, 0, nblk * 64 * sizeof(int16_t), st));
+        ctx->enc_clear_old = false;
+    }
+    ctx->enc_stream = cuda_stream;
+    if (F == 0) {
+        CK(ctx, cudaMemsetAsync(d_offsets, 0, sizeof(uint64_t), st));
+        CK(ctx, cudaMemsetAsync(ctx->d_enc_total, 0, 2 * sizeof(uint64_t), st));
+        return RTJGPU_OK;
+    }
+    const size_t nb = nblk * (size_t)F;
+    if (nb > ctx->enc_blocks_cap) {
+        if (ctx->d_enc_slots) cudaFree(ctx->d_enc_slots);
+        if (ctx->d_enc_lens) cudaFree(ctx->d_enc_lens);
+        if (ctx->d_enc_boff) cudaFree(ctx->d_enc_boff);
+        ctx->d_enc_slots = nullptr; ctx->d_enc_lens = nullptr; ctx->d_enc_boff = nullptr; ctx->enc_blocks_cap = 0;
+        CK(ctx, cudaMalloc(&ctx->d_enc_slots, nb * 64));
+        CK(ctx, cudaMalloc(&ctx->d_enc_lens, nb));
+        CK(ctx, cudaMalloc(&ctx->d_enc_boff, nb * sizeof(uint32_t)));
+        ctx->enc_blocks_cap = nb;
+    }
+    if ((rc = grow_device(ctx, &ctx->d_enc_fsize, &ctx->enc_frames_cap, (size_t)F))) return rc;
+    rtj_encode_args a;
+    a.d_frames = d_frames; a.F = F; a.w = w; a.h = h; a.fmt = ctx->format;
+    a.d_qt = ctx->d_enc_qt; a.lb8 = ctx->enc_lb8; a.cb8 = ctx->enc_cb8; a.quality = ctx->enc_quality;
+    a.key_rate = ctx->enc_key_rate; a.key_count0 = ctx->enc_key_count; a.lmask = ctx->enc_lm; a.cmask = ctx->enc_cm;
+    a.d_old = ctx->d_enc_old; a.d_slots = ctx->d_enc_slots; a.d_lens = ctx->d_enc_lens; a.d_boff = ctx->d_enc_boff;
+    a.d_fsize = ctx->d_enc_fsize; a.d_stream = d_stream; a.capacity = capacity; a.d_offsets = d_offsets;
+    a.d_total = ctx->d_enc_total;
+    const int e = rtj_launch_encode(&a, cuda_stream);
+    if (e < 0) { ctx->last_cuda = -e; return RTJGPU_E_CUDA; }
+    ctx->launches += (uint64_t)e;
+    if (ctx->enc_key_rate) ctx->enc_key_count = (ctx->enc_key_count + F) % (ctx->enc_key_rate + 1);
+    return RTJGPU_OK;
+}
+
+int rtjgpu_get_encode_info(rtjgpu_ctx *ctx, uint64_t *bytes, int *overflow)
+{
+    if (!ctx || !ctx->d_enc_total) return RTJGPU_E_ARG;
+    CK(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)ctx->enc_stream;
+    CK(ctx, cudaMemcpyAsync(ctx->h_enc_total, ctx->d_enc_total, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    CK(ctx, cudaStreamSynchronize(st));
+    if (bytes) *bytes = ctx->h_enc_total[0];
+    if (overflow) *overflow = ctx->h_enc_total[1] != 0;
     return RTJGPU_OK;
 }
 

@@ -71,6 +71,7 @@ extern const uint8_t rtj_zigzag[64];   /* position -> raster, lib/RTjpeg.c:59-74
 void rtj_table_from_quality(int Q, rtj_host_table *out);           /* lib/RTjpeg.c:2344-2369 + 1208-1217 */
 void rtj_table_from_raw(const uint32_t raw[128], rtj_host_table *out); /* lib/RTjpeg.c:2380-2395 */
 void rtj_table_to_device_layout(const rtj_host_table *in, rtj_dev_table *out);
+void rtj_encoder_table_from_quality(int Q, int32_t qt[128], int *lb8, int *cb8);   /* lib/RTjpeg.c:2344-2369 + 277-286 */
 
 /* Device counters of one batch (lives in device memory, mirrored on request). */
 typedef struct rtj_dev_info {
@@ -135,6 +136,25 @@ int rtj_idct_init(void);      /* rtj_idct.cu */
 int rtj_launch_convert(int kind, const uint8_t *d_src, size_t src_frame_bytes, int F, int w, int h,
                        uint8_t *d_out, size_t row_pitch, size_t frame_pitch, unsigned alpha, void *stream);
 int rtj_convert_bpp(int kind);
+
+/* rtj_encode.cu.  What one encode call needs on the device; all pointers device memory. */
+typedef struct rtj_encode_args {
+    const uint8_t *d_frames;       /* F tight pictures */
+    int            F, w, h, fmt;   /* fmt: RTJ_YUV420 or RTJ_YUV422 */
+    const int32_t *d_qt;           /* [128] quantiser multipliers, raster order, luma then chroma */
+    int            lb8, cb8, quality;
+    int            key_rate, key_count0, lmask, cmask;
+    int16_t       *d_old;          /* [nblk][64] the block last sent at every place: state between calls */
+    uint8_t       *d_slots;        /* [F][nblk][64] workspace: every block's bytes */
+    uint8_t       *d_lens;         /* [F][nblk] workspace */
+    uint32_t      *d_boff;         /* [F][nblk] workspace: byte offset of every block inside its packet's payload */
+    uint32_t      *d_fsize;        /* [F] workspace: packet sizes */
+    uint8_t       *d_stream;       /* out: packets back to back, each starting on a multiple of 4 */
+    size_t         capacity;
+    uint64_t      *d_offsets;      /* out: [F + 1] */
+    uint64_t      *d_total;        /* out: [2] bytes needed, 1 if they did not fit */
+} rtj_encode_args;
+int rtj_launch_encode(const rtj_encode_args *a, void *stream);      /* returns launches (> 0) or -cudaError */
 int rtj_kernels_init(void);   /* one-time function attributes (dynamic shared memory opt-in) */
 
 #ifdef __cplusplus

@@ -30,6 +30,7 @@ struct Instance {
     rtjgpu_state st = {0, 0, RTJGPU_TABLE_ZERO, 0};
     int          format = RTJ_YUV420;
     int          key = 0, lm = 0, cm = 0;
+    int          enc_quality = 0;              /* the quality the context's encoder tables stand for */
     int          err = 0;
     /* one-frame staging */
     uint8_t           *h_pkt = nullptr;  size_t h_pkt_cap = 0;    /* pinned */
@@ -140,6 +141,7 @@ int RTjpeg_set_intra(RTjpeg_t *rtj, int *key, int *lm, int *cm)
     if (*cm < 0) *cm = 0;
     if (*cm > 16) *cm = 16;
     in->key = *key; in->lm = *lm; in->cm = *cm;
+    rtjgpu_encoder_set_intra(in->ctx, in->key, in->lm, in->cm);
     return 0;
 }
 
@@ -208,6 +210,45 @@ void convert_rows(Instance *in, int kind, uint8_t **planes, uint8_t **rows)
 } // namespace
 
 extern "C" {
+
+/* include/RTjpeg.h:125, lib/RTjpeg.c:3488: one picture (tight planes of the size and format last set) -> one packet at
+ * sp; returns its size.  The packet is byte for byte the reference's; 0 and a sticky error when the format is the
+ * 8-bit one (see rtjgpu_encode_device) or the device fails. */
+int RTjpeg_compress(RTjpeg_t *rtj, uint8_t *sp, uint8_t **planes)
+{
+    Instance *in = static_cast<Instance *>(rtj);
+    if (!in || !sp || !planes) return 0;
+    const int w = in->st.width, h = in->st.height, fmt = in->format;
+    if (fmt != RTJ_YUV420 && fmt != RTJ_YUV422) { in->err = RTJGPU_E_FORMAT; return 0; }
+    if (w <= 0 || h <= 0 || (w & 15) || (h & 15)) { in->err = RTJGPU_E_SIZE; return 0; }
+    if (in->enc_quality != in->st.quality && in->st.quality) {          /* RTjpeg_set_quality, or a packet decoded since */
+        if (rtjgpu_encoder_set_quality(in->ctx, in->st.quality)) { in->err = RTJGPU_E_CUDA; return 0; }
+        in->enc_quality = in->st.quality;
+    }
+    const size_t ysz = (size_t)w * h, csz = fmt == RTJ_YUV420 ? ysz / 4 : ysz / 2, fsz = ysz + 2 * csz;
+    const size_t cap = (RTJPEG_B200_HEADER_BYTES + (size_t)RTJ_FMT_NBLK(fmt, w, h) * 64 + 15) & ~(size_t)15;
+    /* the staging pair holds the picture, then the packet, then the two offsets */
+    if (ensure(in, 16, fsz + cap + 16)) { in->err = RTJGPU_E_CUDA; return 0; }
+    memcpy(in->h_frame, planes[0], ysz);
+    memcpy(in->h_frame + ysz, planes[1], csz);
+    memcpy(in->h_frame + ysz + csz, planes[2], csz);
+    cudaStream_t s = in->stream;
+    uint8_t *d_pkt = in->d_frame + fsz;
+    uint64_t *d_off = reinterpret_cast<uint64_t *>(in->d_frame + fsz + cap);
+    if (cudaMemcpyAsync(in->d_frame, in->h_frame, fsz, cudaMemcpyHostToDevice, s) != cudaSuccess) { in->err = RTJGPU_E_CUDA; return 0; }
+    rtjgpu_set_format(in->ctx, fmt);
+    int rc = rtjgpu_encode_device(in->ctx, in->d_frame, 1, w, h, d_pkt, cap, d_off, s);
+    if (rc) { in->err = rc; return 0; }
+    uint64_t bytes = 0;
+    int overflow = 0;
+    if ((rc = rtjgpu_get_encode_info(in->ctx, &bytes, &overflow)) || overflow) { in->err = rc ? rc : RTJGPU_E_TOOBIG; return 0; }
+    if (cudaMemcpyAsync(in->h_frame + fsz, d_pkt, (size_t)bytes, cudaMemcpyDeviceToHost, s) != cudaSuccess
+        || cudaStreamSynchronize(s) != cudaSuccess) { in->err = RTJGPU_E_CUDA; return 0; }
+    const uint8_t *pk = in->h_frame + fsz;
+    const uint32_t ds = (uint32_t)pk[0] | (uint32_t)pk[1] << 8 | (uint32_t)pk[2] << 16 | (uint32_t)pk[3] << 24;
+    memcpy(sp, pk, ds);
+    return (int)ds;
+}
 
 void RTjpeg_yuv420rgb32(RTjpeg_t *rtj, uint8_t **planes, uint8_t **rows) { convert_rows(static_cast<Instance *>(rtj), RTJ_CONV_RGB32, planes, rows); }
 void RTjpeg_yuv420bgr32(RTjpeg_t *rtj, uint8_t **planes, uint8_t **rows) { convert_rows(static_cast<Instance *>(rtj), RTJ_CONV_BGR32, planes, rows); }

@@ -97,6 +97,28 @@ void rtj_table_from_quality(int Q, rtj_host_table *out)
     scale_by_aan(out->ciqt);
 }
 
+/* The encoder's quantiser multipliers for quality Q, raster order, luma then chroma, plus the raw-prefix lengths:
+ * RTjpeg_calc_tbls (lib/RTjpeg.c:2344-2369) followed by RTjpeg_dct_init (:277-286). */
+void rtj_encoder_table_from_quality(int Q, int32_t qt[128], int *lb8, int *cb8)
+{
+    if (Q < 1) Q = 1;
+    if (Q > 255) Q = 255;
+    const uint64_t scaled_q = (uint64_t)Q << 25;
+    int32_t lpre[64], cpre[64];
+    for (int i = 0; i < 64; i++) {
+        int32_t ql = (int32_t)((scaled_q / ((uint64_t)annexk_luma[i] << 16)) >> 3);
+        int32_t qc = (int32_t)((scaled_q / ((uint64_t)annexk_chroma[i] << 16)) >> 3);
+        lpre[i] = 65536 / ((ql ? ql : 1) << 3);
+        cpre[i] = 65536 / ((qc ? qc : 1) << 3);
+        ql = (65536 / lpre[i]) >> 3;
+        qc = (65536 / cpre[i]) >> 3;
+        qt[i] = (int32_t)(((uint64_t)ql << 32) / aan_factor(i >> 3, i & 7));
+        qt[64 + i] = (int32_t)(((uint64_t)qc << 32) / aan_factor(i >> 3, i & 7));
+    }
+    *lb8 = raw_prefix(lpre);
+    *cb8 = raw_prefix(cpre);
+}
+
 void rtjgpu_raw_tables_for_quality(int Q, uint32_t raw[128])
 {
     if (Q < 1) Q = 1;

@@ -11,10 +11,9 @@
  *   Level 2  a batch interface (many packets -> many frames in one call), which
  *            is what keeps a B200 busy; Level 1 is its one-frame special case.
  *
- * Scope: the decode half of lib/RTjpeg.c -- RTjpeg_decompress in its three
- * formats (YUV420, the one gmerlin-avdecoder's plugin uses, YUV422 and 8-bit
- * grey).  The encoder half and the colour converters are not part of this
- * library.
+ * Scope: lib/RTjpeg.c -- RTjpeg_decompress in its three formats (YUV420, the
+ * one gmerlin-avdecoder's plugin uses, YUV422 and 8-bit grey), the colour
+ * converters, and RTjpeg_compress for YUV420 and YUV422.
  */
 #ifndef RTJPEG_B200_H
 #define RTJPEG_B200_H
@@ -200,6 +199,25 @@ int  rtjgpu_convert_device(rtjgpu_ctx *ctx, int kind, const uint8_t *d_frames, s
                            int alpha, void *cuda_stream);
 /* Bytes per pixel a converter writes (4, 3, 2 or 1); 0 for an unknown kind. */
 int  rtjgpu_convert_bpp(int kind);
+
+/* ---- encoder: RTjpeg_compress (lib/RTjpeg.c:3488-3524) over a batch that is resident on the device ---------
+ * YUV420 and YUV422 (rtjgpu_set_format); the reference's 8-bit encoder reads outside its plane (:2627) and is not
+ * offered.  A context carries one encoder: its tables (rtjgpu_encoder_set_quality = RTjpeg_set_quality :2408), the
+ * inter-frame parameters (rtjgpu_encoder_set_intra = RTjpeg_set_intra :2455; key_rate 0 = every block coded), the
+ * key counter and the blocks last sent, which carry over from call to call exactly as in an RTjpeg_t.
+ * rtjgpu_encoder_reset puts counter and blocks back to those of a fresh instance. */
+int  rtjgpu_encoder_set_quality(rtjgpu_ctx *ctx, int quality);
+int  rtjgpu_encoder_set_intra(rtjgpu_ctx *ctx, int key_rate, int lm, int cm);
+int  rtjgpu_encoder_reset(rtjgpu_ctx *ctx);
+/* d_frames: F tight pictures of the context's format.  The packets (12-byte RTjpeg_frameheader + block stream, byte
+ * for byte what RTjpeg_compress writes) go to d_stream back to back, each starting on a multiple of 4 bytes, and
+ * d_offsets[0..F] (device memory) receives where each starts and where the last ends -- the layout rtjgpu_plan and
+ * rtjgpu_decode_device take.  When the packets do not fit `capacity` nothing is written; rtjgpu_get_encode_info tells.
+ * Asynchronous on cuda_stream. */
+int  rtjgpu_encode_device(rtjgpu_ctx *ctx, const uint8_t *d_frames, int F, int w, int h,
+                          uint8_t *d_stream, size_t capacity, uint64_t *d_offsets, void *cuda_stream);
+/* Waits for the last rtjgpu_encode_device: bytes its packets take, and whether they did not fit. */
+int  rtjgpu_get_encode_info(rtjgpu_ctx *ctx, uint64_t *bytes, int *overflow);
 
 /* Raw (pre-AAN) tables for RTJGPU_TABLE_CUSTOM, the set_tables path. */
 int  rtjgpu_set_custom_tables(rtjgpu_ctx *ctx, const uint32_t raw[128]);

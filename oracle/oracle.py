@@ -402,6 +402,12 @@ def encode_frames_fmt(clip: Clip, fmt: int, frames: np.ndarray, align: int = 16)
     L = ref_lib()
     frames = _np_u8(frames)
     F = frames.shape[0]
+    if fmt == 2:
+        # RTjpeg_compress8 / RTjpeg_mcompress8 read every block with a row stride of 8 * width (they hand RTjpeg_dctY the
+        # width where it expects width / 8, RTjpeg.c:2627, :3005): up to 56 rows behind the plane.  Give them zeros to read.
+        padded = np.zeros(frames.size + 64 * clip.w, dtype=np.uint8)
+        padded[:frames.size] = frames.reshape(-1)
+        frames = padded[:F * frames.shape[1]].reshape(F, -1)
     cap = (12 + (clip.w // 8) * (clip.h // 8) * 2 * 64 + 64 + align) * max(F, 1) + 64
     buf = np.zeros(cap, dtype=np.uint8)
     offs = np.empty(F + 1, dtype=np.uint64)
@@ -495,3 +501,41 @@ def ref_convert(kind: int, frame: np.ndarray, w: int, h: int, pitch: int | None 
     L.refdrv_convert.argtypes = [C.c_int, C.c_int, C.c_int, _u8p, _u8p, _u8p, _u8p, C.c_size_t]
     L.refdrv_convert.restype = None
     return _convert(L.refdrv_convert, kind, frame, w, h, pitch, fill)
+
+
+# ---- encoder (RTjpeg_compress, RTjpeg.c:3488-3524) --------------------------------------------
+
+class _Encoder(C.Structure):
+    _fields_ = [("fmt", C.c_int), ("width", C.c_int), ("height", C.c_int), ("Q", C.c_int),
+                ("lqt", C.c_int32 * 64), ("cqt", C.c_int32 * 64), ("lb8", C.c_int), ("cb8", C.c_int),
+                ("key_rate", C.c_int), ("key_count", C.c_int), ("lmask", C.c_int), ("cmask", C.c_int),
+                ("nblk", C.c_int), ("old", C.c_void_p)]
+
+
+def encode_frames_oracle(frames: np.ndarray, w: int, h: int, fmt: int, Q: int, key_rate: int = 0, lm: int = 0, cm: int = 0,
+                         align: int = 16):
+    """Restatement of RTjpeg_compress over tight pictures [F, frame_bytes(fmt)]; returns (stream, offsets) laid out like
+    encode_frames_fmt (packets `align`-aligned).  key_rate <= 0 is intra-only, as when RTjpeg_set_intra is never called."""
+    L = oracle_lib()
+    L.rtjo_encoder_init.argtypes = [C.POINTER(_Encoder), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.rtjo_encoder_free.argtypes = [C.POINTER(_Encoder)]
+    L.rtjo_encode_frame.argtypes = [C.POINTER(_Encoder), _u8p, _u8p, _u8p, _u8p]
+    L.rtjo_encode_frame.restype = C.c_long
+    frames = _np_u8(frames)
+    F = frames.shape[0]
+    ysz = w * h
+    csz = ysz // 4 if fmt == 0 else ysz // 2 if fmt == 1 else 0
+    e = _Encoder()
+    L.rtjo_encoder_init(C.byref(e), fmt, w, h, Q, max(key_rate, 0), lm, cm)
+    bound = 12 + (w // 8) * (h // 8) * 2 * 64 + 64
+    tmp = np.zeros(bound, dtype=np.uint8)
+    pkts = []
+    for f in range(F):
+        base = frames[f].ctypes.data
+        n = L.rtjo_encode_frame(C.byref(e), C.cast(base, _u8p), C.cast(base + ysz, _u8p), C.cast(base + ysz + csz, _u8p), _ptr(tmp))
+        if n < 0:
+            L.rtjo_encoder_free(C.byref(e))
+            raise ValueError("the 8-bit encoder of the reference reads outside its plane; not restated")
+        pkts.append(tmp[:n].copy())
+    L.rtjo_encoder_free(C.byref(e))
+    return pack_packets(pkts, align)

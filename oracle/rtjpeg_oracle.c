@@ -12,6 +12,7 @@
  */
 #include "rtjpeg_oracle.h"
 
+#include <stdlib.h>
 #include <string.h>
 
 /* zig-zag position -> raster index.  Same map as RTjpeg_ZZ (RTjpeg.c:59-74),
@@ -414,4 +415,183 @@ void rtjo_convert(int kind, int w, int h, const uint8_t *y, const uint8_t *u, co
             }
         }
     }
+}
+
+/* ------------------------------------------------------------------ */
+/* encoder (RTjpeg_compress, RTjpeg.c:3488-3524)                       */
+/* ------------------------------------------------------------------ */
+
+/* Quantiser tables of the encoder for quality Q: RTjpeg_calc_tbls (:2344-2361) makes lqt, liqt = 65536 / (lqt << 3)
+ * and folds liqt back into lqt = (65536 / liqt) >> 3; RTjpeg_dct_init (:277-286) then divides by the AAN factors. */
+void rtjo_encoder_tables(int Q, int32_t lqt[64], int32_t cqt[64], int *lb8, int *cb8)
+{
+    rtjo_tables t;
+    if (Q < 1) Q = 1;
+    if (Q > 255) Q = 255;
+    uint64_t qual = (uint64_t)Q << 25;
+    int32_t lpre[64], cpre[64];
+    for (int i = 0; i < 64; i++) {
+        int32_t lq = (int32_t)((qual / ((uint64_t)base_luma[i] << 16)) >> 3);
+        int32_t cq = (int32_t)((qual / ((uint64_t)base_chroma[i] << 16)) >> 3);
+        if (lq == 0) lq = 1;
+        if (cq == 0) cq = 1;
+        lpre[i] = 65536 / (lq << 3);
+        cpre[i] = 65536 / (cq << 3);
+        lq = (65536 / lpre[i]) >> 3;
+        cq = (65536 / cpre[i]) >> 3;
+        lqt[i] = (int32_t)(((uint64_t)lq << 32) / aan_q32[i]);
+        cqt[i] = (int32_t)(((uint64_t)cq << 32) / aan_q32[i]);
+    }
+    (void)t;
+    *lb8 = raw_prefix_len(lpre);
+    *cb8 = raw_prefix_len(cpre);
+}
+
+/* One 8-point pass of the forward transform (RTjpeg_dctY :303-340 rows, :346-389 columns): the flow graph is the
+ * same in both, only what is done with its eight results differs.  in: eight samples; e[0..7]: the results before
+ * the pass's own scaling -- e0 = s0 + s1 terms ... as laid out below. */
+static void fdct8(const int32_t x[8], int32_t *r0, int32_t *r4, int32_t *r2, int32_t *r6,
+                  int32_t *r5, int32_t *r3, int32_t *r1, int32_t *r7)
+{
+    int32_t t0 = x[0] + x[7], t7 = x[0] - x[7], t1 = x[1] + x[6], t6 = x[1] - x[6];
+    int32_t t2 = x[2] + x[5], t5 = x[2] - x[5], t3 = x[3] + x[4], t4 = x[3] - x[4];
+    int32_t t10 = t0 + t3, t13 = t0 - t3, t11 = t1 + t2, t12 = t1 - t2;
+    *r0 = t10 + t11;                     /* scaled by << 8 (rows) or DESCALE10 (columns) by the caller */
+    *r4 = t10 - t11;
+    int32_t z1 = (t12 + t13) * 181;
+    *r2 = (t13 << 8) + z1;
+    *r6 = (t13 << 8) - z1;
+    t10 = t4 + t5; t11 = t5 + t6; t12 = t6 + t7;
+    int32_t z5 = (t10 - t12) * 98, z2 = t10 * 139 + z5, z4 = t12 * 334 + z5, z3 = t11 * 181;
+    int32_t z11 = (t7 << 8) + z3, z13 = (t7 << 8) - z3;
+    *r5 = z13 + z2; *r3 = z13 - z2; *r1 = z11 + z4; *r7 = z11 - z4;
+}
+
+/* RTjpeg_dctY (:288-390) followed by RTjpeg_quant (:245-252): 8x8 samples at src (row pitch `pitch`) -> 64 quantised
+ * coefficients in raster order. */
+void rtjo_fdct_quant(const uint8_t *src, int pitch, const int32_t qt[64], int16_t out[64])
+{
+    int32_t ws[64];
+    for (int r = 0; r < 8; r++) {
+        int32_t x[8], a0, a4;
+        for (int c = 0; c < 8; c++) x[c] = src[(size_t)r * pitch + c];
+        fdct8(x, &a0, &a4, &ws[r * 8 + 2], &ws[r * 8 + 6], &ws[r * 8 + 5], &ws[r * 8 + 3], &ws[r * 8 + 1], &ws[r * 8 + 7]);
+        ws[r * 8 + 0] = a0 << 8;
+        ws[r * 8 + 4] = a4 << 8;
+    }
+    for (int c = 0; c < 8; c++) {
+        int32_t x[8], a0, a4, a2, a6, a5, a3, a1, a7;
+        for (int r = 0; r < 8; r++) x[r] = ws[r * 8 + c];
+        fdct8(x, &a0, &a4, &a2, &a6, &a5, &a3, &a1, &a7);
+        int16_t col[8];
+        col[0] = (int16_t)((a0 + 128) >> 8);            /* DESCALE10 */
+        col[4] = (int16_t)((a4 + 128) >> 8);
+        col[2] = (int16_t)((a2 + 32768) >> 16);         /* DESCALE20 */
+        col[6] = (int16_t)((a6 + 32768) >> 16);
+        col[5] = (int16_t)((a5 + 32768) >> 16);
+        col[3] = (int16_t)((a3 + 32768) >> 16);
+        col[1] = (int16_t)((a1 + 32768) >> 16);
+        col[7] = (int16_t)((a7 + 32768) >> 16);
+        for (int r = 0; r < 8; r++) out[r * 8 + c] = col[r];
+    }
+    for (int i = 0; i < 64; i++) out[i] = (int16_t)((out[i] * qt[i] + 32767) >> 16);
+}
+
+/* RTjpeg_b2s (:109-155): DC as an unsigned byte 0..254, bt8 raw signed bytes, then coefficients -64..63 and zero
+ * runs 63 + n.  Returns the bytes written (2 + bt8 .. 64). */
+int rtjo_pack_block(const int16_t blk[64], int bt8, uint8_t *out)
+{
+    const uint8_t *z = zz();
+    int co = 1, ci;
+    int v = blk[z[0]];
+    out[0] = (uint8_t)(v > 254 ? 254 : (v < 0 ? 0 : v));
+    for (ci = 1; ci <= bt8; ci++) {
+        v = blk[z[ci]];
+        out[co++] = (uint8_t)(int8_t)(v > 0 ? (v > 127 ? 127 : v) : (v < -128 ? -128 : v));
+    }
+    for (; ci < 64; ci++) {
+        v = blk[z[ci]];
+        if (v > 0) out[co++] = (uint8_t)(int8_t)(v > 63 ? 63 : v);
+        else if (v < 0) out[co++] = (uint8_t)(int8_t)(v < -64 ? -64 : v);
+        else {
+            int start = ci;
+            do ci++; while (ci < 64 && blk[z[ci]] == 0);
+            out[co++] = (uint8_t)(63 + (ci - start));
+            ci--;
+        }
+    }
+    return co;
+}
+
+void rtjo_encoder_init(rtjo_encoder *e, int fmt, int w, int h, int Q, int key_rate, int lm, int cm)
+{
+    memset(e, 0, sizeof(*e));
+    e->fmt = fmt; e->width = w; e->height = h;
+    e->Q = Q < 1 ? 1 : (Q > 255 ? 255 : Q);
+    rtjo_encoder_tables(e->Q, e->lqt, e->cqt, &e->lb8, &e->cb8);
+    /* RTjpeg_set_intra (:2455-2490) clamps and clears the previous blocks */
+    e->key_rate = key_rate < 0 ? 0 : (key_rate > 255 ? 255 : key_rate);
+    e->lmask = lm < 0 ? 0 : (lm > 16 ? 16 : lm);
+    e->cmask = cm < 0 ? 0 : (cm > 16 ? 16 : cm);
+    e->nblk = fmt == 0 ? (w >> 4) * (h >> 4) * 6 : fmt == 1 ? (w >> 4) * (h >> 3) * 4 : (w >> 3) * (h >> 3);
+    e->old = (int16_t *)calloc((size_t)e->nblk * 64, sizeof(int16_t));
+}
+
+void rtjo_encoder_free(rtjo_encoder *e) { free(e->old); e->old = NULL; }
+
+/* One picture (tight planes) -> one packet at out (12-byte header + block stream); returns its size.
+ * RTjpeg_compress (:3488-3524): key_rate == 0 codes every block (RTjpeg_compressYUV420 :2510-2563 and its siblings),
+ * otherwise every block is first compared with the block last SENT at its place (RTjpeg_bcomp :2827-2838: a block
+ * within +-mask of it in every coefficient becomes the byte 0xFF and leaves the stored block as it is) -- on "key"
+ * pictures too, against blocks of zeros (RTjpeg_mcompressYUV420 :2841-2922). */
+long rtjo_encode_frame(rtjo_encoder *e, const uint8_t *y, const uint8_t *u, const uint8_t *v, uint8_t *out)
+{
+    const int w = e->width, h = e->height, cw = w >> 1, fmt = e->fmt;
+    /* The 8-bit branch of the reference is not restated: RTjpeg_compress8 / RTjpeg_mcompress8 hand RTjpeg_dctY the
+     * picture width where it expects width / 8 (:2627, :3005; dctY steps rows by rskip << 3, :337), so every block
+     * is read with a row stride of 8 * width -- outside the plane for most of the picture.  Undefined there. */
+    if (fmt != 0 && fmt != 1) return -1;
+    const int inter = e->key_rate != 0;
+    if (inter && e->key_count == 0) memset(e->old, 0, (size_t)e->nblk * 64 * sizeof(int16_t));
+    uint8_t *sp = out + 12;
+    const int unit = fmt == 0 ? 6 : fmt == 1 ? 4 : 1, unit_luma = fmt == 0 ? 4 : fmt == 1 ? 2 : 1;
+    const int ux = fmt == 2 ? w >> 3 : w >> 4, uy = fmt == 0 ? h >> 4 : h >> 3;
+    int16_t blk[64];
+    int16_t *old = e->old;
+    for (int gy = 0; gy < uy; gy++)
+        for (int gx = 0; gx < ux; gx++)
+            for (int k = 0; k < unit; k++) {
+                const uint8_t *src;
+                int pitch;
+                if (k < unit_luma) {
+                    pitch = w;
+                    if (fmt == 0) src = y + (size_t)(gy * 16 + (k >> 1) * 8) * w + gx * 16 + (k & 1) * 8;
+                    else if (fmt == 1) src = y + (size_t)(gy * 8) * w + gx * 16 + k * 8;
+                    else src = y + (size_t)(gy * 8) * w + gx * 8;
+                } else {
+                    pitch = cw;
+                    src = (k == unit_luma ? u : v) + (size_t)(gy * 8) * cw + gx * 8;
+                }
+                const int luma = k < unit_luma;
+                rtjo_fdct_quant(src, pitch, luma ? e->lqt : e->cqt, blk);
+                int skip = 0;
+                if (inter) {
+                    const int mask = luma ? e->lmask : e->cmask;
+                    skip = 1;
+                    for (int i = 0; i < 64; i++)
+                        if (abs(old[i] - blk[i]) > mask) { skip = 0; break; }
+                    if (!skip) memcpy(old, blk, sizeof(blk));
+                    old += 64;
+                }
+                if (skip) *sp++ = 0xFF;
+                else sp += rtjo_pack_block(blk, luma ? e->lb8 : e->cb8, sp);
+            }
+    const long ds = (long)(sp - out);
+    out[0] = (uint8_t)ds; out[1] = (uint8_t)(ds >> 8); out[2] = (uint8_t)(ds >> 16); out[3] = (uint8_t)(ds >> 24);
+    out[4] = 12; out[5] = 0;
+    out[6] = (uint8_t)w; out[7] = (uint8_t)(w >> 8); out[8] = (uint8_t)h; out[9] = (uint8_t)(h >> 8);
+    out[10] = (uint8_t)e->Q;
+    out[11] = inter ? (uint8_t)e->key_count : 0;
+    if (inter && ++e->key_count > e->key_rate) e->key_count = 0;
+    return ds;
 }

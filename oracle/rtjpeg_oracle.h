@@ -72,6 +72,22 @@ size_t rtjo_frame_bytes(int fmt, int w, int h);
 long rtjo_decode_packet_fmt(rtjo_decoder *d, int fmt, const uint8_t *pkt, size_t pkt_len,
                             uint8_t *y, uint8_t *u, uint8_t *v);
 
+/* The encoder half (RTjpeg_compress, RTjpeg.c:3488-3524), see rtjpeg_oracle.c. */
+typedef struct {
+    int      fmt, width, height, Q;
+    int32_t  lqt[64], cqt[64];       /* quantiser multipliers, raster order, AAN-divided */
+    int      lb8, cb8;
+    int      key_rate, key_count, lmask, cmask;
+    int      nblk;
+    int16_t *old;                    /* the block last sent at every place, stream order */
+} rtjo_encoder;
+void rtjo_encoder_tables(int Q, int32_t lqt[64], int32_t cqt[64], int *lb8, int *cb8);
+void rtjo_fdct_quant(const uint8_t *src, int pitch, const int32_t qt[64], int16_t out[64]);
+int  rtjo_pack_block(const int16_t blk[64], int bt8, uint8_t *out);
+void rtjo_encoder_init(rtjo_encoder *e, int fmt, int w, int h, int Q, int key_rate, int lm, int cm);
+void rtjo_encoder_free(rtjo_encoder *e);
+long rtjo_encode_frame(rtjo_encoder *e, const uint8_t *y, const uint8_t *u, const uint8_t *v, uint8_t *out);
+
 /* Colour converters of RTjpeg.c:3071-3486 (RTjpeg_yuv420rgb32 ... RTjpeg_yuv422rgb24), see rtjpeg_oracle.c. */
 size_t rtjo_convert_bpp(int kind);
 void rtjo_convert(int kind, int w, int h, const uint8_t *y, const uint8_t *u, const uint8_t *v,

@@ -142,6 +142,21 @@ def convert_case(seed=21):
     print("convert_48x32: 7 converters")
 
 
+def encode_case():
+    """RTjpeg_compress (lib/RTjpeg.c:3488) over a short clip in both chroma layouts: the reference's packets, byte for byte."""
+    w, h, Q, kr, lm = 64, 48, 171, 3, 2
+    s, o = O.encode_clip(O.make_clip(w, h, 255, noise_y=20, noise_c=6, dark=1), 7, threads=1)
+    yuv = O.ref_decode_seq(s, o, w, h)
+    d = dict(Q=Q, key_rate=kr, lm=lm, cm=lm)
+    for fmt, key in ((0, "420"), (1, "422")):
+        pics = O.frames_in_format(yuv, w, h, fmt)
+        pics = np.concatenate([pics, pics[-1:]])
+        st, of = O.encode_frames_fmt(O.make_clip(w, h, Q, kr, lm, lm), fmt, pics)
+        d["pics" + key], d["stream" + key], d["offsets" + key] = pics, st, of
+    np.savez_compressed(os.path.join(OUT, "encode_64x48.npz"), **d)
+    print("encode_64x48: 8 pictures x 2 formats")
+
+
 if __name__ == "__main__":
     O.build()
     assert O.have_ref(), "needs /root/reference"
@@ -155,6 +170,7 @@ if __name__ == "__main__":
     tables_case()
     set_tables_case()
     convert_case()
+    encode_case()
     fmt_case("yuv422_inter_64x48_q200_gop4", 1, 64, 48, 200, 9, key_rate=3, lm=2, cm=2, noise_y=30, noise_c=8, init_fill=0x55)
     fmt_case("yuv422_intra_96x32_q128", 1, 96, 32, 128, 3, noise_y=6, noise_c=3)
     fmt_case("grey_inter_64x48_q255_gop4", 2, 64, 48, 255, 9, key_rate=3, lm=2, cm=2, noise_y=40, init_fill=0x55)

@@ -18,9 +18,9 @@
  *   chain     one thread hops chunk to chunk through the rings: the true entry point
  *             and first block index of every chunk (CS_S / CS_C dependent steps instead
  *             of one per block).
- *   emit      every chunk lane walks its own blocks from its now known entry point and
- *             writes their 32-bit entries to a shared staging area that leaves as
- *             coalesced stores.
+ *   emit      every chunk lane walks its own blocks from its now known entry point and notes
+ *             where each starts; the 32-bit entries are then made by all threads, one block
+ *             each, and written to the table as coalesced stores.
  *
  * Frames of any size stream through in segments of CS_S bytes; the entry point and the
  * block count carry from segment to segment.
@@ -272,7 +272,9 @@ rtj_scan_chunk_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_des
         }
         __syncthreads();
 
-        /* ---- emit ---- */
+        /* ---- emit, in two steps.  The chunk lanes only WALK their blocks (a load and an add per block) and note where
+         *      each starts; making the 32-bit entry of a block -- the longer part -- is then shared out evenly over all
+         *      threads, which also write the entries straight to the table, coalesced. ---- */
         const int nb1 = min(sh.nb, nblk);
         int q = 0, i = 0, qend = 0, myskips = 0, lastend = -1;
         if (tid < nch) {
@@ -280,34 +282,38 @@ rtj_scan_chunk_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_des
             i = (int)sh.base[tid];
             qend = min((tid + 1) * CS_C, lim);
         }
-        __syncthreads();                                   /* the rings are dead: their memory stages the entries */
-        for (int r0 = nb0; r0 < nb1; r0 += CS_STAGE) {
-            const int r1 = min(r0 + CS_STAGE, nb1);
+        __syncthreads();                                   /* the rings are dead: their memory holds the block starts */
+        uint16_t *starts = reinterpret_cast<uint16_t *>(sh.ring);
+        for (int r0 = nb0; r0 < nb1; r0 += 2 * CS_STAGE) {
+            const int r1 = min(r0 + 2 * CS_STAGE, nb1);
             if (tid < nch) {
                 while (q < qend && i < r1) {
-                    const int dl = delb[q + ((q / CS_C) << 2)];
-                    const uint32_t head = lds_u32_unaligned(sh.pay, q + mis);       /* DC, token 1, token 2, token 3 */
-                    const uint32_t last = payb[q + dl - 1];
-                    const bool isff = (head & 0xFFu) == 0xFFu;                      /* skipped block */
-                    /* positions >= eob are zero: a final run of n zeros ends at 64, so it starts at 64 - n */
-                    const int eob = (last - 64u) < 64u ? max(127 - (int)last, dl - 1) : 64;
-                    const uint32_t t1 = (head >> 8) & 0xFFu, t2 = (head >> 16) & 0xFFu;
-                    const uint32_t c1 = (eob >= 2 && (t1 - 64u) >= 64u) ? t1 : 0u;
-                    const uint32_t c2 = (eob >= 3 && (t2 - 64u) >= 64u) ? t2 : 0u;
-                    const uint32_t e_inl = RTJ_ENT_INLINE_BIT | (head & 0xFFu) | (c1 << 8) | (c2 << 16);
-                    const uint32_t e_gen = RTJ_ENT(seg0 + q, eob);
-                    sh.ring[i - r0] = isff ? RTJ_ENT_SKIP : (eob <= 3 ? e_inl : e_gen);
-                    myskips += isff ? 1 : 0;
-                    q += dl;
+                    starts[i - r0] = (uint16_t)q;
+                    q += delb[q + ((q / CS_C) << 2)];
                     i++;
                     lastend = seg0 + q;
                 }
             }
             __syncthreads();
-            for (int k = tid; k < r1 - r0; k += CS_THREADS) out[r0 + k] = sh.ring[k];
+            for (int k = tid; k < r1 - r0; k += CS_THREADS) {
+                const int qq = starts[k];
+                const int dl = delb[qq + ((qq / CS_C) << 2)];
+                const uint32_t head = lds_u32_unaligned(sh.pay, qq + mis);         /* DC, token 1, token 2, token 3 */
+                const uint32_t last = payb[qq + dl - 1];
+                const bool isff = (head & 0xFFu) == 0xFFu;                         /* skipped block */
+                /* positions >= eob are zero: a final run of n zeros ends at 64, so it starts at 64 - n */
+                const int eob = (last - 64u) < 64u ? max(127 - (int)last, dl - 1) : 64;
+                const uint32_t t1 = (head >> 8) & 0xFFu, t2 = (head >> 16) & 0xFFu;
+                const uint32_t c1 = (eob >= 2 && (t1 - 64u) >= 64u) ? t1 : 0u;
+                const uint32_t c2 = (eob >= 3 && (t2 - 64u) >= 64u) ? t2 : 0u;
+                const uint32_t e_inl = RTJ_ENT_INLINE_BIT | (head & 0xFFu) | (c1 << 8) | (c2 << 16);
+                const uint32_t e_gen = RTJ_ENT(seg0 + qq, eob);
+                out[r0 + k] = isff ? RTJ_ENT_SKIP : (eob <= 3 ? e_inl : e_gen);
+                myskips += isff ? 1 : 0;
+            }
             __syncthreads();
         }
-        if (tid < CS_NCH) {                                 /* whole warps: CS_NCH is a multiple of 32 */
+        {
 #pragma unroll
             for (int o = 16; o; o >>= 1) {
                 myskips += __shfl_xor_sync(0xFFFFFFFFu, myskips, o);

@@ -173,6 +173,8 @@ rtj_scan_chunk_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_des
             const uint32_t W0 = wp[0], W1 = wp[1], W2 = wp[2];
             const uint32_t X0 = swar_x(W0), X1 = swar_x(W1), X2 = swar_x(W2);
             uint32_t packed = 0;
+            uint32_t fill8[4];                                          /* positions the first eight tokens fill, for the rare long block */
+            unsigned slow = 0;
 #pragma unroll
             for (int i = 0; i < 4; i++) {
                 /* tokens of a block starting at q0 + i: bytes q0+i+1 .. */
@@ -185,14 +187,19 @@ rtj_scan_chunk_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_des
                 const uint32_t P1 = x1 * 0x01010101u + 0x04030201u + (P0 >> 24) * 0x01010101u;
                 const uint32_t c0 = P0 & 0x80808080u;
                 const uint32_t c1 = P1 & 0x80808080u;
-                int dl;
-                if (c0 | c1) {
-                    const int bit = c0 ? __ffs((int)c0) - 1 : 31 + __ffs((int)c1);
-                    dl = (bit >> 3) + 2;                                /* DC byte + tokens */
-                } else {
-                    dl = 1 + cs_long_block(sh.pay, q0 + mis + i + 1, (int)(P1 >> 24) - 65);
-                }
-                packed |= (uint32_t)dl << (8 * i);
+                /* no branch here: a block longer than DC + 8 tokens (both masks empty) is marked and finished below */
+                const int bit = c0 ? __ffs((int)c0) - 1 : 31 + __ffs((int)c1);
+                packed |= (uint32_t)((bit >> 3) + 2) << (8 * i);        /* DC byte + tokens */
+                slow |= (c0 | c1) ? 0u : 1u << i;
+                fill8[i] = P1 >> 24;
+            }
+            if (slow) {
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+                    if (slow & (1u << i)) {
+                        const int dl = 1 + cs_long_block(sh.pay, q0 + mis + i + 1, (int)fill8[i] - 65);
+                        packed = (packed & ~(0xFFu << (8 * i))) | (uint32_t)dl << (8 * i);
+                    }
             }
             {   /* skipped blocks (lib/RTjpeg.c:2704): a byte 0xFF is a block of its own, one byte long */
                 const uint32_t y = ~W0;

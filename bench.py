@@ -166,7 +166,7 @@ def run_reference_arm(args, rank, world):
                                    f"{threads} threads each with a private decoder and plane set"},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 def main():
@@ -200,8 +200,6 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL's own banner ("NCCL version ...") goes to stdout by default: stdout carries the one JSON line only
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     F = args.frames
@@ -314,7 +312,7 @@ def main():
                           f"lib/RTjpeg.c RTjpeg_decompress, {threads} threads each with a private decoder",
                 "all": fps,
             }
-        print(json.dumps(line), flush=True)
+        _emit(line)
 
     if world > 1:
         dist.barrier()
@@ -322,5 +320,17 @@ def main():
     ctx.close()
 
 
+def _emit(line: dict) -> None:
+    """The one JSON line, on the process's real stdout."""
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
+
+
+_REAL_STDOUT = sys.stdout
+
 if __name__ == "__main__":
+    # Libraries write banners to file descriptor 1 (NCCL prints "NCCL version ..." there when its communicator comes up):
+    # everything that is not the JSON line goes to stderr instead.
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     main()

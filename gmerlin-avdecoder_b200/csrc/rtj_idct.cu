@@ -475,12 +475,11 @@ struct K2Params {
     rtj_dev_info *info;
     const uint32_t *pos;             /* SINGLE: pic_pos of every position of a row, i | off << 16 (rtj_build_lut_kernel) */
     int ahead;                       /* frames between a CTA and the one that follows it on the same SM slot */
+    int wq;                          /* slots of one warp's queue */
 };
 
 constexpr int K2_WARPS = IDCT_THREADS / 32;
 constexpr int K2_PF_LINES = 12;                   /* 128-byte lines of payload asked into L2 for the CTA that follows */
-constexpr int K2_ROUNDS_MAX = (IDCT_MAX_MB * 6 + IDCT_THREADS - 1) / IDCT_THREADS;     /* 6 */
-constexpr int K2_WQ = K2_ROUNDS_MAX * 32;          /* queue slots of one warp: every block it looked at */
 
 } // namespace
 
@@ -494,10 +493,11 @@ constexpr int K2_WQ = K2_ROUNDS_MAX * 32;          /* queue slots of one warp: e
  * SINGLE: the strip is the whole macroblock row (frames up to IDCT_MAX_MB macroblocks wide): no
  * strip arithmetic, and the strip is contiguous in the tight-pitch output planes -> TMA bulk stores.
  */
-template <bool SINGLE, int FMT>
-__global__ void __launch_bounds__(IDCT_THREADS, 8)
+template <bool SINGLE, int FMT, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? 8 : 10)
 rtj_idct_kernel(const K2Params P)
 {
+    constexpr int THREADS = WARPS * 32;
     typedef Geo<FMT> G;
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -520,15 +520,17 @@ rtj_idct_kernel(const K2Params P)
     uint8_t *tile = smem;                                            /* TILE * mbs bytes: Y, U, V */
     const unsigned tile_s = (unsigned)__cvta_generic_to_shared(tile);
     int *s_hard = reinterpret_cast<int *>(tile + G::TILE * mbs);     /* HARD blocks of the strip, per warp */
-    static_assert(K2_WARPS == 4, "s_hard holds four counters");
-    uint32_t *wq_e = reinterpret_cast<uint32_t *>(s_hard + 8) + warp * K2_WQ;      /* this warp's queue: entries ... */
-    uint32_t *wq_p = reinterpret_cast<uint32_t *>(s_hard + 8) + (K2_WARPS + warp) * K2_WQ;   /* ... strip offset | source << 16 */
+    static_assert(WARPS == 3 || WARPS == 4, "s_hard holds four counters per kind");
+    if (WARPS == 3 && tid == 1) { s_hard[3] = 0; s_hard[7] = 0; }
+    const int wq = P.wq;                                             /* queue slots of one warp: every block it looked at */
+    uint32_t *wq_e = reinterpret_cast<uint32_t *>(s_hard + 8) + warp * wq;      /* this warp's queue: entries ... */
+    uint32_t *wq_p = reinterpret_cast<uint32_t *>(s_hard + 8) + (K2_WARPS + warp) * wq;   /* ... strip offset | source << 16 */
 
     /* everything that does not depend on anything else is fetched first: the first round's entry
      * and the frame descriptor; the table constants follow the descriptor */
-    const int rounds = (nb + IDCT_THREADS - 1) / IDCT_THREADS;
+    const int rounds = (nb + THREADS - 1) / THREADS;
     /* the positions of a whole row are the same for every row of every frame: a table, hot in L1 (padded to a
-     * multiple of IDCT_THREADS); strips of wider pictures work them out */
+     * multiple of THREADS); strips of wider pictures work them out */
     auto pos_of = [&](int p) -> PicPos {
         if (SINGLE) {
             const uint32_t v = __ldg(P.pos + p);
@@ -553,13 +555,13 @@ rtj_idct_kernel(const K2Params P)
     /* ---- pass 1, picture order: T2 blocks decode right away, the rest is queued ---- */
     int nfront = 0, nback = 0;                               /* warp-uniform queue fill: M7 | CARRY, HARD */
     for (int r = 0; r < rounds; r++) {
-        const int p = r * IDCT_THREADS + tid;
+        const int p = r * THREADS + tid;
         const PicPos pp = pp_next;
         const bool chroma = off_is_chroma<FMT>(pp.off, mbs);
         uint32_t e = e_first;
         if (r + 1 < rounds) {                                /* next round's entry: in flight during this round */
-            pp_next = pos_of(p + IDCT_THREADS);
-            e_first = p + IDCT_THREADS < nb ? my_ent[pp_next.i] : 0u;
+            pp_next = pos_of(p + THREADS);
+            e_first = p + THREADS < nb ? my_ent[pp_next.i] : 0u;
         }
         int cls = CLS_NONE;
         int x0 = 0, x1 = 0, q = 0;
@@ -609,7 +611,7 @@ rtj_idct_kernel(const K2Params P)
             wq_e[at] = e;
             wq_p[at] = (uint32_t)pp.off | (sf << 16);
         } else if (cls == Q_CARRY || cls == Q_HARD) {
-            const int at = K2_WQ - 1 - (nback + __popc(mB & below));
+            const int at = wq - 1 - (nback + __popc(mB & below));
             /* HARD blocks split once more for the general kernel: long ones (E > 16) apart from the rest */
             const bool full = cls == Q_HARD && !RTJ_ENT_IS_INLINE(e) && RTJ_ENT_EOB(e) > 16;
             wq_e[at] = (uint32_t)pp.i | (cls == Q_CARRY ? 0x80000000u : 0u) | (full ? 0x40000000u : 0u);
@@ -620,7 +622,7 @@ rtj_idct_kernel(const K2Params P)
     }
     /* ... and the part of that frame's payload where its blocks of this row should lie, if the payload is spread
      * evenly over the rows: the M7 blocks read it */
-    if (f + (unsigned)P.ahead < gridDim.y && warp == K2_WARPS - 1 && lane < K2_PF_LINES) {
+    if (f + (unsigned)P.ahead < gridDim.y && warp == WARPS - 1 && lane < K2_PF_LINES) {
         const rtjgpu_frame_desc nd = P.desc[f + (unsigned)P.ahead];
         const unsigned rows_total = SINGLE ? gridDim.x : gridDim.x / (unsigned)P.nstrips;
         const unsigned plen = nd.length > RTJPEG_B200_HEADER_BYTES ? nd.length - RTJPEG_B200_HEADER_BYTES : 0u;
@@ -636,16 +638,16 @@ rtj_idct_kernel(const K2Params P)
     __syncthreads();
     const int n0 = s_hard[4], n1 = n0 + s_hard[5], n2 = n1 + s_hard[6], nM = n2 + s_hard[7];
     const uint32_t *q_e = reinterpret_cast<const uint32_t *>(s_hard + 8);
-    const uint32_t *q_p = q_e + K2_WARPS * K2_WQ;
+    const uint32_t *q_p = q_e + K2_WARPS * wq;
     /* the last warps start first: warp 0 is the one with a part-filled extra round behind it */
-    for (int c0 = (K2_WARPS - 1 - warp) * 32; c0 < nM; c0 += K2_WARPS * 32) {
+    for (int c0 = (WARPS - 1 - warp) * 32; c0 < nM; c0 += WARPS * 32) {
         const int idx = c0 + lane;
         int x[7] = {1008, 0, 0, 0, 0, 0, 0};
         const bool live = idx < nM;
         int off = 0;
         if (live) {
             const int qw = (idx >= n0) + (idx >= n1) + (idx >= n2);
-            const int at = qw * K2_WQ + idx - (qw == 0 ? 0 : qw == 1 ? n0 : qw == 2 ? n1 : n2);
+            const int at = qw * wq + idx - (qw == 0 ? 0 : qw == 1 ? n0 : qw == 2 ? n1 : n2);
             const uint32_t e = q_e[at];
             const uint32_t ps = q_p[at];
             const unsigned sf = ps >> 16;
@@ -672,7 +674,7 @@ rtj_idct_kernel(const K2Params P)
             const bool live = idx < nback;
             uint32_t ie = 0x80000000u;
             int off = 0;
-            if (live) { ie = wq_e[K2_WQ - 1 - idx]; off = (int)wq_p[K2_WQ - 1 - idx]; }
+            if (live) { ie = wq_e[wq - 1 - idx]; off = (int)wq_p[wq - 1 - idx]; }
             const bool hard = live && !(ie >> 31);
             const bool full = hard && ((ie >> 30) & 1u);
             const int bi = (int)(ie & 0x3FFFFFFFu);              /* stream-order index inside the strip */
@@ -737,19 +739,19 @@ rtj_idct_kernel(const K2Params P)
         }
     } else {
         if (G::UNIT_W == 16) {
-            for (int r = warp; r < G::LUMA_ROWS; r += K2_WARPS)
+            for (int r = warp; r < G::LUMA_ROWS; r += WARPS)
                 for (int c = lane; c < mbs; c += 32)                 /* 16-byte vectors per luma row */
                     *reinterpret_cast<uint4 *>(oy + (size_t)r * w + c * 16) =
                         *reinterpret_cast<const uint4 *>(tile + r * lw + c * 16);
         } else {
-            for (int r = warp; r < G::LUMA_ROWS; r += K2_WARPS)
+            for (int r = warp; r < G::LUMA_ROWS; r += WARPS)
                 for (int c = lane; c < mbs; c += 32)                 /* 8-byte vectors: a grey strip may be an odd number of blocks */
                     *reinterpret_cast<uint2 *>(oy + (size_t)r * w + c * 8) =
                         *reinterpret_cast<const uint2 *>(tile + r * lw + c * 8);
         }
         if (G::PLANES == 3) {
             const int segC = lw >> 1;
-            for (int r = warp; r < 16; r += K2_WARPS) {
+            for (int r = warp; r < 16; r += WARPS) {
                 const int pl = r >> 3, rr = r & 7;
                 for (int c = lane; c < (segC >> 3); c += 32)     /* 8-byte vectors per chroma row */
                     *reinterpret_cast<uint2 *>((pl ? ov : ou) + (size_t)rr * cw + c * 8) =
@@ -835,42 +837,72 @@ inline int idct_seg_mb(int mbw, int *nstrips)
     return (mbw + n - 1) / n;
 }
 
-inline size_t idct_smem_bytes(int seg_mb, int fmt)
+/* warps per CTA: three when that spreads the strip's passes of 32 blocks evenly and four does not (a 720-wide row is 9
+ * passes: three rounds of three warps, where four warps would leave three of twelve slots empty and wait for the fourth) */
+inline int idct_warps(int nb)
 {
+    const int passes = (nb + 31) / 32;
+    const int waste4 = (passes + 3) / 4 * 4 - passes, waste3 = (passes + 2) / 3 * 3 - passes;
+    return waste3 < waste4 ? 3 : 4;
+}
+
+inline int idct_wq(int nb, int warps) { return (nb + warps * 32 - 1) / (warps * 32) * 32; }
+
+inline size_t idct_smem_bytes(int seg_mb, int fmt, int warps)
+{
+    const int blk = fmt == 0 ? 6 : fmt == 1 ? 4 : 1;
     size_t s = (size_t)seg_mb * (fmt == 0 ? 384 : fmt == 1 ? 256 : 64);    /* the picture strip */
     s += 32;                                         /* counters */
-    s += (size_t)2 * K2_WARPS * K2_WQ * 4;           /* warp queues */
+    s += (size_t)2 * K2_WARPS * idct_wq(seg_mb * blk, warps) * 4;          /* warp queues (laid out for four) */
     return (s + 15) & ~(size_t)15;
 }
 
 int g_sm_count = 0;
 
-template <bool SINGLE, int FMT>
+template <bool SINGLE, int FMT, int WARPS>
 cudaError_t k2_attr()
 {
-    return cudaFuncSetAttribute(rtj_idct_kernel<SINGLE, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)idct_smem_bytes(IDCT_MAX_MB, FMT));
+    return cudaFuncSetAttribute(rtj_idct_kernel<SINGLE, FMT, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)idct_smem_bytes(IDCT_MAX_MB, FMT, 3));
 }
 
 template <int FMT>
-cudaError_t k2_launch(const K2Params &P, dim3 grid, cudaStream_t st)
+cudaError_t k2_launch(K2Params &P, int grid_x, int F, cudaStream_t st)
 {
-    const size_t smem = idct_smem_bytes(P.seg_mb, FMT);
-    if (P.nstrips == 1) rtj_idct_kernel<true, FMT><<<grid, IDCT_THREADS, smem, st>>>(P);
-    else rtj_idct_kernel<false, FMT><<<grid, IDCT_THREADS, smem, st>>>(P);
+    const int blk = FMT == 0 ? 6 : FMT == 1 ? 4 : 1;
+    const int warps = idct_warps(P.seg_mb * blk);
+    P.wq = idct_wq(P.seg_mb * blk, warps);
+    const int resident = (g_sm_count > 0 ? g_sm_count : 148) * (warps == 4 ? 8 : 10);
+    P.ahead = (resident + grid_x - 1) / grid_x;
+    const size_t smem = idct_smem_bytes(P.seg_mb, FMT, warps);
+    const dim3 grid((unsigned)grid_x, (unsigned)F);
+    if (P.nstrips == 1) {
+        if (warps == 4) rtj_idct_kernel<true, FMT, 4><<<grid, 128, smem, st>>>(P);
+        else rtj_idct_kernel<true, FMT, 3><<<grid, 96, smem, st>>>(P);
+    } else {
+        if (warps == 4) rtj_idct_kernel<false, FMT, 4><<<grid, 128, smem, st>>>(P);
+        else rtj_idct_kernel<false, FMT, 3><<<grid, 96, smem, st>>>(P);
+    }
     return cudaGetLastError();
+}
+
+template <int FMT>
+cudaError_t k2_attrs()
+{
+    cudaError_t e = k2_attr<true, FMT, 4>();
+    if (e == cudaSuccess) e = k2_attr<false, FMT, 4>();
+    if (e == cudaSuccess) e = k2_attr<true, FMT, 3>();
+    if (e == cudaSuccess) e = k2_attr<false, FMT, 3>();
+    return e;
 }
 
 } // namespace
 
 extern "C" int rtj_idct_init(void)
 {
-    cudaError_t e = k2_attr<true, 0>();
-    if (e == cudaSuccess) e = k2_attr<false, 0>();
-    if (e == cudaSuccess) e = k2_attr<true, 1>();
-    if (e == cudaSuccess) e = k2_attr<false, 1>();
-    if (e == cudaSuccess) e = k2_attr<true, 2>();
-    if (e == cudaSuccess) e = k2_attr<false, 2>();
+    cudaError_t e = k2_attrs<0>();
+    if (e == cudaSuccess) e = k2_attrs<1>();
+    if (e == cudaSuccess) e = k2_attrs<2>();
     if (e != cudaSuccess) return (int)e;
     int dev = 0;
     if ((e = cudaGetDevice(&dev)) != cudaSuccess) return (int)e;
@@ -882,7 +914,7 @@ extern "C" int rtj_idct_init(void)
 extern "C" size_t rtj_lut_bytes(int fmt, int w, int h)
 {
     const int nb = RTJ_FMT_UNITS_X(fmt, w) * RTJ_FMT_UNIT_BLOCKS(fmt);
-    return (size_t)((nb + IDCT_THREADS - 1) / IDCT_THREADS * IDCT_THREADS) * sizeof(uint32_t);
+    return (size_t)((nb + 383) / 384 * 384) * sizeof(uint32_t);      /* whole rounds of 96 and of 128 threads */
 }
 
 extern "C" int rtj_launch_build_lut(int fmt, int w, int h, void *d_lut, void *stream)
@@ -911,12 +943,8 @@ extern "C" int rtj_launch_idct(const rtj_launch_args *a, void *stream)
     P.hardq_cap = (unsigned)((size_t)a->F * (size_t)P.nblk);
     P.fmt = fmt;
     P.pos = reinterpret_cast<const uint32_t *>(a->d_lut);
-    dim3 grid((unsigned)(P.nstrips * uy), (unsigned)a->F);
-    {
-        const int resident = (g_sm_count > 0 ? g_sm_count : 148) * 8;
-        P.ahead = (resident + (int)grid.x - 1) / (int)grid.x;
-    }
-    cudaError_t e = fmt == 0 ? k2_launch<0>(P, grid, st) : fmt == 1 ? k2_launch<1>(P, grid, st) : k2_launch<2>(P, grid, st);
+    const int grid_x = P.nstrips * uy;
+    cudaError_t e = fmt == 0 ? k2_launch<0>(P, grid_x, a->F, st) : fmt == 1 ? k2_launch<1>(P, grid_x, a->F, st) : k2_launch<2>(P, grid_x, a->F, st);
     if (e != cudaSuccess) return (int)e;
     /* the queue's length is only known on the device: a fixed grid strides over it */
     const int sms = g_sm_count > 0 ? g_sm_count : 148;

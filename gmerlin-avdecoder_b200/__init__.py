@@ -1,4 +1,4 @@
-"""B200-native RTjpeg YUV420 decoder behind gmerlin-avdecoder's own interfaces.
+"""B200-native RTjpeg decoder (and converters, encoder) behind gmerlin-avdecoder's own interfaces.
 
 The product is the C-ABI library built from ``csrc/`` (CUDA kernels for sm_100a,
 batch context, ``RTjpeg.h``-compatible shim, ``'RTJ0'`` bgav plugin).  This

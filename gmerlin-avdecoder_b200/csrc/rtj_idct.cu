@@ -1,5 +1,5 @@
 /*
- * rtj_idct.cu -- K2 of the RTjpeg YUV420 decoder: unpack + dequantise + integer AAN IDCT +
+ * rtj_idct.cu -- K2 of the RTjpeg decoder: unpack + dequantise + integer AAN IDCT +
  * clamp + planar store, for sm_100a.
  *
  *   rtj_idct_kernel       one CTA per (frame, macroblock row [, strip]).  Replaces the value

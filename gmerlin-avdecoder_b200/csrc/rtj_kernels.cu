@@ -1,5 +1,5 @@
 /*
- * rtj_kernels.cu -- sm_100a kernels of the RTjpeg YUV420 decoder.
+ * rtj_kernels.cu -- sm_100a kernels of the RTjpeg decoder: serial scans, last-writer resolve, scan plan.
  *
  *   K1  rtj_scan_kernel     one warp walks one frame's run-length stream and
  *                           emits a 32-bit entry (payload offset + end-of-block

@@ -1,5 +1,5 @@
 /*
- * rtjpeg_b200.h -- C ABI of the B200-native RTjpeg YUV420 decoder.
+ * rtjpeg_b200.h -- C ABI of the B200-native RTjpeg codec (decoder, colour converters, encoder).
  *
  * Two levels, both plain C (pointers and sizes only, no CUDA or torch types):
  *

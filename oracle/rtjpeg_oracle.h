@@ -1,8 +1,8 @@
 /*
  * rtjpeg_oracle.h -- TEST INFRASTRUCTURE ONLY.
  *
- * CPU restatement of the RTjpeg YUV420 decode path of gmerlin-avdecoder
- * (reference: lib/RTjpeg.c, include/RTjpeg.h).  It exists so that tests/,
+ * CPU restatement of the RTjpeg paths of gmerlin-avdecoder this repository rebuilds -- decode (three formats),
+ * colour converters, encoder (reference: lib/RTjpeg.c, include/RTjpeg.h).  It exists so that tests/,
  * __graft_entry__.smoke() and bench.py's cpu_baseline leg can check the CUDA
  * path.  Nothing in the shipped library (gmerlin-avdecoder_b200/) may include,
  * link or call this file.

@@ -32,6 +32,7 @@ struct Workspace {
     uint32_t     *d_seg_entry = nullptr; size_t seg_cap = 0;         /* entries of entry / base */
     uint32_t     *d_seg_base = nullptr;
     int32_t      *d_seg_nbf = nullptr;   int    seg_frames_cap = 0;
+    uint8_t      *d_seg_del = nullptr;   size_t seg_del_cap = 0;     /* segments */
     size_t        cap_entries = 0;
     int           cap_frames = 0;
     /* K2's position table, rebuilt when the geometry changes */
@@ -138,6 +139,7 @@ int ws_reserve(rtjgpu_ctx *ctx, Workspace *ws, int F, int nblk)
  * with a batch too small to fill the device with one CTA per frame.  Fills *sp (sum == NULL: not used). */
 constexpr int    SEG_AUTO_MAX_FRAMES = 256;
 constexpr size_t SEG_MAX_SUM_BYTES = (size_t)1 << 30;
+constexpr size_t SEG_MAX_DEL_BYTES = (size_t)2 << 30;
 
 int seg_reserve(rtjgpu_ctx *ctx, Workspace *ws, int F, int nblk, int scan_mode, rtj_seg_plan *sp)
 {
@@ -167,6 +169,16 @@ int seg_reserve(rtjgpu_ctx *ctx, Workspace *ws, int F, int nblk, int scan_mode, 
         CK(ctx, cudaMalloc(&ws->d_seg_nbf, (size_t)F * sizeof(int32_t)));
         ws->seg_frames_cap = F;
     }
+    /* the block lengths of the first pass are kept for the second when that fits (it saves the larger half of the second) */
+    if (nseg * RTJ_SEG_DEL_BYTES <= SEG_MAX_DEL_BYTES) {
+        if (nseg > ws->seg_del_cap) {
+            if (ws->d_seg_del) cudaFree(ws->d_seg_del);
+            ws->d_seg_del = nullptr; ws->seg_del_cap = 0;
+            if (cudaMalloc(&ws->d_seg_del, nseg * RTJ_SEG_DEL_BYTES) == cudaSuccess) ws->seg_del_cap = nseg;
+            else { ws->d_seg_del = nullptr; cudaGetLastError(); }         /* no room: the second pass works them out again */
+        }
+        sp->del = ws->seg_del_cap >= nseg ? ws->d_seg_del : nullptr;
+    }
     sp->sum = ws->d_seg_sum; sp->entry = ws->d_seg_entry; sp->base = ws->d_seg_base; sp->nbf = ws->d_seg_nbf;
     sp->maxseg = (int)maxseg;
     return RTJGPU_OK;
@@ -184,6 +196,7 @@ void ws_release(Workspace *ws)
     if (ws->d_seg_entry) cudaFree(ws->d_seg_entry);
     if (ws->d_seg_base) cudaFree(ws->d_seg_base);
     if (ws->d_seg_nbf) cudaFree(ws->d_seg_nbf);
+    if (ws->d_seg_del) cudaFree(ws->d_seg_del);
     if (ws->d_lut) cudaFree(ws->d_lut);
     *ws = Workspace();
 }

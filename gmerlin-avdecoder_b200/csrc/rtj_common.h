@@ -92,11 +92,13 @@ typedef struct rtj_dev_info {
 #define RTJ_SEG_BYTES_MB 4096      /* segment of a frame with raw prefix (rtj_scan_mb.cu) */
 #define RTJ_SEG_NE    384          /* entry offsets a segment is summarised for (64 used without raw prefix) */
 #define RTJ_SEG_UNUSED 0xFFFFFFFFu
+#define RTJ_SEG_DEL_BYTES 9216     /* block lengths of one segment as level 0 leaves them (either kernel), for the second pass */
 typedef struct rtj_seg_plan {
     uint32_t *sum;      /* [F][maxseg][RTJ_SEG_NE]  exit offset | units << 9 */
     uint32_t *entry;    /* [F][maxseg]  entry offset of the segment */
     uint32_t *base;     /* [F][maxseg]  first block index; RTJ_SEG_UNUSED = the frame is complete before it */
     int32_t  *nbf;      /* [F]  blocks the frame's stream holds, capped at nblk */
+    uint8_t  *del;      /* [F][maxseg][RTJ_SEG_DEL_BYTES]  level 0 of the first pass, kept for the second; NULL: worked out again */
     int       maxseg;
 } rtj_seg_plan;
 

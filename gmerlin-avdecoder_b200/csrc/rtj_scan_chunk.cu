@@ -167,8 +167,15 @@ rtj_scan_chunk_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_des
         }
         __syncthreads();
 
-        /* ---- level 0: delta(p) for every position, four positions per thread ---- */
-        for (int q0 = tid * 4; q0 < npos; q0 += CS_THREADS * 4) {
+        /* ---- level 0: delta(p) for every position, four positions per thread.  The second pass of the
+         *      segment-parallel arrangement takes the table its first pass made, where it was kept. ---- */
+        static_assert(CS_DEL_WORDS * 4 <= RTJ_SEG_DEL_BYTES && (CS_DEL_WORDS % 4) == 0, "the table fits the kept copy");
+        uint4 *keep = (PHASE != 0 && sp.del) ? reinterpret_cast<uint4 *>(sp.del + my_seg * RTJ_SEG_DEL_BYTES) : nullptr;
+        if (PHASE == 2 && keep) {
+            uint4 *d4 = reinterpret_cast<uint4 *>(sh.del);
+            for (int v = tid; v < CS_DEL_WORDS / 4; v += CS_THREADS) d4[v] = keep[v];
+        }
+        for (int q0 = tid * 4; q0 < ((PHASE == 2 && keep) ? 0 : npos); q0 += CS_THREADS * 4) {
             const uint32_t *wp = sh.pay + ((q0 + mis) >> 2);
             const uint32_t W0 = wp[0], W1 = wp[1], W2 = wp[2];
             const uint32_t X0 = swar_x(W0), X1 = swar_x(W1), X2 = swar_x(W2);
@@ -210,6 +217,10 @@ rtj_scan_chunk_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_des
             sh.del[(q0 >> 2) + (q0 / CS_C)] = packed;
         }
         __syncthreads();
+        if (PHASE == 1 && keep) {
+            const uint4 *d4 = reinterpret_cast<const uint4 *>(sh.del);
+            for (int v = tid; v < CS_DEL_WORDS / 4; v += CS_THREADS) keep[v] = d4[v];
+        }
 
         /* ---- DP, one lane per chunk, right to left ---- */
         if (tid < nch) {

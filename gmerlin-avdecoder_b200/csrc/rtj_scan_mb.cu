@@ -176,8 +176,15 @@ rtj_scan_mb_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc *
         __syncthreads();
 
         /* ---- level 0: both block-length tables, for the segment and the look-ahead behind it; every
-         *      thread owns a run of MB_RUN consecutive positions (17 words: bank-skewed) ---- */
-        {
+         *      thread owns a run of MB_RUN consecutive positions (17 words: bank-skewed).  The second pass of the
+         *      segment-parallel arrangement takes the tables its first pass made, where they were kept. ---- */
+        static_assert(2 * MB_POS <= RTJ_SEG_DEL_BYTES && (MB_POS % 16) == 0, "both tables fit the kept copy");
+        uint4 *keep = (PHASE != 0 && sp.del) ? reinterpret_cast<uint4 *>(sp.del + my_seg * RTJ_SEG_DEL_BYTES) : nullptr;
+        if (PHASE == 2 && keep) {
+            const int nv = (lb8 != cb8 ? 2 : 1) * (MB_POS / 16);
+            uint4 *d4 = reinterpret_cast<uint4 *>(sh.delL);         /* delL and delC are adjacent */
+            for (int v = tid; v < nv; v += MB_THREADS) d4[v] = keep[v];
+        } else {
             uint8_t *dL = reinterpret_cast<uint8_t *>(sh.delL), *dC = reinterpret_cast<uint8_t *>(sh.delC);
             const int npos2 = npos + MB_DLA;
             const int q_begin = tid * MB_RUN, q_end = min(q_begin + MB_RUN, npos2);
@@ -185,6 +192,11 @@ rtj_scan_mb_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc *
             if (lb8 != cb8) mb_level0_run(payb, dC, q_begin, q_end, cb8);
         }
         __syncthreads();
+        if (PHASE == 1 && keep) {
+            const int nv = (lb8 != cb8 ? 2 : 1) * (MB_POS / 16);
+            const uint4 *d4 = reinterpret_cast<const uint4 *>(sh.delL);
+            for (int v = tid; v < nv; v += MB_THREADS) keep[v] = d4[v];
+        }
 
         /* ---- compose: length of the macroblock that would start at every position ---- */
         for (int q = tid; q < npos; q += MB_THREADS) {

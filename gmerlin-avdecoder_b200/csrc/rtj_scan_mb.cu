@@ -60,9 +60,6 @@ __device__ __forceinline__ uint32_t lds_u32_unaligned(const uint32_t *w, int byt
     return __funnelshift_r(p[0], p[1], (unsigned)(byte & 3) * 8);
 }
 
-/* positions one token fills: a run token (signed value > 63, lib/RTjpeg.c:173) b - 63, anything else 1 */
-__device__ __forceinline__ int token_fill(unsigned v) { return (v - 64u) < 64u ? (int)v - 63 : 1; }
-
 /*
  * Level 0 for one grammar (raw prefix b), positions [q_begin, q_end) -- one thread, left to right.
  * The block that would start at q reads its tokens from ws = q + 1 + b on and ends behind the first
@@ -70,8 +67,8 @@ __device__ __forceinline__ int token_fill(unsigned v) { return (v - 64u) < 64u ?
  * from the front of that window and (the fills being positive) can only push its end further right:
  * two pointers, a constant number of steps per position however long the blocks are.
  */
-__device__ __forceinline__ void mb_level0_run(const uint8_t *__restrict__ payb, uint8_t *__restrict__ del,
-                                              int q_begin, int q_end, int b)
+__device__ __forceinline__ void mb_level0_run(const uint8_t *__restrict__ payb, const uint8_t *__restrict__ fills,
+                                              uint8_t *__restrict__ del, int q_begin, int q_end, int b)
 {
     if (q_begin >= q_end) return;
     if (b >= 63) {                                          /* 63 raw coefficients: no token tail, 64 bytes */
@@ -80,12 +77,13 @@ __device__ __forceinline__ void mb_level0_run(const uint8_t *__restrict__ payb, 
     }
     /* One step per iteration -- either the window grows by a token or a position is finished and the
      * window loses its first token -- so that the lanes of a warp, whose runs need the two kinds of
-     * step in different order, never wait for each other. */
+     * step in different order, never wait for each other.  fills[i] = positions the byte at i fills when read
+     * as a token (a run token b > 63, lib/RTjpeg.c:173: b - 63; anything else 1), made once for both grammars. */
     const int need = 63 - b;
     int q = q_begin, ws = q_begin + 1 + b, n = ws, sum = 0;
     while (q < q_end) {
         const bool grow = sum < need;
-        const int f = token_fill(payb[grow ? n : ws]);
+        const int f = fills[grow ? n : ws];
         if (grow) {
             sum += f;
             n++;
@@ -187,9 +185,16 @@ rtj_scan_mb_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc *
         } else {
             uint8_t *dL = reinterpret_cast<uint8_t *>(sh.delL), *dC = reinterpret_cast<uint8_t *>(sh.delC);
             const int npos2 = npos + MB_DLA;
+            /* what every byte fills when read as a token, for both grammars: in the place of the macroblock lengths,
+             * which are made later.  fill = 1 + (b & 63) for a run token b = 64 .. 127, else 1: four bytes per step. */
+            uint32_t *fw = reinterpret_cast<uint32_t *>(sh.dmb);
+            for (int v = tid; v < (npos + MB_LA + 3) / 4; v += MB_THREADS)
+                fw[v] = swar_x(lds_u32_unaligned(sh.pay, 4 * v + mis)) + 0x01010101u;
+            __syncthreads();
+            const uint8_t *fills = reinterpret_cast<const uint8_t *>(fw);
             const int q_begin = tid * MB_RUN, q_end = min(q_begin + MB_RUN, npos2);
-            mb_level0_run(payb, dL, q_begin, q_end, lb8);
-            if (lb8 != cb8) mb_level0_run(payb, dC, q_begin, q_end, cb8);
+            mb_level0_run(payb, fills, dL, q_begin, q_end, lb8);
+            if (lb8 != cb8) mb_level0_run(payb, fills, dC, q_begin, q_end, cb8);
         }
         __syncthreads();
         if (PHASE == 1 && keep) {

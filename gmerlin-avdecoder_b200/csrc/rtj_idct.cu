@@ -516,6 +516,9 @@ rtj_idct_kernel(const K2Params P)
      * (same strip, P.ahead frames on) into L2 now. */
     if (f + (unsigned)P.ahead < gridDim.y && tid * 32 < nb)
         asm volatile("prefetch.global.L2 [%0];" :: "l"(my_ent + (size_t)P.ahead * (unsigned)P.nblk + tid * 32));
+    /* ... and, in a batch that holds skipped blocks at all, their last writers (two bytes a block) */
+    if (f + (unsigned)P.ahead < gridDim.y && tid >= 32 && (tid - 32) * 64 < nb && P.info->skipped_blocks)
+        asm volatile("prefetch.global.L2 [%0];" :: "l"(P.srcf + frame_blk0 + (size_t)P.ahead * (unsigned)P.nblk + (tid - 32) * 64));
 
     uint8_t *tile = smem;                                            /* TILE * mbs bytes: Y, U, V */
     const unsigned tile_s = (unsigned)__cvta_generic_to_shared(tile);

@@ -112,3 +112,33 @@ def test_rtjpeg_converters_drop_in(kind):
 def test_sha_of_fixture_is_stable():
     g = golden("convert_48x32")
     assert hashlib.sha256(g["pic420"].tobytes()).hexdigest()[:16] == str(g["sha420"])
+
+
+@pytest.mark.gpu
+def test_convert_and_encode_refuse_bad_arguments():
+    import torch
+    import gmerlin_avdecoder_b200 as g
+    from gmerlin_avdecoder_b200 import capi
+    w, h = 64, 48
+    src = torch.zeros(w * h * 3 // 2, dtype=torch.uint8, device="cuda")
+    out = torch.zeros(w * h * 4, dtype=torch.uint8, device="cuda")
+    with g.BatchContext(0) as ctx:
+        def conv(kind=0, src_fb=w * h * 3 // 2, ww=w, hh=h, rp=w * 4, fp=w * h * 4):
+            ctx.convert_device(kind, src.data_ptr(), src_fb, 1, ww, hh, out.data_ptr(), rp, fp)
+        for kwargs, code in [(dict(kind=9), capi.E_FORMAT), (dict(ww=60), capi.E_SIZE), (dict(rp=w * 4 - 16), capi.E_ARG),
+                             (dict(rp=w * 4 + 8), capi.E_ARG), (dict(fp=w * 4 * (h - 1)), capi.E_ARG),
+                             (dict(src_fb=w * h), capi.E_ARG)]:
+            with pytest.raises(g.RTjpegError) as e:
+                conv(**kwargs)
+            assert e.value.code == code, kwargs
+        conv()                                               # and the well-formed call goes through
+        off = torch.zeros(2, dtype=torch.int64, device="cuda")
+        ctx.set_format(2)                                    # the 8-bit encoder is not offered
+        with pytest.raises(g.RTjpegError) as e:
+            ctx.encode_device(src.data_ptr(), 1, w, h, out.data_ptr(), out.numel(), off.data_ptr())
+        assert e.value.code == capi.E_FORMAT
+        ctx.set_format(0)
+        with pytest.raises(g.RTjpegError) as e:
+            ctx.encode_device(src.data_ptr(), 1, 50, h, out.data_ptr(), out.numel(), off.data_ptr())
+        assert e.value.code == capi.E_SIZE
+        torch.cuda.synchronize()

@@ -516,9 +516,6 @@ rtj_idct_kernel(const K2Params P)
      * (same strip, P.ahead frames on) into L2 now. */
     if (f + (unsigned)P.ahead < gridDim.y && tid * 32 < nb)
         asm volatile("prefetch.global.L2 [%0];" :: "l"(my_ent + (size_t)P.ahead * (unsigned)P.nblk + tid * 32));
-    /* ... and, in a batch that holds skipped blocks at all, their last writers (two bytes a block) */
-    if (f + (unsigned)P.ahead < gridDim.y && tid >= 32 && (tid - 32) * 64 < nb && P.info->skipped_blocks)
-        asm volatile("prefetch.global.L2 [%0];" :: "l"(P.srcf + frame_blk0 + (size_t)P.ahead * (unsigned)P.nblk + (tid - 32) * 64));
 
     uint8_t *tile = smem;                                            /* TILE * mbs bytes: Y, U, V */
     const unsigned tile_s = (unsigned)__cvta_generic_to_shared(tile);
@@ -557,6 +554,7 @@ rtj_idct_kernel(const K2Params P)
 
     /* ---- pass 1, picture order: T2 blocks decode right away, the rest is queued ---- */
     int nfront = 0, nback = 0;                               /* warp-uniform queue fill: M7 | CARRY, HARD */
+    bool saw_skip = false;
     for (int r = 0; r < rounds; r++) {
         const int p = r * THREADS + tid;
         const PicPos pp = pp_next;
@@ -572,6 +570,7 @@ rtj_idct_kernel(const K2Params P)
         unsigned sf = f;
         if (p < nb) {
             if (RTJ_ENT_IS_SKIP(e)) {                        /* skipped: take the entry of its last writer */
+                saw_skip = true;
                 const unsigned s = P.srcf[frame_blk0 + pp.i];
                 if (s != RTJ_SRC_CARRY) {
                     sf = s;
@@ -623,6 +622,9 @@ rtj_idct_kernel(const K2Params P)
         nfront += __popc(mM);
         nback += __popc(mB);
     }
+    /* ... where this row held skipped blocks, the last writers of that frame's row (two bytes a block) ... */
+    if (f + (unsigned)P.ahead < gridDim.y && __any_sync(FULL, saw_skip) && lane * 64 < nb && warp == 0)
+        asm volatile("prefetch.global.L2 [%0];" :: "l"(P.srcf + frame_blk0 + (size_t)P.ahead * (unsigned)P.nblk + lane * 64));
     /* ... and the part of that frame's payload where its blocks of this row should lie, if the payload is spread
      * evenly over the rows: the M7 blocks read it */
     if (f + (unsigned)P.ahead < gridDim.y && warp == WARPS - 1 && lane < K2_PF_LINES) {

@@ -271,7 +271,8 @@ rtj_scan_mb_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc *
         }
         __syncthreads();
 
-        /* ---- emit: six entries per macroblock ---- */
+        /* ---- emit, in two steps as in rtj_scan_chunk.cu: the chunk lanes walk their macroblocks and note where every
+         *      block starts and which place of its unit it has; all threads then make the entries and store them. ---- */
         const int nb1 = min(sh.nb, nblk);
         int q = 0, i = 0, qend = 0, myskips = 0, lastend = -1, k6 = 0;
         if (tid < nch) {
@@ -280,50 +281,55 @@ rtj_scan_mb_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc *
             qend = (tid + 1) * MB_C;
         }
         __syncthreads();
-        for (int r0 = nb0; r0 < nb1; r0 += MB_STAGE) {
-            const int r1 = min(r0 + MB_STAGE, nb1);
+        uint16_t *starts = reinterpret_cast<uint16_t *>(sh.ring);          /* start (13 bits) | place in the unit << 13; 0xFFFF: missing */
+        static_assert(MB_POS < (1 << 13) && RTJ_FMT_UNIT_BLOCKS(0) <= 7, "a block start and its place fit 16 bits");
+        for (int r0 = nb0; r0 < nb1; r0 += 2 * MB_STAGE) {
+            const int r1 = min(r0 + 2 * MB_STAGE, nb1);
             if (tid < nch) {
                 /* a macroblock belongs to the chunk it starts in; its later blocks may lie behind the chunk */
                 while ((k6 != 0 || q < min(qend, lim)) && i < r1) {
-                    const int bt8 = k6 < unit_luma ? lb8 : cb8;
-                    uint32_t e;
-                    if (q >= lim) {
-                        e = missing;                                        /* the payload ended inside this macroblock */
-                    } else {
-                        const int dl = (k6 < unit_luma ? dLb : dCb)[q];
-                        const uint32_t head = lds_u32_unaligned(sh.pay, q + mis);
-                        const uint32_t last = payb[q + dl - 1];
-                        const bool isff = (head & 0xFFu) == 0xFFu;
-                        const int eob = bt8 >= 63 ? 64 : ((last - 64u) < 64u ? max(127 - (int)last, dl - 1) : 64);
-                        const uint32_t t1 = (head >> 8) & 0xFFu, t2 = (head >> 16) & 0xFFu;
-                        const uint32_t c1 = (eob >= 2 && (t1 - 64u) >= 64u) ? t1 : 0u;
-                        const uint32_t c2 = (eob >= 3 && (t2 - 64u) >= 64u) ? t2 : 0u;
-                        const uint32_t e_inl = RTJ_ENT_INLINE_BIT | (head & 0xFFu) | (c1 << 8) | (c2 << 16);
-                        const uint32_t e_gen = RTJ_ENT(seg0 + q, eob);
-                        e = isff ? RTJ_ENT_SKIP : ((bt8 == 0 && eob <= 3) ? e_inl : e_gen);
-                        myskips += isff ? 1 : 0;
-                        q += dl;
+                    if (q >= lim) starts[i - r0] = 0xFFFFu;                 /* the payload ended inside this macroblock */
+                    else {
+                        starts[i - r0] = (uint16_t)(q | (k6 << 13));
+                        q += (k6 < unit_luma ? dLb : dCb)[q];
                         lastend = seg0 + q;
                     }
-                    sh.ring[i - r0] = e;
                     i++;
                     k6 = k6 == unit - 1 ? 0 : k6 + 1;
                 }
             }
             __syncthreads();
-            for (int k = tid; k < r1 - r0; k += MB_THREADS) out[r0 + k] = sh.ring[k];
+            for (int k = tid; k < r1 - r0; k += MB_THREADS) {
+                const unsigned st = starts[k];
+                uint32_t e = missing;
+                if (st != 0xFFFFu) {
+                    const int qq = (int)(st & 0x1FFFu), kk = (int)(st >> 13);
+                    const int bt8 = kk < unit_luma ? lb8 : cb8;
+                    const int dl = (kk < unit_luma ? dLb : dCb)[qq];
+                    const uint32_t head = lds_u32_unaligned(sh.pay, qq + mis);
+                    const uint32_t last = payb[qq + dl - 1];
+                    const bool isff = (head & 0xFFu) == 0xFFu;
+                    const int eob = bt8 >= 63 ? 64 : ((last - 64u) < 64u ? max(127 - (int)last, dl - 1) : 64);
+                    const uint32_t t1 = (head >> 8) & 0xFFu, t2 = (head >> 16) & 0xFFu;
+                    const uint32_t c1 = (eob >= 2 && (t1 - 64u) >= 64u) ? t1 : 0u;
+                    const uint32_t c2 = (eob >= 3 && (t2 - 64u) >= 64u) ? t2 : 0u;
+                    const uint32_t e_inl = RTJ_ENT_INLINE_BIT | (head & 0xFFu) | (c1 << 8) | (c2 << 16);
+                    const uint32_t e_gen = RTJ_ENT(seg0 + qq, eob);
+                    e = isff ? RTJ_ENT_SKIP : ((bt8 == 0 && eob <= 3) ? e_inl : e_gen);
+                    myskips += isff ? 1 : 0;
+                }
+                out[r0 + k] = e;
+            }
             __syncthreads();
         }
+        /* the skip counts of all threads, the stream ends of the chunk lanes */
+#pragma unroll
+        for (int o = 16; o; o >>= 1) myskips += __shfl_xor_sync(0xFFFFFFFFu, myskips, o);
+        if (lane == 0 && myskips) atomicAdd(&sh.skips, myskips);
         if (tid < 32) {                                     /* MB_NCH <= 32: the chunk lanes are warp 0 */
 #pragma unroll
-            for (int o = 16; o; o >>= 1) {
-                myskips += __shfl_xor_sync(0xFFFFFFFFu, myskips, o);
-                lastend = max(lastend, __shfl_xor_sync(0xFFFFFFFFu, lastend, o));
-            }
-            if (lane == 0) {
-                sh.skips += myskips;
-                sh.consumed = max(sh.consumed, lastend);
-            }
+            for (int o = 16; o; o >>= 1) lastend = max(lastend, __shfl_xor_sync(0xFFFFFFFFu, lastend, o));
+            if (lane == 0) sh.consumed = max(sh.consumed, lastend);
         }
         __syncthreads();
         if (PHASE != 0) break;

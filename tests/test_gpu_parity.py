@@ -291,3 +291,24 @@ def test_full_size_config2_4096_frames(ctx):
                                         zero_init=False, keep=True)
         got = b.out[c0:c0 + n].cpu().numpy()
         assert np.array_equal(got, want), first_diff(got, want, w, h)
+
+
+@pytest.mark.parametrize("w,h", [(720, 576), (1920, 1088)])
+def test_frames_of_skip_markers_only(ctx, w, h):
+    """A frame that is nothing but 0xFF bytes -- one block per byte, 8192 blocks in a scan segment, more than one
+    emit round holds -- after a coded frame, at a quality without and one with a raw prefix."""
+    nblk = (w // 16) * (h // 16) * 6
+    for Q in (128, 255):
+        s, o = clip(w, h, Q, 2, noise_y=6)
+        sizes = O.packet_sizes(s, o)
+        first = s[int(o[0]):int(o[0]) + int(sizes[0])]
+        allskip = np.full(12 + nblk, 0xFF, dtype=np.uint8)
+        allskip[:12] = first[:12]
+        allskip[0:4] = np.frombuffer(np.uint32(12 + nblk).tobytes(), dtype=np.uint8)
+        second = s[int(o[1]):int(o[1]) + int(sizes[1])]
+        s2, o2 = O.pack_packets([first, allskip, allskip, second, allskip])
+        init = np.full(w * h * 3 // 2, 0x30, dtype=np.uint8)
+        want = reference_frames(s2, o2, w, h, init)
+        got, _ = gpu_decode(ctx, s2, o2, w, h, carry=init)
+        assert np.array_equal(got, want), first_diff(got, want, w, h)
+        assert np.array_equal(want[1], want[0]) and ctx.batch_info().skipped_blocks == 3 * nblk

@@ -56,6 +56,7 @@ HOST_IN_PINNED, HOST_OUT_PINNED = 1, 2
 STREAM_SLACK_BYTES = 128
 TABLE_ZERO, TABLE_CUSTOM = 0, 256
 SCAN_AUTO, SCAN_LANE, SCAN_WARP, SCAN_CHUNK, SCAN_SEGMENT = 0, 1, 2, 3, 4
+PIPELINE_AUTO, PIPELINE_SERIAL = 0, 1
 
 _u8p = C.POINTER(C.c_uint8)
 _u32p = C.POINTER(C.c_uint32)
@@ -116,6 +117,7 @@ def load_library() -> C.CDLL:
     L.rtjgpu_set_custom_tables.argtypes = [vp, _u32p]
     L.rtjgpu_set_scan_mode.argtypes = [vp, C.c_int]
     L.rtjgpu_set_format.argtypes = [vp, C.c_int]
+    L.rtjgpu_set_pipeline.argtypes = [vp, C.c_int, C.c_int]
     L.rtjgpu_convert_device.argtypes = [vp, C.c_int, vp, C.c_size_t, C.c_int, C.c_int, C.c_int, vp, C.c_size_t, C.c_size_t,
                                         C.c_int, vp]
     L.rtjgpu_convert_bpp.argtypes = [C.c_int]
@@ -141,6 +143,8 @@ def load_library() -> C.CDLL:
     L.rtjgpu_launch_count.argtypes = [vp]
     L.rtjgpu_launch_count.restype = C.c_uint64
     L.rtjgpu_split_shards.argtypes = [_u8p, C.c_int, C.c_int, C.POINTER(C.c_int)]
+    L.rtjgpu_split_shards_lead.argtypes = [_u8p, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.rtjgpu_scan_device.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]
     L.rtjgpu_tables_for_quality.argtypes = [C.c_int, _u32p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.rtjgpu_tables_for_quality.restype = None
     L.rtjgpu_tables_from_raw.argtypes = [_u32p, _u32p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
@@ -262,12 +266,29 @@ def nuv_extract_rtj0(data: np.ndarray, hdr: NuvHeader):
     return stream, offsets[:n.value + 1].copy(), tc[:n.value].copy(), int(bad.value)
 
 
-def split_shards(clean: np.ndarray, n: int) -> np.ndarray:
+def split_shards(clean: np.ndarray, n: int, allow_empty: bool = True) -> np.ndarray:
+    """rtjgpu_split_shards: cuts on clean frames only -> first[n + 1].  A shard comes out empty when the clean frames
+    run out; allow_empty=False raises instead."""
     L = load_library()
     clean = np.ascontiguousarray(clean, dtype=np.uint8)
     first = (C.c_int * (n + 1))()
-    _check(L.rtjgpu_split_shards(_u8(clean), len(clean), n, first), "rtjgpu_split_shards")
+    rc = L.rtjgpu_split_shards(_u8(clean), len(clean), n, first)
+    if rc < 0:
+        raise RTjpegError(rc, "rtjgpu_split_shards")
+    if rc > 0 and not allow_empty:
+        raise ValueError(f"rtjgpu_split_shards: {rc} of {n} shards are empty (not enough clean frames); use split_shards_lead")
     return np.array(first[:], dtype=np.int64)
+
+
+def split_shards_lead(clean: np.ndarray, n: int):
+    """rtjgpu_split_shards_lead -> (first[n + 1], lead[n]): shard i decodes frames [first[i] - lead[i], first[i + 1])
+    and keeps the last first[i + 1] - first[i]."""
+    L = load_library()
+    clean = np.ascontiguousarray(clean, dtype=np.uint8)
+    first = (C.c_int * (n + 1))()
+    lead = (C.c_int * n)()
+    _check(L.rtjgpu_split_shards_lead(_u8(clean), len(clean), n, first, lead), "rtjgpu_split_shards_lead")
+    return np.array(first[:], dtype=np.int64), np.array(lead[:], dtype=np.int64)
 
 
 class BatchContext:
@@ -298,6 +319,10 @@ class BatchContext:
     def set_scan_mode(self, mode: int) -> None:
         """0 = auto, 1 = one thread per frame, 2 = one warp per frame."""
         _check(self._L.rtjgpu_set_scan_mode(self._h, mode), "rtjgpu_set_scan_mode")
+
+    def set_pipeline(self, mode: int = PIPELINE_AUTO, slice_frames: int = 0) -> None:
+        """PIPELINE_AUTO: scan of slice s + 1 beside resolve + IDCT of slice s; PIPELINE_SERIAL: stage after stage."""
+        _check(self._L.rtjgpu_set_pipeline(self._h, mode, slice_frames), "rtjgpu_set_pipeline")
 
     def set_format(self, fmt: int) -> None:
         """RTJ_YUV420 (default), RTJ_YUV422 or RTJ_RGB8 (8-bit grey) for the batches that follow."""
@@ -348,6 +373,11 @@ class BatchContext:
                                           _u8(out), None if carry is None else _u8(carry), flags),
                "rtjgpu_decode_host")
         return st
+
+    def scan_device(self, d_stream: int, d_desc: int, F: int, w: int, h: int, cuda_stream: int | None = None) -> None:
+        """K1 only: afterwards skip_counts() / batch_info() describe the batch without it having been decoded."""
+        _check(self._L.rtjgpu_scan_device(self._h, C.c_void_p(d_stream), C.c_void_p(d_desc), F, w, h,
+                                          C.c_void_p(cuda_stream or 0)), "rtjgpu_scan_device")
 
     def sync(self) -> None:
         _check(self._L.rtjgpu_sync(self._h), "rtjgpu_sync")

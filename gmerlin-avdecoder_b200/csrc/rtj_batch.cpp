@@ -25,6 +25,7 @@ struct Workspace {
     uint16_t     *d_src = nullptr;
     uint32_t     *d_hardq = nullptr;
     uint16_t     *d_chunk_last = nullptr;
+    uint16_t     *d_k3_carry = nullptr;  int    k3_carry_cap = 0;    /* [2][nblk]: last writers handed from slice to slice */
     uint32_t     *d_frame_skips = nullptr;
     rtj_dev_info *d_info = nullptr;
     /* segment-parallel scan */
@@ -42,6 +43,15 @@ struct Workspace {
 
 constexpr int HOST_SLOTS = 3;
 constexpr int TIMING_RING = 256;
+
+/* The two streams a large device batch is worked through on (run_kernels): K1 slice by slice on `scan`,
+ * K3 / K2 of every slice behind it on `idct`, forked from and joined to the caller's stream with events. */
+struct Pipeline {
+    cudaStream_t scan = nullptr, idct = nullptr;
+    cudaEvent_t  fork = nullptr, join = nullptr;
+    cudaEvent_t  scanned[RTJ_MAX_SLICES] = {};
+    bool         ready = false;
+};
 
 struct HostSlot {
     cudaStream_t       stream = nullptr;
@@ -82,6 +92,10 @@ struct rtjgpu_ctx {
     size_t         d_host_carry_cap = 0;
     int            scan_mode = RTJGPU_SCAN_AUTO;
     int            format = RTJ_YUV420;
+    Pipeline       pipe;
+    int            pipeline_mode = RTJGPU_PIPELINE_AUTO;
+    int            slice_frames = 576, slice0_frames = 576;   /* multiples of RTJ_RESOLVE_T */
+    bool           scan_priority = true;
     /* encoder: configuration, state between calls, workspace */
     int            enc_quality = 0, enc_lb8 = 0, enc_cb8 = 0;
     int            enc_key_rate = 0, enc_key_count = 0, enc_lm = 0, enc_cm = 0;
@@ -122,8 +136,14 @@ int ws_reserve(rtjgpu_ctx *ctx, Workspace *ws, int F, int nblk)
         CK(ctx, cudaMalloc(&ws->d_ent, need * sizeof(uint32_t)));
         CK(ctx, cudaMalloc(&ws->d_src, need * sizeof(uint16_t)));
         CK(ctx, cudaMalloc(&ws->d_hardq, need * sizeof(uint32_t)));
-        CK(ctx, cudaMalloc(&ws->d_chunk_last, need * sizeof(uint16_t)));   /* ceil(F / 32) rows of nblk: at most F * nblk */
+        CK(ctx, cudaMalloc(&ws->d_chunk_last, ((size_t)F / RTJ_RESOLVE_T + 1) * (size_t)nblk * sizeof(uint16_t)));
         ws->cap_entries = need;
+    }
+    if (nblk > ws->k3_carry_cap) {
+        if (ws->d_k3_carry) cudaFree(ws->d_k3_carry);
+        ws->d_k3_carry = nullptr; ws->k3_carry_cap = 0;
+        CK(ctx, cudaMalloc(&ws->d_k3_carry, (size_t)2 * nblk * sizeof(uint16_t)));
+        ws->k3_carry_cap = nblk;
     }
     if (F > ws->cap_frames) {
         if (ws->d_frame_skips) cudaFree(ws->d_frame_skips);
@@ -190,6 +210,7 @@ void ws_release(Workspace *ws)
     if (ws->d_src) cudaFree(ws->d_src);
     if (ws->d_hardq) cudaFree(ws->d_hardq);
     if (ws->d_chunk_last) cudaFree(ws->d_chunk_last);
+    if (ws->d_k3_carry) cudaFree(ws->d_k3_carry);
     if (ws->d_frame_skips) cudaFree(ws->d_frame_skips);
     if (ws->d_info) cudaFree(ws->d_info);
     if (ws->d_seg_sum) cudaFree(ws->d_seg_sum);
@@ -201,20 +222,75 @@ void ws_release(Workspace *ws)
     *ws = Workspace();
 }
 
-/* K1 -> K3 -> K2 on one stream.  ev != NULL brackets the stages with events. */
+int pipeline_init(rtjgpu_ctx *ctx)
+{
+    Pipeline &p = ctx->pipe;
+    if (p.ready) return RTJGPU_OK;
+    int least = 0, greatest = 0;
+    CK(ctx, cudaDeviceGetStreamPriorityRange(&least, &greatest));
+    CK(ctx, cudaStreamCreateWithPriority(&p.scan, cudaStreamNonBlocking, ctx->scan_priority ? greatest : least));
+    CK(ctx, cudaStreamCreateWithPriority(&p.idct, cudaStreamNonBlocking, least));
+    CK(ctx, cudaEventCreateWithFlags(&p.fork, cudaEventDisableTiming));
+    CK(ctx, cudaEventCreateWithFlags(&p.join, cudaEventDisableTiming));
+    for (int i = 0; i < RTJ_MAX_SLICES; i++) CK(ctx, cudaEventCreateWithFlags(&p.scanned[i], cudaEventDisableTiming));
+    p.ready = true;
+    return RTJGPU_OK;
+}
+
+void pipeline_release(Pipeline *p)
+{
+    if (p->scan) cudaStreamDestroy(p->scan);
+    if (p->idct) cudaStreamDestroy(p->idct);
+    if (p->fork) cudaEventDestroy(p->fork);
+    if (p->join) cudaEventDestroy(p->join);
+    for (int i = 0; i < RTJ_MAX_SLICES; i++) if (p->scanned[i]) cudaEventDestroy(p->scanned[i]);
+    *p = Pipeline();
+}
+
+/* The slices of a batch: [first[i], first[i + 1]), whole chunks of RTJ_RESOLVE_T frames, at most RTJ_MAX_SLICES. */
+int plan_slices(const rtjgpu_ctx *ctx, int F, int *first)
+{
+    auto up = [](int v) { return (v + RTJ_RESOLVE_T - 1) / RTJ_RESOLVE_T * RTJ_RESOLVE_T; };
+    int s0 = up(std::max(ctx->slice0_frames, 1)), sl = up(std::max(ctx->slice_frames, 1));
+    if (F > s0 && (F - s0 + sl - 1) / sl + 1 > RTJ_MAX_SLICES) sl = up((F - s0 + RTJ_MAX_SLICES - 2) / (RTJ_MAX_SLICES - 1));
+    int n = 0;
+    first[0] = 0;
+    for (int at = 0; at < F; n++) {
+        at = std::min(F, at + (n == 0 ? s0 : sl));
+        first[n + 1] = at;
+    }
+    return n;
+}
+
+/*
+ * K1 -> K3 -> K2 -> K2b.  ev != NULL brackets the stages with events.
+ *
+ * The batch is worked through in slices of frames.  Serial arrangement (small batches, the segment-parallel and the
+ * serial scans, RTJGPU_PIPELINE_SERIAL): everything on the caller's stream -- K1 over the batch, K3 slice by slice
+ * (its look-back never leaves a slice), K2 over the batch.  Pipelined arrangement (allow_pipe, two slices or more):
+ * K1 of slice s + 1 runs on a second stream next to K3 / K2 of slice s.  K1 is bound by the ALU pipe and by its
+ * barriers, K2 by the FMA pipe: side by side on an SM they fill each other's idle issue slots.  K1's stream has the
+ * higher priority, so the CTAs of its next slice (one wave, sized by the slice) take their share of every SM as
+ * K2's short-lived CTAs retire.  The last writer of a skipped block lies in an earlier frame, i.e. in a slice
+ * that is already scanned, so nothing else has to be ordered.
+ */
 int run_kernels(rtjgpu_ctx *ctx, Workspace *ws, const uint8_t *d_stream, const rtjgpu_frame_desc *d_desc,
-                int F, int w, int h, uint8_t *d_out, const uint8_t *d_carry, cudaStream_t st, cudaEvent_t *ev)
+                int F, int w, int h, uint8_t *d_out, const uint8_t *d_carry, cudaStream_t st, cudaEvent_t *ev,
+                bool allow_pipe)
 {
     rtj_launch_args a;
     a.d_stream = d_stream; a.d_desc = d_desc; a.d_tables = ctx->d_tables;
     a.F = F; a.w = w; a.h = h;
+    a.f0 = 0; a.f1 = F; a.slice = 0;
     a.fmt = ctx->format;
     a.d_ent = ws->d_ent; a.d_src = ws->d_src; a.d_frame_skips = ws->d_frame_skips; a.d_info = ws->d_info;
     a.d_hardq = ws->d_hardq; a.d_chunk_last = ws->d_chunk_last;
+    a.d_k3_in = nullptr; a.d_k3_out = ws->d_k3_carry;
     a.d_out = d_out; a.d_carry = d_carry;
     a.scan_mode = ctx->scan_mode;
+    const int nblk = RTJ_FMT_NBLK(ctx->format, w, h);
     {
-        const int rc = seg_reserve(ctx, ws, F, RTJ_FMT_NBLK(ctx->format, w, h), ctx->scan_mode, &a.seg);
+        const int rc = seg_reserve(ctx, ws, F, nblk, ctx->scan_mode, &a.seg);
         if (rc) return rc;
     }
 
@@ -236,19 +312,65 @@ int run_kernels(rtjgpu_ctx *ctx, Workspace *ws, const uint8_t *d_stream, const r
         a.d_lut = ws->d_lut;
     }
 
+    int first[RTJ_MAX_SLICES + 1];
+    const int nslices = plan_slices(ctx, F, first);
+    const bool chunk_scan = !a.seg.sum && (ctx->scan_mode == RTJGPU_SCAN_AUTO || ctx->scan_mode == RTJGPU_SCAN_CHUNK);
+    const bool piped = allow_pipe && chunk_scan && nslices >= 2 && ctx->pipeline_mode != RTJGPU_PIPELINE_SERIAL;
+    auto slice_args = [&](int i) {
+        a.f0 = first[i]; a.f1 = first[i + 1]; a.slice = i;
+        a.d_k3_in = i == 0 ? nullptr : ws->d_k3_carry + (size_t)(i & 1) * nblk;
+        a.d_k3_out = ws->d_k3_carry + (size_t)((i + 1) & 1) * nblk;
+    };
+#define LAUNCHED(call, count)                                                  \
+    do {                                                                       \
+        const int e__ = (call);                                                \
+        if (e__ < 0 || ((count) && e__ > 0)) { ctx->last_cuda = e__ < 0 ? -e__ : e__; return RTJGPU_E_CUDA; } \
+        ctx->launches += (count) ? (uint64_t)(count) : (uint64_t)e__;          \
+    } while (0)
+
     CK(ctx, cudaMemcpyAsync(ws->d_info, ctx->h_info_reset, sizeof(rtj_dev_info), cudaMemcpyHostToDevice, st));
     if (ev) CK(ctx, cudaEventRecord(ev[0], st));
-    int e = rtj_launch_scan(&a, st);
-    if (e < 0) { ctx->last_cuda = -e; return RTJGPU_E_CUDA; }
-    ctx->launches += (uint64_t)e;
-    if (ev) CK(ctx, cudaEventRecord(ev[1], st));
-    e = rtj_launch_resolve(&a, st);
-    if (e) { ctx->last_cuda = e; return RTJGPU_E_CUDA; }
-    if (ev) CK(ctx, cudaEventRecord(ev[2], st));
-    e = rtj_launch_idct(&a, st);
-    if (e) { ctx->last_cuda = e; return RTJGPU_E_CUDA; }
+    if (!piped) {
+        LAUNCHED(rtj_launch_scan(&a, st), 0);                  /* returns its launches */
+        if (ev) CK(ctx, cudaEventRecord(ev[1], st));
+        for (int i = 0; i < nslices; i++) {
+            slice_args(i);                                      /* (the one scan over the batch counted its skips as slice 0) */
+            LAUNCHED(rtj_launch_resolve(&a, st), 2);
+        }
+        a.f0 = 0; a.f1 = F;
+        if (ev) CK(ctx, cudaEventRecord(ev[2], st));
+        LAUNCHED(rtj_launch_idct(&a, st), 1);
+        LAUNCHED(rtj_launch_idct_hard(&a, st), 1);
+        if (ev) CK(ctx, cudaEventRecord(ev[3], st));
+        return RTJGPU_OK;
+    }
+
+    {
+        const int rc = pipeline_init(ctx);
+        if (rc) return rc;
+    }
+    Pipeline &p = ctx->pipe;
+    CK(ctx, cudaEventRecord(p.fork, st));
+    CK(ctx, cudaStreamWaitEvent(p.scan, p.fork, 0));
+    CK(ctx, cudaStreamWaitEvent(p.idct, p.fork, 0));
+    for (int i = 0; i < nslices; i++) {
+        slice_args(i);
+        LAUNCHED(rtj_launch_scan(&a, p.scan), 0);
+        CK(ctx, cudaEventRecord(p.scanned[i], p.scan));
+        CK(ctx, cudaStreamWaitEvent(p.idct, p.scanned[i], 0));
+        LAUNCHED(rtj_launch_resolve(&a, p.idct), 2);
+        LAUNCHED(rtj_launch_idct(&a, p.idct), 1);
+    }
+    if (ev) {                                                   /* stages overlap: scan = until the last slice is scanned, idct = the rest */
+        CK(ctx, cudaEventRecord(ev[1], p.scan));
+        CK(ctx, cudaEventRecord(ev[2], p.scan));
+    }
+    a.f0 = 0; a.f1 = F;
+    LAUNCHED(rtj_launch_idct_hard(&a, p.idct), 1);
+    CK(ctx, cudaEventRecord(p.join, p.idct));
+    CK(ctx, cudaStreamWaitEvent(st, p.join, 0));
     if (ev) CK(ctx, cudaEventRecord(ev[3], st));
-    ctx->launches += 4;                     /* K3 (two kernels), K2, K2b */
+#undef LAUNCHED
     return RTJGPU_OK;
 }
 
@@ -314,6 +436,11 @@ int rtjgpu_create(int device, rtjgpu_ctx **out)
     rtjgpu_ctx *ctx = new (std::nothrow) rtjgpu_ctx();
     if (!ctx) return RTJGPU_E_NOMEM;
     ctx->device = device;
+    /* development knobs (tools/): slice sizes of the pipelined arrangement, K1's stream priority */
+    if (const char *v = getenv("RTJPEG_B200_SLICE")) ctx->slice_frames = ctx->slice0_frames = std::max(32, atoi(v));
+    if (const char *v = getenv("RTJPEG_B200_SLICE0")) ctx->slice0_frames = std::max(32, atoi(v));
+    if (const char *v = getenv("RTJPEG_B200_SCAN_PRIO")) ctx->scan_priority = atoi(v) != 0;
+    if (const char *v = getenv("RTJPEG_B200_PIPELINE")) ctx->pipeline_mode = atoi(v) == 1 ? RTJGPU_PIPELINE_SERIAL : RTJGPU_PIPELINE_AUTO;
     int rc = RTJGPU_OK;
     do {
         if ((e = cudaSetDevice(device)) != cudaSuccess) { rc = RTJGPU_E_CUDA; break; }
@@ -348,6 +475,7 @@ void rtjgpu_destroy(rtjgpu_ctx *ctx)
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     ws_release(&ctx->ws);
+    pipeline_release(&ctx->pipe);
     for (int i = 0; i < HOST_SLOTS; i++) {
         HostSlot &s = ctx->slot[i];
         ws_release(&s.ws);
@@ -385,6 +513,14 @@ int rtjgpu_set_scan_mode(rtjgpu_ctx *ctx, int mode)
 {
     if (!ctx || mode < RTJGPU_SCAN_AUTO || mode > RTJGPU_SCAN_SEGMENT) return RTJGPU_E_ARG;
     ctx->scan_mode = mode;
+    return RTJGPU_OK;
+}
+
+int rtjgpu_set_pipeline(rtjgpu_ctx *ctx, int mode, int slice_frames)
+{
+    if (!ctx || (mode != RTJGPU_PIPELINE_AUTO && mode != RTJGPU_PIPELINE_SERIAL) || slice_frames < 0) return RTJGPU_E_ARG;
+    ctx->pipeline_mode = mode;
+    if (slice_frames) ctx->slice_frames = ctx->slice0_frames = (slice_frames + RTJ_RESOLVE_T - 1) / RTJ_RESOLVE_T * RTJ_RESOLVE_T;
     return RTJGPU_OK;
 }
 
@@ -603,7 +739,7 @@ int rtjgpu_decode_device(rtjgpu_ctx *ctx, const uint8_t *d_stream, const rtjgpu_
     int rc = ws_reserve(ctx, &ctx->ws, F, nblk);
     if (rc) return rc;
     cudaEvent_t *ev = ctx->timing ? ctx->ev[ctx->timed_calls % TIMING_RING] : nullptr;
-    rc = run_kernels(ctx, &ctx->ws, d_stream, d_desc, F, w, h, d_out, d_carry, (cudaStream_t)cuda_stream, ev);
+    rc = run_kernels(ctx, &ctx->ws, d_stream, d_desc, F, w, h, d_out, d_carry, (cudaStream_t)cuda_stream, ev, true);
     if (ev && rc == RTJGPU_OK) ctx->timed_calls++;
     ctx->last_F = F;
     ctx->last_stream = cuda_stream;
@@ -674,18 +810,88 @@ int rtjgpu_get_entries(rtjgpu_ctx *ctx, uint32_t *entries, size_t n)
     return RTJGPU_OK;
 }
 
+/* nearest clean frame to `ideal` inside [lo, hi], the later one on a tie; -1: none */
+static int nearest_clean(const uint8_t *clean, int ideal, int lo, int hi)
+{
+    for (int d = 0; ideal - d >= lo || ideal + d <= hi; d++) {
+        if (ideal + d >= lo && ideal + d <= hi && clean[ideal + d]) return ideal + d;
+        if (ideal - d >= lo && ideal - d <= hi && clean[ideal - d]) return ideal - d;
+    }
+    return -1;
+}
+
 int rtjgpu_split_shards(const uint8_t *clean, int F, int n, int *first)
 {
     if (!clean || !first || n < 1 || F < 0) return RTJGPU_E_ARG;
     first[0] = 0;
+    int empty = 0;
     for (int i = 1; i < n; i++) {
-        /* ideal cut, then the nearest clean frame at or after it (never before the previous cut) */
-        long ideal = (long)F * i / n;
-        int cut = (int)std::max<long>(ideal, first[i - 1]);
-        while (cut < F && !clean[cut]) cut++;
+        /* the clean frame nearest to the ideal cut, behind the previous cut and leaving a frame for every later shard
+         * where the clean frames allow it; without any, the shard comes out empty -- and is counted */
+        const int ideal = (int)((long long)F * i / n);
+        const int lo = first[i - 1] + 1, hi = F - 1;
+        int cut = lo <= hi ? nearest_clean(clean, std::min(std::max(ideal, lo), hi), lo, hi) : -1;
+        if (cut < 0) cut = F;
         first[i] = cut;
     }
     first[n] = F;
+    for (int i = 0; i < n; i++) empty += first[i + 1] == first[i];
+    return F == 0 ? 0 : empty;
+}
+
+int rtjgpu_split_shards_lead(const uint8_t *clean, int F, int n, int *first, int *lead)
+{
+    if (!clean || !first || !lead || n < 1 || F < 0) return RTJGPU_E_ARG;
+    first[0] = 0;
+    lead[0] = 0;                                            /* frame 0 starts from the caller's picture */
+    const int win = std::max(1, F / (2 * n));              /* how far a cut may move to find a clean frame: half a shard */
+    for (int i = 1; i < n; i++) {
+        const int ideal = (int)((long long)F * i / n);
+        const int lo = std::min(first[i - 1] + 1, F);
+        const int hi = std::max(lo, F - (n - i));                          /* a frame for every shard, while F >= n */
+        const int at = std::min(std::max(ideal, lo), hi);
+        if (at >= F) { first[i] = F; lead[i] = 0; continue; }              /* fewer frames than shards: an empty one */
+        const int c = nearest_clean(clean, at, std::max(lo, at - win), std::min(hi, at + win));
+        if (c >= 0) { first[i] = c; lead[i] = 0; continue; }
+        /* no clean frame near: cut at the ideal place and decode again from the last clean frame before it --
+         * or from frame 0 and the caller's picture when there is none */
+        int back = at;
+        while (back > 0 && !clean[back]) back--;
+        first[i] = at;
+        lead[i] = at - back;
+    }
+    first[n] = F;
+    return RTJGPU_OK;
+}
+
+int rtjgpu_scan_device(rtjgpu_ctx *ctx, const uint8_t *d_stream, const rtjgpu_frame_desc *d_desc, int F, int w, int h,
+                       void *cuda_stream)
+{
+    if (!ctx || F < 0) return RTJGPU_E_ARG;
+    if (F == 0) { ctx->last_F = 0; return RTJGPU_OK; }
+    if (!d_stream || !d_desc || ((uintptr_t)d_stream & 3)) return RTJGPU_E_ARG;
+    if (w <= 0 || h <= 0 || (w & 15) || (h & 15) || w > 65535 || h > 65535) return RTJGPU_E_SIZE;
+    if (F > RTJGPU_MAX_FRAMES_PER_BATCH) return RTJGPU_E_TOOBIG;
+    CK(ctx, cudaSetDevice(ctx->device));
+    const int nblk = RTJ_FMT_NBLK(ctx->format, w, h);
+    if ((uint64_t)F * (uint64_t)nblk >= (1ull << 32)) return RTJGPU_E_TOOBIG;
+    int rc = ws_reserve(ctx, &ctx->ws, F, nblk);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    rtj_launch_args a;
+    memset(&a, 0, sizeof(a));
+    a.d_stream = d_stream; a.d_desc = d_desc; a.d_tables = ctx->d_tables;
+    a.F = F; a.w = w; a.h = h; a.f0 = 0; a.f1 = F; a.slice = 0;
+    a.fmt = ctx->format;
+    a.d_ent = ctx->ws.d_ent; a.d_frame_skips = ctx->ws.d_frame_skips; a.d_info = ctx->ws.d_info;
+    a.scan_mode = ctx->scan_mode;
+    if ((rc = seg_reserve(ctx, &ctx->ws, F, nblk, ctx->scan_mode, &a.seg))) return rc;
+    CK(ctx, cudaMemcpyAsync(ctx->ws.d_info, ctx->h_info_reset, sizeof(rtj_dev_info), cudaMemcpyHostToDevice, st));
+    const int e = rtj_launch_scan(&a, st);
+    if (e < 0) { ctx->last_cuda = -e; return RTJGPU_E_CUDA; }
+    ctx->launches += (uint64_t)e;
+    ctx->last_F = F;
+    ctx->last_stream = cuda_stream;
     return RTJGPU_OK;
 }
 
@@ -818,7 +1024,7 @@ int rtjgpu_decode_host(rtjgpu_ctx *ctx, const uint8_t *h_stream, const uint64_t 
         CK(ctx, cudaMemsetAsync(s.d_in + in_bytes, 0x7F, RTJGPU_STREAM_SLACK_BYTES, s.stream));
         CK(ctx, cudaMemcpyAsync(s.d_desc, s.h_desc, sizeof(rtjgpu_frame_desc) * (size_t)n, cudaMemcpyHostToDevice, s.stream));
         if (prev_decoded) CK(ctx, cudaStreamWaitEvent(s.stream, prev_decoded, 0));   /* carry comes from the previous chunk */
-        if ((rc = run_kernels(ctx, &s.ws, s.d_in, s.d_desc, n, w, h, s.d_out, d_prev, s.stream, nullptr))) { result = rc; break; }
+        if ((rc = run_kernels(ctx, &s.ws, s.d_in, s.d_desc, n, w, h, s.d_out, d_prev, s.stream, nullptr, false))) { result = rc; break; }
         CK(ctx, cudaEventRecord(s.decoded, s.stream));
         CK(ctx, cudaMemcpyAsync(s.h_info, s.ws.d_info, sizeof(rtj_dev_info), cudaMemcpyDeviceToHost, s.stream));
         prev_decoded = s.decoded;

@@ -73,6 +73,11 @@ void rtj_table_from_raw(const uint32_t raw[128], rtj_host_table *out); /* lib/RT
 void rtj_table_to_device_layout(const rtj_host_table *in, rtj_dev_table *out);
 void rtj_encoder_table_from_quality(int Q, int32_t qt[128], int *lb8, int *cb8);   /* lib/RTjpeg.c:2344-2369 + 277-286 */
 
+/* A batch is worked through in SLICES of frames (rtj_batch.cpp, run_kernels): K1 of slice s + 1 shares the SMs
+ * with K3 / K2 of slice s.  Slices are whole chunks of RTJ_RESOLVE_T frames, at most RTJ_MAX_SLICES per batch. */
+#define RTJ_RESOLVE_T  32
+#define RTJ_MAX_SLICES 128
+
 /* Device counters of one batch (lives in device memory, mirrored on request). */
 typedef struct rtj_dev_info {
     unsigned long long skipped_blocks;
@@ -81,6 +86,7 @@ typedef struct rtj_dev_info {
     int                first_bad_frame;
     unsigned int       hard_blocks;      /* K2 -> K2b queue: mid-size blocks, filled from the front ... */
     unsigned int       hard_full;        /* ... and long blocks, filled from the back */
+    unsigned int       slice_skips[RTJ_MAX_SLICES];   /* 0xFF markers per slice of frames (K1), what K3 decides on */
 } rtj_dev_info;
 
 /* ---- segment-parallel scan (few, large frames): a frame's 8 KB segments are parsed by separate
@@ -108,6 +114,8 @@ typedef struct rtj_launch_args {
     const rtjgpu_frame_desc *d_desc;
     const rtj_dev_table     *d_tables;
     int                      F, w, h;
+    int                      f0, f1;        /* the frames this launch covers (a slice); K1 segment-parallel and the serial flavours: 0, F */
+    int                      slice;         /* index of the slice [f0, f1) */
     int                      fmt;           /* RTJ_YUV420 / RTJ_YUV422 / RTJ_RGB8 */
     uint32_t                *d_ent;         /* [F][nblk] */
     uint16_t                *d_src;         /* [F][nblk] */
@@ -115,6 +123,8 @@ typedef struct rtj_launch_args {
     rtj_dev_info            *d_info;
     uint32_t                *d_hardq;       /* [F * nblk] global block indices queued for K2b */
     uint16_t                *d_chunk_last;  /* [ceil(F / 32)][nblk] K3: last writer inside each chunk of frames */
+    const uint16_t          *d_k3_in;       /* [nblk] K3: last writer before this slice (NULL: the first slice) */
+    uint16_t                *d_k3_out;      /* [nblk] K3: last writer before the next slice */
     uint8_t                 *d_out;
     const uint8_t           *d_carry;
     const void              *d_lut;         /* K2: position table of this geometry (rtj_launch_build_lut) */
@@ -129,7 +139,8 @@ int rtj_scan_chunk_init(void);
 int rtj_launch_scan_mb(const rtj_launch_args *a, int phase, void *stream);       /* rtj_scan_mb.cu */
 int rtj_scan_mb_init(void);
 int rtj_launch_resolve(const rtj_launch_args *a, void *stream);
-int rtj_launch_idct(const rtj_launch_args *a, void *stream);
+int rtj_launch_idct(const rtj_launch_args *a, void *stream);           /* K2 over the slice */
+int rtj_launch_idct_hard(const rtj_launch_args *a, void *stream);      /* K2b over the batch's queue, after the last slice */
 /* d_lut: rtj_lut_bytes() bytes -- where each block of a row of units goes, for K2 */
 size_t rtj_lut_bytes(int fmt, int w, int h);
 int rtj_launch_build_lut(int fmt, int w, int h, void *d_lut, void *stream);

@@ -467,6 +467,7 @@ struct K2Params {
     const uint32_t *ent;
     const uint16_t *srcf;
     int nblk, w, h, seg_mb, nstrips;
+    int f0, F;                       /* first frame of this launch (blockIdx.y = 0); frames of the batch */
     uint8_t *out;
     const uint8_t *carry;
     int fmt;
@@ -501,7 +502,7 @@ rtj_idct_kernel(const K2Params P)
     typedef Geo<FMT> G;
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const unsigned f = blockIdx.y;
+    const unsigned f = blockIdx.y + (unsigned)P.f0;
     const int w = P.w, h = P.h, mbw = w / G::UNIT_W;           /* units per picture row */
     const int strip = SINGLE ? 0 : (int)(blockIdx.x % (unsigned)P.nstrips);
     const int my = SINGLE ? (int)blockIdx.x : (int)(blockIdx.x / (unsigned)P.nstrips);
@@ -514,7 +515,7 @@ rtj_idct_kernel(const K2Params P)
     /* A CTA lives a few microseconds, of which the first read of its entries from DRAM -- under the write traffic of
      * this kernel -- is a good part.  So it asks for the entries of the CTA that will take its place when it retires
      * (same strip, P.ahead frames on) into L2 now. */
-    if (f + (unsigned)P.ahead < gridDim.y && tid * 32 < nb)
+    if (f + (unsigned)P.ahead < (unsigned)P.F && tid * 32 < nb)
         asm volatile("prefetch.global.L2 [%0];" :: "l"(my_ent + (size_t)P.ahead * (unsigned)P.nblk + tid * 32));
 
     uint8_t *tile = smem;                                            /* TILE * mbs bytes: Y, U, V */
@@ -623,11 +624,11 @@ rtj_idct_kernel(const K2Params P)
         nback += __popc(mB);
     }
     /* ... where this row held skipped blocks, the last writers of that frame's row (two bytes a block) ... */
-    if (f + (unsigned)P.ahead < gridDim.y && __any_sync(FULL, saw_skip) && lane * 64 < nb && warp == 0)
+    if (f + (unsigned)P.ahead < (unsigned)P.F && __any_sync(FULL, saw_skip) && lane * 64 < nb && warp == 0)
         asm volatile("prefetch.global.L2 [%0];" :: "l"(P.srcf + frame_blk0 + (size_t)P.ahead * (unsigned)P.nblk + lane * 64));
     /* ... and the part of that frame's payload where its blocks of this row should lie, if the payload is spread
      * evenly over the rows: the M7 blocks read it */
-    if (f + (unsigned)P.ahead < gridDim.y && warp == WARPS - 1 && lane < K2_PF_LINES) {
+    if (f + (unsigned)P.ahead < (unsigned)P.F && warp == WARPS - 1 && lane < K2_PF_LINES) {
         const rtjgpu_frame_desc nd = P.desc[f + (unsigned)P.ahead];
         const unsigned rows_total = SINGLE ? gridDim.x : gridDim.x / (unsigned)P.nstrips;
         const unsigned plen = nd.length > RTJPEG_B200_HEADER_BYTES ? nd.length - RTJPEG_B200_HEADER_BYTES : 0u;
@@ -948,12 +949,20 @@ extern "C" int rtj_launch_idct(const rtj_launch_args *a, void *stream)
     P.hardq_cap = (unsigned)((size_t)a->F * (size_t)P.nblk);
     P.fmt = fmt;
     P.pos = reinterpret_cast<const uint32_t *>(a->d_lut);
+    P.f0 = a->f0; P.F = a->F;
     const int grid_x = P.nstrips * uy;
-    cudaError_t e = fmt == 0 ? k2_launch<0>(P, grid_x, a->F, st) : fmt == 1 ? k2_launch<1>(P, grid_x, a->F, st) : k2_launch<2>(P, grid_x, a->F, st);
-    if (e != cudaSuccess) return (int)e;
+    const int nf = a->f1 - a->f0;
+    cudaError_t e = fmt == 0 ? k2_launch<0>(P, grid_x, nf, st) : fmt == 1 ? k2_launch<1>(P, grid_x, nf, st) : k2_launch<2>(P, grid_x, nf, st);
+    return (int)e;
+}
+
+extern "C" int rtj_launch_idct_hard(const rtj_launch_args *a, void *stream)
+{
     /* the queue's length is only known on the device: a fixed grid strides over it */
     const int sms = g_sm_count > 0 ? g_sm_count : 148;
-    rtj_idct_hard_kernel<<<sms * 4, 128, 0, st>>>(
-        a->d_stream, a->d_desc, a->d_tables, a->d_ent, a->d_src, P.nblk, a->w, a->h, fmt, a->d_out, a->d_hardq, P.hardq_cap, a->d_info);
+    const int nblk = RTJ_FMT_NBLK(a->fmt, a->w, a->h);
+    rtj_idct_hard_kernel<<<sms * 4, 128, 0, (cudaStream_t)stream>>>(
+        a->d_stream, a->d_desc, a->d_tables, a->d_ent, a->d_src, nblk, a->w, a->h, a->fmt, a->d_out, a->d_hardq,
+        (unsigned)((size_t)a->F * (size_t)nblk), a->d_info);
     return (int)cudaGetLastError();
 }

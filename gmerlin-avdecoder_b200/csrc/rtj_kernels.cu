@@ -150,7 +150,10 @@ rtj_scan_warp_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc
 
     if (lane == 0) {
         frame_skips[f] = (uint32_t)skips;
-        if (skips) atomicAdd(&info->skipped_blocks, (unsigned long long)skips);
+        if (skips) {
+            atomicAdd(&info->skipped_blocks, (unsigned long long)skips);
+            atomicAdd(&info->slice_skips[0], (unsigned)skips);          /* the serial flavours scan the batch in one go */
+        }
         atomicAdd(&info->payload_bytes, (unsigned long long)min(consumed, len));
         if (consumed > len || len > (int)RTJGPU_MAX_PAYLOAD_BYTES) {
             atomicAdd(&info->bad_frames, 1u);
@@ -297,7 +300,10 @@ rtj_scan_lane_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc
     const bool bad = res.blk < nblk || res.consumed > len;
     for (int b = res.blk; b < nblk; b++) out[b] = RTJ_ENT(len, 1);
     frame_skips[f] = (uint32_t)res.skips;
-    if (res.skips) atomicAdd(&info->skipped_blocks, (unsigned long long)res.skips);
+    if (res.skips) {
+        atomicAdd(&info->skipped_blocks, (unsigned long long)res.skips);
+        atomicAdd(&info->slice_skips[0], (unsigned)res.skips);
+    }
     atomicAdd(&info->payload_bytes, (unsigned long long)min(res.consumed, len));
     if (bad || len > (int)RTJGPU_MAX_PAYLOAD_BYTES) {
         atomicAdd(&info->bad_frames, 1u);
@@ -314,49 +320,67 @@ rtj_scan_lane_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc
  * frames -- serial in the reference, where it is simply "the picture persists" -- is spread over
  * F / RESOLVE_T times nblk threads:
  *   rtj_resolve_last_kernel   last frame of the chunk that coded the position (or none)
- *   rtj_resolve_kernel        carry-in = nearest earlier chunk with a writer (a short look-back,
- *                             usually one step), then the walk over the chunk's own frames that
- *                             gives every skipped block its last writer.
+ *   rtj_resolve_kernel        carry-in = nearest earlier chunk with a writer, then the walk over the
+ *                             chunk's own frames that gives every skipped block its last writer.
+ * Both work on one SLICE of the batch, frames [f0, f1) = chunks [c_lo, c_hi): the look-back stays inside
+ * the slice (a few chunks), and what lies before the slice comes as one value per position, `carry_in`,
+ * which the previous slice's last chunk left in its `carry_out`.  A slice whose frames -- and all frames
+ * before them -- hold no skip marker has nothing to resolve: every position was written by frame f1 - 1.
+ * (slice_skips[0 .. slice] are final when K3 of that slice runs; the batch-wide count is not, K1 of later
+ * slices may be running.)
  */
-constexpr int RESOLVE_T = 32;
+constexpr int RESOLVE_T = RTJ_RESOLVE_T;
+
+__device__ __forceinline__ bool k3_any_skips(const rtj_dev_info *__restrict__ info, int slice)
+{
+    unsigned any = 0;
+    for (int s = 0; s <= slice; s++) any |= info->slice_skips[s];
+    return any != 0;
+}
 
 extern "C" __global__ void __launch_bounds__(128)
-rtj_resolve_last_kernel(const uint32_t *__restrict__ ent, uint16_t *__restrict__ chunk_last, int F, int nblk,
-                        const rtj_dev_info *__restrict__ info)
+rtj_resolve_last_kernel(const uint32_t *__restrict__ ent, uint16_t *__restrict__ chunk_last, int f0, int f1, int nblk,
+                        const rtj_dev_info *__restrict__ info, int slice)
 {
-    if (info->skipped_blocks == 0) return;           /* intra-only batch: nothing to resolve */
+    if (!k3_any_skips(info, slice)) return;          /* nothing to resolve so far */
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nblk) return;
-    for (int c = blockIdx.y; c * RESOLVE_T < F; c += gridDim.y) {
-        const int f0 = c * RESOLVE_T, f1 = min(F, f0 + RESOLVE_T);
+    for (int c = f0 / RESOLVE_T + blockIdx.y; c * RESOLVE_T < f1; c += gridDim.y) {
+        const int fa = c * RESOLVE_T, fb = min(f1, fa + RESOLVE_T);
         unsigned last = RTJ_SRC_CARRY;
         uint32_t e[8];
-        int f = f0;
-        for (; f + 8 <= f1; f += 8) {
+        int f = fa;
+        for (; f + 8 <= fb; f += 8) {
 #pragma unroll
             for (int j = 0; j < 8; j++) e[j] = ent[(size_t)(f + j) * nblk + b];
 #pragma unroll
             for (int j = 0; j < 8; j++) if (!RTJ_ENT_IS_SKIP(e[j])) last = (unsigned)(f + j);
         }
-        for (; f < f1; f++) if (!RTJ_ENT_IS_SKIP(ent[(size_t)f * nblk + b])) last = (unsigned)f;
+        for (; f < fb; f++) if (!RTJ_ENT_IS_SKIP(ent[(size_t)f * nblk + b])) last = (unsigned)f;
         chunk_last[(size_t)c * nblk + b] = (uint16_t)last;
     }
 }
 
 extern "C" __global__ void __launch_bounds__(128)
 rtj_resolve_kernel(const uint32_t *__restrict__ ent, const uint16_t *__restrict__ chunk_last,
-                   uint16_t *__restrict__ src, int F, int nblk, const rtj_dev_info *__restrict__ info)
+                   uint16_t *__restrict__ src, int f0, int f1, int nblk, const rtj_dev_info *__restrict__ info, int slice,
+                   const uint16_t *__restrict__ carry_in, uint16_t *__restrict__ carry_out)
 {
-    if (info->skipped_blocks == 0) return;
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nblk) return;
-    for (int c0 = blockIdx.y; c0 * RESOLVE_T < F; c0 += gridDim.y) {
-        const int f0 = c0 * RESOLVE_T, f1 = min(F, f0 + RESOLVE_T);
+    if (!k3_any_skips(info, slice)) {
+        if (blockIdx.y == 0) carry_out[b] = (uint16_t)(f1 - 1);     /* every frame so far wrote every position */
+        return;
+    }
+    const int c_lo = f0 / RESOLVE_T;
+    for (int c0 = c_lo + blockIdx.y; c0 * RESOLVE_T < f1; c0 += gridDim.y) {
+        const int fa = c0 * RESOLVE_T, fb = min(f1, fa + RESOLVE_T);
         unsigned last = RTJ_SRC_CARRY;
-        for (int c = c0 - 1; c >= 0 && last == RTJ_SRC_CARRY; c--) last = chunk_last[(size_t)c * nblk + b];
+        for (int c = c0 - 1; c >= c_lo && last == RTJ_SRC_CARRY; c--) last = chunk_last[(size_t)c * nblk + b];
+        if (last == RTJ_SRC_CARRY && carry_in) last = carry_in[b];
         uint32_t e[8];
-        int f = f0;
-        for (; f + 8 <= f1; f += 8) {
+        int f = fa;
+        for (; f + 8 <= fb; f += 8) {
 #pragma unroll
             for (int j = 0; j < 8; j++) e[j] = ent[(size_t)(f + j) * nblk + b];
 #pragma unroll
@@ -365,11 +389,12 @@ rtj_resolve_kernel(const uint32_t *__restrict__ ent, const uint16_t *__restrict_
                 else last = (unsigned)(f + j);
             }
         }
-        for (; f < f1; f++) {
+        for (; f < fb; f++) {
             const uint32_t ee = ent[(size_t)f * nblk + b];
             if (RTJ_ENT_IS_SKIP(ee)) src[(size_t)f * nblk + b] = (uint16_t)last;
             else last = (unsigned)f;
         }
+        if (fb == f1) carry_out[b] = (uint16_t)last;                 /* the slice's last chunk: what the next slice starts from */
     }
 }
 
@@ -466,9 +491,10 @@ extern "C" int rtj_launch_resolve(const rtj_launch_args *a, void *stream)
     const int nblk = RTJ_FMT_NBLK(a->fmt, a->w, a->h);
     /* a batch without skip markers only pays for the launches: keep the grid modest and let a CTA
      * stride over the chunks of frames */
-    const int nchunks = (a->F + RESOLVE_T - 1) / RESOLVE_T;
+    const int nchunks = (a->f1 - a->f0 + RESOLVE_T - 1) / RESOLVE_T;    /* f0 is a multiple of RESOLVE_T */
     dim3 grid((unsigned)((nblk + 127) / 128), (unsigned)(nchunks < 16 ? nchunks : 16));
-    rtj_resolve_last_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(a->d_ent, a->d_chunk_last, a->F, nblk, a->d_info);
-    rtj_resolve_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(a->d_ent, a->d_chunk_last, a->d_src, a->F, nblk, a->d_info);
+    rtj_resolve_last_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(a->d_ent, a->d_chunk_last, a->f0, a->f1, nblk, a->d_info, a->slice);
+    rtj_resolve_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(a->d_ent, a->d_chunk_last, a->d_src, a->f0, a->f1, nblk, a->d_info,
+                                                               a->slice, a->d_k3_in, a->d_k3_out);
     return (int)cudaGetLastError();
 }

@@ -98,12 +98,12 @@ __global__ void __launch_bounds__(CS_THREADS, 8)
 rtj_scan_chunk_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc *__restrict__ desc,
                       const rtj_dev_table *__restrict__ tables, int F, int nblk,
                       uint32_t *__restrict__ ent, uint32_t *__restrict__ frame_skips,
-                      rtj_dev_info *__restrict__ info, const rtj_seg_plan sp)
+                      rtj_dev_info *__restrict__ info, const rtj_seg_plan sp, int f0, int slice)
 {
     extern __shared__ __align__(16) uint8_t cs_smem[];
     CsShared &sh = *reinterpret_cast<CsShared *>(cs_smem);
     const int tid = threadIdx.x, lane = tid & 31;
-    const int f = PHASE == 0 ? blockIdx.x : blockIdx.y;
+    const int f = (PHASE == 0 ? blockIdx.x : blockIdx.y) + f0;        /* F: one behind the last frame of this launch */
     if (f >= F) return;
     const rtjgpu_frame_desc d = desc[f];
     if (tables[d.table].bt8[0] | tables[d.table].bt8[1]) return;     /* raw prefix: the serial kernels' frame */
@@ -354,6 +354,7 @@ rtj_scan_chunk_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_des
             if (skips) {
                 atomicAdd(&frame_skips[f], (uint32_t)skips);
                 atomicAdd(&info->skipped_blocks, (unsigned long long)skips);
+                atomicAdd(&info->slice_skips[slice], (unsigned)skips);
             }
             if (nb0 < nbf && nbf <= sh.nb) {
                 const int consumed = sh.consumed;
@@ -373,7 +374,10 @@ rtj_scan_chunk_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_des
     if (tid == 0) {
         const int consumed = sh.consumed, skips = sh.skips;
         frame_skips[f] = (uint32_t)skips;
-        if (skips) atomicAdd(&info->skipped_blocks, (unsigned long long)skips);
+        if (skips) {
+            atomicAdd(&info->skipped_blocks, (unsigned long long)skips);
+            atomicAdd(&info->slice_skips[slice], (unsigned)skips);
+        }
         atomicAdd(&info->payload_bytes, (unsigned long long)min(consumed, len));
         if (nbf < nblk || consumed > len || len > (int)RTJGPU_MAX_PAYLOAD_BYTES) {
             atomicAdd(&info->bad_frames, 1u);
@@ -395,15 +399,16 @@ extern "C" int rtj_launch_scan_chunk(const rtj_launch_args *a, int phase, void *
     static_assert(CS_S == RTJ_SEG_BYTES, "segment size is shared with the frame-level chain");
     const int nblk = RTJ_FMT_NBLK(a->fmt, a->w, a->h);
     cudaStream_t st = (cudaStream_t)stream;
-    const dim3 grid = phase == 0 ? dim3((unsigned)a->F) : dim3((unsigned)a->seg.maxseg, (unsigned)a->F);
+    const int nf = a->f1 - a->f0;
+    const dim3 grid = phase == 0 ? dim3((unsigned)nf) : dim3((unsigned)a->seg.maxseg, (unsigned)nf);
     if (phase == 0)
         rtj_scan_chunk_kernel<0><<<grid, CS_THREADS, sizeof(CsShared), st>>>(
-            a->d_stream, a->d_desc, a->d_tables, a->F, nblk, a->d_ent, a->d_frame_skips, a->d_info, a->seg);
+            a->d_stream, a->d_desc, a->d_tables, a->f1, nblk, a->d_ent, a->d_frame_skips, a->d_info, a->seg, a->f0, a->slice);
     else if (phase == 1)
         rtj_scan_chunk_kernel<1><<<grid, CS_THREADS, sizeof(CsShared), st>>>(
-            a->d_stream, a->d_desc, a->d_tables, a->F, nblk, a->d_ent, a->d_frame_skips, a->d_info, a->seg);
+            a->d_stream, a->d_desc, a->d_tables, a->f1, nblk, a->d_ent, a->d_frame_skips, a->d_info, a->seg, a->f0, a->slice);
     else
         rtj_scan_chunk_kernel<2><<<grid, CS_THREADS, sizeof(CsShared), st>>>(
-            a->d_stream, a->d_desc, a->d_tables, a->F, nblk, a->d_ent, a->d_frame_skips, a->d_info, a->seg);
+            a->d_stream, a->d_desc, a->d_tables, a->f1, nblk, a->d_ent, a->d_frame_skips, a->d_info, a->seg, a->f0, a->slice);
     return (int)cudaGetLastError();
 }

@@ -107,13 +107,13 @@ __global__ void __launch_bounds__(MB_THREADS, 7)
 rtj_scan_mb_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc *__restrict__ desc,
                    const rtj_dev_table *__restrict__ tables, int F, int nblk,
                    uint32_t *__restrict__ ent, uint32_t *__restrict__ frame_skips,
-                   rtj_dev_info *__restrict__ info, const rtj_seg_plan sp)
+                   rtj_dev_info *__restrict__ info, const rtj_seg_plan sp, int f0, int slice)
 {
     constexpr int unit = RTJ_FMT_UNIT_BLOCKS(FMT), unit_luma = RTJ_FMT_UNIT_LUMA(FMT);
     extern __shared__ __align__(16) uint8_t mb_smem[];
     MbShared &sh = *reinterpret_cast<MbShared *>(mb_smem);
     const int tid = threadIdx.x, lane = tid & 31;
-    const int f = PHASE == 0 ? blockIdx.x : blockIdx.y;
+    const int f = (PHASE == 0 ? blockIdx.x : blockIdx.y) + f0;        /* F: one behind the last frame of this launch */
     if (f >= F) return;
     const rtjgpu_frame_desc d = desc[f];
     const int lb8 = tables[d.table].bt8[0], cb8 = tables[d.table].bt8[1];
@@ -343,6 +343,7 @@ rtj_scan_mb_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc *
             if (skips) {
                 atomicAdd(&frame_skips[f], (uint32_t)skips);
                 atomicAdd(&info->skipped_blocks, (unsigned long long)skips);
+                atomicAdd(&info->slice_skips[slice], (unsigned)skips);
             }
             if (nb0 < nbf && nbf <= sh.nb) {
                 const int consumed = sh.consumed;
@@ -362,7 +363,10 @@ rtj_scan_mb_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc *
     if (tid == 0) {
         const int consumed = sh.consumed, skips = sh.skips;
         frame_skips[f] = (uint32_t)skips;
-        if (skips) atomicAdd(&info->skipped_blocks, (unsigned long long)skips);
+        if (skips) {
+            atomicAdd(&info->skipped_blocks, (unsigned long long)skips);
+            atomicAdd(&info->slice_skips[slice], (unsigned)skips);
+        }
         atomicAdd(&info->payload_bytes, (unsigned long long)min(consumed, len));
         if (nbf < nblk || consumed > len || len > (int)RTJGPU_MAX_PAYLOAD_BYTES) {
             atomicAdd(&info->bad_frames, 1u);
@@ -376,16 +380,17 @@ namespace {
 template <int FMT>
 cudaError_t scan_mb_launch(const rtj_launch_args *a, int phase, int nblk, cudaStream_t st)
 {
-    const dim3 grid = phase == 0 ? dim3((unsigned)a->F) : dim3((unsigned)a->seg.maxseg, (unsigned)a->F);
+    const int nf = a->f1 - a->f0;
+    const dim3 grid = phase == 0 ? dim3((unsigned)nf) : dim3((unsigned)a->seg.maxseg, (unsigned)nf);
     if (phase == 0)
         rtj_scan_mb_kernel<0, FMT><<<grid, MB_THREADS, sizeof(MbShared), st>>>(
-            a->d_stream, a->d_desc, a->d_tables, a->F, nblk, a->d_ent, a->d_frame_skips, a->d_info, a->seg);
+            a->d_stream, a->d_desc, a->d_tables, a->f1, nblk, a->d_ent, a->d_frame_skips, a->d_info, a->seg, a->f0, a->slice);
     else if (phase == 1)
         rtj_scan_mb_kernel<1, FMT><<<grid, MB_THREADS, sizeof(MbShared), st>>>(
-            a->d_stream, a->d_desc, a->d_tables, a->F, nblk, a->d_ent, a->d_frame_skips, a->d_info, a->seg);
+            a->d_stream, a->d_desc, a->d_tables, a->f1, nblk, a->d_ent, a->d_frame_skips, a->d_info, a->seg, a->f0, a->slice);
     else
         rtj_scan_mb_kernel<2, FMT><<<grid, MB_THREADS, sizeof(MbShared), st>>>(
-            a->d_stream, a->d_desc, a->d_tables, a->F, nblk, a->d_ent, a->d_frame_skips, a->d_info, a->seg);
+            a->d_stream, a->d_desc, a->d_tables, a->f1, nblk, a->d_ent, a->d_frame_skips, a->d_info, a->seg, a->f0, a->slice);
     return cudaGetLastError();
 }
 

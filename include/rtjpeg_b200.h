@@ -146,7 +146,9 @@ typedef struct rtjgpu_state {
 } rtjgpu_state;
 
 /* Per-stage device time of the last rtjgpu_decode_device call, milliseconds
- * (CUDA events on the launch stream; filled only when timing is enabled). */
+ * (CUDA events on the launch stream; filled only when timing is enabled).  In the pipelined arrangement
+ * (rtjgpu_set_pipeline) the stages overlap: scan_ms is then the time until the last slice is scanned,
+ * resolve_ms 0 and idct_ms the remainder. */
 typedef struct rtjgpu_timing {
     float scan_ms;      /* K1 block-offset scan */
     float resolve_ms;   /* K3 last-writer resolution (0 when the batch has no skipped block) */
@@ -181,6 +183,16 @@ int  rtjgpu_last_cuda_error(const rtjgpu_ctx *ctx);
 #define RTJGPU_SCAN_CHUNK   3
 #define RTJGPU_SCAN_SEGMENT 4
 int  rtjgpu_set_scan_mode(rtjgpu_ctx *ctx, int mode);
+
+/* How a large device batch is worked through.  AUTO (the default): in slices of frames, the scan of slice s + 1 on
+ * a second CUDA stream beside resolve + IDCT of slice s (the stages are bound by different pipes of the SM and fill
+ * each other's idle issue slots); the call still orders everything after the work already on cuda_stream and
+ * cuda_stream after its own work.  SERIAL: every stage on cuda_stream, one after the other -- per-stage times
+ * (rtjgpu_timing) are only separable in this arrangement.  slice_frames: frames per slice, 0 = keep the current
+ * value (default 576); rounded up to a multiple of 32. */
+#define RTJGPU_PIPELINE_AUTO   0
+#define RTJGPU_PIPELINE_SERIAL 1
+int  rtjgpu_set_pipeline(rtjgpu_ctx *ctx, int mode, int slice_frames);
 
 /* Picture format of the batches this context decodes (RTJ_YUV420, the default, RTJ_YUV422 or RTJ_RGB8 =
  * 8-bit grey): what RTjpeg_set_format is to an RTjpeg_t (lib/RTjpeg.c:2421, dispatch :3580-3585).  Frames
@@ -271,12 +283,27 @@ int  rtjgpu_get_skip_counts(rtjgpu_ctx *ctx, uint32_t *counts, int F);
 /* Number of kernels this library has launched on the context so far. */
 uint64_t rtjgpu_launch_count(const rtjgpu_ctx *ctx);
 
-/* Host-side multi-GPU split: cut F frames into n contiguous shards of roughly
- * equal frame count such that every shard starts on a clean frame
- * (clean[f] != 0).  first[n+1] receives the shard starts (first[n] = F).  A
- * shard may come out empty when there are not enough clean frames.  Pure host
- * arithmetic, no CUDA. */
+/* K1 alone: the block-offset scan of a device-resident batch, without decoding it.  Afterwards rtjgpu_get_skip_counts
+ * and rtjgpu_get_batch_info tell which frames are clean and whether every packet holds its picture -- what a host needs
+ * to cut an inter-coded stream into shards before it decodes anything.  Same arguments as rtjgpu_decode_device. */
+int  rtjgpu_scan_device(rtjgpu_ctx *ctx, const uint8_t *d_stream, const rtjgpu_frame_desc *d_desc, int F, int w, int h,
+                        void *cuda_stream);
+
+/* Host-side multi-GPU split (pure host arithmetic, no CUDA).  Frames are coded against the picture before them
+ * (lib/video_rtjpeg.c:81 decodes every packet into one persistent frame; a block marked 0xFF keeps what is there,
+ * lib/RTjpeg.c:2704), so a stream can only be cut where the next frame rewrites everything: at a CLEAN frame
+ * (clean[f] != 0: no skip marker in frame f, rtjgpu_get_skip_counts; the header's `key` byte is only a hint).
+ *
+ * rtjgpu_split_shards: n contiguous shards of roughly equal frame count, every cut on the clean frame nearest to the
+ * ideal place (behind the previous cut).  first[n + 1] receives the shard starts (first[n] = F).  Returns the number
+ * of shards that came out EMPTY because the clean frames ran out (0 = every shard has work), or a negative RTJGPU_E_*.
+ *
+ * rtjgpu_split_shards_lead: never an empty shard while F >= n.  A cut moves at most half a shard to reach a clean frame;
+ * where there is none it stays at the ideal place and lead[i] tells how many frames BEFORE first[i] shard i has to
+ * decode as well (back to the last clean frame, or to frame 0 and the caller's picture) and throw away: shard i
+ * decodes frames [first[i] - lead[i], first[i + 1]) and keeps the last first[i + 1] - first[i] of them. */
 int  rtjgpu_split_shards(const uint8_t *clean, int F, int n, int *first);
+int  rtjgpu_split_shards_lead(const uint8_t *clean, int F, int n, int *first, int *lead);
 
 /* Host-only table derivation, no CUDA involved (what the context uploads at
  * creation): the 128 AAN-scaled entries RTjpeg_get_tables would return after

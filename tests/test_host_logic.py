@@ -136,14 +136,48 @@ def test_split_shards_cuts_only_on_clean_frames():
     clean[::30] = 1                                      # GOP 30, every key frame clean
     first = g.split_shards(clean, 4)
     assert list(first) == [0, 30, 60, 90, 120]
-    first = g.split_shards(clean, 3)                     # ideal cuts 40, 80 -> next clean frames 60, 90
-    assert list(first) == [0, 60, 90, 120]
+    first = g.split_shards(clean, 3)                     # ideal cuts 40, 80 -> the nearest clean frames 30, 90
+    assert list(first) == [0, 30, 90, 120]
     clean[:] = 0
-    clean[0] = 1                                         # nothing clean after frame 0: the path does not shard
+    clean[0] = 1                                         # nothing clean after frame 0: the path does not shard ...
     assert list(g.split_shards(clean, 4)) == [0, 120, 120, 120, 120]
+    with pytest.raises(ValueError):                      # ... and says so when asked to
+        g.split_shards(clean, 4, allow_empty=False)
     clean[:] = 1                                         # intra-only: equal split
     assert list(g.split_shards(clean, 8)) == [0, 15, 30, 45, 60, 75, 90, 105, 120]
     assert list(g.split_shards(np.zeros(0, dtype=np.uint8), 2)) == [0, 0, 0]
+
+
+def test_split_shards_lead_never_leaves_a_shard_empty():
+    F = 120
+    clean = np.zeros(F, dtype=np.uint8)
+    clean[::30] = 1
+    first, lead = g.split_shards_lead(clean, 4)
+    assert list(first) == [0, 30, 60, 90, 120] and list(lead) == [0, 0, 0, 0]
+    first, lead = g.split_shards_lead(clean, 8)          # ideal cuts 15, 30, 45 ...: half of them have no clean frame within 7
+    assert list(first) == [0, 15, 30, 45, 60, 75, 90, 105, 120]
+    assert list(lead) == [0, 15, 0, 15, 0, 15, 0, 15]
+    clean[:] = 0                                         # no clean frame at all, not even frame 0: everything from the start
+    first, lead = g.split_shards_lead(clean, 4)
+    assert list(first) == [0, 30, 60, 90, 120] and list(lead) == [0, 30, 60, 90]
+    clean[:] = 0
+    clean[50] = 1                                        # one clean frame: cuts near it snap to it, later ones lead back to it
+    first, lead = g.split_shards_lead(clean, 4)
+    assert list(first) == [0, 30, 50, 90, 120] and list(lead) == [0, 30, 0, 40]
+    rng = np.random.default_rng(3)
+    for _ in range(200):                                 # every shard has work while F >= n; leads end on a clean frame or 0
+        F = int(rng.integers(1, 300))
+        n = int(rng.integers(1, 9))
+        clean = (rng.random(F) < rng.choice([0.0, 0.02, 0.2, 1.0])).astype(np.uint8)
+        first, lead = g.split_shards_lead(clean, n)
+        assert first[0] == 0 and first[-1] == F and (np.diff(first) >= 0).all()
+        if F >= n:
+            assert (np.diff(first) > 0).all()
+        for i in range(n):
+            a = int(first[i] - lead[i])
+            assert a >= 0 and (lead[i] == 0 or a == 0 or clean[a])
+            if i and lead[i] == 0 and first[i] < F and first[i + 1] > first[i]:
+                assert clean[first[i]]
 
 
 def test_split_shards_agrees_with_oracle_decode():

@@ -1,12 +1,14 @@
 """The N>1 path on CPU: two ranks over gloo, each owning one shard of an inter-coded stream.
 
 The data path has no collective: a batch is cut on the host at clean
-frames (rtjgpu_split_shards) and every rank decodes its shard from nothing.  What can be
+frames (rtjgpu_split_shards_lead) and every rank decodes its shard from nothing.  What can be
 checked without a GPU is the host-side logic: that every rank derives the same cut from the
-same per-frame skip counts, that the shards tile the batch, and that decoding the shards
-independently reproduces the sequential picture sequence.  The oracle stands in for the
-decode here -- as the checker, the only role it is allowed (bench.py's N>1 GPU run does the
-same split with the CUDA decoder behind it)."""
+same per-frame skip counts, that the shards tile the batch, that a shard which cannot start on
+a clean frame leads back to one, and that decoding the shards independently reproduces the
+sequential picture sequence.  The ORACLE stands in for the decoder here -- as the checker, the
+only role it is allowed.  The CUDA decode of independently started shards is what
+tests/test_gpu_shards.py checks on the GPU box, and bench.py's `config5` leg times it with one
+rank per GPU."""
 import hashlib
 import os
 import socket
@@ -36,7 +38,7 @@ def _clean_frames(s, o, w, h, Q):
                      for f in range(len(o) - 1)], dtype=np.uint8)
 
 
-def _rank_main(rank, world, port, name, w, h, Q, out_dir):
+def _rank_main(rank, world, port, name, w, h, Q, out_dir, mask_clean):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -45,12 +47,18 @@ def _rank_main(rank, world, port, name, w, h, Q, out_dir):
         s, o = gd["stream"], gd["offsets"]
         F = len(o) - 1
         clean = _clean_frames(s, o, w, h, Q)
-        first = g.split_shards(clean, world)                    # every rank computes the same cut
-        cuts = [torch.zeros(world + 1, dtype=torch.int64) for _ in range(world)]
-        dist.all_gather(cuts, torch.from_numpy(first.copy()))
+        if mask_clean:                                          # pretend the clean frames near the cut are not: the shard must lead back
+            clean = clean.copy()
+            clean[F // 2 - 2:F // 2 + 3] = 0
+        first, lead = g.split_shards_lead(clean, world)         # every rank computes the same cut
+        cuts = [torch.zeros(2 * world + 1, dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(cuts, torch.from_numpy(np.concatenate([first, lead])))
         assert all(torch.equal(c, cuts[0]) for c in cuts)
         a, b = int(first[rank]), int(first[rank + 1])
-        frames = O.decode_stream(s, o[a:b + 1], w, h) if b > a else np.zeros((0, w * h * 3 // 2), np.uint8)
+        assert b > a and (not mask_clean or rank == 0 or lead[rank] > 0)
+        lo = a - int(lead[rank])
+        garbage = np.full(w * h * 3 // 2, 0xA5, dtype=np.uint8)   # a shard that does not start at frame 0 starts from anything
+        frames = O.decode_stream(s, o[lo:b + 1], w, h, init=None if lo == 0 else garbage)[a - lo:]
         # per-frame digests travel, the frames stay where they were decoded
         dig = torch.zeros(F, 16, dtype=torch.uint8)
         for i in range(b - a):
@@ -69,10 +77,11 @@ def _rank_main(rank, world, port, name, w, h, Q, out_dir):
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("mask_clean", [False, True])
 @pytest.mark.parametrize("name,w,h,Q", [("inter_64x48_q200_gop6", 64, 48, 200)])
-def test_two_ranks_decode_disjoint_shards(tmp_path, name, w, h, Q):
+def test_two_ranks_decode_disjoint_shards(tmp_path, name, w, h, Q, mask_clean):
     world = 2
-    mp.spawn(_rank_main, args=(world, _free_port(), name, w, h, Q, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_rank_main, args=(world, _free_port(), name, w, h, Q, str(tmp_path), mask_clean), nprocs=world, join=True)
     assert (tmp_path / "ok").exists()
 
 

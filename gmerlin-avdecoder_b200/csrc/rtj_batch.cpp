@@ -111,6 +111,8 @@ struct rtjgpu_ctx {
     uint64_t      *h_enc_total = nullptr;     /* pinned */
     void          *enc_stream = nullptr;
     uint64_t       host_bad = 0;              /* overrun frames seen by the current rtjgpu_decode_host call */
+    uint32_t      *h_host_skips = nullptr;    size_t host_skips_cap = 0;   /* pinned: per-frame skip counts of that call */
+    int            host_F = 0;
 };
 
 namespace {
@@ -490,6 +492,7 @@ void rtjgpu_destroy(rtjgpu_ctx *ctx)
         if (s.stream) cudaStreamDestroy(s.stream);
     }
     if (ctx->d_host_carry) cudaFree(ctx->d_host_carry);
+    if (ctx->h_host_skips) cudaFreeHost(ctx->h_host_skips);
     if (ctx->d_enc_qt) cudaFree(ctx->d_enc_qt);
     if (ctx->d_enc_old) cudaFree(ctx->d_enc_old);
     if (ctx->d_enc_slots) cudaFree(ctx->d_enc_slots);
@@ -673,14 +676,20 @@ int rtjgpu_set_custom_tables(rtjgpu_ctx *ctx, const uint32_t raw[128])
     rtj_table_from_raw(raw, &ctx->h_tables[RTJGPU_TABLE_CUSTOM]);
     rtj_dev_table dev;
     rtj_table_to_device_layout(&ctx->h_tables[RTJGPU_TABLE_CUSTOM], &dev);
-    /* ordered after everything already queued on the device */
-    CK(ctx, cudaDeviceSynchronize());
+    /* ordered after the batches this context has queued (its own streams and the caller's last one); other contexts'
+     * work on the device is none of its business */
+    if (cudaStreamSynchronize((cudaStream_t)ctx->last_stream) != cudaSuccess) {    /* the caller's stream may be gone by now */
+        cudaGetLastError();
+        CK(ctx, cudaDeviceSynchronize());
+    }
+    if (ctx->pipe.ready) { CK(ctx, cudaStreamSynchronize(ctx->pipe.scan)); CK(ctx, cudaStreamSynchronize(ctx->pipe.idct)); }
+    if (ctx->slots_ready) for (int i = 0; i < HOST_SLOTS; i++) CK(ctx, cudaStreamSynchronize(ctx->slot[i].stream));
     CK(ctx, cudaMemcpy(ctx->d_tables + RTJGPU_TABLE_CUSTOM, &dev, sizeof(dev), cudaMemcpyHostToDevice));
     return RTJGPU_OK;
 }
 
 /* internal: host tables in the reference's raster order (for RTjpeg_get_tables) */
-const rtj_host_table *rtjgpu_host_table(const rtjgpu_ctx *ctx, int table)
+const rtj_host_table *rtj_ctx_host_table(const rtjgpu_ctx *ctx, int table)
 {
     if (!ctx || table < 0 || table >= RTJ_NUM_TABLES) return nullptr;
     return &ctx->h_tables[table];
@@ -688,23 +697,34 @@ const rtj_host_table *rtjgpu_host_table(const rtjgpu_ctx *ctx, int table)
 
 int rtjgpu_plan(const uint8_t *stream, const uint64_t *offsets, int F, rtjgpu_state *state, rtjgpu_frame_desc *desc)
 {
+    return rtjgpu_plan_n(stream, offsets, nullptr, F, state, desc);
+}
+
+int rtjgpu_plan_n(const uint8_t *stream, const uint64_t *offsets, const uint32_t *lengths, int F, rtjgpu_state *state,
+                  rtjgpu_frame_desc *desc)
+{
     if (!stream || !offsets || !state || (F > 0 && !desc) || F < 0) return RTJGPU_E_ARG;
     if (F > RTJGPU_MAX_FRAMES_PER_BATCH) return RTJGPU_E_TOOBIG;
     rtjgpu_state st = *state;
     int bw = 0, bh = 0;
     for (int f = 0; f < F; f++) {
         if (offsets[f + 1] < offsets[f]) return RTJGPU_E_ARG;
-        const uint64_t avail = offsets[f + 1] - offsets[f];
+        uint64_t avail = offsets[f + 1] - offsets[f];
+        if (lengths) {
+            if (lengths[f] > avail) return RTJGPU_E_ARG;
+            avail = lengths[f];
+        }
         if (avail < RTJPEG_B200_HEADER_BYTES) return RTJGPU_E_HEADER;
         if (offsets[f] & 3u) return RTJGPU_E_ARG;
         const uint8_t *p = stream + offsets[f];
         /* packed little-endian header, include/RTjpeg.h:100-109 */
         const uint32_t framesize = rd_u32le(p);
         const int w = rd_u16le(p + 6), h = rd_u16le(p + 8), q = p[10];
-        /* the reference never reads framesize/headersize (lib/RTjpeg.c:3565-3586); here the
-         * smaller of framesize and the bytes actually present bounds every read */
+        /* the reference never reads framesize/headersize (lib/RTjpeg.c:3565-3586).  With the packets' true lengths
+         * given, neither does this; without them the slot [offsets[f], offsets[f + 1]) may end in alignment padding,
+         * and the smaller of framesize and the slot bounds every read */
         uint64_t len = avail;
-        if (framesize >= RTJPEG_B200_HEADER_BYTES && framesize < len) len = framesize;
+        if (!lengths && framesize >= RTJPEG_B200_HEADER_BYTES && framesize < len) len = framesize;
         if (len - RTJPEG_B200_HEADER_BYTES > RTJGPU_MAX_PAYLOAD_BYTES) return RTJGPU_E_TOOBIG;
         if (w != st.width || h != st.height) { st.width = w; st.height = h; }   /* :3568-3574 */
         if (w == 0 || h == 0 || (w & 15) || (h & 15)) return RTJGPU_E_SIZE;     /* the row loop of :2701 needs /16 */
@@ -730,6 +750,8 @@ int rtjgpu_decode_device(rtjgpu_ctx *ctx, const uint8_t *d_stream, const rtjgpu_
     if (!ctx || F < 0) return RTJGPU_E_ARG;
     if (F == 0) { ctx->last_F = 0; return RTJGPU_OK; }
     if (!d_stream || !d_desc || !d_out) return RTJGPU_E_ARG;
+    /* K1 reads the stream as 32-bit words, K2 leaves its strips as 16-byte bulk stores and reads the carry as 8-byte rows */
+    if (((uintptr_t)d_stream & 3) || ((uintptr_t)d_desc & 7) || ((uintptr_t)d_out & 15) || ((uintptr_t)d_carry & 7)) return RTJGPU_E_ARG;
     if (w <= 0 || h <= 0 || (w & 15) || (h & 15) || w > 65535 || h > 65535) return RTJGPU_E_SIZE;
     if (F > RTJGPU_MAX_FRAMES_PER_BATCH) return RTJGPU_E_TOOBIG;
     CK(ctx, cudaSetDevice(ctx->device));
@@ -803,7 +825,7 @@ int rtjgpu_get_skip_counts(rtjgpu_ctx *ctx, uint32_t *counts, int F)
 }
 
 /* internal, for the Level-1 shim: block entries of the last device batch */
-int rtjgpu_get_entries(rtjgpu_ctx *ctx, uint32_t *entries, size_t n)
+int rtj_ctx_get_entries(rtjgpu_ctx *ctx, uint32_t *entries, size_t n)
 {
     if (!ctx || !entries) return RTJGPU_E_ARG;
     CK(ctx, cudaMemcpy(entries, ctx->ws.d_ent, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
@@ -947,17 +969,26 @@ static int slots_init(rtjgpu_ctx *ctx)
 static int slot_drain(rtjgpu_ctx *ctx, HostSlot &s)
 {
     if (!s.busy) return RTJGPU_OK;
-    CK(ctx, cudaStreamSynchronize(s.stream));
-    ctx->host_bad += s.h_info->bad_frames;
-    if (s.pending_dst) memcpy(s.pending_dst, s.h_out, s.pending_bytes);
-    s.pending_dst = nullptr;
+    const cudaError_t e = cudaStreamSynchronize(s.stream);
+    if (e == cudaSuccess) {
+        ctx->host_bad += s.h_info->bad_frames;
+        if (s.pending_dst) memcpy(s.pending_dst, s.h_out, s.pending_bytes);
+    }
+    s.pending_dst = nullptr;              /* whatever happened: never again touch the memory of the call that queued this */
     s.pending_bytes = 0;
     s.busy = false;
+    if (e != cudaSuccess) { ctx->last_cuda = (int)e; return RTJGPU_E_CUDA; }
     return RTJGPU_OK;
 }
 
 int rtjgpu_decode_host(rtjgpu_ctx *ctx, const uint8_t *h_stream, const uint64_t *offsets, int F,
                        rtjgpu_state *state, uint8_t *h_out, uint8_t *h_carry_inout, int flags)
+{
+    return rtjgpu_decode_host_n(ctx, h_stream, offsets, nullptr, F, state, h_out, h_carry_inout, flags);
+}
+
+int rtjgpu_decode_host_n(rtjgpu_ctx *ctx, const uint8_t *h_stream, const uint64_t *offsets, const uint32_t *lengths, int F,
+                         rtjgpu_state *state, uint8_t *h_out, uint8_t *h_carry_inout, int flags)
 {
     if (!ctx || !state || F < 0) return RTJGPU_E_ARG;
     if (F == 0) return RTJGPU_OK;
@@ -967,7 +998,7 @@ int rtjgpu_decode_host(rtjgpu_ctx *ctx, const uint8_t *h_stream, const uint64_t 
     if (rc) return rc;
 
     /* geometry from the first header; rtjgpu_plan re-checks every frame */
-    if (offsets[1] - offsets[0] < RTJPEG_B200_HEADER_BYTES) return RTJGPU_E_HEADER;
+    if ((lengths ? (uint64_t)lengths[0] : offsets[1] - offsets[0]) < RTJPEG_B200_HEADER_BYTES) return RTJGPU_E_HEADER;
     const int w = rd_u16le(h_stream + offsets[0] + 6), h = rd_u16le(h_stream + offsets[0] + 8);
     if (w == 0 || h == 0 || (w & 15) || (h & 15)) return RTJGPU_E_SIZE;
     const size_t fsz = RTJ_FMT_FRAME_BYTES(ctx->format, w, h);
@@ -981,6 +1012,8 @@ int rtjgpu_decode_host(rtjgpu_ctx *ctx, const uint8_t *h_stream, const uint64_t 
 
     rc = grow_device(ctx, &ctx->d_host_carry, &ctx->d_host_carry_cap, fsz);
     if (rc) return rc;
+    if ((rc = grow_pinned(ctx, &ctx->h_host_skips, &ctx->host_skips_cap, (size_t)F))) return rc;
+    ctx->host_F = 0;
     const bool have_carry = h_carry_inout != nullptr;
     if (have_carry)
         CK(ctx, cudaMemcpy(ctx->d_host_carry, h_carry_inout, fsz, cudaMemcpyHostToDevice));
@@ -990,7 +1023,12 @@ int rtjgpu_decode_host(rtjgpu_ctx *ctx, const uint8_t *h_stream, const uint64_t 
     rtjgpu_state st = *state;
     int result = RTJGPU_OK;
     ctx->host_bad = 0;
+    std::vector<uint64_t> rel;
 
+    /* inside the loop a failing CUDA call must not return: the slots already in flight hold pointers into this call's
+     * h_out and have to be drained first */
+#define CKB(call)                                                                          \
+    { const cudaError_t e__ = (call); if (e__ != cudaSuccess) { ctx->last_cuda = (int)e__; result = RTJGPU_E_CUDA; break; } }
     for (int c0 = 0, ci = 0; c0 < F; c0 += chunk, ci++) {
         const int n = std::min(chunk, F - c0);
         HostSlot &s = ctx->slot[ci % HOST_SLOTS];
@@ -1009,9 +1047,9 @@ int rtjgpu_decode_host(rtjgpu_ctx *ctx, const uint8_t *h_stream, const uint64_t 
         if ((rc = ws_reserve(ctx, &s.ws, n, nblk))) { result = rc; break; }
 
         /* descriptors relative to the chunk's own device buffer */
-        std::vector<uint64_t> rel((size_t)n + 1);
+        rel.resize((size_t)n + 1);
         for (int i = 0; i <= n; i++) rel[(size_t)i] = offsets[c0 + i] - b0;
-        if ((rc = rtjgpu_plan(h_stream + b0, rel.data(), n, &st, s.h_desc))) { result = rc; break; }
+        if ((rc = rtjgpu_plan_n(h_stream + b0, rel.data(), lengths ? lengths + c0 : nullptr, n, &st, s.h_desc))) { result = rc; break; }
         if (st.width != w || st.height != h) { result = RTJGPU_E_SIZE; break; }
 
         const uint8_t *src = h_stream + b0;
@@ -1020,28 +1058,30 @@ int rtjgpu_decode_host(rtjgpu_ctx *ctx, const uint8_t *h_stream, const uint64_t 
             memcpy(s.h_in, src, in_bytes);
             src = s.h_in;
         }
-        CK(ctx, cudaMemcpyAsync(s.d_in, src, in_bytes, cudaMemcpyHostToDevice, s.stream));
-        CK(ctx, cudaMemsetAsync(s.d_in + in_bytes, 0x7F, RTJGPU_STREAM_SLACK_BYTES, s.stream));
-        CK(ctx, cudaMemcpyAsync(s.d_desc, s.h_desc, sizeof(rtjgpu_frame_desc) * (size_t)n, cudaMemcpyHostToDevice, s.stream));
-        if (prev_decoded) CK(ctx, cudaStreamWaitEvent(s.stream, prev_decoded, 0));   /* carry comes from the previous chunk */
+        CKB(cudaMemcpyAsync(s.d_in, src, in_bytes, cudaMemcpyHostToDevice, s.stream));
+        CKB(cudaMemsetAsync(s.d_in + in_bytes, 0x7F, RTJGPU_STREAM_SLACK_BYTES, s.stream));
+        CKB(cudaMemcpyAsync(s.d_desc, s.h_desc, sizeof(rtjgpu_frame_desc) * (size_t)n, cudaMemcpyHostToDevice, s.stream));
+        if (prev_decoded) CKB(cudaStreamWaitEvent(s.stream, prev_decoded, 0));   /* carry comes from the previous chunk */
         if ((rc = run_kernels(ctx, &s.ws, s.d_in, s.d_desc, n, w, h, s.d_out, d_prev, s.stream, nullptr, false))) { result = rc; break; }
-        CK(ctx, cudaEventRecord(s.decoded, s.stream));
-        CK(ctx, cudaMemcpyAsync(s.h_info, s.ws.d_info, sizeof(rtj_dev_info), cudaMemcpyDeviceToHost, s.stream));
+        CKB(cudaEventRecord(s.decoded, s.stream));
+        CKB(cudaMemcpyAsync(s.h_info, s.ws.d_info, sizeof(rtj_dev_info), cudaMemcpyDeviceToHost, s.stream));
+        CKB(cudaMemcpyAsync(ctx->h_host_skips + c0, s.ws.d_frame_skips, sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToHost, s.stream));
         prev_decoded = s.decoded;
         d_prev = s.d_out + fsz * (size_t)(n - 1);
 
         uint8_t *dst = h_out + fsz * (size_t)c0;
         if (flags & RTJGPU_HOST_OUT_PINNED) {
-            CK(ctx, cudaMemcpyAsync(dst, s.d_out, fsz * (size_t)n, cudaMemcpyDeviceToHost, s.stream));
+            CKB(cudaMemcpyAsync(dst, s.d_out, fsz * (size_t)n, cudaMemcpyDeviceToHost, s.stream));
             s.pending_dst = nullptr;
         } else {
             if ((rc = grow_pinned(ctx, &s.h_out, &s.h_out_cap, fsz * (size_t)n))) { result = rc; break; }
-            CK(ctx, cudaMemcpyAsync(s.h_out, s.d_out, fsz * (size_t)n, cudaMemcpyDeviceToHost, s.stream));
+            CKB(cudaMemcpyAsync(s.h_out, s.d_out, fsz * (size_t)n, cudaMemcpyDeviceToHost, s.stream));
             s.pending_dst = dst;
             s.pending_bytes = fsz * (size_t)n;
         }
         s.busy = true;
     }
+#undef CKB
     /* drain in issue order so that later chunks' carries are complete */
     for (int i = 0; i < HOST_SLOTS; i++) {
         int rc2 = slot_drain(ctx, ctx->slot[i]);
@@ -1051,8 +1091,16 @@ int rtjgpu_decode_host(rtjgpu_ctx *ctx, const uint8_t *h_stream, const uint64_t 
     if (result == RTJGPU_OK || result == RTJGPU_E_OVERRUN) {
         if (have_carry) memcpy(h_carry_inout, h_out + fsz * (size_t)(F - 1), fsz);
         *state = st;
+        ctx->host_F = F;
     }
     return result;
+}
+
+int rtjgpu_get_host_skip_counts(rtjgpu_ctx *ctx, uint32_t *counts, int F)
+{
+    if (!ctx || !counts || F < 0 || F > ctx->host_F) return RTJGPU_E_ARG;
+    if (F) memcpy(counts, ctx->h_host_skips, sizeof(uint32_t) * (size_t)F);
+    return RTJGPU_OK;
 }
 
 } // extern "C"

@@ -545,7 +545,7 @@ rtj_idct_kernel(const K2Params P)
     PicPos pp_next = pos_of(tid);
     uint32_t e_first = tid < nb ? my_ent[pp_next.i] : 0u;
     const rtjgpu_frame_desc fd = P.desc[f];
-    const unsigned mytable = fd.table;
+    const unsigned mytable = min((unsigned)fd.table, (unsigned)RTJ_NUM_TABLES - 1u);     /* descriptors are the caller's memory */
     const rtj_dev_table *tb = &P.tables[mytable];
     const uint8_t *frame_pay = P.stream + fd.offset + RTJPEG_B200_HEADER_BYTES;
     const int bt8_l = tb->bt8[0], bt8_c = tb->bt8[1];
@@ -807,7 +807,7 @@ rtj_idct_hard_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc
             e = ent[(size_t)sf * nblk + i];
         }
         const int chroma = (i % unit) >= unit_luma;
-        const rtj_dev_table *t = &tables[desc[sf].table];
+        const rtj_dev_table *t = &tables[min((int)desc[sf].table, RTJ_NUM_TABLES - 1)];
         const uint8_t *src = stream + desc[sf].offset + RTJPEG_B200_HEADER_BYTES + (e & RTJ_ENT_OFF_MASK);
         uint32_t px[16];
         if (full) {

@@ -54,8 +54,9 @@ rtj_scan_warp_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc
     const rtjgpu_frame_desc d = desc[f];
     const uint8_t *pay = stream + d.offset + RTJPEG_B200_HEADER_BYTES;
     const int len = d.length > RTJPEG_B200_HEADER_BYTES ? (int)d.length - RTJPEG_B200_HEADER_BYTES : 0;
-    const int lb8 = tables[d.table].bt8[0];
-    const int cb8 = tables[d.table].bt8[1];
+    const rtj_dev_table &tab = tables[min((int)d.table, RTJ_NUM_TABLES - 1)];     /* descriptors are the caller's memory */
+    const int lb8 = tab.bt8[0];
+    const int cb8 = tab.bt8[1];
     if (raw_only && (lb8 | cb8) == 0) return;        /* rtj_scan_chunk_kernel has done this frame */
     uint32_t *out = ent + (size_t)f * nblk;
 
@@ -213,7 +214,7 @@ __device__ __forceinline__ LaneResult lane_scan_frame(const uint8_t *__restrict_
         if (RAW) k6 = k6 == unit - 1 ? 0 : k6 + 1;
         sink ^= touch3;
         touch3 = touch2; touch2 = touch1; touch1 = touch0;
-        touch0 = __ldg(base4 + ((o + 160) >> 2));
+        touch0 = __ldg(base4 + (min(o + 160, len + (int)RTJGPU_STREAM_SLACK_BYTES - 4) >> 2));   /* never behind the slack */
 
         /* the block's first byte and its first eight tokens */
         uint32_t first, t0, t1;
@@ -288,8 +289,9 @@ rtj_scan_lane_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc
     const rtjgpu_frame_desc d = desc[f];
     const uint8_t *pay = stream + d.offset + RTJPEG_B200_HEADER_BYTES;
     const int len = d.length > RTJPEG_B200_HEADER_BYTES ? (int)d.length - RTJPEG_B200_HEADER_BYTES : 0;
-    const int lb8 = tables[d.table].bt8[0];
-    const int cb8 = tables[d.table].bt8[1];
+    const rtj_dev_table &tab = tables[min((int)d.table, RTJ_NUM_TABLES - 1)];     /* descriptors are the caller's memory */
+    const int lb8 = tab.bt8[0];
+    const int cb8 = tab.bt8[1];
     if (raw_only && (lb8 | cb8) == 0) return;        /* rtj_scan_chunk_kernel has done this frame */
     uint32_t *out = ent + (size_t)f * nblk;
 
@@ -412,7 +414,8 @@ rtj_scan_plan_kernel(const rtjgpu_frame_desc *__restrict__ desc, const rtj_dev_t
     const rtjgpu_frame_desc d = desc[f];
     const int len = d.length > RTJPEG_B200_HEADER_BYTES ? (int)d.length - RTJPEG_B200_HEADER_BYTES : 0;
     /* with a raw prefix the summaries count macroblocks (rtj_scan_mb.cu), without it blocks */
-    const bool raw = (tables[d.table].bt8[0] | tables[d.table].bt8[1]) != 0;
+    const rtj_dev_table &tab = tables[min((int)d.table, RTJ_NUM_TABLES - 1)];
+    const bool raw = (tab.bt8[0] | tab.bt8[1]) != 0;
     const int unit = raw ? unit_blocks : 1;
     const int segbytes = raw ? RTJ_SEG_BYTES_MB : RTJ_SEG_BYTES;
     int e = 0, nb = 0, seg = 0;

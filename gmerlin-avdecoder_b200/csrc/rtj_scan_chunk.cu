@@ -106,7 +106,10 @@ rtj_scan_chunk_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_des
     const int f = (PHASE == 0 ? blockIdx.x : blockIdx.y) + f0;        /* F: one behind the last frame of this launch */
     if (f >= F) return;
     const rtjgpu_frame_desc d = desc[f];
-    if (tables[d.table].bt8[0] | tables[d.table].bt8[1]) return;     /* raw prefix: the serial kernels' frame */
+    {
+        const rtj_dev_table &tab = tables[min((int)d.table, RTJ_NUM_TABLES - 1)];      /* descriptors are the caller's memory */
+        if (tab.bt8[0] | tab.bt8[1]) return;                           /* raw prefix: rtj_scan_mb_kernel's frame */
+    }
 
     const uint8_t *pay = stream + d.offset + RTJPEG_B200_HEADER_BYTES;
     const int len = d.length > RTJPEG_B200_HEADER_BYTES ? (int)d.length - RTJPEG_B200_HEADER_BYTES : 0;

@@ -116,7 +116,8 @@ rtj_scan_mb_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc *
     const int f = (PHASE == 0 ? blockIdx.x : blockIdx.y) + f0;        /* F: one behind the last frame of this launch */
     if (f >= F) return;
     const rtjgpu_frame_desc d = desc[f];
-    const int lb8 = tables[d.table].bt8[0], cb8 = tables[d.table].bt8[1];
+    const rtj_dev_table &tab = tables[min((int)d.table, RTJ_NUM_TABLES - 1)];          /* descriptors are the caller's memory */
+    const int lb8 = tab.bt8[0], cb8 = tab.bt8[1];
     if ((lb8 | cb8) == 0) return;                       /* no raw prefix: rtj_scan_chunk_kernel's frame */
 
     const uint8_t *pay = stream + d.offset + RTJPEG_B200_HEADER_BYTES;

@@ -18,10 +18,12 @@
 #include <new>
 #include <vector>
 
+#include <algorithm>
+
 #include "rtj_common.h"
 
-extern "C" const rtj_host_table *rtjgpu_host_table(const rtjgpu_ctx *ctx, int table);
-extern "C" int rtjgpu_get_entries(rtjgpu_ctx *ctx, uint32_t *entries, size_t n);
+extern "C" const rtj_host_table *rtj_ctx_host_table(const rtjgpu_ctx *ctx, int table);
+extern "C" int rtj_ctx_get_entries(rtjgpu_ctx *ctx, uint32_t *entries, size_t n);
 
 namespace {
 
@@ -148,7 +150,7 @@ int RTjpeg_set_intra(RTjpeg_t *rtj, int *key, int *lm, int *cm)
 void RTjpeg_get_tables(RTjpeg_t *rtj, uint32_t *tables)
 {
     Instance *in = static_cast<Instance *>(rtj);
-    const rtj_host_table *t = rtjgpu_host_table(in->ctx, in->st.table);
+    const rtj_host_table *t = rtj_ctx_host_table(in->ctx, in->st.table);
     for (int i = 0; i < 64; i++) {
         tables[i] = (uint32_t)t->liqt[i];
         tables[64 + i] = (uint32_t)t->ciqt[i];
@@ -277,12 +279,17 @@ int RTjpeg_b200_decompress_n(RTjpeg_t *rtj, const uint8_t *sp, size_t len, uint8
     rtjgpu_state st = in->st;
     const uint64_t offs[2] = {0, (uint64_t)len};
     rtjgpu_frame_desc desc;
-    int rc = rtjgpu_plan(sp, offs, 1, &st, &desc);     /* sp may be unaligned: offset 0 is what is planned */
+    if (len > (size_t)RTJGPU_MAX_PAYLOAD_BYTES + RTJPEG_B200_HEADER_BYTES) return fail(in, RTJGPU_E_TOOBIG);
+    const uint32_t len32 = (uint32_t)len;
+    int rc = rtjgpu_plan_n(sp, offs, &len32, 1, &st, &desc);     /* sp may be unaligned: offset 0 is what is planned */
     if (rc) return fail(in, rc);
     const int w = st.width, h = st.height;
     const size_t fsz = RTJ_FMT_FRAME_BYTES(fmt, w, h);
     const int nblk = RTJ_FMT_NBLK(fmt, w, h);
-    const size_t plen = desc.length;
+    /* never more than the grammar can consume (64 bytes a block): a header whose framesize is far too large must not
+     * make the host read far past the caller's packet before any block is looked at */
+    const size_t plen = std::min<size_t>(desc.length, RTJPEG_B200_HEADER_BYTES + (size_t)nblk * 64);
+    desc.length = (uint32_t)plen;
 
     if ((rc = ensure(in, plen + RTJGPU_STREAM_SLACK_BYTES, fsz))) return fail(in, rc);
     memcpy(in->h_pkt, sp, plen);
@@ -315,7 +322,7 @@ int RTjpeg_b200_decompress_n(RTjpeg_t *rtj, const uint8_t *sp, size_t len, uint8
     } else {
         /* copy back only what this frame coded; skipped blocks keep the caller's pixels */
         in->entries.resize((size_t)nblk);
-        if ((rc = rtjgpu_get_entries(in->ctx, in->entries.data(), (size_t)nblk))) return fail(in, rc);
+        if ((rc = rtj_ctx_get_entries(in->ctx, in->entries.data(), (size_t)nblk))) return fail(in, rc);
         const int cw = w >> 1;
         const int unit = RTJ_FMT_UNIT_BLOCKS(fmt), unit_luma = RTJ_FMT_UNIT_LUMA(fmt), ux = RTJ_FMT_UNITS_X(fmt, w);
         for (int b = 0; b < nblk; b++) {

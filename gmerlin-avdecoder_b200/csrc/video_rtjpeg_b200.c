@@ -41,8 +41,16 @@
  *     skipped block of later inter-coded frames, stays as it was; frames decoded ahead across a dropped
  *     packet are therefore decoded again, from the picture last delivered, before they are served;
  *   - a packet that is truncated, malformed or of the wrong size ends the stream when ITS turn comes,
- *     after every frame before it was served.
- * RTJPEG_B200_LOOKAHEAD sets K (1 = the reference's one-packet behaviour).
+ *     after every frame before it was served;
+ *   - a seek (bgav_video_resync, lib/video.c:525-562, calls .resync after the stream's packet queue was flushed)
+ *     drops every packet and frame held: what comes next is what the stream hands out next.  The picture and the
+ *     decoder state stay, as they do in the reference's RTjpeg_t and priv->frame;
+ *   - bgav_video_skipto's shortcut for intra-only streams (lib/video.c:613-630) consumes packets from the stream
+ *     behind the decoder's back and leaves s->out_time at the first packet it kept.  Held packets that end at or
+ *     before s->out_time are therefore dropped undecoded before the next frame is served -- the packets the
+ *     shortcut would have consumed had they still been in the stream's queue.  (It cannot know the time asked
+ *     for: a target INSIDE the held packets lands on the first packet behind them, up to K - 1 frames late.)
+ * RTJPEG_B200_LOOKAHEAD sets K (1 = the reference's one-packet behaviour, exact in every respect).
  */
 typedef struct {
     rtjgpu_ctx    *ctx;
@@ -55,9 +63,14 @@ typedef struct {
     int            n, head;              /* packets held / next one to serve */
     int            bad;                  /* the packet after the held ones was unusable: the stream ends there */
     gavl_source_status_t tail;           /* why the last fill stopped early (EOF / AGAIN), else OK */
-    /* frames decoded ahead: [dec_lo, dec_hi) of the held packets */
+    /* frames decoded ahead */
     uint8_t       *frames;               /* pinned, K * fsz */
-    int            dec_lo, dec_hi, slow; /* slow: a batch failed, the rest of the held packets decode one by one */
+    uint8_t       *ok;                   /* K: frames[i] is the picture after held packet i */
+    uint8_t       *clean;                /* K: held packet i carries no skip marker (known once it was decoded) */
+    uint32_t      *skips;                /* K: scratch for the per-frame skip counts of a batch */
+    uint64_t      *rel;                  /* K + 1: scratch for packet offsets relative to a batch */
+    uint32_t      *lens;                 /* K: scratch for the packets' true lengths */
+    int            slow;                 /* a batch failed: the rest of the held packets decode one by one */
     uint8_t       *picture;              /* pinned, fsz: the picture last delivered ... */
     const uint8_t *last;                 /* ... or where it still sits among the decoded frames */
     uint8_t       *carry;                /* pinned, fsz: scratch for rtjgpu_decode_host's in/out picture */
@@ -73,6 +86,11 @@ static void free_priv(rtjpeg_b200_priv_t *priv)
     rtjgpu_host_free(priv->carry);
     free(priv->off);
     free(priv->meta);
+    free(priv->ok);
+    free(priv->clean);
+    free(priv->skips);
+    free(priv->rel);
+    free(priv->lens);
     if (priv->ctx) rtjgpu_destroy(priv->ctx);
     free(priv);
 }
@@ -105,7 +123,13 @@ static int init_rtjpeg_b200(bgav_stream_t *s)
     priv->carry = rtjgpu_host_alloc(fsz);
     priv->off = calloc((size_t)priv->K + 1, sizeof(*priv->off));
     priv->meta = calloc((size_t)priv->K, sizeof(*priv->meta));
-    if (!priv->frames || !priv->picture || !priv->carry || !priv->off || !priv->meta) { free_priv(priv); return 0; }
+    priv->ok = calloc((size_t)priv->K, 1);
+    priv->clean = calloc((size_t)priv->K, 1);
+    priv->skips = calloc((size_t)priv->K, sizeof(*priv->skips));
+    priv->rel = calloc((size_t)priv->K + 1, sizeof(*priv->rel));
+    priv->lens = calloc((size_t)priv->K, sizeof(*priv->lens));
+    if (!priv->frames || !priv->picture || !priv->carry || !priv->off || !priv->meta || !priv->ok || !priv->clean
+        || !priv->skips || !priv->rel || !priv->lens) { free_priv(priv); return 0; }
     memset(priv->picture, 0, fsz);               /* gavl_video_frame_create hands out a cleared frame */
     priv->last = priv->picture;
     priv->st.width = priv->st.height = 0;
@@ -131,7 +155,8 @@ static void fill_ring(bgav_stream_t *s, rtjpeg_b200_priv_t *priv)
         priv->last = priv->picture;
     }
     priv->n = priv->head = 0;
-    priv->dec_lo = priv->dec_hi = 0;
+    memset(priv->ok, 0, (size_t)priv->K);
+    memset(priv->clean, 0, (size_t)priv->K);
     priv->slow = 0;
     priv->off[0] = 0;
     priv->tail = GAVL_SOURCE_OK;
@@ -173,15 +198,38 @@ static void fill_ring(bgav_stream_t *s, rtjpeg_b200_priv_t *priv)
 /* Decode held packets [from, to) from the picture last delivered.  0 on success. */
 static int decode_range(rtjpeg_b200_priv_t *priv, int from, int to)
 {
-    uint64_t rel[LOOKAHEAD_MAX + 1];
+    uint64_t *rel = priv->rel;
     for (int i = from; i <= to; i++) rel[i - from] = priv->off[i] - priv->off[from];
-    /* the end of the last packet is its true length, not the aligned slot */
-    rel[to - from] = priv->off[to - 1] - priv->off[from] + (uint64_t)priv->meta[to - 1].buf.len;
+    /* the packets' true lengths (gavl_packet_t.buf.len), not their aligned slots and not the header's framesize,
+     * which the reference never reads (lib/RTjpeg.c:3565-3586) */
+    for (int i = from; i < to; i++) priv->lens[i - from] = (uint32_t)priv->meta[i].buf.len;
     rtjgpu_state st = priv->st;
     memcpy(priv->carry, priv->last, priv->fsz);
-    return rtjgpu_decode_host(priv->ctx, priv->pk + priv->off[from], rel, to - from, &st,
-                              priv->frames + (size_t)from * priv->fsz, priv->carry,
-                              RTJGPU_HOST_IN_PINNED | RTJGPU_HOST_OUT_PINNED);
+    const int rc = rtjgpu_decode_host_n(priv->ctx, priv->pk + priv->off[from], rel, priv->lens, to - from, &st,
+                                        priv->frames + (size_t)from * priv->fsz, priv->carry,
+                                        RTJGPU_HOST_IN_PINNED | RTJGPU_HOST_OUT_PINNED);
+    if (rc != RTJGPU_OK) return rc;
+    /* a frame without skip markers rewrites the whole picture: what follows it does not depend on what precedes it */
+    if (rtjgpu_get_host_skip_counts(priv->ctx, priv->skips, to - from) == RTJGPU_OK)
+        for (int i = from; i < to; i++) priv->clean[i] = priv->skips[i - from] == 0;
+    memset(priv->ok + from, 1, (size_t)(to - from));
+    return RTJGPU_OK;
+}
+
+/* Held packets the host has moved past behind the decoder's back (bgav_video_skipto's intra-only shortcut,
+ * lib/video.c:613-630, leaves s->out_time at the first packet it kept): dropped undecoded, like its own. */
+static void drop_passed_packets(bgav_stream_t *s, rtjpeg_b200_priv_t *priv)
+{
+    if (s->out_time == GAVL_TIME_UNDEFINED) return;
+    int dropped = 0;
+    while (priv->head < priv->n) {
+        const bgav_packet_t *m = &priv->meta[priv->head];
+        if (!(m->pts < s->out_time && m->pts + m->duration <= s->out_time)) break;
+        priv->head++;
+        dropped = 1;
+    }
+    if (dropped)                               /* what was decoded ahead assumed these packets had been decoded */
+        for (int i = priv->head; i < priv->n && !priv->clean[i]; i++) priv->ok[i] = 0;
 }
 
 /* lib/video_rtjpeg.c:62-90 */
@@ -189,6 +237,7 @@ static gavl_source_status_t decode_rtjpeg_b200(bgav_stream_t *s, gavl_video_fram
 {
     rtjpeg_b200_priv_t *priv = s->decoder_priv;
 
+    drop_passed_packets(s, priv);
     if (priv->head == priv->n) {
         if (priv->bad) return GAVL_SOURCE_EOF;   /* the unusable packet's turn */
         fill_ring(s, priv);
@@ -197,16 +246,18 @@ static gavl_source_status_t decode_rtjpeg_b200(bgav_stream_t *s, gavl_video_fram
 
     if (!f) {                                   /* skip this frame: its packet is dropped undecoded */
         priv->head++;
-        priv->dec_lo = priv->dec_hi = 0;        /* what was decoded ahead assumed this packet had been decoded */
+        /* what was decoded ahead assumed this packet had been decoded: the frames up to the next clean one are void */
+        for (int i = priv->head; i < priv->n && !priv->clean[i]; i++) priv->ok[i] = 0;
         return GAVL_SOURCE_OK;
     }
 
-    if (priv->head < priv->dec_lo || priv->head >= priv->dec_hi) {
+    if (!priv->ok[priv->head]) {
         int rc = RTJGPU_E_ARG;
         if (!priv->slow) {
-            rc = decode_range(priv, priv->head, priv->n);
-            if (rc == RTJGPU_OK) { priv->dec_lo = priv->head; priv->dec_hi = priv->n; }
-            else priv->slow = 1;                /* some packet ahead is damaged: find it one by one */
+            int to = priv->head + 1;            /* up to the next frame that is still good (a clean frame or the end) */
+            while (to < priv->n && !priv->ok[to]) to++;
+            rc = decode_range(priv, priv->head, to);
+            if (rc != RTJGPU_OK) priv->slow = 1;  /* some packet ahead is damaged: find it one by one */
         }
         if (rc != RTJGPU_OK) {
             rc = decode_range(priv, priv->head, priv->head + 1);
@@ -215,8 +266,6 @@ static gavl_source_status_t decode_rtjpeg_b200(bgav_stream_t *s, gavl_video_fram
                 priv->bad = 1;
                 return GAVL_SOURCE_EOF;
             }
-            priv->dec_lo = priv->head;
-            priv->dec_hi = priv->head + 1;
         }
     }
 
@@ -232,12 +281,33 @@ static gavl_source_status_t decode_rtjpeg_b200(bgav_stream_t *s, gavl_video_fram
     /* the decoder state moves past this packet (lib/RTjpeg.c:3568-3579); a dropped packet never touches it */
     {
         const uint64_t one[2] = {0, (uint64_t)priv->meta[priv->head].buf.len};
+        const uint32_t len = (uint32_t)priv->meta[priv->head].buf.len;
         rtjgpu_frame_desc d;
-        rtjgpu_plan(priv->pk + priv->off[priv->head], one, 1, &priv->st, &d);
+        rtjgpu_plan_n(priv->pk + priv->off[priv->head], one, &len, 1, &priv->st, &d);
     }
     priv->last = pic;
     priv->head++;
     return GAVL_SOURCE_OK;
+}
+
+/* include/avdec_private.h:90-118 (.resync), called by bgav_video_resync (lib/video.c:561-562) after a seek: the
+ * stream's packet queue was flushed, so every packet held here -- and every frame decoded from them -- is stale.
+ * The reference registers no resync because it holds nothing between calls; its RTjpeg_t (size, quality, tables)
+ * and its picture survive a seek, and so do they here. */
+static void resync_rtjpeg_b200(bgav_stream_t *s)
+{
+    rtjpeg_b200_priv_t *priv = s->decoder_priv;
+    if (!priv) return;
+    if (priv->last != priv->picture) {
+        memcpy(priv->picture, priv->last, priv->fsz);
+        priv->last = priv->picture;
+    }
+    priv->n = priv->head = 0;
+    memset(priv->ok, 0, (size_t)priv->K);
+    memset(priv->clean, 0, (size_t)priv->K);
+    priv->slow = 0;
+    priv->bad = 0;
+    priv->tail = GAVL_SOURCE_OK;
 }
 
 /* lib/video_rtjpeg.c:93-101 */
@@ -256,6 +326,7 @@ static bgav_video_decoder_t rtjpeg_b200_decoder = {
     .init    = init_rtjpeg_b200,
     .decode  = decode_rtjpeg_b200,
     .close   = close_rtjpeg_b200,
+    .resync  = resync_rtjpeg_b200,
 };
 
 /* include/codecs.h:97, lib/video_rtjpeg.c:112 */

@@ -58,6 +58,8 @@ typedef struct {
     int pixelformat;
 } gavl_video_format_t;
 
+#define GAVL_TIME_UNDEFINED ((int64_t)0x8000000000000000LL)     /* gavl/gavltime.h */
+
 typedef struct {
     uint8_t *planes[GAVL_MAX_PLANES];
     int      strides[GAVL_MAX_PLANES];
@@ -108,6 +110,7 @@ struct bgav_stream_s {
             gavl_video_format_t *format;
         } video;
     } data;
+    int64_t            out_time;                  /* include/avdec_private.h:300: end of the last frame delivered, or where a skip landed */
     void              *host_priv;                 /* stub only: the test host's packet queue */
 };
 

@@ -93,6 +93,27 @@ void RTjpeg_set_tables(RTjpeg_t *rtj, uint32_t *tables);
  * RTjpeg_b200_last_error(). */
 void RTjpeg_decompress(RTjpeg_t *rtj, uint8_t *sp, uint8_t **planes);
 
+/* include/RTjpeg.h:123, lib/RTjpeg.c:3488.  One picture (planes[0..2] = Y, U, V, tight pitch, in the instance's
+ * format: YUV420 or YUV422) into one packet at sp -- 12-byte header + block stream, byte for byte the reference's,
+ * inter-frame block skipping (RTjpeg_set_intra) included.  Returns the packet's size in bytes; the caller sizes sp
+ * (worst case 12 + 64 bytes per block), as with the reference.  The reference's 8-bit format is not offered: its
+ * encoder reads outside the plane (lib/RTjpeg.c:2627); 0 is returned and RTJGPU_E_FORMAT left for
+ * RTjpeg_b200_last_error. */
+int RTjpeg_compress(RTjpeg_t *rtj, uint8_t *sp, uint8_t **planes);
+
+/* include/RTjpeg.h:128-136, lib/RTjpeg.c:3077-3486.  Colour conversion of one decoded picture: planes[0..2] = Y, Cb, Cr
+ * (tight pitch, the instance's width and height), rows[r] = start of output row r.  Bit-exact integer arithmetic of
+ * the reference (16 fractional bits).  The 32-bit converters step over the fourth byte of a pixel like the reference
+ * does (:3147). */
+void RTjpeg_yuv420rgb32(RTjpeg_t *rtj, uint8_t **planes, uint8_t **rows);   /* include/RTjpeg.h:128, lib/RTjpeg.c:3123 */
+void RTjpeg_yuv420bgr32(RTjpeg_t *rtj, uint8_t **planes, uint8_t **rows);   /* :129, lib/RTjpeg.c:3192 */
+void RTjpeg_yuv420rgb24(RTjpeg_t *rtj, uint8_t **planes, uint8_t **rows);   /* :130, lib/RTjpeg.c:3261 */
+void RTjpeg_yuv420bgr24(RTjpeg_t *rtj, uint8_t **planes, uint8_t **rows);   /* :131, lib/RTjpeg.c:3326 */
+void RTjpeg_yuv420rgb16(RTjpeg_t *rtj, uint8_t **planes, uint8_t **rows);   /* :132, lib/RTjpeg.c:3391 */
+void RTjpeg_yuv420rgb8(RTjpeg_t *rtj, uint8_t **planes, uint8_t **rows);    /* :133, lib/RTjpeg.c:3477 */
+void RTjpeg_yuv422rgb24(RTjpeg_t *rtj, uint8_t **planes, uint8_t **rows);   /* :135, lib/RTjpeg.c:3077 */
+#define RTjpeg_yuv422rgb8(x, y, z) RTjpeg_yuv420rgb8(x, y, z)               /* :136 */
+
 /* Same as RTjpeg_decompress but with the packet length known to the caller
  * (gavl_packet_t.buf.len in lib/video_rtjpeg.c:81), so a truncated packet is
  * refused instead of read past.  Returns 0 or a negative RTJGPU_E_* code. */
@@ -242,6 +263,12 @@ int  rtjgpu_set_custom_tables(rtjgpu_ctx *ctx, const uint32_t raw[128]);
  * is advanced past the batch on success. */
 int  rtjgpu_plan(const uint8_t *stream, const uint64_t *offsets, int F,
                  rtjgpu_state *state, rtjgpu_frame_desc *desc);
+/* The same with the packets' TRUE lengths (lengths[f] bytes from offsets[f], at most the slot): what a caller that
+ * knows them -- gavl_packet_t.buf.len in lib/video_rtjpeg.c:81 -- should use.  The header's framesize field is then
+ * ignored altogether, as the reference ignores it (lib/RTjpeg.c:3565-3586).  rtjgpu_plan, which only sees slots that
+ * may end in alignment padding, lets a framesize smaller than the slot bound the packet. */
+int  rtjgpu_plan_n(const uint8_t *stream, const uint64_t *offsets, const uint32_t *lengths, int F,
+                   rtjgpu_state *state, rtjgpu_frame_desc *desc);
 
 /* Device-resident decode: stream, descriptors, output and carry all live in
  * device memory.  d_out receives F tight YUV420 frames (w*h*3/2 bytes each,
@@ -249,7 +276,9 @@ int  rtjgpu_plan(const uint8_t *stream, const uint64_t *offsets, int F,
  * is the picture before the first frame: skipped blocks that no frame of the
  * batch has written yet are taken from it (lib/video_rtjpeg.c:81 decodes into
  * one persistent frame).  cuda_stream is a cudaStream_t passed as void*
- * (NULL = the legacy default stream).  Asynchronous: returns after the launches. */
+ * (NULL = the legacy default stream).  Asynchronous: returns after the launches.
+ * Alignment (RTJGPU_E_ARG otherwise): d_stream 4 bytes -- and every packet offset a multiple of 4, which rtjgpu_plan
+ * checks --, d_desc 8, d_out 16 (frames are w*h*3/2 bytes, a multiple of 16, apart), d_carry 8. */
 int  rtjgpu_decode_device(rtjgpu_ctx *ctx, const uint8_t *d_stream,
                           const rtjgpu_frame_desc *d_desc, int F, int w, int h,
                           uint8_t *d_out, const uint8_t *d_carry, void *cuda_stream);
@@ -263,6 +292,12 @@ int  rtjgpu_decode_device(rtjgpu_ctx *ctx, const uint8_t *d_stream,
 #define RTJGPU_HOST_OUT_PINNED  2   /* h_out is page-locked: DMA straight into it */
 int  rtjgpu_decode_host(rtjgpu_ctx *ctx, const uint8_t *h_stream, const uint64_t *offsets, int F,
                         rtjgpu_state *state, uint8_t *h_out, uint8_t *h_carry_inout, int flags);
+/* ... with the packets' true lengths (see rtjgpu_plan_n); lengths == NULL is rtjgpu_decode_host. */
+int  rtjgpu_decode_host_n(rtjgpu_ctx *ctx, const uint8_t *h_stream, const uint64_t *offsets, const uint32_t *lengths, int F,
+                          rtjgpu_state *state, uint8_t *h_out, uint8_t *h_carry_inout, int flags);
+
+/* Per-frame skipped-block counts of the last successful rtjgpu_decode_host call (F entries, F at most that call's). */
+int  rtjgpu_get_host_skip_counts(rtjgpu_ctx *ctx, uint32_t *counts, int F);
 
 /* Wait for everything this context has launched. */
 int  rtjgpu_sync(rtjgpu_ctx *ctx);

@@ -85,6 +85,7 @@ bgav_stream_t *stub_stream_create(int image_w, int image_h)
     s->m = (gavl_dictionary_t *)h;
     s->data.video.format = &h->fmt;
     s->fourcc = BGAV_MK_FOURCC('R', 'T', 'J', '0');
+    s->out_time = GAVL_TIME_UNDEFINED;
     return s;
 }
 
@@ -117,7 +118,37 @@ int stub_decode(bgav_video_decoder_t *d, bgav_stream_t *s, uint8_t *y, uint8_t *
     f.strides[0] = sy; f.strides[1] = sc; f.strides[2] = sc;
     int st = (int)d->decode(s, y ? &f : NULL);
     if (pts_out) *pts_out = f.timestamp;
+    /* lib/video.c:274,295: the stream's clock follows the frames handed out */
+    if (y && st == (int)GAVL_SOURCE_OK) s->out_time = f.timestamp + f.duration;
     return st;
+}
+
+/* a seek as the decoder sees it (bgav_video_resync, lib/video.c:525-562): the stream's queue now starts at packet
+ * `next`, then the decoder's resync -- when it registered one -- is called */
+void stub_seek(bgav_video_decoder_t *d, bgav_stream_t *s, int next)
+{
+    host_t *h = s->host_priv;
+    h->rd = next;
+    s->out_time = h->pk[next < h->n ? next : h->n - 1].pts;
+    if (d->resync) d->resync(s);
+}
+
+int stub_has_resync(bgav_video_decoder_t *d) { return d->resync != NULL; }
+
+/* bgav_video_skipto for a stream without P frames (lib/video.c:613-630): packets are taken from the stream, not
+ * through the decoder, until the next one ends behind `time`; returns how many it consumed, -1 at the end */
+int stub_skipto_intra(bgav_stream_t *s, int64_t time)
+{
+    host_t *h = s->host_priv;
+    int consumed = 0;
+    for (;;) {
+        if (h->rd >= h->n) return -1;
+        bgav_packet_t *p = &h->pk[h->rd];
+        if (p->pts + p->duration > time) { s->out_time = p->pts; return consumed; }
+        h->rd++;
+        h->done_calls++;
+        consumed++;
+    }
 }
 
 void stub_stream_info(bgav_stream_t *s, int *fw, int *fh, int *pixfmt, int *done_calls, char *key, char *val)

@@ -120,6 +120,10 @@ def host():
     H.stub_stream_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
                                    C.POINTER(C.c_int), C.c_char_p, C.c_char_p]
     H.stub_stream_destroy.argtypes = [vp]
+    H.stub_seek.argtypes = [vp, vp, C.c_int]
+    H.stub_seek.restype = None
+    H.stub_has_resync.argtypes = [vp]
+    H.stub_skipto_intra.argtypes = [vp, C.c_int64]
     P.bgav_init_video_decoders_rtjpeg.restype = None
     P.bgav_init_video_decoders_rtjpeg()                      # what bgav_codecs_init does, lib/codecs.c:176
     return H
@@ -263,3 +267,104 @@ def test_plugin_serves_frames_before_a_damaged_packet(host, monkeypatch):
     host.stub_close(dec, st)
     host.stub_stream_destroy(st)
 
+
+
+def _open(host, s, o, w, h):
+    sizes = O.packet_sizes(s, o).astype(np.uint32)
+    dec = host.stub_find_decoder(FOURCC_RTJ0)
+    st = host.stub_stream_create(w, h)
+    offs = np.ascontiguousarray(o[:-1], dtype=np.uint64)
+    host.stub_stream_set_packets(st, s.ctypes.data, offs.ctypes.data, sizes.ctypes.data, len(o) - 1)
+    assert host.stub_init(dec, st) == 1
+    return dec, st, sizes, offs
+
+
+@pytest.mark.parametrize("lookahead", [1, 7, 32])
+def test_plugin_resync_drops_what_it_read_ahead(host, lookahead, monkeypatch):
+    """A seek (bgav_video_resync, lib/video.c:525-562): the stream's queue is flushed and repositioned, then .resync
+    is called.  The reference holds no packet between calls, so after a seek it decodes whatever comes next into
+    the picture it has (lib/video_rtjpeg.c:81).  The plugin, which reads ahead, must do the same: drop the packets
+    and frames it holds, keep picture and decoder state."""
+    monkeypatch.setenv("RTJPEG_B200_LOOKAHEAD", str(lookahead))
+    w, h, F = 96, 64, 60
+    s, o = clip(w, h, 128, F, key_rate=9, lm=2, cm=2, noise_y=4)
+    s = np.ascontiguousarray(s)
+    dec, st, sizes, offs = _open(host, s, o, w, h)
+    assert host.stub_has_resync(dec) == 1
+    Y = np.zeros((h, w), dtype=np.uint8); U = np.zeros((h // 2, w // 2), dtype=np.uint8); V = np.zeros_like(U)
+    od = O.OracleDecoder()
+    ref = np.zeros(w * h * 3 // 2, dtype=np.uint8)
+    pts = C.c_int64()
+
+    def play(frames):
+        for f in frames:
+            assert host.stub_decode(dec, st, Y.ctypes.data, U.ctypes.data, V.ctypes.data, w, w // 2, C.byref(pts)) == 1
+            od.decode(s[int(o[f]):int(o[f]) + int(sizes[f])], ref)
+            assert pts.value == 1000 + 40 * f, (f, pts.value)
+            assert np.array_equal(np.concatenate([Y.ravel(), U.ravel(), V.ravel()]), ref), f
+
+    play(range(0, 10))                       # the ring now holds packets far beyond 10
+    host.stub_seek(dec, st, 43)              # forward, into the middle of a GOP: inter frames land on the old picture
+    play(range(43, 50))
+    host.stub_seek(dec, st, 20)              # backward, onto a key frame
+    play(range(20, 33))
+    host.stub_seek(dec, st, 58)              # near the end
+    play(range(58, 60))
+    assert host.stub_decode(dec, st, Y.ctypes.data, U.ctypes.data, V.ctypes.data, w, w // 2, None) == 0
+    host.stub_seek(dec, st, 5)               # and a seek after the end of the stream was reported
+    play(range(5, 8))
+    host.stub_close(dec, st)
+    host.stub_stream_destroy(st)
+
+
+def test_plugin_follows_the_hosts_intra_skip(host, monkeypatch):
+    """bgav_video_skipto's shortcut for streams without P frames (lib/video.c:613-630) takes packets from the
+    stream without asking the decoder and leaves s->out_time at the first packet it kept.  The packets the plugin
+    holds lie before that one: they are dropped undecoded, and the next frame is the one the host expects."""
+    monkeypatch.setenv("RTJPEG_B200_LOOKAHEAD", "8")
+    w, h, F = 96, 64, 40
+    s, o = clip(w, h, 128, F, noise_y=4)
+    s = np.ascontiguousarray(s)
+    want = reference_frames(s, o, w, h, np.zeros(w * h * 3 // 2, dtype=np.uint8))
+    dec, st, sizes, offs = _open(host, s, o, w, h)
+    Y = np.zeros((h, w), dtype=np.uint8); U = np.zeros((h // 2, w // 2), dtype=np.uint8); V = np.zeros_like(U)
+    pts = C.c_int64()
+
+    def next_frame():
+        assert host.stub_decode(dec, st, Y.ctypes.data, U.ctypes.data, V.ctypes.data, w, w // 2, C.byref(pts)) == 1
+        f = (pts.value - 1000) // 40
+        assert np.array_equal(np.concatenate([Y.ravel(), U.ravel(), V.ravel()]), want[f]), f
+        return f
+
+    assert [next_frame() for _ in range(3)] == [0, 1, 2]          # packets 3..7 are held
+    assert host.stub_skipto_intra(st, 1000 + 40 * 20 + 1) == 12    # the host eats packets 8..19 itself
+    assert next_frame() == 20
+    assert [next_frame() for _ in range(2)] == [21, 22]            # packets 23..27 are held
+    # a target inside the held packets: the host finds the stream's next packet already behind it and eats nothing;
+    # the plugin cannot know the time asked for and lands on that packet (documented: up to K - 1 frames late)
+    assert host.stub_skipto_intra(st, 1000 + 40 * 25 + 1) == 0
+    assert next_frame() == 28
+    host.stub_close(dec, st)
+    host.stub_stream_destroy(st)
+
+
+def test_plugin_redecodes_only_up_to_the_next_clean_frame(host, monkeypatch):
+    """A dropped packet voids the frames decoded ahead of it only up to the next frame without skip markers."""
+    monkeypatch.setenv("RTJPEG_B200_LOOKAHEAD", "32")
+    w, h, F = 96, 64, 32
+    s, o = clip(w, h, 128, F, key_rate=7, lm=2, cm=2, noise_y=4)
+    s = np.ascontiguousarray(s)
+    dec, st, sizes, offs = _open(host, s, o, w, h)
+    Y = np.zeros((h, w), dtype=np.uint8); U = np.zeros((h // 2, w // 2), dtype=np.uint8); V = np.zeros_like(U)
+    od = O.OracleDecoder()
+    ref = np.zeros(w * h * 3 // 2, dtype=np.uint8)
+    L = g.load_library()
+    for f in range(F):
+        if f in (2, 3, 12):
+            assert host.stub_decode(dec, st, None, None, None, 0, 0, None) == 1
+            continue
+        assert host.stub_decode(dec, st, Y.ctypes.data, U.ctypes.data, V.ctypes.data, w, w // 2, None) == 1
+        od.decode(s[int(o[f]):int(o[f]) + int(sizes[f])], ref)
+        assert np.array_equal(np.concatenate([Y.ravel(), U.ravel(), V.ravel()]), ref), f
+    host.stub_close(dec, st)
+    host.stub_stream_destroy(st)

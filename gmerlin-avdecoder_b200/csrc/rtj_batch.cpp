@@ -824,10 +824,11 @@ int rtjgpu_get_skip_counts(rtjgpu_ctx *ctx, uint32_t *counts, int F)
     return RTJGPU_OK;
 }
 
-/* internal, for the Level-1 shim: block entries of the last device batch */
-int rtj_ctx_get_entries(rtjgpu_ctx *ctx, uint32_t *entries, size_t n)
+int rtjgpu_get_entries(rtjgpu_ctx *ctx, uint32_t *entries, size_t n)
 {
-    if (!ctx || !entries) return RTJGPU_E_ARG;
+    if (!ctx || !entries || n > ctx->ws.cap_entries) return RTJGPU_E_ARG;
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaDeviceSynchronize());
     CK(ctx, cudaMemcpy(entries, ctx->ws.d_ent, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     return RTJGPU_OK;
 }

@@ -23,7 +23,6 @@
 #include "rtj_common.h"
 
 extern "C" const rtj_host_table *rtj_ctx_host_table(const rtjgpu_ctx *ctx, int table);
-extern "C" int rtj_ctx_get_entries(rtjgpu_ctx *ctx, uint32_t *entries, size_t n);
 
 namespace {
 
@@ -322,7 +321,7 @@ int RTjpeg_b200_decompress_n(RTjpeg_t *rtj, const uint8_t *sp, size_t len, uint8
     } else {
         /* copy back only what this frame coded; skipped blocks keep the caller's pixels */
         in->entries.resize((size_t)nblk);
-        if ((rc = rtj_ctx_get_entries(in->ctx, in->entries.data(), (size_t)nblk))) return fail(in, rc);
+        if ((rc = rtjgpu_get_entries(in->ctx, in->entries.data(), (size_t)nblk))) return fail(in, rc);
         const int cw = w >> 1;
         const int unit = RTJ_FMT_UNIT_BLOCKS(fmt), unit_luma = RTJ_FMT_UNIT_LUMA(fmt), ux = RTJ_FMT_UNITS_X(fmt, w);
         for (int b = 0; b < nblk; b++) {

@@ -315,6 +315,13 @@ int  rtjgpu_get_batch_info(rtjgpu_ctx *ctx, rtjgpu_batch_info *out); /* syncs */
  * an inter-coded stream into independent segments. */
 int  rtjgpu_get_skip_counts(rtjgpu_ctx *ctx, uint32_t *counts, int F);
 
+/* Diagnostic: the first n block entries K1 made for the last device batch (frame-major, nblk per frame), 32 bits each --
+ * 0xFFFFFFFF a skipped block; bit 31 set: a block of at most three coefficients carried in the entry itself (DC byte,
+ * then the coefficients at zig-zag 1 and 2); else byte offset in the frame's payload (25 bits) and end-of-block
+ * bound - 1 (6 bits above them).  What RTjpeg_decompress uses to copy back only the blocks a frame coded, and what
+ * the parity tests compare with the reference grammar's walk.  Synchronous. */
+int  rtjgpu_get_entries(rtjgpu_ctx *ctx, uint32_t *entries, size_t n);
+
 /* Number of kernels this library has launched on the context so far. */
 uint64_t rtjgpu_launch_count(const rtjgpu_ctx *ctx);
 

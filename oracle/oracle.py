@@ -211,6 +211,9 @@ def ref_lib():
         L.refdrv_decode_threaded.argtypes = [_u8p, _u64p, C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int,
                                              C.c_int, C.c_int, _u8p]
         L.refdrv_decode_threaded.restype = C.c_double
+        L.refdrv_decode_threaded_tables.argtypes = [_u8p, _u64p, C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int,
+                                                    C.c_int, C.c_int, _u8p, _u32p]
+        L.refdrv_decode_threaded_tables.restype = C.c_double
         L.refdrv_tables_for_quality.argtypes = [C.c_int, _u32p]
         L.refdrv_decode_with_tables.argtypes = [_u32p, _u8p, C.c_int, C.c_int, _u8p]
         _ref = L
@@ -274,18 +277,21 @@ def ref_decode_seq(stream, offsets, w, h, init=None, keep_all=True):
     return frames if keep_all else last
 
 
-def ref_decode_threaded(stream, offsets, segments, w, h, threads, zero_init=True, keep=False):
-    """Threaded reference decode; returns (seconds, frames or None)."""
+def ref_decode_threaded(stream, offsets, segments, w, h, threads, zero_init=True, keep=False, raw_tables=None):
+    """Threaded reference decode; returns (seconds, frames or None).  raw_tables: 128 raw entries every worker loads
+    with RTjpeg_set_tables first (the packets then carry quality 0)."""
     stream = _np_u8(stream)
     offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
     seg = np.ascontiguousarray(segments, dtype=np.int32)
     F = int(seg[-1])
     fsz = w * h * 3 // 2
     frames = np.empty((F, fsz), dtype=np.uint8) if keep else None
-    secs = ref_lib().refdrv_decode_threaded(_ptr(stream), _ptr(offsets, _u64p),
-                                            seg.ctypes.data_as(C.POINTER(C.c_int)), len(seg) - 1,
-                                            w, h, threads, 1 if zero_init else 0,
-                                            None if frames is None else _ptr(frames))
+    raw = None if raw_tables is None else np.ascontiguousarray(raw_tables, dtype=np.uint32)
+    secs = ref_lib().refdrv_decode_threaded_tables(_ptr(stream), _ptr(offsets, _u64p),
+                                                   seg.ctypes.data_as(C.POINTER(C.c_int)), len(seg) - 1,
+                                                   w, h, threads, 1 if zero_init else 0,
+                                                   None if frames is None else _ptr(frames),
+                                                   None if raw is None else _ptr(raw, _u32p))
     return float(secs), frames
 
 

@@ -249,6 +249,7 @@ typedef struct {
     uint8_t *frames_out;        /* may be NULL */
     int zero_init;              /* clear the planes at every segment start */
     uint64_t checksum;
+    const uint32_t *raw;        /* NULL, or 128 raw tables loaded with RTjpeg_set_tables before the first packet */
 } dec_job;
 
 
@@ -259,6 +260,15 @@ static void *dec_worker(void *arg)
     uint8_t *pl_mem = (uint8_t *)malloc(fsz);
     uint8_t *pl[3] = { pl_mem, pl_mem + ysz, pl_mem + ysz * 5 / 4 };
     RTjpeg_t *d = ref_RTjpeg_init();
+    if (j->raw) {
+        /* the set_tables path: they stay in force while the packets' quality byte equals the decoder's Q (0 on a
+         * fresh instance, lib/RTjpeg.c:3575-3579) */
+        uint32_t tmp[128];
+        int ww = j->w, hh = j->h;
+        memcpy(tmp, j->raw, sizeof(tmp));
+        ref_RTjpeg_set_size(d, &ww, &hh);
+        ref_RTjpeg_set_tables(d, tmp);
+    }
     uint64_t acc = 0;
     for (int s = j->s0; s < j->s1; s++) {
         if (j->zero_init || s == j->s0) memset(pl_mem, 0, fsz);
@@ -284,9 +294,21 @@ static void *dec_worker(void *arg)
  * is not charged a memset the reference would not do).  Returns wall seconds
  * for the decode only (CLOCK_MONOTONIC).
  */
+double refdrv_decode_threaded_tables(const uint8_t *stream, const uint64_t *offsets,
+                                     const int *seg, int nseg, int w, int h, int threads,
+                                     int zero_init, uint8_t *frames_out, const uint32_t *raw);
+
 double refdrv_decode_threaded(const uint8_t *stream, const uint64_t *offsets,
                               const int *seg, int nseg, int w, int h, int threads,
                               int zero_init, uint8_t *frames_out)
+{
+    return refdrv_decode_threaded_tables(stream, offsets, seg, nseg, w, h, threads, zero_init, frames_out, NULL);
+}
+
+/* the same with every worker's decoder given raw tables through RTjpeg_set_tables first (packets carry quality 0) */
+double refdrv_decode_threaded_tables(const uint8_t *stream, const uint64_t *offsets,
+                                     const int *seg, int nseg, int w, int h, int threads,
+                                     int zero_init, uint8_t *frames_out, const uint32_t *raw)
 {
     if (threads < 1) threads = 1;
     if (threads > nseg) threads = nseg;
@@ -302,7 +324,7 @@ double refdrv_decode_threaded(const uint8_t *stream, const uint64_t *offsets,
         int e = s;
         while (e < nseg && seg[e + 1] <= want) e++;
         if (i == threads - 1) e = nseg;
-        jobs[i] = (dec_job){ stream, offsets, seg, s, e, w, h, frames_out, zero_init, 0 };
+        jobs[i] = (dec_job){ stream, offsets, seg, s, e, w, h, frames_out, zero_init, 0, raw };
         s = e;
         pthread_create(&th[i], NULL, dec_worker, &jobs[i]);
     }

@@ -55,7 +55,7 @@ E_CUDA, E_ARG, E_HEADER, E_SIZE, E_FORMAT, E_OVERRUN, E_TOOBIG, E_NOMEM = -1, -2
 HOST_IN_PINNED, HOST_OUT_PINNED = 1, 2
 STREAM_SLACK_BYTES = 128
 TABLE_ZERO, TABLE_CUSTOM = 0, 256
-SCAN_AUTO, SCAN_LANE, SCAN_WARP, SCAN_CHUNK, SCAN_SEGMENT = 0, 1, 2, 3, 4
+SCAN_AUTO, SCAN_LANE, SCAN_WARP, SCAN_CHUNK, SCAN_SEGMENT, SCAN_WALK = 0, 1, 2, 3, 4, 5
 PIPELINE_AUTO, PIPELINE_SERIAL = 0, 1
 
 _u8p = C.POINTER(C.c_uint8)
@@ -132,6 +132,8 @@ def load_library() -> C.CDLL:
         getattr(L, name).restype = None
     L.rtjgpu_plan.argtypes = [_u8p, _u64p, C.c_int, C.POINTER(State), vp]
     L.rtjgpu_decode_device.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp]
+    L.rtjgpu_decode_device_rgb.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_size_t, C.c_size_t, C.c_int,
+                                           vp, vp, vp]
     L.rtjgpu_decode_host.argtypes = [vp, _u8p, _u64p, C.c_int, C.POINTER(State), _u8p, _u8p, C.c_int]
     L.rtjgpu_sync.argtypes = [vp]
     L.rtjgpu_enable_timing.argtypes = [vp, C.c_int]
@@ -362,6 +364,15 @@ class BatchContext:
         _check(self._L.rtjgpu_decode_device(self._h, C.c_void_p(d_stream), C.c_void_p(d_desc), F, w, h,
                                             C.c_void_p(d_out), C.c_void_p(d_carry or 0),
                                             C.c_void_p(cuda_stream or 0)), "rtjgpu_decode_device")
+
+    def decode_device_rgb(self, d_stream: int, d_desc: int, F: int, w: int, h: int, kind: int, d_rgb: int, row_pitch: int,
+                          frame_pitch: int, alpha: int = 0, d_carry: int | None = None, d_last_yuv: int | None = None,
+                          cuda_stream: int | None = None) -> None:
+        """rtjgpu_decode_device with the converter `kind` (CONV_*) fused into the decode: packed pixels out."""
+        _check(self._L.rtjgpu_decode_device_rgb(self._h, C.c_void_p(d_stream), C.c_void_p(d_desc), F, w, h, kind,
+                                                C.c_void_p(d_rgb), row_pitch, frame_pitch, alpha, C.c_void_p(d_carry or 0),
+                                                C.c_void_p(d_last_yuv or 0), C.c_void_p(cuda_stream or 0)),
+               "rtjgpu_decode_device_rgb")
 
     def decode_host(self, stream: np.ndarray, offsets: np.ndarray, out: np.ndarray, state: State | None = None,
                     carry: np.ndarray | None = None, flags: int = 0) -> State:

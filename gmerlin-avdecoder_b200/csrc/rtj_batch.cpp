@@ -26,6 +26,7 @@ struct Workspace {
     uint32_t     *d_hardq = nullptr;
     uint16_t     *d_chunk_last = nullptr;
     uint16_t     *d_k3_carry = nullptr;  int    k3_carry_cap = 0;    /* [2][nblk]: last writers handed from slice to slice */
+    int2         *d_walk = nullptr;      int    walk_cap = 0;        /* [F]: where every frame's walker stands between slices */
     uint32_t     *d_frame_skips = nullptr;
     rtj_dev_info *d_info = nullptr;
     /* segment-parallel scan */
@@ -94,8 +95,8 @@ struct rtjgpu_ctx {
     int            format = RTJ_YUV420;
     Pipeline       pipe;
     int            pipeline_mode = RTJGPU_PIPELINE_AUTO;
-    int            slice_frames = 576, slice0_frames = 576;   /* multiples of RTJ_RESOLVE_T */
-    bool           scan_priority = true;
+    int            slice_frames = 1184, slice0_frames = 1184;   /* multiples of RTJ_RESOLVE_T */
+    bool           scan_priority = false;
     /* encoder: configuration, state between calls, workspace */
     int            enc_quality = 0, enc_lb8 = 0, enc_cb8 = 0;
     int            enc_key_rate = 0, enc_key_count = 0, enc_lm = 0, enc_cm = 0;
@@ -152,6 +153,12 @@ int ws_reserve(rtjgpu_ctx *ctx, Workspace *ws, int F, int nblk)
         ws->d_frame_skips = nullptr; ws->cap_frames = 0;
         CK(ctx, cudaMalloc(&ws->d_frame_skips, (size_t)F * sizeof(uint32_t)));
         ws->cap_frames = F;
+    }
+    if (F > ws->walk_cap) {
+        if (ws->d_walk) cudaFree(ws->d_walk);
+        ws->d_walk = nullptr; ws->walk_cap = 0;
+        CK(ctx, cudaMalloc(&ws->d_walk, (size_t)F * sizeof(int2)));
+        ws->walk_cap = F;
     }
     if (!ws->d_info) CK(ctx, cudaMalloc(&ws->d_info, sizeof(rtj_dev_info)));
     return RTJGPU_OK;
@@ -213,6 +220,7 @@ void ws_release(Workspace *ws)
     if (ws->d_hardq) cudaFree(ws->d_hardq);
     if (ws->d_chunk_last) cudaFree(ws->d_chunk_last);
     if (ws->d_k3_carry) cudaFree(ws->d_k3_carry);
+    if (ws->d_walk) cudaFree(ws->d_walk);
     if (ws->d_frame_skips) cudaFree(ws->d_frame_skips);
     if (ws->d_info) cudaFree(ws->d_info);
     if (ws->d_seg_sum) cudaFree(ws->d_seg_sum);
@@ -276,19 +284,33 @@ int plan_slices(const rtjgpu_ctx *ctx, int F, int *first)
  * K2's short-lived CTAs retire.  The last writer of a skipped block lies in an earlier frame, i.e. in a slice
  * that is already scanned, so nothing else has to be ordered.
  */
+/* where K2's pixels go when they leave as packed RGB (rtjgpu_decode_device_rgb) */
+struct RgbOut {
+    uint8_t *d_rgb = nullptr;
+    size_t   row_pitch = 0, frame_pitch = 0;
+    int      kind = 0;
+    unsigned alpha = 0;
+    uint8_t *d_last_yuv = nullptr;
+};
+
 int run_kernels(rtjgpu_ctx *ctx, Workspace *ws, const uint8_t *d_stream, const rtjgpu_frame_desc *d_desc,
                 int F, int w, int h, uint8_t *d_out, const uint8_t *d_carry, cudaStream_t st, cudaEvent_t *ev,
-                bool allow_pipe)
+                bool allow_pipe, const RgbOut *rgb = nullptr)
 {
     rtj_launch_args a;
     a.d_stream = d_stream; a.d_desc = d_desc; a.d_tables = ctx->d_tables;
     a.F = F; a.w = w; a.h = h;
     a.f0 = 0; a.f1 = F; a.slice = 0;
     a.fmt = ctx->format;
+    a.row0 = 0; a.row1 = RTJ_FMT_UNITS_Y(ctx->format, h);
+    a.d_walk = ws->d_walk;
     a.d_ent = ws->d_ent; a.d_src = ws->d_src; a.d_frame_skips = ws->d_frame_skips; a.d_info = ws->d_info;
     a.d_hardq = ws->d_hardq; a.d_chunk_last = ws->d_chunk_last;
     a.d_k3_in = nullptr; a.d_k3_out = ws->d_k3_carry;
     a.d_out = d_out; a.d_carry = d_carry;
+    a.d_rgb = rgb ? rgb->d_rgb : nullptr;
+    a.rgb_row_pitch = rgb ? rgb->row_pitch : 0; a.rgb_frame_pitch = rgb ? rgb->frame_pitch : 0;
+    a.rgb_kind = rgb ? rgb->kind : 0; a.rgb_alpha = rgb ? rgb->alpha : 0; a.d_last_yuv = rgb ? rgb->d_last_yuv : nullptr;
     a.scan_mode = ctx->scan_mode;
     const int nblk = RTJ_FMT_NBLK(ctx->format, w, h);
     {
@@ -342,7 +364,7 @@ int run_kernels(rtjgpu_ctx *ctx, Workspace *ws, const uint8_t *d_stream, const r
         a.f0 = 0; a.f1 = F;
         if (ev) CK(ctx, cudaEventRecord(ev[2], st));
         LAUNCHED(rtj_launch_idct(&a, st), 1);
-        LAUNCHED(rtj_launch_idct_hard(&a, st), 1);
+        if (!rgb) LAUNCHED(rtj_launch_idct_hard(&a, st), 1);
         if (ev) CK(ctx, cudaEventRecord(ev[3], st));
         return RTJGPU_OK;
     }
@@ -368,7 +390,7 @@ int run_kernels(rtjgpu_ctx *ctx, Workspace *ws, const uint8_t *d_stream, const r
         CK(ctx, cudaEventRecord(ev[2], p.scan));
     }
     a.f0 = 0; a.f1 = F;
-    LAUNCHED(rtj_launch_idct_hard(&a, p.idct), 1);
+    if (!rgb) LAUNCHED(rtj_launch_idct_hard(&a, p.idct), 1);
     CK(ctx, cudaEventRecord(p.join, p.idct));
     CK(ctx, cudaStreamWaitEvent(st, p.join, 0));
     if (ev) CK(ctx, cudaEventRecord(ev[3], st));
@@ -514,7 +536,7 @@ void rtjgpu_enable_timing(rtjgpu_ctx *ctx, int on) { if (ctx) ctx->timing = on !
 
 int rtjgpu_set_scan_mode(rtjgpu_ctx *ctx, int mode)
 {
-    if (!ctx || mode < RTJGPU_SCAN_AUTO || mode > RTJGPU_SCAN_SEGMENT) return RTJGPU_E_ARG;
+    if (!ctx || mode < RTJGPU_SCAN_AUTO || mode > RTJGPU_SCAN_WALK) return RTJGPU_E_ARG;
     ctx->scan_mode = mode;
     return RTJGPU_OK;
 }
@@ -762,6 +784,39 @@ int rtjgpu_decode_device(rtjgpu_ctx *ctx, const uint8_t *d_stream, const rtjgpu_
     if (rc) return rc;
     cudaEvent_t *ev = ctx->timing ? ctx->ev[ctx->timed_calls % TIMING_RING] : nullptr;
     rc = run_kernels(ctx, &ctx->ws, d_stream, d_desc, F, w, h, d_out, d_carry, (cudaStream_t)cuda_stream, ev, true);
+    if (ev && rc == RTJGPU_OK) ctx->timed_calls++;
+    ctx->last_F = F;
+    ctx->last_stream = cuda_stream;
+    return rc;
+}
+
+int rtjgpu_decode_device_rgb(rtjgpu_ctx *ctx, const uint8_t *d_stream, const rtjgpu_frame_desc *d_desc, int F,
+                             int w, int h, int kind, uint8_t *d_rgb, size_t row_pitch, size_t frame_pitch, int alpha,
+                             const uint8_t *d_carry, uint8_t *d_last_yuv, void *cuda_stream)
+{
+    if (!ctx || F < 0) return RTJGPU_E_ARG;
+    if (ctx->format != RTJ_YUV420) return RTJGPU_E_FORMAT;                     /* the reference's converters are yuv420 ones */
+    if (kind != RTJ_CONV_RGB32 && kind != RTJ_CONV_BGR32 && kind != RTJ_CONV_RGB24 && kind != RTJ_CONV_BGR24 && kind != RTJ_CONV_RGB16)
+        return RTJGPU_E_FORMAT;
+    if (F == 0) { ctx->last_F = 0; return RTJGPU_OK; }
+    if (!d_stream || !d_desc || !d_rgb) return RTJGPU_E_ARG;
+    if (w <= 0 || h <= 0 || (w & 15) || (h & 15) || w > 65535 || h > 65535) return RTJGPU_E_SIZE;
+    if (F > RTJGPU_MAX_FRAMES_PER_BATCH) return RTJGPU_E_TOOBIG;
+    const int bpp = rtj_convert_bpp(kind);
+    if (((uintptr_t)d_stream & 3) || ((uintptr_t)d_desc & 7) || ((uintptr_t)d_rgb & 15) || ((uintptr_t)d_carry & 7)
+        || ((uintptr_t)d_last_yuv & 15) || (row_pitch & 15) || (frame_pitch & 15) || row_pitch < (size_t)w * bpp
+        || frame_pitch < row_pitch * (size_t)h)
+        return RTJGPU_E_ARG;
+    CK(ctx, cudaSetDevice(ctx->device));
+    const int nblk = RTJ_FMT_NBLK(ctx->format, w, h);
+    if ((uint64_t)F * (uint64_t)nblk >= (1ull << 32)) return RTJGPU_E_TOOBIG;
+    int rc = ws_reserve(ctx, &ctx->ws, F, nblk);
+    if (rc) return rc;
+    RgbOut o;
+    o.d_rgb = d_rgb; o.row_pitch = row_pitch; o.frame_pitch = frame_pitch; o.kind = kind; o.alpha = (unsigned)alpha & 0xFFu;
+    o.d_last_yuv = d_last_yuv;
+    cudaEvent_t *ev = ctx->timing ? ctx->ev[ctx->timed_calls % TIMING_RING] : nullptr;
+    rc = run_kernels(ctx, &ctx->ws, d_stream, d_desc, F, w, h, nullptr, d_carry, (cudaStream_t)cuda_stream, ev, true, &o);
     if (ev && rc == RTJGPU_OK) ctx->timed_calls++;
     ctx->last_F = F;
     ctx->last_stream = cuda_stream;

@@ -116,6 +116,8 @@ typedef struct rtj_launch_args {
     int                      F, w, h;
     int                      f0, f1;        /* the frames this launch covers (a slice); K1 segment-parallel and the serial flavours: 0, F */
     int                      slice;         /* index of the slice [f0, f1) */
+    int                      row0, row1;    /* the rows of units K2 of this launch covers (all of them, as things are) */
+    void                    *d_walk;        /* [F] int2: rtj_scan_walk_kernel's state between slices of blocks */
     int                      fmt;           /* RTJ_YUV420 / RTJ_YUV422 / RTJ_RGB8 */
     uint32_t                *d_ent;         /* [F][nblk] */
     uint16_t                *d_src;         /* [F][nblk] */
@@ -128,6 +130,12 @@ typedef struct rtj_launch_args {
     uint8_t                 *d_out;
     const uint8_t           *d_carry;
     const void              *d_lut;         /* K2: position table of this geometry (rtj_launch_build_lut) */
+    /* K2 with the fused colour conversion (d_rgb != NULL): packed pixels instead of planes */
+    uint8_t                 *d_rgb;
+    size_t                   rgb_row_pitch, rgb_frame_pitch;
+    int                      rgb_kind;      /* RTJ_CONV_RGB32 / BGR32 / RGB24 / BGR24 / RGB16 */
+    unsigned                 rgb_alpha;
+    uint8_t                 *d_last_yuv;    /* the batch's last frame as planes too, or NULL */
     int                      scan_mode;     /* RTJGPU_SCAN_* */
     rtj_seg_plan             seg;           /* workspace of the segment-parallel scan (sum == NULL: not available) */
 } rtj_launch_args;
@@ -137,6 +145,9 @@ int rtj_launch_scan(const rtj_launch_args *a, void *stream);          /* returns
 int rtj_launch_scan_chunk(const rtj_launch_args *a, int phase, void *stream);    /* rtj_scan_chunk.cu */
 int rtj_scan_chunk_init(void);
 int rtj_launch_scan_mb(const rtj_launch_args *a, int phase, void *stream);       /* rtj_scan_mb.cu */
+int rtj_launch_scan_walk(const rtj_launch_args *a, int b0, int b1, void *stream);   /* rtj_scan_walk.cu: blocks [b0, b1) of every frame */
+int rtj_scan_walk_init(void);
+
 int rtj_scan_mb_init(void);
 int rtj_launch_resolve(const rtj_launch_args *a, void *stream);
 int rtj_launch_idct(const rtj_launch_args *a, void *stream);           /* K2 over the slice */

@@ -29,6 +29,7 @@
 #include <stdint.h>
 
 #include "rtj_common.h"
+#include "rtj_convert.cuh"
 
 namespace {
 
@@ -468,6 +469,7 @@ struct K2Params {
     const uint16_t *srcf;
     int nblk, w, h, seg_mb, nstrips;
     int f0, F;                       /* first frame of this launch (blockIdx.y = 0); frames of the batch */
+    int row0, rows;                  /* first row of units of this launch (blockIdx.x = 0); rows of units of a picture */
     uint8_t *out;
     const uint8_t *carry;
     int fmt;
@@ -475,9 +477,63 @@ struct K2Params {
     unsigned hardq_cap;              /* entries of hardq: F * nblk */
     rtj_dev_info *info;
     const uint32_t *pos;             /* SINGLE: pic_pos of every position of a row, i | off << 16 (rtj_build_lut_kernel) */
+    /* RGB: the strip leaves as packed pixels (out / fmt unused) */
+    uint8_t *rgb;                    /* picture row r of frame f at rgb + f * rgb_frame_pitch + r * rgb_row_pitch */
+    size_t rgb_row_pitch, rgb_frame_pitch;
+    int rgb_kind;                    /* RTJ_CONV_RGB32 / BGR32 / RGB24 / BGR24 / RGB16 */
+    unsigned rgb_alpha;
+    uint8_t *last_yuv;               /* RGB: the batch's last frame as planes as well (the next batch's carry), or NULL */
     int ahead;                       /* frames between a CTA and the one that follows it on the same SM slot */
     int wq;                          /* slots of one warp's queue */
 };
+
+/* The general decoder for one block that K2's sparse classes do not take (long blocks; blocks whose last writer used
+ * other tables): gidx = frame * nblk + block.  `full`: more than 16 coefficients -- the reference's two full passes, fed
+ * byte by byte; else the first 16 zig-zag positions (rows 0..5, columns 0..4) from 24 bytes held in registers. */
+__device__ __forceinline__ void decode_general(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc *__restrict__ desc,
+                                               const rtj_dev_table *__restrict__ tables, const uint32_t *__restrict__ ent,
+                                               const uint16_t *__restrict__ srcf, int nblk, uint32_t gidx, int chroma, bool full,
+                                               uint32_t (&px)[16])
+{
+    const unsigned f = gidx / (unsigned)nblk;
+    const int i = (int)(gidx - f * (unsigned)nblk);
+    uint32_t e = ent[gidx];
+    unsigned sf = f;
+    if (RTJ_ENT_IS_SKIP(e)) {                    /* queued skipped blocks always have a writer in the batch */
+        sf = srcf[gidx];
+        e = ent[(size_t)sf * nblk + i];
+    }
+    const rtj_dev_table *t = &tables[min((int)desc[sf].table, RTJ_NUM_TABLES - 1)];
+    const uint8_t *src = stream + desc[sf].offset + RTJPEG_B200_HEADER_BYTES + (e & RTJ_ENT_OFF_MASK);
+    if (RTJ_ENT_IS_INLINE(e)) {
+        const int x0 = wrap16((int)(e & 0xFFu) * t->iq[chroma][0]) + 4;
+        const int x1 = wrap16((int)(signed char)((e >> 8) & 0xFFu) * t->iq[chroma][1]);
+        const int q = wrap16((int)(signed char)((e >> 16) & 0xFFu) * t->iq[chroma][2]);
+        t2_pixels(x0, x1, q, false, px);
+    } else if (full) {
+        MemBytes by(src);
+        int x[64];
+        unpack_block<64>(by, t->iq[chroma], t->bt8[chroma], x);
+        idct_general<64>(x, px);
+    } else {
+        RegBytes<6> by(src);
+        int x[16];
+        unpack_block<16>(by, t->iq[chroma], t->bt8[chroma], x);
+        idct_general<16>(x, px);
+    }
+}
+
+/* the same as a call (the fused-RGB kernel's rare path: kept out of line so that it does not set the kernel's registers) */
+__device__ __noinline__ void decode_general_call(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc *__restrict__ desc,
+                                                 const rtj_dev_table *__restrict__ tables, const uint32_t *__restrict__ ent,
+                                                 const uint16_t *__restrict__ srcf, int nblk, uint32_t gidx, int chroma, int full,
+                                                 uint32_t *__restrict__ px16)
+{
+    uint32_t px[16];
+    decode_general(stream, desc, tables, ent, srcf, nblk, gidx, chroma, full != 0, px);
+#pragma unroll
+    for (int r = 0; r < 16; r++) px16[r] = px[r];
+}
 
 constexpr int K2_WARPS = IDCT_THREADS / 32;
 constexpr int K2_PF_LINES = 12;                   /* 128-byte lines of payload asked into L2 for the CTA that follows */
@@ -494,10 +550,17 @@ constexpr int K2_PF_LINES = 12;                   /* 128-byte lines of payload a
  * SINGLE: the strip is the whole macroblock row (frames up to IDCT_MAX_MB macroblocks wide): no
  * strip arithmetic, and the strip is contiguous in the tight-pitch output planes -> TMA bulk stores.
  */
-template <bool SINGLE, int FMT, int WARPS>
+/* RGBK: RGB_NONE = planes leave; RTJ_CONV_RGB32 .. RTJ_CONV_RGB16 = that converter fused into the store (one kernel per
+ * kind: the conversion doubles the kernel's arithmetic and wants its registers); RGB_ANY = the kind is read at run time
+ * (strips of very wide pictures: not worth five more kernels) */
+constexpr int RGB_NONE = -1, RGB_ANY = 99;
+
+template <bool SINGLE, int FMT, int WARPS, int RGBK>
 __global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? 8 : 10)
 rtj_idct_kernel(const K2Params P)
 {
+    constexpr bool RGB = RGBK != RGB_NONE;
+    static_assert(!RGB || FMT == 0, "the fused converters are the reference's yuv420 ones");
     constexpr int THREADS = WARPS * 32;
     typedef Geo<FMT> G;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -505,7 +568,7 @@ rtj_idct_kernel(const K2Params P)
     const unsigned f = blockIdx.y + (unsigned)P.f0;
     const int w = P.w, h = P.h, mbw = w / G::UNIT_W;           /* units per picture row */
     const int strip = SINGLE ? 0 : (int)(blockIdx.x % (unsigned)P.nstrips);
-    const int my = SINGLE ? (int)blockIdx.x : (int)(blockIdx.x / (unsigned)P.nstrips);
+    const int my = P.row0 + (SINGLE ? (int)blockIdx.x : (int)(blockIdx.x / (unsigned)P.nstrips));
     const int mx0 = strip * P.seg_mb;
     const int mbs = SINGLE ? mbw : min(P.seg_mb, mbw - mx0);
     const int nb = mbs * G::BLK;
@@ -630,7 +693,7 @@ rtj_idct_kernel(const K2Params P)
      * evenly over the rows: the M7 blocks read it */
     if (f + (unsigned)P.ahead < (unsigned)P.F && warp == WARPS - 1 && lane < K2_PF_LINES) {
         const rtjgpu_frame_desc nd = P.desc[f + (unsigned)P.ahead];
-        const unsigned rows_total = SINGLE ? gridDim.x : gridDim.x / (unsigned)P.nstrips;
+        const unsigned rows_total = (unsigned)P.rows;
         const unsigned plen = nd.length > RTJPEG_B200_HEADER_BYTES ? nd.length - RTJPEG_B200_HEADER_BYTES : 0u;
         const unsigned at = (unsigned)(((unsigned long long)plen * (unsigned)my) / rows_total);
         const unsigned o = (at & ~127u) + (unsigned)lane * 128u;
@@ -684,7 +747,16 @@ rtj_idct_kernel(const K2Params P)
             const bool hard = live && !(ie >> 31);
             const bool full = hard && ((ie >> 30) & 1u);
             const int bi = (int)(ie & 0x3FFFFFFFu);              /* stream-order index inside the strip */
-            const unsigned mH = __ballot_sync(FULL, hard && !full), mF = __ballot_sync(FULL, full);
+            if (RGB) {
+                /* no planes for rtj_idct_hard_kernel to patch: the general decoder runs here, out of line */
+                if (hard) {
+                    uint32_t px[16];
+                    decode_general_call(P.stream, P.desc, P.tables, P.ent, P.srcf, P.nblk, frame_blk0 + (unsigned)bi,
+                                        off_is_chroma<FMT>(off, mbs) ? 1 : 0, full ? 1 : 0, px);
+                    store_block<FMT>(tile_s, off, mbs, px);
+                }
+            }
+            const unsigned mH = RGB ? 0u : __ballot_sync(FULL, hard && !full), mF = RGB ? 0u : __ballot_sync(FULL, full);
             if (mH | mF) {
                 /* the device queue is filled from both ends: mid-size blocks from the front, long ones from the back */
                 unsigned base = 0, baseF = 0;
@@ -723,12 +795,42 @@ rtj_idct_kernel(const K2Params P)
     /* ---- the strip leaves the SM (a strip made of HARD blocks only has nothing to say) ---- */
     if (SINGLE) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
-    if (s_hard[0] + s_hard[1] + s_hard[2] + s_hard[3] == nb) return;
+    const int lw = G::UNIT_W * mbs;                              /* luma bytes per strip row */
+    if (RGB) {
+        /* The strip -- 16 luma rows, 8 rows of Cb and of Cr: exactly what the reference's converters read for 16 output
+         * rows (lib/RTjpeg.c:3123-3190) -- leaves as packed pixels.  A thread takes 8 pixels of two rows (one chroma row):
+         * aligned 8- / 4-byte shared loads, 16- / 8-byte global stores, contiguous across the warp. */
+        using namespace rtjcv;
+        const int chunks = lw >> 3;
+        const uint8_t *tU = tile + G::CHROMA_AT * mbs, *tV = tU + 64 * mbs;
+        const int kind = RGBK == RGB_ANY ? P.rgb_kind : RGBK;
+        const int bpp = (kind == RTJ_CONV_RGB32 || kind == RTJ_CONV_BGR32) ? 4 : kind == RTJ_CONV_RGB16 ? 2 : 3;
+        uint8_t *base = P.rgb + (size_t)f * P.rgb_frame_pitch + (size_t)(my * 16) * P.rgb_row_pitch + (size_t)(mx0 * 16) * bpp;
+        for (int item = tid; item < 8 * chunks; item += THREADS) {
+            const int rp = item / chunks, c = item - rp * chunks;
+            const uint2 y0 = *reinterpret_cast<const uint2 *>(tile + (2 * rp) * lw + c * 8);
+            const uint2 y1 = *reinterpret_cast<const uint2 *>(tile + (2 * rp + 1) * lw + c * 8);
+            const uint32_t ub = *reinterpret_cast<const uint32_t *>(tU + rp * (lw >> 1) + c * 4);
+            const uint32_t vb = *reinterpret_cast<const uint32_t *>(tV + rp * (lw >> 1) + c * 4);
+            Chroma ct[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) ct[k] = chroma_terms((ub >> (8 * k)) & 0xFFu, (vb >> (8 * k)) & 0xFFu);
+            uint8_t *o = base + (size_t)(2 * rp) * P.rgb_row_pitch + (size_t)c * (8 * bpp);
+            switch (kind) {
+            case RTJ_CONV_RGB32: row8<RTJ_CONV_RGB32>(y0, ct, P.rgb_alpha, o); row8<RTJ_CONV_RGB32>(y1, ct, P.rgb_alpha, o + P.rgb_row_pitch); break;
+            case RTJ_CONV_BGR32: row8<RTJ_CONV_BGR32>(y0, ct, P.rgb_alpha, o); row8<RTJ_CONV_BGR32>(y1, ct, P.rgb_alpha, o + P.rgb_row_pitch); break;
+            case RTJ_CONV_RGB24: row8<RTJ_CONV_RGB24>(y0, ct, P.rgb_alpha, o); row8<RTJ_CONV_RGB24>(y1, ct, P.rgb_alpha, o + P.rgb_row_pitch); break;
+            case RTJ_CONV_BGR24: row8<RTJ_CONV_BGR24>(y0, ct, P.rgb_alpha, o); row8<RTJ_CONV_BGR24>(y1, ct, P.rgb_alpha, o + P.rgb_row_pitch); break;
+            default:             row8<RTJ_CONV_RGB16>(y0, ct, P.rgb_alpha, o); row8<RTJ_CONV_RGB16>(y1, ct, P.rgb_alpha, o + P.rgb_row_pitch); break;
+            }
+        }
+        if (!P.last_yuv || f + 1u != (unsigned)P.F) return;      /* the last frame also leaves as planes: the next batch's carry */
+    } else if (s_hard[0] + s_hard[1] + s_hard[2] + s_hard[3] == nb) return;
     const size_t fsz = RTJ_FMT_FRAME_BYTES(FMT, w, h);
     const int cw = w >> 1;
-    const int lw = G::UNIT_W * mbs;                              /* luma bytes per strip row */
-    uint8_t *oy = P.out + (size_t)f * fsz + (size_t)(my * G::LUMA_ROWS) * w + mx0 * G::UNIT_W;
-    uint8_t *ou = P.out + (size_t)f * fsz + (size_t)w * h + (size_t)(my * 8) * cw + mx0 * 8;
+    uint8_t *const planes = RGB ? P.last_yuv : P.out + (size_t)f * fsz;
+    uint8_t *oy = planes + (size_t)(my * G::LUMA_ROWS) * w + mx0 * G::UNIT_W;
+    uint8_t *ou = planes + (size_t)w * h + (size_t)(my * 8) * cw + mx0 * 8;
     uint8_t *ov = ou + (FMT == 0 ? (size_t)cw * (h >> 1) : (size_t)cw * h);
     const uint8_t *tileU = tile + G::CHROMA_AT * mbs, *tileV = tileU + 64 * mbs;
     if (SINGLE) {
@@ -800,32 +902,9 @@ rtj_idct_hard_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc
         const uint32_t gidx = full ? hardq[hardq_cap - 1u - (k - n16)] : hardq[k];
         const unsigned f = gidx / (unsigned)nblk;
         const int i = (int)(gidx - f * (unsigned)nblk);
-        uint32_t e = ent[gidx];
-        unsigned sf = f;
-        if (RTJ_ENT_IS_SKIP(e)) {                    /* queued skipped blocks always have a writer in the batch */
-            sf = srcf[gidx];
-            e = ent[(size_t)sf * nblk + i];
-        }
         const int chroma = (i % unit) >= unit_luma;
-        const rtj_dev_table *t = &tables[min((int)desc[sf].table, RTJ_NUM_TABLES - 1)];
-        const uint8_t *src = stream + desc[sf].offset + RTJPEG_B200_HEADER_BYTES + (e & RTJ_ENT_OFF_MASK);
         uint32_t px[16];
-        if (full) {
-            MemBytes by(src);
-            int x[64];
-            unpack_block<64>(by, t->iq[chroma], t->bt8[chroma], x);
-            idct_general<64>(x, px);
-        } else if (RTJ_ENT_IS_INLINE(e)) {
-            const int x0 = wrap16((int)(e & 0xFFu) * t->iq[chroma][0]) + 4;
-            const int x1 = wrap16((int)(signed char)((e >> 8) & 0xFFu) * t->iq[chroma][1]);
-            const int q = wrap16((int)(signed char)((e >> 16) & 0xFFu) * t->iq[chroma][2]);
-            t2_pixels(x0, x1, q, false, px);
-        } else {
-            RegBytes<6> by(src);
-            int x[16];
-            unpack_block<16>(by, t->iq[chroma], t->bt8[chroma], x);
-            idct_general<16>(x, px);
-        }
+        decode_general(stream, desc, tables, ent, srcf, nblk, gidx, chroma, full, px);
         int pitch;
         uint8_t *dst = block_dst(out + (size_t)f * fsz, fmt, i, w, h, pitch);
 #pragma unroll
@@ -865,16 +944,17 @@ inline size_t idct_smem_bytes(int seg_mb, int fmt, int warps)
 
 int g_sm_count = 0;
 
-template <bool SINGLE, int FMT, int WARPS>
+template <bool SINGLE, int FMT, int WARPS, int RGBK>
 cudaError_t k2_attr()
 {
-    return cudaFuncSetAttribute(rtj_idct_kernel<SINGLE, FMT, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    return cudaFuncSetAttribute(rtj_idct_kernel<SINGLE, FMT, WARPS, RGBK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)idct_smem_bytes(IDCT_MAX_MB, FMT, 3));
 }
 
-template <int FMT>
+template <int FMT, int RGBK>
 cudaError_t k2_launch(K2Params &P, int grid_x, int F, cudaStream_t st)
 {
+    constexpr int RGBS = RGBK == RGB_NONE ? RGB_NONE : RGB_ANY;          /* what the strip kernels are instantiated with */
     const int blk = FMT == 0 ? 6 : FMT == 1 ? 4 : 1;
     const int warps = idct_warps(P.seg_mb * blk);
     P.wq = idct_wq(P.seg_mb * blk, warps);
@@ -883,22 +963,23 @@ cudaError_t k2_launch(K2Params &P, int grid_x, int F, cudaStream_t st)
     const size_t smem = idct_smem_bytes(P.seg_mb, FMT, warps);
     const dim3 grid((unsigned)grid_x, (unsigned)F);
     if (P.nstrips == 1) {
-        if (warps == 4) rtj_idct_kernel<true, FMT, 4><<<grid, 128, smem, st>>>(P);
-        else rtj_idct_kernel<true, FMT, 3><<<grid, 96, smem, st>>>(P);
+        if (warps == 4) rtj_idct_kernel<true, FMT, 4, RGBK><<<grid, 128, smem, st>>>(P);
+        else rtj_idct_kernel<true, FMT, 3, RGBK><<<grid, 96, smem, st>>>(P);
     } else {
-        if (warps == 4) rtj_idct_kernel<false, FMT, 4><<<grid, 128, smem, st>>>(P);
-        else rtj_idct_kernel<false, FMT, 3><<<grid, 96, smem, st>>>(P);
+        if (warps == 4) rtj_idct_kernel<false, FMT, 4, RGBS><<<grid, 128, smem, st>>>(P);
+        else rtj_idct_kernel<false, FMT, 3, RGBS><<<grid, 96, smem, st>>>(P);
     }
     return cudaGetLastError();
 }
 
-template <int FMT>
+template <int FMT, int RGBK>
 cudaError_t k2_attrs()
 {
-    cudaError_t e = k2_attr<true, FMT, 4>();
-    if (e == cudaSuccess) e = k2_attr<false, FMT, 4>();
-    if (e == cudaSuccess) e = k2_attr<true, FMT, 3>();
-    if (e == cudaSuccess) e = k2_attr<false, FMT, 3>();
+    constexpr int RGBS = RGBK == RGB_NONE ? RGB_NONE : RGB_ANY;
+    cudaError_t e = k2_attr<true, FMT, 4, RGBK>();
+    if (e == cudaSuccess) e = k2_attr<false, FMT, 4, RGBS>();
+    if (e == cudaSuccess) e = k2_attr<true, FMT, 3, RGBK>();
+    if (e == cudaSuccess) e = k2_attr<false, FMT, 3, RGBS>();
     return e;
 }
 
@@ -906,9 +987,14 @@ cudaError_t k2_attrs()
 
 extern "C" int rtj_idct_init(void)
 {
-    cudaError_t e = k2_attrs<0>();
-    if (e == cudaSuccess) e = k2_attrs<1>();
-    if (e == cudaSuccess) e = k2_attrs<2>();
+    cudaError_t e = k2_attrs<0, RGB_NONE>();
+    if (e == cudaSuccess) e = k2_attrs<0, RTJ_CONV_RGB32>();
+    if (e == cudaSuccess) e = k2_attrs<0, RTJ_CONV_BGR32>();
+    if (e == cudaSuccess) e = k2_attrs<0, RTJ_CONV_RGB24>();
+    if (e == cudaSuccess) e = k2_attrs<0, RTJ_CONV_BGR24>();
+    if (e == cudaSuccess) e = k2_attrs<0, RTJ_CONV_RGB16>();
+    if (e == cudaSuccess) e = k2_attrs<1, RGB_NONE>();
+    if (e == cudaSuccess) e = k2_attrs<2, RGB_NONE>();
     if (e != cudaSuccess) return (int)e;
     int dev = 0;
     if ((e = cudaGetDevice(&dev)) != cudaSuccess) return (int)e;
@@ -950,9 +1036,24 @@ extern "C" int rtj_launch_idct(const rtj_launch_args *a, void *stream)
     P.fmt = fmt;
     P.pos = reinterpret_cast<const uint32_t *>(a->d_lut);
     P.f0 = a->f0; P.F = a->F;
-    const int grid_x = P.nstrips * uy;
+    P.row0 = a->row0; P.rows = uy;
+    const int grid_x = P.nstrips * (a->row1 - a->row0);
     const int nf = a->f1 - a->f0;
-    cudaError_t e = fmt == 0 ? k2_launch<0>(P, grid_x, nf, st) : fmt == 1 ? k2_launch<1>(P, grid_x, nf, st) : k2_launch<2>(P, grid_x, nf, st);
+    P.rgb = a->d_rgb; P.rgb_row_pitch = a->rgb_row_pitch; P.rgb_frame_pitch = a->rgb_frame_pitch;
+    P.rgb_kind = a->rgb_kind; P.rgb_alpha = a->rgb_alpha & 0xFFu; P.last_yuv = a->d_last_yuv;
+    if (a->d_rgb) {
+        if (fmt != 0) return (int)cudaErrorInvalidValue;
+        switch (a->rgb_kind) {
+        case RTJ_CONV_RGB32: return (int)k2_launch<0, RTJ_CONV_RGB32>(P, grid_x, nf, st);
+        case RTJ_CONV_BGR32: return (int)k2_launch<0, RTJ_CONV_BGR32>(P, grid_x, nf, st);
+        case RTJ_CONV_RGB24: return (int)k2_launch<0, RTJ_CONV_RGB24>(P, grid_x, nf, st);
+        case RTJ_CONV_BGR24: return (int)k2_launch<0, RTJ_CONV_BGR24>(P, grid_x, nf, st);
+        case RTJ_CONV_RGB16: return (int)k2_launch<0, RTJ_CONV_RGB16>(P, grid_x, nf, st);
+        default: return (int)cudaErrorInvalidValue;
+        }
+    }
+    cudaError_t e = fmt == 0 ? k2_launch<0, RGB_NONE>(P, grid_x, nf, st) : fmt == 1 ? k2_launch<1, RGB_NONE>(P, grid_x, nf, st)
+                                                                        : k2_launch<2, RGB_NONE>(P, grid_x, nf, st);
     return (int)e;
 }
 

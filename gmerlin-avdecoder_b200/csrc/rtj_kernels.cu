@@ -445,6 +445,7 @@ extern "C" int rtj_kernels_init(void)
     int e = rtj_idct_init();
     if (e) return e;
     if ((e = rtj_scan_mb_init())) return e;
+    if ((e = rtj_scan_walk_init())) return e;
     return rtj_scan_chunk_init();
 }
 
@@ -475,6 +476,12 @@ extern "C" int rtj_launch_scan(const rtj_launch_args *a, void *stream)
     }
     /* rtjgpu_set_scan_mode() forces one serial flavour for every frame: one lane per frame (cheap in
      * issue slots, latency hidden only by very large batches) or one warp per frame. */
+    if (a->scan_mode == RTJGPU_SCAN_WALK) {
+        /* the walker takes the frames without raw prefix, rtj_scan_mb_kernel the others */
+        int e = rtj_launch_scan_walk(a, 0, nblk, stream);
+        if (!e) e = rtj_launch_scan_mb(a, 0, stream);
+        return e ? -e : 2;
+    }
     if (a->scan_mode == RTJGPU_SCAN_LANE) {
         rtj_scan_lane_kernel<<<(a->F + 31) / 32, 32, 0, st>>>(
             a->d_stream, a->d_desc, a->d_tables, a->F, nblk, a->d_ent, a->d_frame_skips, a->d_info, 0,

@@ -196,13 +196,15 @@ int  rtjgpu_last_cuda_error(const rtjgpu_ctx *ctx);
  * chunk-parallel arrangements by batch size: CHUNK = one CTA per frame walks the frame's 8 KB
  * segments in turn (every byte position examined in parallel inside a segment) -- many frames;
  * SEGMENT = the segments of a frame go to separate CTAs, with a frame-level chain between a summary
- * pass and an emit pass -- few, large frames (and the one-frame RTjpeg_decompress).  LANE / WARP
- * force a serial walk instead: one thread per frame or one warp per frame. */
+ * pass and an emit pass -- few, large frames (and the one-frame RTjpeg_decompress).  LANE / WARP / WALK
+ * force a serial walk instead: one thread per frame or one warp per frame.  The serial flavours are independent
+ * implementations of the grammar, kept for cross-checks; they are several times slower than what AUTO picks. */
 #define RTJGPU_SCAN_AUTO    0
 #define RTJGPU_SCAN_LANE    1
 #define RTJGPU_SCAN_WARP    2
 #define RTJGPU_SCAN_CHUNK   3
 #define RTJGPU_SCAN_SEGMENT 4
+#define RTJGPU_SCAN_WALK    5     /* one thread per frame, payload staged through shared memory with cp.async (not for raw-prefix frames) */
 int  rtjgpu_set_scan_mode(rtjgpu_ctx *ctx, int mode);
 
 /* How a large device batch is worked through.  AUTO (the default): in slices of frames, the scan of slice s + 1 on
@@ -282,6 +284,20 @@ int  rtjgpu_plan_n(const uint8_t *stream, const uint64_t *offsets, const uint32_
 int  rtjgpu_decode_device(rtjgpu_ctx *ctx, const uint8_t *d_stream,
                           const rtjgpu_frame_desc *d_desc, int F, int w, int h,
                           uint8_t *d_out, const uint8_t *d_carry, void *cuda_stream);
+
+/* Device-resident decode STRAIGHT TO PACKED PIXELS: rtjgpu_decode_device with one of the reference's yuv420 converters
+ * (RTJ_CONV_RGB32 / BGR32 / RGB24 / BGR24 / RGB16: RTjpeg_yuv420rgb32 ..., lib/RTjpeg.c:3123-3475) fused into the kernel
+ * that makes the pixels -- a macroblock row (16 luma rows, 8 of Cb and Cr) is converted while it still sits in shared
+ * memory, so the planes are never written to, nor read back from, device memory.  Bit for bit what RTjpeg_decompress
+ * followed by the converter gives.  Picture row r of frame f goes to d_rgb + f * frame_pitch + r * row_pitch (both
+ * multiples of 16, as d_rgb); the fourth byte of a 32-bit pixel receives `alpha`.  d_carry: the picture before the batch
+ * as PLANES (w*h*3/2 bytes, or NULL = zeros), as for rtjgpu_decode_device; d_last_yuv (w*h*3/2 bytes, 16-byte aligned, or
+ * NULL) receives the batch's last frame as planes -- the next batch's d_carry.  Contexts in RTJ_YUV420 format only.
+ * Meant for streams of ordinary quality: blocks outside the sparse classes (more than seven coefficients) are decoded
+ * by a slow path inside the kernel here, not by the separate general kernel. */
+int  rtjgpu_decode_device_rgb(rtjgpu_ctx *ctx, const uint8_t *d_stream, const rtjgpu_frame_desc *d_desc, int F,
+                              int w, int h, int kind, uint8_t *d_rgb, size_t row_pitch, size_t frame_pitch, int alpha,
+                              const uint8_t *d_carry, uint8_t *d_last_yuv, void *cuda_stream);
 
 /* Host-buffer decode: packets in host memory in, frames in host memory out.
  * The batch is cut into chunks that move through pinned staging buffers with

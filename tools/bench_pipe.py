@@ -28,15 +28,14 @@ def main():
     desc, _ = g.plan(stream, offsets)
     b = D.upload(stream, desc, w, h, device=0)
     ref = None
-    cases = [("serial", dict(RTJPEG_B200_PIPELINE="1"))]
-    for prio in (1, 0):
-        for sl in (288, 448, 576, 736, 896, 1184):
-            cases.append((f"pipe slice={sl} prio={prio}", dict(RTJPEG_B200_SLICE=str(sl), RTJPEG_B200_SCAN_PRIO=str(prio))))
-    for s0, sl in ((1184, 576), (1184, 448), (1184, 736), (296, 576), (148, 576), (576, 288)):
-        cases.append((f"pipe slice0={s0} slice={sl} prio=1",
-                      dict(RTJPEG_B200_SLICE=str(sl), RTJPEG_B200_SLICE0=str(s0), RTJPEG_B200_SCAN_PRIO="1")))
+    cases = [("serial", dict(RTJPEG_B200_PIPELINE="1")),
+             ]
+    for sl in (576, 1184, 2048):
+        for prio in (0, 1):
+            cases.append((f"frame slices {sl} prio={prio}", dict(RTJPEG_B200_SLICE=str(sl), RTJPEG_B200_SCAN_PRIO=str(prio))))
     for name, env in cases:
-        for k in ("RTJPEG_B200_PIPELINE", "RTJPEG_B200_SLICE", "RTJPEG_B200_SLICE0", "RTJPEG_B200_SCAN_PRIO"):
+        for k in ("RTJPEG_B200_PIPELINE", "RTJPEG_B200_SLICE", "RTJPEG_B200_SLICE0", "RTJPEG_B200_SCAN_PRIO",
+                  "RTJPEG_B200_WALK_MIN", "RTJPEG_B200_WALK_SLICES", "RTJPEG_B200_WALK_THREADS", "RTJPEG_B200_WALK_EXCLUSIVE"):
             os.environ.pop(k, None)
         os.environ.update(env)
         ctx = g.BatchContext(0)

@@ -16,6 +16,6 @@ The directory name carries a hyphen (it is the reference's name); import it as
 from .capi import (  # noqa: F401
     BatchContext, BatchInfo, RTjpeg, RTjpegError, State, Timing,
     FRAME_DESC_DTYPE, HOST_IN_PINNED, HOST_OUT_PINNED, LIB_PATH, PLUGIN_PATH, STREAM_SLACK_BYTES,
-    TABLE_CUSTOM, TABLE_ZERO, PIPELINE_AUTO, PIPELINE_SERIAL, CONV_BPP, CONVERTERS, NuvHeader, build_library, load_library, nuv_extract_rtj0, nuv_open, nuv_packets, nuv_probe,
+    TABLE_CUSTOM, TABLE_ZERO, PIPELINE_AUTO, PIPELINE_SERIAL, PIPELINE_SLICED, CONV_BPP, CONVERTERS, NuvHeader, build_library, load_library, nuv_extract_rtj0, nuv_open, nuv_packets, nuv_probe,
     plan, raw_tables_for_quality, split_shards, split_shards_lead, tables_for_quality, tables_from_raw,
 )

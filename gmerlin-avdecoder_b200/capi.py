@@ -56,7 +56,7 @@ HOST_IN_PINNED, HOST_OUT_PINNED = 1, 2
 STREAM_SLACK_BYTES = 128
 TABLE_ZERO, TABLE_CUSTOM = 0, 256
 SCAN_AUTO, SCAN_LANE, SCAN_WARP, SCAN_CHUNK, SCAN_SEGMENT, SCAN_WALK = 0, 1, 2, 3, 4, 5
-PIPELINE_AUTO, PIPELINE_SERIAL = 0, 1
+PIPELINE_AUTO, PIPELINE_SERIAL, PIPELINE_SLICED = 0, 1, 2
 
 _u8p = C.POINTER(C.c_uint8)
 _u32p = C.POINTER(C.c_uint32)
@@ -323,7 +323,7 @@ class BatchContext:
         _check(self._L.rtjgpu_set_scan_mode(self._h, mode), "rtjgpu_set_scan_mode")
 
     def set_pipeline(self, mode: int = PIPELINE_AUTO, slice_frames: int = 0) -> None:
-        """PIPELINE_AUTO: scan of slice s + 1 beside resolve + IDCT of slice s; PIPELINE_SERIAL: stage after stage."""
+        """PIPELINE_SERIAL (= AUTO at present): stage after stage; PIPELINE_SLICED: scan of slice s + 1 beside resolve + IDCT of slice s."""
         _check(self._L.rtjgpu_set_pipeline(self._h, mode, slice_frames), "rtjgpu_set_pipeline")
 
     def set_format(self, fmt: int) -> None:

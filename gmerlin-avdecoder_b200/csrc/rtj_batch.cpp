@@ -97,6 +97,7 @@ struct rtjgpu_ctx {
     int            pipeline_mode = RTJGPU_PIPELINE_AUTO;
     int            slice_frames = 1184, slice0_frames = 1184;   /* multiples of RTJ_RESOLVE_T */
     bool           scan_priority = false;
+    bool           slices_forced = false;     /* rtjgpu_set_pipeline / the environment gave a slice size: it holds in either arrangement */
     /* encoder: configuration, state between calls, workspace */
     int            enc_quality = 0, enc_lb8 = 0, enc_cb8 = 0;
     int            enc_key_rate = 0, enc_key_count = 0, enc_lm = 0, enc_cm = 0;
@@ -262,6 +263,8 @@ int plan_slices(const rtjgpu_ctx *ctx, int F, int *first)
 {
     auto up = [](int v) { return (v + RTJ_RESOLVE_T - 1) / RTJ_RESOLVE_T * RTJ_RESOLVE_T; };
     int s0 = up(std::max(ctx->slice0_frames, 1)), sl = up(std::max(ctx->slice_frames, 1));
+    /* stage after stage, slices only serve to bound K3's look-back: few and large (two launches each) */
+    if (ctx->pipeline_mode != RTJGPU_PIPELINE_SLICED && !ctx->slices_forced) s0 = sl = std::max(sl, 4096);
     if (F > s0 && (F - s0 + sl - 1) / sl + 1 > RTJ_MAX_SLICES) sl = up((F - s0 + RTJ_MAX_SLICES - 2) / (RTJ_MAX_SLICES - 1));
     int n = 0;
     first[0] = 0;
@@ -339,7 +342,7 @@ int run_kernels(rtjgpu_ctx *ctx, Workspace *ws, const uint8_t *d_stream, const r
     int first[RTJ_MAX_SLICES + 1];
     const int nslices = plan_slices(ctx, F, first);
     const bool chunk_scan = !a.seg.sum && (ctx->scan_mode == RTJGPU_SCAN_AUTO || ctx->scan_mode == RTJGPU_SCAN_CHUNK);
-    const bool piped = allow_pipe && chunk_scan && nslices >= 2 && ctx->pipeline_mode != RTJGPU_PIPELINE_SERIAL;
+    const bool piped = allow_pipe && chunk_scan && nslices >= 2 && ctx->pipeline_mode == RTJGPU_PIPELINE_SLICED;
     auto slice_args = [&](int i) {
         a.f0 = first[i]; a.f1 = first[i + 1]; a.slice = i;
         a.d_k3_in = i == 0 ? nullptr : ws->d_k3_carry + (size_t)(i & 1) * nblk;
@@ -461,10 +464,10 @@ int rtjgpu_create(int device, rtjgpu_ctx **out)
     if (!ctx) return RTJGPU_E_NOMEM;
     ctx->device = device;
     /* development knobs (tools/): slice sizes of the pipelined arrangement, K1's stream priority */
-    if (const char *v = getenv("RTJPEG_B200_SLICE")) ctx->slice_frames = ctx->slice0_frames = std::max(32, atoi(v));
+    if (const char *v = getenv("RTJPEG_B200_SLICE")) { ctx->slice_frames = ctx->slice0_frames = std::max(32, atoi(v)); ctx->slices_forced = true; }
     if (const char *v = getenv("RTJPEG_B200_SLICE0")) ctx->slice0_frames = std::max(32, atoi(v));
     if (const char *v = getenv("RTJPEG_B200_SCAN_PRIO")) ctx->scan_priority = atoi(v) != 0;
-    if (const char *v = getenv("RTJPEG_B200_PIPELINE")) ctx->pipeline_mode = atoi(v) == 1 ? RTJGPU_PIPELINE_SERIAL : RTJGPU_PIPELINE_AUTO;
+    if (const char *v = getenv("RTJPEG_B200_PIPELINE")) ctx->pipeline_mode = std::min(std::max(atoi(v), 0), (int)RTJGPU_PIPELINE_SLICED);
     int rc = RTJGPU_OK;
     do {
         if ((e = cudaSetDevice(device)) != cudaSuccess) { rc = RTJGPU_E_CUDA; break; }
@@ -543,9 +546,12 @@ int rtjgpu_set_scan_mode(rtjgpu_ctx *ctx, int mode)
 
 int rtjgpu_set_pipeline(rtjgpu_ctx *ctx, int mode, int slice_frames)
 {
-    if (!ctx || (mode != RTJGPU_PIPELINE_AUTO && mode != RTJGPU_PIPELINE_SERIAL) || slice_frames < 0) return RTJGPU_E_ARG;
+    if (!ctx || mode < RTJGPU_PIPELINE_AUTO || mode > RTJGPU_PIPELINE_SLICED || slice_frames < 0) return RTJGPU_E_ARG;
     ctx->pipeline_mode = mode;
-    if (slice_frames) ctx->slice_frames = ctx->slice0_frames = (slice_frames + RTJ_RESOLVE_T - 1) / RTJ_RESOLVE_T * RTJ_RESOLVE_T;
+    if (slice_frames) {
+        ctx->slice_frames = ctx->slice0_frames = (slice_frames + RTJ_RESOLVE_T - 1) / RTJ_RESOLVE_T * RTJ_RESOLVE_T;
+        ctx->slices_forced = true;
+    }
     return RTJGPU_OK;
 }
 
@@ -962,6 +968,8 @@ int rtjgpu_scan_device(rtjgpu_ctx *ctx, const uint8_t *d_stream, const rtjgpu_fr
     a.F = F; a.w = w; a.h = h; a.f0 = 0; a.f1 = F; a.slice = 0;
     a.fmt = ctx->format;
     a.d_ent = ctx->ws.d_ent; a.d_frame_skips = ctx->ws.d_frame_skips; a.d_info = ctx->ws.d_info;
+    a.d_walk = ctx->ws.d_walk;
+    a.row1 = RTJ_FMT_UNITS_Y(ctx->format, h);
     a.scan_mode = ctx->scan_mode;
     if ((rc = seg_reserve(ctx, &ctx->ws, F, nblk, ctx->scan_mode, &a.seg))) return rc;
     CK(ctx, cudaMemcpyAsync(ctx->ws.d_info, ctx->h_info_reset, sizeof(rtj_dev_info), cudaMemcpyHostToDevice, st));

@@ -28,6 +28,9 @@ extern "C" {
 #define RTJ_ENT_INLINE_BIT 0x80000000u
 #define RTJ_ENT_INLINE(dc, c1, c2) \
     (RTJ_ENT_INLINE_BIT | ((uint32_t)(dc) & 0xFFu) | (((uint32_t)(c1) & 0xFFu) << 8) | (((uint32_t)(c2) & 0xFFu) << 16))
+/* K3 replaces the skip marker of a block whose last writer's entry is inline -- and was written under the same tables --
+ * by a COPY of that entry (bit 30 tells): such a block needs no look-up of its last writer in K2 any more. */
+#define RTJ_ENT_COPY_BIT 0x40000000u
 #define RTJ_ENT_IS_SKIP(e) ((e) == RTJ_ENT_SKIP)
 #define RTJ_ENT_IS_INLINE(e) (((e) & RTJ_ENT_INLINE_BIT) != 0u && (e) != RTJ_ENT_SKIP)
 #define RTJ_ENT_EOB(e) ((int)(((e) >> RTJ_ENT_OFF_BITS) & 63u) + 1)

@@ -364,9 +364,10 @@ rtj_resolve_last_kernel(const uint32_t *__restrict__ ent, uint16_t *__restrict__
 }
 
 extern "C" __global__ void __launch_bounds__(128)
-rtj_resolve_kernel(const uint32_t *__restrict__ ent, const uint16_t *__restrict__ chunk_last,
+rtj_resolve_kernel(uint32_t *__restrict__ ent, const uint16_t *__restrict__ chunk_last,
                    uint16_t *__restrict__ src, int f0, int f1, int nblk, const rtj_dev_info *__restrict__ info, int slice,
-                   const uint16_t *__restrict__ carry_in, uint16_t *__restrict__ carry_out)
+                   const uint16_t *__restrict__ carry_in, uint16_t *__restrict__ carry_out,
+                   const rtjgpu_frame_desc *__restrict__ desc)
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nblk) return;
@@ -380,21 +381,43 @@ rtj_resolve_kernel(const uint32_t *__restrict__ ent, const uint16_t *__restrict_
         unsigned last = RTJ_SRC_CARRY;
         for (int c = c0 - 1; c >= c_lo && last == RTJ_SRC_CARRY; c--) last = chunk_last[(size_t)c * nblk + b];
         if (last == RTJ_SRC_CARRY && carry_in) last = carry_in[b];
+        /* the last writer's entry, when it is an inline one (the block travels in it), and the tables it was written under:
+         * a skipped block of a frame with the same tables gets a copy of it (RTJ_ENT_COPY_BIT) in the place of its marker */
+        uint32_t last_e = 0;
+        unsigned last_tab = 0;
+        if (last != RTJ_SRC_CARRY) {
+            const uint32_t e = ent[(size_t)last * nblk + b];
+            if (RTJ_ENT_IS_INLINE(e)) { last_e = e | RTJ_ENT_COPY_BIT; last_tab = desc[last].table; }
+        }
         uint32_t e[8];
+        unsigned tab[8];
         int f = fa;
         for (; f + 8 <= fb; f += 8) {
 #pragma unroll
-            for (int j = 0; j < 8; j++) e[j] = ent[(size_t)(f + j) * nblk + b];
+            for (int j = 0; j < 8; j++) { e[j] = ent[(size_t)(f + j) * nblk + b]; tab[j] = desc[f + j].table; }
 #pragma unroll
             for (int j = 0; j < 8; j++) {
-                if (RTJ_ENT_IS_SKIP(e[j])) src[(size_t)(f + j) * nblk + b] = (uint16_t)last;
-                else last = (unsigned)(f + j);
+                if (RTJ_ENT_IS_SKIP(e[j])) {
+                    src[(size_t)(f + j) * nblk + b] = (uint16_t)last;
+                    if (last_e && tab[j] == last_tab) ent[(size_t)(f + j) * nblk + b] = last_e;
+                } else {
+                    last = (unsigned)(f + j);
+                    last_e = RTJ_ENT_IS_INLINE(e[j]) ? (e[j] | RTJ_ENT_COPY_BIT) : 0u;
+                    last_tab = tab[j];
+                }
             }
         }
         for (; f < fb; f++) {
             const uint32_t ee = ent[(size_t)f * nblk + b];
-            if (RTJ_ENT_IS_SKIP(ee)) src[(size_t)f * nblk + b] = (uint16_t)last;
-            else last = (unsigned)f;
+            const unsigned tb = desc[f].table;
+            if (RTJ_ENT_IS_SKIP(ee)) {
+                src[(size_t)f * nblk + b] = (uint16_t)last;
+                if (last_e && tb == last_tab) ent[(size_t)f * nblk + b] = last_e;
+            } else {
+                last = (unsigned)f;
+                last_e = RTJ_ENT_IS_INLINE(ee) ? (ee | RTJ_ENT_COPY_BIT) : 0u;
+                last_tab = tb;
+            }
         }
         if (fb == f1) carry_out[b] = (uint16_t)last;                 /* the slice's last chunk: what the next slice starts from */
     }
@@ -505,6 +528,6 @@ extern "C" int rtj_launch_resolve(const rtj_launch_args *a, void *stream)
     dim3 grid((unsigned)((nblk + 127) / 128), (unsigned)(nchunks < 16 ? nchunks : 16));
     rtj_resolve_last_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(a->d_ent, a->d_chunk_last, a->f0, a->f1, nblk, a->d_info, a->slice);
     rtj_resolve_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(a->d_ent, a->d_chunk_last, a->d_src, a->f0, a->f1, nblk, a->d_info,
-                                                               a->slice, a->d_k3_in, a->d_k3_out);
+                                                               a->slice, a->d_k3_in, a->d_k3_out, a->d_desc);
     return (int)cudaGetLastError();
 }

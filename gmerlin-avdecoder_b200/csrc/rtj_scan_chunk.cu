@@ -203,6 +203,13 @@ rtj_scan_chunk_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_des
                 slow |= (c0 | c1) ? 0u : 1u << i;
                 fill8[i] = P1 >> 24;
             }
+            /* skipped blocks (lib/RTjpeg.c:2704): a byte 0xFF is a block of its own, one byte long */
+            const uint32_t y = ~W0;
+            const uint32_t z = ~(((y & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | y | 0x7F7F7F7Fu);          /* bit 7 of every byte of W0 that is 0xFF */
+            /* ... and needs no token walk at all: inside a run of skip markers every position sees "coefficients" of -1
+             * without end, i.e. the longest possible block -- the slow path, for a length that is thrown away.  (Bit i of
+             * the product: byte i of z >> 7.) */
+            slow &= ~(((z >> 7) * 0x00204081u) >> 21);
             if (slow) {
 #pragma unroll
                 for (int i = 0; i < 4; i++)
@@ -211,9 +218,7 @@ rtj_scan_chunk_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_des
                         packed = (packed & ~(0xFFu << (8 * i))) | (uint32_t)dl << (8 * i);
                     }
             }
-            {   /* skipped blocks (lib/RTjpeg.c:2704): a byte 0xFF is a block of its own, one byte long */
-                const uint32_t y = ~W0;
-                const uint32_t z = ~(((y & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | y | 0x7F7F7F7Fu);      /* bit 7 of every byte of W0 that is 0xFF */
+            {
                 const uint32_t m = (z >> 7) * 0xFFu;
                 packed = (packed & ~m) | (0x01010101u & m);
             }

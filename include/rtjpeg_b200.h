@@ -207,14 +207,16 @@ int  rtjgpu_last_cuda_error(const rtjgpu_ctx *ctx);
 #define RTJGPU_SCAN_WALK    5     /* one thread per frame, payload staged through shared memory with cp.async (not for raw-prefix frames) */
 int  rtjgpu_set_scan_mode(rtjgpu_ctx *ctx, int mode);
 
-/* How a large device batch is worked through.  AUTO (the default): in slices of frames, the scan of slice s + 1 on
- * a second CUDA stream beside resolve + IDCT of slice s (the stages are bound by different pipes of the SM and fill
- * each other's idle issue slots); the call still orders everything after the work already on cuda_stream and
- * cuda_stream after its own work.  SERIAL: every stage on cuda_stream, one after the other -- per-stage times
- * (rtjgpu_timing) are only separable in this arrangement.  slice_frames: frames per slice, 0 = keep the current
- * value (default 576); rounded up to a multiple of 32. */
+/* How a large device batch is worked through.  SERIAL (what AUTO stands for at present): every stage on cuda_stream, one
+ * after the other; per-stage times (rtjgpu_timing) are separable.  SLICED: in slices of frames, the scan of slice s + 1 on
+ * a second CUDA stream beside resolve + IDCT of slice s; the call still orders everything after the work already on
+ * cuda_stream and cuda_stream after its own work.  (Measured on a B200, DESIGN.md section 4: both stages are bound by
+ * instruction issue, side by side they take each other's slots -- +1 .. 3 % on intra batches, -13 % on skip-heavy ones;
+ * kept for hardware where that differs.)  slice_frames: frames per slice, 0 = keep the current value (default 1184);
+ * rounded up to a multiple of 32.  K3's look-back for last writers never leaves a slice in either arrangement. */
 #define RTJGPU_PIPELINE_AUTO   0
 #define RTJGPU_PIPELINE_SERIAL 1
+#define RTJGPU_PIPELINE_SLICED 2
 int  rtjgpu_set_pipeline(rtjgpu_ctx *ctx, int mode, int slice_frames);
 
 /* Picture format of the batches this context decodes (RTJ_YUV420, the default, RTJ_YUV422 or RTJ_RGB8 =
@@ -334,7 +336,9 @@ int  rtjgpu_get_skip_counts(rtjgpu_ctx *ctx, uint32_t *counts, int F);
 /* Diagnostic: the first n block entries K1 made for the last device batch (frame-major, nblk per frame), 32 bits each --
  * 0xFFFFFFFF a skipped block; bit 31 set: a block of at most three coefficients carried in the entry itself (DC byte,
  * then the coefficients at zig-zag 1 and 2); else byte offset in the frame's payload (25 bits) and end-of-block
- * bound - 1 (6 bits above them).  What RTjpeg_decompress uses to copy back only the blocks a frame coded, and what
+ * bound - 1 (6 bits above them).  After rtjgpu_scan_device these are K1's entries as made; after a decode, K3 has replaced
+ * the marker of every skipped block whose last writer's entry is of the second kind (and was written under the same
+ * tables) by a copy of that entry with bit 30 set.  What RTjpeg_decompress uses to copy back only the blocks a frame coded, and what
  * the parity tests compare with the reference grammar's walk.  Synchronous. */
 int  rtjgpu_get_entries(rtjgpu_ctx *ctx, uint32_t *entries, size_t n);
 

@@ -62,7 +62,7 @@ def test_intra_720x576(kind):
 
 
 @pytest.mark.parametrize("kind", [capi.CONV_RGB32, capi.CONV_BGR24, capi.CONV_RGB16])
-@pytest.mark.parametrize("scan,pipeline,slice_frames", [(capi.SCAN_AUTO, capi.PIPELINE_AUTO, 0), (capi.SCAN_CHUNK, capi.PIPELINE_AUTO, 32),
+@pytest.mark.parametrize("scan,pipeline,slice_frames", [(capi.SCAN_AUTO, capi.PIPELINE_SLICED, 0), (capi.SCAN_CHUNK, capi.PIPELINE_SLICED, 32),
                                                         (capi.SCAN_CHUNK, capi.PIPELINE_SERIAL, 64)])
 def test_inter_with_carry(kind, scan, pipeline, slice_frames):
     """Skipped blocks come from their last writer or from the picture before the batch -- planes, whatever leaves."""

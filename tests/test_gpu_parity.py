@@ -135,11 +135,22 @@ def test_carry_across_batches(ctx):
     assert np.array_equal(np.concatenate([first, second]), want)
 
 
+def _scan_only(ctx, s, o, w, h):
+    """K1 alone (rtjgpu_scan_device): the entries as the scan makes them, before K3 touches the skipped ones."""
+    desc, _ = g.plan(s, o)
+    b = D.upload(s, desc, w, h)
+    ctx.set_format(0)
+    ctx.scan_device(b.stream.data_ptr(), b.desc.data_ptr(), b.F, w, h, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert ctx.batch_info().bad_frames == 0
+    return b
+
+
 def test_scan_entries_match_oracle_walker(ctx):
     s, o = clip(208, 112, 200, 6, key_rate=2, lm=3, cm=3, noise_y=25, noise_c=5)
     w, h = 208, 112
     nblk = (w // 16) * (h // 16) * 6
-    gpu_decode(ctx, s, o, w, h)
+    _scan_only(ctx, s, o, w, h)
     L = g.load_library()
     ent = np.zeros(6 * nblk, dtype=np.uint32)
     L.rtjgpu_get_entries.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
@@ -157,7 +168,7 @@ def test_scan_entries_match_oracle_walker(ctx):
         assert not (inline & ~chroma).any()
         assert (eob[inline] <= 3).all()
         if ctx.flavour in ("lane", "warp"):
-            assert not inline.any()                      # the serial kernels never emit inline entries
+            assert not inline.any()                      # these serial kernels never emit inline entries
         gen = coded & ~inline
         assert ((ent[f] & 0x1FFFFFF)[gen] == offs[gen]).all()
         # the kernel's bound may exceed the exact end-of-block, never undercut it
@@ -174,7 +185,7 @@ def test_scan_entries_inline_format(ctx):
     s, o = clip(208, 112, 128, 4, key_rate=1, lm=2, cm=2, noise_y=12, noise_c=3)
     w, h = 208, 112
     nblk = (w // 16) * (h // 16) * 6
-    gpu_decode(ctx, s, o, w, h)
+    _scan_only(ctx, s, o, w, h)
     L = g.load_library()
     ent = np.zeros(4 * nblk, dtype=np.uint32)
     L.rtjgpu_get_entries.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
@@ -204,6 +215,41 @@ def test_scan_entries_inline_format(ctx):
                 assert (e & 0x1FFFFFF) == offs[b] and ((e >> 25) & 63) + 1 >= max(int(eob[b]), 4)
                 seen_general += 1
     assert seen_inline and seen_general
+
+
+def test_k3_gives_skipped_blocks_a_copy_of_an_inline_last_writer(ctx):
+    """After a decode, the marker of a skipped block whose last writer's entry is an inline one (same tables) has been
+    replaced by that entry with bit 30 set; every other skipped block keeps its marker."""
+    if ctx.flavour in ("lane", "warp"):
+        pytest.skip("inline entries come from the other scans")
+    w, h, F = 208, 112, 12
+    s, o = clip(w, h, 128, F, key_rate=5, lm=3, cm=3, noise_y=6)
+    nblk = (w // 16) * (h // 16) * 6
+    L = g.load_library()
+    L.rtjgpu_get_entries.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    _scan_only(ctx, s, o, w, h)
+    k1 = np.zeros(F * nblk, dtype=np.uint32)
+    assert L.rtjgpu_get_entries(ctx._h, C.c_void_p(k1.ctypes.data), k1.size) == 0
+    k1 = k1.reshape(F, nblk)
+    gpu_decode(ctx, s, o, w, h)
+    k3 = np.zeros(F * nblk, dtype=np.uint32)
+    assert L.rtjgpu_get_entries(ctx._h, C.c_void_p(k3.ctypes.data), k3.size) == 0
+    k3 = k3.reshape(F, nblk)
+    copies = 0
+    last = np.full(nblk, -1)
+    for f in range(F):
+        skip = k1[f] == 0xFFFFFFFF
+        assert np.array_equal(k3[f][~skip], k1[f][~skip])                  # coded blocks are left alone
+        for b in np.flatnonzero(skip):
+            lw = last[b]
+            inl = lw >= 0 and (k1[lw, b] >> 31) == 1
+            if inl:
+                assert k3[f, b] == (k1[lw, b] | 0x40000000), (f, b)
+                copies += 1
+            else:
+                assert k3[f, b] == 0xFFFFFFFF, (f, b)
+        last[~skip] = f
+    assert copies > 100
 
 
 def test_edge_geometries(ctx):

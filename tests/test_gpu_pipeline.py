@@ -26,7 +26,7 @@ def _ctx(pipeline, slice_frames, scan=capi.SCAN_CHUNK):
     return c
 
 
-ARRANGEMENTS = [(capi.PIPELINE_AUTO, 32), (capi.PIPELINE_AUTO, 64), (capi.PIPELINE_AUTO, 96), (capi.PIPELINE_SERIAL, 32),
+ARRANGEMENTS = [(capi.PIPELINE_SLICED, 32), (capi.PIPELINE_SLICED, 64), (capi.PIPELINE_SLICED, 96), (capi.PIPELINE_SERIAL, 32),
                 (capi.PIPELINE_SERIAL, 576)]
 
 
@@ -85,7 +85,7 @@ def test_last_writer_many_chunks_back(pipeline, slice_frames):
         assert np.array_equal(got, want), first_diff(got, want, w, h)
 
 
-@pytest.mark.parametrize("pipeline,slice_frames", [(capi.PIPELINE_AUTO, 32), (capi.PIPELINE_SERIAL, 64)])
+@pytest.mark.parametrize("pipeline,slice_frames", [(capi.PIPELINE_SLICED, 32), (capi.PIPELINE_SERIAL, 64)])
 def test_never_written_positions_take_the_carry(pipeline, slice_frames):
     """No frame of the batch writes the left half of the picture: those blocks come from the picture before the
     batch in every slice."""
@@ -113,7 +113,7 @@ def test_pipelined_equals_serial_on_the_bench_shape():
     s, o = clip(w, h, 128, F)
     with _ctx(capi.PIPELINE_SERIAL, 0, scan=capi.SCAN_AUTO) as c:
         serial, _ = gpu_decode(c, s, o, w, h)
-    with _ctx(capi.PIPELINE_AUTO, 0, scan=capi.SCAN_AUTO) as c:
+    with _ctx(capi.PIPELINE_SLICED, 0, scan=capi.SCAN_AUTO) as c:
         piped, _ = gpu_decode(c, s, o, w, h)
         assert c.batch_info().bad_frames == 0
     assert np.array_equal(serial, piped)

@@ -35,6 +35,8 @@ struct Workspace {
     uint32_t     *d_seg_base = nullptr;
     int32_t      *d_seg_nbf = nullptr;   int    seg_frames_cap = 0;
     uint8_t      *d_seg_del = nullptr;   size_t seg_del_cap = 0;     /* segments */
+    uint32_t     *d_seg_gsum = nullptr;  size_t seg_gsum_cap = 0;    /* groups */
+    uint32_t     *d_seg_gentry = nullptr, *d_seg_gbase = nullptr;
     size_t        cap_entries = 0;
     int           cap_frames = 0;
     /* K2's position table, rebuilt when the geometry changes */
@@ -139,7 +141,7 @@ int ws_reserve(rtjgpu_ctx *ctx, Workspace *ws, int F, int nblk)
         ws->d_ent = nullptr; ws->d_src = nullptr; ws->d_hardq = nullptr; ws->d_chunk_last = nullptr; ws->cap_entries = 0;
         CK(ctx, cudaMalloc(&ws->d_ent, need * sizeof(uint32_t)));
         CK(ctx, cudaMalloc(&ws->d_src, need * sizeof(uint16_t)));
-        CK(ctx, cudaMalloc(&ws->d_hardq, need * sizeof(uint32_t)));
+        CK(ctx, cudaMalloc(&ws->d_hardq, need * 2 * sizeof(uint32_t)));       /* two words an entry: destination and source block */
         CK(ctx, cudaMalloc(&ws->d_chunk_last, ((size_t)F / RTJ_RESOLVE_T + 1) * (size_t)nblk * sizeof(uint16_t)));
         ws->cap_entries = need;
     }
@@ -209,6 +211,20 @@ int seg_reserve(rtjgpu_ctx *ctx, Workspace *ws, int F, int nblk, int scan_mode, 
         }
         sp->del = ws->seg_del_cap >= nseg ? ws->d_seg_del : nullptr;
     }
+    if (maxseg >= RTJ_SEG_GROUP_MIN_SEGS) {
+        const size_t ngroups = (maxseg + RTJ_SEG_GROUP - 1) / RTJ_SEG_GROUP, ng = (size_t)F * ngroups;
+        if (ng > ws->seg_gsum_cap) {
+            if (ws->d_seg_gsum) cudaFree(ws->d_seg_gsum);
+            if (ws->d_seg_gentry) cudaFree(ws->d_seg_gentry);
+            if (ws->d_seg_gbase) cudaFree(ws->d_seg_gbase);
+            ws->d_seg_gsum = ws->d_seg_gentry = ws->d_seg_gbase = nullptr; ws->seg_gsum_cap = 0;
+            CK(ctx, cudaMalloc(&ws->d_seg_gsum, ng * RTJ_SEG_NE * sizeof(uint32_t)));
+            CK(ctx, cudaMalloc(&ws->d_seg_gentry, ng * sizeof(uint32_t)));
+            CK(ctx, cudaMalloc(&ws->d_seg_gbase, ng * sizeof(uint32_t)));
+            ws->seg_gsum_cap = ng;
+        }
+        sp->gsum = ws->d_seg_gsum; sp->gentry = ws->d_seg_gentry; sp->gbase = ws->d_seg_gbase; sp->ngroups = (int)ngroups;
+    }
     sp->sum = ws->d_seg_sum; sp->entry = ws->d_seg_entry; sp->base = ws->d_seg_base; sp->nbf = ws->d_seg_nbf;
     sp->maxseg = (int)maxseg;
     return RTJGPU_OK;
@@ -229,6 +245,9 @@ void ws_release(Workspace *ws)
     if (ws->d_seg_base) cudaFree(ws->d_seg_base);
     if (ws->d_seg_nbf) cudaFree(ws->d_seg_nbf);
     if (ws->d_seg_del) cudaFree(ws->d_seg_del);
+    if (ws->d_seg_gsum) cudaFree(ws->d_seg_gsum);
+    if (ws->d_seg_gentry) cudaFree(ws->d_seg_gentry);
+    if (ws->d_seg_gbase) cudaFree(ws->d_seg_gbase);
     if (ws->d_lut) cudaFree(ws->d_lut);
     *ws = Workspace();
 }
@@ -367,7 +386,7 @@ int run_kernels(rtjgpu_ctx *ctx, Workspace *ws, const uint8_t *d_stream, const r
         a.f0 = 0; a.f1 = F;
         if (ev) CK(ctx, cudaEventRecord(ev[2], st));
         LAUNCHED(rtj_launch_idct(&a, st), 1);
-        if (!rgb) LAUNCHED(rtj_launch_idct_hard(&a, st), 1);
+        if (!rgb) LAUNCHED(rtj_launch_idct_hard(&a, st), 2);
         if (ev) CK(ctx, cudaEventRecord(ev[3], st));
         return RTJGPU_OK;
     }
@@ -393,7 +412,7 @@ int run_kernels(rtjgpu_ctx *ctx, Workspace *ws, const uint8_t *d_stream, const r
         CK(ctx, cudaEventRecord(ev[2], p.scan));
     }
     a.f0 = 0; a.f1 = F;
-    if (!rgb) LAUNCHED(rtj_launch_idct_hard(&a, p.idct), 1);
+    if (!rgb) LAUNCHED(rtj_launch_idct_hard(&a, p.idct), 2);
     CK(ctx, cudaEventRecord(p.join, p.idct));
     CK(ctx, cudaStreamWaitEvent(st, p.join, 0));
     if (ev) CK(ctx, cudaEventRecord(ev[3], st));

@@ -109,7 +109,14 @@ typedef struct rtj_seg_plan {
     int32_t  *nbf;      /* [F]  blocks the frame's stream holds, capped at nblk */
     uint8_t  *del;      /* [F][maxseg][RTJ_SEG_DEL_BYTES]  level 0 of the first pass, kept for the second; NULL: worked out again */
     int       maxseg;
+    /* frames of many segments: the chain hops groups of RTJ_SEG_GROUP segments (gsum == NULL: it hops segments) */
+    uint32_t *gsum;     /* [F][ngroups][RTJ_SEG_NE]  exit offset | units << 9 of a group */
+    uint32_t *gentry;   /* [F][ngroups]  entry offset of the group's first segment */
+    uint32_t *gbase;    /* [F][ngroups]  first block index; RTJ_SEG_UNUSED = behind the payload */
+    int       ngroups;
 } rtj_seg_plan;
+#define RTJ_SEG_GROUP 16
+#define RTJ_SEG_GROUP_MIN_SEGS 64      /* frames of fewer segments are chained segment by segment */
 
 /* ---- kernel launchers (rtj_kernels.cu); stream is a cudaStream_t ----------- */
 typedef struct rtj_launch_args {
@@ -126,7 +133,7 @@ typedef struct rtj_launch_args {
     uint16_t                *d_src;         /* [F][nblk] */
     uint32_t                *d_frame_skips; /* [F] */
     rtj_dev_info            *d_info;
-    uint32_t                *d_hardq;       /* [F * nblk] global block indices queued for K2b */
+    uint32_t                *d_hardq;       /* [F * nblk][2] K2 -> K2b queue: destination block, source block (frame * nblk + block) */
     uint16_t                *d_chunk_last;  /* [ceil(F / 32)][nblk] K3: last writer inside each chunk of frames */
     const uint16_t          *d_k3_in;       /* [nblk] K3: last writer before this slice (NULL: the first slice) */
     uint16_t                *d_k3_out;      /* [nblk] K3: last writer before the next slice */

@@ -681,7 +681,7 @@ rtj_idct_kernel(const K2Params P)
             /* HARD blocks split once more for the general kernel: long ones (E > 16) apart from the rest */
             const bool full = cls == Q_HARD && !RTJ_ENT_IS_INLINE(e) && RTJ_ENT_EOB(e) > 16;
             wq_e[at] = (uint32_t)pp.i | (cls == Q_CARRY ? 0x80000000u : 0u) | (full ? 0x40000000u : 0u);
-            wq_p[at] = (uint32_t)pp.off;
+            wq_p[at] = (uint32_t)pp.off | (sf << 16);
         }
         nfront += __popc(mM);
         nback += __popc(mB);
@@ -743,7 +743,8 @@ rtj_idct_kernel(const K2Params P)
             const bool live = idx < nback;
             uint32_t ie = 0x80000000u;
             int off = 0;
-            if (live) { ie = wq_e[wq - 1 - idx]; off = (int)wq_p[wq - 1 - idx]; }
+            unsigned hsf = f;                                    /* the frame whose stream holds a HARD block: its last writer */
+            if (live) { ie = wq_e[wq - 1 - idx]; const uint32_t ps = wq_p[wq - 1 - idx]; off = (int)(ps & 0xFFFFu); hsf = ps >> 16; }
             const bool hard = live && !(ie >> 31);
             const bool full = hard && ((ie >> 30) & 1u);
             const int bi = (int)(ie & 0x3FFFFFFFu);              /* stream-order index inside the strip */
@@ -767,8 +768,11 @@ rtj_idct_kernel(const K2Params P)
                 base = __shfl_sync(FULL, base, 0);
                 baseF = __shfl_sync(FULL, baseF, 0);
                 const unsigned below = (1u << lane) - 1u;
-                if (hard && !full) P.hardq[base + __popc(mH & below)] = frame_blk0 + (unsigned)bi;
-                if (full) P.hardq[P.hardq_cap - 1u - (baseF + __popc(mF & below))] = frame_blk0 + (unsigned)bi;
+                /* a queue entry: the block's place in its frame (and whether it is a chroma block), the frame the pixels
+                 * go to and the frame whose stream holds the block (its last writer) */
+                const uint2 rec = make_uint2((strip_blk0 + (unsigned)bi) | (off_is_chroma<FMT>(off, mbs) ? 0x80000000u : 0u), f | (hsf << 16));
+                if (hard && !full) reinterpret_cast<uint2 *>(P.hardq)[base + __popc(mH & below)] = rec;
+                if (full) reinterpret_cast<uint2 *>(P.hardq)[P.hardq_cap - 1u - (baseF + __popc(mF & below))] = rec;
                 nhard += __popc(mH) + __popc(mF);
             }
             if (live && !hard) {
@@ -882,34 +886,174 @@ __global__ void rtj_build_lut_kernel(uint32_t *__restrict__ pos, int mbs, int np
 /* K2b: the general decoder for queued blocks                                  */
 /* ------------------------------------------------------------------------ */
 
-/* One thread per queued block.  The queue holds mid-size blocks (E <= 16, or carried inline but last
- * written under other tables) at its front and long blocks at its back, so that a warp runs one flow
- * graph: the first 16 zig-zag positions touch rows 0..5 and columns 0..4 only and fit 24 bytes held in
- * registers; long blocks take the reference's full two passes, fed byte by byte. */
+/*
+ * The queue holds blocks of at most 16 coefficients (and blocks carried inline whose last writer used other tables) at its
+ * front, longer blocks at its back; an entry names the block's place in its frame, the frame its pixels go to and the
+ * frame whose stream holds it.
+ *
+ * rtj_idct_hard16_kernel: the front.  One thread per block: the first 16 zig-zag positions touch rows 0..5 and columns 0..4
+ * only and fit 24 bytes held in registers.
+ */
 extern "C" __global__ void __launch_bounds__(128)
-rtj_idct_hard_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc *__restrict__ desc,
-                     const rtj_dev_table *__restrict__ tables, const uint32_t *__restrict__ ent,
-                     const uint16_t *__restrict__ srcf, int nblk, int w, int h, int fmt,
-                     uint8_t *__restrict__ out, const uint32_t *__restrict__ hardq, unsigned hardq_cap,
-                     const rtj_dev_info *__restrict__ info)
+rtj_idct_hard16_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc *__restrict__ desc,
+                       const rtj_dev_table *__restrict__ tables, const uint32_t *__restrict__ ent,
+                       int nblk, int w, int h, int fmt, uint8_t *__restrict__ out, const uint32_t *__restrict__ hardq,
+                       const rtj_dev_info *__restrict__ info)
 {
-    const unsigned n16 = info->hard_blocks, nfull = info->hard_full;
+    const unsigned n16 = info->hard_blocks;
     const size_t fsz = RTJ_FMT_FRAME_BYTES(fmt, w, h);
-    const int unit = RTJ_FMT_UNIT_BLOCKS(fmt), unit_luma = RTJ_FMT_UNIT_LUMA(fmt);
-    const unsigned stride = gridDim.x * blockDim.x, first = blockIdx.x * blockDim.x + threadIdx.x;
-    for (unsigned k = first; k < n16 + nfull; k += stride) {
-        const bool full = k >= n16;
-        const uint32_t gidx = full ? hardq[hardq_cap - 1u - (k - n16)] : hardq[k];
-        const unsigned f = gidx / (unsigned)nblk;
-        const int i = (int)(gidx - f * (unsigned)nblk);
-        const int chroma = (i % unit) >= unit_luma;
+    const unsigned stride = gridDim.x * blockDim.x;
+    for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < n16; k += stride) {
+        const uint2 rec = reinterpret_cast<const uint2 *>(hardq)[k];
+        const int i = (int)(rec.x & 0x7FFFFFFFu), chroma = (int)(rec.x >> 31);
+        const unsigned f = rec.y & 0xFFFFu, sf = rec.y >> 16;
+        const uint32_t e = ent[(size_t)sf * nblk + i];
+        const rtjgpu_frame_desc sd = desc[sf];
+        const rtj_dev_table *t = &tables[min((int)sd.table, RTJ_NUM_TABLES - 1)];
         uint32_t px[16];
-        decode_general(stream, desc, tables, ent, srcf, nblk, gidx, chroma, full, px);
+        if (RTJ_ENT_IS_INLINE(e)) {
+            const int x0 = wrap16((int)(e & 0xFFu) * t->iq[chroma][0]) + 4;
+            const int x1 = wrap16((int)(signed char)((e >> 8) & 0xFFu) * t->iq[chroma][1]);
+            const int q = wrap16((int)(signed char)((e >> 16) & 0xFFu) * t->iq[chroma][2]);
+            t2_pixels(x0, x1, q, false, px);
+        } else {
+            RegBytes<6> by(stream + sd.offset + RTJPEG_B200_HEADER_BYTES + (e & RTJ_ENT_OFF_MASK));
+            int x[16];
+            unpack_block<16>(by, t->iq[chroma], t->bt8[chroma], x);
+            idct_general<16>(x, px);
+        }
         int pitch;
         uint8_t *dst = block_dst(out + (size_t)f * fsz, fmt, i, w, h, pitch);
 #pragma unroll
         for (int r = 0; r < 8; r++)
             *reinterpret_cast<uint2 *>(dst + (size_t)r * pitch) = make_uint2(px[2 * r], px[2 * r + 1]);
+    }
+}
+
+/*
+ * rtj_idct_hard_kernel: the back -- long blocks.  EIGHT LANES per block, four blocks per warp.  (One thread per block, 110
+ * registers, the block's bytes fetched one by one in a dependent chain, kept 16 warps per SM waiting for memory: 43 % of
+ * the issue slots used on a dense 1920x1088 stream.)  The block's up to 64 bytes arrive as one coalesced read, eight bytes
+ * a lane.  Every byte's place in the zig-zag order is a prefix sum of what the bytes before it fill (lib/RTjpeg.c:162-183:
+ * DC and the raw prefix one place each, a run token b - 63, any other token one), made within the lane and scanned over
+ * the eight lanes; the dequantised coefficients are scattered into an 8x8 matrix in shared memory.  First pass
+ * (:2221-2285): one COLUMN per lane; second pass (:2287-2330): one ROW per lane, after a transposition through shared
+ * memory; every lane stores its row's eight pixels.
+ */
+__constant__ uint8_t c_zz_raster[64] = {
+#define RTJ_RASTER(k, r, c) (r) * 8 + (c),
+    RTJ_ZZ_LIST(RTJ_RASTER)
+#undef RTJ_RASTER
+};
+
+constexpr int HB_THREADS = 128;
+
+extern "C" __global__ void __launch_bounds__(HB_THREADS)
+rtj_idct_hard_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc *__restrict__ desc,
+                     const rtj_dev_table *__restrict__ tables, const uint32_t *__restrict__ ent,
+                     int nblk, int w, int h, int fmt,
+                     uint8_t *__restrict__ out, const uint32_t *__restrict__ hardq, unsigned hardq_cap,
+                     const rtj_dev_info *__restrict__ info)
+{
+    __shared__ __align__(16) int16_t s_m[HB_THREADS / 8][72];        /* coefficients, raster order; 36 words a block: the four blocks of a warp on different banks */
+    __shared__ int32_t s_w[HB_THREADS / 8][8][9];                     /* first-pass results, rows padded to nine words */
+    __shared__ uint8_t s_zz[64];                                      /* zig-zag place -> raster place (indexed per lane: not for the constant cache) */
+    if (threadIdx.x < 64) s_zz[threadIdx.x] = c_zz_raster[threadIdx.x];
+    __syncthreads();
+    const unsigned total = info->hard_full;
+    const size_t fsz = RTJ_FMT_FRAME_BYTES(fmt, w, h);
+    const int lane = threadIdx.x & 31, l = lane & 7, grp = threadIdx.x >> 3;
+    int16_t *M = s_m[grp];
+    const int16_t *Mc = M + l;                                        /* this lane's column */
+    int32_t *Wc = &s_w[grp][0][l];                                    /* ... of the first pass's results: row r at Wc[9 r] */
+    const int32_t *Wr = &s_w[grp][l][0];                              /* this lane's row */
+    const unsigned stride = gridDim.x * (HB_THREADS / 8);
+    for (unsigned kb = (blockIdx.x * (HB_THREADS / 32) + (threadIdx.x >> 5)) * 4; kb < total; kb += stride) {       /* warp-uniform */
+        const unsigned k = kb + (unsigned)(lane >> 3);
+        const bool live = k < total;
+        const uint2 rec = !live ? make_uint2(0u, 0u) : reinterpret_cast<const uint2 *>(hardq)[hardq_cap - 1u - k];
+        const int i = (int)(rec.x & 0x7FFFFFFFu), chroma = (int)(rec.x >> 31);
+        const unsigned f = rec.y & 0xFFFFu, sf = rec.y >> 16;
+        const uint32_t e = live ? ent[(size_t)sf * nblk + i] : 0u;
+        const rtjgpu_frame_desc sd = desc[sf];
+        const rtj_dev_table *t = &tables[min((int)sd.table, RTJ_NUM_TABLES - 1)];
+        const int32_t *iq = t->iq[chroma];
+        const int bt8 = t->bt8[chroma];
+
+        /* the block's bytes 8l .. 8l + 7 */
+        uint32_t b0, b1;
+        {
+            const uint8_t *src = stream + sd.offset + RTJPEG_B200_HEADER_BYTES + (e & RTJ_ENT_OFF_MASK);
+            const uintptr_t a = reinterpret_cast<uintptr_t>(src);
+            const uint32_t *wp = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3) + 2 * l;
+            const unsigned sh = (unsigned)(a & 3) * 8;
+            const uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2);     /* slack bytes follow the stream */
+            b0 = __funnelshift_r(w0, w1, sh);
+            b1 = __funnelshift_r(w1, w2, sh);
+        }
+        /* what every byte fills: DC and the raw prefix (bytes 0 .. bt8) one place each, a run token b - 63, else one */
+        uint32_t x0, x1;
+        {
+            const uint32_t r0 = b0 & ~(b0 >> 1) & 0x40404040u, r1 = b1 & ~(b1 >> 1) & 0x40404040u;
+            x0 = (b0 & ((r0 >> 6) * 0x3Fu)) + 0x01010101u;
+            x1 = (b1 & ((r1 >> 6) * 0x3Fu)) + 0x01010101u;
+            const int nraw = min(max(bt8 + 1 - 8 * l, 0), 8);
+            const uint32_t m0 = nraw >= 4 ? 0xFFFFFFFFu : (1u << (8 * nraw)) - 1u;
+            const uint32_t m1 = nraw >= 8 ? 0xFFFFFFFFu : nraw <= 4 ? 0u : (1u << (8 * (nraw - 4))) - 1u;
+            x0 = (x0 & ~m0) | (0x01010101u & m0);
+            x1 = (x1 & ~m1) | (0x01010101u & m1);
+        }
+        /* zig-zag place of each of the lane's bytes: places filled before it -- within the lane, then over the eight lanes */
+        int pos[8];
+        {
+            int acc = 0;
+#pragma unroll
+            for (int m = 0; m < 8; m++) { pos[m] = acc; acc += (int)(((m < 4 ? x0 : x1) >> (8 * (m & 3))) & 0xFFu); }
+            int incl = acc;
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) {
+                const int up = __shfl_up_sync(FULL, incl, o, 8);
+                if (l >= o) incl += up;
+            }
+            const int before = incl - acc;
+#pragma unroll
+            for (int m = 0; m < 8; m++) pos[m] += before;
+        }
+        *reinterpret_cast<uint4 *>(M + 8 * l) = make_uint4(0u, 0u, 0u, 0u);
+        __syncwarp();
+        if (pos[0] < 64) {
+#pragma unroll
+            for (int m = 0; m < 8; m++) {
+                const uint32_t bv = ((m < 4 ? b0 : b1) >> (8 * (m & 3))) & 0xFFu;
+                const bool lit = 8 * l + m <= bt8 || (bv - 64u) >= 64u;           /* not a run token */
+                if (lit && pos[m] < 64) {
+                    const int c = (l | m) == 0 ? (int)bv : (int)(signed char)bv;  /* the DC byte is unsigned (lib/RTjpeg.c:164) */
+                    M[s_zz[pos[m]]] = (int16_t)(c * __ldg(iq + pos[m]));
+                }
+            }
+        }
+        __syncwarp();
+        /* first pass: column l */
+        {
+            int y[8];
+            aan8((int)Mc[0] + (l == 0 ? 4 : 0),                         /* DESCALE's rounding term rides on the DC path */
+                 Mc[8], Mc[16], Mc[24], Mc[32], Mc[40], Mc[48], Mc[56], y);
+#pragma unroll
+            for (int r = 0; r < 8; r++) Wc[9 * r] = y[r];
+        }
+        __syncwarp();
+        /* second pass: row l, descale, clamp */
+        {
+            int y[8];
+            aan8(Wr[0], Wr[1], Wr[2], Wr[3], Wr[4], Wr[5], Wr[6], Wr[7], y);
+            if (live) {
+                int pitch;
+                uint8_t *dst = block_dst(out + (size_t)f * fsz, fmt, i, w, h, pitch);
+                *reinterpret_cast<uint2 *>(dst + (size_t)l * pitch) =
+                    make_uint2(descale_pack4(y[0], y[1], y[2], y[3]), descale_pack4(y[4], y[5], y[6], y[7]));
+            }
+        }
+        __syncwarp();
     }
 }
 
@@ -1062,8 +1206,10 @@ extern "C" int rtj_launch_idct_hard(const rtj_launch_args *a, void *stream)
     /* the queue's length is only known on the device: a fixed grid strides over it */
     const int sms = g_sm_count > 0 ? g_sm_count : 148;
     const int nblk = RTJ_FMT_NBLK(a->fmt, a->w, a->h);
-    rtj_idct_hard_kernel<<<sms * 4, 128, 0, (cudaStream_t)stream>>>(
-        a->d_stream, a->d_desc, a->d_tables, a->d_ent, a->d_src, nblk, a->w, a->h, a->fmt, a->d_out, a->d_hardq,
+    rtj_idct_hard16_kernel<<<sms * 8, 128, 0, (cudaStream_t)stream>>>(
+        a->d_stream, a->d_desc, a->d_tables, a->d_ent, nblk, a->w, a->h, a->fmt, a->d_out, a->d_hardq, a->d_info);
+    rtj_idct_hard_kernel<<<sms * 16, HB_THREADS, 0, (cudaStream_t)stream>>>(
+        a->d_stream, a->d_desc, a->d_tables, a->d_ent, nblk, a->w, a->h, a->fmt, a->d_out, a->d_hardq,
         (unsigned)((size_t)a->F * (size_t)nblk), a->d_info);
     return (int)cudaGetLastError();
 }

@@ -427,6 +427,56 @@ rtj_resolve_kernel(uint32_t *__restrict__ ent, const uint16_t *__restrict__ chun
 /* K1, segment-parallel flavour: the frame-level chain between the two passes */
 /* ------------------------------------------------------------------------ */
 
+/* what the frame-level chain needs to know about a frame */
+struct PlanFrame { int len, unit, segbytes, nseg; };
+
+__device__ __forceinline__ PlanFrame plan_frame(const rtjgpu_frame_desc *__restrict__ desc, const rtj_dev_table *__restrict__ tables,
+                                                int f, int maxseg, int unit_blocks)
+{
+    const rtjgpu_frame_desc d = desc[f];
+    PlanFrame p;
+    p.len = d.length > RTJPEG_B200_HEADER_BYTES ? (int)d.length - RTJPEG_B200_HEADER_BYTES : 0;
+    /* with a raw prefix the summaries count macroblocks (rtj_scan_mb.cu), without it blocks */
+    const rtj_dev_table &tab = tables[min((int)d.table, RTJ_NUM_TABLES - 1)];
+    const bool raw = (tab.bt8[0] | tab.bt8[1]) != 0;
+    p.unit = raw ? unit_blocks : 1;
+    p.segbytes = raw ? RTJ_SEG_BYTES_MB : RTJ_SEG_BYTES;
+    p.nseg = (int)min((long long)maxseg, ((long long)p.len + p.segbytes - 1) / p.segbytes);   /* segments that hold payload */
+    return p;
+}
+
+/* The frame's closing: blocks it holds, the missing ones' harmless entries, the flag of a frame without any block (every
+ * other frame is closed by the segment that holds its last block). */
+__device__ __forceinline__ void plan_close(int f, int nb, int nblk, int len, uint32_t *__restrict__ ent, uint32_t *__restrict__ frame_skips,
+                                           rtj_dev_info *__restrict__ info, const rtj_seg_plan &sp)
+{
+    const int nbf = min(nb, nblk);
+    sp.nbf[f] = nbf;
+    frame_skips[f] = 0;
+    for (int b = nbf; b < nblk; b++) ent[(size_t)f * nblk + b] = RTJ_ENT(min(len, (int)RTJ_ENT_OFF_MASK), 1);
+    if (nbf == 0 && nblk > 0) {
+        atomicAdd(&info->bad_frames, 1u);
+        atomicMin((unsigned int *)&info->first_bad_frame, (unsigned int)f);
+    }
+}
+
+/* segments [s0, s1) of frame f from (entry e, nb blocks before): their entry offsets and first block indices; segments behind
+ * the payload or behind the frame's last block are marked unused.  Returns the blocks before segment s1. */
+__device__ __forceinline__ int plan_walk(const PlanFrame &p, int f, int s0, int s1, int e, int nb, int nblk, const rtj_seg_plan &sp)
+{
+    for (int seg = s0; seg < s1; seg++) {
+        const size_t idx = (size_t)f * sp.maxseg + seg;
+        if (seg >= p.nseg || nb >= nblk) { sp.base[idx] = RTJ_SEG_UNUSED; continue; }
+        sp.entry[idx] = (uint32_t)e;
+        sp.base[idx] = (uint32_t)nb;
+        const uint32_t v = sp.sum[idx * RTJ_SEG_NE + e];
+        e = min((int)(v & 511u), RTJ_SEG_NE - 1);
+        nb += p.unit * (int)(v >> 9);
+    }
+    return nb;
+}
+
+/* One thread per frame: the whole chain.  For frames of a few dozen segments. */
 extern "C" __global__ void __launch_bounds__(64)
 rtj_scan_plan_kernel(const rtjgpu_frame_desc *__restrict__ desc, const rtj_dev_table *__restrict__ tables, int F, int nblk,
                      uint32_t *__restrict__ ent, uint32_t *__restrict__ frame_skips, rtj_dev_info *__restrict__ info,
@@ -434,33 +484,79 @@ rtj_scan_plan_kernel(const rtjgpu_frame_desc *__restrict__ desc, const rtj_dev_t
 {
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= F) return;
-    const rtjgpu_frame_desc d = desc[f];
-    const int len = d.length > RTJPEG_B200_HEADER_BYTES ? (int)d.length - RTJPEG_B200_HEADER_BYTES : 0;
-    /* with a raw prefix the summaries count macroblocks (rtj_scan_mb.cu), without it blocks */
-    const rtj_dev_table &tab = tables[min((int)d.table, RTJ_NUM_TABLES - 1)];
-    const bool raw = (tab.bt8[0] | tab.bt8[1]) != 0;
-    const int unit = raw ? unit_blocks : 1;
-    const int segbytes = raw ? RTJ_SEG_BYTES_MB : RTJ_SEG_BYTES;
-    int e = 0, nb = 0, seg = 0;
-    for (; seg < sp.maxseg && (long long)seg * segbytes < len && nb < nblk; seg++) {
-        const size_t idx = (size_t)f * sp.maxseg + seg;
-        sp.entry[idx] = (uint32_t)e;
-        sp.base[idx] = (uint32_t)nb;
-        const uint32_t v = sp.sum[idx * RTJ_SEG_NE + e];
+    const PlanFrame p = plan_frame(desc, tables, f, sp.maxseg, unit_blocks);
+    const int nb = plan_walk(p, f, 0, sp.maxseg, 0, 0, nblk, sp);
+    plan_close(f, nb, nblk, p.len, ent, frame_skips, info, sp);
+}
+
+/*
+ * Frames of hundreds of segments (a dense 1920x1088 frame: 500): the chain above is as many dependent loads from a table
+ * that does not fit the L2 -- 0.39 ms for a batch of 128 such frames, a tenth of the whole scan.  In three steps instead:
+ *   groups   every group of RTJ_SEG_GROUP segments is summarised like a segment is: for every entry offset, where the parse
+ *            leaves the group and how many units it starts (one thread per entry offset, 16 dependent loads, all groups
+ *            of all frames at once)
+ *   chain    one thread per frame hops group to group
+ *   fill     one thread per group walks its segments from the group's now known entry
+ */
+extern "C" __global__ void __launch_bounds__(RTJ_SEG_NE)
+rtj_scan_plan_group_kernel(const rtjgpu_frame_desc *__restrict__ desc, const rtj_dev_table *__restrict__ tables, const rtj_seg_plan sp,
+                           int unit_blocks)
+{
+    const int f = blockIdx.y, g = blockIdx.x, e0 = threadIdx.x;
+    const PlanFrame p = plan_frame(desc, tables, f, sp.maxseg, unit_blocks);
+    const int s0 = g * RTJ_SEG_GROUP, s1 = min(s0 + RTJ_SEG_GROUP, sp.maxseg);
+    if (s1 > p.nseg) return;                         /* a group that is not all payload is walked, not summarised */
+    int e = e0, units = 0;
+    for (int seg = s0; seg < s1; seg++) {
+        const uint32_t v = sp.sum[((size_t)f * sp.maxseg + seg) * RTJ_SEG_NE + e];
+        e = min((int)(v & 511u), RTJ_SEG_NE - 1);
+        units += (int)(v >> 9);
+    }
+    sp.gsum[((size_t)f * sp.ngroups + g) * RTJ_SEG_NE + e0] = (uint32_t)e | ((uint32_t)units << 9);
+}
+
+extern "C" __global__ void __launch_bounds__(64)
+rtj_scan_plan_chain_kernel(const rtjgpu_frame_desc *__restrict__ desc, const rtj_dev_table *__restrict__ tables, int F,
+                           const rtj_seg_plan sp, int unit_blocks)
+{
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= F) return;
+    const PlanFrame p = plan_frame(desc, tables, f, sp.maxseg, unit_blocks);
+    int e = 0, nb = 0;
+    for (int g = 0; g < sp.ngroups; g++) {
+        const size_t idx = (size_t)f * sp.ngroups + g;
+        sp.gentry[idx] = (uint32_t)e;
+        sp.gbase[idx] = (uint32_t)nb;
+        if (min((g + 1) * RTJ_SEG_GROUP, sp.maxseg) > p.nseg) {          /* the payload ends in this group: nothing behind it matters */
+            for (int g2 = g + 1; g2 < sp.ngroups; g2++) sp.gbase[(size_t)f * sp.ngroups + g2] = RTJ_SEG_UNUSED;
+            break;
+        }
+        const uint32_t v = sp.gsum[idx * RTJ_SEG_NE + e];
         e = (int)(v & 511u);
-        nb += unit * (int)(v >> 9);
+        nb += p.unit * (int)(v >> 9);
     }
-    for (int s2 = seg; s2 < sp.maxseg; s2++) sp.base[(size_t)f * sp.maxseg + s2] = RTJ_SEG_UNUSED;
-    const int nbf = min(nb, nblk);
-    sp.nbf[f] = nbf;
-    frame_skips[f] = 0;
-    /* a frame whose stream ends early: give the missing blocks a harmless entry; a frame without any
-     * block is closed here, every other frame by the segment that holds its last block */
-    for (int b = nbf; b < nblk; b++) ent[(size_t)f * nblk + b] = RTJ_ENT(min(len, (int)RTJ_ENT_OFF_MASK), 1);
-    if (nbf == 0 && nblk > 0) {
-        atomicAdd(&info->bad_frames, 1u);
-        atomicMin((unsigned int *)&info->first_bad_frame, (unsigned int)f);
-    }
+}
+
+extern "C" __global__ void __launch_bounds__(64)
+rtj_scan_plan_fill_kernel(const rtjgpu_frame_desc *__restrict__ desc, const rtj_dev_table *__restrict__ tables, int F, int nblk,
+                          uint32_t *__restrict__ ent, uint32_t *__restrict__ frame_skips, rtj_dev_info *__restrict__ info,
+                          const rtj_seg_plan sp, int unit_blocks)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= F * sp.ngroups) return;
+    const int f = t / sp.ngroups, g = t - f * sp.ngroups;
+    const PlanFrame p = plan_frame(desc, tables, f, sp.maxseg, unit_blocks);
+    const int s0 = g * RTJ_SEG_GROUP, s1 = min(s0 + RTJ_SEG_GROUP, sp.maxseg);
+    const uint32_t gb = sp.gbase[(size_t)f * sp.ngroups + g];
+    int nb;
+    if (gb == RTJ_SEG_UNUSED) {
+        nb = nblk;                                                     /* behind the payload: every segment unused */
+        for (int seg = s0; seg < s1; seg++) sp.base[(size_t)f * sp.maxseg + seg] = RTJ_SEG_UNUSED;
+    } else
+        nb = plan_walk(p, f, s0, s1, (int)sp.gentry[(size_t)f * sp.ngroups + g], (int)gb, nblk, sp);
+    /* the group that holds the payload's last segment knows how many blocks the frame's stream holds */
+    const int glast = p.nseg > 0 ? (p.nseg - 1) / RTJ_SEG_GROUP : 0;
+    if (g == glast) plan_close(f, p.nseg > 0 ? nb : 0, nblk, p.len, ent, frame_skips, info, sp);
 }
 
 extern "C" int rtj_kernels_init(void)
@@ -484,13 +580,22 @@ extern "C" int rtj_launch_scan(const rtj_launch_args *a, void *stream)
             int e = rtj_launch_scan_chunk(a, 1, stream);
             if (!e) e = rtj_launch_scan_mb(a, 1, stream);
             if (e) return -e;
-            rtj_scan_plan_kernel<<<(a->F + 63) / 64, 64, 0, st>>>(a->d_desc, a->d_tables, a->F, nblk, a->d_ent,
-                                                                  a->d_frame_skips, a->d_info, a->seg,
-                                                                  RTJ_FMT_UNIT_BLOCKS(a->fmt));
+            int launches = 5;
+            if (a->seg.gsum) {
+                const int ub = RTJ_FMT_UNIT_BLOCKS(a->fmt);
+                rtj_scan_plan_group_kernel<<<dim3((unsigned)a->seg.ngroups, (unsigned)a->F), RTJ_SEG_NE, 0, st>>>(a->d_desc, a->d_tables, a->seg, ub);
+                rtj_scan_plan_chain_kernel<<<(a->F + 63) / 64, 64, 0, st>>>(a->d_desc, a->d_tables, a->F, a->seg, ub);
+                rtj_scan_plan_fill_kernel<<<(a->F * a->seg.ngroups + 63) / 64, 64, 0, st>>>(a->d_desc, a->d_tables, a->F, nblk, a->d_ent,
+                                                                                          a->d_frame_skips, a->d_info, a->seg, ub);
+                launches = 7;
+            } else
+                rtj_scan_plan_kernel<<<(a->F + 63) / 64, 64, 0, st>>>(a->d_desc, a->d_tables, a->F, nblk, a->d_ent,
+                                                                      a->d_frame_skips, a->d_info, a->seg,
+                                                                      RTJ_FMT_UNIT_BLOCKS(a->fmt));
             if ((e = (int)cudaGetLastError())) return -e;
             e = rtj_launch_scan_chunk(a, 2, stream);
             if (!e) e = rtj_launch_scan_mb(a, 2, stream);
-            return e ? -e : 5;
+            return e ? -e : launches;
         }
         int e = rtj_launch_scan_chunk(a, 0, stream);
         if (e) return -e;

@@ -38,6 +38,9 @@ constexpr int MB_RING = MB_C + 2;                   /* u16 per lane: 257 words (
 constexpr int MB_STAGE = MB_NCH * MB_RING / 2;      /* staged entries per emit round (aliases the rings) */
 constexpr int MB_POS = MB_S + MB_DLA;               /* positions with block lengths */
 constexpr int MB_RUN = 36;                          /* positions per thread in level 0 */
+constexpr int MB_PFX = 64;                          /* dense path: bytes per thread when the running sums are made */
+constexpr int MB_PFX_THREADS = (MB_S + MB_LA + MB_PFX - 1) / MB_PFX;
+static_assert(MB_PFX_THREADS <= MB_THREADS, "one thread per 64 bytes of running sums");
 static_assert(MB_RUN * MB_THREADS >= MB_POS && (MB_RUN % 4) == 0 && ((MB_RUN / 4) & 1), "level-0 runs cover the positions; odd word stride");
 
 struct MbShared {
@@ -48,8 +51,14 @@ struct MbShared {
     uint32_t ring[MB_STAGE];                        /* u16 rings during DP/chain, staged u32 entries during emit */
     uint32_t base[MB_NCH + 1];
     uint16_t entq[MB_NCH];
+    uint32_t tot[MB_PFX_THREADS + 1];               /* level 0, dense path: what each thread's 64 bytes fill */
     int entry, nb, skips, consumed;
 };
+/* level 0, dense path: running sums S (16 bit) of what the bytes fill, and T, the inverse of S over half a segment, in the
+ * space of dmb and ring */
+constexpr int MB_S_ENTRIES = MB_PFX_THREADS * MB_PFX;
+constexpr int MB_T_CAP = ((int)(sizeof(uint16_t) * (MB_S + 2 * MB_NCH) + sizeof(uint32_t) * MB_STAGE) - 2 * MB_S_ENTRIES) / 2;
+static_assert(MB_T_CAP >= MB_POS / 2 + 64 + 63 + 256, "the inverse table covers half a segment of mostly one-place bytes");
 
 __device__ __forceinline__ uint32_t swar_runs(uint32_t t) { return t & ~(t >> 1) & 0x40404040u; }
 __device__ __forceinline__ uint32_t swar_x(uint32_t t) { return t & ((swar_runs(t) >> 6) * 0x3Fu); }
@@ -186,16 +195,103 @@ rtj_scan_mb_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc *
         } else {
             uint8_t *dL = reinterpret_cast<uint8_t *>(sh.delL), *dC = reinterpret_cast<uint8_t *>(sh.delC);
             const int npos2 = npos + MB_DLA;
-            /* what every byte fills when read as a token, for both grammars: in the place of the macroblock lengths,
-             * which are made later.  fill = 1 + (b & 63) for a run token b = 64 .. 127, else 1: four bytes per step. */
-            uint32_t *fw = reinterpret_cast<uint32_t *>(sh.dmb);
-            for (int v = tid; v < (npos + MB_LA + 3) / 4; v += MB_THREADS)
-                fw[v] = swar_x(lds_u32_unaligned(sh.pay, 4 * v + mis)) + 0x01010101u;
+            /* DENSE segments -- long blocks, nearly every byte a coefficient that fills one place (the high-quality stress
+             * stream: two grammars, 54- and 63-token windows) -- take another way than the two-pointer walk below, which
+             * spends some 35 instructions a position there.  With S[i] = places the bytes 0 .. i fill when read as tokens,
+             * the block that would start at q ends with the first byte n for which S[n] - S[q + b] >= 63 - b: n is one look-up
+             * in T, the inverse of S (T[v] = first i with S[i] >= v).  T has one entry per place filled, so it only fits
+             * where runs are short: half a segment at a time, and only if both halves fit. */
+            uint16_t *S = reinterpret_cast<uint16_t *>(sh.dmb);
+            uint16_t *T = S + MB_S_ENTRIES;
+            const int nby = npos + MB_LA;
+            const int nthr = (nby + MB_PFX - 1) / MB_PFX;
+            /* how many places the segment's bytes fill in all: what tells a dense segment from the usual kind (many times
+             * as many places as bytes), before anything is spent on S */
+            {
+                uint32_t part = 0;
+                for (int v = tid; v < (nby + 3) / 4; v += MB_THREADS) {
+                    const uint32_t x = swar_x(lds_u32_unaligned(sh.pay, 4 * v + mis)) + 0x01010101u;
+                    part += (x & 0x00FF00FFu) + ((x >> 8) & 0x00FF00FFu);              /* two 16-bit sums */
+                }
+                part = (part & 0xFFFFu) + (part >> 16);
+#pragma unroll
+                for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xFFFFFFFFu, part, o);
+                if (lane == 0) sh.tot[tid >> 5] = part;
+            }
             __syncthreads();
-            const uint8_t *fills = reinterpret_cast<const uint8_t *>(fw);
-            const int q_begin = tid * MB_RUN, q_end = min(q_begin + MB_RUN, npos2);
-            mb_level0_run(payb, fills, dL, q_begin, q_end, lb8);
-            if (lb8 != cb8) mb_level0_run(payb, fills, dC, q_begin, q_end, cb8);
+            const uint32_t places = sh.tot[0] + sh.tot[1] + sh.tot[2] + sh.tot[3];
+            /* rounds the dense path would take (a half or a quarter of the segment's positions each), 0: not dense */
+            int rounds = places * 5u <= 8u * (unsigned)MB_T_CAP ? 2 : places * 5u <= 16u * (unsigned)MB_T_CAP ? 4 : 0;
+            __syncthreads();                                                         /* tot is used again */
+            if (rounds) {
+                if (tid < nthr) {
+                    uint32_t *S2 = reinterpret_cast<uint32_t *>(S) + tid * (MB_PFX / 2);
+                    uint32_t acc = 0;
+#pragma unroll 4
+                    for (int wv = 0; wv < MB_PFX / 4; wv++) {
+                        const uint32_t x = swar_x(lds_u32_unaligned(sh.pay, MB_PFX * tid + 4 * wv + mis)) + 0x01010101u;
+                        const uint32_t a0 = acc + (x & 0xFFu), a1 = a0 + ((x >> 8) & 0xFFu), a2 = a1 + ((x >> 16) & 0xFFu);
+                        acc = a2 + (x >> 24);
+                        S2[2 * wv] = a0 | a1 << 16;
+                        S2[2 * wv + 1] = a2 | acc << 16;
+                    }
+                    sh.tot[tid] = acc;
+                }
+                __syncthreads();
+                if (tid < nthr && tid > 0) {
+                    uint32_t off = 0;
+                    for (int k = 0; k < tid; k++) off += sh.tot[k];
+                    uint32_t *S2 = reinterpret_cast<uint32_t *>(S) + tid * (MB_PFX / 2);
+#pragma unroll 4
+                    for (int wv = 0; wv < MB_PFX / 2; wv++) S2[wv] += off * 0x00010001u;   /* places < 65536: no carry between the halves */
+                }
+                __syncthreads();
+                /* every round's T must fit: places filled from the round's first position to its last window's end */
+                for (;;) {
+                    const int R = MB_POS / rounds;
+                    bool fits = true;
+                    for (int r = 0; r * R < npos2; r++)
+                        fits = fits && (int)S[min(min((r + 1) * R, npos2) + 63 + 64, nby - 1)] - (int)S[r * R] < MB_T_CAP - 64;
+                    if (fits || rounds == 4) { rounds = fits ? rounds : 0; break; }
+                    rounds = 4;
+                }
+            }
+            if (rounds) {
+                const int R = MB_POS / rounds;
+                for (int r = 0; r * R < npos2; r++) {
+                    const int qlo = r * R, qhi = min(qlo + R, npos2);
+                    const int v0 = S[qlo];
+                    if (r) __syncthreads();                                          /* the round before is done with T */
+                    /* T over the places (v0, v0 + cap): byte i covers the places S[i - 1] + 1 .. S[i] */
+                    for (int i2 = qlo + 1 + tid; i2 <= min(qhi + 63 + 64, nby - 1); i2 += MB_THREADS) {
+                        const int hi = (int)S[i2] - v0, lo = (int)S[i2 - 1] - v0;
+                        for (int v = lo + 1; v <= min(hi, MB_T_CAP - 1); v++) T[v] = (uint16_t)i2;
+                    }
+                    __syncthreads();
+                    for (int q = qlo + tid; q < qhi; q += MB_THREADS) {
+                        const bool ff = payb[q] == 0xFFu;           /* skipped block (lib/RTjpeg.c:2704): a block of its own, one byte long */
+                        /* the block's tokens start behind byte q + b and have 63 - b places to fill */
+                        const int nL = lb8 >= 63 ? q + 63 : (int)T[(int)S[q + lb8] + 63 - lb8 - v0];
+                        dL[q] = (uint8_t)(ff ? 1 : nL + 1 - q);
+                        if (lb8 != cb8) {
+                            const int nC = cb8 >= 63 ? q + 63 : (int)T[(int)S[q + cb8] + 63 - cb8 - v0];
+                            dC[q] = (uint8_t)(ff ? 1 : nC + 1 - q);
+                        }
+                    }
+                }
+            } else {
+                __syncthreads();                                                     /* S gives way to the fills */
+                /* what every byte fills when read as a token, for both grammars: in the place of the macroblock lengths,
+                 * which are made later.  fill = 1 + (b & 63) for a run token b = 64 .. 127, else 1: four bytes per step. */
+                uint32_t *fw = reinterpret_cast<uint32_t *>(sh.dmb);
+                for (int v = tid; v < (npos + MB_LA + 3) / 4; v += MB_THREADS)
+                    fw[v] = swar_x(lds_u32_unaligned(sh.pay, 4 * v + mis)) + 0x01010101u;
+                __syncthreads();
+                const uint8_t *fills = reinterpret_cast<const uint8_t *>(fw);
+                const int q_begin = tid * MB_RUN, q_end = min(q_begin + MB_RUN, npos2);
+                mb_level0_run(payb, fills, dL, q_begin, q_end, lb8);
+                if (lb8 != cb8) mb_level0_run(payb, fills, dC, q_begin, q_end, cb8);
+            }
         }
         __syncthreads();
         if (PHASE == 1 && keep) {
@@ -204,8 +300,17 @@ rtj_scan_mb_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc *
             for (int v = tid; v < nv; v += MB_THREADS) keep[v] = d4[v];
         }
 
+        /* The second pass of the segment-parallel arrangement knows where its segment is entered and how many blocks lie
+         * before and in it (rtj_scan_plan_kernel): nothing has to be found out for every possible entry any more -- one
+         * thread walks the segment's blocks from the known entry, all threads make the entries. */
+        if (PHASE == 2 && tid == 0) {
+            const uint32_t nxt = blockIdx.x + 1 < (unsigned)sp.maxseg ? sp.base[my_seg + 1] : RTJ_SEG_UNUSED;
+            sh.nb = nxt != RTJ_SEG_UNUSED ? (int)nxt : sp.nbf[f];
+            sh.entq[0] = (uint16_t)sh.entry;
+            sh.base[0] = (uint32_t)nb0;
+        }
         /* ---- compose: length of the macroblock that would start at every position ---- */
-        for (int q = tid; q < npos; q += MB_THREADS) {
+        for (int q = tid; q < (PHASE == 2 ? 0 : npos); q += MB_THREADS) {
             int n = q;
 #pragma unroll
             for (int k = 0; k < unit_luma; k++) n += dLb[n];
@@ -222,7 +327,7 @@ rtj_scan_mb_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc *
          *      a right-to-left recurrence over the 512 positions of a chunk would keep one lane per chunk busy. ---- */
         {
             uint16_t *rings = reinterpret_cast<uint16_t *>(sh.ring);
-            for (int q = tid; q < npos; q += MB_THREADS) {
+            for (int q = tid; q < (PHASE == 2 ? 0 : npos); q += MB_THREADS) {
                 const int c = q / MB_C, cend = (c + 1) * MB_C;
                 uint32_t v = 0;                                             /* nothing starts behind the payload */
                 if (q < lim) {
@@ -256,7 +361,7 @@ rtj_scan_mb_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc *
         }
 
         /* ---- chain ---- */
-        if (tid == 0) {
+        if (PHASE != 2 && tid == 0) {
             const uint16_t *rings = reinterpret_cast<const uint16_t *>(sh.ring);
             int e = sh.entry, nb = nb0;
             for (int j = 0; j < nch; j++) {
@@ -275,18 +380,19 @@ rtj_scan_mb_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc *
         /* ---- emit, in two steps as in rtj_scan_chunk.cu: the chunk lanes walk their macroblocks and note where every
          *      block starts and which place of its unit it has; all threads then make the entries and store them. ---- */
         const int nb1 = min(sh.nb, nblk);
+        const int nwalk = PHASE == 2 ? 1 : nch;                            /* walkers: one per chunk, or one for the segment */
         int q = 0, i = 0, qend = 0, myskips = 0, lastend = -1, k6 = 0;
-        if (tid < nch) {
+        if (tid < nwalk) {
             q = sh.entq[tid];
             i = (int)sh.base[tid];
-            qend = (tid + 1) * MB_C;
+            qend = PHASE == 2 ? npos : (tid + 1) * MB_C;
         }
         __syncthreads();
         uint16_t *starts = reinterpret_cast<uint16_t *>(sh.ring);          /* start (13 bits) | place in the unit << 13; 0xFFFF: missing */
         static_assert(MB_POS < (1 << 13) && RTJ_FMT_UNIT_BLOCKS(0) <= 7, "a block start and its place fit 16 bits");
         for (int r0 = nb0; r0 < nb1; r0 += 2 * MB_STAGE) {
             const int r1 = min(r0 + 2 * MB_STAGE, nb1);
-            if (tid < nch) {
+            if (tid < nwalk) {
                 /* a macroblock belongs to the chunk it starts in; its later blocks may lie behind the chunk */
                 while ((k6 != 0 || q < min(qend, lim)) && i < r1) {
                     if (q >= lim) starts[i - r0] = 0xFFFFu;                 /* the payload ended inside this macroblock */

@@ -2,7 +2,7 @@
 """Per-source-line table of one kernel from an ncu report: executed warp instructions and stall samples of every
 SASS instruction, attributed through the cubin's line table (nvdisasm -gi) to the line of the KERNEL BODY it was
 inlined into (and, with --inner, to the innermost line as well).
-Usage: ncu_lines.py report.ncu-rep cubin kernel-regex [--inner] [--min PCT]"""
+Usage: ncu_lines.py report.ncu-rep cubin kernel-regex [--inner] [--min PCT] [--nth N]"""
 import collections
 import csv
 import os
@@ -18,10 +18,11 @@ def main():
     out = subprocess.run(["ncu", "-i", rep, "--csv", "--page", "source", "--kernel-name", "regex:" + pat],
                          capture_output=True, text=True).stdout
     src = list(csv.reader(out.splitlines()))
-    for j in range(2, len(src)):
-        if src[j] == src[1]:
-            src = src[:j - 1]
-            break
+    # one listing per matching launch: "--nth N" picks one (default the first)
+    starts = [i for i, r in enumerate(src) if r and r[0] == "Kernel Name"] + [len(src)]
+    nth = int(sys.argv[sys.argv.index("--nth") + 1]) if "--nth" in sys.argv else 0
+    print("#", src[starts[nth]][1][:110])
+    src = src[starts[nth]:starts[nth + 1]]
     h = src[1]
     iex, ism, isrc = h.index("Instructions Executed"), h.index("# Samples"), h.index("Source")
     rows = src[2:]

@@ -55,7 +55,7 @@ E_CUDA, E_ARG, E_HEADER, E_SIZE, E_FORMAT, E_OVERRUN, E_TOOBIG, E_NOMEM = -1, -2
 HOST_IN_PINNED, HOST_OUT_PINNED = 1, 2
 STREAM_SLACK_BYTES = 128
 TABLE_ZERO, TABLE_CUSTOM = 0, 256
-SCAN_AUTO, SCAN_LANE, SCAN_WARP, SCAN_CHUNK, SCAN_SEGMENT, SCAN_WALK = 0, 1, 2, 3, 4, 5
+SCAN_AUTO, SCAN_LANE, SCAN_WARP, SCAN_CHUNK, SCAN_SEGMENT, SCAN_WALK, SCAN_SYNC = 0, 1, 2, 3, 4, 5, 6
 PIPELINE_AUTO, PIPELINE_SERIAL, PIPELINE_SLICED = 0, 1, 2
 
 _u8p = C.POINTER(C.c_uint8)

@@ -154,7 +154,7 @@ int ws_reserve(rtjgpu_ctx *ctx, Workspace *ws, int F, int nblk)
     if (F > ws->cap_frames) {
         if (ws->d_frame_skips) cudaFree(ws->d_frame_skips);
         ws->d_frame_skips = nullptr; ws->cap_frames = 0;
-        CK(ctx, cudaMalloc(&ws->d_frame_skips, (size_t)F * sizeof(uint32_t)));
+        CK(ctx, cudaMalloc(&ws->d_frame_skips, (size_t)2 * F * sizeof(uint32_t)));      /* ... and K1's hand-over flags behind them */
         ws->cap_frames = F;
     }
     if (F > ws->walk_cap) {
@@ -326,6 +326,7 @@ int run_kernels(rtjgpu_ctx *ctx, Workspace *ws, const uint8_t *d_stream, const r
     a.fmt = ctx->format;
     a.row0 = 0; a.row1 = RTJ_FMT_UNITS_Y(ctx->format, h);
     a.d_walk = ws->d_walk;
+    a.d_redo = ws->d_frame_skips + ws->cap_frames;
     a.d_ent = ws->d_ent; a.d_src = ws->d_src; a.d_frame_skips = ws->d_frame_skips; a.d_info = ws->d_info;
     a.d_hardq = ws->d_hardq; a.d_chunk_last = ws->d_chunk_last;
     a.d_k3_in = nullptr; a.d_k3_out = ws->d_k3_carry;
@@ -486,6 +487,7 @@ int rtjgpu_create(int device, rtjgpu_ctx **out)
     if (const char *v = getenv("RTJPEG_B200_SLICE")) { ctx->slice_frames = ctx->slice0_frames = std::max(32, atoi(v)); ctx->slices_forced = true; }
     if (const char *v = getenv("RTJPEG_B200_SLICE0")) ctx->slice0_frames = std::max(32, atoi(v));
     if (const char *v = getenv("RTJPEG_B200_SCAN_PRIO")) ctx->scan_priority = atoi(v) != 0;
+    if (const char *v = getenv("RTJPEG_B200_SCAN")) ctx->scan_mode = std::min(std::max(atoi(v), 0), (int)RTJGPU_SCAN_SYNC);
     if (const char *v = getenv("RTJPEG_B200_PIPELINE")) ctx->pipeline_mode = std::min(std::max(atoi(v), 0), (int)RTJGPU_PIPELINE_SLICED);
     int rc = RTJGPU_OK;
     do {
@@ -558,7 +560,7 @@ void rtjgpu_enable_timing(rtjgpu_ctx *ctx, int on) { if (ctx) ctx->timing = on !
 
 int rtjgpu_set_scan_mode(rtjgpu_ctx *ctx, int mode)
 {
-    if (!ctx || mode < RTJGPU_SCAN_AUTO || mode > RTJGPU_SCAN_WALK) return RTJGPU_E_ARG;
+    if (!ctx || mode < RTJGPU_SCAN_AUTO || mode > RTJGPU_SCAN_SYNC) return RTJGPU_E_ARG;
     ctx->scan_mode = mode;
     return RTJGPU_OK;
 }
@@ -988,6 +990,7 @@ int rtjgpu_scan_device(rtjgpu_ctx *ctx, const uint8_t *d_stream, const rtjgpu_fr
     a.fmt = ctx->format;
     a.d_ent = ctx->ws.d_ent; a.d_frame_skips = ctx->ws.d_frame_skips; a.d_info = ctx->ws.d_info;
     a.d_walk = ctx->ws.d_walk;
+    a.d_redo = ctx->ws.d_frame_skips + ctx->ws.cap_frames;
     a.row1 = RTJ_FMT_UNITS_Y(ctx->format, h);
     a.scan_mode = ctx->scan_mode;
     if ((rc = seg_reserve(ctx, &ctx->ws, F, nblk, ctx->scan_mode, &a.seg))) return rc;

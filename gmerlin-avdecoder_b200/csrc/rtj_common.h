@@ -128,6 +128,7 @@ typedef struct rtj_launch_args {
     int                      slice;         /* index of the slice [f0, f1) */
     int                      row0, row1;    /* the rows of units K2 of this launch covers (all of them, as things are) */
     void                    *d_walk;        /* [F] int2: rtj_scan_walk_kernel's state between slices of blocks */
+    uint32_t                *d_redo;        /* [F] rtj_scan_sync_kernel: frames it leaves to rtj_scan_chunk_kernel */
     int                      fmt;           /* RTJ_YUV420 / RTJ_YUV422 / RTJ_RGB8 */
     uint32_t                *d_ent;         /* [F][nblk] */
     uint16_t                *d_src;         /* [F][nblk] */
@@ -154,6 +155,9 @@ int rtj_launch_scan(const rtj_launch_args *a, void *stream);          /* returns
 /* phase: 0 = one CTA per frame does everything, 1 = segment summaries, 2 = segment emit */
 int rtj_launch_scan_chunk(const rtj_launch_args *a, int phase, void *stream);    /* rtj_scan_chunk.cu */
 int rtj_scan_chunk_init(void);
+int rtj_launch_scan_chunk_redo(const rtj_launch_args *a, const uint32_t *redo, void *stream);   /* one CTA per frame, flagged frames only */
+int rtj_launch_scan_sync(const rtj_launch_args *a, uint32_t *redo, void *stream);               /* rtj_scan_sync.cu */
+int rtj_scan_sync_init(void);
 int rtj_launch_scan_mb(const rtj_launch_args *a, int phase, void *stream);       /* rtj_scan_mb.cu */
 int rtj_launch_scan_walk(const rtj_launch_args *a, int b0, int b1, void *stream);   /* rtj_scan_walk.cu: blocks [b0, b1) of every frame */
 int rtj_scan_walk_init(void);

@@ -565,6 +565,7 @@ extern "C" int rtj_kernels_init(void)
     if (e) return e;
     if ((e = rtj_scan_mb_init())) return e;
     if ((e = rtj_scan_walk_init())) return e;
+    if ((e = rtj_scan_sync_init())) return e;
     return rtj_scan_chunk_init();
 }
 
@@ -574,6 +575,16 @@ extern "C" int rtj_launch_scan(const rtj_launch_args *a, void *stream)
     cudaStream_t st = (cudaStream_t)stream;
     /* AUTO: the chunk-parallel kernels -- rtj_scan_chunk_kernel takes every frame without a raw prefix,
      * rtj_scan_mb_kernel the others; each returns at once on the other's frames. */
+    if (a->scan_mode == RTJGPU_SCAN_SYNC || (a->scan_mode == RTJGPU_SCAN_AUTO && !a->seg.sum)) {
+        /* one CTA per frame.  Frames without a raw prefix: the self-synchronising walk; the frames it hands over (streams
+         * that do not forget their past) are scanned by rtj_scan_chunk_kernel right behind it.  SYNC keeps every such
+         * frame in the walk (the cross-check of the parity suite). */
+        uint32_t *redo = a->scan_mode == RTJGPU_SCAN_AUTO ? a->d_redo : nullptr;
+        int e = rtj_launch_scan_sync(a, redo, stream);
+        if (!e && redo) e = rtj_launch_scan_chunk_redo(a, redo, stream);
+        if (!e) e = rtj_launch_scan_mb(a, 0, stream);
+        return e ? -e : (redo ? 3 : 2);
+    }
     if (a->scan_mode == RTJGPU_SCAN_AUTO || a->scan_mode == RTJGPU_SCAN_CHUNK || a->scan_mode == RTJGPU_SCAN_SEGMENT) {
         if (a->seg.sum) {
             /* few frames: their segments are parsed by separate CTAs -- summaries, frame-level chain, emit */

@@ -98,13 +98,15 @@ __global__ void __launch_bounds__(CS_THREADS, 8)
 rtj_scan_chunk_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc *__restrict__ desc,
                       const rtj_dev_table *__restrict__ tables, int F, int nblk,
                       uint32_t *__restrict__ ent, uint32_t *__restrict__ frame_skips,
-                      rtj_dev_info *__restrict__ info, const rtj_seg_plan sp, int f0, int slice)
+                      rtj_dev_info *__restrict__ info, const rtj_seg_plan sp, int f0, int slice,
+                      const uint32_t *__restrict__ redo)
 {
     extern __shared__ __align__(16) uint8_t cs_smem[];
     CsShared &sh = *reinterpret_cast<CsShared *>(cs_smem);
     const int tid = threadIdx.x, lane = tid & 31;
     const int f = (PHASE == 0 ? blockIdx.x : blockIdx.y) + f0;        /* F: one behind the last frame of this launch */
     if (f >= F) return;
+    if (PHASE == 0 && redo && !redo[f]) return;                        /* behind rtj_scan_sync_kernel: the frames it left */
     const rtjgpu_frame_desc d = desc[f];
     {
         const rtj_dev_table &tab = tables[min((int)d.table, RTJ_NUM_TABLES - 1)];      /* descriptors are the caller's memory */
@@ -411,12 +413,20 @@ extern "C" int rtj_launch_scan_chunk(const rtj_launch_args *a, int phase, void *
     const dim3 grid = phase == 0 ? dim3((unsigned)nf) : dim3((unsigned)a->seg.maxseg, (unsigned)nf);
     if (phase == 0)
         rtj_scan_chunk_kernel<0><<<grid, CS_THREADS, sizeof(CsShared), st>>>(
-            a->d_stream, a->d_desc, a->d_tables, a->f1, nblk, a->d_ent, a->d_frame_skips, a->d_info, a->seg, a->f0, a->slice);
+            a->d_stream, a->d_desc, a->d_tables, a->f1, nblk, a->d_ent, a->d_frame_skips, a->d_info, a->seg, a->f0, a->slice, nullptr);
     else if (phase == 1)
         rtj_scan_chunk_kernel<1><<<grid, CS_THREADS, sizeof(CsShared), st>>>(
-            a->d_stream, a->d_desc, a->d_tables, a->f1, nblk, a->d_ent, a->d_frame_skips, a->d_info, a->seg, a->f0, a->slice);
+            a->d_stream, a->d_desc, a->d_tables, a->f1, nblk, a->d_ent, a->d_frame_skips, a->d_info, a->seg, a->f0, a->slice, nullptr);
     else
         rtj_scan_chunk_kernel<2><<<grid, CS_THREADS, sizeof(CsShared), st>>>(
-            a->d_stream, a->d_desc, a->d_tables, a->f1, nblk, a->d_ent, a->d_frame_skips, a->d_info, a->seg, a->f0, a->slice);
+            a->d_stream, a->d_desc, a->d_tables, a->f1, nblk, a->d_ent, a->d_frame_skips, a->d_info, a->seg, a->f0, a->slice, nullptr);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int rtj_launch_scan_chunk_redo(const rtj_launch_args *a, const uint32_t *redo, void *stream)
+{
+    const int nblk = RTJ_FMT_NBLK(a->fmt, a->w, a->h);
+    rtj_scan_chunk_kernel<0><<<(unsigned)(a->f1 - a->f0), CS_THREADS, sizeof(CsShared), (cudaStream_t)stream>>>(
+        a->d_stream, a->d_desc, a->d_tables, a->f1, nblk, a->d_ent, a->d_frame_skips, a->d_info, a->seg, a->f0, a->slice, redo);
     return (int)cudaGetLastError();
 }

@@ -205,6 +205,7 @@ int  rtjgpu_last_cuda_error(const rtjgpu_ctx *ctx);
 #define RTJGPU_SCAN_CHUNK   3
 #define RTJGPU_SCAN_SEGMENT 4
 #define RTJGPU_SCAN_WALK    5     /* one thread per frame, payload staged through shared memory with cp.async (not for raw-prefix frames) */
+#define RTJGPU_SCAN_SYNC    6     /* one CTA per frame, every lane walks from its chunk's synchronisation point (not for raw-prefix frames) */
 int  rtjgpu_set_scan_mode(rtjgpu_ctx *ctx, int mode);
 
 /* How a large device batch is worked through.  SERIAL (what AUTO stands for at present): every stage on cuda_stream, one

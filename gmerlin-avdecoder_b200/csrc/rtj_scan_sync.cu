@@ -48,17 +48,19 @@
 namespace {
 
 constexpr unsigned FULL = 0xFFFFFFFFu;
-constexpr int SY_THREADS = 128;
+constexpr int SY_THREADS = 64;
 constexpr int SY_WARPS = SY_THREADS / 32;
-constexpr int SY_GMAX = 39;                                /* 8-byte groups per chunk: odd */
-constexpr int SY_GMIN = 17;                                /* short frames use fewer lanes, not shorter chunks */
+constexpr int SY_GMAX = 79;                                /* 8-byte groups per chunk: odd */
+constexpr int SY_LEAD = 32;                                /* groups of the lead-in walk in front of a chunk (256 bytes) */
+constexpr int SY_GMIN = SY_LEAD + 1;                       /* short frames use fewer lanes, not shorter chunks */
 constexpr int SY_SEG_MAX = SY_THREADS * SY_GMAX * 8;       /* bytes of a frame in shared memory at a time */
-constexpr int SY_LA = 80;                                  /* bytes walked behind a segment: the block that starts on its last
-                                                            * byte (<= 64 bytes) and the start behind it, whole groups */
+constexpr int SY_LA = 80;                                  /* bytes walked behind a segment that is not the frame's last: the block that
+                                                            * starts on its last byte (<= 64 bytes) and the start behind it, whole groups */
 constexpr int SY_PAY_BYTES = SY_SEG_MAX + SY_LA + 16;      /* + what an unaligned 8-byte read may touch */
 constexpr int SY_WORDS = (SY_SEG_MAX + SY_LA + 31) / 32;   /* bit map words */
-constexpr int SY_STAGE = 2048;                             /* block starts staged per emit round */
+constexpr int SY_STAGE = 3072;                             /* block starts staged per emit round */
 constexpr int SY_KMAX = (SY_WORDS + SY_THREADS - 1) / SY_THREADS;
+constexpr int SY_MAX_DIRTY = 8;                            /* more chunks than this entered in the wrong state: not this kernel's stream */
 
 static_assert((SY_GMAX & 1) == 1 && (SY_GMIN & 1) == 1, "odd chunk lengths: conflict-free 8-byte reads");
 static_assert(SY_SEG_MAX + SY_LA < 65536, "positions inside a segment are 16 bit");
@@ -69,7 +71,7 @@ struct SyShared {
     uint32_t bits[SY_WORDS + 1];         /* bit p: a block starts at byte p of the segment */
     uint16_t pre[SY_WORDS + 2];          /* blocks that start before word w's 32 positions */
     uint16_t starts[SY_STAGE + 2];       /* one emit round's block starts */
-    int16_t  sg[SY_THREADS + 1];         /* group index of every lane's synchronisation point, -1: none */
+    int8_t   exitst[SY_THREADS];         /* the state every lane's walk left its chunk in */
     int      wsum[SY_WARPS];
     int      carry;                      /* state at the first byte of the next segment */
     int      nb;                         /* blocks started so far in this frame */
@@ -105,56 +107,56 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, unsigned
                  :: "r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
 }
 
-/* per byte of a word: run length - 1 (0..63) in run tokens 01xxxxxx, 0 in every other byte: what the byte fills, less one */
-__device__ __forceinline__ uint32_t swar_x(uint32_t t)
+/* byte k of w, sign-extended (prmt: a selector nibble's top bit replicates the chosen byte's sign) */
+template <int K>
+__device__ __forceinline__ int sext_byte(uint32_t w)
 {
-    const uint32_t runs = t & ~(t >> 1) & 0x40404040u;
-    return t & ((runs >> 6) * 0x3Fu);
+    int d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(w), "r"(0u), "n"(0x8880 + 0x1111 * K));
+    return d;
 }
-/* bit 7 of every byte that is 0xFF */
-__device__ __forceinline__ uint32_t swar_ff(uint32_t t)
+template <int K>
+__device__ __forceinline__ int zext_byte(uint32_t w)
 {
-    const uint32_t y = ~t;
-    return ~(((y & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | y | 0x7F7F7F7Fu);
+    int d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(w), "r"(0u), "n"(0x4440 + K));
+    return d;
 }
 
-/* Phase B: one state over four bytes.  r > 0: places still to fill; r <= 0: the next byte starts a block. */
+/* One state over four bytes.  r > 0: places of the block still to fill; r <= 0: the next byte starts a block (a DC byte: 63
+ * places behind it; the skip marker 0xFF: a block of its own).  A run token 01xxxxxx fills x + 1 places, any other byte one.
+ * bm gets a bit for every byte that starts a block. */
+template <bool BITS>
 __device__ __forceinline__ void walk4(uint32_t W, int &r, uint32_t &bm, int bit0)
 {
-    const uint32_t X = swar_x(W);
-    const uint32_t G = 0x3F3F3F3Fu ^ ((swar_ff(W) >> 7) * 0x3Fu);        /* the state behind a block's first byte: 63, or 0 behind a skip marker */
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const int x = (int)__byte_perm(X, 0, 0x4440 + k);
-        const int g = (int)__byte_perm(G, 0, 0x4440 + k);
-        const bool at = r <= 0;
-        const int t = r - 1 - x;
-        r = at ? g : t;
-        if (at) bm |= 1u << (bit0 + k);
+    const uint32_t runs = W & ~(W >> 1) & 0x40404040u;                   /* bit 6 of every run token */
+    const uint32_t NX = ~(W & (runs - (runs >> 6)));                     /* per byte, as a signed byte: -(what it fills) */
+    const uint32_t y = ~W;
+    const uint32_t z = ~((y & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) & W & 0x80808080u;   /* bit 7 of every byte that is 0xFF */
+    const uint32_t G = 0x3F3F3F3Fu & ~(z - (z >> 7));                    /* the state behind a block's first byte: 63, or 0 behind a skip marker */
+#define SY_STEP(k)                                                     \
+    {                                                                  \
+        const int nx = sext_byte<k>(NX), g = zext_byte<k>(G);          \
+        const bool at = r <= 0;                                        \
+        r = at ? g : r + nx;                                           \
+        if (BITS && at) bm |= 1u << (bit0 + k);                        \
     }
+    SY_STEP(0) SY_STEP(1) SY_STEP(2) SY_STEP(3)
+#undef SY_STEP
 }
 
-/* Phase A: the SET of states a parse may be in, over four bytes.  Bit i of (hi:lo) = "i + 1 places to fill" (i = 0..62),
- * d = "the next byte starts a block".  A token that fills f places moves every r to r - f: a shift; what drops out at
- * the bottom has finished its block. */
-__device__ __forceinline__ void set4(uint32_t W, uint32_t &lo, uint32_t &hi, uint32_t &d)
+/* groups [g0, g1) from state r; BITS: leave the starts in the bit map */
+template <bool BITS>
+__device__ __forceinline__ int walk_groups(const uint2 *pay8, uint8_t *bits8, int g0, int g1, int r)
 {
-    uint32_t X = swar_x(W);
-    X -= ((X + 0x01010101u) >> 6) & 0x01010101u;                         /* a run of 64 fills like a run of 63: shifts stay below 64 */
-    const uint32_t Z = swar_ff(W) >> 7;
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const unsigned f = __byte_perm(X, 0, 0x4440 + k) + 1u;           /* 1..63 */
-        const unsigned ff = (Z >> (8 * k)) & 1u;
-        const unsigned long long R = ((unsigned long long)hi << 32) | lo;
-        const unsigned long long out = R << (64u - f);                   /* the r's <= f */
-        const unsigned long long S = R >> f;
-        lo = (uint32_t)S;
-        hi = (uint32_t)(S >> 32);
-        const uint32_t fin = min((uint32_t)out | (uint32_t)(out >> 32), 1u);
-        hi |= (d & ~ff) << 30;                                           /* a DC byte: 63 places to fill */
-        d = fin | (d & ff);                                              /* a skip marker: the next byte starts a block again */
+    for (int g = g0; g < g1; g++) {
+        const uint2 w = pay8[g];
+        uint32_t bm = 0;
+        walk4<BITS>(w.x, r, bm, 0);
+        walk4<BITS>(w.y, r, bm, 4);
+        if (BITS) bits8[g] = (uint8_t)bm;
     }
+    return r;
 }
 
 __device__ __forceinline__ uint32_t lds_u32_unaligned(const uint32_t *w, int byte)
@@ -201,9 +203,10 @@ rtj_scan_sync_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc
     const uint8_t *payb = reinterpret_cast<const uint8_t *>(sh.pay);
     uint8_t *bits8 = reinterpret_cast<uint8_t *>(sh.bits);
 
-    /* positions: byte p of the frame is gbase[p]; the payload is [mis, end) */
+    /* positions: byte p of the frame is gbase[p]; the payload is [mis, end).  A frame that fits one segment leaves room for
+     * the start behind its last block (end + 1 at most) inside the lanes' chunks. */
     const int end = len > 0 ? mis + len : 0;
-    const int G = end > SY_SEG_MAX ? SY_GMAX : max(SY_GMIN, ((end + SY_THREADS * 8 - 1) / (SY_THREADS * 8)) | 1);
+    const int G = end + 8 > SY_SEG_MAX ? SY_GMAX : max(SY_GMIN, ((end + 8 + SY_THREADS * 8 - 1) / (SY_THREADS * 8)) | 1);
     const int SEG = SY_THREADS * G * 8;
     const uint32_t mbar = smem_u32(&sh.mbar);
 
@@ -224,7 +227,8 @@ rtj_scan_sync_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc
         const int lim = end - seg0;                                    /* the payload ends at byte lim of this segment */
         const int first = seg0 == 0 ? mis : 0;
         const int climit = min(SEG, lim);                              /* starts before it are this segment's blocks */
-        const int gtot = min(SEG + SY_LA, (lim + SY_LA + 7) & ~7) >> 3; /* groups to walk */
+        const bool more = lim + 8 > SEG;                               /* the frame goes on behind this segment */
+        const int gtot = more ? (SEG + SY_LA) >> 3 : (lim + 8 + 7) >> 3;   /* groups to walk: up to the start behind the last block */
         const int wtot = (gtot * 8 + 31) >> 5;                         /* bit map words they fill (the last one maybe in part) */
 
         /* ---- load: one bulk copy; what lies behind the payload reads 0x7F, a run token that ends any block (the packet's
@@ -247,55 +251,50 @@ rtj_scan_sync_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc
         }
         __syncthreads();
 
-        /* ---- phase A: the synchronisation point of every chunk ---- */
+        /* ---- lead-in: every lane walks the SY_LEAD groups in front of its chunk from a guessed state ("a block starts
+         *      here").  Run-length streams forget their past within a handful of blocks: at the chunk's first byte the
+         *      walk is, as a rule, in the true state.  Whether it is, is checked below -- never assumed. ---- */
         const uint2 *pay8 = reinterpret_cast<const uint2 *>(sh.pay);
-        int sg = -1, r = 0;
-        if (tid == 0) {
-            sg = 0;
-            r = seg0 == 0 ? 0 : sh.carry;
-        } else if (tid * G * 8 < lim) {
-            uint32_t lo = 0xFFFFFFFFu, hi = 0x7FFFFFFFu, dd = 1u;
-            const uint2 *p = pay8 + tid * G;
-            for (int g = 0; g < G; g++) {
-                const uint2 w = p[g];
-                set4(w.x, lo, hi, dd);
-                set4(w.y, lo, hi, dd);
-                if (__popc(lo) + __popc(hi) + (int)dd == 1) {
-                    sg = tid * G + g + 1;
-                    r = dd ? 0 : (hi ? 64 - __clz((int)hi) : 32 - __clz((int)lo));
-                    break;
-                }
-            }
-        }
-        sh.sg[tid] = (int16_t)sg;
-        /* streams that do not forget their past: leave the frame to the kernel whose cost does not depend on the content */
-        {
-            const int active = min(SY_THREADS, (lim + G * 8 - 1) / (G * 8));
-            const int lost = __syncthreads_count(tid < active && sg < 0);
-            if (redo && lost > max(2, active >> 3)) {
+        const int g0 = tid * G, g1 = min(g0 + G, gtot);                /* this lane's chunk, in groups */
+        int r_in = 0;                                                  /* the state the chunk is entered in */
+        if (tid == 0) r_in = seg0 == 0 ? 0 : sh.carry;
+        else if (g0 < gtot) r_in = walk_groups<false>(pay8, nullptr, g0 - SY_LEAD, g0, 0);
+
+        /* ---- walk: the chunk, from that state; one bit per byte that starts a block ---- */
+        int r_out = r_in;
+        if (g0 < gtot) r_out = walk_groups<true>(pay8, bits8, g0, g1, r_in);
+        sh.exitst[tid] = (int8_t)r_out;
+        __syncthreads();
+
+        /* ---- check: a chunk must have been entered in the state its left neighbour ended in.  Where not, it is walked
+         *      again from that state; its own exit state may change in turn, so this repeats until nothing changes (one
+         *      round as a rule; after round k the first k chunks are final whatever the stream). ---- */
+        for (int round = 0;; round++) {
+            const int want = tid > 0 ? (int)sh.exitst[tid - 1] : r_in;
+            /* states <= 0 all mean "a block starts here" */
+            const bool dirty = tid > 0 && g0 < gtot && max(want, 0) != max(r_in, 0);
+            const int ndirty = __syncthreads_count(dirty);
+            if (ndirty == 0) break;
+            if (redo && round == 0 && ndirty > SY_MAX_DIRTY) {
+                /* a stream that does not forget its past: leave the frame to the kernel whose cost does not depend on the content */
                 if (tid == 0) redo[f] = 1u;
                 return;
             }
-        }
-
-        /* ---- phase B: from the lane's synchronisation point to the next lane's ---- */
-        if (sg >= 0) {
-            int gend = gtot;
-            for (int j = tid + 1; j < SY_THREADS; j++) {
-                const int s = sh.sg[j];
-                if (s >= 0) { gend = min(s, gtot); break; }
+            if (dirty) {
+                r_in = want;
+                r_out = walk_groups<true>(pay8, bits8, g0, g1, r_in);
+                sh.exitst[tid] = (int8_t)r_out;
             }
-            const int gcarry = SY_THREADS * G - 1;                     /* behind this group the next segment starts */
-            for (int g = sg; g < gend; g++) {
-                const uint2 w = pay8[g];
-                uint32_t bm = 0;
-                walk4(w.x, r, bm, 0);
-                walk4(w.y, r, bm, 4);
-                bits8[g] = (uint8_t)bm;
-                if (g == gcarry) sh.carry = r;
-            }
+            __syncthreads();
         }
-        __syncthreads();
+        if (more) {
+            /* the state the next segment starts in; the look-ahead behind this one */
+            if (tid == SY_THREADS - 1) {
+                sh.carry = r_out;
+                walk_groups<true>(pay8, bits8, SY_THREADS * G, gtot, r_out);
+            }
+            __syncthreads();
+        }
 
         /* ---- count: blocks that start before every word of the bit map ---- */
         {
@@ -348,11 +347,18 @@ rtj_scan_sync_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc
         int myskips = 0, lastend = -1;
         for (int lo = 0; lo < nemit; lo += SY_STAGE) {
             const int n = min(SY_STAGE, nemit - lo);
-            for (int w = tid; w < wtot; w += SY_THREADS) {
-                int idx = (int)sh.pre[w] - lo;
-                if (idx > n || (int)sh.pre[w + 1] - lo <= 0) continue;
-                uint32_t v = sy_mask(sh.bits[w], w, first, climit);
-                while (v) {
+            {
+                /* one start per turn of the loop, words taken in turn: lanes stay busy whatever their words hold */
+                int w = tid - SY_THREADS, idx = 0;
+                uint32_t v = 0;
+                for (;;) {
+                    if (v == 0u) {
+                        w += SY_THREADS;
+                        if (w >= wtot) break;
+                        idx = (int)sh.pre[w] - lo;
+                        if (idx <= n && (int)sh.pre[w + 1] - lo > 0) v = sy_mask(sh.bits[w], w, first, climit);
+                        continue;
+                    }
                     const int b = __ffs((int)v) - 1;
                     v &= v - 1u;
                     if ((unsigned)idx <= (unsigned)n) sh.starts[idx] = (uint16_t)(w * 32 + b);

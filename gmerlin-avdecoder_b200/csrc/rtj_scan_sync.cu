@@ -50,26 +50,21 @@ namespace {
 constexpr unsigned FULL = 0xFFFFFFFFu;
 constexpr int SY_THREADS = 64;
 constexpr int SY_WARPS = SY_THREADS / 32;
-constexpr int SY_GMAX = 79;                                /* 8-byte groups per chunk: odd */
-constexpr int SY_LEAD = 32;                                /* groups of the lead-in walk in front of a chunk (256 bytes) */
-constexpr int SY_GMIN = SY_LEAD + 1;                       /* short frames use fewer lanes, not shorter chunks */
-constexpr int SY_SEG_MAX = SY_THREADS * SY_GMAX * 8;       /* bytes of a frame in shared memory at a time */
+constexpr int SY_LEAD = 16;                                /* 16-byte pieces of the lead-in walk in front of a chunk (256 bytes) */
+constexpr int SY_PMIN = SY_LEAD + 2;                       /* pieces per chunk at least (even): short frames use fewer lanes, not shorter chunks */
+constexpr int SY_PMAX = 40;                                /* ... at most (even): a chunk's bit map is whole 32-bit words */
+constexpr int SY_SEG_MAX = SY_THREADS * SY_PMAX * 16;      /* bytes of a frame worked on at a time */
 constexpr int SY_LA = 80;                                  /* bytes walked behind a segment that is not the frame's last: the block that
-                                                            * starts on its last byte (<= 64 bytes) and the start behind it, whole groups */
-constexpr int SY_PAY_BYTES = SY_SEG_MAX + SY_LA + 16;      /* + what an unaligned 8-byte read may touch */
-constexpr int SY_WORDS = (SY_SEG_MAX + SY_LA + 31) / 32;   /* bit map words */
-constexpr int SY_STAGE = 3072;                             /* block starts staged per emit round */
-constexpr int SY_KMAX = (SY_WORDS + SY_THREADS - 1) / SY_THREADS;
+                                                            * starts on its last byte (<= 64 bytes) and the start behind it, whole pieces */
+constexpr int SY_WORDS = (SY_SEG_MAX + SY_LA + 31) / 32 + 1;   /* bit map words */
+constexpr int SY_STAGE = 10240;                            /* block starts staged per emit round */
 constexpr int SY_MAX_DIRTY = 8;                            /* more chunks than this entered in the wrong state: not this kernel's stream */
 
-static_assert((SY_GMAX & 1) == 1 && (SY_GMIN & 1) == 1, "odd chunk lengths: conflict-free 8-byte reads");
-static_assert(SY_SEG_MAX + SY_LA < 65536, "positions inside a segment are 16 bit");
-static_assert((SY_PAY_BYTES % 16) == 0, "bulk copies move 16-byte pieces");
+static_assert((SY_PMAX & 1) == 0 && (SY_PMIN & 1) == 0, "a chunk's bit map is whole 32-bit words");
+static_assert(SY_SEG_MAX + SY_LA + 16 < 65536, "positions inside a segment are 16 bit");
 
 struct SyShared {
-    alignas(16) uint32_t pay[SY_PAY_BYTES / 4];      /* the segment's bytes: pay[0] is the 16-byte line the frame's payload starts in */
-    uint32_t bits[SY_WORDS + 1];         /* bit p: a block starts at byte p of the segment */
-    uint16_t pre[SY_WORDS + 2];          /* blocks that start before word w's 32 positions */
+    uint32_t bits[SY_WORDS];             /* bit p: a block starts at byte p of the segment */
     uint16_t starts[SY_STAGE + 2];       /* one emit round's block starts */
     int8_t   exitst[SY_THREADS];         /* the state every lane's walk left its chunk in */
     int      wsum[SY_WARPS];
@@ -77,35 +72,8 @@ struct SyShared {
     int      nb;                         /* blocks started so far in this frame */
     int      skips;
     int      consumed;
-    int      total;                      /* block starts in this segment */
-    int      sentinel;                   /* first block start behind them */
-    alignas(8) unsigned long long mbar;
+    int      sentinel;                   /* first block start behind the segment's blocks */
 };
-static_assert(offsetof(SyShared, pay) == 0, "bulk copies and 16-byte stores: the payload leads the (16-byte aligned) block");
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t mbar, unsigned count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(mbar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, unsigned bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mbar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t mbar, unsigned parity)
-{
-    unsigned done;
-    do {
-        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                     : "=r"(done) : "r"(mbar), "r"(parity) : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, unsigned bytes, uint32_t mbar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 :: "r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
-}
 
 /* byte k of w, sign-extended (prmt: a selector nibble's top bit replicates the chosen byte's sign) */
 template <int K>
@@ -145,39 +113,67 @@ __device__ __forceinline__ void walk4(uint32_t W, int &r, uint32_t &bm, int bit0
 #undef SY_STEP
 }
 
-/* groups [g0, g1) from state r; BITS: leave the starts in the bit map */
-template <bool BITS>
-__device__ __forceinline__ int walk_groups(const uint2 *pay8, uint8_t *bits8, int g0, int g1, int r)
+/* What the walks read: the segment's 16-byte pieces straight from the packet (a lane's pieces lie in a row, so each 128-byte
+ * line is fetched once and then lives in L1 for the lane's next seven reads).  Bytes behind the payload read 0x7F, a run token
+ * that ends any block; the bytes in front of it (the payload starts 0..12 bytes into its first piece) read 0xFF, "skip
+ * markers" whose starts do not count.  The packet's own memory is never read past its last 16-byte line. */
+struct SySeg {
+    const uint4 *src;        /* piece 0 */
+    int lim;                 /* the payload ends at byte lim of the segment */
+    int first;               /* ... and starts at byte first (0 but for the frame's first segment) */
+};
+__device__ __forceinline__ uint32_t sy_fix_word(uint32_t w, int at, int lim, int first)      /* at: byte position of the word */
 {
-    for (int g = g0; g < g1; g++) {
-        const uint2 w = pay8[g];
+    if (at + 4 > lim) {
+        const int nv = lim - at;
+        const uint32_t m = nv <= 0 ? 0u : (1u << (8 * nv)) - 1u;
+        w = (w & m) | (0x7F7F7F7Fu & ~m);
+    }
+    if (at < first) {
+        const int nf = first - at;
+        const uint32_t m = nf >= 4 ? 0xFFFFFFFFu : (1u << (8 * nf)) - 1u;
+        w |= m;
+    }
+    return w;
+}
+__device__ __forceinline__ uint4 sy_piece(const SySeg &sg, int i)
+{
+    const int at = i * 16;
+    uint4 w = make_uint4(0x7F7F7F7Fu, 0x7F7F7F7Fu, 0x7F7F7F7Fu, 0x7F7F7F7Fu);
+    if (at < sg.lim) {
+        w = __ldg(sg.src + i);
+        if (at + 16 > sg.lim || at < sg.first) {
+            w.x = sy_fix_word(w.x, at, sg.lim, sg.first);
+            w.y = sy_fix_word(w.y, at + 4, sg.lim, sg.first);
+            w.z = sy_fix_word(w.z, at + 8, sg.lim, sg.first);
+            w.w = sy_fix_word(w.w, at + 12, sg.lim, sg.first);
+        }
+    }
+    return w;
+}
+
+/* pieces [p0, p1) from state r; BITS: leave the starts in the bit map */
+template <bool BITS>
+__device__ __forceinline__ int walk_pieces(const SySeg &sg, uint16_t *bits16, int p0, int p1, int r)
+{
+    if (p0 >= p1) return r;
+    uint4 cur = sy_piece(sg, p0);
+    for (int i = p0; i < p1; i++) {
+        const uint4 nxt = sy_piece(sg, min(i + 1, p1 - 1));            /* asked for one piece ahead of its use */
         uint32_t bm = 0;
-        walk4<BITS>(w.x, r, bm, 0);
-        walk4<BITS>(w.y, r, bm, 4);
-        if (BITS) bits8[g] = (uint8_t)bm;
+        walk4<BITS>(cur.x, r, bm, 0);
+        walk4<BITS>(cur.y, r, bm, 4);
+        walk4<BITS>(cur.z, r, bm, 8);
+        walk4<BITS>(cur.w, r, bm, 12);
+        if (BITS) bits16[i] = (uint16_t)bm;
+        cur = nxt;
     }
     return r;
 }
 
-__device__ __forceinline__ uint32_t lds_u32_unaligned(const uint32_t *w, int byte)
-{
-    const uint32_t *p = w + (byte >> 2);
-    return __funnelshift_r(p[0], p[1], (unsigned)(byte & 3) * 8);
-}
-
-/* the starts of word w that count: positions [first, limit) of the segment */
-__device__ __forceinline__ uint32_t sy_mask(uint32_t v, int w, int first, int limit)
-{
-    if (w == 0) v &= ~((1u << first) - 1u);                              /* first <= 12 */
-    const int wc = limit >> 5;
-    if (w > wc) v = 0u;
-    else if (w == wc) v &= (1u << (limit & 31)) - 1u;
-    return v;
-}
-
 } // namespace
 
-__global__ void __launch_bounds__(SY_THREADS, 4)
+__global__ void __launch_bounds__(SY_THREADS, 8)
 rtj_scan_sync_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc *__restrict__ desc,
                      const rtj_dev_table *__restrict__ tables, int F, int nblk,
                      uint32_t *__restrict__ ent, uint32_t *__restrict__ frame_skips,
@@ -200,69 +196,44 @@ rtj_scan_sync_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc
     const int mis = (int)(reinterpret_cast<uintptr_t>(pay) & 15);     /* 0, 4, 8 or 12: packets start 4-byte aligned */
     const uint8_t *gbase = pay - mis;                                   /* 16-byte aligned, never before the packet */
     uint32_t *out = ent + (size_t)f * nblk;
-    const uint8_t *payb = reinterpret_cast<const uint8_t *>(sh.pay);
-    uint8_t *bits8 = reinterpret_cast<uint8_t *>(sh.bits);
+    uint16_t *bits16 = reinterpret_cast<uint16_t *>(sh.bits);
 
     /* positions: byte p of the frame is gbase[p]; the payload is [mis, end).  A frame that fits one segment leaves room for
      * the start behind its last block (end + 1 at most) inside the lanes' chunks. */
     const int end = len > 0 ? mis + len : 0;
-    const int G = end + 8 > SY_SEG_MAX ? SY_GMAX : max(SY_GMIN, ((end + 8 + SY_THREADS * 8 - 1) / (SY_THREADS * 8)) | 1);
-    const int SEG = SY_THREADS * G * 8;
-    const uint32_t mbar = smem_u32(&sh.mbar);
+    const int P = end + 8 > SY_SEG_MAX ? SY_PMAX : max(SY_PMIN, ((end + 8 + SY_THREADS * 32 - 1) / (SY_THREADS * 32)) * 2);
+    const int SEG = SY_THREADS * P * 16;
 
     if (tid == 0) {
         sh.carry = 0;
         sh.nb = 0;
         sh.skips = 0;
         sh.consumed = 0;
-        mbar_init(mbar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
-    unsigned parity = 0;
     for (int seg0 = 0; seg0 < end; seg0 += SEG) {
         const int nb0 = sh.nb;
         if (nb0 >= nblk) break;                                        /* uniform: everybody reads the same word */
-        const int lim = end - seg0;                                    /* the payload ends at byte lim of this segment */
-        const int first = seg0 == 0 ? mis : 0;
+        SySeg sg;
+        sg.src = reinterpret_cast<const uint4 *>(gbase + seg0);
+        sg.lim = end - seg0;
+        sg.first = seg0 == 0 ? mis : 0;
+        const int lim = sg.lim, first = sg.first;
         const int climit = min(SEG, lim);                              /* starts before it are this segment's blocks */
         const bool more = lim + 8 > SEG;                               /* the frame goes on behind this segment */
-        const int gtot = more ? (SEG + SY_LA) >> 3 : (lim + 8 + 7) >> 3;   /* groups to walk: up to the start behind the last block */
-        const int wtot = (gtot * 8 + 31) >> 5;                         /* bit map words they fill (the last one maybe in part) */
+        const int ptot = more ? (SEG + SY_LA) >> 4 : (lim + 8 + 15) >> 4;   /* pieces to walk: up to the start behind the last block */
 
-        /* ---- load: one bulk copy; what lies behind the payload reads 0x7F, a run token that ends any block (the packet's
-         *      own bytes are never read past its last 16-byte line) ---- */
-        const int nbuf = gtot * 8 + 16;
-        const int nload = min(nbuf & ~15, (lim + 15) & ~15);
-        if (tid == 0) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   /* the previous segment's reads are done (barrier below) */
-            mbar_expect_tx(mbar, (unsigned)nload);
-            bulk_g2s(smem_u32(sh.pay), gbase + seg0, (unsigned)nload, mbar);
-        }
-        for (int b = nload + tid * 16; b < nbuf; b += SY_THREADS * 16)
-            *reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(sh.pay) + b) = make_uint4(0x7F7F7F7Fu, 0x7F7F7F7Fu, 0x7F7F7F7Fu, 0x7F7F7F7Fu);
-        mbar_wait(mbar, parity);
-        parity ^= 1u;
-        if (tid < 16) {
-            uint8_t *pb = reinterpret_cast<uint8_t *>(sh.pay);
-            if (lim + tid < nload) pb[lim + tid] = 0x7F;               /* at most 15 bytes */
-            if (tid < first) pb[tid] = 0xFF;                           /* in front of the payload: "skip markers", whose starts do not count */
-        }
-        __syncthreads();
-
-        /* ---- lead-in: every lane walks the SY_LEAD groups in front of its chunk from a guessed state ("a block starts
+        /* ---- lead-in: every lane walks the SY_LEAD pieces in front of its chunk from a guessed state ("a block starts
          *      here").  Run-length streams forget their past within a handful of blocks: at the chunk's first byte the
          *      walk is, as a rule, in the true state.  Whether it is, is checked below -- never assumed. ---- */
-        const uint2 *pay8 = reinterpret_cast<const uint2 *>(sh.pay);
-        const int g0 = tid * G, g1 = min(g0 + G, gtot);                /* this lane's chunk, in groups */
+        const int p0 = tid * P, p1 = min(p0 + P, ptot);                /* this lane's chunk, in pieces */
         int r_in = 0;                                                  /* the state the chunk is entered in */
         if (tid == 0) r_in = seg0 == 0 ? 0 : sh.carry;
-        else if (g0 < gtot) r_in = walk_groups<false>(pay8, nullptr, g0 - SY_LEAD, g0, 0);
+        else if (p0 < ptot) r_in = walk_pieces<false>(sg, nullptr, p0 - SY_LEAD, p0, 0);
 
         /* ---- walk: the chunk, from that state; one bit per byte that starts a block ---- */
-        int r_out = r_in;
-        if (g0 < gtot) r_out = walk_groups<true>(pay8, bits8, g0, g1, r_in);
+        int r_out = walk_pieces<true>(sg, bits16, p0, p1, r_in);
         sh.exitst[tid] = (int8_t)r_out;
         __syncthreads();
 
@@ -272,7 +243,7 @@ rtj_scan_sync_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc
         for (int round = 0;; round++) {
             const int want = tid > 0 ? (int)sh.exitst[tid - 1] : r_in;
             /* states <= 0 all mean "a block starts here" */
-            const bool dirty = tid > 0 && g0 < gtot && max(want, 0) != max(r_in, 0);
+            const bool dirty = tid > 0 && p0 < ptot && max(want, 0) != max(r_in, 0);
             const int ndirty = __syncthreads_count(dirty);
             if (ndirty == 0) break;
             if (redo && round == 0 && ndirty > SY_MAX_DIRTY) {
@@ -282,28 +253,41 @@ rtj_scan_sync_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc
             }
             if (dirty) {
                 r_in = want;
-                r_out = walk_groups<true>(pay8, bits8, g0, g1, r_in);
+                r_out = walk_pieces<true>(sg, bits16, p0, p1, r_in);
                 sh.exitst[tid] = (int8_t)r_out;
             }
             __syncthreads();
         }
-        if (more) {
+        if (more && tid == SY_THREADS - 1) {
             /* the state the next segment starts in; the look-ahead behind this one */
-            if (tid == SY_THREADS - 1) {
-                sh.carry = r_out;
-                walk_groups<true>(pay8, bits8, SY_THREADS * G, gtot, r_out);
-            }
-            __syncthreads();
+            sh.carry = r_out;
+            walk_pieces<true>(sg, bits16, SY_THREADS * P, ptot, r_out);
         }
+        __syncthreads();
 
-        /* ---- count: blocks that start before every word of the bit map ---- */
+        /* ---- the first start at or behind climit is where the segment's last block ends; the starts that do not count
+         *      (in front of the payload, behind climit) leave the bit map ---- */
+        if (tid == 0) {
+            const int wend = (ptot * 16 + 31) >> 5;
+            int s = climit;
+            for (int w = climit >> 5; w < wend; w++) {
+                uint32_t v = sh.bits[w];
+                if (w == (climit >> 5)) v &= ~((1u << (climit & 31)) - 1u);
+                if (w == wend - 1 && ((ptot * 16) & 31)) v &= 0xFFFFu;
+                if (v) { s = w * 32 + __ffs((int)v) - 1; break; }
+            }
+            sh.sentinel = s;
+            sh.bits[0] &= ~((1u << first) - 1u);                                     /* first <= 12 */
+            for (int w = climit >> 5; w < wend; w++) sh.bits[w] = w == (climit >> 5) ? sh.bits[w] & ((1u << (climit & 31)) - 1u) : 0u;
+        }
+        __syncthreads();
+
+        /* ---- count: every lane the starts of its own chunk; a scan over the lanes ---- */
+        const int w0 = p0 >> 1, w1 = (min(p0 + P, ptot) + 1) >> 1;     /* the chunk's bit map words (P is even) */
+        int cnt = 0;
+        for (int w = w0; w < w1; w++) cnt += __popc(sh.bits[w]);
+        int base, total;
         {
-            const int K = (wtot + SY_THREADS - 1) / SY_THREADS;
-            const int w0 = tid * K;
-            int cnt = 0;
-#pragma unroll
-            for (int i = 0; i < SY_KMAX; i++)
-                if (i < K && w0 + i < wtot) cnt += __popc(sy_mask(sh.bits[w0 + i], w0 + i, first, climit));
             int incl = cnt;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -312,77 +296,80 @@ rtj_scan_sync_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc
             }
             if (lane == 31) sh.wsum[warp] = incl;
             __syncthreads();
-            int base = incl - cnt, total = 0;
+            base = incl - cnt;
+            total = 0;
 #pragma unroll
             for (int k = 0; k < SY_WARPS; k++) {
                 const int s = sh.wsum[k];
                 if (k < warp) base += s;
                 total += s;
             }
-#pragma unroll
-            for (int i = 0; i < SY_KMAX; i++)
-                if (i < K && w0 + i < wtot) {
-                    sh.pre[w0 + i] = (uint16_t)base;
-                    base += __popc(sy_mask(sh.bits[w0 + i], w0 + i, first, climit));
-                }
-            if (tid == 0) {
-                sh.pre[wtot] = (uint16_t)total;
-                sh.total = total;
-                /* the first start at or behind climit: where the segment's last block ends */
-                int s = climit;
-                for (int w = climit >> 5; w < wtot; w++) {
-                    uint32_t v = sh.bits[w];
-                    if (w == (climit >> 5)) v &= ~((1u << (climit & 31)) - 1u);
-                    if (w == wtot - 1 && ((gtot * 8) & 31)) v &= (1u << ((gtot * 8) & 31)) - 1u;
-                    if (v) { s = w * 32 + __ffs((int)v) - 1; break; }
-                }
-                sh.sentinel = s;
-            }
         }
-        __syncthreads();
 
-        /* ---- emit: the list of starts, round by round, then one block per thread ---- */
-        const int total = sh.total;
+        /* ---- emit: the list of starts (every lane its chunk's), then one block per thread ---- */
         const int nemit = min(total, nblk - nb0);
         int myskips = 0, lastend = -1;
+        const uint32_t *gw = reinterpret_cast<const uint32_t *>(gbase + seg0);
+        const uint8_t *gb = gbase + seg0;
         for (int lo = 0; lo < nemit; lo += SY_STAGE) {
             const int n = min(SY_STAGE, nemit - lo);
             {
-                /* one start per turn of the loop, words taken in turn: lanes stay busy whatever their words hold */
-                int w = tid - SY_THREADS, idx = 0;
+                /* One start per turn, the same instructions for every lane whatever its words hold (nothing to diverge on):
+                 * a lane out of bits takes its next word in the same turn.  Turns: the busiest lane's starts + words. */
+                const bool mine = base <= lo + n && base + cnt > lo;
+                int turns = mine ? cnt + (w1 - w0) : 0;
+#pragma unroll
+                for (int o = 16; o; o >>= 1) turns = max(turns, __shfl_xor_sync(FULL, turns, o));
+                int idx = base - lo, w = w0, pos0 = 0;
                 uint32_t v = 0;
-                for (;;) {
-                    if (v == 0u) {
-                        w += SY_THREADS;
-                        if (w >= wtot) break;
-                        idx = (int)sh.pre[w] - lo;
-                        if (idx <= n && (int)sh.pre[w + 1] - lo > 0) v = sy_mask(sh.bits[w], w, first, climit);
-                        continue;
-                    }
+                const uint32_t starts_s = (uint32_t)__cvta_generic_to_shared(sh.starts);
+                for (int t = 0; t < turns; t++) {
+                    const bool need = v == 0u;
+                    const uint32_t vn = sh.bits[min(w, w1 - 1 >= w0 ? w1 - 1 : w0)];
+                    if (need) { v = w < w1 ? vn : 0u; pos0 = w * 32; w++; }
                     const int b = __ffs((int)v) - 1;
+                    const bool ok = mine && v != 0u && (unsigned)idx <= (unsigned)n;
+                    asm volatile("{ .reg .pred p; setp.ne.u32 p, %0, 0; @p st.shared.u16 [%1], %2; }"
+                                 :: "r"((unsigned)ok), "r"(starts_s + 2u * (unsigned)max(idx, 0)), "h"((uint16_t)(pos0 + b)) : "memory");
+                    idx += v != 0u ? 1 : 0;
                     v &= v - 1u;
-                    if ((unsigned)idx <= (unsigned)n) sh.starts[idx] = (uint16_t)(w * 32 + b);
-                    idx++;
                 }
             }
             if (tid == 0 && lo + n == total) sh.starts[n] = (uint16_t)sh.sentinel;
             __syncthreads();
-            for (int k = tid; k < n; k += SY_THREADS) {
-                const int qq = sh.starts[k], nx = sh.starts[k + 1];
-                const int dl = nx - qq;
-                const uint32_t head = lds_u32_unaligned(sh.pay, qq);               /* DC, token 1, token 2, token 3 */
-                const uint32_t last = payb[nx - 1];
-                const bool isff = (head & 0xFFu) == 0xFFu;                         /* skipped block */
-                /* positions >= eob are zero: a final run of n zeros ends at 64, so it starts at 64 - n */
-                const int eob = (last - 64u) < 64u ? max(127 - (int)last, dl - 1) : 64;
-                const uint32_t t1 = (head >> 8) & 0xFFu, t2 = (head >> 16) & 0xFFu;
-                const uint32_t c1 = (eob >= 2 && (t1 - 64u) >= 64u) ? t1 : 0u;
-                const uint32_t c2 = (eob >= 3 && (t2 - 64u) >= 64u) ? t2 : 0u;
-                const uint32_t e_inl = RTJ_ENT_INLINE_BIT | (head & 0xFFu) | (c1 << 8) | (c2 << 16);
-                const uint32_t e_gen = RTJ_ENT(seg0 + qq - mis, eob);
-                out[nb0 + lo + k] = isff ? RTJ_ENT_SKIP : (eob <= 3 ? e_inl : e_gen);
-                myskips += isff ? 1 : 0;
-                lastend = max(lastend, seg0 + nx - mis);
+            /* two blocks a thread and turn: the loads of both are under way before either is used */
+            for (int k = tid; k < n; k += 2 * SY_THREADS) {
+                const int kb = min(k + SY_THREADS, n - 1);
+                const int qa = sh.starts[k], na = sh.starts[k + 1], qb = sh.starts[kb], nb_ = sh.starts[kb + 1];
+                const uint32_t *wa = gw + (qa >> 2), *wb = gw + (qb >> 2);
+                const uint32_t a0 = __ldg(wa), a1 = __ldg(wa + 1), b0 = __ldg(wb), b1 = __ldg(wb + 1);
+                const uint32_t la = __ldg(gb + na - 1), lb = __ldg(gb + nb_ - 1);
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int qq = h ? qb : qa, nx = h ? nb_ : na;
+                    uint32_t head = __funnelshift_r(h ? b0 : a0, h ? b1 : a1, (unsigned)(qq & 3) * 8);    /* DC, token 1, token 2, token 3 */
+                    uint32_t last = h ? lb : la;
+                    const int dl = nx - qq;
+                    if (qq + 4 > lim) {                                                 /* the payload's last bytes: 0x7F behind them */
+                        const uint32_t m = (1u << (8 * (lim - qq))) - 1u;               /* 1..3 bytes are the payload's */
+                        head = (head & m) | (0x7F7F7F7Fu & ~m);
+                    }
+                    if (nx > lim) last = 0x7Fu;                                        /* the last block, cut short */
+                    const bool isff = (head & 0xFFu) == 0xFFu;                         /* skipped block */
+                    /* positions >= eob are zero: a final run of n zeros ends at 64, so it starts at 64 - n */
+                    const int eob = (last - 64u) < 64u ? max(127 - (int)last, dl - 1) : 64;
+                    const uint32_t t1 = (head >> 8) & 0xFFu, t2 = (head >> 16) & 0xFFu;
+                    const uint32_t c1 = (eob >= 2 && (t1 - 64u) >= 64u) ? t1 : 0u;
+                    const uint32_t c2 = (eob >= 3 && (t2 - 64u) >= 64u) ? t2 : 0u;
+                    const uint32_t e_inl = RTJ_ENT_INLINE_BIT | (head & 0xFFu) | (c1 << 8) | (c2 << 16);
+                    const uint32_t e_gen = RTJ_ENT(seg0 + qq - mis, eob);
+                    const int kk = h ? k + SY_THREADS : k;
+                    if (kk < n) {
+                        out[nb0 + lo + kk] = isff ? RTJ_ENT_SKIP : (eob <= 3 ? e_inl : e_gen);
+                        myskips += isff ? 1 : 0;
+                        lastend = max(lastend, seg0 + nx - mis);
+                    }
+                }
             }
             __syncthreads();
         }

@@ -1,0 +1,137 @@
+"""K1, self-synchronising flavour (csrc/rtj_scan_sync.cu): the paths the general parity suite does not reach by itself --
+frames of several segments, streams whose parse does NOT synchronise (repair rounds when the flavour is forced, the
+hand-over to the chunk-parallel kernel under AUTO), and entry tables / counters identical to the chunk-parallel kernel's on
+damaged streams.  Pixels are checked against the reference (lib/RTjpeg.c compiled by oracle/Makefile)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+import gmerlin_avdecoder_b200 as g
+from gmerlin_avdecoder_b200 import capi
+from gmerlin_avdecoder_b200 import device as D
+from oracle import oracle as O
+from gpu_util import first_diff, gpu_decode
+from streams import clip, reference_frames
+
+pytestmark = pytest.mark.gpu
+
+
+def _ctx(mode):
+    c = g.BatchContext(0)
+    c.set_scan_mode(mode)
+    return c
+
+
+def _entries(ctx, s, o, w, h):
+    """rtjgpu_scan_device alone: the entry table as K1 leaves it, and the batch counters."""
+    desc, _ = g.plan(s, o)
+    b = D.upload(s, desc, w, h)
+    ctx.set_format(0)
+    ctx.scan_device(b.stream.data_ptr(), b.desc.data_ptr(), b.F, w, h, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    nblk = (w // 16) * (h // 16) * 6
+    ent = np.zeros(b.F * nblk, dtype=np.uint32)
+    L = g.load_library()
+    L.rtjgpu_get_entries.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    assert L.rtjgpu_get_entries(ctx._h, C.c_void_p(ent.ctypes.data), ent.size) == 0
+    bi = ctx.batch_info()
+    return ent.reshape(b.F, nblk), (bi.skipped_blocks, bi.payload_bytes, bi.bad_frames, bi.first_bad_frame)
+
+
+@pytest.mark.parametrize("kw", [dict(Q=128), dict(Q=128, key_rate=3, lm=2, cm=2), dict(Q=170, noise_y=12, noise_c=4)])
+def test_frames_of_several_segments(kw):
+    """1920x1088: 150 .. 400 KB of payload a frame, four to ten segments, the state carried from one to the next."""
+    assert O.have_ref()
+    kw = dict(kw)
+    Q = kw.pop("Q")
+    w, h, F = 1920, 1088, 3
+    s, o = clip(w, h, Q, F, **kw)
+    assert int(O.packet_sizes(s, o).min()) > 2 * 40960                   # three segments or more
+    want = reference_frames(s, o, w, h)
+    with _ctx(capi.SCAN_SYNC) as c:
+        got, _ = gpu_decode(c, s, o, w, h)
+        assert np.array_equal(got, want), first_diff(got, want, w, h)
+        assert c.batch_info().bad_frames == 0
+
+
+def _dense_packets(w, h, n, seed):
+    rng = np.random.default_rng(seed)
+    return [O.random_wellformed_packet(rng, w, h, 128, skip_prob=0.02, dense_prob=0.97, extreme=False) for _ in range(n)]
+
+
+def test_stream_that_does_not_synchronise_forced():
+    """Nearly every block is 64 coefficient bytes long: a walk entered in the wrong state stays wrong for whole chunks.  With
+    the flavour forced, the repair rounds must still arrive at the one true parse."""
+    assert O.have_ref()
+    w, h = 320, 240
+    pk = _dense_packets(w, h, 3, 5)
+    s, o = O.pack_packets(pk)
+    want = reference_frames(s, o, w, h)
+    with _ctx(capi.SCAN_SYNC) as c, _ctx(capi.SCAN_CHUNK) as k:
+        got, _ = gpu_decode(c, s, o, w, h)
+        assert np.array_equal(got, want), first_diff(got, want, w, h)
+        e1, i1 = _entries(c, s, o, w, h)
+        e2, i2 = _entries(k, s, o, w, h)
+        assert np.array_equal(e1, e2) and i1 == i2
+
+
+def test_stream_that_does_not_synchronise_is_handed_over_under_auto():
+    """AUTO with a batch large enough for one CTA per frame: frames whose chunks are entered in the wrong state too often go
+    to the chunk-parallel kernel, the others stay; pixels and counters as ever."""
+    assert O.have_ref()
+    w, h = 320, 240
+    dense = _dense_packets(w, h, 2, 9)
+    s0, o0 = clip(w, h, 128, 2, noise_y=6)
+    sizes = O.packet_sizes(s0, o0)
+    calm = [s0[int(o0[i]):int(o0[i]) + int(sizes[i])] for i in range(2)]
+    order = [dense[0], calm[0], dense[1], calm[1]] * 75                 # 300 frames: above AUTO's segment-parallel limit
+    s, o = O.pack_packets(order)
+    want4 = reference_frames(*O.pack_packets(order[:4]), w, h)
+    with _ctx(capi.SCAN_AUTO) as c:
+        got, _ = gpu_decode(c, s, o, w, h)
+        bi = c.batch_info()
+        assert bi.bad_frames == 0
+        assert bi.payload_bytes == sum(p.size - 12 for p in order)
+    # intra frames, no skip markers in the calm ones; the dense ones hold a few: compare frame by frame with its sequence's reference
+    seq = reference_frames(s, o, w, h)
+    assert np.array_equal(got, seq), first_diff(got, seq, w, h)
+    assert np.array_equal(seq[:4], want4)
+
+
+@pytest.mark.parametrize("cut", [1, 2, 3, 7, 64, 1000, -1, -2, -5, -63])
+def test_damaged_streams_same_entries_as_the_chunk_kernel(cut):
+    """A packet cut short (from the front: keep `cut` payload bytes; from the back: drop -cut bytes), followed by garbage
+    in the stream's slack: both kernels see the same blocks, flag the same frame and count the same bytes."""
+    w, h = 208, 112
+    s, o = clip(w, h, 128, 3, key_rate=2, lm=2, cm=2, noise_y=10)
+    sizes = O.packet_sizes(s, o)
+    n1 = int(sizes[1])
+    keep = 12 + cut if cut > 0 else n1 + cut
+    pk = [s[int(o[0]):int(o[0]) + int(sizes[0])], s[int(o[1]):int(o[1]) + keep].copy(), s[int(o[2]):int(o[2]) + int(sizes[2])]]
+    pk[1][0:4] = np.frombuffer(np.uint32(pk[1].size).tobytes(), dtype=np.uint8)
+    s2, o2 = O.pack_packets(pk, align=4)                                 # packets 4-byte aligned: every misalignment of the payload
+    with _ctx(capi.SCAN_SYNC) as c, _ctx(capi.SCAN_CHUNK) as k:
+        e1, i1 = _entries(c, s2, o2, w, h)
+        e2, i2 = _entries(k, s2, o2, w, h)
+    assert i1 == i2 and i1[2] == 1 and i1[3] == 1
+    assert np.array_equal(e1, e2)
+
+
+@pytest.mark.parametrize("align", [4, 16])
+def test_every_payload_misalignment_and_frame_size(align):
+    """Frames of very different sizes back to back (a one-macroblock frame next to a large one is not possible in one
+    batch: sizes vary through the content instead), packets at every 4-byte alignment: entries as the chunk kernel's."""
+    w, h = 352, 288
+    s, o = clip(w, h, 100, 9, key_rate=4, lm=1, cm=1, noise_y=14, noise_c=3)
+    sizes = O.packet_sizes(s, o)
+    pk = [s[int(o[i]):int(o[i]) + int(sizes[i])] for i in range(9)]
+    s2, o2 = O.pack_packets(pk, align=align)
+    with _ctx(capi.SCAN_SYNC) as c, _ctx(capi.SCAN_CHUNK) as k:
+        e1, i1 = _entries(c, s2, o2, w, h)
+        e2, i2 = _entries(k, s2, o2, w, h)
+        assert np.array_equal(e1, e2) and i1 == i2 and i1[2] == 0
+        got, _ = gpu_decode(c, s2, o2, w, h)
+    want = reference_frames(s2, o2, w, h)
+    assert np.array_equal(got, want), first_diff(got, want, w, h)

@@ -152,23 +152,48 @@ __device__ __forceinline__ uint4 sy_piece(const SySeg &sg, int i)
     return w;
 }
 
-/* pieces [p0, p1) from state r; BITS: leave the starts in the bit map */
+/* pieces [p0, p1) from state r; BITS: leave the starts in the bit map.  Pieces that lie wholly inside the payload -- all but
+ * the frame's first and last -- are read without a look at the payload's bounds, one piece ahead of their use. */
+template <bool BITS>
+__device__ __forceinline__ void walk16(const uint4 w, int &r, uint16_t *bits16, int i)
+{
+    uint32_t bm = 0;
+    walk4<BITS>(w.x, r, bm, 0);
+    walk4<BITS>(w.y, r, bm, 4);
+    walk4<BITS>(w.z, r, bm, 8);
+    walk4<BITS>(w.w, r, bm, 12);
+    if (BITS) bits16[i] = (uint16_t)bm;
+}
 template <bool BITS>
 __device__ __forceinline__ int walk_pieces(const SySeg &sg, uint16_t *bits16, int p0, int p1, int r)
 {
-    if (p0 >= p1) return r;
-    uint4 cur = sy_piece(sg, p0);
-    for (int i = p0; i < p1; i++) {
-        const uint4 nxt = sy_piece(sg, min(i + 1, p1 - 1));            /* asked for one piece ahead of its use */
-        uint32_t bm = 0;
-        walk4<BITS>(cur.x, r, bm, 0);
-        walk4<BITS>(cur.y, r, bm, 4);
-        walk4<BITS>(cur.z, r, bm, 8);
-        walk4<BITS>(cur.w, r, bm, 12);
-        if (BITS) bits16[i] = (uint16_t)bm;
-        cur = nxt;
+    int i = p0;
+    if (i < p1 && i == 0 && sg.first) { walk16<BITS>(sy_piece(sg, 0), r, bits16, 0); i = 1; }
+    const int pin = min(p1, sg.lim >> 4);
+    if (i < pin) {
+        uint4 cur = __ldg(sg.src + i);
+        for (; i < pin; i++) {
+            const uint4 nxt = __ldg(sg.src + min(i + 1, pin - 1));
+            walk16<BITS>(cur, r, bits16, i);
+            cur = nxt;
+        }
     }
+    for (; i < p1; i++) walk16<BITS>(sy_piece(sg, i), r, bits16, i);
     return r;
+}
+
+/* The 32-bit entry of a block (rtj_common.h): head = its first four bytes (DC, token 1, 2, 3), last = its last byte,
+ * dl = its length, off = its offset in the payload. */
+__device__ __forceinline__ uint32_t sy_entry(uint32_t head, uint32_t last, int dl, int off)
+{
+    /* positions >= eob are zero: a final run of n zeros ends at 64, so it starts at 64 - n */
+    const int eob = (last - 64u) < 64u ? max(127 - (int)last, dl - 1) : 64;
+    const uint32_t t1 = (head >> 8) & 0xFFu, t2 = (head >> 16) & 0xFFu;
+    const uint32_t c1 = (eob >= 2 && (t1 - 64u) >= 64u) ? t1 : 0u;
+    const uint32_t c2 = (eob >= 3 && (t2 - 64u) >= 64u) ? t2 : 0u;
+    const uint32_t e_inl = RTJ_ENT_INLINE_BIT | (head & 0xFFu) | (c1 << 8) | (c2 << 16);
+    const uint32_t e_gen = RTJ_ENT(off, eob);
+    return (head & 0xFFu) == 0xFFu ? RTJ_ENT_SKIP : (eob <= 3 ? e_inl : e_gen);      /* 0xFF: a skipped block */
 }
 
 } // namespace
@@ -320,17 +345,17 @@ rtj_scan_sync_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc
                 int turns = mine ? cnt + (w1 - w0) : 0;
 #pragma unroll
                 for (int o = 16; o; o >>= 1) turns = max(turns, __shfl_xor_sync(FULL, turns, o));
+                /* (a lane whose starts all lie outside this round never stores: its indices are out of [0, n]) */
                 int idx = base - lo, w = w0, pos0 = 0;
                 uint32_t v = 0;
                 const uint32_t starts_s = (uint32_t)__cvta_generic_to_shared(sh.starts);
                 for (int t = 0; t < turns; t++) {
-                    const bool need = v == 0u;
-                    const uint32_t vn = sh.bits[min(w, w1 - 1 >= w0 ? w1 - 1 : w0)];
-                    if (need) { v = w < w1 ? vn : 0u; pos0 = w * 32; w++; }
+                    const uint32_t vn = sh.bits[min(w, SY_WORDS - 1)];
+                    if (v == 0u) { v = w < w1 ? vn : 0u; pos0 = w * 32; w++; }
                     const int b = __ffs((int)v) - 1;
-                    const bool ok = mine && v != 0u && (unsigned)idx <= (unsigned)n;
+                    const bool ok = v != 0u && (unsigned)idx <= (unsigned)n;
                     asm volatile("{ .reg .pred p; setp.ne.u32 p, %0, 0; @p st.shared.u16 [%1], %2; }"
-                                 :: "r"((unsigned)ok), "r"(starts_s + 2u * (unsigned)max(idx, 0)), "h"((uint16_t)(pos0 + b)) : "memory");
+                                 :: "r"((unsigned)ok), "r"(starts_s + 2u * (unsigned)idx), "h"((uint16_t)(pos0 + b)) : "memory");
                     idx += v != 0u ? 1 : 0;
                     v &= v - 1u;
                 }
@@ -338,36 +363,41 @@ rtj_scan_sync_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc
             if (tid == 0 && lo + n == total) sh.starts[n] = (uint16_t)sh.sentinel;
             __syncthreads();
             /* two blocks a thread and turn: the loads of both are under way before either is used */
+            uint32_t *op = out + nb0 + lo;
             for (int k = tid; k < n; k += 2 * SY_THREADS) {
                 const int kb = min(k + SY_THREADS, n - 1);
                 const int qa = sh.starts[k], na = sh.starts[k + 1], qb = sh.starts[kb], nb_ = sh.starts[kb + 1];
                 const uint32_t *wa = gw + (qa >> 2), *wb = gw + (qb >> 2);
                 const uint32_t a0 = __ldg(wa), a1 = __ldg(wa + 1), b0 = __ldg(wb), b1 = __ldg(wb + 1);
                 const uint32_t la = __ldg(gb + na - 1), lb = __ldg(gb + nb_ - 1);
-#pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    const int qq = h ? qb : qa, nx = h ? nb_ : na;
-                    uint32_t head = __funnelshift_r(h ? b0 : a0, h ? b1 : a1, (unsigned)(qq & 3) * 8);    /* DC, token 1, token 2, token 3 */
-                    uint32_t last = h ? lb : la;
-                    const int dl = nx - qq;
-                    if (qq + 4 > lim) {                                                 /* the payload's last bytes: 0x7F behind them */
-                        const uint32_t m = (1u << (8 * (lim - qq))) - 1u;               /* 1..3 bytes are the payload's */
-                        head = (head & m) | (0x7F7F7F7Fu & ~m);
-                    }
-                    if (nx > lim) last = 0x7Fu;                                        /* the last block, cut short */
-                    const bool isff = (head & 0xFFu) == 0xFFu;                         /* skipped block */
-                    /* positions >= eob are zero: a final run of n zeros ends at 64, so it starts at 64 - n */
-                    const int eob = (last - 64u) < 64u ? max(127 - (int)last, dl - 1) : 64;
-                    const uint32_t t1 = (head >> 8) & 0xFFu, t2 = (head >> 16) & 0xFFu;
-                    const uint32_t c1 = (eob >= 2 && (t1 - 64u) >= 64u) ? t1 : 0u;
-                    const uint32_t c2 = (eob >= 3 && (t2 - 64u) >= 64u) ? t2 : 0u;
-                    const uint32_t e_inl = RTJ_ENT_INLINE_BIT | (head & 0xFFu) | (c1 << 8) | (c2 << 16);
-                    const uint32_t e_gen = RTJ_ENT(seg0 + qq - mis, eob);
-                    const int kk = h ? k + SY_THREADS : k;
-                    if (kk < n) {
-                        out[nb0 + lo + kk] = isff ? RTJ_ENT_SKIP : (eob <= 3 ? e_inl : e_gen);
-                        myskips += isff ? 1 : 0;
-                        lastend = max(lastend, seg0 + nx - mis);
+                const uint32_t ea = sy_entry(__funnelshift_r(a0, a1, (unsigned)(qa & 3) * 8), la, na - qa, seg0 + qa - mis);
+                const uint32_t eb = sy_entry(__funnelshift_r(b0, b1, (unsigned)(qb & 3) * 8), lb, nb_ - qb, seg0 + qb - mis);
+                op[k] = ea;
+                myskips += ea == RTJ_ENT_SKIP ? 1 : 0;
+                lastend = max(lastend, na);
+                if (k + SY_THREADS < n) {
+                    op[k + SY_THREADS] = eb;
+                    myskips += eb == RTJ_ENT_SKIP ? 1 : 0;
+                    lastend = max(lastend, nb_);
+                }
+            }
+            /* the payload's last bytes: a block that starts on one of the last three, or that is cut short, must see 0x7F
+             * behind the payload, not what follows the packet in memory -- at most the list's last four blocks */
+            if (lo + n == total && lim < climit + SY_LA) {
+                __syncthreads();
+                const int k = n - 1 - tid;
+                if (tid < 4 && k >= 0) {
+                    const int qq = sh.starts[k], nx = sh.starts[k + 1];
+                    if (qq + 4 > lim || nx > lim) {
+                        const uint32_t *wp = gw + (qq >> 2);
+                        uint32_t head = __funnelshift_r(__ldg(wp), __ldg(wp + 1), (unsigned)(qq & 3) * 8);
+                        uint32_t last = __ldg(gb + min(nx, lim) - 1);
+                        if (qq + 4 > lim) {
+                            const uint32_t m = (1u << (8 * (lim - qq))) - 1u;           /* 1..3 bytes are the payload's */
+                            head = (head & m) | (0x7F7F7F7Fu & ~m);
+                        }
+                        if (nx > lim) last = 0x7Fu;                                    /* the last block, cut short */
+                        op[k] = sy_entry(head, last, nx - qq, seg0 + qq - mis);
                     }
                 }
             }
@@ -381,7 +411,7 @@ rtj_scan_sync_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc
             }
             if (lane == 0) {
                 if (myskips) atomicAdd(&sh.skips, myskips);
-                if (lastend >= 0) atomicMax(&sh.consumed, lastend);
+                if (lastend >= 0) atomicMax(&sh.consumed, seg0 + lastend - mis);
             }
             if (tid == 0) sh.nb = nb0 + total;
         }

@@ -75,39 +75,30 @@ struct SyShared {
     int      sentinel;                   /* first block start behind the segment's blocks */
 };
 
-/* byte k of w, sign-extended (prmt: a selector nibble's top bit replicates the chosen byte's sign) */
-template <int K>
-__device__ __forceinline__ int sext_byte(uint32_t w)
-{
-    int d;
-    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(w), "r"(0u), "n"(0x8880 + 0x1111 * K));
-    return d;
-}
-template <int K>
-__device__ __forceinline__ int zext_byte(uint32_t w)
-{
-    int d;
-    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(w), "r"(0u), "n"(0x4440 + K));
-    return d;
-}
-
 /* One state over four bytes.  r > 0: places of the block still to fill; r <= 0: the next byte starts a block (a DC byte: 63
  * places behind it; the skip marker 0xFF: a block of its own).  A run token 01xxxxxx fills x + 1 places, any other byte one.
- * bm gets a bit for every byte that starts a block. */
-template <bool BITS>
-__device__ __forceinline__ void walk4(uint32_t W, int &r, uint32_t &bm, int bit0)
+ * bm gets a bit for every byte that starts a block.
+ *
+ * The kernel is bound by the ALU pipe (LOP3 / SHF / PRMT / ISETP / SEL: one warp instruction every two clocks), while the
+ * FMA pipe idles.  dp4a with a one-hot second operand picks a byte out of a word AND adds it to the state in one
+ * instruction of the FMA pipe (measured, tools/pipe_rates2.cu: 0.5 / clock, pairs 1:1 with LOP3): the per-byte step is
+ * two of them, one compare and one select. */
+template <bool BITS, int bit0>
+__device__ __forceinline__ void walk4(uint32_t W, int &r, uint32_t &bm)
 {
     const uint32_t runs = W & ~(W >> 1) & 0x40404040u;                   /* bit 6 of every run token */
     const uint32_t NX = ~(W & (runs - (runs >> 6)));                     /* per byte, as a signed byte: -(what it fills) */
     const uint32_t y = ~W;
     const uint32_t z = ~((y & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) & W & 0x80808080u;   /* bit 7 of every byte that is 0xFF */
     const uint32_t G = 0x3F3F3F3Fu & ~(z - (z >> 7));                    /* the state behind a block's first byte: 63, or 0 behind a skip marker */
-#define SY_STEP(k)                                                     \
-    {                                                                  \
-        const int nx = sext_byte<k>(NX), g = zext_byte<k>(G);          \
-        const bool at = r <= 0;                                        \
-        r = at ? g : r + nx;                                           \
-        if (BITS && at) bm |= 1u << (bit0 + k);                        \
+#define SY_STEP(k)                                                                                   \
+    {                                                                                                \
+        int t, g;                                                                                    \
+        asm("dp4a.s32.u32 %0, %1, %2, %3;" : "=r"(t) : "r"(NX), "r"(1u << (8 * k)), "r"(r));         \
+        asm("dp4a.u32.u32 %0, %1, %2, %3;" : "=r"(g) : "r"(G), "r"(1u << (8 * k)), "r"(0));          \
+        const bool at = r <= 0;                                                                      \
+        r = at ? g : t;                                                                              \
+        if (BITS) asm("{ .reg .pred p; setp.ne.u32 p, %1, 0; @p add.u32 %0, %0, %2; }" : "+r"(bm) : "r"((unsigned)at), "n"(1u << (bit0 + k))); \
     }
     SY_STEP(0) SY_STEP(1) SY_STEP(2) SY_STEP(3)
 #undef SY_STEP
@@ -158,10 +149,10 @@ template <bool BITS>
 __device__ __forceinline__ void walk16(const uint4 w, int &r, uint16_t *bits16, int i)
 {
     uint32_t bm = 0;
-    walk4<BITS>(w.x, r, bm, 0);
-    walk4<BITS>(w.y, r, bm, 4);
-    walk4<BITS>(w.z, r, bm, 8);
-    walk4<BITS>(w.w, r, bm, 12);
+    walk4<BITS, 0>(w.x, r, bm);
+    walk4<BITS, 4>(w.y, r, bm);
+    walk4<BITS, 8>(w.z, r, bm);
+    walk4<BITS, 12>(w.w, r, bm);
     if (BITS) bits16[i] = (uint16_t)bm;
 }
 template <bool BITS>

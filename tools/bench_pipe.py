@@ -32,7 +32,7 @@ def main():
              ]
     for sl in (576, 1184, 2048):
         for prio in (0, 1):
-            cases.append((f"frame slices {sl} prio={prio}", dict(RTJPEG_B200_SLICE=str(sl), RTJPEG_B200_SCAN_PRIO=str(prio))))
+            cases.append((f"frame slices {sl} prio={prio}", dict(RTJPEG_B200_PIPELINE="2", RTJPEG_B200_SLICE=str(sl), RTJPEG_B200_SCAN_PRIO=str(prio))))
     for name, env in cases:
         for k in ("RTJPEG_B200_PIPELINE", "RTJPEG_B200_SLICE", "RTJPEG_B200_SLICE0", "RTJPEG_B200_SCAN_PRIO",
                   "RTJPEG_B200_WALK_MIN", "RTJPEG_B200_WALK_SLICES", "RTJPEG_B200_WALK_THREADS", "RTJPEG_B200_WALK_EXCLUSIVE"):

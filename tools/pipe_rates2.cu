@@ -10,6 +10,9 @@
 #define MNX(x,y)  asm volatile("max.s32 %0, %0, %1;" : "+r"(x) : "r"(y));
 #define SHL(x,y)  asm volatile("shl.b32 %0, %0, 1;" : "+r"(x));
 #define BFE(x,y)  asm volatile("bfe.u32 %0, %0, 3, 9;" : "+r"(x));
+#define DP4(x,y)  asm volatile("dp4a.s32.u32 %0, %1, %2, %0;" : "+r"(x) : "r"(y), "r"(m));
+#define SETSEL(x,y) asm volatile("{ .reg .pred p; setp.le.s32 p, %0, 0; selp.u32 %0, %1, %0, p; }" : "+r"(x) : "r"(y));
+#define POPC(x,y) asm volatile("popc.b32 %0, %0;" : "+r"(x));
 #define VMX(x,y)  asm volatile("vmax2.s32.s32.s32 %0, %0, %1, %2;" : "+r"(x) : "r"(y), "r"(m));
 template <int MODE>
 __global__ void k(unsigned *out, int iters, unsigned seed)
@@ -29,6 +32,11 @@ __global__ void k(unsigned *out, int iters, unsigned seed)
             if (MODE == 6) { LOP(a0,a1) MAD(a1,a2) LOP(a2,a3) MAD(a3,a4) LOP(a4,a5) MAD(a5,a6) LOP(a6,a7) MAD(a7,a0) }
             if (MODE == 7) { LOP(a0,a1) ADD(a1,a2) SHF(a2,a3) PRM(a3,a4) LOP(a4,a5) ADD(a5,a6) SHF(a6,a7) PRM(a7,a0) }
             if (MODE == 8) { REP8(SHL) }
+            if (MODE == 10) { REP8(DP4) }
+            if (MODE == 11) { LOP(a0,a1) DP4(a1,a2) LOP(a2,a3) DP4(a3,a4) LOP(a4,a5) DP4(a5,a6) LOP(a6,a7) DP4(a7,a0) }
+            if (MODE == 12) { MAD(a0,a1) DP4(a1,a2) MAD(a2,a3) DP4(a3,a4) MAD(a4,a5) DP4(a5,a6) MAD(a6,a7) DP4(a7,a0) }
+            if (MODE == 13) { REP8(SETSEL) }
+            if (MODE == 14) { REP8(POPC) }
             if (MODE == 9) { LOP(a0,a1) LOP(a1,a2) MAD(a2,a3) LOP(a3,a4) LOP(a4,a5) MAD(a5,a6) LOP(a6,a7) LOP(a7,a0) }
         }
     }
@@ -53,5 +61,6 @@ int main()
 {
     run<0>("LOP3"); run<1>("SHF"); run<2>("PRMT"); run<3>("add.u32"); run<4>("mad.lo (IMAD)"); run<5>("max.s32");
     run<6>("LOP3:IMAD 1:1"); run<7>("LOP3/ADD/SHF/PRMT"); run<8>("shl imm"); run<9>("LOP3:IMAD 3:1");
+    run<10>("dp4a (IDP.4A)"); run<11>("LOP3:dp4a 1:1"); run<12>("IMAD:dp4a 1:1"); run<13>("setp+selp pair (counted as 1)"); run<14>("popc");
     return 0;
 }

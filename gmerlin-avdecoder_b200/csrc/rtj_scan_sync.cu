@@ -353,23 +353,34 @@ rtj_scan_sync_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc
             }
             if (tid == 0 && lo + n == total) sh.starts[n] = (uint16_t)sh.sentinel;
             __syncthreads();
-            /* two blocks a thread and turn: the loads of both are under way before either is used */
+            /* four blocks a thread and turn: the loads of all four are under way before any is used (the payload comes
+             * from L2 by now: several hundred clocks) */
             uint32_t *op = out + nb0 + lo;
-            for (int k = tid; k < n; k += 2 * SY_THREADS) {
-                const int kb = min(k + SY_THREADS, n - 1);
-                const int qa = sh.starts[k], na = sh.starts[k + 1], qb = sh.starts[kb], nb_ = sh.starts[kb + 1];
-                const uint32_t *wa = gw + (qa >> 2), *wb = gw + (qb >> 2);
-                const uint32_t a0 = __ldg(wa), a1 = __ldg(wa + 1), b0 = __ldg(wb), b1 = __ldg(wb + 1);
-                const uint32_t la = __ldg(gb + na - 1), lb = __ldg(gb + nb_ - 1);
-                const uint32_t ea = sy_entry(__funnelshift_r(a0, a1, (unsigned)(qa & 3) * 8), la, na - qa, seg0 + qa - mis);
-                const uint32_t eb = sy_entry(__funnelshift_r(b0, b1, (unsigned)(qb & 3) * 8), lb, nb_ - qb, seg0 + qb - mis);
-                op[k] = ea;
-                myskips += ea == RTJ_ENT_SKIP ? 1 : 0;
-                lastend = max(lastend, na);
-                if (k + SY_THREADS < n) {
-                    op[k + SY_THREADS] = eb;
-                    myskips += eb == RTJ_ENT_SKIP ? 1 : 0;
-                    lastend = max(lastend, nb_);
+            constexpr int U = 4;
+            for (int k = tid; k < n; k += U * SY_THREADS) {
+                int qq[U], nx[U];
+                uint32_t h0[U], h1[U], lb[U];
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    const int ku = min(k + u * SY_THREADS, n - 1);
+                    qq[u] = sh.starts[ku];
+                    nx[u] = sh.starts[ku + 1];
+                }
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    const uint32_t *wp = gw + (qq[u] >> 2);
+                    h0[u] = __ldg(wp);
+                    h1[u] = __ldg(wp + 1);
+                    lb[u] = __ldg(gb + nx[u] - 1);
+                }
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    const uint32_t e = sy_entry(__funnelshift_r(h0[u], h1[u], (unsigned)(qq[u] & 3) * 8), lb[u], nx[u] - qq[u], seg0 + qq[u] - mis);
+                    if (k + u * SY_THREADS < n) {
+                        op[k + u * SY_THREADS] = e;
+                        myskips += e == RTJ_ENT_SKIP ? 1 : 0;
+                        lastend = max(lastend, nx[u]);
+                    }
                 }
             }
             /* the payload's last bytes: a block that starts on one of the last three, or that is cut short, must see 0x7F

@@ -148,7 +148,10 @@ int ws_reserve(rtjgpu_ctx *ctx, Workspace *ws, int F, int nblk)
     if (nblk > ws->k3_carry_cap) {
         if (ws->d_k3_carry) cudaFree(ws->d_k3_carry);
         ws->d_k3_carry = nullptr; ws->k3_carry_cap = 0;
-        CK(ctx, cudaMalloc(&ws->d_k3_carry, (size_t)2 * nblk * sizeof(uint16_t)));
+        /* ... and behind them K3's arrival counters, one per 128 positions (zero between launches: the last arrival resets its own) */
+        const size_t carry_bytes = ((size_t)2 * nblk * sizeof(uint16_t) + 15) & ~(size_t)15, count_bytes = ((size_t)nblk / 128 + 1) * sizeof(uint32_t);
+        CK(ctx, cudaMalloc(&ws->d_k3_carry, carry_bytes + count_bytes));
+        CK(ctx, cudaMemset(reinterpret_cast<uint8_t *>(ws->d_k3_carry) + carry_bytes, 0, count_bytes));
         ws->k3_carry_cap = nblk;
     }
     if (F > ws->cap_frames) {
@@ -330,6 +333,7 @@ int run_kernels(rtjgpu_ctx *ctx, Workspace *ws, const uint8_t *d_stream, const r
     a.d_ent = ws->d_ent; a.d_src = ws->d_src; a.d_frame_skips = ws->d_frame_skips; a.d_info = ws->d_info;
     a.d_hardq = ws->d_hardq; a.d_chunk_last = ws->d_chunk_last;
     a.d_k3_in = nullptr; a.d_k3_out = ws->d_k3_carry;
+    a.d_k3_count = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(ws->d_k3_carry) + (((size_t)2 * ws->k3_carry_cap * sizeof(uint16_t) + 15) & ~(size_t)15));
     a.d_out = d_out; a.d_carry = d_carry;
     a.d_rgb = rgb ? rgb->d_rgb : nullptr;
     a.rgb_row_pitch = rgb ? rgb->row_pitch : 0; a.rgb_frame_pitch = rgb ? rgb->frame_pitch : 0;

@@ -138,6 +138,7 @@ typedef struct rtj_launch_args {
     uint16_t                *d_chunk_last;  /* [ceil(F / 32)][nblk] K3: last writer inside each chunk of frames */
     const uint16_t          *d_k3_in;       /* [nblk] K3: last writer before this slice (NULL: the first slice) */
     uint16_t                *d_k3_out;      /* [nblk] K3: last writer before the next slice */
+    uint32_t                *d_k3_count;    /* [nblk / 128 + 1] K3: CTAs of rtj_resolve_last_kernel that are done with a group of positions */
     uint8_t                 *d_out;
     const uint8_t           *d_carry;
     const void              *d_lut;         /* K2: position table of this geometry (rtj_launch_build_lut) */

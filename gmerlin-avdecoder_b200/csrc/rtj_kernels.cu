@@ -26,6 +26,7 @@
  */
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "rtj_common.h"
 
@@ -342,24 +343,57 @@ __device__ __forceinline__ bool k3_any_skips(const rtj_dev_info *__restrict__ in
 
 extern "C" __global__ void __launch_bounds__(128)
 rtj_resolve_last_kernel(const uint32_t *__restrict__ ent, uint16_t *__restrict__ chunk_last, int f0, int f1, int nblk,
-                        const rtj_dev_info *__restrict__ info, int slice)
+                        const rtj_dev_info *__restrict__ info, int slice, uint32_t *__restrict__ arrived)
 {
     if (!k3_any_skips(info, slice)) return;          /* nothing to resolve so far */
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= nblk) return;
-    for (int c = f0 / RESOLVE_T + blockIdx.y; c * RESOLVE_T < f1; c += gridDim.y) {
-        const int fa = c * RESOLVE_T, fb = min(f1, fa + RESOLVE_T);
-        unsigned last = RTJ_SRC_CARRY;
-        uint32_t e[8];
-        int f = fa;
-        for (; f + 8 <= fb; f += 8) {
+    if (b < nblk)
+        for (int c = f0 / RESOLVE_T + blockIdx.y; c * RESOLVE_T < f1; c += gridDim.y) {
+            const int fa = c * RESOLVE_T, fb = min(f1, fa + RESOLVE_T);
+            unsigned last = RTJ_SRC_CARRY;
+            uint32_t e[8];
+            int f = fa;
+            for (; f + 8 <= fb; f += 8) {
 #pragma unroll
-            for (int j = 0; j < 8; j++) e[j] = ent[(size_t)(f + j) * nblk + b];
+                for (int j = 0; j < 8; j++) e[j] = ent[(size_t)(f + j) * nblk + b];
 #pragma unroll
-            for (int j = 0; j < 8; j++) if (!RTJ_ENT_IS_SKIP(e[j])) last = (unsigned)(f + j);
+                for (int j = 0; j < 8; j++) if (!RTJ_ENT_IS_SKIP(e[j])) last = (unsigned)(f + j);
+            }
+            for (; f < fb; f++) if (!RTJ_ENT_IS_SKIP(ent[(size_t)f * nblk + b])) last = (unsigned)f;
+            chunk_last[(size_t)c * nblk + b] = (uint16_t)last;
         }
-        for (; f < fb; f++) if (!RTJ_ENT_IS_SKIP(ent[(size_t)f * nblk + b])) last = (unsigned)f;
-        chunk_last[(size_t)c * nblk + b] = (uint16_t)last;
+    /* The CTA that arrives last for this group of positions turns chunk_last into a running maximum down the slice's chunks
+     * -- chunk_last[c] := the last writer in chunks c_lo .. c -- so that rtj_resolve_kernel finds its carry-in with ONE read
+     * however long nobody wrote a position (a static background: the look-back used to walk chunk by chunk, once per later
+     * chunk). */
+    __shared__ bool s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned n = atomicAdd(&arrived[blockIdx.x], 1u);
+        s_last = n == gridDim.y - 1;
+        if (s_last) arrived[blockIdx.x] = 0u;                /* ready for the next launch */
+    }
+    __syncthreads();
+    if (!s_last || b >= nblk) return;
+    __threadfence();
+    const int c_lo = f0 / RESOLVE_T, c_hi = (f1 + RESOLVE_T - 1) / RESOLVE_T;
+    unsigned run = RTJ_SRC_CARRY;
+    int c = c_lo;
+    for (; c + 8 <= c_hi; c += 8) {
+        unsigned v[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) v[j] = __ldcg(&chunk_last[(size_t)(c + j) * nblk + b]);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            if (v[j] != RTJ_SRC_CARRY) run = v[j];
+            chunk_last[(size_t)(c + j) * nblk + b] = (uint16_t)run;
+        }
+    }
+    for (; c < c_hi; c++) {
+        const unsigned v = __ldcg(&chunk_last[(size_t)c * nblk + b]);
+        if (v != RTJ_SRC_CARRY) run = v;
+        chunk_last[(size_t)c * nblk + b] = (uint16_t)run;
     }
 }
 
@@ -378,8 +412,7 @@ rtj_resolve_kernel(uint32_t *__restrict__ ent, const uint16_t *__restrict__ chun
     const int c_lo = f0 / RESOLVE_T;
     for (int c0 = c_lo + blockIdx.y; c0 * RESOLVE_T < f1; c0 += gridDim.y) {
         const int fa = c0 * RESOLVE_T, fb = min(f1, fa + RESOLVE_T);
-        unsigned last = RTJ_SRC_CARRY;
-        for (int c = c0 - 1; c >= c_lo && last == RTJ_SRC_CARRY; c--) last = chunk_last[(size_t)c * nblk + b];
+        unsigned last = c0 > c_lo ? chunk_last[(size_t)(c0 - 1) * nblk + b] : RTJ_SRC_CARRY;   /* rtj_resolve_last_kernel's running maximum */
         if (last == RTJ_SRC_CARRY && carry_in) last = carry_in[b];
         /* the last writer's entry, when it is an inline one (the block travels in it), and the tables it was written under:
          * a skipped block of a frame with the same tables gets a copy of it (RTJ_ENT_COPY_BIT) in the place of its marker */
@@ -641,8 +674,9 @@ extern "C" int rtj_launch_resolve(const rtj_launch_args *a, void *stream)
     /* a batch without skip markers only pays for the launches: keep the grid modest and let a CTA
      * stride over the chunks of frames */
     const int nchunks = (a->f1 - a->f0 + RESOLVE_T - 1) / RESOLVE_T;    /* f0 is a multiple of RESOLVE_T */
-    dim3 grid((unsigned)((nblk + 127) / 128), (unsigned)(nchunks < 16 ? nchunks : 16));
-    rtj_resolve_last_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(a->d_ent, a->d_chunk_last, a->f0, a->f1, nblk, a->d_info, a->slice);
+    static const int ymax = getenv("RTJPEG_B200_K3Y") ? atoi(getenv("RTJPEG_B200_K3Y")) : 32;
+    dim3 grid((unsigned)((nblk + 127) / 128), (unsigned)(nchunks < ymax ? nchunks : ymax));
+    rtj_resolve_last_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(a->d_ent, a->d_chunk_last, a->f0, a->f1, nblk, a->d_info, a->slice, a->d_k3_count);
     rtj_resolve_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(a->d_ent, a->d_chunk_last, a->d_src, a->f0, a->f1, nblk, a->d_info,
                                                                a->slice, a->d_k3_in, a->d_k3_out, a->d_desc);
     return (int)cudaGetLastError();

@@ -455,7 +455,7 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int32", "data": "synthetic",
             "config": config_dict(batch.payload_bytes / F, F),
-            "arrangement": "rtjgpu_set_pipeline AUTO: K1 of slice s+1 on a second stream beside K3 + K2 of slice s",
+            "arrangement": "rtjgpu_set_pipeline AUTO = serial: K1 (rtj_scan_sync_kernel, + the chunk kernel for frames it hands over), K3, K2, K2b one after the other on the caller's stream",
             "clocks": clocks,
             "gpu_launches": launches,
             "e2e": {"value": e2e_value, "unit": "frames/s", "steps": e2e_steps,
@@ -479,11 +479,12 @@ def main():
                 "int_issue_frac": {
                     "what": "warp instructions per launch (one committed ncu capture) / (592 SM sub-partitions x SM clock "
                             "x this run's kernel time): share of the issue slots used",
-                    "K1": issue_frac("rtj_scan_chunk_kernel", stage_ms["scan"]),
+                    "K1": issue_frac("rtj_scan_sync_kernel", stage_ms["scan"]),
                     "K2": issue_frac("rtj_idct_kernel", k2_ms),
                     "whole_path": (None if F != FRAMES or not facts.get("rtj_idct_kernel", {}).get("warp_instructions_per_launch_configs1")
+                                   or not facts.get("rtj_scan_sync_kernel", {}).get("warp_instructions_per_launch_configs1")
                                    else (facts["rtj_idct_kernel"]["warp_instructions_per_launch_configs1"]
-                                         + facts["rtj_scan_chunk_kernel"]["warp_instructions_per_launch_configs1"])
+                                         + facts["rtj_scan_sync_kernel"]["warp_instructions_per_launch_configs1"])
                                    / (SM_SUBPARTITIONS * sm_hz * ms_max / args.steps * 1e-3)),
                 },
             },

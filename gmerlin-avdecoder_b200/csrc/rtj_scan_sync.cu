@@ -156,20 +156,27 @@ __device__ __forceinline__ void walk16(const uint4 w, int &r, uint16_t *bits16, 
     if (BITS) bits16[i] = (uint16_t)bm;
 }
 template <bool BITS>
-__device__ __forceinline__ int walk_pieces(const SySeg &sg, uint16_t *bits16, int p0, int p1, int r)
+__device__ __noinline__ int walk_pieces(const SySeg sg, uint16_t *bits16, int p0, int p1, int r)
 {
+    constexpr int D = 4;                                               /* pieces on their way at any time */
     int i = p0;
     if (i < p1 && i == 0 && sg.first) { walk16<BITS>(sy_piece(sg, 0), r, bits16, 0); i = 1; }
     const int pin = min(p1, sg.lim >> 4);
-    if (i < pin) {
-        uint4 cur = __ldg(sg.src + i);
-        for (; i < pin; i++) {
-            const uint4 nxt = __ldg(sg.src + min(i + 1, pin - 1));
-            walk16<BITS>(cur, r, bits16, i);
-            cur = nxt;
+    if (i + D <= pin) {
+        /* a new sector comes from L2, several hundred clocks, and the walk of one piece takes about as long */
+        uint4 buf[D];
+#pragma unroll
+        for (int j = 0; j < D; j++) buf[j] = __ldg(sg.src + i + j);
+        for (; i + D <= pin; i += D) {
+#pragma unroll
+            for (int j = 0; j < D; j++) {
+                const uint4 cur = buf[j];
+                buf[j] = __ldg(sg.src + min(i + D + j, pin - 1));
+                walk16<BITS>(cur, r, bits16, i + j);
+            }
         }
     }
-    for (; i < p1; i++) walk16<BITS>(sy_piece(sg, i), r, bits16, i);
+    for (; i < p1; i++) walk16<BITS>(sy_piece(sg, i), r, bits16, i);     /* the last few, and what lies behind the payload */
     return r;
 }
 

@@ -25,6 +25,8 @@ struct Workspace {
     uint16_t     *d_src = nullptr;
     uint32_t     *d_hardq = nullptr;
     uint16_t     *d_chunk_last = nullptr;
+    uint32_t     *d_chunk_mask = nullptr;     /* (owns the allocation d_chunk_last points into) */
+    size_t        cap_chunk = 0;
     uint16_t     *d_k3_carry = nullptr;  int    k3_carry_cap = 0;    /* [2][nblk]: last writers handed from slice to slice */
     int2         *d_walk = nullptr;      int    walk_cap = 0;        /* [F]: where every frame's walker stands between slices */
     uint32_t     *d_frame_skips = nullptr;
@@ -137,14 +139,22 @@ int ws_reserve(rtjgpu_ctx *ctx, Workspace *ws, int F, int nblk)
         if (ws->d_ent) cudaFree(ws->d_ent);
         if (ws->d_src) cudaFree(ws->d_src);
         if (ws->d_hardq) cudaFree(ws->d_hardq);
-        if (ws->d_chunk_last) cudaFree(ws->d_chunk_last);
-        ws->d_ent = nullptr; ws->d_src = nullptr; ws->d_hardq = nullptr; ws->d_chunk_last = nullptr; ws->cap_entries = 0;
+        ws->d_ent = nullptr; ws->d_src = nullptr; ws->d_hardq = nullptr; ws->cap_entries = 0;
         CK(ctx, cudaMalloc(&ws->d_ent, need * sizeof(uint32_t)));
         CK(ctx, cudaMalloc(&ws->d_src, need * sizeof(uint16_t)));
         CK(ctx, cudaMalloc(&ws->d_hardq, need * 2 * sizeof(uint32_t)));       /* two words an entry: destination and source block */
-        CK(ctx, cudaMalloc(&ws->d_chunk_last, ((size_t)F / RTJ_RESOLVE_T + 1) * (size_t)nblk * sizeof(uint16_t)));
         ws->cap_entries = need;
     }
+    /* K3's per-chunk notes: a 32-bit skip mask and a 16-bit last writer per (chunk of frames, position), the masks first.
+     * (Sized on its own: few frames of a large picture need more of these than many frames of a small one.) */
+    const size_t nchunk = ((size_t)F / RTJ_RESOLVE_T + 1) * (size_t)nblk;
+    if (nchunk > ws->cap_chunk) {
+        if (ws->d_chunk_mask) cudaFree(ws->d_chunk_mask);
+        ws->d_chunk_mask = nullptr; ws->d_chunk_last = nullptr; ws->cap_chunk = 0;
+        CK(ctx, cudaMalloc(&ws->d_chunk_mask, nchunk * (sizeof(uint32_t) + sizeof(uint16_t))));
+        ws->cap_chunk = nchunk;
+    }
+    ws->d_chunk_last = reinterpret_cast<uint16_t *>(ws->d_chunk_mask + ws->cap_chunk);
     if (nblk > ws->k3_carry_cap) {
         if (ws->d_k3_carry) cudaFree(ws->d_k3_carry);
         ws->d_k3_carry = nullptr; ws->k3_carry_cap = 0;
@@ -238,7 +248,7 @@ void ws_release(Workspace *ws)
     if (ws->d_ent) cudaFree(ws->d_ent);
     if (ws->d_src) cudaFree(ws->d_src);
     if (ws->d_hardq) cudaFree(ws->d_hardq);
-    if (ws->d_chunk_last) cudaFree(ws->d_chunk_last);
+    if (ws->d_chunk_mask) cudaFree(ws->d_chunk_mask);
     if (ws->d_k3_carry) cudaFree(ws->d_k3_carry);
     if (ws->d_walk) cudaFree(ws->d_walk);
     if (ws->d_frame_skips) cudaFree(ws->d_frame_skips);
@@ -331,7 +341,7 @@ int run_kernels(rtjgpu_ctx *ctx, Workspace *ws, const uint8_t *d_stream, const r
     a.d_walk = ws->d_walk;
     a.d_redo = ws->d_frame_skips + ws->cap_frames;
     a.d_ent = ws->d_ent; a.d_src = ws->d_src; a.d_frame_skips = ws->d_frame_skips; a.d_info = ws->d_info;
-    a.d_hardq = ws->d_hardq; a.d_chunk_last = ws->d_chunk_last;
+    a.d_hardq = ws->d_hardq; a.d_chunk_last = ws->d_chunk_last; a.d_chunk_mask = ws->d_chunk_mask;
     a.d_k3_in = nullptr; a.d_k3_out = ws->d_k3_carry;
     a.d_k3_count = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(ws->d_k3_carry) + (((size_t)2 * ws->k3_carry_cap * sizeof(uint16_t) + 15) & ~(size_t)15));
     a.d_out = d_out; a.d_carry = d_carry;

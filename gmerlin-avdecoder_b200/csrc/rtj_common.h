@@ -136,6 +136,7 @@ typedef struct rtj_launch_args {
     rtj_dev_info            *d_info;
     uint32_t                *d_hardq;       /* [F * nblk][2] K2 -> K2b queue: destination block, source block (frame * nblk + block) */
     uint16_t                *d_chunk_last;  /* [ceil(F / 32)][nblk] K3: last writer inside each chunk of frames */
+    uint32_t                *d_chunk_mask;  /* [ceil(F / 32)][nblk] K3: which of the chunk's frames skipped the position */
     const uint16_t          *d_k3_in;       /* [nblk] K3: last writer before this slice (NULL: the first slice) */
     uint16_t                *d_k3_out;      /* [nblk] K3: last writer before the next slice */
     uint32_t                *d_k3_count;    /* [nblk / 128 + 1] K3: CTAs of rtj_resolve_last_kernel that are done with a group of positions */

@@ -342,8 +342,8 @@ __device__ __forceinline__ bool k3_any_skips(const rtj_dev_info *__restrict__ in
 }
 
 extern "C" __global__ void __launch_bounds__(128)
-rtj_resolve_last_kernel(const uint32_t *__restrict__ ent, uint16_t *__restrict__ chunk_last, int f0, int f1, int nblk,
-                        const rtj_dev_info *__restrict__ info, int slice, uint32_t *__restrict__ arrived)
+rtj_resolve_last_kernel(const uint32_t *__restrict__ ent, uint16_t *__restrict__ chunk_last, uint32_t *__restrict__ chunk_mask,
+                        int f0, int f1, int nblk, const rtj_dev_info *__restrict__ info, int slice, uint32_t *__restrict__ arrived)
 {
     if (!k3_any_skips(info, slice)) return;          /* nothing to resolve so far */
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -351,16 +351,24 @@ rtj_resolve_last_kernel(const uint32_t *__restrict__ ent, uint16_t *__restrict__
         for (int c = f0 / RESOLVE_T + blockIdx.y; c * RESOLVE_T < f1; c += gridDim.y) {
             const int fa = c * RESOLVE_T, fb = min(f1, fa + RESOLVE_T);
             unsigned last = RTJ_SRC_CARRY;
+            uint32_t skipped = 0;                            /* bit j: frame fa + j skipped the position -- rtj_resolve_kernel reads only the others */
             uint32_t e[8];
             int f = fa;
             for (; f + 8 <= fb; f += 8) {
 #pragma unroll
                 for (int j = 0; j < 8; j++) e[j] = ent[(size_t)(f + j) * nblk + b];
 #pragma unroll
-                for (int j = 0; j < 8; j++) if (!RTJ_ENT_IS_SKIP(e[j])) last = (unsigned)(f + j);
+                for (int j = 0; j < 8; j++) {
+                    if (!RTJ_ENT_IS_SKIP(e[j])) last = (unsigned)(f + j);
+                    else skipped |= 1u << (f + j - fa);
+                }
             }
-            for (; f < fb; f++) if (!RTJ_ENT_IS_SKIP(ent[(size_t)f * nblk + b])) last = (unsigned)f;
+            for (; f < fb; f++) {
+                if (!RTJ_ENT_IS_SKIP(ent[(size_t)f * nblk + b])) last = (unsigned)f;
+                else skipped |= 1u << (f - fa);
+            }
             chunk_last[(size_t)c * nblk + b] = (uint16_t)last;
+            chunk_mask[(size_t)c * nblk + b] = skipped;
         }
     /* The CTA that arrives last for this group of positions turns chunk_last into a running maximum down the slice's chunks
      * -- chunk_last[c] := the last writer in chunks c_lo .. c -- so that rtj_resolve_kernel finds its carry-in with ONE read
@@ -398,7 +406,7 @@ rtj_resolve_last_kernel(const uint32_t *__restrict__ ent, uint16_t *__restrict__
 }
 
 extern "C" __global__ void __launch_bounds__(128)
-rtj_resolve_kernel(uint32_t *__restrict__ ent, const uint16_t *__restrict__ chunk_last,
+rtj_resolve_kernel(uint32_t *__restrict__ ent, const uint16_t *__restrict__ chunk_last, const uint32_t *__restrict__ chunk_mask,
                    uint16_t *__restrict__ src, int f0, int f1, int nblk, const rtj_dev_info *__restrict__ info, int slice,
                    const uint16_t *__restrict__ carry_in, uint16_t *__restrict__ carry_out,
                    const rtjgpu_frame_desc *__restrict__ desc)
@@ -422,17 +430,24 @@ rtj_resolve_kernel(uint32_t *__restrict__ ent, const uint16_t *__restrict__ chun
             const uint32_t e = ent[(size_t)last * nblk + b];
             if (RTJ_ENT_IS_INLINE(e)) { last_e = e | RTJ_ENT_COPY_BIT; last_tab = desc[last].table; }
         }
+        /* skipped blocks are known from the first pass's mask: only the coded entries are read.  A skipped block gets a copy of
+         * its last writer's inline entry, or -- where there is none to copy -- its last writer's frame in src[] (K2 looks there
+         * only for entries that are still skip markers). */
+        const uint32_t skipped = chunk_mask[(size_t)c0 * nblk + b];
         uint32_t e[8];
         unsigned tab[8];
         int f = fa;
         for (; f + 8 <= fb; f += 8) {
 #pragma unroll
-            for (int j = 0; j < 8; j++) { e[j] = ent[(size_t)(f + j) * nblk + b]; tab[j] = desc[f + j].table; }
+            for (int j = 0; j < 8; j++) {
+                e[j] = (skipped >> (f + j - fa)) & 1u ? RTJ_ENT_SKIP : ent[(size_t)(f + j) * nblk + b];
+                tab[j] = desc[f + j].table;
+            }
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 if (RTJ_ENT_IS_SKIP(e[j])) {
-                    src[(size_t)(f + j) * nblk + b] = (uint16_t)last;
                     if (last_e && tab[j] == last_tab) ent[(size_t)(f + j) * nblk + b] = last_e;
+                    else src[(size_t)(f + j) * nblk + b] = (uint16_t)last;
                 } else {
                     last = (unsigned)(f + j);
                     last_e = RTJ_ENT_IS_INLINE(e[j]) ? (e[j] | RTJ_ENT_COPY_BIT) : 0u;
@@ -441,11 +456,11 @@ rtj_resolve_kernel(uint32_t *__restrict__ ent, const uint16_t *__restrict__ chun
             }
         }
         for (; f < fb; f++) {
-            const uint32_t ee = ent[(size_t)f * nblk + b];
+            const uint32_t ee = (skipped >> (f - fa)) & 1u ? RTJ_ENT_SKIP : ent[(size_t)f * nblk + b];
             const unsigned tb = desc[f].table;
             if (RTJ_ENT_IS_SKIP(ee)) {
-                src[(size_t)f * nblk + b] = (uint16_t)last;
                 if (last_e && tb == last_tab) ent[(size_t)f * nblk + b] = last_e;
+                else src[(size_t)f * nblk + b] = (uint16_t)last;
             } else {
                 last = (unsigned)f;
                 last_e = RTJ_ENT_IS_INLINE(ee) ? (ee | RTJ_ENT_COPY_BIT) : 0u;
@@ -676,8 +691,8 @@ extern "C" int rtj_launch_resolve(const rtj_launch_args *a, void *stream)
     const int nchunks = (a->f1 - a->f0 + RESOLVE_T - 1) / RESOLVE_T;    /* f0 is a multiple of RESOLVE_T */
     static const int ymax = getenv("RTJPEG_B200_K3Y") ? atoi(getenv("RTJPEG_B200_K3Y")) : 32;
     dim3 grid((unsigned)((nblk + 127) / 128), (unsigned)(nchunks < ymax ? nchunks : ymax));
-    rtj_resolve_last_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(a->d_ent, a->d_chunk_last, a->f0, a->f1, nblk, a->d_info, a->slice, a->d_k3_count);
-    rtj_resolve_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(a->d_ent, a->d_chunk_last, a->d_src, a->f0, a->f1, nblk, a->d_info,
+    rtj_resolve_last_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(a->d_ent, a->d_chunk_last, a->d_chunk_mask, a->f0, a->f1, nblk, a->d_info, a->slice, a->d_k3_count);
+    rtj_resolve_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(a->d_ent, a->d_chunk_last, a->d_chunk_mask, a->d_src, a->f0, a->f1, nblk, a->d_info,
                                                                a->slice, a->d_k3_in, a->d_k3_out, a->d_desc);
     return (int)cudaGetLastError();
 }

@@ -135,3 +135,19 @@ def test_every_payload_misalignment_and_frame_size(align):
         got, _ = gpu_decode(c, s2, o2, w, h)
     want = reference_frames(s2, o2, w, h)
     assert np.array_equal(got, want), first_diff(got, want, w, h)
+
+
+def test_workspace_few_large_frames_after_many_small_ones():
+    """One context, first many frames of a small picture, then few frames of a large one with skipped blocks: the second
+    batch needs fewer entries than the first but more of K3's per-chunk notes (one row per 32 frames AND position)."""
+    assert O.have_ref()
+    with _ctx(capi.SCAN_AUTO) as c:
+        s, o = clip(64, 48, 128, 600, key_rate=8, lm=1, cm=1, noise_y=4)
+        got, _ = gpu_decode(c, s, o, 64, 48)
+        want = reference_frames(s, o, 64, 48)
+        assert np.array_equal(got, want), first_diff(got, want, 64, 48)
+        w, h = 1280, 720
+        s, o = clip(w, h, 128, 3, key_rate=2, lm=2, cm=2, noise_y=4)
+        got, _ = gpu_decode(c, s, o, w, h)
+        want = reference_frames(s, o, w, h)
+        assert np.array_equal(got, want), first_diff(got, want, w, h)

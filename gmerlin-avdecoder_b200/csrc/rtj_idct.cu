@@ -900,6 +900,8 @@ rtj_idct_hard16_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_de
                        int nblk, int w, int h, int fmt, uint8_t *__restrict__ out, const uint32_t *__restrict__ hardq,
                        const rtj_dev_info *__restrict__ info)
 {
+    /* rtj_idct_hard_kernel, launched behind this kernel, takes the other end of the queue: it may start alongside */
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const unsigned n16 = info->hard_blocks;
     const size_t fsz = RTJ_FMT_FRAME_BYTES(fmt, w, h);
     const unsigned stride = gridDim.x * blockDim.x;
@@ -1208,8 +1210,19 @@ extern "C" int rtj_launch_idct_hard(const rtj_launch_args *a, void *stream)
     const int nblk = RTJ_FMT_NBLK(a->fmt, a->w, a->h);
     rtj_idct_hard16_kernel<<<sms * 8, 128, 0, (cudaStream_t)stream>>>(
         a->d_stream, a->d_desc, a->d_tables, a->d_ent, nblk, a->w, a->h, a->fmt, a->d_out, a->d_hardq, a->d_info);
-    rtj_idct_hard_kernel<<<sms * 16, HB_THREADS, 0, (cudaStream_t)stream>>>(
-        a->d_stream, a->d_desc, a->d_tables, a->d_ent, nblk, a->w, a->h, a->fmt, a->d_out, a->d_hardq,
-        (unsigned)((size_t)a->F * (size_t)nblk), a->d_info);
-    return (int)cudaGetLastError();
+    /* (programmatic stream serialisation, no wait: the two kernels patch different blocks; what both depend on -- K2's queue --
+     * was complete before the first of them started) */
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(sms * 16));
+    cfg.blockDim = dim3(HB_THREADS);
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, rtj_idct_hard_kernel, a->d_stream, a->d_desc, a->d_tables, (const uint32_t *)a->d_ent, nblk,
+                                             a->w, a->h, a->fmt, a->d_out, (const uint32_t *)a->d_hardq,
+                                             (unsigned)((size_t)a->F * (size_t)nblk), (const rtj_dev_info *)a->d_info);
+    return e != cudaSuccess ? (int)e : (int)cudaGetLastError();
 }

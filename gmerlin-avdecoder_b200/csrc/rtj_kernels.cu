@@ -345,6 +345,7 @@ extern "C" __global__ void __launch_bounds__(128)
 rtj_resolve_last_kernel(const uint32_t *__restrict__ ent, uint16_t *__restrict__ chunk_last, uint32_t *__restrict__ chunk_mask,
                         int f0, int f1, int nblk, const rtj_dev_info *__restrict__ info, int slice, uint32_t *__restrict__ arrived)
 {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");      /* rtj_resolve_kernel may take its places */
     if (!k3_any_skips(info, slice)) return;          /* nothing to resolve so far */
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b < nblk)
@@ -413,10 +414,12 @@ rtj_resolve_kernel(uint32_t *__restrict__ ent, const uint16_t *__restrict__ chun
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nblk) return;
-    if (!k3_any_skips(info, slice)) {
+    if (!k3_any_skips(info, slice)) {                               /* (K1's counters: final before rtj_resolve_last_kernel started) */
         if (blockIdx.y == 0) carry_out[b] = (uint16_t)(f1 - 1);     /* every frame so far wrote every position */
         return;
     }
+    /* launched with programmatic stream serialisation behind rtj_resolve_last_kernel: resident early, its notes final from here */
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const int c_lo = f0 / RESOLVE_T;
     for (int c0 = c_lo + blockIdx.y; c0 * RESOLVE_T < f1; c0 += gridDim.y) {
         const int fa = c0 * RESOLVE_T, fb = min(f1, fa + RESOLVE_T);
@@ -692,7 +695,18 @@ extern "C" int rtj_launch_resolve(const rtj_launch_args *a, void *stream)
     static const int ymax = getenv("RTJPEG_B200_K3Y") ? atoi(getenv("RTJPEG_B200_K3Y")) : 32;
     dim3 grid((unsigned)((nblk + 127) / 128), (unsigned)(nchunks < ymax ? nchunks : ymax));
     rtj_resolve_last_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(a->d_ent, a->d_chunk_last, a->d_chunk_mask, a->f0, a->f1, nblk, a->d_info, a->slice, a->d_k3_count);
-    rtj_resolve_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(a->d_ent, a->d_chunk_last, a->d_chunk_mask, a->d_src, a->f0, a->f1, nblk, a->d_info,
-                                                               a->slice, a->d_k3_in, a->d_k3_out, a->d_desc);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(128);
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, rtj_resolve_kernel, a->d_ent, (const uint16_t *)a->d_chunk_last, (const uint32_t *)a->d_chunk_mask,
+                                             a->d_src, a->f0, a->f1, nblk, (const rtj_dev_info *)a->d_info, a->slice, a->d_k3_in, a->d_k3_out,
+                                             a->d_desc);
+    if (e != cudaSuccess) return (int)e;
     return (int)cudaGetLastError();
 }

@@ -106,7 +106,13 @@ rtj_scan_chunk_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_des
     const int tid = threadIdx.x, lane = tid & 31;
     const int f = (PHASE == 0 ? blockIdx.x : blockIdx.y) + f0;        /* F: one behind the last frame of this launch */
     if (f >= F) return;
-    if (PHASE == 0 && redo && !redo[f]) return;                        /* behind rtj_scan_sync_kernel: the frames it left */
+    if (PHASE == 0 && redo) {
+        /* behind rtj_scan_sync_kernel, launched with programmatic stream serialisation: this grid may be resident before
+         * that one is done (and lets the grid behind itself in likewise); its flags are final after the wait */
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        if (!redo[f]) return;                                          /* only the frames it left */
+    }
     const rtjgpu_frame_desc d = desc[f];
     {
         const rtj_dev_table &tab = tables[min((int)d.table, RTJ_NUM_TABLES - 1)];      /* descriptors are the caller's memory */
@@ -426,7 +432,17 @@ extern "C" int rtj_launch_scan_chunk(const rtj_launch_args *a, int phase, void *
 extern "C" int rtj_launch_scan_chunk_redo(const rtj_launch_args *a, const uint32_t *redo, void *stream)
 {
     const int nblk = RTJ_FMT_NBLK(a->fmt, a->w, a->h);
-    rtj_scan_chunk_kernel<0><<<(unsigned)(a->f1 - a->f0), CS_THREADS, sizeof(CsShared), (cudaStream_t)stream>>>(
-        a->d_stream, a->d_desc, a->d_tables, a->f1, nblk, a->d_ent, a->d_frame_skips, a->d_info, a->seg, a->f0, a->slice, redo);
-    return (int)cudaGetLastError();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(a->f1 - a->f0));
+    cfg.blockDim = dim3(CS_THREADS);
+    cfg.dynamicSmemBytes = sizeof(CsShared);
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, rtj_scan_chunk_kernel<0>, a->d_stream, a->d_desc, a->d_tables, a->f1, nblk, a->d_ent,
+                                             a->d_frame_skips, a->d_info, a->seg, a->f0, a->slice, redo);
+    return e != cudaSuccess ? (int)e : (int)cudaGetLastError();
 }

@@ -489,10 +489,24 @@ cudaError_t scan_mb_launch(const rtj_launch_args *a, int phase, int nblk, cudaSt
 {
     const int nf = a->f1 - a->f0;
     const dim3 grid = phase == 0 ? dim3((unsigned)nf) : dim3((unsigned)a->seg.maxseg, (unsigned)nf);
-    if (phase == 0)
-        rtj_scan_mb_kernel<0, FMT><<<grid, MB_THREADS, sizeof(MbShared), st>>>(
-            a->d_stream, a->d_desc, a->d_tables, a->f1, nblk, a->d_ent, a->d_frame_skips, a->d_info, a->seg, a->f0, a->slice);
-    else if (phase == 1)
+    if (phase == 0) {
+        /* One CTA per frame, behind the kernel that takes the frames without a raw prefix.  The two share nothing (every frame
+         * is one kernel's or the other's), so this grid may start while that one's last CTAs are still at work: programmatic
+         * stream serialisation, and no wait for the grid in front. */
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid;
+        cfg.blockDim = dim3(MB_THREADS);
+        cfg.dynamicSmemBytes = sizeof(MbShared);
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        const cudaError_t e = cudaLaunchKernelEx(&cfg, rtj_scan_mb_kernel<0, FMT>, a->d_stream, a->d_desc, a->d_tables, a->f1, nblk, a->d_ent,
+                                                 a->d_frame_skips, a->d_info, a->seg, a->f0, a->slice);
+        if (e != cudaSuccess) return e;
+    } else if (phase == 1)
         rtj_scan_mb_kernel<1, FMT><<<grid, MB_THREADS, sizeof(MbShared), st>>>(
             a->d_stream, a->d_desc, a->d_tables, a->f1, nblk, a->d_ent, a->d_frame_skips, a->d_info, a->seg, a->f0, a->slice);
     else

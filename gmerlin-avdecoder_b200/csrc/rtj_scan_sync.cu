@@ -205,6 +205,9 @@ rtj_scan_sync_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc
     extern __shared__ __align__(16) uint8_t sy_smem[];
     SyShared &sh = *reinterpret_cast<SyShared *>(sy_smem);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    /* the kernels launched behind this one (the hand-over pass, the raw-prefix pass: both find nothing to do on most batches)
+     * may take their places on the SMs while this grid's last CTAs are still at work */
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int f = blockIdx.x + f0;
     if (f >= F) return;
     if (redo && tid == 0) redo[f] = 0u;

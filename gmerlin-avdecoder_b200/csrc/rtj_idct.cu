@@ -565,6 +565,7 @@ rtj_idct_kernel(const K2Params P)
     typedef Geo<FMT> G;
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    asm volatile("griddepcontrol.wait;" ::: "memory");        /* resident before K3 is done (launch_pdl); K3's entries are final from here */
     const unsigned f = blockIdx.y + (unsigned)P.f0;
     const int w = P.w, h = P.h, mbw = w / G::UNIT_W;           /* units per picture row */
     const int strip = SINGLE ? 0 : (int)(blockIdx.x % (unsigned)P.nstrips);
@@ -900,7 +901,9 @@ rtj_idct_hard16_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_de
                        int nblk, int w, int h, int fmt, uint8_t *__restrict__ out, const uint32_t *__restrict__ hardq,
                        const rtj_dev_info *__restrict__ info)
 {
-    /* rtj_idct_hard_kernel, launched behind this kernel, takes the other end of the queue: it may start alongside */
+    /* resident before K2 is done (launch_pdl): its queue is final after the wait.  rtj_idct_hard_kernel, launched behind this
+     * kernel, takes the other end of the queue: from here on it may start alongside. */
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const unsigned n16 = info->hard_blocks;
     const size_t fsz = RTJ_FMT_FRAME_BYTES(fmt, w, h);
@@ -1097,6 +1100,24 @@ cudaError_t k2_attr()
                                 (int)idct_smem_bytes(IDCT_MAX_MB, FMT, 3));
 }
 
+/* a launch with programmatic stream serialisation: the grid may become resident while the kernel in front of it in the stream
+ * is still at work; it calls griddepcontrol.wait before it touches what that kernel makes */
+template <typename K, typename... A>
+cudaError_t launch_pdl(K kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t st, A... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 template <int FMT, int RGBK>
 cudaError_t k2_launch(K2Params &P, int grid_x, int F, cudaStream_t st)
 {
@@ -1108,14 +1129,15 @@ cudaError_t k2_launch(K2Params &P, int grid_x, int F, cudaStream_t st)
     P.ahead = (resident + grid_x - 1) / grid_x;
     const size_t smem = idct_smem_bytes(P.seg_mb, FMT, warps);
     const dim3 grid((unsigned)grid_x, (unsigned)F);
+    cudaError_t e;
     if (P.nstrips == 1) {
-        if (warps == 4) rtj_idct_kernel<true, FMT, 4, RGBK><<<grid, 128, smem, st>>>(P);
-        else rtj_idct_kernel<true, FMT, 3, RGBK><<<grid, 96, smem, st>>>(P);
+        if (warps == 4) e = launch_pdl(rtj_idct_kernel<true, FMT, 4, RGBK>, grid, dim3(128), smem, st, P);
+        else e = launch_pdl(rtj_idct_kernel<true, FMT, 3, RGBK>, grid, dim3(96), smem, st, P);
     } else {
-        if (warps == 4) rtj_idct_kernel<false, FMT, 4, RGBS><<<grid, 128, smem, st>>>(P);
-        else rtj_idct_kernel<false, FMT, 3, RGBS><<<grid, 96, smem, st>>>(P);
+        if (warps == 4) e = launch_pdl(rtj_idct_kernel<false, FMT, 4, RGBS>, grid, dim3(128), smem, st, P);
+        else e = launch_pdl(rtj_idct_kernel<false, FMT, 3, RGBS>, grid, dim3(96), smem, st, P);
     }
-    return cudaGetLastError();
+    return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 template <int FMT, int RGBK>
@@ -1208,8 +1230,10 @@ extern "C" int rtj_launch_idct_hard(const rtj_launch_args *a, void *stream)
     /* the queue's length is only known on the device: a fixed grid strides over it */
     const int sms = g_sm_count > 0 ? g_sm_count : 148;
     const int nblk = RTJ_FMT_NBLK(a->fmt, a->w, a->h);
-    rtj_idct_hard16_kernel<<<sms * 8, 128, 0, (cudaStream_t)stream>>>(
-        a->d_stream, a->d_desc, a->d_tables, a->d_ent, nblk, a->w, a->h, a->fmt, a->d_out, a->d_hardq, a->d_info);
+    cudaError_t e16 = launch_pdl(rtj_idct_hard16_kernel, dim3((unsigned)(sms * 8)), dim3(128), 0, (cudaStream_t)stream,
+                                 a->d_stream, a->d_desc, a->d_tables, (const uint32_t *)a->d_ent, nblk, a->w, a->h, a->fmt, a->d_out,
+                                 (const uint32_t *)a->d_hardq, (const rtj_dev_info *)a->d_info);
+    if (e16 != cudaSuccess) return (int)e16;
     /* (programmatic stream serialisation, no wait: the two kernels patch different blocks; what both depend on -- K2's queue --
      * was complete before the first of them started) */
     cudaLaunchConfig_t cfg = {};

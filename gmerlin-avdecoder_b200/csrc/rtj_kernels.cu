@@ -353,13 +353,13 @@ rtj_resolve_last_kernel(const uint32_t *__restrict__ ent, uint16_t *__restrict__
             const int fa = c * RESOLVE_T, fb = min(f1, fa + RESOLVE_T);
             unsigned last = RTJ_SRC_CARRY;
             uint32_t skipped = 0;                            /* bit j: frame fa + j skipped the position -- rtj_resolve_kernel reads only the others */
-            uint32_t e[8];
+            uint32_t e[16];
             int f = fa;
-            for (; f + 8 <= fb; f += 8) {
+            for (; f + 16 <= fb; f += 16) {
 #pragma unroll
-                for (int j = 0; j < 8; j++) e[j] = ent[(size_t)(f + j) * nblk + b];
+                for (int j = 0; j < 16; j++) e[j] = ent[(size_t)(f + j) * nblk + b];
 #pragma unroll
-                for (int j = 0; j < 8; j++) {
+                for (int j = 0; j < 16; j++) {
                     if (!RTJ_ENT_IS_SKIP(e[j])) last = (unsigned)(f + j);
                     else skipped |= 1u << (f + j - fa);
                 }

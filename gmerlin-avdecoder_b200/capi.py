@@ -118,6 +118,7 @@ def load_library() -> C.CDLL:
     L.rtjgpu_set_scan_mode.argtypes = [vp, C.c_int]
     L.rtjgpu_set_format.argtypes = [vp, C.c_int]
     L.rtjgpu_set_pipeline.argtypes = [vp, C.c_int, C.c_int]
+    L.rtjgpu_set_frame_runs.argtypes = [vp, C.c_int]
     L.rtjgpu_convert_device.argtypes = [vp, C.c_int, vp, C.c_size_t, C.c_int, C.c_int, C.c_int, vp, C.c_size_t, C.c_size_t,
                                         C.c_int, vp]
     L.rtjgpu_convert_bpp.argtypes = [C.c_int]
@@ -321,6 +322,10 @@ class BatchContext:
     def set_scan_mode(self, mode: int) -> None:
         """0 = auto, 1 = one thread per frame, 2 = one warp per frame."""
         _check(self._L.rtjgpu_set_scan_mode(self._h, mode), "rtjgpu_set_scan_mode")
+
+    def set_frame_runs(self, frames: int = 0) -> None:
+        """rtjgpu_set_frame_runs: 0 = by the batch before, 1 = every frame for itself, n = runs of n frames per CTA of K2."""
+        _check(self._L.rtjgpu_set_frame_runs(self._h, frames), "rtjgpu_set_frame_runs")
 
     def set_pipeline(self, mode: int = PIPELINE_AUTO, slice_frames: int = 0) -> None:
         """PIPELINE_SERIAL (= AUTO at present): stage after stage; PIPELINE_SLICED: scan of slice s + 1 beside resolve + IDCT of slice s."""

@@ -101,6 +101,8 @@ struct rtjgpu_ctx {
     int            pipeline_mode = RTJGPU_PIPELINE_AUTO;
     int            slice_frames = 1184, slice0_frames = 1184;   /* multiples of RTJ_RESOLVE_T */
     bool           scan_priority = false;
+    int            frame_run = 0;             /* rtjgpu_set_frame_runs: 0 = by the batch before, 1 = off, n = forced */
+    unsigned long long *h_skips_seen = nullptr;    /* pinned: skipped blocks of the last batch whose K3 has run */
     bool           slices_forced = false;     /* rtjgpu_set_pipeline / the environment gave a slice size: it holds in either arrangement */
     /* encoder: configuration, state between calls, workspace */
     int            enc_quality = 0, enc_lb8 = 0, enc_cb8 = 0;
@@ -338,6 +340,11 @@ int run_kernels(rtjgpu_ctx *ctx, Workspace *ws, const uint8_t *d_stream, const r
     a.f0 = 0; a.f1 = F; a.slice = 0;
     a.fmt = ctx->format;
     a.row0 = 0; a.row1 = RTJ_FMT_UNITS_Y(ctx->format, h);
+    /* K2 works through runs of frames with the strip staying on chip when the stream skips blocks -- which only the device
+     * knows for this batch.  The batch before is the guide (its count arrives in pinned memory; a count that is not there yet
+     * is the one before it): streams do not change their nature from batch to batch, and either arrangement is exact. */
+    a.k2_run = ctx->frame_run ? ctx->frame_run : (*(volatile unsigned long long *)ctx->h_skips_seen ? RTJ_K2_RUN_FRAMES : 1);
+    a.h_skips_seen = ctx->h_skips_seen;
     a.d_walk = ws->d_walk;
     a.d_redo = ws->d_frame_skips + ws->cap_frames;
     a.d_ent = ws->d_ent; a.d_src = ws->d_src; a.d_frame_skips = ws->d_frame_skips; a.d_info = ws->d_info;
@@ -502,6 +509,7 @@ int rtjgpu_create(int device, rtjgpu_ctx **out)
     if (const char *v = getenv("RTJPEG_B200_SLICE0")) ctx->slice0_frames = std::max(32, atoi(v));
     if (const char *v = getenv("RTJPEG_B200_SCAN_PRIO")) ctx->scan_priority = atoi(v) != 0;
     if (const char *v = getenv("RTJPEG_B200_SCAN")) ctx->scan_mode = std::min(std::max(atoi(v), 0), (int)RTJGPU_SCAN_SYNC);
+    if (const char *v = getenv("RTJPEG_B200_K2_RUN")) ctx->frame_run = std::min(std::max(atoi(v), 0), 64);
     if (const char *v = getenv("RTJPEG_B200_PIPELINE")) ctx->pipeline_mode = std::min(std::max(atoi(v), 0), (int)RTJGPU_PIPELINE_SLICED);
     int rc = RTJGPU_OK;
     do {
@@ -516,6 +524,8 @@ int rtjgpu_create(int device, rtjgpu_ctx **out)
         if ((e = cudaMemcpy(ctx->d_tables, dev.data(), sizeof(rtj_dev_table) * RTJ_NUM_TABLES, cudaMemcpyHostToDevice)) != cudaSuccess) { rc = RTJGPU_E_CUDA; break; }
         if ((e = cudaMallocHost(&ctx->h_info_reset, sizeof(rtj_dev_info))) != cudaSuccess) { rc = RTJGPU_E_CUDA; break; }
         if ((e = cudaMallocHost(&ctx->h_info, sizeof(rtj_dev_info))) != cudaSuccess) { rc = RTJGPU_E_CUDA; break; }
+        if ((e = cudaMallocHost(&ctx->h_skips_seen, sizeof(unsigned long long))) != cudaSuccess) { rc = RTJGPU_E_CUDA; break; }
+        *ctx->h_skips_seen = 0;
         memset(ctx->h_info_reset, 0, sizeof(rtj_dev_info));
         ctx->h_info_reset->first_bad_frame = -1;
         *ctx->h_info = *ctx->h_info_reset;
@@ -564,6 +574,7 @@ void rtjgpu_destroy(rtjgpu_ctx *ctx)
     if (ctx->d_tables) cudaFree(ctx->d_tables);
     if (ctx->h_info_reset) cudaFreeHost(ctx->h_info_reset);
     if (ctx->h_info) cudaFreeHost(ctx->h_info);
+    if (ctx->h_skips_seen) cudaFreeHost(ctx->h_skips_seen);
     for (int i = 0; i < TIMING_RING * 4; i++) if (ctx->ev[i / 4][i % 4]) cudaEventDestroy(ctx->ev[i / 4][i % 4]);
     delete ctx;
 }
@@ -587,6 +598,13 @@ int rtjgpu_set_pipeline(rtjgpu_ctx *ctx, int mode, int slice_frames)
         ctx->slice_frames = ctx->slice0_frames = (slice_frames + RTJ_RESOLVE_T - 1) / RTJ_RESOLVE_T * RTJ_RESOLVE_T;
         ctx->slices_forced = true;
     }
+    return RTJGPU_OK;
+}
+
+int rtjgpu_set_frame_runs(rtjgpu_ctx *ctx, int frames)
+{
+    if (!ctx || frames < 0 || frames > 64) return RTJGPU_E_ARG;
+    ctx->frame_run = frames;
     return RTJGPU_OK;
 }
 

@@ -79,6 +79,7 @@ void rtj_encoder_table_from_quality(int Q, int32_t qt[128], int *lb8, int *cb8);
 /* A batch is worked through in SLICES of frames (rtj_batch.cpp, run_kernels): K1 of slice s + 1 shares the SMs
  * with K3 / K2 of slice s.  Slices are whole chunks of RTJ_RESOLVE_T frames, at most RTJ_MAX_SLICES per batch. */
 #define RTJ_RESOLVE_T  32
+#define RTJ_K2_RUN_FRAMES 8      /* frames a CTA of K2 works through in turn on streams that skip blocks */
 #define RTJ_MAX_SLICES 128
 
 /* Device counters of one batch (lives in device memory, mirrored on request). */
@@ -127,6 +128,8 @@ typedef struct rtj_launch_args {
     int                      f0, f1;        /* the frames this launch covers (a slice); K1 segment-parallel and the serial flavours: 0, F */
     int                      slice;         /* index of the slice [f0, f1) */
     int                      row0, row1;    /* the rows of units K2 of this launch covers (all of them, as things are) */
+    int                      k2_run;        /* frames a CTA of K2 works through in turn, the strip staying on chip (1: one frame per CTA) */
+    unsigned long long      *h_skips_seen;  /* pinned host word K3 leaves the batch's skip count in (what the next batch's k2_run goes by), or NULL */
     void                    *d_walk;        /* [F] int2: rtj_scan_walk_kernel's state between slices of blocks */
     uint32_t                *d_redo;        /* [F] rtj_scan_sync_kernel: frames it leaves to rtj_scan_chunk_kernel */
     int                      fmt;           /* RTJ_YUV420 / RTJ_YUV422 / RTJ_RGB8 */

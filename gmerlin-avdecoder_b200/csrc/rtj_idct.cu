@@ -469,6 +469,7 @@ struct K2Params {
     const uint16_t *srcf;
     int nblk, w, h, seg_mb, nstrips;
     int f0, F;                       /* first frame of this launch (blockIdx.y = 0); frames of the batch */
+    int f_end, run;                  /* one behind the launch's last frame; frames a CTA works through in turn (blockIdx.y counts runs) */
     int row0, rows;                  /* first row of units of this launch (blockIdx.x = 0); rows of units of a picture */
     uint8_t *out;
     const uint8_t *carry;
@@ -555,7 +556,8 @@ constexpr int K2_PF_LINES = 12;                   /* 128-byte lines of payload a
  * (strips of very wide pictures: not worth five more kernels) */
 constexpr int RGB_NONE = -1, RGB_ANY = 99;
 
-template <bool SINGLE, int FMT, int WARPS, int RGBK>
+/* RUN: a CTA works through P.run frames in turn (below); false: one frame, and none of the run's bookkeeping is compiled in */
+template <bool SINGLE, int FMT, int WARPS, int RGBK, bool RUN>
 __global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? 8 : 10)
 rtj_idct_kernel(const K2Params P)
 {
@@ -566,7 +568,12 @@ rtj_idct_kernel(const K2Params P)
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     asm volatile("griddepcontrol.wait;" ::: "memory");        /* resident before K3 is done (launch_pdl); K3's entries are final from here */
-    const unsigned f = blockIdx.y + (unsigned)P.f0;
+    /* A CTA works through a RUN of frames of its row of units, the strip staying in shared memory from frame to frame: what a
+     * frame skips (lib/RTjpeg.c:2704 -- the block keeps what the picture held) is then simply not touched, instead of being
+     * decoded again from its last writer's stream for every frame it persists in.  P.run == 1: one frame per CTA. */
+    const unsigned f_first = (unsigned)P.f0 + blockIdx.y * (RUN ? (unsigned)P.run : 1u);
+    const unsigned f_last = RUN ? min(f_first + (unsigned)P.run, (unsigned)P.f_end) : f_first + 1u;       /* one behind */
+    constexpr bool runs = RUN;
     const int w = P.w, h = P.h, mbw = w / G::UNIT_W;           /* units per picture row */
     const int strip = SINGLE ? 0 : (int)(blockIdx.x % (unsigned)P.nstrips);
     const int my = P.row0 + (SINGLE ? (int)blockIdx.x : (int)(blockIdx.x / (unsigned)P.nstrips));
@@ -574,13 +581,6 @@ rtj_idct_kernel(const K2Params P)
     const int mbs = SINGLE ? mbw : min(P.seg_mb, mbw - mx0);
     const int nb = mbs * G::BLK;
     const unsigned strip_blk0 = (unsigned)(my * mbw + mx0) * (unsigned)G::BLK;
-    const unsigned frame_blk0 = f * (unsigned)P.nblk + strip_blk0;   /* F * nblk < 2^32 (checked by the host) */
-    const uint32_t *my_ent = P.ent + frame_blk0;
-    /* A CTA lives a few microseconds, of which the first read of its entries from DRAM -- under the write traffic of
-     * this kernel -- is a good part.  So it asks for the entries of the CTA that will take its place when it retires
-     * (same strip, P.ahead frames on) into L2 now. */
-    if (f + (unsigned)P.ahead < (unsigned)P.F && tid * 32 < nb)
-        asm volatile("prefetch.global.L2 [%0];" :: "l"(my_ent + (size_t)P.ahead * (unsigned)P.nblk + tid * 32));
 
     uint8_t *tile = smem;                                            /* TILE * mbs bytes: Y, U, V */
     const unsigned tile_s = (unsigned)__cvta_generic_to_shared(tile);
@@ -590,9 +590,6 @@ rtj_idct_kernel(const K2Params P)
     const int wq = P.wq;                                             /* queue slots of one warp: every block it looked at */
     uint32_t *wq_e = reinterpret_cast<uint32_t *>(s_hard + 8) + warp * wq;      /* this warp's queue: entries ... */
     uint32_t *wq_p = reinterpret_cast<uint32_t *>(s_hard + 8) + (K2_WARPS + warp) * wq;   /* ... strip offset | source << 16 */
-
-    /* everything that does not depend on anything else is fetched first: the first round's entry
-     * and the frame descriptor; the table constants follow the descriptor */
     const int rounds = (nb + THREADS - 1) / THREADS;
     /* the positions of a whole row are the same for every row of every frame: a table, hot in L1 (padded to a
      * multiple of THREADS); strips of wider pictures work them out */
@@ -606,6 +603,21 @@ rtj_idct_kernel(const K2Params P)
         }
         return G::pic_pos(p, mbs);
     };
+    unsigned valid = 0;              /* bit r: the strip holds the picture's pixels at this thread's position of round r */
+
+    for (unsigned f = f_first; f < f_last; f++) {
+    const unsigned frame_blk0 = f * (unsigned)P.nblk + strip_blk0;   /* F * nblk < 2^32 (checked by the host) */
+    const uint32_t *my_ent = P.ent + frame_blk0;
+    /* A CTA lives a few microseconds, of which the first read of its entries from DRAM -- under the write traffic of
+     * this kernel -- is a good part.  So it asks for the entries it will want next into L2 now: those of the CTA that will
+     * take its place when it retires (same strip, P.ahead frames on), or, working through a run, those of its next frame. */
+    const unsigned pf = runs ? 1u : (unsigned)P.ahead;
+    const bool pf_ok = runs ? f + 1u < f_last : f + pf < (unsigned)P.F;
+    if (pf_ok && tid * 32 < nb)
+        asm volatile("prefetch.global.L2 [%0];" :: "l"(my_ent + (size_t)pf * (unsigned)P.nblk + tid * 32));
+
+    /* everything that does not depend on anything else is fetched first: the first round's entry
+     * and the frame descriptor; the table constants follow the descriptor */
     PicPos pp_next = pos_of(tid);
     uint32_t e_first = tid < nb ? my_ent[pp_next.i] : 0u;
     const rtjgpu_frame_desc fd = P.desc[f];
@@ -633,7 +645,10 @@ rtj_idct_kernel(const K2Params P)
         int x0 = 0, x1 = 0, q = 0;
         bool safe = true;
         unsigned sf = f;
-        if (p < nb) {
+        /* working through a run: a block this frame skips (its marker, or K3's copy of an inline last writer: both carry
+         * bits 31 and 30) whose pixels the strip still holds from the frame before is left alone */
+        const bool keep = runs && f != f_first && ((valid >> r) & 1u) && (e & 0xC0000000u) == 0xC0000000u;
+        if (p < nb && !keep) {
             if (RTJ_ENT_IS_SKIP(e)) {                        /* skipped: take the entry of its last writer */
                 saw_skip = true;
                 const unsigned s = P.srcf[frame_blk0 + pp.i];
@@ -664,6 +679,8 @@ rtj_idct_kernel(const K2Params P)
             }
             if (cls == CLS_T2) safe = t2_safe(x0, x1, q);
         }
+        /* what is decoded or copied into the strip leaves it valid; a HARD block's pixels only reach the frame in device memory */
+        if (runs && !keep) valid = (valid & ~(1u << r)) | ((cls != CLS_NONE && (RGB || cls != Q_HARD)) ? 1u << r : 0u);
         const bool packed = __all_sync(FULL, safe);          /* one epilogue flavour per warp */
         if (cls == CLS_T2) {
             uint32_t px[16];
@@ -688,12 +705,12 @@ rtj_idct_kernel(const K2Params P)
         nback += __popc(mB);
     }
     /* ... where this row held skipped blocks, the last writers of that frame's row (two bytes a block) ... */
-    if (f + (unsigned)P.ahead < (unsigned)P.F && __any_sync(FULL, saw_skip) && lane * 64 < nb && warp == 0)
-        asm volatile("prefetch.global.L2 [%0];" :: "l"(P.srcf + frame_blk0 + (size_t)P.ahead * (unsigned)P.nblk + lane * 64));
+    if (pf_ok && __any_sync(FULL, saw_skip) && lane * 64 < nb && warp == 0)
+        asm volatile("prefetch.global.L2 [%0];" :: "l"(P.srcf + frame_blk0 + (size_t)pf * (unsigned)P.nblk + lane * 64));
     /* ... and the part of that frame's payload where its blocks of this row should lie, if the payload is spread
      * evenly over the rows: the M7 blocks read it */
-    if (f + (unsigned)P.ahead < (unsigned)P.F && warp == WARPS - 1 && lane < K2_PF_LINES) {
-        const rtjgpu_frame_desc nd = P.desc[f + (unsigned)P.ahead];
+    if (pf_ok && warp == WARPS - 1 && lane < K2_PF_LINES) {
+        const rtjgpu_frame_desc nd = P.desc[f + pf];
         const unsigned rows_total = (unsigned)P.rows;
         const unsigned plen = nd.length > RTJPEG_B200_HEADER_BYTES ? nd.length - RTJPEG_B200_HEADER_BYTES : 0u;
         const unsigned at = (unsigned)(((unsigned long long)plen * (unsigned)my) / rows_total);
@@ -801,6 +818,7 @@ rtj_idct_kernel(const K2Params P)
     if (SINGLE) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
     const int lw = G::UNIT_W * mbs;                              /* luma bytes per strip row */
+    bool planes_leave = true;
     if (RGB) {
         /* The strip -- 16 luma rows, 8 rows of Cb and of Cr: exactly what the reference's converters read for 16 output
          * rows (lib/RTjpeg.c:3123-3190) -- leaves as packed pixels.  A thread takes 8 pixels of two rows (one chroma row):
@@ -829,8 +847,9 @@ rtj_idct_kernel(const K2Params P)
             default:             row8<RTJ_CONV_RGB16>(y0, ct, P.rgb_alpha, o); row8<RTJ_CONV_RGB16>(y1, ct, P.rgb_alpha, o + P.rgb_row_pitch); break;
             }
         }
-        if (!P.last_yuv || f + 1u != (unsigned)P.F) return;      /* the last frame also leaves as planes: the next batch's carry */
-    } else if (s_hard[0] + s_hard[1] + s_hard[2] + s_hard[3] == nb) return;
+        if (!P.last_yuv || f + 1u != (unsigned)P.F) planes_leave = false;      /* the last frame also leaves as planes: the next batch's carry */
+    } else if (s_hard[0] + s_hard[1] + s_hard[2] + s_hard[3] == nb) planes_leave = false;
+    if (planes_leave) {
     const size_t fsz = RTJ_FMT_FRAME_BYTES(FMT, w, h);
     const int cw = w >> 1;
     uint8_t *const planes = RGB ? P.last_yuv : P.out + (size_t)f * fsz;
@@ -871,6 +890,10 @@ rtj_idct_kernel(const K2Params P)
                         *reinterpret_cast<const uint2 *>((pl ? tileV : tileU) + rr * segC + c * 8);
             }
         }
+    }
+    }
+    /* the run's next frame writes into the strip: everybody is done reading it (thread 0 has waited for its bulk stores) */
+    if (runs) __syncthreads();
     }
 }
 
@@ -1096,8 +1119,12 @@ int g_sm_count = 0;
 template <bool SINGLE, int FMT, int WARPS, int RGBK>
 cudaError_t k2_attr()
 {
-    return cudaFuncSetAttribute(rtj_idct_kernel<SINGLE, FMT, WARPS, RGBK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)idct_smem_bytes(IDCT_MAX_MB, FMT, 3));
+    cudaError_t e = cudaFuncSetAttribute(rtj_idct_kernel<SINGLE, FMT, WARPS, RGBK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)idct_smem_bytes(IDCT_MAX_MB, FMT, 3));
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(rtj_idct_kernel<SINGLE, FMT, WARPS, RGBK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)idct_smem_bytes(IDCT_MAX_MB, FMT, 3));
+    return e;
 }
 
 /* a launch with programmatic stream serialisation: the grid may become resident while the kernel in front of it in the stream
@@ -1128,14 +1155,23 @@ cudaError_t k2_launch(K2Params &P, int grid_x, int F, cudaStream_t st)
     const int resident = (g_sm_count > 0 ? g_sm_count : 148) * (warps == 4 ? 8 : 10);
     P.ahead = (resident + grid_x - 1) / grid_x;
     const size_t smem = idct_smem_bytes(P.seg_mb, FMT, warps);
-    const dim3 grid((unsigned)grid_x, (unsigned)F);
+    P.run = P.run < 1 ? 1 : P.run;
+    const dim3 grid((unsigned)grid_x, (unsigned)((F + P.run - 1) / P.run));
     cudaError_t e;
-    if (P.nstrips == 1) {
-        if (warps == 4) e = launch_pdl(rtj_idct_kernel<true, FMT, 4, RGBK>, grid, dim3(128), smem, st, P);
-        else e = launch_pdl(rtj_idct_kernel<true, FMT, 3, RGBK>, grid, dim3(96), smem, st, P);
+    if (P.run > 1) {
+        if (P.nstrips == 1) {
+            if (warps == 4) e = launch_pdl(rtj_idct_kernel<true, FMT, 4, RGBK, true>, grid, dim3(128), smem, st, P);
+            else e = launch_pdl(rtj_idct_kernel<true, FMT, 3, RGBK, true>, grid, dim3(96), smem, st, P);
+        } else {
+            if (warps == 4) e = launch_pdl(rtj_idct_kernel<false, FMT, 4, RGBS, true>, grid, dim3(128), smem, st, P);
+            else e = launch_pdl(rtj_idct_kernel<false, FMT, 3, RGBS, true>, grid, dim3(96), smem, st, P);
+        }
+    } else if (P.nstrips == 1) {
+        if (warps == 4) e = launch_pdl(rtj_idct_kernel<true, FMT, 4, RGBK, false>, grid, dim3(128), smem, st, P);
+        else e = launch_pdl(rtj_idct_kernel<true, FMT, 3, RGBK, false>, grid, dim3(96), smem, st, P);
     } else {
-        if (warps == 4) e = launch_pdl(rtj_idct_kernel<false, FMT, 4, RGBS>, grid, dim3(128), smem, st, P);
-        else e = launch_pdl(rtj_idct_kernel<false, FMT, 3, RGBS>, grid, dim3(96), smem, st, P);
+        if (warps == 4) e = launch_pdl(rtj_idct_kernel<false, FMT, 4, RGBS, false>, grid, dim3(128), smem, st, P);
+        else e = launch_pdl(rtj_idct_kernel<false, FMT, 3, RGBS, false>, grid, dim3(96), smem, st, P);
     }
     return e != cudaSuccess ? e : cudaGetLastError();
 }
@@ -1203,7 +1239,7 @@ extern "C" int rtj_launch_idct(const rtj_launch_args *a, void *stream)
     P.hardq_cap = (unsigned)((size_t)a->F * (size_t)P.nblk);
     P.fmt = fmt;
     P.pos = reinterpret_cast<const uint32_t *>(a->d_lut);
-    P.f0 = a->f0; P.F = a->F;
+    P.f0 = a->f0; P.F = a->F; P.f_end = a->f1; P.run = a->k2_run;
     P.row0 = a->row0; P.rows = uy;
     const int grid_x = P.nstrips * (a->row1 - a->row0);
     const int nf = a->f1 - a->f0;

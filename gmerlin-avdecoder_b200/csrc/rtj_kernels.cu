@@ -410,9 +410,12 @@ extern "C" __global__ void __launch_bounds__(128)
 rtj_resolve_kernel(uint32_t *__restrict__ ent, const uint16_t *__restrict__ chunk_last, const uint32_t *__restrict__ chunk_mask,
                    uint16_t *__restrict__ src, int f0, int f1, int nblk, const rtj_dev_info *__restrict__ info, int slice,
                    const uint16_t *__restrict__ carry_in, uint16_t *__restrict__ carry_out,
-                   const rtjgpu_frame_desc *__restrict__ desc)
+                   const rtjgpu_frame_desc *__restrict__ desc, unsigned long long *__restrict__ skips_seen)
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    /* how many blocks the batch skipped, left where the host sees it without asking (pinned memory): the next batch's
+     * arrangement of K2 goes by it */
+    if (skips_seen && b == 0 && blockIdx.y == 0) *skips_seen = info->skipped_blocks;
     if (b >= nblk) return;
     if (!k3_any_skips(info, slice)) {                               /* (K1's counters: final before rtj_resolve_last_kernel started) */
         if (blockIdx.y == 0) carry_out[b] = (uint16_t)(f1 - 1);     /* every frame so far wrote every position */
@@ -706,7 +709,7 @@ extern "C" int rtj_launch_resolve(const rtj_launch_args *a, void *stream)
     cfg.numAttrs = 1;
     const cudaError_t e = cudaLaunchKernelEx(&cfg, rtj_resolve_kernel, a->d_ent, (const uint16_t *)a->d_chunk_last, (const uint32_t *)a->d_chunk_mask,
                                              a->d_src, a->f0, a->f1, nblk, (const rtj_dev_info *)a->d_info, a->slice, a->d_k3_in, a->d_k3_out,
-                                             a->d_desc);
+                                             a->d_desc, a->h_skips_seen);
     if (e != cudaSuccess) return (int)e;
     return (int)cudaGetLastError();
 }

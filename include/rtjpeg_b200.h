@@ -224,6 +224,14 @@ int  rtjgpu_set_pipeline(rtjgpu_ctx *ctx, int mode, int slice_frames);
  * 8-bit grey): what RTjpeg_set_format is to an RTjpeg_t (lib/RTjpeg.c:2421, dispatch :3580-3585).  Frames
  * come out as tight planes: YUV420 w*h*3/2 bytes (Y, U, V), YUV422 w*h*2 bytes (Y, then U and V of
  * (w/2) x h), grey w*h bytes.  Width and height must be multiples of 16 in every format here. */
+/* How K2 (IDCT + store) walks a device batch.  frames = 1: one CTA per (frame, row of macroblocks), every frame for itself.
+ * frames = n > 1: a CTA works through n consecutive frames of its row, the row's pixels staying in shared memory from frame to
+ * frame -- what a frame skips (lib/RTjpeg.c:2704: the block keeps what the persistent picture of lib/video_rtjpeg.c:81 held) is
+ * then not touched at all, instead of being decoded again from its last writer's stream for every frame it persists in.
+ * frames = 0 (the default): 8 when the batch before this one held skip markers, else 1 -- only the device knows about this
+ * batch's markers at launch time, and streams do not change their nature from batch to batch.  The frames are the same either
+ * way, bit for bit. */
+int  rtjgpu_set_frame_runs(rtjgpu_ctx *ctx, int frames);
 int  rtjgpu_set_format(rtjgpu_ctx *ctx, int format);
 
 /* The converters above over a batch that is resident on the device -- typically the frames

@@ -50,16 +50,17 @@ namespace {
 constexpr unsigned FULL = 0xFFFFFFFFu;
 constexpr int SY_THREADS = 64;
 constexpr int SY_WARPS = SY_THREADS / 32;
-constexpr int SY_LEAD = 16;                                /* 16-byte pieces of the lead-in walk in front of a chunk (256 bytes) */
-constexpr int SY_PMIN = SY_LEAD + 2;                       /* pieces per chunk at least (even): short frames use fewer lanes, not shorter chunks */
+constexpr int SY_LEAD = 4;                                 /* 16-byte pieces of the lead-in walk in front of a chunk (64 bytes) */
+constexpr int SY_PMIN = 18;                                /* pieces per chunk at least (even): short frames use fewer lanes, not shorter chunks */
 constexpr int SY_PMAX = 40;                                /* ... at most (even): a chunk's bit map is whole 32-bit words */
 constexpr int SY_SEG_MAX = SY_THREADS * SY_PMAX * 16;      /* bytes of a frame worked on at a time */
 constexpr int SY_LA = 80;                                  /* bytes walked behind a segment that is not the frame's last: the block that
                                                             * starts on its last byte (<= 64 bytes) and the start behind it, whole pieces */
 constexpr int SY_WORDS = (SY_SEG_MAX + SY_LA + 31) / 32 + 1;   /* bit map words */
 constexpr int SY_STAGE = 10240;                            /* block starts staged per emit round */
-constexpr int SY_MAX_DIRTY = 8;                            /* more chunks than this entered in the wrong state: not this kernel's stream */
+constexpr int SY_MAX_LOST = 8;                             /* more chunks than this whose repair walk never fell in step: not this kernel's stream */
 
+static_assert(SY_PMIN >= SY_LEAD + 2, "a lead-in lies inside the chunk in front");
 static_assert((SY_PMAX & 1) == 0 && (SY_PMIN & 1) == 0, "a chunk's bit map is whole 32-bit words");
 static_assert(SY_SEG_MAX + SY_LA + 16 < 65536, "positions inside a segment are 16 bit");
 
@@ -146,7 +147,7 @@ __device__ __forceinline__ uint4 sy_piece(const SySeg &sg, int i)
 /* pieces [p0, p1) from state r; BITS: leave the starts in the bit map.  Pieces that lie wholly inside the payload -- all but
  * the frame's first and last -- are read without a look at the payload's bounds, one piece ahead of their use. */
 template <bool BITS>
-__device__ __forceinline__ void walk16(const uint4 w, int &r, uint16_t *bits16, int i)
+__device__ __forceinline__ uint32_t walk16(const uint4 w, int &r, uint16_t *bits16, int i)
 {
     uint32_t bm = 0;
     walk4<BITS, 0>(w.x, r, bm);
@@ -154,6 +155,7 @@ __device__ __forceinline__ void walk16(const uint4 w, int &r, uint16_t *bits16, 
     walk4<BITS, 8>(w.z, r, bm);
     walk4<BITS, 12>(w.w, r, bm);
     if (BITS) bits16[i] = (uint16_t)bm;
+    return bm;
 }
 template <bool BITS>
 __device__ __noinline__ int walk_pieces(const SySeg sg, uint16_t *bits16, int p0, int p1, int r)
@@ -178,6 +180,20 @@ __device__ __noinline__ int walk_pieces(const SySeg sg, uint16_t *bits16, int p0
     }
     for (; i < p1; i++) walk16<BITS>(sy_piece(sg, i), r, bits16, i);     /* the last few, and what lies behind the payload */
     return r;
+}
+
+/* A repair walk: the chunk again, from the state it should have been entered in -- but only until it falls in step with the
+ * walk made before: a byte at which both start a block.  From there on the two are the same walk (and wrongly entered walks
+ * fall in step within a few blocks: that is what the lead-in relies on), so the rest of the chunk's bit map and its exit
+ * state stand.  Returns false if that did not happen inside the chunk; r is then the chunk's new exit state. */
+__device__ __noinline__ bool walk_repair(const SySeg sg, uint16_t *bits16, int p0, int p1, int &r)
+{
+    for (int i = p0; i < p1; i++) {
+        const uint32_t before = bits16[i];
+        const uint32_t now = walk16<true>(sy_piece(sg, i), r, bits16, i);
+        if (now & before) return true;
+    }
+    return false;
 }
 
 /* The 32-bit entry of a block (rtj_common.h): head = its first four bytes (DC, token 1, 2, 3), last = its last byte,
@@ -252,7 +268,7 @@ rtj_scan_sync_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc
 
         /* ---- lead-in: every lane walks the SY_LEAD pieces in front of its chunk from a guessed state ("a block starts
          *      here").  Run-length streams forget their past within a handful of blocks: at the chunk's first byte the
-         *      walk is, as a rule, in the true state.  Whether it is, is checked below -- never assumed. ---- */
+         *      walk is, more often than not, in the true state.  Whether it is, is checked below -- never assumed. ---- */
         const int p0 = tid * P, p1 = min(p0 + P, ptot);                /* this lane's chunk, in pieces */
         int r_in = 0;                                                  /* the state the chunk is entered in */
         if (tid == 0) r_in = seg0 == 0 ? 0 : sh.carry;
@@ -263,26 +279,31 @@ rtj_scan_sync_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc
         sh.exitst[tid] = (int8_t)r_out;
         __syncthreads();
 
-        /* ---- check: a chunk must have been entered in the state its left neighbour ended in.  Where not, it is walked
-         *      again from that state; its own exit state may change in turn, so this repeats until nothing changes (one
-         *      round as a rule; after round k the first k chunks are final whatever the stream). ---- */
+        /* ---- check: a chunk must have been entered in the state its left neighbour ended in.  Where not (the lead-in is
+         *      short: one lane in ten), a repair walk starts from that state and runs until it falls in step with the first
+         *      walk, a few blocks on; the chunk's exit state stands then.  A repair that runs to the chunk's end without
+         *      falling in step changes the exit state, and the next chunk is checked again: after round k the first k chunks
+         *      are final whatever the stream, so the result never depends on the guesses -- they only cost time. ---- */
         for (int round = 0;; round++) {
             const int want = tid > 0 ? (int)sh.exitst[tid - 1] : r_in;
             /* states <= 0 all mean "a block starts here" */
             const bool dirty = tid > 0 && p0 < ptot && max(want, 0) != max(r_in, 0);
-            const int ndirty = __syncthreads_count(dirty);
-            if (ndirty == 0) break;
-            if (redo && round == 0 && ndirty > SY_MAX_DIRTY) {
+            if (__syncthreads_count(dirty) == 0) break;
+            bool lost = false;
+            if (dirty) {
+                int r = r_in = want;
+                if (!walk_repair(sg, bits16, p0, p1, r)) {
+                    lost = true;
+                    r_out = r;
+                    sh.exitst[tid] = (int8_t)r;
+                }
+            }
+            const int nlost = __syncthreads_count(lost);
+            if (redo && round == 0 && nlost > SY_MAX_LOST) {
                 /* a stream that does not forget its past: leave the frame to the kernel whose cost does not depend on the content */
                 if (tid == 0) redo[f] = 1u;
                 return;
             }
-            if (dirty) {
-                r_in = want;
-                r_out = walk_pieces<true>(sg, bits16, p0, p1, r_in);
-                sh.exitst[tid] = (int8_t)r_out;
-            }
-            __syncthreads();
         }
         if (more && tid == SY_THREADS - 1) {
             /* the state the next segment starts in; the look-ahead behind this one */

@@ -65,14 +65,20 @@ __device__ __forceinline__ size_t block_at(int fmt, int i, int w, int h, int &pi
 
 } // namespace
 
-extern "C" __global__ void __launch_bounds__(EN_THREADS)
+/* INTER: pictures are compared with the blocks last sent (key_rate != 0); false: none of that is compiled in */
+template <bool INTER>
+__global__ void __launch_bounds__(EN_THREADS, INTER ? 3 : 4)
 rtj_encode_blocks_kernel(const rtj_encode_args A, int nblk, int nruns, int period, int first_boundary)
 {
+    __shared__ int32_t s_qt[128];                           /* the quantiser's multipliers: read 64 times a block */
+    s_qt[threadIdx.x] = A.d_qt[threadIdx.x];
+    static_assert(EN_THREADS == 128, "one multiplier a thread");
+    __syncthreads();
     const int b = blockIdx.x * EN_THREADS + threadIdx.x;
     const int run = blockIdx.y;
     if (b >= nblk) return;
     /* the pictures of this run: [f0, f1).  Run 0 may continue a run of the call before (key_count0 != 0). */
-    const bool inter = A.key_rate != 0;
+    constexpr bool inter = INTER;
     int f0, f1;
     if (!inter) { f0 = run; f1 = run + 1; }
     else if (first_boundary == 0) { f0 = run * period; f1 = min(f0 + period, A.F); }
@@ -82,14 +88,16 @@ rtj_encode_blocks_kernel(const rtj_encode_args A, int nblk, int nruns, int perio
     int pitch;
     const size_t at = block_at(A.fmt, b, A.w, A.h, pitch);
     const bool luma = A.fmt == RTJ_YUV420 ? (b % 6) < 4 : (b & 3) < 2;
-    const int32_t *qt = A.d_qt + (luma ? 0 : 64);
+    const int32_t *qt = s_qt + (luma ? 0 : 64);
     const int bt8 = luma ? A.lb8 : A.cb8, mask = luma ? A.lmask : A.cmask;
 
     /* the block last sent here, two coefficients per register */
-    uint32_t old[32];
+    uint32_t old[INTER ? 32 : 1];
     const bool continues = inter && run == 0 && A.key_count0 != 0;
+    if (INTER) {
 #pragma unroll
-    for (int k = 0; k < 32; k++) old[k] = continues ? reinterpret_cast<const uint32_t *>(A.d_old + (size_t)b * 64)[k] : 0u;
+        for (int k = 0; k < 32; k++) old[k] = continues ? reinterpret_cast<const uint32_t *>(A.d_old + (size_t)b * 64)[k] : 0u;
+    }
 
     for (int f = f0; f < f1; f++) {
         const uint8_t *src = A.d_frames + (size_t)f * fsz + at;
@@ -120,17 +128,17 @@ rtj_encode_blocks_kernel(const rtj_encode_args A, int nblk, int nruns, int perio
             }
         }
         bool skip = false;
-        if (inter) {
+        if (INTER) {
             bool same = true;
 #pragma unroll
-            for (int k = 0; k < 32; k++) {
+            for (int k = 0; k < (INTER ? 32 : 0); k++) {
                 const int o0 = (int)(short)(old[k] & 0xFFFFu), o1 = (int)(short)(old[k] >> 16);
                 same = same && abs(o0 - blk[2 * k]) <= mask && abs(o1 - blk[2 * k + 1]) <= mask;
             }
             skip = same;
             if (!same) {
 #pragma unroll
-                for (int k = 0; k < 32; k++) old[k] = ((uint32_t)blk[2 * k] & 0xFFFFu) | ((uint32_t)blk[2 * k + 1] << 16);
+                for (int k = 0; k < (INTER ? 32 : 0); k++) old[k] = ((uint32_t)blk[2 * k] & 0xFFFFu) | ((uint32_t)blk[2 * k + 1] << 16);
             }
         }
         uint8_t *slot = A.d_slots + ((size_t)f * nblk + b) * 64;
@@ -139,24 +147,39 @@ rtj_encode_blocks_kernel(const rtj_encode_args A, int nblk, int nruns, int perio
         else {
             const int dc = blk[0];
             slot[co++] = (uint8_t)(dc > 254 ? 254 : (dc < 0 ? 0 : dc));
+            /* the last coefficient that is not zero, to the next multiple of eight zig-zag places: everything behind it is one
+             * run token (most blocks of ordinary material end within the first sixteen places) */
+            int tail = 0;
+#pragma unroll
+            for (int g = 7; g >= 1; g--) {
+                int any = 0;
+#pragma unroll
+                for (int k = 0; k < 8; k++) any |= blk[EN_ZZ[8 * g + k]];
+                if (tail == 0 && any) tail = 8 * g + 8;
+            }
+            if (tail == 0) tail = 8;
+            tail = max(tail, min(bt8 + 1, 64));                        /* the raw prefix is always written */
             int zeros = 0;
 #pragma unroll
             for (int ci = 1; ci < 64; ci++) {
-                const int v = blk[EN_ZZ[ci]];
-                if (ci <= bt8) slot[co++] = (uint8_t)(v > 0 ? min(v, 127) : max(v, -128));
-                else if (v != 0) {
-                    if (zeros) { slot[co++] = (uint8_t)(63 + zeros); zeros = 0; }
-                    slot[co++] = (uint8_t)(v > 0 ? min(v, 63) : max(v, -64));
-                } else zeros++;
+                if (ci < tail) {
+                    const int v = blk[EN_ZZ[ci]];
+                    if (ci <= bt8) slot[co++] = (uint8_t)(v > 0 ? min(v, 127) : max(v, -128));
+                    else if (v != 0) {
+                        if (zeros) { slot[co++] = (uint8_t)(63 + zeros); zeros = 0; }
+                        slot[co++] = (uint8_t)(v > 0 ? min(v, 63) : max(v, -64));
+                    } else zeros++;
+                }
             }
+            zeros += 64 - tail;                                        /* the places from tail on are zero */
             if (zeros) slot[co++] = (uint8_t)(63 + zeros);
         }
         A.d_lens[(size_t)f * nblk + b] = (uint8_t)co;
     }
     /* the run that ends the batch leaves its blocks for the next call */
-    if (inter && f1 == A.F) {
+    if (INTER && f1 == A.F) {
 #pragma unroll
-        for (int k = 0; k < 32; k++) reinterpret_cast<uint32_t *>(A.d_old + (size_t)b * 64)[k] = old[k];
+        for (int k = 0; k < (INTER ? 32 : 0); k++) reinterpret_cast<uint32_t *>(A.d_old + (size_t)b * 64)[k] = old[k];
     }
 }
 
@@ -262,7 +285,8 @@ extern "C" int rtj_launch_encode(const rtj_encode_args *a, void *stream)
     else if (first_boundary == 0) nruns = (a->F + period - 1) / period;
     else nruns = 1 + (a->F > first_boundary ? (a->F - first_boundary + period - 1) / period : 0);
     const unsigned gx = (unsigned)((nblk + EN_THREADS - 1) / EN_THREADS);
-    rtj_encode_blocks_kernel<<<dim3(gx, (unsigned)nruns), EN_THREADS, 0, st>>>(*a, nblk, nruns, period, first_boundary);
+    if (inter) rtj_encode_blocks_kernel<true><<<dim3(gx, (unsigned)nruns), EN_THREADS, 0, st>>>(*a, nblk, nruns, period, first_boundary);
+    else rtj_encode_blocks_kernel<false><<<dim3(gx, (unsigned)nruns), EN_THREADS, 0, st>>>(*a, nblk, nruns, period, first_boundary);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return -(int)e;
     rtj_encode_layout_kernel<<<(unsigned)a->F, 256, 0, st>>>(a->d_lens, a->d_boff, a->d_fsize, nblk);

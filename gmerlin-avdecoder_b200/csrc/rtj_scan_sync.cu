@@ -10,31 +10,35 @@
  * depends on every byte before it -- but only through that one state.
  *
  * rtj_scan_chunk.cu makes the scan parallel by working out, for EVERY byte position, the length of the block
- * that would start there (~64 thread instructions per payload byte).  This kernel cuts the payload into one chunk per
- * lane and asks, per chunk, a cheaper question first:
+ * that would start there (~64 thread instructions per payload byte).  This kernel relies on a property of the
+ * grammar instead: run-length streams FORGET.  Start a walk anywhere, in any state, and within a handful of blocks
+ * it starts a block at a byte where the true parse starts one too -- from there on the two are the same walk
+ * (measured on the bench stream: 6 bytes in the median, 49 at the 90th percentile).  One CTA of 64 lanes per frame:
  *
- *   phase A   from the chunk's first byte on, ALL 64 states at once -- the set of states a parse could be in, a 63-bit
- *             mask of the r's plus one flag, advanced by a shift per byte -- until the set has shrunk to ONE state.
- *             From that byte on (the chunk's synchronisation point) the parse is known whatever came before:
- *             run-length streams forget their past quickly (a handful of blocks; measured on the bench stream:
- *             22 bytes in the median, 41 on average).  No guess, no verification: the true state is always one
- *             of the 64.
- *   phase B   every lane walks, one state, ~9 instructions a byte, from its own synchronisation point to the next
- *             lane's and leaves one bit per byte: "a block starts here".  Lane 0 starts from the frame's first
- *             byte (or from the state the previous segment ended in).  A lane that found no synchronisation point
- *             inside its chunk simply has no piece of its own; its left neighbour walks on.
- *   emit      the bit map is counted (prefix sum per 32 positions), turned into a list of block starts, and the
- *             32-bit entries are made by all threads, one block each, exactly as rtj_scan_chunk.cu makes them.
+ *   lead-in   the payload is cut into one chunk per lane.  Every lane walks the 64 bytes in front of its chunk from
+ *             a GUESSED state ("a block starts here") ...
+ *   walk      ... and then its chunk, ~8 instructions a byte, leaving one bit per byte: "a block starts here".
+ *             Lane 0 starts from the frame's first byte (or from the state the previous segment ended in).
+ *   check     a chunk must have been entered in the state its left neighbour ended in.  Where not (one chunk in ten
+ *             with so short a lead-in), a repair walk starts from that state and runs until it falls in step with
+ *             the walk made before; the rest of the chunk's bit map and its exit state then stand.  A repair that
+ *             reaches the chunk's end changes the exit state, and the next chunk is checked again: after round k the
+ *             first k chunks are final whatever the stream.  The guesses cost time when they are wrong, never
+ *             exactness (tests/test_sync_model.py pins the argument on the CPU).
+ *   emit      every lane lists the starts of its own chunk (a branch-free loop: one start per turn, the same
+ *             instructions for every lane), and the 32-bit entries are made by all threads, four blocks each per
+ *             turn, exactly as rtj_scan_chunk.cu makes them; stores coalesced.
  *
- * Streams that do not forget (every block 64 coefficient bytes long: noise at a high quality) would leave the whole
- * frame to lane 0.  The CTA sees that after phase A -- too many lanes without a synchronisation point -- and hands the
- * frame over (redo[f] = 1) to rtj_scan_chunk_kernel, which is launched behind this kernel and takes the flagged
- * frames only; its cost does not depend on the content.
+ * Streams that do not forget (every block 64 coefficient bytes long: noise at a high quality) would turn the check
+ * into a serial walk, one chunk a round.  The CTA sees that after the first round -- too many repairs that never fell
+ * in step -- and hands the frame over (redo[f] = 1) to rtj_scan_chunk_kernel, which is launched behind this kernel and
+ * takes the flagged frames only; its cost does not depend on the content.
  *
- * The payload of a frame (<= 39 KB a segment; larger frames in several segments, the state carried from one to the
- * next) arrives in shared memory as ONE bulk copy (cp.async.bulk, completion on an mbarrier).  Lanes read their
- * chunks as 8-byte groups; a chunk is an odd number of groups long, so that the 16 lanes of a half warp hit 16
- * different banks pairs.
+ * The payload is read straight from the packet, 16 bytes a lane and read (a lane's reads lie in a row: every 32-byte
+ * sector comes from L2 once), four reads under way; shared memory only holds the bit map and the list of starts
+ * (26 KB: eight CTAs, sixteen warps per SM).  Frames of more than 40 KB are worked through in segments, the state
+ * carried from one to the next.  (Earlier versions -- the set of all 64 states tracked as a bit mask until one is
+ * left; the payload in shared memory by one bulk copy -- are in the history and in DESIGN.md section 4.)
  *
  * Scope: frames whose tables have no raw 8-bit prefix (lb8 == cb8 == 0), like rtj_scan_chunk.cu; the others are
  * rtj_scan_mb_kernel's.  Same entries (rtj_common.h), counters and malformed-stream policy as the other flavours.

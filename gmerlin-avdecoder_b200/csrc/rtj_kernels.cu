@@ -1,25 +1,22 @@
 /*
  * rtj_kernels.cu -- sm_100a kernels of the RTjpeg decoder: serial scans, last-writer resolve, scan plan.
  *
- *   K1  rtj_scan_kernel     one warp walks one frame's run-length stream and
- *                           emits a 32-bit entry (payload offset + end-of-block
- *                           bound, or "skipped") for every 8x8 block.  Replaces
- *                           the `sp += RTjpeg_s2b(...)` pointer chase of
- *                           RTjpeg_decompressYUV420 (lib/RTjpeg.c:2701-2745) and
- *                           the length logic of RTjpeg_s2b (:157-186).
- *   K3  rtj_resolve_kernel  per block position, a last-writer scan over the
- *                           frames of the batch: for every skipped block, which
- *                           earlier frame coded it last.  Replaces the implicit
- *                           "skipped blocks keep the previous picture" state of
- *                           the reference (lib/video_rtjpeg.c:81 decodes every
- *                           packet into the same persistent frame).
- *   K2  rtj_idct_kernel     one CTA per (frame, macroblock row): unpack +
- *                           dequantise (RTjpeg_s2b value path, :162-183) +
- *                           integer AAN IDCT and clamp (RTjpeg_idct, :2209-2332)
- *                           into a shared-memory picture strip that leaves as
- *                           128-bit stores.  Blocks are bucketed by sparsity
- *                           class inside the CTA so that a warp runs one
- *                           specialised flow graph without divergence.
+ *   K1  (serial flavours)   rtj_scan_lane_kernel / rtj_scan_warp_kernel: one thread or one warp walks one frame's
+ *                           run-length stream and emits a 32-bit entry (payload offset + end-of-block bound, or
+ *                           "skipped") for every 8x8 block.  Replaces the `sp += RTjpeg_s2b(...)` pointer chase of
+ *                           RTjpeg_decompressYUV420 (lib/RTjpeg.c:2701-2745) and the length logic of RTjpeg_s2b
+ *                           (:157-186).  Kept as cross-checks; what AUTO runs is in rtj_scan_sync.cu (frames without
+ *                           a raw prefix), rtj_scan_chunk.cu (what that kernel hands over; the segment passes) and
+ *                           rtj_scan_mb.cu (frames with a raw prefix).  rtj_launch_scan below picks.
+ *   K3  rtj_resolve_last_kernel + rtj_resolve_kernel
+ *                           per block position, a last-writer scan over the frames of the batch: for every skipped
+ *                           block, which earlier frame coded it last (and, where that frame's entry carries the block
+ *                           inline, a copy of it).  Replaces the implicit "skipped blocks keep the previous picture"
+ *                           state of the reference (lib/video_rtjpeg.c:81 decodes every packet into the same
+ *                           persistent frame).
+ *   K1  rtj_scan_plan_*     the frame-level chain between the two passes of the segment-parallel arrangement.
+ *
+ * K2 (unpack + dequantise + integer AAN IDCT + clamp + store, rtj_idct_kernel) and K2b are in rtj_idct.cu.
  *
  * All arithmetic is 32-bit integer and bit-exact with the reference: no tensor
  * cores, no floating point.

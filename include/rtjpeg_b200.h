@@ -192,13 +192,14 @@ const char *rtjgpu_strerror(int code);
 /* cudaError_t of the last failing CUDA call on this context, as int. */
 int  rtjgpu_last_cuda_error(const rtjgpu_ctx *ctx);
 
-/* Which flavour of the block-offset scan (K1) runs.  AUTO (the default) picks between the two
- * chunk-parallel arrangements by batch size: CHUNK = one CTA per frame walks the frame's 8 KB
- * segments in turn (every byte position examined in parallel inside a segment) -- many frames;
- * SEGMENT = the segments of a frame go to separate CTAs, with a frame-level chain between a summary
- * pass and an emit pass -- few, large frames (and the one-frame RTjpeg_decompress).  LANE / WARP / WALK
- * force a serial walk instead: one thread per frame or one warp per frame.  The serial flavours are independent
- * implementations of the grammar, kept for cross-checks; they are several times slower than what AUTO picks. */
+/* Which flavour of the block-offset scan (K1) runs.  AUTO (the default) picks by batch size: many frames -- one CTA per
+ * frame, SYNC for frames without a raw prefix (lanes walk the stream from guessed states and repair what was guessed
+ * wrong; frames whose streams do not synchronise are handed to CHUNK's kernel) and the macroblock-level kernel for the
+ * others; few, large frames (and the one-frame RTjpeg_decompress) -- SEGMENT: the 8 KB segments of a frame go to separate
+ * CTAs, with a frame-level chain between a summary pass and an emit pass.  CHUNK = one CTA per frame walks the frame's
+ * segments in turn, every byte position examined in parallel inside a segment (round 1's kernel; its cost does not depend
+ * on the content).  LANE / WARP / WALK force a serial walk instead: one thread per frame or one warp per frame.  Every
+ * flavour is an independent implementation of the grammar and gives the same entries; the parity suite runs under each. */
 #define RTJGPU_SCAN_AUTO    0
 #define RTJGPU_SCAN_LANE    1
 #define RTJGPU_SCAN_WARP    2

@@ -19,6 +19,7 @@ e2e       same metric through the C ABI's host entry point (rtjgpu_decode_host):
 roofline  dominant kernel (K2), timed ALONE: separate steps in the serial arrangement (every stage on the caller's
           stream, CUDA events recorded by the library between the stages); algorithmic bytes = payload read + planes
           written.  whole_path_frac is the same bytes over the headline step time.
+on_device_consumers   end to end with the frames consumed on the device (fused RGB32 out; transcode through the GPU encoder)
 other_configs   the parity configs of BASELINE.json (inter GOP 30 at two masks, Q32 / Q255, 1920x1088 dense), measured in
           the same process after the headline (rank 0, N = 1).
 config5   BASELINE.json configs[4]: ONE inter-coded 1920x1088 stream, cut at clean frames on the host
@@ -259,6 +260,68 @@ def other_config(torch, g, D, name, w, h, q, frames, peak, sm_hz, steps=10, **kw
     ctx.close()
     del b
     torch.cuda.empty_cache()
+    return out
+
+
+def on_device_consumers(torch, g, D, peak, F=1024, steps=5):
+    """End to end through host buffers with the frames CONSUMED ON THE DEVICE, so that 622 KB a frame need not cross PCIe
+    (`e2e` above is bound by exactly that): packets in, decode, then (a) the reference's yuv420 -> RGB32 conversion fused into
+    the decode and the packed pixels out, (b) the GPU encoder (a transcode at another quality) and packets out.  configs[1]
+    geometry and stream, F frames a step; pinned host buffers; copies inside the timed region, wall clock."""
+    from gmerlin_avdecoder_b200 import capi
+    w, h = 720, 576
+    stream, offsets, _ = make_workload(F, seed=1)
+    desc, _ = g.plan(stream, offsets)
+    h_in = torch.from_numpy(stream).pin_memory()
+    h_desc = torch.from_numpy(desc.view(np.uint8)).pin_memory()
+    d_in = torch.empty(stream.size + g.STREAM_SLACK_BYTES, dtype=torch.uint8, device="cuda")
+    d_desc = torch.empty(h_desc.numel(), dtype=torch.uint8, device="cuda")
+    out = {}
+    st = torch.cuda.current_stream().cuda_stream
+    with g.BatchContext(torch.cuda.current_device()) as ctx:
+        # (a) decode -> RGB32 on the device -> host
+        pitch = w * 4
+        d_rgb = torch.empty((F, h, pitch), dtype=torch.uint8, device="cuda")
+        h_rgb = torch.empty((F, h, pitch), dtype=torch.uint8).pin_memory()
+
+        def rgb_step():
+            d_in[:stream.size].copy_(h_in, non_blocking=True)
+            d_desc.copy_(h_desc, non_blocking=True)
+            ctx.decode_device_rgb(d_in.data_ptr(), d_desc.data_ptr(), F, w, h, capi.CONV_RGB32, d_rgb.data_ptr(), pitch, h * pitch,
+                                  0xFF, None, None, st)
+            h_rgb.copy_(d_rgb, non_blocking=True)
+            torch.cuda.synchronize()
+
+        # (b) decode -> encode at Q = 64 on the device -> host
+        d_yuv = torch.empty((F, w * h * 3 // 2), dtype=torch.uint8, device="cuda")
+        cap = stream.size * 2 + (1 << 20)
+        d_pk = torch.empty(cap, dtype=torch.uint8, device="cuda")
+        d_off = torch.zeros(F + 1, dtype=torch.int64, device="cuda")
+        h_pk = torch.empty(cap, dtype=torch.uint8).pin_memory()
+        sizes = {}
+
+        def transcode_step():
+            d_in[:stream.size].copy_(h_in, non_blocking=True)
+            d_desc.copy_(h_desc, non_blocking=True)
+            ctx.decode_device(d_in.data_ptr(), d_desc.data_ptr(), F, w, h, d_yuv.data_ptr(), None, st)
+            ctx.encoder_config(64, 0, 0, 0)
+            ctx.encode_device(d_yuv.data_ptr(), F, w, h, d_pk.data_ptr(), cap, d_off.data_ptr(), st)
+            nbytes, overflow = ctx.encode_info()                       # (syncs: the size of what goes back)
+            assert not overflow
+            h_pk[:nbytes].copy_(d_pk[:nbytes], non_blocking=True)
+            torch.cuda.synchronize()
+            sizes["out"] = nbytes
+
+        for name, fn in (("decode_rgb32_d2h", rgb_step), ("decode_encode_d2h", transcode_step)):
+            fn()
+            fn()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                fn()
+            dt = time.perf_counter() - t0
+            d2h = int(F * h * pitch) if name == "decode_rgb32_d2h" else int(sizes["out"])
+            out[name] = {"value": F * steps / dt, "unit": "frames/s", "frames_per_step": F, "steps": steps,
+                         "h2d_bytes_per_step": int(stream.size + h_desc.numel()), "d2h_bytes_per_step": d2h}
     return out
 
 
@@ -514,6 +577,12 @@ def main():
             other_config(torch, g, D, "configs[3]: 1920x1088 Q=255 dense", 1920, 1088, 255, 128, peak, sm_hz, steps=5,
                          noise_y=60, noise_c=20),
         ]
+
+    if rank == 0 and world == 1 and not args.no_other_configs:
+        try:
+            line["on_device_consumers"] = on_device_consumers(torch, g, D, peak)
+        except Exception as exc:  # noqa: BLE001 -- informational: the line stands without it
+            line["on_device_consumers"] = {"error": repr(exc)}
 
     if not args.no_config5:
         c5 = run_config5(torch, dist, g, D, rank, world, local, max(3, min(args.steps, 20)), peak)

@@ -30,6 +30,10 @@ __device__ constexpr int EN_ZZ[64] = {
     0, 8, 1, 2, 9, 16, 24, 17, 10, 3, 4, 11, 18, 25, 32, 40, 33, 26, 19, 12, 5, 6, 13, 20, 27, 34, 41, 48, 56, 49, 42, 35,
     28, 21, 14, 7, 15, 22, 29, 36, 43, 50, 57, 58, 51, 44, 37, 30, 23, 31, 38, 45, 52, 59, 60, 53, 46, 39, 47, 54, 61, 62, 55, 63};
 
+/* ... and raster index i is zig-zag position EN_RANK[i] */
+__device__ constexpr int EN_RANK[64] = {
+    0, 2, 3, 9, 10, 20, 21, 35, 1, 4, 8, 11, 19, 22, 34, 36, 5, 7, 12, 18, 23, 33, 37, 48, 6, 13, 17, 24, 32, 38, 47, 49, 14, 16, 25, 31, 39, 46, 50, 57, 15, 26, 30, 40, 45, 51, 56, 58, 27, 29, 41, 44, 52, 55, 59, 62, 28, 42, 43, 53, 54, 60, 61, 63};
+
 /* the 8-point flow graph shared by both passes (:303-340, :346-389); r0 and r4 come out unscaled */
 __device__ __forceinline__ void fdct8(const int (&x)[8], int &r0, int &r1, int &r2, int &r3, int &r4, int &r5, int &r6, int &r7)
 {
@@ -71,6 +75,9 @@ __global__ void __launch_bounds__(EN_THREADS, INTER ? 3 : 4)
 rtj_encode_blocks_kernel(const rtj_encode_args A, int nblk, int nruns, int period, int first_boundary)
 {
     __shared__ int32_t s_qt[128];                           /* the quantiser's multipliers: read 64 times a block */
+    /* a row a thread: the block's token values in zig-zag order, then -- in place -- its bytes (RTjpeg_b2s never writes more
+     * bytes than it has read places); 17 words: the rows of a warp on different banks */
+    __shared__ uint32_t s_zz[EN_THREADS][17];
     s_qt[threadIdx.x] = A.d_qt[threadIdx.x];
     static_assert(EN_THREADS == 128, "one multiplier a thread");
     __syncthreads();
@@ -113,7 +120,9 @@ rtj_encode_blocks_kernel(const rtj_encode_args A, int nblk, int nruns, int perio
             ws[r * 8 + 0] = r0 << 8;
             ws[r * 8 + 4] = r4 << 8;
         }
-        int blk[64];
+        uint8_t *row = reinterpret_cast<uint8_t *>(s_zz[threadIdx.x]);
+        int blk[INTER ? 64 : 1];
+        int dc = 0;
 #pragma unroll
         for (int c = 0; c < 8; c++) {
             int x[8], y[8];
@@ -124,7 +133,16 @@ rtj_encode_blocks_kernel(const rtj_encode_args A, int nblk, int nruns, int perio
             for (int r = 0; r < 8; r++) {
                 /* DESCALE10 for rows 0 and 4, DESCALE20 for the others (:272-273), each narrowed to int16; then RTjpeg_quant */
                 const int v = (int)(short)((r == 0 || r == 4) ? (y[r] + 128) >> 8 : (y[r] + 32768) >> 16);
-                blk[r * 8 + c] = (int)(short)((v * qt[r * 8 + c] + 32767) >> 16);
+                const int q = (int)(short)((v * qt[r * 8 + c] + 32767) >> 16);
+                if (INTER) blk[r * 8 + c] = q;
+                /* what RTjpeg_b2s (:109-155) makes of the value at its zig-zag place: clamped to a byte inside the raw prefix,
+                 * to -64 .. 63 behind it */
+                const int place = EN_RANK[r * 8 + c];
+                if (place == 0) dc = q;
+                else {
+                    const int lim = place <= bt8 ? 127 : 63;
+                    row[place] = (uint8_t)(q > 0 ? min(q, lim) : max(q, -lim - 1));
+                }
             }
         }
         bool skip = false;
@@ -142,38 +160,33 @@ rtj_encode_blocks_kernel(const rtj_encode_args A, int nblk, int nruns, int perio
             }
         }
         uint8_t *slot = A.d_slots + ((size_t)f * nblk + b) * 64;
-        int co = 0;
-        if (skip) slot[co++] = 0xFF;
+        int co = 1;
+        if (skip) row[0] = 0xFF;
         else {
-            const int dc = blk[0];
-            slot[co++] = (uint8_t)(dc > 254 ? 254 : (dc < 0 ? 0 : dc));
-            /* the last coefficient that is not zero, to the next multiple of eight zig-zag places: everything behind it is one
-             * run token (most blocks of ordinary material end within the first sixteen places) */
-            int tail = 0;
-#pragma unroll
-            for (int g = 7; g >= 1; g--) {
-                int any = 0;
-#pragma unroll
-                for (int k = 0; k < 8; k++) any |= blk[EN_ZZ[8 * g + k]];
-                if (tail == 0 && any) tail = 8 * g + 8;
+            row[0] = (uint8_t)(dc > 254 ? 254 : (dc < 0 ? 0 : dc));
+            /* the last place that gets a byte of its own: the last value that is not zero, or the raw prefix's end;
+             * everything behind it is one run token (most blocks of ordinary material end within the first ten places) */
+            int last = 0;
+            for (int wv = 15; wv >= 0; wv--) {
+                uint32_t x4 = s_zz[threadIdx.x][wv];
+                if (wv == 0) x4 &= 0xFFFFFF00u;
+                if (x4) { last = 4 * wv + 3 - (__clz((int)x4) >> 3); break; }
             }
-            if (tail == 0) tail = 8;
-            tail = max(tail, min(bt8 + 1, 64));                        /* the raw prefix is always written */
+            last = max(last, min(bt8, 63));
             int zeros = 0;
-#pragma unroll
-            for (int ci = 1; ci < 64; ci++) {
-                if (ci < tail) {
-                    const int v = blk[EN_ZZ[ci]];
-                    if (ci <= bt8) slot[co++] = (uint8_t)(v > 0 ? min(v, 127) : max(v, -128));
-                    else if (v != 0) {
-                        if (zeros) { slot[co++] = (uint8_t)(63 + zeros); zeros = 0; }
-                        slot[co++] = (uint8_t)(v > 0 ? min(v, 63) : max(v, -64));
-                    } else zeros++;
-                }
+            for (int ci = 1; ci <= last; ci++) {
+                const int v = (int)(signed char)row[ci];
+                if (ci <= bt8) row[co++] = (uint8_t)v;
+                else if (v != 0) {
+                    if (zeros) { row[co++] = (uint8_t)(63 + zeros); zeros = 0; }
+                    row[co++] = (uint8_t)v;
+                } else zeros++;
             }
-            zeros += 64 - tail;                                        /* the places from tail on are zero */
-            if (zeros) slot[co++] = (uint8_t)(63 + zeros);
+            zeros += 63 - last;                                        /* the places behind `last` are zero */
+            if (zeros) row[co++] = (uint8_t)(63 + zeros);
         }
+        /* the bytes leave as words (what lies behind the block's last byte in its slot is never read) */
+        for (int k = 0; k < (co + 3) >> 2; k++) reinterpret_cast<uint32_t *>(slot)[k] = s_zz[threadIdx.x][k];
         A.d_lens[(size_t)f * nblk + b] = (uint8_t)co;
     }
     /* the run that ends the batch leaves its blocks for the next call */

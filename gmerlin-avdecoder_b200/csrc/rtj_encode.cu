@@ -78,6 +78,9 @@ rtj_encode_blocks_kernel(const rtj_encode_args A, int nblk, int nruns, int perio
     /* a row a thread: the block's token values in zig-zag order, then -- in place -- its bytes (RTjpeg_b2s never writes more
      * bytes than it has read places); 17 words: the rows of a warp on different banks */
     __shared__ uint32_t s_zz[EN_THREADS][17];
+    /* INTER: the quantised block itself, two values a word as the stored blocks hold them, for the comparison (kept out of
+     * the registers: the transform's 64 intermediate values live there) */
+    __shared__ uint32_t s_q[INTER ? EN_THREADS : 1][33];
     s_qt[threadIdx.x] = A.d_qt[threadIdx.x];
     static_assert(EN_THREADS == 128, "one multiplier a thread");
     __syncthreads();
@@ -121,7 +124,7 @@ rtj_encode_blocks_kernel(const rtj_encode_args A, int nblk, int nruns, int perio
             ws[r * 8 + 4] = r4 << 8;
         }
         uint8_t *row = reinterpret_cast<uint8_t *>(s_zz[threadIdx.x]);
-        int blk[INTER ? 64 : 1];
+        int16_t *qrow = reinterpret_cast<int16_t *>(s_q[INTER ? threadIdx.x : 0]);
         int dc = 0;
 #pragma unroll
         for (int c = 0; c < 8; c++) {
@@ -134,7 +137,7 @@ rtj_encode_blocks_kernel(const rtj_encode_args A, int nblk, int nruns, int perio
                 /* DESCALE10 for rows 0 and 4, DESCALE20 for the others (:272-273), each narrowed to int16; then RTjpeg_quant */
                 const int v = (int)(short)((r == 0 || r == 4) ? (y[r] + 128) >> 8 : (y[r] + 32768) >> 16);
                 const int q = (int)(short)((v * qt[r * 8 + c] + 32767) >> 16);
-                if (INTER) blk[r * 8 + c] = q;
+                if (INTER) qrow[r * 8 + c] = (int16_t)q;
                 /* what RTjpeg_b2s (:109-155) makes of the value at its zig-zag place: clamped to a byte inside the raw prefix,
                  * to -64 .. 63 behind it */
                 const int place = EN_RANK[r * 8 + c];
@@ -150,13 +153,15 @@ rtj_encode_blocks_kernel(const rtj_encode_args A, int nblk, int nruns, int perio
             bool same = true;
 #pragma unroll
             for (int k = 0; k < (INTER ? 32 : 0); k++) {
+                const uint32_t nw = s_q[INTER ? threadIdx.x : 0][k];
                 const int o0 = (int)(short)(old[k] & 0xFFFFu), o1 = (int)(short)(old[k] >> 16);
-                same = same && abs(o0 - blk[2 * k]) <= mask && abs(o1 - blk[2 * k + 1]) <= mask;
+                const int n0 = (int)(short)(nw & 0xFFFFu), n1 = (int)(short)(nw >> 16);
+                same = same && abs(o0 - n0) <= mask && abs(o1 - n1) <= mask;
             }
             skip = same;
             if (!same) {
 #pragma unroll
-                for (int k = 0; k < (INTER ? 32 : 0); k++) old[k] = ((uint32_t)blk[2 * k] & 0xFFFFu) | ((uint32_t)blk[2 * k + 1] << 16);
+                for (int k = 0; k < (INTER ? 32 : 0); k++) old[k] = s_q[INTER ? threadIdx.x : 0][k];
             }
         }
         uint8_t *slot = A.d_slots + ((size_t)f * nblk + b) * 64;

@@ -102,7 +102,7 @@ struct rtjgpu_ctx {
     int            slice_frames = 1184, slice0_frames = 1184;   /* multiples of RTJ_RESOLVE_T */
     bool           scan_priority = false;
     int            frame_run = 0;             /* rtjgpu_set_frame_runs: 0 = by the batch before, 1 = off, n = forced */
-    unsigned long long *h_skips_seen = nullptr;    /* pinned: skipped blocks of the last batch whose K3 has run */
+    unsigned long long *h_skips_seen = nullptr;    /* pinned: skipped blocks, raw-prefix frames of the last batch whose K3 has run */
     bool           slices_forced = false;     /* rtjgpu_set_pipeline / the environment gave a slice size: it holds in either arrangement */
     /* encoder: configuration, state between calls, workspace */
     int            enc_quality = 0, enc_lb8 = 0, enc_cb8 = 0;
@@ -184,14 +184,28 @@ int ws_reserve(rtjgpu_ctx *ctx, Workspace *ws, int F, int nblk)
 
 /* Workspace of the segment-parallel scan, when the batch qualifies: forced by the scan mode, or AUTO
  * with a batch too small to fill the device with one CTA per frame.  Fills *sp (sum == NULL: not used). */
-constexpr int    SEG_AUTO_MAX_FRAMES = 256;
+/* AUTO's choice between one CTA per frame and the segment-parallel arrangement.  The host knows the batch's geometry, not
+ * its payload (packets and descriptors are device memory): a block of ordinary material is ~4 bytes.  Measured on a B200
+ * (DESIGN.md section 3): one CTA per frame takes ~40 us per 40 KB segment of a frame whatever the batch, until the batch
+ * fills the device; the segment-parallel passes take ~55 us + 11 ns per KB of batch.  Frames of one segment (up to about
+ * 720x576) are never worth cutting up; large frames are, in small batches (a single 1920x1088 frame: 0.06 against 0.18 ms). */
+bool auto_wants_segments(const rtjgpu_ctx *ctx, int F, int nblk)
+{
+    /* Frames with a raw prefix (quality above 170) are another matter: their kernel walks 4 KB segments at ~25 us each, and
+     * a frame is many of them.  Whether a batch holds such frames only the device knows; the batch before is the guide (its
+     * count arrives in pinned memory, like the skip count that K2's arrangement goes by). */
+    if (((volatile unsigned long long *)ctx->h_skips_seen)[1]) return F <= 256;
+    const double frame_kb = (double)nblk * 4.0 / 1024.0;
+    const int nseg = (int)((frame_kb + 39.99) / 40.0);
+    return nseg > 1 && 0.055 + 1.1e-5 * (double)F * frame_kb < 0.040 * (double)nseg;
+}
 constexpr size_t SEG_MAX_SUM_BYTES = (size_t)1 << 30;
 constexpr size_t SEG_MAX_DEL_BYTES = (size_t)2 << 30;
 
 int seg_reserve(rtjgpu_ctx *ctx, Workspace *ws, int F, int nblk, int scan_mode, rtj_seg_plan *sp)
 {
     memset(sp, 0, sizeof(*sp));
-    if (scan_mode != RTJGPU_SCAN_SEGMENT && !(scan_mode == RTJGPU_SCAN_AUTO && F <= SEG_AUTO_MAX_FRAMES)) return RTJGPU_OK;
+    if (scan_mode != RTJGPU_SCAN_SEGMENT && !(scan_mode == RTJGPU_SCAN_AUTO && auto_wants_segments(ctx, F, nblk))) return RTJGPU_OK;
     /* a frame needs at most 64 bytes per block */
     const size_t maxseg = ((size_t)nblk * 64 + RTJ_SEG_BYTES_MB - 1) / RTJ_SEG_BYTES_MB + 1;   /* the smaller segment size rules */
     const size_t nseg = (size_t)F * maxseg, nsum = nseg * RTJ_SEG_NE;
@@ -524,8 +538,8 @@ int rtjgpu_create(int device, rtjgpu_ctx **out)
         if ((e = cudaMemcpy(ctx->d_tables, dev.data(), sizeof(rtj_dev_table) * RTJ_NUM_TABLES, cudaMemcpyHostToDevice)) != cudaSuccess) { rc = RTJGPU_E_CUDA; break; }
         if ((e = cudaMallocHost(&ctx->h_info_reset, sizeof(rtj_dev_info))) != cudaSuccess) { rc = RTJGPU_E_CUDA; break; }
         if ((e = cudaMallocHost(&ctx->h_info, sizeof(rtj_dev_info))) != cudaSuccess) { rc = RTJGPU_E_CUDA; break; }
-        if ((e = cudaMallocHost(&ctx->h_skips_seen, sizeof(unsigned long long))) != cudaSuccess) { rc = RTJGPU_E_CUDA; break; }
-        *ctx->h_skips_seen = 0;
+        if ((e = cudaMallocHost(&ctx->h_skips_seen, 2 * sizeof(unsigned long long))) != cudaSuccess) { rc = RTJGPU_E_CUDA; break; }
+        ctx->h_skips_seen[0] = ctx->h_skips_seen[1] = 0;
         memset(ctx->h_info_reset, 0, sizeof(rtj_dev_info));
         ctx->h_info_reset->first_bad_frame = -1;
         *ctx->h_info = *ctx->h_info_reset;

@@ -90,6 +90,7 @@ typedef struct rtj_dev_info {
     int                first_bad_frame;
     unsigned int       hard_blocks;      /* K2 -> K2b queue: mid-size blocks, filled from the front ... */
     unsigned int       hard_full;        /* ... and long blocks, filled from the back */
+    unsigned int       raw_frames;       /* frames whose tables have a raw prefix (K1 counts them; AUTO's next choice of arrangement goes by it) */
     unsigned int       slice_skips[RTJ_MAX_SLICES];   /* 0xFF markers per slice of frames (K1), what K3 decides on */
 } rtj_dev_info;
 

@@ -412,7 +412,10 @@ rtj_resolve_kernel(uint32_t *__restrict__ ent, const uint16_t *__restrict__ chun
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     /* how many blocks the batch skipped, left where the host sees it without asking (pinned memory): the next batch's
      * arrangement of K2 goes by it */
-    if (skips_seen && b == 0 && blockIdx.y == 0) *skips_seen = info->skipped_blocks;
+    if (skips_seen && b == 0 && blockIdx.y == 0) {
+        skips_seen[0] = info->skipped_blocks;
+        skips_seen[1] = info->raw_frames;                           /* ... and AUTO's choice of K1's arrangement */
+    }
     if (b >= nblk) return;
     if (!k3_any_skips(info, slice)) {                               /* (K1's counters: final before rtj_resolve_last_kernel started) */
         if (blockIdx.y == 0) carry_out[b] = (uint16_t)(f1 - 1);     /* every frame so far wrote every position */
@@ -479,7 +482,7 @@ rtj_resolve_kernel(uint32_t *__restrict__ ent, const uint16_t *__restrict__ chun
 /* ------------------------------------------------------------------------ */
 
 /* what the frame-level chain needs to know about a frame */
-struct PlanFrame { int len, unit, segbytes, nseg; };
+struct PlanFrame { int len, unit, segbytes, nseg; bool raw; };
 
 __device__ __forceinline__ PlanFrame plan_frame(const rtjgpu_frame_desc *__restrict__ desc, const rtj_dev_table *__restrict__ tables,
                                                 int f, int maxseg, int unit_blocks)
@@ -490,6 +493,7 @@ __device__ __forceinline__ PlanFrame plan_frame(const rtjgpu_frame_desc *__restr
     /* with a raw prefix the summaries count macroblocks (rtj_scan_mb.cu), without it blocks */
     const rtj_dev_table &tab = tables[min((int)d.table, RTJ_NUM_TABLES - 1)];
     const bool raw = (tab.bt8[0] | tab.bt8[1]) != 0;
+    p.raw = raw;
     p.unit = raw ? unit_blocks : 1;
     p.segbytes = raw ? RTJ_SEG_BYTES_MB : RTJ_SEG_BYTES;
     p.nseg = (int)min((long long)maxseg, ((long long)p.len + p.segbytes - 1) / p.segbytes);   /* segments that hold payload */
@@ -536,6 +540,7 @@ rtj_scan_plan_kernel(const rtjgpu_frame_desc *__restrict__ desc, const rtj_dev_t
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= F) return;
     const PlanFrame p = plan_frame(desc, tables, f, sp.maxseg, unit_blocks);
+    if (p.raw) atomicAdd(&info->raw_frames, 1u);
     const int nb = plan_walk(p, f, 0, sp.maxseg, 0, 0, nblk, sp);
     plan_close(f, nb, nblk, p.len, ent, frame_skips, info, sp);
 }
@@ -597,6 +602,7 @@ rtj_scan_plan_fill_kernel(const rtjgpu_frame_desc *__restrict__ desc, const rtj_
     if (t >= F * sp.ngroups) return;
     const int f = t / sp.ngroups, g = t - f * sp.ngroups;
     const PlanFrame p = plan_frame(desc, tables, f, sp.maxseg, unit_blocks);
+    if (p.raw && g == 0) atomicAdd(&info->raw_frames, 1u);
     const int s0 = g * RTJ_SEG_GROUP, s1 = min(s0 + RTJ_SEG_GROUP, sp.maxseg);
     const uint32_t gb = sp.gbase[(size_t)f * sp.ngroups + g];
     int nb;

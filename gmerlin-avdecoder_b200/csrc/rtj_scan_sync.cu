@@ -234,7 +234,10 @@ rtj_scan_sync_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc
     const rtjgpu_frame_desc d = desc[f];
     {
         const rtj_dev_table &tab = tables[min((int)d.table, RTJ_NUM_TABLES - 1)];
-        if (tab.bt8[0] | tab.bt8[1]) return;                           /* raw prefix: rtj_scan_mb_kernel's frame */
+        if (tab.bt8[0] | tab.bt8[1]) {                                 /* raw prefix: rtj_scan_mb_kernel's frame */
+            if (tid == 0) atomicAdd(&info->raw_frames, 1u);
+            return;
+        }
     }
 
     const uint8_t *pay = stream + d.offset + RTJPEG_B200_HEADER_BYTES;

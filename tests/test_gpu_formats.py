@@ -16,11 +16,11 @@ FMT_CLIPS = ["yuv422_inter_64x48_q200_gop4", "yuv422_intra_96x32_q128", "grey_in
              "grey_intra_96x32_q64"]
 
 
-@pytest.fixture(scope="module", params=["auto", "chunk", "lane", "warp", "sync", "runs"])
+@pytest.fixture(scope="module", params=["auto", "chunk", "lane", "warp", "sync", "runs", "segment"])
 def ctx(request):
     c = g.BatchContext(0)
     c.set_scan_mode({"auto": capi.SCAN_AUTO, "chunk": capi.SCAN_CHUNK, "lane": capi.SCAN_LANE,
-                     "warp": capi.SCAN_WARP, "sync": capi.SCAN_SYNC, "runs": capi.SCAN_AUTO}[request.param])
+                     "warp": capi.SCAN_WARP, "sync": capi.SCAN_SYNC, "runs": capi.SCAN_AUTO, "segment": capi.SCAN_SEGMENT}[request.param])
     if request.param == "runs":
         c.set_frame_runs(3)              # K2 works through runs of three frames, the strip staying on chip
     c.flavour = request.param

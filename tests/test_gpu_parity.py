@@ -15,14 +15,14 @@ from streams import clip, golden, interleave, reference_frames
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module", params=["auto", "chunk", "lane", "warp", "walk", "sync", "runs"])
+@pytest.fixture(scope="module", params=["auto", "chunk", "lane", "warp", "walk", "sync", "runs", "segment"])
 def ctx(request):
     """Every parity case runs under all flavours of the block-offset scan (K1): the default (which
     picks the segment-parallel arrangement for the small batches of this suite and one CTA per frame
     for the full-size one), one CTA per frame forced, and each serial kernel alone."""
     c = g.BatchContext(0)
     c.set_scan_mode({"auto": capi.SCAN_AUTO, "chunk": capi.SCAN_CHUNK, "lane": capi.SCAN_LANE,
-                     "warp": capi.SCAN_WARP, "walk": capi.SCAN_WALK, "sync": capi.SCAN_SYNC, "runs": capi.SCAN_AUTO}[request.param])
+                     "warp": capi.SCAN_WARP, "walk": capi.SCAN_WALK, "sync": capi.SCAN_SYNC, "runs": capi.SCAN_AUTO, "segment": capi.SCAN_SEGMENT}[request.param])
     if request.param == "runs":
         c.set_frame_runs(3)              # K2 works through runs of three frames, the strip staying on chip
     c.flavour = request.param

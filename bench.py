@@ -241,7 +241,7 @@ def other_config(torch, g, D, name, w, h, q, frames, peak, sm_hz, steps=10, **kw
     b = D.upload(stream, desc, w, h, device=0)
     for _ in range(3):
         D.decode(ctx, b)
-    torch.cuda.synchronize()
+        torch.cuda.synchronize()      # the library arranges a batch by what the batch before held (skipped blocks, raw prefixes)
     info = ctx.batch_info()
     assert info.bad_frames == 0
     ms, _ = time_steps(torch, D, ctx, b, steps, torch.cuda.synchronize)

@@ -24,7 +24,7 @@ def run(name, w, h, Q, F, steps=10, **kw):
     ctx.enable_timing(True)
     for _ in range(3):
         D.decode(ctx, b)
-    torch.cuda.synchronize()
+        torch.cuda.synchronize()      # the library arranges a batch by what the batch before held (skipped blocks, raw prefixes)
     info = ctx.batch_info()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()

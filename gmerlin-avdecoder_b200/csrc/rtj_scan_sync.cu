@@ -46,33 +46,36 @@
 #include <cuda_runtime.h>
 #include <stddef.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "rtj_common.h"
 
 namespace {
 
 constexpr unsigned FULL = 0xFFFFFFFFu;
-constexpr int SY_THREADS = 64;
-constexpr int SY_WARPS = SY_THREADS / 32;
+/* Lanes a frame (the CTA's threads): 128, or 256 in small batches, where a frame's latency is what counts; 64 is kept for
+ * comparison (rtj_launch_scan_sync picks). */
+constexpr int SY_MAX_THREADS = 256;
 constexpr int SY_LEAD = 4;                                 /* 16-byte pieces of the lead-in walk in front of a chunk (64 bytes) */
-constexpr int SY_PMIN = 18;                                /* pieces per chunk at least (even): short frames use fewer lanes, not shorter chunks */
-constexpr int SY_PMAX = 40;                                /* ... at most (even): a chunk's bit map is whole 32-bit words */
-constexpr int SY_SEG_MAX = SY_THREADS * SY_PMAX * 16;      /* bytes of a frame worked on at a time */
+constexpr int SY_SEG_MAX = 40960;                          /* bytes of a frame worked on at a time */
+__host__ __device__ constexpr int sy_pmax(int threads) { return SY_SEG_MAX / (16 * threads); }             /* pieces per chunk at most (even): a chunk's bit map is whole 32-bit words */
+__host__ __device__ constexpr int sy_pmin(int threads) { return sy_pmax(threads) < 18 ? sy_pmax(threads) : 18; }   /* ... at least (even): short frames use fewer lanes, not shorter chunks */
 constexpr int SY_LA = 80;                                  /* bytes walked behind a segment that is not the frame's last: the block that
                                                             * starts on its last byte (<= 64 bytes) and the start behind it, whole pieces */
 constexpr int SY_WORDS = (SY_SEG_MAX + SY_LA + 31) / 32 + 1;   /* bit map words */
 constexpr int SY_STAGE = 10240;                            /* block starts staged per emit round */
 constexpr int SY_MAX_LOST = 8;                             /* more chunks than this whose repair walk never fell in step: not this kernel's stream */
 
-static_assert(SY_PMIN >= SY_LEAD + 2, "a lead-in lies inside the chunk in front");
-static_assert((SY_PMAX & 1) == 0 && (SY_PMIN & 1) == 0, "a chunk's bit map is whole 32-bit words");
+static_assert(sy_pmin(SY_MAX_THREADS) >= SY_LEAD + 2, "a lead-in lies inside the chunk in front");
+static_assert((sy_pmax(64) & 1) == 0 && (sy_pmax(128) & 1) == 0 && (sy_pmax(256) & 1) == 0 && (sy_pmin(64) & 1) == 0 && (sy_pmin(256) & 1) == 0,
+              "a chunk's bit map is whole 32-bit words");
 static_assert(SY_SEG_MAX + SY_LA + 16 < 65536, "positions inside a segment are 16 bit");
 
 struct SyShared {
     uint32_t bits[SY_WORDS];             /* bit p: a block starts at byte p of the segment */
     uint16_t starts[SY_STAGE + 2];       /* one emit round's block starts */
-    int8_t   exitst[SY_THREADS];         /* the state every lane's walk left its chunk in */
-    int      wsum[SY_WARPS];
+    int8_t   exitst[SY_MAX_THREADS];     /* the state every lane's walk left its chunk in */
+    int      wsum[SY_MAX_THREADS / 32];
     int      carry;                      /* state at the first byte of the next segment */
     int      nb;                         /* blocks started so far in this frame */
     int      skips;
@@ -216,7 +219,8 @@ __device__ __forceinline__ uint32_t sy_entry(uint32_t head, uint32_t last, int d
 
 } // namespace
 
-__global__ void __launch_bounds__(SY_THREADS, 8)
+template <int SY_THREADS>
+__global__ void __launch_bounds__(SY_THREADS, 512 / SY_THREADS)
 rtj_scan_sync_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc *__restrict__ desc,
                      const rtj_dev_table *__restrict__ tables, int F, int nblk,
                      uint32_t *__restrict__ ent, uint32_t *__restrict__ frame_skips,
@@ -250,6 +254,7 @@ rtj_scan_sync_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc
     /* positions: byte p of the frame is gbase[p]; the payload is [mis, end).  A frame that fits one segment leaves room for
      * the start behind its last block (end + 1 at most) inside the lanes' chunks. */
     const int end = len > 0 ? mis + len : 0;
+    constexpr int SY_WARPS = SY_THREADS / 32, SY_PMAX = sy_pmax(SY_THREADS), SY_PMIN = sy_pmin(SY_THREADS);
     const int P = end + 8 > SY_SEG_MAX ? SY_PMAX : max(SY_PMIN, ((end + 8 + SY_THREADS * 32 - 1) / (SY_THREADS * 32)) * 2);
     const int SEG = SY_THREADS * P * 16;
 
@@ -478,7 +483,9 @@ rtj_scan_sync_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc
 
 extern "C" int rtj_scan_sync_init(void)
 {
-    cudaError_t e = cudaFuncSetAttribute(rtj_scan_sync_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SyShared));
+    cudaError_t e = cudaFuncSetAttribute(rtj_scan_sync_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SyShared));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(rtj_scan_sync_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SyShared));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(rtj_scan_sync_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SyShared));
     return e == cudaSuccess ? 0 : (int)e;
 }
 
@@ -487,7 +494,20 @@ extern "C" int rtj_launch_scan_sync(const rtj_launch_args *a, uint32_t *redo, vo
 {
     const int nblk = RTJ_FMT_NBLK(a->fmt, a->w, a->h);
     const int nf = a->f1 - a->f0;
-    rtj_scan_sync_kernel<<<(unsigned)nf, SY_THREADS, sizeof(SyShared), (cudaStream_t)stream>>>(
-        a->d_stream, a->d_desc, a->d_tables, a->f1, nblk, a->d_ent, a->d_frame_skips, a->d_info, redo, a->f0, a->slice);
+    /* Lanes a frame.  Few frames: 256 (a frame's latency is the batch's: 1920x1088, 120 frames: 0.20 ms with 64 lanes, 0.11 with
+     * 128, 0.09 with 256).  Many: 128 -- 320-byte chunks at the bench point; 64 lanes with chunks twice as long spend less on
+     * lead-ins but are 6 % slower there (0.255 against 0.239 ms per 4096 frames), 256 lose to their lead-ins. */
+    static const int forced = getenv("RTJPEG_B200_SYNC_THREADS") ? atoi(getenv("RTJPEG_B200_SYNC_THREADS")) : 0;
+    const int threads = forced ? forced : nf <= 300 ? 256 : 128;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (threads >= 256)
+        rtj_scan_sync_kernel<256><<<(unsigned)nf, 256, sizeof(SyShared), st>>>(
+            a->d_stream, a->d_desc, a->d_tables, a->f1, nblk, a->d_ent, a->d_frame_skips, a->d_info, redo, a->f0, a->slice);
+    else if (threads >= 128)
+        rtj_scan_sync_kernel<128><<<(unsigned)nf, 128, sizeof(SyShared), st>>>(
+            a->d_stream, a->d_desc, a->d_tables, a->f1, nblk, a->d_ent, a->d_frame_skips, a->d_info, redo, a->f0, a->slice);
+    else
+        rtj_scan_sync_kernel<64><<<(unsigned)nf, 64, sizeof(SyShared), st>>>(
+            a->d_stream, a->d_desc, a->d_tables, a->f1, nblk, a->d_ent, a->d_frame_skips, a->d_info, redo, a->f0, a->slice);
     return (int)cudaGetLastError();
 }

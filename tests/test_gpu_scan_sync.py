@@ -151,3 +151,18 @@ def test_workspace_few_large_frames_after_many_small_ones():
         got, _ = gpu_decode(c, s, o, w, h)
         want = reference_frames(s, o, w, h)
         assert np.array_equal(got, want), first_diff(got, want, w, h)
+
+
+@pytest.mark.parametrize("F", [40, 400, 700])
+def test_every_lane_count(F):
+    """The kernel runs 256, 128 or 64 lanes a frame by the size of the batch (few frames: more lanes, shorter chunks)."""
+    assert O.have_ref()
+    w, h = 176, 144
+    s, o = clip(w, h, 110, F, key_rate=11, lm=1, cm=2, noise_y=9, noise_c=2)
+    want = reference_frames(s, o, w, h)
+    with _ctx(capi.SCAN_SYNC) as c, _ctx(capi.SCAN_CHUNK) as k:
+        got, _ = gpu_decode(c, s, o, w, h)
+        assert np.array_equal(got, want), first_diff(got, want, w, h)
+        e1, i1 = _entries(c, s, o, w, h)
+        e2, i2 = _entries(k, s, o, w, h)
+        assert np.array_equal(e1, e2) and i1 == i2

@@ -58,7 +58,7 @@ constexpr unsigned FULL = 0xFFFFFFFFu;
 constexpr int SY_MAX_THREADS = 256;
 constexpr int SY_LEAD = 4;                                 /* 16-byte pieces of the lead-in walk in front of a chunk (64 bytes) */
 constexpr int SY_SEG_MAX = 40960;                          /* bytes of a frame worked on at a time */
-__host__ __device__ constexpr int sy_pmax(int threads) { return SY_SEG_MAX / (16 * threads); }             /* pieces per chunk at most (even): a chunk's bit map is whole 32-bit words */
+__host__ __device__ constexpr int sy_pmax(int threads) { return (SY_SEG_MAX / (16 * threads)) & ~1; }             /* pieces per chunk at most (even): a chunk's bit map is whole 32-bit words */
 __host__ __device__ constexpr int sy_pmin(int threads) { return sy_pmax(threads) < 18 ? sy_pmax(threads) : 18; }   /* ... at least (even): short frames use fewer lanes, not shorter chunks */
 constexpr int SY_LA = 80;                                  /* bytes walked behind a segment that is not the frame's last: the block that
                                                             * starts on its last byte (<= 64 bytes) and the start behind it, whole pieces */
@@ -496,7 +496,7 @@ extern "C" int rtj_launch_scan_sync(const rtj_launch_args *a, uint32_t *redo, vo
     const int nf = a->f1 - a->f0;
     /* Lanes a frame.  Few frames: 256 (a frame's latency is the batch's: 1920x1088, 120 frames: 0.20 ms with 64 lanes, 0.11 with
      * 128, 0.09 with 256).  Many: 128 -- 320-byte chunks at the bench point; 64 lanes with chunks twice as long spend less on
-     * lead-ins but are 6 % slower there (0.255 against 0.239 ms per 4096 frames), 256 lose to their lead-ins. */
+     * lead-ins but are 6 % slower there (0.255 against 0.239 ms per 4096 frames), 256 lose to their lead-ins (96: 0.254, 160: 0.276). */
     static const int forced = getenv("RTJPEG_B200_SYNC_THREADS") ? atoi(getenv("RTJPEG_B200_SYNC_THREADS")) : 0;
     const int threads = forced ? forced : nf <= 300 ? 256 : 128;
     cudaStream_t st = (cudaStream_t)stream;

@@ -167,7 +167,7 @@ __device__ __forceinline__ uint32_t walk16(const uint4 w, int &r, uint16_t *bits
 template <bool BITS>
 __device__ __noinline__ int walk_pieces(const SySeg sg, uint16_t *bits16, int p0, int p1, int r)
 {
-    constexpr int D = 4;                                               /* pieces on their way at any time */
+    constexpr int D = 2;                                               /* pieces on their way at any time (measured at 128 lanes a frame: 1: 0.233 ms, 2: 0.231, 3: 0.237, 4: 0.247) */
     int i = p0;
     if (i < p1 && i == 0 && sg.first) { walk16<BITS>(sy_piece(sg, 0), r, bits16, 0); i = 1; }
     const int pin = min(p1, sg.lim >> 4);

@@ -13,7 +13,8 @@
  * that would start there (~64 thread instructions per payload byte).  This kernel relies on a property of the
  * grammar instead: run-length streams FORGET.  Start a walk anywhere, in any state, and within a handful of blocks
  * it starts a block at a byte where the true parse starts one too -- from there on the two are the same walk
- * (measured on the bench stream: 6 bytes in the median, 49 at the 90th percentile).  One CTA of 64 lanes per frame:
+ * (measured on the bench stream: 6 bytes in the median, 49 at the 90th percentile).  One CTA per frame, 128 lanes
+ * (256 in small batches, where a frame's latency is the batch's):
  *
  *   lead-in   the payload is cut into one chunk per lane.  Every lane walks the 64 bytes in front of its chunk from
  *             a GUESSED state ("a block starts here") ...
@@ -35,8 +36,8 @@
  * takes the flagged frames only; its cost does not depend on the content.
  *
  * The payload is read straight from the packet, 16 bytes a lane and read (a lane's reads lie in a row: every 32-byte
- * sector comes from L2 once), four reads under way; shared memory only holds the bit map and the list of starts
- * (26 KB: eight CTAs, sixteen warps per SM).  Frames of more than 40 KB are worked through in segments, the state
+ * sector comes from L2 once), two reads under way; shared memory only holds the bit map and the list of starts
+ * (26 KB, 80 registers: six CTAs, 24 warps per SM).  Frames of more than 40 KB are worked through in segments, the state
  * carried from one to the next.  (Earlier versions -- the set of all 64 states tracked as a bit mask until one is
  * left; the payload in shared memory by one bulk copy -- are in the history and in DESIGN.md section 4.)
  *

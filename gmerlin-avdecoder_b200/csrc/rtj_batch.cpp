@@ -102,7 +102,8 @@ struct rtjgpu_ctx {
     int            slice_frames = 1184, slice0_frames = 1184;   /* multiples of RTJ_RESOLVE_T */
     bool           scan_priority = false;
     int            frame_run = 0;             /* rtjgpu_set_frame_runs: 0 = by the batch before, 1 = off, n = forced */
-    unsigned long long *h_skips_seen = nullptr;    /* pinned: skipped blocks, raw-prefix frames of the last batch whose K3 has run */
+    unsigned long long *h_skips_seen = nullptr;    /* pinned: skipped blocks, raw-prefix frames of the last batch whose K3 has run; raw-prefix frames
+                                                    * the self-synchronising walk gave up when it was last tried */
     bool           slices_forced = false;     /* rtjgpu_set_pipeline / the environment gave a slice size: it holds in either arrangement */
     /* encoder: configuration, state between calls, workspace */
     int            enc_quality = 0, enc_lb8 = 0, enc_cb8 = 0;
@@ -194,7 +195,10 @@ bool auto_wants_segments(const rtjgpu_ctx *ctx, int F, int nblk)
     /* Frames with a raw prefix (quality above 170) are another matter: their kernel walks 4 KB segments at ~25 us each, and
      * a frame is many of them.  Whether a batch holds such frames only the device knows; the batch before is the guide (its
      * count arrives in pinned memory, like the skip count that K2's arrangement goes by). */
-    if (((volatile unsigned long long *)ctx->h_skips_seen)[1]) return F <= 256;
+    /* (The self-synchronising walk takes such frames at a few us per 40 KB when their streams forget their past -- ordinary
+     * material does; noise at a high quality does not, and is what the segment-parallel passes remain for.) */
+    const volatile unsigned long long *seen = ctx->h_skips_seen;
+    if (seen[1]) return F <= 256 && seen[2] != 0;
     const double frame_kb = (double)nblk * 4.0 / 1024.0;
     const int nseg = (int)((frame_kb + 39.99) / 40.0);
     return nseg > 1 && 0.055 + 1.1e-5 * (double)F * frame_kb < 0.040 * (double)nseg;
@@ -359,6 +363,7 @@ int run_kernels(rtjgpu_ctx *ctx, Workspace *ws, const uint8_t *d_stream, const r
      * is the one before it): streams do not change their nature from batch to batch, and either arrangement is exact. */
     a.k2_run = ctx->frame_run ? ctx->frame_run : (*(volatile unsigned long long *)ctx->h_skips_seen ? RTJ_K2_RUN_FRAMES : 1);
     a.h_skips_seen = ctx->h_skips_seen;
+    a.raw_expected = ((volatile unsigned long long *)ctx->h_skips_seen)[1] != 0;
     a.d_walk = ws->d_walk;
     a.d_redo = ws->d_frame_skips + ws->cap_frames;
     a.d_ent = ws->d_ent; a.d_src = ws->d_src; a.d_frame_skips = ws->d_frame_skips; a.d_info = ws->d_info;
@@ -538,8 +543,8 @@ int rtjgpu_create(int device, rtjgpu_ctx **out)
         if ((e = cudaMemcpy(ctx->d_tables, dev.data(), sizeof(rtj_dev_table) * RTJ_NUM_TABLES, cudaMemcpyHostToDevice)) != cudaSuccess) { rc = RTJGPU_E_CUDA; break; }
         if ((e = cudaMallocHost(&ctx->h_info_reset, sizeof(rtj_dev_info))) != cudaSuccess) { rc = RTJGPU_E_CUDA; break; }
         if ((e = cudaMallocHost(&ctx->h_info, sizeof(rtj_dev_info))) != cudaSuccess) { rc = RTJGPU_E_CUDA; break; }
-        if ((e = cudaMallocHost(&ctx->h_skips_seen, 2 * sizeof(unsigned long long))) != cudaSuccess) { rc = RTJGPU_E_CUDA; break; }
-        ctx->h_skips_seen[0] = ctx->h_skips_seen[1] = 0;
+        if ((e = cudaMallocHost(&ctx->h_skips_seen, 3 * sizeof(unsigned long long))) != cudaSuccess) { rc = RTJGPU_E_CUDA; break; }
+        ctx->h_skips_seen[0] = ctx->h_skips_seen[1] = ctx->h_skips_seen[2] = 0;
         memset(ctx->h_info_reset, 0, sizeof(rtj_dev_info));
         ctx->h_info_reset->first_bad_frame = -1;
         *ctx->h_info = *ctx->h_info_reset;
@@ -1037,6 +1042,7 @@ int rtjgpu_scan_device(rtjgpu_ctx *ctx, const uint8_t *d_stream, const rtjgpu_fr
     a.d_ent = ctx->ws.d_ent; a.d_frame_skips = ctx->ws.d_frame_skips; a.d_info = ctx->ws.d_info;
     a.d_walk = ctx->ws.d_walk;
     a.d_redo = ctx->ws.d_frame_skips + ctx->ws.cap_frames;
+    a.raw_expected = ((volatile unsigned long long *)ctx->h_skips_seen)[1] != 0;
     a.row1 = RTJ_FMT_UNITS_Y(ctx->format, h);
     a.scan_mode = ctx->scan_mode;
     if ((rc = seg_reserve(ctx, &ctx->ws, F, nblk, ctx->scan_mode, &a.seg))) return rc;

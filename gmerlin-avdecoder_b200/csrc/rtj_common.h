@@ -91,6 +91,8 @@ typedef struct rtj_dev_info {
     unsigned int       hard_blocks;      /* K2 -> K2b queue: mid-size blocks, filled from the front ... */
     unsigned int       hard_full;        /* ... and long blocks, filled from the back */
     unsigned int       raw_frames;       /* frames whose tables have a raw prefix (K1 counts them; AUTO's next choice of arrangement goes by it) */
+    unsigned int       raw_walked;       /* ... of these, taken up by the self-synchronising walk (rtj_scan_sync_kernel<.., true>) */
+    unsigned int       raw_given_up;     /* ... and left to rtj_scan_mb_kernel by it: streams that do not forget their past */
     unsigned int       slice_skips[RTJ_MAX_SLICES];   /* 0xFF markers per slice of frames (K1), what K3 decides on */
 } rtj_dev_info;
 
@@ -132,7 +134,8 @@ typedef struct rtj_launch_args {
     int                      k2_run;        /* frames a CTA of K2 works through in turn, the strip staying on chip (1: one frame per CTA) */
     unsigned long long      *h_skips_seen;  /* pinned host word K3 leaves the batch's skip count in (what the next batch's k2_run goes by), or NULL */
     void                    *d_walk;        /* [F] int2: rtj_scan_walk_kernel's state between slices of blocks */
-    uint32_t                *d_redo;        /* [F] rtj_scan_sync_kernel: frames it leaves to rtj_scan_chunk_kernel */
+    uint32_t                *d_redo;        /* [F] rtj_scan_sync_kernel: frames it leaves to rtj_scan_chunk_kernel / rtj_scan_mb_kernel (RTJ_REDO_*) */
+    int                      raw_expected;  /* the batch before held frames with a raw prefix: launch the walk that takes them */
     int                      fmt;           /* RTJ_YUV420 / RTJ_YUV422 / RTJ_RGB8 */
     uint32_t                *d_ent;         /* [F][nblk] */
     uint16_t                *d_src;         /* [F][nblk] */
@@ -162,9 +165,13 @@ int rtj_launch_scan(const rtj_launch_args *a, void *stream);          /* returns
 int rtj_launch_scan_chunk(const rtj_launch_args *a, int phase, void *stream);    /* rtj_scan_chunk.cu */
 int rtj_scan_chunk_init(void);
 int rtj_launch_scan_chunk_redo(const rtj_launch_args *a, const uint32_t *redo, void *stream);   /* one CTA per frame, flagged frames only */
-int rtj_launch_scan_sync(const rtj_launch_args *a, uint32_t *redo, void *stream);               /* rtj_scan_sync.cu */
+/* rtj_scan_sync.cu.  redo[f]: 0 = the frame is done; else the kernel it is left to */
+#define RTJ_REDO_CHUNK 1u
+#define RTJ_REDO_MB    2u
+int rtj_launch_scan_sync(const rtj_launch_args *a, uint32_t *redo, int handover, void *stream);
+int rtj_launch_scan_sync_raw(const rtj_launch_args *a, uint32_t *redo, int handover, void *stream);   /* the frames marked RTJ_REDO_MB */
 int rtj_scan_sync_init(void);
-int rtj_launch_scan_mb(const rtj_launch_args *a, int phase, void *stream);       /* rtj_scan_mb.cu */
+int rtj_launch_scan_mb(const rtj_launch_args *a, int phase, const uint32_t *redo, void *stream);       /* rtj_scan_mb.cu; redo (phase 0): only the frames marked RTJ_REDO_MB */
 int rtj_launch_scan_walk(const rtj_launch_args *a, int b0, int b1, void *stream);   /* rtj_scan_walk.cu: blocks [b0, b1) of every frame */
 int rtj_scan_walk_init(void);
 

@@ -415,6 +415,7 @@ rtj_resolve_kernel(uint32_t *__restrict__ ent, const uint16_t *__restrict__ chun
     if (skips_seen && b == 0 && blockIdx.y == 0) {
         skips_seen[0] = info->skipped_blocks;
         skips_seen[1] = info->raw_frames;                           /* ... and AUTO's choice of K1's arrangement */
+        if (info->raw_walked) skips_seen[2] = info->raw_given_up;   /* (a batch in which the walk was not tried says nothing about it) */
     }
     if (b >= nblk) return;
     if (!k3_any_skips(info, slice)) {                               /* (K1's counters: final before rtj_resolve_last_kernel started) */
@@ -636,17 +637,22 @@ extern "C" int rtj_launch_scan(const rtj_launch_args *a, void *stream)
         /* one CTA per frame.  Frames without a raw prefix: the self-synchronising walk; the frames it hands over (streams
          * that do not forget their past) are scanned by rtj_scan_chunk_kernel right behind it.  SYNC keeps every such
          * frame in the walk (the cross-check of the parity suite). */
-        uint32_t *redo = a->scan_mode == RTJGPU_SCAN_AUTO ? a->d_redo : nullptr;
-        int e = rtj_launch_scan_sync(a, redo, stream);
-        if (!e && redo) e = rtj_launch_scan_chunk_redo(a, redo, stream);
-        if (!e) e = rtj_launch_scan_mb(a, 0, stream);
-        return e ? -e : (redo ? 3 : 2);
+        /* Frames with a raw prefix: the walk's other instantiation, launched where the batch before held such frames (or the
+         * flavour is forced); what it gives up -- and, where it was not launched, every such frame -- is rtj_scan_mb_kernel's. */
+        const int handover = a->scan_mode == RTJGPU_SCAN_AUTO;
+        const bool raw_pass = a->scan_mode == RTJGPU_SCAN_SYNC || a->raw_expected;
+        uint32_t *redo = a->d_redo;
+        int e = rtj_launch_scan_sync(a, redo, handover, stream);
+        if (!e && handover) e = rtj_launch_scan_chunk_redo(a, redo, stream);
+        if (!e && raw_pass) e = rtj_launch_scan_sync_raw(a, redo, handover, stream);
+        if (!e) e = rtj_launch_scan_mb(a, 0, redo, stream);
+        return e ? -e : 2 + (handover ? 1 : 0) + (raw_pass ? 1 : 0);
     }
     if (a->scan_mode == RTJGPU_SCAN_AUTO || a->scan_mode == RTJGPU_SCAN_CHUNK || a->scan_mode == RTJGPU_SCAN_SEGMENT) {
         if (a->seg.sum) {
             /* few frames: their segments are parsed by separate CTAs -- summaries, frame-level chain, emit */
             int e = rtj_launch_scan_chunk(a, 1, stream);
-            if (!e) e = rtj_launch_scan_mb(a, 1, stream);
+            if (!e) e = rtj_launch_scan_mb(a, 1, nullptr, stream);
             if (e) return -e;
             int launches = 5;
             if (a->seg.gsum) {
@@ -662,12 +668,12 @@ extern "C" int rtj_launch_scan(const rtj_launch_args *a, void *stream)
                                                                       RTJ_FMT_UNIT_BLOCKS(a->fmt));
             if ((e = (int)cudaGetLastError())) return -e;
             e = rtj_launch_scan_chunk(a, 2, stream);
-            if (!e) e = rtj_launch_scan_mb(a, 2, stream);
+            if (!e) e = rtj_launch_scan_mb(a, 2, nullptr, stream);
             return e ? -e : launches;
         }
         int e = rtj_launch_scan_chunk(a, 0, stream);
         if (e) return -e;
-        e = rtj_launch_scan_mb(a, 0, stream);
+        e = rtj_launch_scan_mb(a, 0, nullptr, stream);
         return e ? -e : 2;
     }
     /* rtjgpu_set_scan_mode() forces one serial flavour for every frame: one lane per frame (cheap in
@@ -675,7 +681,7 @@ extern "C" int rtj_launch_scan(const rtj_launch_args *a, void *stream)
     if (a->scan_mode == RTJGPU_SCAN_WALK) {
         /* the walker takes the frames without raw prefix, rtj_scan_mb_kernel the others */
         int e = rtj_launch_scan_walk(a, 0, nblk, stream);
-        if (!e) e = rtj_launch_scan_mb(a, 0, stream);
+        if (!e) e = rtj_launch_scan_mb(a, 0, nullptr, stream);
         return e ? -e : 2;
     }
     if (a->scan_mode == RTJGPU_SCAN_LANE) {

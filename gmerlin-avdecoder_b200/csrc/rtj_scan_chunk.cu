@@ -111,7 +111,7 @@ rtj_scan_chunk_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_des
          * that one is done (and lets the grid behind itself in likewise); its flags are final after the wait */
         asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
         asm volatile("griddepcontrol.wait;" ::: "memory");
-        if (!redo[f]) return;                                          /* only the frames it left */
+        if (redo[f] != RTJ_REDO_CHUNK) return;                         /* only the frames it left */
     }
     const rtjgpu_frame_desc d = desc[f];
     {

@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(MB_THREADS, 7)
 rtj_scan_mb_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc *__restrict__ desc,
                    const rtj_dev_table *__restrict__ tables, int F, int nblk,
                    uint32_t *__restrict__ ent, uint32_t *__restrict__ frame_skips,
-                   rtj_dev_info *__restrict__ info, const rtj_seg_plan sp, int f0, int slice)
+                   rtj_dev_info *__restrict__ info, const rtj_seg_plan sp, int f0, int slice, const uint32_t *__restrict__ redo)
 {
     constexpr int unit = RTJ_FMT_UNIT_BLOCKS(FMT), unit_luma = RTJ_FMT_UNIT_LUMA(FMT);
     extern __shared__ __align__(16) uint8_t mb_smem[];
@@ -124,6 +124,13 @@ rtj_scan_mb_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc *
     const int tid = threadIdx.x, lane = tid & 31;
     const int f = (PHASE == 0 ? blockIdx.x : blockIdx.y) + f0;        /* F: one behind the last frame of this launch */
     if (f >= F) return;
+    if (PHASE == 0 && redo) {
+        /* behind the self-synchronising walks (rtj_scan_sync.cu): only the frames they marked as this kernel's; the marks are
+         * final when the grids in front are done */
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        if (redo[f] != RTJ_REDO_MB) return;
+    }
     const rtjgpu_frame_desc d = desc[f];
     const rtj_dev_table &tab = tables[min((int)d.table, RTJ_NUM_TABLES - 1)];          /* descriptors are the caller's memory */
     const int lb8 = tab.bt8[0], cb8 = tab.bt8[1];
@@ -395,8 +402,10 @@ rtj_scan_mb_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc *
             if (tid < nwalk) {
                 /* a macroblock belongs to the chunk it starts in; its later blocks may lie behind the chunk */
                 while ((k6 != 0 || q < min(qend, lim)) && i < r1) {
-                    if (q >= lim) starts[i - r0] = 0xFFFFu;                 /* the payload ended inside this macroblock */
-                    else {
+                    if (q >= lim) {
+                        starts[i - r0] = 0xFFFFu;                           /* the payload ended inside this macroblock: */
+                        lastend = max(lastend, seg0 + lim + 1);             /* a frame that wants more than it has is flagged */
+                    } else {
                         starts[i - r0] = (uint16_t)(q | (k6 << 13));
                         q += (k6 < unit_luma ? dLb : dCb)[q];
                         lastend = seg0 + q;
@@ -485,14 +494,15 @@ rtj_scan_mb_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc *
 namespace {
 
 template <int FMT>
-cudaError_t scan_mb_launch(const rtj_launch_args *a, int phase, int nblk, cudaStream_t st)
+cudaError_t scan_mb_launch(const rtj_launch_args *a, int phase, int nblk, const uint32_t *redo, cudaStream_t st)
 {
     const int nf = a->f1 - a->f0;
     const dim3 grid = phase == 0 ? dim3((unsigned)nf) : dim3((unsigned)a->seg.maxseg, (unsigned)nf);
     if (phase == 0) {
         /* One CTA per frame, behind the kernel that takes the frames without a raw prefix.  The two share nothing (every frame
          * is one kernel's or the other's), so this grid may start while that one's last CTAs are still at work: programmatic
-         * stream serialisation, and no wait for the grid in front. */
+         * stream serialisation, and no wait for the grid in front -- unless the kernels in front say which frames are left
+         * (redo), which is known when they are done. */
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = grid;
         cfg.blockDim = dim3(MB_THREADS);
@@ -504,14 +514,14 @@ cudaError_t scan_mb_launch(const rtj_launch_args *a, int phase, int nblk, cudaSt
         cfg.attrs = attr;
         cfg.numAttrs = 1;
         const cudaError_t e = cudaLaunchKernelEx(&cfg, rtj_scan_mb_kernel<0, FMT>, a->d_stream, a->d_desc, a->d_tables, a->f1, nblk, a->d_ent,
-                                                 a->d_frame_skips, a->d_info, a->seg, a->f0, a->slice);
+                                                 a->d_frame_skips, a->d_info, a->seg, a->f0, a->slice, redo);
         if (e != cudaSuccess) return e;
     } else if (phase == 1)
         rtj_scan_mb_kernel<1, FMT><<<grid, MB_THREADS, sizeof(MbShared), st>>>(
-            a->d_stream, a->d_desc, a->d_tables, a->f1, nblk, a->d_ent, a->d_frame_skips, a->d_info, a->seg, a->f0, a->slice);
+            a->d_stream, a->d_desc, a->d_tables, a->f1, nblk, a->d_ent, a->d_frame_skips, a->d_info, a->seg, a->f0, a->slice, nullptr);
     else
         rtj_scan_mb_kernel<2, FMT><<<grid, MB_THREADS, sizeof(MbShared), st>>>(
-            a->d_stream, a->d_desc, a->d_tables, a->f1, nblk, a->d_ent, a->d_frame_skips, a->d_info, a->seg, a->f0, a->slice);
+            a->d_stream, a->d_desc, a->d_tables, a->f1, nblk, a->d_ent, a->d_frame_skips, a->d_info, a->seg, a->f0, a->slice, nullptr);
     return cudaGetLastError();
 }
 
@@ -526,13 +536,13 @@ cudaError_t scan_mb_attr()
 
 } // namespace
 
-extern "C" int rtj_launch_scan_mb(const rtj_launch_args *a, int phase, void *stream)
+extern "C" int rtj_launch_scan_mb(const rtj_launch_args *a, int phase, const uint32_t *redo, void *stream)
 {
     static_assert(MB_S == RTJ_SEG_BYTES_MB && MB_DLA <= RTJ_SEG_NE, "segment size and entry range are shared with the frame-level chain");
     const int nblk = RTJ_FMT_NBLK(a->fmt, a->w, a->h);
     cudaStream_t st = (cudaStream_t)stream;
-    return (int)(a->fmt == 0 ? scan_mb_launch<0>(a, phase, nblk, st) : a->fmt == 1 ? scan_mb_launch<1>(a, phase, nblk, st)
-                                                                     : scan_mb_launch<2>(a, phase, nblk, st));
+    return (int)(a->fmt == 0 ? scan_mb_launch<0>(a, phase, nblk, redo, st) : a->fmt == 1 ? scan_mb_launch<1>(a, phase, nblk, redo, st)
+                                                                           : scan_mb_launch<2>(a, phase, nblk, redo, st));
 }
 
 extern "C" int rtj_scan_mb_init(void)

@@ -58,6 +58,7 @@ constexpr unsigned FULL = 0xFFFFFFFFu;
  * comparison (rtj_launch_scan_sync picks). */
 constexpr int SY_MAX_THREADS = 256;
 constexpr int SY_LEAD = 4;                                 /* 16-byte pieces of the lead-in walk in front of a chunk (64 bytes) */
+constexpr int SY_LEAD_RAW = 12;                            /* ... for frames with a raw prefix (192 bytes) */
 constexpr int SY_SEG_MAX = 40960;                          /* bytes of a frame worked on at a time */
 __host__ __device__ constexpr int sy_pmax(int threads) { return (SY_SEG_MAX / (16 * threads)) & ~1; }             /* pieces per chunk at most (even): a chunk's bit map is whole 32-bit words */
 __host__ __device__ constexpr int sy_pmin(int threads) { return sy_pmax(threads) < 18 ? sy_pmax(threads) : 18; }   /* ... at least (even): short frames use fewer lanes, not shorter chunks */
@@ -75,7 +76,7 @@ static_assert(SY_SEG_MAX + SY_LA + 16 < 65536, "positions inside a segment are 1
 struct SyShared {
     uint32_t bits[SY_WORDS];             /* bit p: a block starts at byte p of the segment */
     uint16_t starts[SY_STAGE + 2];       /* one emit round's block starts */
-    int8_t   exitst[SY_MAX_THREADS];     /* the state every lane's walk left its chunk in */
+    int16_t  exitst[SY_MAX_THREADS];     /* the state every lane's walk left its chunk in (raw-prefix frames: and the block's place in its unit) */
     int      wsum[SY_MAX_THREADS / 32];
     int      carry;                      /* state at the first byte of the next segment */
     int      nb;                         /* blocks started so far in this frame */
@@ -92,8 +93,34 @@ struct SyShared {
  * FMA pipe idles.  dp4a with a one-hot second operand picks a byte out of a word AND adds it to the state in one
  * instruction of the FMA pipe (measured, tools/pipe_rates2.cu: 0.5 / clock, pairs 1:1 with LOP3): the per-byte step is
  * two of them, one compare and one select. */
-template <bool BITS, int bit0>
-__device__ __forceinline__ void walk4(uint32_t W, int &r, uint32_t &bm)
+/* Frames whose tables have a RAW PREFIX (lib/RTjpeg.c:2362-2367, read by RTjpeg_s2b :165-169: the first bt8 bytes behind the
+ * DC are coefficients whatever their value; bt8 differs between luma and chroma) need two more things in the state: which
+ * block of its unit (macroblock: 4 luma + 2 chroma) the walk is in, and whether it is still inside the prefix.  The place in
+ * the unit is kept as a PRMT selector, 0x7770 | place: one PRMT looks up the threshold above which r means "inside the
+ * prefix" (63 - bt8 of the block's plane), another the selector of the next place.  Bytes 0 .. 5 of the two tables are the
+ * places, byte 7 is what the selector's upper nibbles pick: 0 in the thresholds, 0x77 in the successors. */
+struct SyTab {
+    uint32_t thlo, thhi, nlo, nhi;
+};
+constexpr uint32_t SY_SEL = 0x77777770u;
+__device__ __forceinline__ SyTab sy_make_tab(int unit, int unit_luma, int lb8, int cb8)
+{
+    unsigned long long th = 0, nx = 0x7700000000000000ull;
+    for (int p = 0; p < unit; p++) {
+        th |= (unsigned long long)(63 - min(p < unit_luma ? lb8 : cb8, 63)) << (8 * p);
+        nx |= (unsigned long long)(0x70 | (p + 1 == unit ? 0 : p + 1)) << (8 * p);
+    }
+    SyTab t;
+    t.thlo = (uint32_t)th; t.thhi = (uint32_t)(th >> 32); t.nlo = (uint32_t)nx; t.nhi = (uint32_t)(nx >> 32);
+    return t;
+}
+/* a walk's state as one word: r in the low byte (signed), the place in the unit above it */
+__device__ __forceinline__ int sy_pack(int r, uint32_t c) { return (r & 0xFF) | (int)((c & 7u) << 8); }
+__device__ __forceinline__ int sy_r(int st) { return (int)(int8_t)st; }
+__device__ __forceinline__ uint32_t sy_c(int st) { return SY_SEL | (uint32_t)(st >> 8); }
+
+template <bool BITS, int bit0, bool RAW>
+__device__ __forceinline__ void walk4(uint32_t W, int &r, uint32_t &c, const SyTab &tb, uint32_t &bm)
 {
     const uint32_t runs = W & ~(W >> 1) & 0x40404040u;                   /* bit 6 of every run token */
     const uint32_t NX = ~(W & (runs - (runs >> 6)));                     /* per byte, as a signed byte: -(what it fills) */
@@ -106,6 +133,13 @@ __device__ __forceinline__ void walk4(uint32_t W, int &r, uint32_t &bm)
         asm("dp4a.s32.u32 %0, %1, %2, %3;" : "=r"(t) : "r"(NX), "r"(1u << (8 * k)), "r"(r));         \
         asm("dp4a.u32.u32 %0, %1, %2, %3;" : "=r"(g) : "r"(G), "r"(1u << (8 * k)), "r"(0));          \
         const bool at = r <= 0;                                                                      \
+        if (RAW) {                                                                                   \
+            /* inside the prefix every byte is a coefficient: one place */                           \
+            const int thr = (int)__byte_perm(tb.thlo, tb.thhi, c);                                   \
+            const uint32_t cn = __byte_perm(tb.nlo, tb.nhi, c);                                      \
+            t = r > thr ? r - 1 : t;                                                                 \
+            c = at ? cn : c;                       /* the block that starts here is the unit's next */ \
+        }                                                                                            \
         r = at ? g : t;                                                                              \
         if (BITS) asm("{ .reg .pred p; setp.ne.u32 p, %1, 0; @p add.u32 %0, %0, %2; }" : "+r"(bm) : "r"((unsigned)at), "n"(1u << (bit0 + k))); \
     }
@@ -154,23 +188,26 @@ __device__ __forceinline__ uint4 sy_piece(const SySeg &sg, int i)
 
 /* pieces [p0, p1) from state r; BITS: leave the starts in the bit map.  Pieces that lie wholly inside the payload -- all but
  * the frame's first and last -- are read without a look at the payload's bounds, one piece ahead of their use. */
-template <bool BITS>
-__device__ __forceinline__ uint32_t walk16(const uint4 w, int &r, uint16_t *bits16, int i)
+template <bool BITS, bool RAW>
+__device__ __forceinline__ uint32_t walk16(const uint4 w, int &r, uint32_t &c, const SyTab &tb, uint16_t *bits16, int i)
 {
     uint32_t bm = 0;
-    walk4<BITS, 0>(w.x, r, bm);
-    walk4<BITS, 4>(w.y, r, bm);
-    walk4<BITS, 8>(w.z, r, bm);
-    walk4<BITS, 12>(w.w, r, bm);
+    walk4<BITS, 0, RAW>(w.x, r, c, tb, bm);
+    walk4<BITS, 4, RAW>(w.y, r, c, tb, bm);
+    walk4<BITS, 8, RAW>(w.z, r, c, tb, bm);
+    walk4<BITS, 12, RAW>(w.w, r, c, tb, bm);
     if (BITS) bits16[i] = (uint16_t)bm;
     return bm;
 }
-template <bool BITS>
-__device__ __noinline__ int walk_pieces(const SySeg sg, uint16_t *bits16, int p0, int p1, int r)
+/* st: the state -- r itself, or sy_pack(r, place) for frames with a raw prefix */
+template <bool BITS, bool RAW>
+__device__ __noinline__ int walk_pieces(const SySeg sg, uint16_t *bits16, int p0, int p1, int st, const SyTab tb)
 {
     constexpr int D = 2;                                               /* pieces on their way at any time (measured at 128 lanes a frame: 1: 0.233 ms, 2: 0.231, 3: 0.237, 4: 0.247) */
+    int r = RAW ? sy_r(st) : st;
+    uint32_t c = RAW ? sy_c(st) : 0u;
     int i = p0;
-    if (i < p1 && i == 0 && sg.first) { walk16<BITS>(sy_piece(sg, 0), r, bits16, 0); i = 1; }
+    if (i < p1 && i == 0 && sg.first) { walk16<BITS, RAW>(sy_piece(sg, 0), r, c, tb, bits16, 0); i = 1; }
     const int pin = min(p1, sg.lim >> 4);
     if (i + D <= pin) {
         /* a new sector comes from L2, several hundred clocks, and the walk of one piece takes about as long */
@@ -182,50 +219,75 @@ __device__ __noinline__ int walk_pieces(const SySeg sg, uint16_t *bits16, int p0
             for (int j = 0; j < D; j++) {
                 const uint4 cur = buf[j];
                 buf[j] = __ldg(sg.src + min(i + D + j, pin - 1));
-                walk16<BITS>(cur, r, bits16, i + j);
+                walk16<BITS, RAW>(cur, r, c, tb, bits16, i + j);
             }
         }
     }
-    for (; i < p1; i++) walk16<BITS>(sy_piece(sg, i), r, bits16, i);     /* the last few, and what lies behind the payload */
-    return r;
+    for (; i < p1; i++) walk16<BITS, RAW>(sy_piece(sg, i), r, c, tb, bits16, i);     /* the last few, and what lies behind the payload */
+    return RAW ? sy_pack(r, c) : r;
 }
 
 /* A repair walk: the chunk again, from the state it should have been entered in -- but only until it falls in step with the
  * walk made before: a byte at which both start a block.  From there on the two are the same walk (and wrongly entered walks
  * fall in step within a few blocks: that is what the lead-in relies on), so the rest of the chunk's bit map and its exit
- * state stand.  Returns false if that did not happen inside the chunk; r is then the chunk's new exit state. */
-__device__ __noinline__ bool walk_repair(const SySeg sg, uint16_t *bits16, int p0, int p1, int &r)
+ * state stand.  Returns false if that did not happen inside the chunk; st is then the chunk's new exit state.
+ * With a raw prefix the two walks must also agree on WHICH block of its unit starts at that byte.  The bit map does not say;
+ * the number of starts each walk has made since the chunk's first byte does: place = place at entry + starts so far.
+ * was: the state the first walk entered the chunk in. */
+template <bool RAW>
+__device__ __noinline__ bool walk_repair(const SySeg sg, uint16_t *bits16, int p0, int p1, int &st, int was, int unit, const SyTab tb)
 {
+    int r = RAW ? sy_r(st) : st;
+    uint32_t c = RAW ? sy_c(st) : 0u;
+    /* places are taken BEHIND a start (the state's place is that of the block under way): the walks agree at a common
+     * start if (place at entry + starts up to and including it) is the same for both, modulo the unit */
+    int ahead = RAW ? (was >> 8) - (st >> 8) + unit : 0;               /* the first walk's place less this walk's, >= 0 */
     for (int i = p0; i < p1; i++) {
         const uint32_t before = bits16[i];
-        const uint32_t now = walk16<true>(sy_piece(sg, i), r, bits16, i);
-        if (now & before) return true;
+        const uint32_t now = walk16<true, RAW>(sy_piece(sg, i), r, c, tb, bits16, i);
+        const uint32_t both = now & before;
+        if (!RAW) {
+            if (both) { st = r; return true; }
+        } else {
+            if (both) {
+                /* at the piece's last common start: walks in step at an earlier one are in step there too */
+                const uint32_t upto = (2u << (31 - __clz((int)both))) - 1u;
+                if ((ahead + __popc(before & upto) - __popc(now & upto) + 16 * unit) % unit == 0) { st = sy_pack(r, c); return true; }
+            }
+            ahead += __popc(before) - __popc(now);
+            ahead = (ahead % unit + unit) % unit;
+        }
     }
+    st = RAW ? sy_pack(r, c) : r;
     return false;
 }
 
 /* The 32-bit entry of a block (rtj_common.h): head = its first four bytes (DC, token 1, 2, 3), last = its last byte,
  * dl = its length, off = its offset in the payload. */
-__device__ __forceinline__ uint32_t sy_entry(uint32_t head, uint32_t last, int dl, int off)
+__device__ __forceinline__ uint32_t sy_entry(uint32_t head, uint32_t last, int dl, int off, int bt8 = 0)
 {
-    /* positions >= eob are zero: a final run of n zeros ends at 64, so it starts at 64 - n */
-    const int eob = (last - 64u) < 64u ? max(127 - (int)last, dl - 1) : 64;
+    /* positions >= eob are zero: a final run of n zeros ends at 64, so it starts at 64 - n (bt8 = 63: no tokens at all) */
+    const int eob = bt8 >= 63 ? 64 : (last - 64u) < 64u ? max(127 - (int)last, dl - 1) : 64;
     const uint32_t t1 = (head >> 8) & 0xFFu, t2 = (head >> 16) & 0xFFu;
     const uint32_t c1 = (eob >= 2 && (t1 - 64u) >= 64u) ? t1 : 0u;
     const uint32_t c2 = (eob >= 3 && (t2 - 64u) >= 64u) ? t2 : 0u;
     const uint32_t e_inl = RTJ_ENT_INLINE_BIT | (head & 0xFFu) | (c1 << 8) | (c2 << 16);
     const uint32_t e_gen = RTJ_ENT(off, eob);
-    return (head & 0xFFu) == 0xFFu ? RTJ_ENT_SKIP : (eob <= 3 ? e_inl : e_gen);      /* 0xFF: a skipped block */
+    return (head & 0xFFu) == 0xFFu ? RTJ_ENT_SKIP : (bt8 == 0 && eob <= 3 ? e_inl : e_gen);      /* 0xFF: a skipped block */
 }
 
 } // namespace
 
-template <int SY_THREADS>
+/* redo[f]: 0 the frame is done, RTJ_REDO_CHUNK / RTJ_REDO_MB it is left to rtj_scan_chunk_kernel / rtj_scan_mb_kernel (rtj_common.h).
+ * RAW = false takes the frames without a raw prefix and marks the others RTJ_REDO_MB; RAW = true, launched behind it where
+ * such frames are expected, takes those.  handover = 0: never give a frame up (the parity suite's cross-check). */
+template <int SY_THREADS, bool RAW>
 __global__ void __launch_bounds__(SY_THREADS, 512 / SY_THREADS)
 rtj_scan_sync_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc *__restrict__ desc,
                      const rtj_dev_table *__restrict__ tables, int F, int nblk,
                      uint32_t *__restrict__ ent, uint32_t *__restrict__ frame_skips,
-                     rtj_dev_info *__restrict__ info, uint32_t *__restrict__ redo, int f0, int slice)
+                     rtj_dev_info *__restrict__ info, uint32_t *__restrict__ redo, int handover, int f0, int slice,
+                     int unit, int unit_luma, int lead)
 {
     extern __shared__ __align__(16) uint8_t sy_smem[];
     SyShared &sh = *reinterpret_cast<SyShared *>(sy_smem);
@@ -233,17 +295,25 @@ rtj_scan_sync_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc
     /* the kernels launched behind this one (the hand-over pass, the raw-prefix pass: both find nothing to do on most batches)
      * may take their places on the SMs while this grid's last CTAs are still at work */
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (RAW) asm volatile("griddepcontrol.wait;" ::: "memory");       /* the flags of the kernels in front are final */
     const int f = blockIdx.x + f0;
     if (f >= F) return;
-    if (redo && tid == 0) redo[f] = 0u;
     const rtjgpu_frame_desc d = desc[f];
-    {
-        const rtj_dev_table &tab = tables[min((int)d.table, RTJ_NUM_TABLES - 1)];
-        if (tab.bt8[0] | tab.bt8[1]) {                                 /* raw prefix: rtj_scan_mb_kernel's frame */
-            if (tid == 0) atomicAdd(&info->raw_frames, 1u);
-            return;
+    const rtj_dev_table &tab = tables[min((int)d.table, RTJ_NUM_TABLES - 1)];
+    const int lb8 = tab.bt8[0], cb8 = tab.bt8[1];
+    if (!RAW) {
+        const bool raw = (lb8 | cb8) != 0;                             /* raw prefix: the other instantiation's frame, or rtj_scan_mb_kernel's */
+        if (tid == 0) {
+            redo[f] = raw ? RTJ_REDO_MB : 0u;
+            if (raw) atomicAdd(&info->raw_frames, 1u);
         }
+        if (raw) return;
+    } else {
+        if (redo[f] != RTJ_REDO_MB) return;
+        if (tid == 0) atomicAdd(&info->raw_walked, 1u);
     }
+    const SyTab tb = RAW ? sy_make_tab(unit, unit_luma, lb8, cb8) : SyTab{0u, 0u, 0u, 0u};
+    const int MARG = RAW ? SY_LA : 8;                                  /* bytes behind the payload's end in which the start behind the last block lies */
 
     const uint8_t *pay = stream + d.offset + RTJPEG_B200_HEADER_BYTES;
     const int len = d.length > RTJPEG_B200_HEADER_BYTES ? (int)d.length - RTJPEG_B200_HEADER_BYTES : 0;
@@ -256,7 +326,7 @@ rtj_scan_sync_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc
      * the start behind its last block (end + 1 at most) inside the lanes' chunks. */
     const int end = len > 0 ? mis + len : 0;
     constexpr int SY_WARPS = SY_THREADS / 32, SY_PMAX = sy_pmax(SY_THREADS), SY_PMIN = sy_pmin(SY_THREADS);
-    const int P = end + 8 > SY_SEG_MAX ? SY_PMAX : max(SY_PMIN, ((end + 8 + SY_THREADS * 32 - 1) / (SY_THREADS * 32)) * 2);
+    const int P = end + MARG > SY_SEG_MAX ? SY_PMAX : max(SY_PMIN, ((end + MARG + SY_THREADS * 32 - 1) / (SY_THREADS * 32)) * 2);
     const int SEG = SY_THREADS * P * 16;
 
     if (tid == 0) {
@@ -276,20 +346,26 @@ rtj_scan_sync_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc
         sg.first = seg0 == 0 ? mis : 0;
         const int lim = sg.lim, first = sg.first;
         const int climit = min(SEG, lim);                              /* starts before it are this segment's blocks */
-        const bool more = lim + 8 > SEG;                               /* the frame goes on behind this segment */
-        const int ptot = more ? (SEG + SY_LA) >> 4 : (lim + 8 + 15) >> 4;   /* pieces to walk: up to the start behind the last block */
+        const bool more = lim + MARG > SEG;                            /* the frame goes on behind this segment */
+        const int ptot = more ? (SEG + SY_LA) >> 4 : (lim + MARG + 15) >> 4;   /* pieces to walk: up to the start behind the last block */
 
         /* ---- lead-in: every lane walks the SY_LEAD pieces in front of its chunk from a guessed state ("a block starts
          *      here").  Run-length streams forget their past within a handful of blocks: at the chunk's first byte the
          *      walk is, more often than not, in the true state.  Whether it is, is checked below -- never assumed. ---- */
         const int p0 = tid * P, p1 = min(p0 + P, ptot);                /* this lane's chunk, in pieces */
-        int r_in = 0;                                                  /* the state the chunk is entered in */
-        if (tid == 0) r_in = seg0 == 0 ? 0 : sh.carry;
-        else if (p0 < ptot) r_in = walk_pieces<false>(sg, nullptr, p0 - SY_LEAD, p0, 0);
+        /* raw prefix: the guess is "the first block of a unit starts here" -- a walk that is wrong about the place falls out of
+         * step with the stream at the next block of the other plane, and in again a few blocks on, with another place: it
+         * takes some 80 bytes in the median (170 at the 99th percentile) until place and byte are both right, hence the longer
+         * lead-in.  The frame's first byte is the one place known: behind the `first` bytes in front of the payload, which
+         * read as skip markers and each count as a block, the unit's first block must start. */
+        const int guess = RAW ? sy_pack(0, (uint32_t)(unit - 1)) : 0;
+        int r_in = guess;                                              /* the state the chunk is entered in */
+        if (tid == 0) r_in = seg0 != 0 ? sh.carry : RAW ? sy_pack(0, (uint32_t)(((unit - 1 - first) % unit + unit) % unit)) : 0;
+        else if (p0 < ptot) r_in = walk_pieces<false, RAW>(sg, nullptr, p0 - (RAW ? lead : SY_LEAD), p0, guess, tb);
 
         /* ---- walk: the chunk, from that state; one bit per byte that starts a block ---- */
-        int r_out = walk_pieces<true>(sg, bits16, p0, p1, r_in);
-        sh.exitst[tid] = (int8_t)r_out;
+        int r_out = walk_pieces<true, RAW>(sg, bits16, p0, p1, r_in, tb);
+        sh.exitst[tid] = (int16_t)r_out;
         __syncthreads();
 
         /* ---- check: a chunk must have been entered in the state its left neighbour ended in.  Where not (the lead-in is
@@ -300,28 +376,33 @@ rtj_scan_sync_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc
         for (int round = 0;; round++) {
             const int want = tid > 0 ? (int)sh.exitst[tid - 1] : r_in;
             /* states <= 0 all mean "a block starts here" */
-            const bool dirty = tid > 0 && p0 < ptot && max(want, 0) != max(r_in, 0);
+            const bool dirty = tid > 0 && p0 < ptot &&
+                               (RAW ? (max(sy_r(want), 0) != max(sy_r(r_in), 0) || (want >> 8) != (r_in >> 8)) : max(want, 0) != max(r_in, 0));
             if (__syncthreads_count(dirty) == 0) break;
             bool lost = false;
             if (dirty) {
-                int r = r_in = want;
-                if (!walk_repair(sg, bits16, p0, p1, r)) {
+                int r = want;
+                if (!walk_repair<RAW>(sg, bits16, p0, p1, r, r_in, unit, tb)) {
                     lost = true;
                     r_out = r;
-                    sh.exitst[tid] = (int8_t)r;
+                    sh.exitst[tid] = (int16_t)r;
                 }
+                r_in = want;
             }
             const int nlost = __syncthreads_count(lost);
-            if (redo && round == 0 && nlost > SY_MAX_LOST) {
+            if (handover && round == 0 && nlost > SY_MAX_LOST) {
                 /* a stream that does not forget its past: leave the frame to the kernel whose cost does not depend on the content */
-                if (tid == 0) redo[f] = 1u;
+                if (tid == 0) {
+                    redo[f] = RAW ? RTJ_REDO_MB : RTJ_REDO_CHUNK;
+                    if (RAW) atomicAdd(&info->raw_given_up, 1u);
+                }
                 return;
             }
         }
         if (more && tid == SY_THREADS - 1) {
             /* the state the next segment starts in; the look-ahead behind this one */
             sh.carry = r_out;
-            walk_pieces<true>(sg, bits16, SY_THREADS * P, ptot, r_out);
+            walk_pieces<true, RAW>(sg, bits16, SY_THREADS * P, ptot, r_out, tb);
         }
         __syncthreads();
 
@@ -419,7 +500,9 @@ rtj_scan_sync_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc
                 }
 #pragma unroll
                 for (int u = 0; u < U; u++) {
-                    const uint32_t e = sy_entry(__funnelshift_r(h0[u], h1[u], (unsigned)(qq[u] & 3) * 8), lb[u], nx[u] - qq[u], seg0 + qq[u] - mis);
+                    /* raw prefix: the block's place in its unit tells its plane, and that the prefix's length */
+                    const int bt8 = RAW ? ((nb0 + lo + k + u * SY_THREADS) % unit < unit_luma ? lb8 : cb8) : 0;
+                    const uint32_t e = sy_entry(__funnelshift_r(h0[u], h1[u], (unsigned)(qq[u] & 3) * 8), lb[u], nx[u] - qq[u], seg0 + qq[u] - mis, bt8);
                     if (k + u * SY_THREADS < n) {
                         op[k + u * SY_THREADS] = e;
                         myskips += e == RTJ_ENT_SKIP ? 1 : 0;
@@ -443,7 +526,7 @@ rtj_scan_sync_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc
                             head = (head & m) | (0x7F7F7F7Fu & ~m);
                         }
                         if (nx > lim) last = 0x7Fu;                                    /* the last block, cut short */
-                        op[k] = sy_entry(head, last, nx - qq, seg0 + qq - mis);
+                        op[k] = sy_entry(head, last, nx - qq, seg0 + qq - mis, RAW ? ((nb0 + lo + k) % unit < unit_luma ? lb8 : cb8) : 0);
                     }
                 }
             }
@@ -469,6 +552,7 @@ rtj_scan_sync_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc
     for (int b = nbf + tid; b < nblk; b += SY_THREADS) out[b] = RTJ_ENT(min(len, (int)RTJ_ENT_OFF_MASK), 1);
     if (tid == 0) {
         const int consumed = sh.consumed, skips = sh.skips;
+        if (RAW) redo[f] = 0u;
         frame_skips[f] = (uint32_t)skips;
         if (skips) {
             atomicAdd(&info->skipped_blocks, (unsigned long long)skips);
@@ -482,18 +566,47 @@ rtj_scan_sync_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc
     }
 }
 
+namespace {
+
+template <int T, bool RAW>
+cudaError_t sy_attr()
+{
+    return cudaFuncSetAttribute(rtj_scan_sync_kernel<T, RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SyShared));
+}
+
+template <int T, bool RAW>
+cudaError_t sy_launch(const rtj_launch_args *a, uint32_t *redo, int handover, int lead, cudaStream_t st)
+{
+    const int nblk = RTJ_FMT_NBLK(a->fmt, a->w, a->h);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(a->f1 - a->f0));
+    cfg.blockDim = dim3(T);
+    cfg.dynamicSmemBytes = sizeof(SyShared);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = RAW ? 1 : 0;                         /* the raw-prefix pass sits behind the other and may take its place early */
+    return cudaLaunchKernelEx(&cfg, rtj_scan_sync_kernel<T, RAW>, a->d_stream, a->d_desc, a->d_tables, a->f1, nblk, a->d_ent, a->d_frame_skips,
+                              a->d_info, redo, handover, a->f0, a->slice, RTJ_FMT_UNIT_BLOCKS(a->fmt), RTJ_FMT_UNIT_LUMA(a->fmt), lead);
+}
+
+} // namespace
+
 extern "C" int rtj_scan_sync_init(void)
 {
-    cudaError_t e = cudaFuncSetAttribute(rtj_scan_sync_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SyShared));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(rtj_scan_sync_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SyShared));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(rtj_scan_sync_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SyShared));
+    cudaError_t e = sy_attr<64, false>();
+    if (e == cudaSuccess) e = sy_attr<128, false>();
+    if (e == cudaSuccess) e = sy_attr<256, false>();
+    if (e == cudaSuccess) e = sy_attr<64, true>();
+    if (e == cudaSuccess) e = sy_attr<128, true>();
     return e == cudaSuccess ? 0 : (int)e;
 }
 
-/* redo: [F] flags (NULL: never hand a frame over) */
-extern "C" int rtj_launch_scan_sync(const rtj_launch_args *a, uint32_t *redo, void *stream)
+/* redo: [F] flags; handover = 0: never give a frame up */
+extern "C" int rtj_launch_scan_sync(const rtj_launch_args *a, uint32_t *redo, int handover, void *stream)
 {
-    const int nblk = RTJ_FMT_NBLK(a->fmt, a->w, a->h);
     const int nf = a->f1 - a->f0;
     /* Lanes a frame.  Few frames: 256 (a frame's latency is the batch's: 1920x1088, 120 frames: 0.20 ms with 64 lanes, 0.11 with
      * 128, 0.09 with 256).  Many: 128 -- 320-byte chunks at the bench point; 64 lanes with chunks twice as long spend less on
@@ -501,14 +614,21 @@ extern "C" int rtj_launch_scan_sync(const rtj_launch_args *a, uint32_t *redo, vo
     static const int forced = getenv("RTJPEG_B200_SYNC_THREADS") ? atoi(getenv("RTJPEG_B200_SYNC_THREADS")) : 0;
     const int threads = forced ? forced : nf <= 300 ? 256 : 128;
     cudaStream_t st = (cudaStream_t)stream;
-    if (threads >= 256)
-        rtj_scan_sync_kernel<256><<<(unsigned)nf, 256, sizeof(SyShared), st>>>(
-            a->d_stream, a->d_desc, a->d_tables, a->f1, nblk, a->d_ent, a->d_frame_skips, a->d_info, redo, a->f0, a->slice);
-    else if (threads >= 128)
-        rtj_scan_sync_kernel<128><<<(unsigned)nf, 128, sizeof(SyShared), st>>>(
-            a->d_stream, a->d_desc, a->d_tables, a->f1, nblk, a->d_ent, a->d_frame_skips, a->d_info, redo, a->f0, a->slice);
-    else
-        rtj_scan_sync_kernel<64><<<(unsigned)nf, 64, sizeof(SyShared), st>>>(
-            a->d_stream, a->d_desc, a->d_tables, a->f1, nblk, a->d_ent, a->d_frame_skips, a->d_info, redo, a->f0, a->slice);
-    return (int)cudaGetLastError();
+    const cudaError_t e = threads >= 256 ? sy_launch<256, false>(a, redo, handover, 0, st)
+                          : threads >= 128 ? sy_launch<128, false>(a, redo, handover, 0, st)
+                                           : sy_launch<64, false>(a, redo, handover, 0, st);
+    return (int)e;
+}
+
+/* The frames with a raw prefix (rtj_launch_scan_sync has marked them): launched behind it where the batch is expected to
+ * hold such frames; what it gives up (dense streams: noise at a high quality) stays marked for rtj_scan_mb_kernel. */
+extern "C" int rtj_launch_scan_sync_raw(const rtj_launch_args *a, uint32_t *redo, int handover, void *stream)
+{
+    static const int forced = getenv("RTJPEG_B200_SYNC_RAW_THREADS") ? atoi(getenv("RTJPEG_B200_SYNC_RAW_THREADS")) : 0;
+    static const int lead_env = getenv("RTJPEG_B200_SYNC_RAW_LEAD") ? atoi(getenv("RTJPEG_B200_SYNC_RAW_LEAD")) : 0;
+    const int threads = forced ? forced : 128;
+    /* lead-in, in 16-byte pieces: inside the chunk in front, whatever the frame's size */
+    const int lead = min(max(lead_env ? lead_env : SY_LEAD_RAW, 1), sy_pmin(threads >= 128 ? 128 : 64) - 2);
+    cudaStream_t st = (cudaStream_t)stream;
+    return (int)(threads >= 128 ? sy_launch<128, true>(a, redo, handover, lead, st) : sy_launch<64, true>(a, redo, handover, lead, st));
 }

@@ -166,3 +166,95 @@ def test_every_lane_count(F):
         e1, i1 = _entries(c, s, o, w, h)
         e2, i2 = _entries(k, s, o, w, h)
         assert np.array_equal(e1, e2) and i1 == i2
+
+
+# ---- frames with a raw prefix (quality above 170): the walk's other instantiation ------------------------------------------
+
+@pytest.mark.parametrize("Q,w,h", [(171, 208, 112), (200, 208, 112), (255, 208, 112), (255, 720, 576), (228, 1280, 720)])
+def test_raw_prefix_frames_walked(Q, w, h):
+    """SYNC forces the walk for every frame: pixels as the reference's, entries and counters as rtj_scan_mb_kernel's (CHUNK).
+    720x576 at Q=255 is three segments a frame, 1280x720 six."""
+    assert O.have_ref()
+    s, o = clip(w, h, Q, 3, noise_y=5, noise_c=2)
+    assert O.tables_from_quality(Q).lb8 > 0
+    want = reference_frames(s, o, w, h)
+    with _ctx(capi.SCAN_SYNC) as c, _ctx(capi.SCAN_CHUNK) as k:
+        got, _ = gpu_decode(c, s, o, w, h)
+        assert np.array_equal(got, want), first_diff(got, want, w, h)
+        e1, i1 = _entries(c, s, o, w, h)
+        e2, i2 = _entries(k, s, o, w, h)
+        assert i1 == i2 and i1[2] == 0
+        assert np.array_equal(e1, e2)
+
+
+def test_raw_prefix_inter_stream_and_quality_changes():
+    """Skip markers between blocks with a prefix, and frames with and without prefix in one batch (each kernel takes its own)."""
+    assert O.have_ref()
+    w, h = 176, 144
+    a = clip(w, h, 255, 6, key_rate=3, lm=2, cm=2, noise_y=6)
+    b = clip(w, h, 120, 6, noise_y=6)
+    c_ = clip(w, h, 190, 6, key_rate=2, lm=1, cm=1, noise_y=3, noise_c=3)
+    from streams import interleave
+    s, o = interleave([a, b, c_])
+    want = reference_frames(s, o, w, h)
+    for mode in (capi.SCAN_SYNC, capi.SCAN_AUTO):
+        with _ctx(mode) as c, _ctx(capi.SCAN_CHUNK) as k:
+            for _ in range(2):                                           # AUTO: the second batch expects raw-prefix frames
+                got, _ = gpu_decode(c, s, o, w, h)
+                assert np.array_equal(got, want), first_diff(got, want, w, h)
+            e1, i1 = _entries(c, s, o, w, h)
+            e2, i2 = _entries(k, s, o, w, h)
+            assert i1 == i2 and np.array_equal(e1, e2)
+
+
+def test_raw_prefix_dense_stream_is_given_up_under_auto():
+    """Noise at a high quality: blocks of 64 bytes, a parse that never forgets.  Forced, the repair rounds get there; under
+    AUTO the walk gives such frames up and rtj_scan_mb_kernel takes them -- from the third batch on in the segment-parallel
+    arrangement (the host has seen that the walk does not pay)."""
+    assert O.have_ref()
+    w, h = 320, 240
+    s, o = clip(w, h, 255, 3, noise_y=100, noise_c=60)
+    assert int(O.packet_sizes(s, o).min()) > 50 * (w // 16) * (h // 16) * 6 // 2
+    want = reference_frames(s, o, w, h)
+    with _ctx(capi.SCAN_SYNC) as c:
+        got, _ = gpu_decode(c, s, o, w, h)
+        assert np.array_equal(got, want), first_diff(got, want, w, h)
+    with _ctx(capi.SCAN_AUTO) as c:
+        for _ in range(4):
+            got, _ = gpu_decode(c, s, o, w, h)
+            assert np.array_equal(got, want), first_diff(got, want, w, h)
+            assert c.batch_info().bad_frames == 0
+
+
+@pytest.mark.parametrize("cut", [1, 5, 11, 12, 64, 1000, -1, -2, -9, -12, -63])
+def test_raw_prefix_damaged_streams_same_entries_as_the_mb_kernel(cut):
+    w, h = 208, 112
+    s, o = clip(w, h, 255, 3, key_rate=2, lm=2, cm=2, noise_y=10)
+    sizes = O.packet_sizes(s, o)
+    n1 = int(sizes[1])
+    keep = 12 + cut if cut > 0 else n1 + cut
+    pk = [s[int(o[0]):int(o[0]) + int(sizes[0])], s[int(o[1]):int(o[1]) + keep].copy(), s[int(o[2]):int(o[2]) + int(sizes[2])]]
+    pk[1][0:4] = np.frombuffer(np.uint32(pk[1].size).tobytes(), dtype=np.uint8)
+    s2, o2 = O.pack_packets(pk, align=4)
+    with _ctx(capi.SCAN_SYNC) as c, _ctx(capi.SCAN_CHUNK) as k:
+        e1, i1 = _entries(c, s2, o2, w, h)
+        e2, i2 = _entries(k, s2, o2, w, h)
+    assert i1 == i2 and i1[2] == 1 and i1[3] == 1
+    assert np.array_equal(e1, e2)
+
+
+@pytest.mark.parametrize("fmt", [1, 2])
+@pytest.mark.parametrize("Q", [190, 255])
+def test_raw_prefix_other_unit_sizes(fmt, Q):
+    """YUV422 (units of 2 luma + 2 chroma blocks) and 8-bit grey (every block luma): the place tables follow the format."""
+    assert O.have_ref()
+    from streams import reference_frames_fmt
+    w, h = 176, 144
+    s, o = O.encode_clip_fmt(w, h, Q, 4, fmt, 2, 1, 1, noise_y=5, noise_c=2)
+    init = np.full(O.frame_bytes(fmt, w, h), 0x3C, dtype=np.uint8)
+    want = reference_frames_fmt(s, o, w, h, fmt, init)
+    with _ctx(capi.SCAN_SYNC) as c:
+        c.set_format(fmt)
+        got, _ = gpu_decode(c, s, o, w, h, carry=init, fmt=fmt)
+        assert np.array_equal(got, want), first_diff(got, want, w, h)
+        assert c.batch_info().bad_frames == 0

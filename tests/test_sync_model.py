@@ -141,3 +141,127 @@ def test_random_bytes_and_damaged_streams():
         for lead in (0, 32):
             got, _, _ = chunked_starts(pay, 17, lead)
             assert np.array_equal(got, want)
+
+
+# ---- frames with a raw prefix (quality above 170): the state also holds the block's place in its unit -------------------
+
+def step_raw(r, c, b, thr, unit):
+    """(state, place of the block under way, byte) -> (state, place, does the byte start a block).  Inside the prefix
+    (r above the plane's threshold 63 - bt8) every byte is a coefficient: one place, whatever its value."""
+    if r <= 0:
+        return (0 if b == 0xFF else 63), (c + 1) % unit, True
+    if r > thr[c]:
+        return r - 1, c, False
+    return r - ((b - 63) if 64 <= b <= 127 else 1), c, False
+
+
+def serial_starts_raw(pay, thr, unit):
+    r, c, out = 0, unit - 1, np.zeros(len(pay), dtype=bool)
+    for i, b in enumerate(pay):
+        r, c, out[i] = step_raw(r, c, int(b), thr, unit)
+    return out
+
+
+def chunked_starts_raw(pay, nchunks, lead, thr, unit):
+    """The kernel's scheme with the place in the state: a repair walk is in step with the walk made before at a byte where
+    both start a block AND both take it for the same block of its unit -- the place of the earlier walk is its place at the
+    chunk's first byte plus the starts it made since (the bit map holds no places)."""
+    n = len(pay)
+    C = max(1, -(-n // nchunks))
+    bounds = [(c * C, min((c + 1) * C, n)) for c in range(nchunks) if c * C < n]
+    bits = np.zeros(n, dtype=bool)
+    entered, left = [], []
+    for k, (a, e) in enumerate(bounds):
+        st = (0, unit - 1)
+        if k > 0:
+            for i in range(max(a - lead, 0), a):
+                st = step_raw(*st, int(pay[i]), thr, unit)[:2]
+        entered.append(st)
+        r, c = st
+        for i in range(a, e):
+            r, c, bits[i] = step_raw(r, c, int(pay[i]), thr, unit)
+        left.append((r, c))
+    same = lambda x, y: max(x[0], 0) == max(y[0], 0) and x[1] == y[1]
+    rounds, wrong = 0, 0
+    while True:
+        dirty = [k for k in range(1, len(bounds)) if not same(left[k - 1], entered[k])]
+        if not dirty:
+            break
+        rounds += 1
+        wrong += len(dirty) if rounds == 1 else 0
+        want = {k: left[k - 1] for k in dirty}
+        for k in dirty:
+            a, e = bounds[k]
+            was_c = entered[k][1]
+            r, c = entered[k] = want[k]
+            ahead = (was_c - c) % unit                      # the earlier walk's place less this walk's
+            in_step = False
+            for i in range(a, e):
+                before = bits[i]
+                r, c, bits[i] = step_raw(r, c, int(pay[i]), thr, unit)
+                ahead = (ahead + int(before) - int(bits[i])) % unit
+                if bits[i] and before and ahead == 0:
+                    in_step = True
+                    break
+            if not in_step:
+                left[k] = (r, c)
+        assert rounds <= len(bounds)
+    return bits, rounds, wrong
+
+
+def _bt8(Q):
+    t = O.tables_from_quality(Q)
+    return int(t.lb8), int(t.cb8)
+
+
+@pytest.mark.parametrize("Q", [171, 200, 255])
+def test_raw_prefix_machine_finds_the_walkers_blocks(Q):
+    w, h = 160, 96
+    s, o = clip(w, h, Q, 2, noise_y=6, noise_c=2)
+    lb8, cb8 = _bt8(Q)
+    thr = [63 - lb8] * 4 + [63 - cb8] * 2
+    nmb = (w // 16) * (h // 16)
+    for f in range(2):
+        pay = payload_of(s, o, f)
+        n, offs, eob = O.walk_payload(pay, nmb, lb8, cb8)
+        assert n == len(pay)
+        at = np.flatnonzero(serial_starts_raw(pay, thr, 6))
+        coded = np.asarray(eob) > 0
+        assert len(at) == len(coded)
+        assert np.array_equal(at[coded], np.asarray(offs, dtype=np.int64)[coded])
+
+
+@pytest.mark.parametrize("lead", [0, 64, 192])
+@pytest.mark.parametrize("Q", [180, 255])
+def test_raw_prefix_guess_and_repair_equals_the_serial_walk(Q, lead):
+    s, o = clip(352, 288, Q, 1, noise_y=4, noise_c=1)
+    lb8, cb8 = _bt8(Q)
+    thr = [63 - lb8] * 4 + [63 - cb8] * 2
+    pay = payload_of(s, o, 0)
+    want = serial_starts_raw(pay, thr, 6)
+    got, rounds, wrong = chunked_starts_raw(pay, 64, lead, thr, 6)
+    assert np.array_equal(got, want)
+    if lead >= 192:
+        assert wrong <= 8 and rounds <= 3                    # a walk that is wrong about byte or place is right ~80 bytes on
+
+
+def test_raw_prefix_streams_in_step_by_byte_but_not_by_place():
+    """Skip markers only: every byte starts a block, so any two walks share every start -- and are the same walk only if
+    they also agree on the place.  A repair that looked at the bit map alone would stop at once and keep a wrong exit
+    place; with a DC-plus-prefix luma block behind the markers the parse would then go wrong."""
+    rng = np.random.default_rng(5)
+    unit, thr = 6, [63 - 9] * 4 + [63] * 2
+    blocks = []
+    for k in range(600):
+        if rng.random() < 0.7:
+            blocks.append(np.array([0xFF], dtype=np.uint8))
+        elif k % 6 < 4:
+            blocks.append(np.concatenate([rng.integers(0, 255, size=10), [127]]).astype(np.uint8))
+        else:
+            blocks.append(np.array([rng.integers(0, 255), 126], dtype=np.uint8))
+    pay = np.concatenate(blocks)
+    want = serial_starts_raw(pay, thr, unit)
+    assert int(want.sum()) == 600
+    for lead in (0, 16, 64):
+        got, _, _ = chunked_starts_raw(pay, 23, lead, thr, unit)
+        assert np.array_equal(got, want)

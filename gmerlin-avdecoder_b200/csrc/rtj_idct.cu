@@ -98,6 +98,7 @@ __device__ __forceinline__ uint32_t descale_pack4(int y0, int y1, int y2, int y3
 template <int NW>
 struct RegBytes {
     uint32_t u[NW];
+    __device__ __forceinline__ RegBytes() {}
     __device__ __forceinline__ explicit RegBytes(const uint8_t *__restrict__ src)
     {
         const uintptr_t a = reinterpret_cast<uintptr_t>(src);
@@ -147,6 +148,34 @@ __device__ __forceinline__ void unpack_block(Bytes &by, IQ iq, int bt8, int (&x)
         const int v = (take && !run) ? bb : 0;
         z = take ? (run ? bb - 64 : 0) : z - 1;
         by.advance(take);
+        x[k] = wrap16(v * iq[k]);
+    }
+}
+
+/* The same for a block of at most 16 coefficients under a raw prefix of BT8 bytes (lib/RTjpeg.c:165-169; 4, 8 or 9 with the
+ * tables of a quality above 170): the DC byte and the prefix sit at fixed places of the 24 bytes held in registers, and
+ * only the 15 - BT8 places behind them are walked as tokens, over a window of three words instead of six. */
+template <int BT8, typename IQ>
+__device__ __forceinline__ void unpack_block16_prefix(const RegBytes<6> &by, IQ iq, int (&x)[16])
+{
+    static_assert(BT8 >= 1 && BT8 <= 11, "the tokens behind the prefix fit twelve bytes that start inside the first three words");
+    x[0] = wrap16((int)(by.u[0] & 0xFFu) * iq[0]) + 4;
+#pragma unroll
+    for (int k = 1; k <= BT8; k++) x[k] = wrap16((int)(signed char)((by.u[k >> 2] >> (8 * (k & 3))) & 0xFFu) * iq[k]);
+    constexpr int b0 = BT8 + 1, w0 = b0 >> 2;
+    constexpr unsigned sh = (unsigned)(b0 & 3) * 8u;
+    RegBytes<3> t;
+#pragma unroll
+    for (int i = 0; i < 3; i++) t.u[i] = __funnelshift_r(by.u[w0 + i], w0 + i + 1 < 6 ? by.u[w0 + i + 1] : 0u, sh);
+    int z = 0;
+#pragma unroll
+    for (int k = BT8 + 1; k < 16; k++) {
+        const bool take = z == 0;
+        const int bb = t.peek_s8();
+        const bool run = take && bb > 63;
+        const int v = (take && !run) ? bb : 0;
+        z = take ? (run ? bb - 64 : 0) : z - 1;
+        t.advance(take);
         x[k] = wrap16(v * iq[k]);
     }
 }
@@ -931,13 +960,43 @@ rtj_idct_hard16_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_de
     const unsigned n16 = info->hard_blocks;
     const size_t fsz = RTJ_FMT_FRAME_BYTES(fmt, w, h);
     const unsigned stride = gridDim.x * blockDim.x;
-    for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < n16; k += stride) {
-        const uint2 rec = reinterpret_cast<const uint2 *>(hardq)[k];
-        const int i = (int)(rec.x & 0x7FFFFFFFu), chroma = (int)(rec.x >> 31);
-        const unsigned f = rec.y & 0xFFFFu, sf = rec.y >> 16;
-        const uint32_t e = ent[(size_t)sf * nblk + i];
+    const unsigned k0 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k0 >= n16) return;
+    /* A block is three reads deep -- the queue's record, the entry and descriptor it names, the bytes those point at -- and
+     * a thread works through some forty blocks: with the reads of one block made only when the block before is stored, the
+     * warps spent half their time waiting (long scoreboard on each of the three).  Three stages, three blocks under way:
+     * while block j is unpacked and transformed, the bytes of j + 1, the entry of j + 2 and the record of j + 3 are on their
+     * way.  (Records past the queue's end repeat its last one: read, never used.) */
+    struct Src {
+        uint32_t e;
+        uint32_t table;
+        const uint8_t *bytes;
+    };
+    const uint2 *Q = reinterpret_cast<const uint2 *>(hardq);
+    auto ld_rec = [&](unsigned k) { return Q[min(k, n16 - 1u)]; };
+    auto ld_src = [&](const uint2 rec) {
+        const unsigned sf = rec.y >> 16;
+        Src r;
+        r.e = ent[(size_t)sf * nblk + (rec.x & 0x7FFFFFFFu)];
         const rtjgpu_frame_desc sd = desc[sf];
-        const rtj_dev_table *t = &tables[min((int)sd.table, RTJ_NUM_TABLES - 1)];
+        r.table = sd.table;
+        r.bytes = stream + sd.offset + RTJPEG_B200_HEADER_BYTES;
+        return r;
+    };
+    /* (an inline entry holds no offset: its bytes are not used, any address inside the packet will do) */
+    auto ld_bytes = [&](const Src &sr) { return RegBytes<6>(sr.bytes + (RTJ_ENT_IS_INLINE(sr.e) ? 0u : (sr.e & RTJ_ENT_OFF_MASK))); };
+    uint2 rec0 = ld_rec(k0), rec1 = ld_rec(k0 + stride), rec2 = ld_rec(k0 + 2u * stride);
+    Src sr0 = ld_src(rec0), sr1 = ld_src(rec1);
+    RegBytes<6> by = ld_bytes(sr0);
+    for (unsigned k = k0; k < n16; k += stride) {
+        const RegBytes<6> by1 = ld_bytes(sr1);
+        const Src sr2 = ld_src(rec2);
+        const uint2 rec3 = ld_rec(k + 3u * stride);
+
+        const int i = (int)(rec0.x & 0x7FFFFFFFu), chroma = (int)(rec0.x >> 31);
+        const unsigned f = rec0.y & 0xFFFFu;
+        const uint32_t e = sr0.e;
+        const rtj_dev_table *t = &tables[min((int)sr0.table, RTJ_NUM_TABLES - 1)];
         uint32_t px[16];
         if (RTJ_ENT_IS_INLINE(e)) {
             const int x0 = wrap16((int)(e & 0xFFu) * t->iq[chroma][0]) + 4;
@@ -945,9 +1004,12 @@ rtj_idct_hard16_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_de
             const int q = wrap16((int)(signed char)((e >> 16) & 0xFFu) * t->iq[chroma][2]);
             t2_pixels(x0, x1, q, false, px);
         } else {
-            RegBytes<6> by(stream + sd.offset + RTJPEG_B200_HEADER_BYTES + (e & RTJ_ENT_OFF_MASK));
             int x[16];
-            unpack_block<16>(by, t->iq[chroma], t->bt8[chroma], x);
+            const int bt8 = t->bt8[chroma];
+            if (bt8 == 9) unpack_block16_prefix<9>(by, t->iq[chroma], x);            /* the prefixes of the quality tables */
+            else if (bt8 == 8) unpack_block16_prefix<8>(by, t->iq[chroma], x);
+            else if (bt8 == 4) unpack_block16_prefix<4>(by, t->iq[chroma], x);
+            else unpack_block<16>(by, t->iq[chroma], bt8, x);
             idct_general<16>(x, px);
         }
         int pitch;
@@ -955,6 +1017,9 @@ rtj_idct_hard16_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_de
 #pragma unroll
         for (int r = 0; r < 8; r++)
             *reinterpret_cast<uint2 *>(dst + (size_t)r * pitch) = make_uint2(px[2 * r], px[2 * r + 1]);
+        rec0 = rec1; rec1 = rec2; rec2 = rec3;
+        sr0 = sr1; sr1 = sr2;
+        by = by1;
     }
 }
 
@@ -1266,7 +1331,7 @@ extern "C" int rtj_launch_idct_hard(const rtj_launch_args *a, void *stream)
     /* the queue's length is only known on the device: a fixed grid strides over it */
     const int sms = g_sm_count > 0 ? g_sm_count : 148;
     const int nblk = RTJ_FMT_NBLK(a->fmt, a->w, a->h);
-    cudaError_t e16 = launch_pdl(rtj_idct_hard16_kernel, dim3((unsigned)(sms * 8)), dim3(128), 0, (cudaStream_t)stream,
+    cudaError_t e16 = launch_pdl(rtj_idct_hard16_kernel, dim3((unsigned)(sms * 7)), dim3(128), 0, (cudaStream_t)stream,      /* 70 registers: seven CTAs a SM */
                                  a->d_stream, a->d_desc, a->d_tables, (const uint32_t *)a->d_ent, nblk, a->w, a->h, a->fmt, a->d_out,
                                  (const uint32_t *)a->d_hardq, (const rtj_dev_info *)a->d_info);
     if (e16 != cudaSuccess) return (int)e16;

@@ -820,7 +820,9 @@ rtj_idct_kernel(const K2Params P)
                 const uint2 rec = make_uint2((strip_blk0 + (unsigned)bi) | (off_is_chroma<FMT>(off, mbs) ? 0x80000000u : 0u), f | (hsf << 16));
                 if (hard && !full) reinterpret_cast<uint2 *>(P.hardq)[base + __popc(mH & below)] = rec;
                 if (full) reinterpret_cast<uint2 *>(P.hardq)[P.hardq_cap - 1u - (baseF + __popc(mF & below))] = rec;
-                nhard += __popc(mH) + __popc(mF);
+                /* (the luma blocks among them in the upper half: a strip whose luma blocks are all HARD keeps its luma rows) */
+                const unsigned mC = __ballot_sync(FULL, off_is_chroma<FMT>(off, mbs));
+                nhard += __popc(mH) + __popc(mF) + (__popc((mH | mF) & ~mC) << 16);
             }
             if (live && !hard) {
                 uint32_t px[16];
@@ -847,7 +849,7 @@ rtj_idct_kernel(const K2Params P)
     if (SINGLE) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
     const int lw = G::UNIT_W * mbs;                              /* luma bytes per strip row */
-    bool planes_leave = true;
+    bool planes_leave = true, luma_leaves = true;
     if (RGB) {
         /* The strip -- 16 luma rows, 8 rows of Cb and of Cr: exactly what the reference's converters read for 16 output
          * rows (lib/RTjpeg.c:3123-3190) -- leaves as packed pixels.  A thread takes 8 pixels of two rows (one chroma row):
@@ -877,7 +879,13 @@ rtj_idct_kernel(const K2Params P)
             }
         }
         if (!P.last_yuv || f + 1u != (unsigned)P.F) planes_leave = false;      /* the last frame also leaves as planes: the next batch's carry */
-    } else if (s_hard[0] + s_hard[1] + s_hard[2] + s_hard[3] == nb) planes_leave = false;
+    } else {
+        /* What rtj_idct_hard*_kernel patch need not be written here first.  All blocks HARD: nothing leaves; all luma blocks
+         * (a quality above 170, where every luma block carries ten coefficients or more): the chroma rows only. */
+        const int hs = s_hard[0] + s_hard[1] + s_hard[2] + s_hard[3];
+        if ((hs & 0xFFFF) == nb) planes_leave = false;
+        else if (G::PLANES == 3 && (hs >> 16) == nb - 2 * mbs) luma_leaves = false;
+    }
     if (planes_leave) {
     const size_t fsz = RTJ_FMT_FRAME_BYTES(FMT, w, h);
     const int cw = w >> 1;
@@ -890,7 +898,7 @@ rtj_idct_kernel(const K2Params P)
         /* the luma rows and the 2 x 8 chroma rows are each one contiguous run in the tight-pitch planes:
          * TMA bulk stores issued by one thread */
         if (tid == 0) {
-            bulk_store(oy, tile, (unsigned)(G::LUMA_ROWS * lw));
+            if (luma_leaves) bulk_store(oy, tile, (unsigned)(G::LUMA_ROWS * lw));
             if (G::PLANES == 3) {
                 bulk_store(ou, tileU, 64u * (unsigned)mbs);
                 bulk_store(ov, tileV, 64u * (unsigned)mbs);
@@ -899,7 +907,8 @@ rtj_idct_kernel(const K2Params P)
             asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         }
     } else {
-        if (G::UNIT_W == 16) {
+        if (!luma_leaves) {
+        } else if (G::UNIT_W == 16) {
             for (int r = warp; r < G::LUMA_ROWS; r += WARPS)
                 for (int c = lane; c < mbs; c += 32)                 /* 16-byte vectors per luma row */
                     *reinterpret_cast<uint4 *>(oy + (size_t)r * w + c * 16) =

@@ -5,9 +5,10 @@
  *                           run-length stream and emits a 32-bit entry (payload offset + end-of-block bound, or
  *                           "skipped") for every 8x8 block.  Replaces the `sp += RTjpeg_s2b(...)` pointer chase of
  *                           RTjpeg_decompressYUV420 (lib/RTjpeg.c:2701-2745) and the length logic of RTjpeg_s2b
- *                           (:157-186).  Kept as cross-checks; what AUTO runs is in rtj_scan_sync.cu (frames without
- *                           a raw prefix), rtj_scan_chunk.cu (what that kernel hands over; the segment passes) and
- *                           rtj_scan_mb.cu (frames with a raw prefix).  rtj_launch_scan below picks.
+ *                           (:157-186).  Kept as cross-checks; what AUTO runs is in rtj_scan_sync.cu (the walk, one
+ *                           instantiation for frames without a raw prefix, one for those with), rtj_scan_chunk.cu and
+ *                           rtj_scan_mb.cu (what the walks hand over, without / with a raw prefix; the segment passes).
+ *                           rtj_launch_scan below picks.
  *   K3  rtj_resolve_last_kernel + rtj_resolve_kernel
  *                           per block position, a last-writer scan over the frames of the batch: for every skipped
  *                           block, which earlier frame coded it last (and, where that frame's entry carries the block

@@ -41,8 +41,9 @@
  * carried from one to the next.  (Earlier versions -- the set of all 64 states tracked as a bit mask until one is
  * left; the payload in shared memory by one bulk copy -- are in the history and in DESIGN.md section 4.)
  *
- * Scope: frames whose tables have no raw 8-bit prefix (lb8 == cb8 == 0), like rtj_scan_chunk.cu; the others are
- * rtj_scan_mb_kernel's.  Same entries (rtj_common.h), counters and malformed-stream policy as the other flavours.
+ * Frames whose tables have a raw 8-bit prefix (lb8 / cb8 != 0: a quality above 170) are walked by the kernel's second
+ * instantiation (RAW), launched behind the first: the state then also holds the block's place in its unit, see SyTab below.
+ * Same entries (rtj_common.h), counters and malformed-stream policy as the other flavours.
  */
 #include <cuda_runtime.h>
 #include <stddef.h>

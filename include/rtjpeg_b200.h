@@ -193,9 +193,9 @@ const char *rtjgpu_strerror(int code);
 int  rtjgpu_last_cuda_error(const rtjgpu_ctx *ctx);
 
 /* Which flavour of the block-offset scan (K1) runs.  AUTO (the default) picks by batch size: many frames -- one CTA per
- * frame, SYNC for frames without a raw prefix (lanes walk the stream from guessed states and repair what was guessed
- * wrong; frames whose streams do not synchronise are handed to CHUNK's kernel) and the macroblock-level kernel for the
- * others; few, large frames (and the one-frame RTjpeg_decompress) -- SEGMENT: the 8 KB segments of a frame go to separate
+ * frame, SYNC (lanes walk the stream from guessed states and repair what was guessed wrong; frames whose streams do not
+ * synchronise are handed to CHUNK's kernel, or, where the tables have a raw prefix, to the macroblock-level kernel --
+ * which also takes every raw-prefix frame of a batch in which none was expected); few, large frames (and the one-frame RTjpeg_decompress) -- SEGMENT: the 8 KB segments of a frame go to separate
  * CTAs, with a frame-level chain between a summary pass and an emit pass.  CHUNK = one CTA per frame walks the frame's
  * segments in turn, every byte position examined in parallel inside a segment (round 1's kernel; its cost does not depend
  * on the content).  LANE / WARP / WALK force a serial walk instead: one thread per frame or one warp per frame.  Every
@@ -206,7 +206,7 @@ int  rtjgpu_last_cuda_error(const rtjgpu_ctx *ctx);
 #define RTJGPU_SCAN_CHUNK   3
 #define RTJGPU_SCAN_SEGMENT 4
 #define RTJGPU_SCAN_WALK    5     /* one thread per frame, payload staged through shared memory with cp.async (not for raw-prefix frames) */
-#define RTJGPU_SCAN_SYNC    6     /* one CTA per frame, every lane walks from its chunk's synchronisation point (not for raw-prefix frames) */
+#define RTJGPU_SCAN_SYNC    6     /* one CTA per frame, every lane walks from its chunk's synchronisation point; no frame is handed over */
 int  rtjgpu_set_scan_mode(rtjgpu_ctx *ctx, int mode);
 
 /* How a large device batch is worked through.  SERIAL (what AUTO stands for at present): every stage on cuda_stream, one

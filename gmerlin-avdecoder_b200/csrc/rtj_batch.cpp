@@ -198,7 +198,16 @@ bool auto_wants_segments(const rtjgpu_ctx *ctx, int F, int nblk)
     /* (The self-synchronising walk takes such frames at a few us per 40 KB when their streams forget their past -- ordinary
      * material does; noise at a high quality does not, and is what the segment-parallel passes remain for.) */
     const volatile unsigned long long *seen = ctx->h_skips_seen;
-    if (seen[1]) return F <= 256 && seen[2] != 0;
+    if (seen[1]) {
+        if (seen[2]) return F <= 256;
+        /* measured at a quality of 255 (~9 bytes a block): the walk ~21 us per 40 KB segment of a frame whatever the batch
+         * (720x576: 0.067 ms for 1 .. 96 frames; 1920x1088: 0.22 - 0.25 ms for 4 .. 32), the segment-parallel passes
+         * ~90 us + 20 ns per KB of batch (720x576: 0.097 / 0.133 / 0.239 ms for 1 / 32 / 96 frames; 1920x1088: 0.123 / 0.370 ms
+         * for 4 / 32): segments for a handful of large frames only */
+        const double raw_kb = (double)nblk * 9.0 / 1024.0;
+        const int raw_nseg = (int)((raw_kb + 39.99) / 40.0);
+        return 0.090 + 2.0e-5 * (double)F * raw_kb < 0.021 * (double)raw_nseg;
+    }
     const double frame_kb = (double)nblk * 4.0 / 1024.0;
     const int nseg = (int)((frame_kb + 39.99) / 40.0);
     return nseg > 1 && 0.055 + 1.1e-5 * (double)F * frame_kb < 0.040 * (double)nseg;

@@ -498,6 +498,7 @@ struct K2Params {
     const uint16_t *srcf;
     int nblk, w, h, seg_mb, nstrips;
     int f0, F;                       /* first frame of this launch (blockIdx.y = 0); frames of the batch */
+    int reserve;                     /* launch the RES instantiation */
     int f_end, run;                  /* one behind the launch's last frame; frames a CTA works through in turn (blockIdx.y counts runs) */
     int row0, rows;                  /* first row of units of this launch (blockIdx.x = 0); rows of units of a picture */
     uint8_t *out;
@@ -586,7 +587,9 @@ constexpr int K2_PF_LINES = 12;                   /* 128-byte lines of payload a
 constexpr int RGB_NONE = -1, RGB_ANY = 99;
 
 /* RUN: a CTA works through P.run frames in turn (below); false: one frame, and none of the run's bookkeeping is compiled in */
-template <bool SINGLE, int FMT, int WARPS, int RGBK, bool RUN>
+/* RES: a warp reserves its places in K2b's queue with one request per row (streams in which most blocks go that way: a quality
+ * above 170; chosen by the batch before, like RUN) */
+template <bool SINGLE, int FMT, int WARPS, int RGBK, bool RUN, bool RES = false>
 __global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? 8 : 10)
 rtj_idct_kernel(const K2Params P)
 {
@@ -785,6 +788,27 @@ rtj_idct_kernel(const K2Params P)
      *      rtj_idct_hard_kernel through the device queue ---- */
     int nhard = 0;
     if (nback) {                                             /* warp-uniform */
+        /* The warp's places in the device queue, both ends: ONE request per warp and row -- an atomic on a word every CTA of
+         * the grid adds to, a trip to L2 and back -- instead of one per 32 blocks: above a quality of 170 every luma block
+         * goes this way, eight requests one behind the other.  The counts come from the warp's own queue. */
+        unsigned qbase16 = 0, qbaseF = 0;
+        /* (a template parameter: as a run-time choice the code costs the kernel 0.65 % on streams that never use it) */
+        const bool reserve = RES && !RGB && nback > 32;      /* (a single pass asks for itself, as ever) */
+        if (reserve) {
+            int nq16 = 0, nqF = 0;
+            for (int c0 = 0; c0 < nback; c0 += 32) {
+                const uint32_t ie = c0 + lane < nback ? wq_e[wq - 1 - (c0 + lane)] : 0x80000000u;
+                const unsigned mH = __ballot_sync(FULL, !(ie >> 31)), mF = __ballot_sync(FULL, (ie >> 30) == 1u);
+                nq16 += __popc(mH & ~mF);
+                nqF += __popc(mF);
+            }
+            if (lane == 0) {
+                if (nq16) qbase16 = atomicAdd(&P.info->hard_blocks, (unsigned)nq16);
+                if (nqF) qbaseF = atomicAdd(&P.info->hard_full, (unsigned)nqF);
+            }
+            qbase16 = __shfl_sync(FULL, qbase16, 0);
+            qbaseF = __shfl_sync(FULL, qbaseF, 0);
+        }
         for (int c0 = 0; c0 < nback; c0 += 32) {
             const int idx = c0 + lane;
             const bool live = idx < nback;
@@ -807,13 +831,18 @@ rtj_idct_kernel(const K2Params P)
             const unsigned mH = RGB ? 0u : __ballot_sync(FULL, hard && !full), mF = RGB ? 0u : __ballot_sync(FULL, full);
             if (mH | mF) {
                 /* the device queue is filled from both ends: mid-size blocks from the front, long ones from the back */
-                unsigned base = 0, baseF = 0;
-                if (lane == 0) {
-                    if (mH) base = atomicAdd(&P.info->hard_blocks, (unsigned)__popc(mH));
-                    if (mF) baseF = atomicAdd(&P.info->hard_full, (unsigned)__popc(mF));
+                unsigned base = qbase16, baseF = qbaseF;
+                if (reserve) {
+                    qbase16 += (unsigned)__popc(mH);
+                    qbaseF += (unsigned)__popc(mF);
+                } else {
+                    if (lane == 0) {
+                        if (mH) base = atomicAdd(&P.info->hard_blocks, (unsigned)__popc(mH));
+                        if (mF) baseF = atomicAdd(&P.info->hard_full, (unsigned)__popc(mF));
+                    }
+                    base = __shfl_sync(FULL, base, 0);
+                    baseF = __shfl_sync(FULL, baseF, 0);
                 }
-                base = __shfl_sync(FULL, base, 0);
-                baseF = __shfl_sync(FULL, baseF, 0);
                 const unsigned below = (1u << lane) - 1u;
                 /* a queue entry: the block's place in its frame (and whether it is a chroma block), the frame the pixels
                  * go to and the frame whose stream holds the block (its last writer) */
@@ -1198,6 +1227,9 @@ cudaError_t k2_attr()
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(rtj_idct_kernel<SINGLE, FMT, WARPS, RGBK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)idct_smem_bytes(IDCT_MAX_MB, FMT, 3));
+    if (RGBK == RGB_NONE && e == cudaSuccess)
+        e = cudaFuncSetAttribute(rtj_idct_kernel<SINGLE, FMT, WARPS, RGB_NONE, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)idct_smem_bytes(IDCT_MAX_MB, FMT, 3));
     return e;
 }
 
@@ -1239,6 +1271,14 @@ cudaError_t k2_launch(K2Params &P, int grid_x, int F, cudaStream_t st)
         } else {
             if (warps == 4) e = launch_pdl(rtj_idct_kernel<false, FMT, 4, RGBS, true>, grid, dim3(128), smem, st, P);
             else e = launch_pdl(rtj_idct_kernel<false, FMT, 3, RGBS, true>, grid, dim3(96), smem, st, P);
+        }
+    } else if (RGBK == RGB_NONE && P.reserve) {
+        if (P.nstrips == 1) {
+            if (warps == 4) e = launch_pdl(rtj_idct_kernel<true, FMT, 4, RGB_NONE, false, true>, grid, dim3(128), smem, st, P);
+            else e = launch_pdl(rtj_idct_kernel<true, FMT, 3, RGB_NONE, false, true>, grid, dim3(96), smem, st, P);
+        } else {
+            if (warps == 4) e = launch_pdl(rtj_idct_kernel<false, FMT, 4, RGB_NONE, false, true>, grid, dim3(128), smem, st, P);
+            else e = launch_pdl(rtj_idct_kernel<false, FMT, 3, RGB_NONE, false, true>, grid, dim3(96), smem, st, P);
         }
     } else if (P.nstrips == 1) {
         if (warps == 4) e = launch_pdl(rtj_idct_kernel<true, FMT, 4, RGBK, false>, grid, dim3(128), smem, st, P);
@@ -1313,7 +1353,7 @@ extern "C" int rtj_launch_idct(const rtj_launch_args *a, void *stream)
     P.hardq_cap = (unsigned)((size_t)a->F * (size_t)P.nblk);
     P.fmt = fmt;
     P.pos = reinterpret_cast<const uint32_t *>(a->d_lut);
-    P.f0 = a->f0; P.F = a->F; P.f_end = a->f1; P.run = a->k2_run;
+    P.f0 = a->f0; P.F = a->F; P.f_end = a->f1; P.run = a->k2_run; P.reserve = a->raw_expected;
     P.row0 = a->row0; P.rows = uy;
     const int grid_x = P.nstrips * (a->row1 - a->row0);
     const int nf = a->f1 - a->f0;

@@ -59,6 +59,9 @@ constexpr unsigned FULL = 0xFFFFFFFFu;
  * comparison (rtj_launch_scan_sync picks). */
 constexpr int SY_MAX_THREADS = 256;
 constexpr int SY_LEAD = 4;                                 /* 16-byte pieces of the lead-in walk in front of a chunk (64 bytes) */
+#ifndef SY_RAW_WARPS
+#define SY_RAW_WARPS 28                                       /* resident warps per SM the raw-prefix instantiation is compiled for */
+#endif
 constexpr int SY_LEAD_RAW = 12;                            /* ... for frames with a raw prefix (192 bytes) */
 constexpr int SY_SEG_MAX = 40960;                          /* bytes of a frame worked on at a time */
 __host__ __device__ constexpr int sy_pmax(int threads) { return (SY_SEG_MAX / (16 * threads)) & ~1; }             /* pieces per chunk at most (even): a chunk's bit map is whole 32-bit words */
@@ -128,6 +131,10 @@ __device__ __forceinline__ void walk4(uint32_t W, int &r, uint32_t &c, const SyT
     const uint32_t y = ~W;
     const uint32_t z = ~((y & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) & W & 0x80808080u;   /* bit 7 of every byte that is 0xFF */
     const uint32_t G = 0x3F3F3F3Fu & ~(z - (z >> 7));                    /* the state behind a block's first byte: 63, or 0 behind a skip marker */
+    /* One byte: the new state is r - (what the byte fills); r - 1 inside a raw prefix; G's byte where a block starts.  All three
+     * are dp4a (FMA pipe); the later two are PREDICATED and overwrite the first, so that no select is spent on the choice: the
+     * ALU pipe -- the kernel's bound -- sees one compare (two with a prefix), the table look-ups and the bit for the map. */
+#ifdef SY_SELECT_STEP                                       /* (A/B builds: the step with selects, as it was) */
 #define SY_STEP(k)                                                                                   \
     {                                                                                                \
         int t, g;                                                                                    \
@@ -135,15 +142,66 @@ __device__ __forceinline__ void walk4(uint32_t W, int &r, uint32_t &c, const SyT
         asm("dp4a.u32.u32 %0, %1, %2, %3;" : "=r"(g) : "r"(G), "r"(1u << (8 * k)), "r"(0));          \
         const bool at = r <= 0;                                                                      \
         if (RAW) {                                                                                   \
-            /* inside the prefix every byte is a coefficient: one place */                           \
             const int thr = (int)__byte_perm(tb.thlo, tb.thhi, c);                                   \
             const uint32_t cn = __byte_perm(tb.nlo, tb.nhi, c);                                      \
-            t = r > thr ? r - 1 : t;                                                                 \
-            c = at ? cn : c;                       /* the block that starts here is the unit's next */ \
+            int t1;                                                                                  \
+            asm("dp4a.s32.u32 %0, %1, %2, %3;" : "=r"(t1) : "r"(0xFFFFFFFFu), "r"(1u), "r"(r));      \
+            t = r > thr ? t1 : t;                                                                    \
+            c = at ? cn : c;                                                                         \
         }                                                                                            \
         r = at ? g : t;                                                                              \
         if (BITS) asm("{ .reg .pred p; setp.ne.u32 p, %1, 0; @p add.u32 %0, %0, %2; }" : "+r"(bm) : "r"((unsigned)at), "n"(1u << (bit0 + k))); \
     }
+#else
+#define SY_STEP(k)                                                                                   \
+    if (!RAW) {                                                                                      \
+        if (BITS)                                                                                    \
+            asm("{ .reg .pred pa; .reg .s32 rn;\n\t"                                                 \
+                "setp.le.s32 pa, %0, 0;\n\t"                                                         \
+                "dp4a.s32.u32 rn, %2, %4, %0;\n\t"                                                   \
+                "@pa dp4a.u32.u32 rn, %3, %4, %5;\n\t"                                               \
+                "@pa add.u32 %1, %1, %6;\n\t"                                                        \
+                "mov.s32 %0, rn; }"                                                                  \
+                : "+r"(r), "+r"(bm) : "r"(NX), "r"(G), "r"(1u << (8 * k)), "r"(0), "n"(1u << (bit0 + k)));   \
+        else                                                                                         \
+            asm("{ .reg .pred pa; .reg .s32 rn;\n\t"                                                 \
+                "setp.le.s32 pa, %0, 0;\n\t"                                                         \
+                "dp4a.s32.u32 rn, %1, %3, %0;\n\t"                                                   \
+                "@pa dp4a.u32.u32 rn, %2, %3, %4;\n\t"                                               \
+                "mov.s32 %0, rn; }"                                                                  \
+                : "+r"(r) : "r"(NX), "r"(G), "r"(1u << (8 * k)), "r"(0));                            \
+    } else {                                                                                         \
+        /* inside the prefix (r above the plane's threshold) every byte is a coefficient: one place; the block that starts \
+         * here is the unit's next */                                                                \
+        if (BITS)                                                                                    \
+            asm("{ .reg .pred pa, pr; .reg .s32 rn; .reg .b32 th;\n\t"                               \
+                "setp.le.s32 pa, %0, 0;\n\t"                                                         \
+                "prmt.b32 th, %7, %8, %1;\n\t"                                                       \
+                "setp.gt.s32 pr, %0, th;\n\t"                                                        \
+                "dp4a.s32.u32 rn, %3, %5, %0;\n\t"                                                   \
+                "@pr dp4a.s32.u32 rn, %11, %12, %0;\n\t"                                             \
+                "@pa dp4a.u32.u32 rn, %4, %5, %6;\n\t"                                               \
+                "@pa prmt.b32 %1, %9, %10, %1;\n\t"                                                  \
+                "@pa add.u32 %2, %2, %13;\n\t"                                                       \
+                "mov.s32 %0, rn; }"                                                                  \
+                : "+r"(r), "+r"(c), "+r"(bm)                                                         \
+                : "r"(NX), "r"(G), "r"(1u << (8 * k)), "r"(0), "r"(tb.thlo), "r"(tb.thhi), "r"(tb.nlo), "r"(tb.nhi), \
+                  "r"(0xFFFFFFFFu), "r"(1u), "n"(1u << (bit0 + k)));                                 \
+        else                                                                                         \
+            asm("{ .reg .pred pa, pr; .reg .s32 rn; .reg .b32 th;\n\t"                               \
+                "setp.le.s32 pa, %0, 0;\n\t"                                                         \
+                "prmt.b32 th, %6, %7, %1;\n\t"                                                       \
+                "setp.gt.s32 pr, %0, th;\n\t"                                                        \
+                "dp4a.s32.u32 rn, %2, %4, %0;\n\t"                                                   \
+                "@pr dp4a.s32.u32 rn, %10, %11, %0;\n\t"                                             \
+                "@pa dp4a.u32.u32 rn, %3, %4, %5;\n\t"                                               \
+                "@pa prmt.b32 %1, %8, %9, %1;\n\t"                                                   \
+                "mov.s32 %0, rn; }"                                                                  \
+                : "+r"(r), "+r"(c)                                                                   \
+                : "r"(NX), "r"(G), "r"(1u << (8 * k)), "r"(0), "r"(tb.thlo), "r"(tb.thhi), "r"(tb.nlo), "r"(tb.nhi), \
+                  "r"(0xFFFFFFFFu), "r"(1u));                                                        \
+    }
+#endif
     SY_STEP(0) SY_STEP(1) SY_STEP(2) SY_STEP(3)
 #undef SY_STEP
 }
@@ -283,7 +341,7 @@ __device__ __forceinline__ uint32_t sy_entry(uint32_t head, uint32_t last, int d
  * RAW = false takes the frames without a raw prefix and marks the others RTJ_REDO_MB; RAW = true, launched behind it where
  * such frames are expected, takes those.  handover = 0: never give a frame up (the parity suite's cross-check). */
 template <int SY_THREADS, bool RAW>
-__global__ void __launch_bounds__(SY_THREADS, 512 / SY_THREADS)
+__global__ void __launch_bounds__(SY_THREADS, (RAW ? SY_RAW_WARPS * 32 : 512) / SY_THREADS)
 rtj_scan_sync_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc *__restrict__ desc,
                      const rtj_dev_table *__restrict__ tables, int F, int nblk,
                      uint32_t *__restrict__ ent, uint32_t *__restrict__ frame_skips,

@@ -258,3 +258,26 @@ def test_raw_prefix_other_unit_sizes(fmt, Q):
         got, _ = gpu_decode(c, s, o, w, h, carry=init, fmt=fmt)
         assert np.array_equal(got, want), first_diff(got, want, w, h)
         assert c.batch_info().bad_frames == 0
+
+
+def test_raw_prefix_few_large_frames_under_auto():
+    """AUTO, batch after batch of two 1920x1088 frames at a quality of 255: the first batch knows nothing (rtj_scan_mb_kernel
+    takes the frames), the second expects raw-prefix frames and -- a handful of large frames -- goes segment-parallel, and a
+    batch of 40 frames of the same stream is walked.  Pixels as the reference's every time."""
+    assert O.have_ref()
+    w, h = 1920, 1088
+    s, o = clip(w, h, 255, 2, noise_y=4, noise_c=1)
+    want = reference_frames(s, o, w, h)
+    sizes = O.packet_sizes(s, o)
+    pk = [s[int(o[i]):int(o[i]) + int(sizes[i])] for i in range(2)]
+    s40, o40 = O.pack_packets(pk * 20)
+    with _ctx(capi.SCAN_AUTO) as c:
+        for _ in range(3):
+            got, _ = gpu_decode(c, s, o, w, h)
+            assert np.array_equal(got, want), first_diff(got, want, w, h)
+            assert c.batch_info().bad_frames == 0
+        got, _ = gpu_decode(c, s40, o40, w, h)
+        for k in range(20):
+            assert np.array_equal(got[2 * k:2 * k + 2], want), first_diff(got[2 * k:2 * k + 2], want, w, h)
+        got, _ = gpu_decode(c, s, o, w, h)
+        assert np.array_equal(got, want), first_diff(got, want, w, h)

@@ -281,3 +281,21 @@ def test_raw_prefix_few_large_frames_under_auto():
             assert np.array_equal(got[2 * k:2 * k + 2], want), first_diff(got[2 * k:2 * k + 2], want, w, h)
         got, _ = gpu_decode(c, s, o, w, h)
         assert np.array_equal(got, want), first_diff(got, want, w, h)
+
+
+def test_batches_with_and_without_raw_prefix_in_turn():
+    """What a batch is arranged by -- raw-prefix frames, skipped blocks in the batch before -- is a guess about THIS batch:
+    one context, batches of different nature in turn, every guess wrong once.  Pixels as the reference's each time."""
+    assert O.have_ref()
+    w, h = 352, 288
+    clips = [clip(w, h, 255, 5, noise_y=5, noise_c=2),                       # raw prefix, intra
+             clip(w, h, 128, 5, key_rate=3, lm=2, cm=2, noise_y=5),          # no prefix, skipped blocks
+             clip(w, h, 200, 5, key_rate=2, lm=1, cm=1, noise_y=5),          # raw prefix, skipped blocks
+             clip(w, h, 100, 5, noise_y=5)]                                  # no prefix, intra
+    want = [reference_frames(s, o, w, h) for s, o in clips]
+    with _ctx(capi.SCAN_AUTO) as c:
+        for turn in (0, 1, 2, 3, 0, 2, 1, 3, 3, 0):
+            s, o = clips[turn]
+            got, _ = gpu_decode(c, s, o, w, h)
+            assert np.array_equal(got, want[turn]), (turn, first_diff(got, want[turn], w, h))
+            assert c.batch_info().bad_frames == 0

@@ -21,6 +21,7 @@
  * under a grammar without prefix (chroma at the standard tables) still go inline when short.
  */
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdint.h>
 
 #include "rtj_common.h"
@@ -58,6 +59,7 @@ struct MbShared {
  * space of dmb and ring */
 constexpr int MB_S_ENTRIES = MB_PFX_THREADS * MB_PFX;
 constexpr int MB_T_CAP = ((int)(sizeof(uint16_t) * (MB_S + 2 * MB_NCH) + sizeof(uint32_t) * MB_STAGE) - 2 * MB_S_ENTRIES) / 2;
+static_assert((offsetof(MbShared, dmb) + 2 * MB_S_ENTRIES) % 16 == 0 && MB_T_CAP % 8 == 0, "T is read and written sixteen bytes at a time");
 static_assert(MB_T_CAP >= MB_POS / 2 + 64 + 63 + 256, "the inverse table covers half a segment of mostly one-place bytes");
 
 __device__ __forceinline__ uint32_t swar_runs(uint32_t t) { return t & ~(t >> 1) & 0x40404040u; }
@@ -269,10 +271,64 @@ rtj_scan_mb_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc *
                     const int qlo = r * R, qhi = min(qlo + R, npos2);
                     const int v0 = S[qlo];
                     if (r) __syncthreads();                                          /* the round before is done with T */
-                    /* T over the places (v0, v0 + cap): byte i covers the places S[i - 1] + 1 .. S[i] */
-                    for (int i2 = qlo + 1 + tid; i2 <= min(qhi + 63 + 64, nby - 1); i2 += MB_THREADS) {
-                        const int hi = (int)S[i2] - v0, lo = (int)S[i2 - 1] - v0;
-                        for (int v = lo + 1; v <= min(hi, MB_T_CAP - 1); v++) T[v] = (uint16_t)i2;
+                    /* T over the places (v0, v0 + cap): byte i covers the places S[i - 1] + 1 .. S[i].  Bytes read as run tokens
+                     * cover up to 64 places and every fourth byte of noise reads as one, so T has some nine entries a byte: instead
+                     * of a store per entry (a loop whose length differs from lane to lane), every byte marks the FIRST place it
+                     * covers with its index, and a running maximum over T -- indices grow with the places -- fills in the rest:
+                     * each warp a quarter of T, 256 entries (one 16-byte read a lane) at a time. */
+                    const int i2max = min(qhi + 63 + 64, nby - 1);
+                    const int nT8 = min(((int)S[i2max] - v0 + 1 + 7) >> 3, MB_T_CAP >> 3);      /* entries in use, in eights */
+                    uint4 *T4 = reinterpret_cast<uint4 *>(T);
+                    for (int j = tid; j < nT8; j += MB_THREADS) T4[j] = make_uint4(0u, 0u, 0u, 0u);
+                    __syncthreads();
+                    for (int i2 = qlo + 1 + tid; i2 <= i2max; i2 += MB_THREADS) {
+                        const int first = (int)S[i2 - 1] - v0 + 1;
+                        if (first < 8 * nT8) T[first] = (uint16_t)i2;
+                    }
+                    __syncthreads();
+                    {
+                        const int warp = tid >> 5;
+                        const int per = ((nT8 + 4 * 32 - 1) / (4 * 32)) * 32;                  /* eights per warp: whole tiles of 32 */
+                        const int j0 = warp * per, j1 = min(j0 + per, nT8);
+                        /* what the quarters in front of this warp's hold at most */
+                        uint32_t m = 0;
+                        for (int j = j0 + lane; j < j1; j += 32) {
+                            const uint4 w = T4[j];
+                            m = __vmaxu2(__vmaxu2(m, w.x), __vmaxu2(__vmaxu2(w.y, w.z), w.w));
+                        }
+                        m = max(m & 0xFFFFu, m >> 16);
+#pragma unroll
+                        for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
+                        if (lane == 0) sh.tot[warp] = m;
+                        __syncthreads();
+                        uint32_t carry = 0;                                                    /* the largest index in front of the tile */
+                        for (int k = 0; k < warp; k++) carry = max(carry, sh.tot[k]);
+                        for (int jt = j0; jt < j1; jt += 32) {
+                            const int j = jt + lane;
+                            uint4 w = j < j1 ? T4[j] : make_uint4(0u, 0u, 0u, 0u);
+                            /* running maximum inside the lane's eight entries: low half first, then the high half over it */
+                            uint32_t run = 0;
+#define MB_RUNMAX(word)                                                                       \
+                            {                                                                 \
+                                const uint32_t lo16 = max(run, (word) & 0xFFFFu);             \
+                                run = max(lo16, (word) >> 16);                                \
+                                (word) = lo16 | run << 16;                                    \
+                            }
+                            MB_RUNMAX(w.x) MB_RUNMAX(w.y) MB_RUNMAX(w.z) MB_RUNMAX(w.w)
+#undef MB_RUNMAX
+                            /* ... over the lanes in front, and the tiles in front */
+                            uint32_t incl = run;
+#pragma unroll
+                            for (int o = 1; o < 32; o <<= 1) {
+                                const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                                if (lane >= o) incl = max(incl, up);
+                            }
+                            uint32_t before = __shfl_up_sync(0xFFFFFFFFu, incl, 1);
+                            before = max(lane ? before : 0u, carry);
+                            const uint32_t b2 = before * 0x00010001u;
+                            if (j < j1) T4[j] = make_uint4(__vmaxu2(w.x, b2), __vmaxu2(w.y, b2), __vmaxu2(w.z, b2), __vmaxu2(w.w, b2));
+                            carry = max(carry, __shfl_sync(0xFFFFFFFFu, incl, 31));
+                        }
                     }
                     __syncthreads();
                     for (int q = qlo + tid; q < qhi; q += MB_THREADS) {

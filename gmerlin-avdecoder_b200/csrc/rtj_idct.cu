@@ -1099,29 +1099,66 @@ rtj_idct_hard_kernel(const uint8_t *__restrict__ stream, const rtjgpu_frame_desc
     int32_t *Wc = &s_w[grp][0][l];                                    /* ... of the first pass's results: row r at Wc[9 r] */
     const int32_t *Wr = &s_w[grp][l][0];                              /* this lane's row */
     const unsigned stride = gridDim.x * (HB_THREADS / 8);
-    for (unsigned kb = (blockIdx.x * (HB_THREADS / 32) + (threadIdx.x >> 5)) * 4; kb < total; kb += stride) {       /* warp-uniform */
+    /* As in rtj_idct_hard16_kernel a block is three reads deep (queue record; entry and descriptor; bytes), and a warp works
+     * through some twenty groups of four blocks: three groups under way, one stage apart, so that the reads of a group are
+     * made while the two groups in front of it are transformed.  (Lanes past the queue's end read block 0 of frame 0.) */
+    struct Src {
+        uint32_t e, table;
+        const uint32_t *wp;          /* the lane's three words */
+        unsigned sh;
+    };
+    auto ld_rec = [&](unsigned kb) {
+        const unsigned k = kb + (unsigned)(lane >> 3);
+        return k < total ? reinterpret_cast<const uint2 *>(hardq)[hardq_cap - 1u - k] : make_uint2(0u, 0u);
+    };
+    auto ld_src = [&](unsigned kb, const uint2 rec) {
+        const unsigned k = kb + (unsigned)(lane >> 3);
+        const unsigned sf = rec.y >> 16;
+        Src r;
+        r.e = k < total ? ent[(size_t)sf * nblk + (rec.x & 0x7FFFFFFFu)] : 0u;
+        const rtjgpu_frame_desc sd = desc[sf];
+        r.table = sd.table;
+        const uintptr_t a = reinterpret_cast<uintptr_t>(stream + sd.offset + RTJPEG_B200_HEADER_BYTES);
+        r.wp = reinterpret_cast<const uint32_t *>(a);      /* packets start on a multiple of 4; the block's offset is added when the entry is there */
+        r.sh = 0;
+        return r;
+    };
+    struct Words {
+        uint32_t w0, w1, w2;
+        unsigned sh;
+    };
+    auto ld_words = [&](const Src &sr) {
+        const uintptr_t a = reinterpret_cast<uintptr_t>(sr.wp) + (sr.e & RTJ_ENT_OFF_MASK);
+        const uint32_t *wp = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3) + 2 * l;
+        Words w;
+        w.w0 = __ldg(wp); w.w1 = __ldg(wp + 1); w.w2 = __ldg(wp + 2);                    /* slack bytes follow the stream */
+        w.sh = (unsigned)(a & 3) * 8;
+        return w;
+    };
+    const unsigned kb0 = (blockIdx.x * (HB_THREADS / 32) + (threadIdx.x >> 5)) * 4;
+    if (kb0 >= total) return;                                                           /* warp-uniform */
+    uint2 rec0 = ld_rec(kb0), rec1 = ld_rec(kb0 + stride), rec2 = ld_rec(kb0 + 2u * stride);
+    Src sr0 = ld_src(kb0, rec0), sr1 = ld_src(kb0 + stride, rec1);
+    Words wd = ld_words(sr0);
+    for (unsigned kb = kb0; kb < total; kb += stride) {       /* warp-uniform */
+        const Words wd1 = ld_words(sr1);
+        const Src sr2 = ld_src(kb + 2u * stride, rec2);
+        const uint2 rec3 = ld_rec(kb + 3u * stride);
+
         const unsigned k = kb + (unsigned)(lane >> 3);
         const bool live = k < total;
-        const uint2 rec = !live ? make_uint2(0u, 0u) : reinterpret_cast<const uint2 *>(hardq)[hardq_cap - 1u - k];
+        const uint2 rec = rec0;
         const int i = (int)(rec.x & 0x7FFFFFFFu), chroma = (int)(rec.x >> 31);
-        const unsigned f = rec.y & 0xFFFFu, sf = rec.y >> 16;
-        const uint32_t e = live ? ent[(size_t)sf * nblk + i] : 0u;
-        const rtjgpu_frame_desc sd = desc[sf];
-        const rtj_dev_table *t = &tables[min((int)sd.table, RTJ_NUM_TABLES - 1)];
+        const unsigned f = rec.y & 0xFFFFu;
+        const rtj_dev_table *t = &tables[min((int)sr0.table, RTJ_NUM_TABLES - 1)];
         const int32_t *iq = t->iq[chroma];
         const int bt8 = t->bt8[chroma];
 
         /* the block's bytes 8l .. 8l + 7 */
-        uint32_t b0, b1;
-        {
-            const uint8_t *src = stream + sd.offset + RTJPEG_B200_HEADER_BYTES + (e & RTJ_ENT_OFF_MASK);
-            const uintptr_t a = reinterpret_cast<uintptr_t>(src);
-            const uint32_t *wp = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3) + 2 * l;
-            const unsigned sh = (unsigned)(a & 3) * 8;
-            const uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2);     /* slack bytes follow the stream */
-            b0 = __funnelshift_r(w0, w1, sh);
-            b1 = __funnelshift_r(w1, w2, sh);
-        }
+        const uint32_t b0 = __funnelshift_r(wd.w0, wd.w1, wd.sh), b1 = __funnelshift_r(wd.w1, wd.w2, wd.sh);
+        rec0 = rec1; rec1 = rec2; rec2 = rec3;
+        sr0 = sr1; sr1 = sr2;
+        wd = wd1;
         /* what every byte fills: DC and the raw prefix (bytes 0 .. bt8) one place each, a run token b - 63, else one */
         uint32_t x0, x1;
         {
